@@ -338,8 +338,9 @@ def test_reference_iteration_replay_runs_and_aliased_step_tracks_it():
     y_r = 1 + 0.05 * rng.standard_normal((8, 1)); y_f = 0.05 * rng.standard_normal((8, 1)); y_g = np.ones((8, 1))
     r = o.gan_iteration_reference(dis, gen, gan, ng, x, z_d, z_g, y_r, y_f, y_g)
     assert all(np.isfinite(r[k]) for k in ("score_d_real", "score_d_fake", "score_gan"))
-    # after the copies the three graphs agree on the shared tensors (J:429-510)
-    np.testing.assert_array_equal(gan.layers[ng + 2].params["W"], dis.layers[2].params["W"])
+    # the lr-0 "frozen" D inside gan still decays by l2*W during gan.fit ...
+    np.testing.assert_allclose(gan.layers[ng + 2].params["W"], dis.layers[2].params["W"] * (1 - 1e-4), rtol=1e-12)
+    # ... and after the gan -> gen copies (J:474-510) the generator graphs agree
     np.testing.assert_array_equal(gen.layers[1].params["W"], gan.layers[1].params["W"])
 
 
