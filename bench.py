@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec for the full adversarial G+D step (BASELINE.json metric) on synthetic 64x64x3 batches.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c4|c5]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path: x_fake = G(z_d); D update on (x_real, y_real)+(x_fake, y_fake);
+G update through D on z_g with labels 1 -- J:408-471 without I/O -- through libb200gan.so (hand-written sm_100a CUDA).
+Workload at N=1: BASELINE configs[1] = 64x64x3 DCGAN, z=100, bf16, batch 128 per GPU (weak scaling: 128/GPU).
+
+`value`   : images/sec with inputs resident in HBM, per-step CUDA-event time on the launching stream, max over ranks.
+`e2e`     : the same metric through the host-buffer C-ABI call b2g_gan_step (H2D of x_real/z/labels from pinned memory and
+            D2H of the three losses inside the timed region) -- the call the Java driver makes per iteration.
+`roofline`: the dominant tensor-core kernel timed live (CUDA events, on the library's stream) against MEASURED_PEAKS.json.
+`cpu_baseline`: the oracle port (NumPy/OpenBLAS im2col+SGEMM restatement of DL4J's nd4j-native algorithm) on this box's cores.
+--impl reference: that CPU restatement IS the reference arm (DL4J itself cannot run: no JVM in the image).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (image size, z, nf, nc, per-GPU batch)
+    "c2": dict(size=64, z=100, nf=64, nc=3, batch=128, desc="64x64x3 DCGAN z=100 (4-layer G/D) bf16 batch 128 per GPU"),
+    "c4": dict(size=128, z=100, nf=64, nc=3, batch=32, desc="128x128x3 DCGAN (5-layer G/D) bf16 batch 32 per GPU"),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(power)) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def algorithmic_flops_per_image(cfg):
+    from gan_deeplearning4j_b200 import models as m
+    gf = m.forward_macs(m.dcgan_generator(cfg["size"], cfg["z"], cfg["nf"], cfg["nc"]), (cfg["z"],))
+    df = m.forward_macs(m.dcgan_discriminator(cfg["size"], cfg["nf"], cfg["nc"]), (cfg["nc"], cfg["size"], cfg["size"]))
+    return 2.0 * (4 * gf + 8 * df), gf, df        # F = 2*(4*G_f + 8*D_f)
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port timed on the host cores (cpu_baseline leg and --impl reference)
+# ------------------------------------------------------------------------------------------------------
+def cpu_step_rate(cfg, sample_batch, steps, warmup):
+    from oracle import dl4j_oracle as o        # bench.py's cpu_baseline / reference legs may execute oracle/
+    q = o.Quirks(xent_clip_eps=0.0)
+    G = o.dcgan_generator(cfg["size"], cfg["z"], cfg["nf"], cfg["nc"], dtype=np.float32, quirks=q)
+    D = o.dcgan_discriminator(cfg["size"], cfg["nf"], cfg["nc"], dtype=np.float32, quirks=q)
+    data = o.synthetic_batch(sample_batch, cfg["size"], cfg["nc"], cfg["z"], seed=666)
+    for _ in range(warmup):
+        o.gan_step(G, D, *data)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        r = o.gan_step(G, D, *data)
+    dt = time.perf_counter() - t0
+    assert np.isfinite(r["loss_g"])
+    return sample_batch * steps / dt, dt / steps
+
+
+def run_reference(args, cfg, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = 32
+    steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))
+    ips, sec = cpu_step_rate(cfg, sample, steps, warmup)
+    line = {
+        "impl": "reference", "metric": "images/sec (full G+D step)", "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["desc"], "global_batch": sample, "note": "bounded sample: batch 32 per step on the host CPU; DL4J 1.0.0-beta3 cannot run here (no JVM), "
+                   "this is the im2col+SGEMM (OpenBLAS) restatement of its nd4j-native algorithm (oracle/dl4j_oracle.py)"},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": f"{steps} steps x batch {sample}, fp32 NumPy/OpenBLAS, all {cores} host threads"},
+        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------
+def dominant_kernel_roofline(b, ctx, cfg, batch, peaks):
+    """Time the dominant tensor-core kernel alone (D2 fprop shape of the D-step: 2N images) with CUDA events."""
+    size, nf = cfg["size"], cfg["nf"]
+    n = 2 * batch
+    h = size // 2
+    geom = dict(n=n, h=h, w=h, c=nf, oh=h // 2, ow=h // 2, o=2 * nf, kh=4, kw=4, sh=2, sw=2, ph=1, pw=1)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((n, h, h, nf), dtype=np.float32)
+    w = (rng.standard_normal((2 * nf, 4, 4, nf), dtype=np.float32) / np.sqrt(16 * nf)).astype(np.float32)
+    flops = 2.0 * n * (h // 2) * (h // 2) * (2 * nf) * (16 * nf)
+    out_size = n * (h // 2) * (h // 2) * 2 * nf
+    res = {}
+    for impl, name in ((1, "tcgen05"), (0, "simt")):
+        try:
+            _, ms = b.test_conv(ctx, 0, impl, b.BF16, geom, x, w, out_size, iters=20)
+            res[name] = ms
+        except b.B200GanError as e:
+            res[name] = None
+            res[name + "_error"] = str(e)[:120]
+    ms = res.get("tcgen05") or res.get("simt")
+    ach = flops / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": None,
+            "kernel": ("tcgen05 " if res.get("tcgen05") else "SIMT ") + f"conv fprop {n}x{h}x{h}x{nf} -> {2 * nf}, 4x4 s2 p1 (D2, D-step batch)",
+            "flops_per_launch": flops, "ms_per_launch": ms, "peak_source": peaks["source"] + " (burst cuBLAS bf16)", "detail_ms": res}
+
+
+def run_ours(args, cfg, rank, world, local_rank):
+    import torch
+    import gan_deeplearning4j_b200 as b
+    from gan_deeplearning4j_b200 import models as m
+    from oracle import dl4j_oracle as o      # only for synthetic_batch + the cpu_baseline leg
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    ctx = b.Context(local_rank)
+    if world > 1:
+        ids = [b.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.comm_init(world, rank, ids[0])
+    n = cfg["batch"]
+    gs = m.dcgan_generator(cfg["size"], cfg["z"], cfg["nf"], cfg["nc"])
+    ds = m.dcgan_discriminator(cfg["size"], cfg["nf"], cfg["nc"])
+    G = b.Net(ctx, gs, (cfg["z"],), max_batch=n, precision=b.BF16, xent_clip_eps=0.0, seed=666)
+    D = b.Net(ctx, ds, (cfg["nc"], cfg["size"], cfg["size"]), max_batch=2 * n, precision=b.BF16, xent_clip_eps=0.0, bn_groups=2, seed=667)
+    gan = b.Gan(G, D, fake_bn_train=False, use_cuda_graph=True)
+    data = o.synthetic_batch(n, cfg["size"], cfg["nc"], cfg["z"], seed=666 + rank)    # each rank draws its own slice
+    pinned = [torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).pin_memory() for a in data]
+    ptrs = [t.data_ptr() for t in pinned]
+    h2d = int(sum(t.numel() * 4 for t in pinned)); d2h = 16
+    gan.upload(*[t.numpy() for t in pinned])
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+        ctx.sync()
+
+    # ---- resident-input timing: per-step CUDA events on the library stream, L2 flushed between steps
+    for _ in range(max(3, args.warmup)):
+        gan.step_resident(n)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count()
+    step_ms = []
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.flush_l2()
+        gan.step_resident(n)
+        step_ms.append(gan.last_step_ms())
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    losses = gan.losses()
+    total_ms = float(sum(step_ms))
+    # ---- end to end through the host-buffer entry point
+    lo = np.zeros(3, np.float32)
+    for _ in range(3):
+        gan.step_ptr(ptrs, n, lo)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        gan.step_ptr(ptrs, n, lo)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([total_ms, e2e_s], device=f"cuda:{local_rank}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_s = float(t[0]), float(t[1])
+    if rank == 0:
+        peaks = load_peaks()
+        F, gf, df = algorithmic_flops_per_image(cfg)
+        global_batch = n * world
+        ips = global_batch * args.steps / (total_ms * 1e-3)
+        e2e_ips = global_batch * args.steps / e2e_s
+        roof = dominant_kernel_roofline(b, ctx, cfg, n, peaks)
+        step_tf = F * ips / world / 1e12
+        cores = os.cpu_count() or 1
+        cpu_ips, cpu_sec = cpu_step_rate(cfg, 32, 4, 1)
+        line = {
+            "metric": "images/sec (full G+D step)", "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": cfg["desc"], "global_batch": global_batch, "parallelism": f"dp{world}", "l2": "flushed between steps (256 MiB memset, outside the per-step CUDA-event brackets)",
+                       "fake_bn": "inference (gen.output, J:420)", "cuda_graph": world == 1, "step": "G(z_d) -> D update on real|fake -> G update through D"},
+            "roofline": roof,
+            "step_roofline": {"algorithmic_gflop_per_image": F / 1e9, "achieved_tflops_per_gpu": step_tf, "peak": peaks["bf16_tflops_sustained"], "frac": step_tf / peaks["bf16_tflops_sustained"],
+                              "peak_source": peaks["source"] + " (sustained cuBLAS bf16)"},
+            "cpu_baseline": {"value": cpu_ips, "unit": "images/s", "cores": cores, "kind": "port",
+                             "sample": f"4 steps x batch 32 of the same workload, fp32 NumPy/OpenBLAS im2col+SGEMM restatement of DL4J nd4j-native, {cores} host threads"},
+            "e2e": {"value": e2e_ips, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall,
+            "losses": [float(v) for v in losses],
+        }
+        print(json.dumps(line), flush=True)
+    gan.close(); G.close(); D.close(); ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference(args, cfg, rank, world)
+    else:
+        run_ours(args, cfg, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,820 @@
+// engine.cu -- host side of libb200gan.so: the chain-graph executor (ComputationGraph.init / output /
+// computeGradientAndScore / fit), the fused adversarial step, the NCCL gradient all-reduce, and the
+// C-ABI declared in include/b200gan.h.
+//
+// What it replaces in the reference (J = Java/src/main/java/org/deeplearning4j/dl4jGANComputerVision.java):
+//   ComputationGraph.init()            J:166,222,311   -> b2g_net_create   (one arena: params | grads | updater state | activations)
+//   ComputationGraph.output()          J:170,420       -> b2g_net_output
+//   SparkComputationGraph.fit()        J:426,471       -> b2g_net_fit / b2g_gan_step
+//   Layer.getParam/setParam            J:429-510       -> b2g_net_get_param / b2g_net_set_param (aliasing inside b2g_gan)
+//   ParameterAveragingTrainingMaster   J:325-333       -> b2g_ctx_comm_init + ncclAllReduce of the gradient vector
+// Arithmetic contract: oracle/dl4j_oracle.py (DL4J 1.0.0-beta3 semantics).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/b200gan.h"
+#include "kernels.h"
+
+using namespace b2g;
+
+// ------------------------------------------------------------------ errors ---------------------------
+static thread_local char g_err[1024] = "";
+static int32_t fail(int32_t code, const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap); return code;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(B2G_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
+#define B2(call) do { int32_t r_ = (call); if (r_ != 0) return r_; } while (0)
+#define CHECK_KERNELS() CU(cudaGetLastError())
+
+// ------------------------------------------------------------------ NCCL (dlopen, no link-time dep) ----
+struct NcclId { char internal[128]; };
+typedef int (*fn_ncclGetUniqueId)(NcclId*);
+typedef int (*fn_ncclCommInitRank)(void**, int, NcclId, int);
+typedef int (*fn_ncclAllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_ncclCommDestroy)(void*);
+typedef const char* (*fn_ncclGetErrorString)(int);
+static struct { void* h; fn_ncclGetUniqueId uid; fn_ncclCommInitRank init; fn_ncclAllReduce ar; fn_ncclCommDestroy destroy; fn_ncclGetErrorString errstr; } g_nccl = {};
+static int32_t nccl_load() {
+  if (g_nccl.h) return 0;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) { g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.h) break; }
+  if (!g_nccl.h) return fail(B2G_ERR_NCCL, "dlopen(libnccl.so.2) failed: %s", dlerror());
+  g_nccl.uid = (fn_ncclGetUniqueId)dlsym(g_nccl.h, "ncclGetUniqueId");
+  g_nccl.init = (fn_ncclCommInitRank)dlsym(g_nccl.h, "ncclCommInitRank");
+  g_nccl.ar = (fn_ncclAllReduce)dlsym(g_nccl.h, "ncclAllReduce");
+  g_nccl.destroy = (fn_ncclCommDestroy)dlsym(g_nccl.h, "ncclCommDestroy");
+  g_nccl.errstr = (fn_ncclGetErrorString)dlsym(g_nccl.h, "ncclGetErrorString");
+  if (!g_nccl.uid || !g_nccl.init || !g_nccl.ar || !g_nccl.destroy) return fail(B2G_ERR_NCCL, "libnccl is missing symbols");
+  return 0;
+}
+#define NC(call) do { int e_ = (call); if (e_ != 0) return fail(B2G_ERR_NCCL, "%s -> %s", #call, g_nccl.errstr ? g_nccl.errstr(e_) : "nccl error"); } while (0)
+
+// ------------------------------------------------------------------ context --------------------------
+struct b2g_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaDeviceProp prop;
+  void* comm = nullptr; int world = 1, rank = 0;
+  bool tc_ok = false;
+  cudaEvent_t t0 = nullptr, t1 = nullptr; void* flush_buf = nullptr; size_t flush_bytes = 0;
+};
+
+struct LayerRT {
+  b2g_layer_desc d;
+  int ih = 1, iw = 1, ic = 1, oh = 1, ow = 1, oc = 1;         // per-example NHWC dims
+  size_t in_elems = 0, out_elems = 0;
+  ConvGeom geom{};                                             // conv-equivalent geometry (N filled per call)
+  int64_t off_W = -1, n_W = 0, off_b = -1, off_gamma = -1, off_beta = -1, off_mean = -1, off_var = -1;
+  int64_t off_W_bf = -1, off_Wt_bf = -1;
+  int wA = 0, wTaps = 0, wB = 0;                               // internal weight layout [A][taps][B]
+  void* out = nullptr; bool out_alias = false;
+  void* probs = nullptr;                                       // OUTPUT / LOSS: sigmoid(logits)
+  uint8_t* argmax = nullptr;
+  float* bn_mean = nullptr; float* bn_invstd = nullptr;
+  int fused_act = ACT_IDENTITY; float fused_alpha = 0.f;       // BN followed by an ActivationLayer
+  bool act_fused_into_prev = false;
+  bool has_gemm() const { return d.type == B2G_LAYER_CONV2D || d.type == B2G_LAYER_DECONV2D || d.type == B2G_LAYER_DENSE || d.type == B2G_LAYER_OUTPUT; }
+};
+
+struct b2g_net {
+  b2g_ctx* ctx = nullptr;
+  b2g_net_config cfg{};
+  std::vector<LayerRT> L;
+  int prec = PREC_F32;
+  int64_t n_params = 0;
+  float *params = nullptr, *grads = nullptr, *st0 = nullptr, *st1 = nullptr;
+  __nv_bfloat16* shadow = nullptr; int64_t n_shadow = 0;
+  std::vector<UpdSeg> segs; UpdSeg* segs_dev = nullptr; int32_t* chunk_seg_dev = nullptr; int64_t* chunk_off_dev = nullptr; int nchunks = 0;
+  int64_t *l2_off_dev = nullptr, *l2_len_dev = nullptr; float* l2_coef_dev = nullptr; int n_l2 = 0;
+  int* step_dev = nullptr;
+  int max_rows = 0;                    // cfg.max_batch
+  size_t in_elems = 0;
+  void* input = nullptr;               // T NHWC [max_rows][in_elems]
+  float* stage_f32 = nullptr; size_t stage_floats = 0;   // host<->device fp32 staging (inputs, outputs, params)
+  float* labels_dev = nullptr;         // [max_rows]
+  void *epsA = nullptr, *epsB = nullptr; size_t eps_elems = 0;
+  float* scratch = nullptr; size_t scratch_floats = 0;
+  float* loss_dev = nullptr;           // [8]
+  double* l2_dev = nullptr;
+  void* input_grad = nullptr;          // where the last backward left d(loss)/d(input), or null
+  int last_rows = 0;
+  std::vector<void*> allocs;
+};
+
+template <typename P>
+static int32_t dalloc(b2g_net* n, P** p, size_t bytes) {
+  void* q = nullptr; if (bytes == 0) bytes = 16;
+  cudaError_t e = cudaMalloc(&q, bytes);
+  if (e != cudaSuccess) return fail(B2G_ERR_OOM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  n->allocs.push_back(q); *p = (P*)q; return 0;
+}
+
+// ------------------------------------------------------------------ host RNG for Xavier init -----------
+static inline uint64_t splitmix(uint64_t& s) { uint64_t z = (s += 0x9E3779B97F4A7C15ull); z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); }
+static inline double urand(uint64_t& s) { return ((splitmix(s) >> 11) + 0.5) * (1.0 / 9007199254740992.0); }
+static inline float nrand(uint64_t& s) { double u1 = urand(s), u2 = urand(s); return (float)(sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2)); }
+
+// ------------------------------------------------------------------ layout helpers (host) ---------------
+// DL4J conv W [A][B][taps] ('c' order [nOut,nIn,kH,kW] / deconv [nIn,nOut,kH,kW]) <-> internal [A][taps][B]
+static void w_dl4j_to_internal(const float* src, float* dst, int A, int B, int taps) {
+  for (int a = 0; a < A; ++a) for (int b = 0; b < B; ++b) for (int t = 0; t < taps; ++t) dst[((size_t)a * taps + t) * B + b] = src[((size_t)a * B + b) * taps + t];
+}
+static void w_internal_to_dl4j(const float* src, float* dst, int A, int B, int taps) {
+  for (int a = 0; a < A; ++a) for (int b = 0; b < B; ++b) for (int t = 0; t < taps; ++t) dst[((size_t)a * B + b) * taps + t] = src[((size_t)a * taps + t) * B + b];
+}
+
+// ------------------------------------------------------------------ net construction --------------------
+static int32_t net_build(b2g_net* n, const b2g_layer_desc* layers, int32_t nl) {
+  const b2g_net_config& c = n->cfg;
+  int h = c.in_h, w = c.in_w, ch = c.in_c;
+  n->in_elems = (size_t)h * w * ch;
+  int64_t off = 0, off_bf = 0;
+  for (int i = 0; i < nl; ++i) {
+    LayerRT l; l.d = layers[i]; l.d.name[B2G_NAME_LEN - 1] = 0;
+    l.ih = h; l.iw = w; l.ic = ch; l.in_elems = (size_t)h * w * ch;
+    b2g_layer_desc& d = l.d;
+    if (d.has_bias < 0) d.has_bias = 1;
+    switch (d.type) {
+      case B2G_LAYER_CONV2D: {
+        if (d.n_in == 0) d.n_in = ch; if (d.n_in != ch) return fail(B2G_ERR_SHAPE, "layer %s: nIn %d != incoming channels %d", d.name, d.n_in, ch);
+        if (d.s_h < 1) d.s_h = 1; if (d.s_w < 1) d.s_w = 1;
+        l.oh = (h - d.k_h + 2 * d.p_h) / d.s_h + 1; l.ow = (w - d.k_w + 2 * d.p_w) / d.s_w + 1; l.oc = d.n_out;   // ConvolutionMode.Truncate
+        if (l.oh < 1 || l.ow < 1) return fail(B2G_ERR_SHAPE, "layer %s: kernel larger than input", d.name);
+        l.geom = ConvGeom{0, h, w, ch, l.oh, l.ow, d.n_out, d.k_h, d.k_w, d.s_h, d.s_w, d.p_h, d.p_w};
+        l.wA = d.n_out; l.wTaps = d.k_h * d.k_w; l.wB = d.n_in;
+        if (d.has_bias) { l.off_b = off; off += d.n_out; }                 // ConvolutionParamInitializer: [b | W]
+        l.off_W = off; l.n_W = (int64_t)l.wA * l.wTaps * l.wB; off += l.n_W;
+      } break;
+      case B2G_LAYER_DECONV2D: {
+        if (d.n_in == 0) d.n_in = ch; if (d.n_in != ch) return fail(B2G_ERR_SHAPE, "layer %s: nIn %d != incoming channels %d", d.name, d.n_in, ch);
+        if (d.s_h < 1) d.s_h = 1; if (d.s_w < 1) d.s_w = 1;
+        l.oh = d.s_h * (h - 1) + d.k_h - 2 * d.p_h; l.ow = d.s_w * (w - 1) + d.k_w - 2 * d.p_w; l.oc = d.n_out;
+        // conv-equivalent: conv input = deconv output, conv output = deconv input
+        l.geom = ConvGeom{0, l.oh, l.ow, d.n_out, h, w, d.n_in, d.k_h, d.k_w, d.s_h, d.s_w, d.p_h, d.p_w};
+        l.wA = d.n_in; l.wTaps = d.k_h * d.k_w; l.wB = d.n_out;
+        if (d.has_bias) { l.off_b = off; off += d.n_out; }
+        l.off_W = off; l.n_W = (int64_t)l.wA * l.wTaps * l.wB; off += l.n_W;
+      } break;
+      case B2G_LAYER_DENSE: case B2G_LAYER_OUTPUT: {
+        if (h != 1 || w != 1) return fail(B2G_ERR_SHAPE, "layer %s: dense layer needs a feed-forward input (insert CNN_TO_FF)", d.name);
+        if (d.n_in == 0) d.n_in = ch; if (d.n_in != ch) return fail(B2G_ERR_SHAPE, "layer %s: nIn %d != incoming features %d", d.name, d.n_in, ch);
+        l.oh = l.ow = 1; l.oc = d.n_out;
+        l.geom = ConvGeom{0, 1, 1, ch, 1, 1, d.n_out, 1, 1, 1, 1, 0, 0};
+        l.wA = d.n_out; l.wTaps = 1; l.wB = d.n_in;                        // 'f'-order [nIn,nOut] == row-major [nOut][nIn]
+        l.off_W = off; l.n_W = (int64_t)d.n_in * d.n_out; off += l.n_W;    // DefaultParamInitializer: [W | b]
+        if (d.has_bias) { l.off_b = off; off += d.n_out; }
+        if (d.type == B2G_LAYER_OUTPUT) { d.act = B2G_ACT_IDENTITY; if (d.n_out != 1) return fail(B2G_ERR_UNSUPPORTED, "layer %s: XENT output supports nOut=1", d.name); }
+      } break;
+      case B2G_LAYER_BATCHNORM: {
+        d.n_in = d.n_out = ch; l.oh = h; l.ow = w; l.oc = ch;
+        if (d.bn_decay <= 0.f) d.bn_decay = 0.9f; if (d.bn_eps <= 0.f) d.bn_eps = 1e-5f;
+        l.off_gamma = off; l.off_beta = off + ch; l.off_mean = off + 2 * ch; l.off_var = off + 3 * ch; off += 4 * (int64_t)ch;
+      } break;
+      case B2G_LAYER_ACTIVATION: l.oh = h; l.ow = w; l.oc = ch; break;
+      case B2G_LAYER_MAXPOOL:
+        if (d.s_h < 1) d.s_h = 1; if (d.s_w < 1) d.s_w = 1;
+        l.oh = (h - d.k_h) / d.s_h + 1; l.ow = (w - d.k_w) / d.s_w + 1; l.oc = ch;
+        if (d.k_h * d.k_w > 255) return fail(B2G_ERR_UNSUPPORTED, "layer %s: pooling window too large", d.name);
+        break;
+      case B2G_LAYER_UPSAMPLE2D: if (d.k_h < 1) d.k_h = 2; l.oh = h * d.k_h; l.ow = w * d.k_h; l.oc = ch; break;
+      case B2G_LAYER_LOSS: l.oh = h; l.ow = w; l.oc = ch; if ((size_t)h * w * ch != 1) return fail(B2G_ERR_UNSUPPORTED, "layer %s: XENT loss needs one logit per example", d.name); break;
+      case B2G_LAYER_FF_TO_CNN:
+        if ((size_t)d.pre_h * d.pre_w * d.pre_c != l.in_elems) return fail(B2G_ERR_SHAPE, "layer %s: FeedForwardToCnn(%d,%d,%d) != %zu features", d.name, d.pre_h, d.pre_w, d.pre_c, l.in_elems);
+        l.oh = d.pre_h; l.ow = d.pre_w; l.oc = d.pre_c; break;
+      case B2G_LAYER_CNN_TO_FF: l.oh = l.ow = 1; l.oc = h * w * ch; break;
+      default: return fail(B2G_ERR_ARG, "layer %d: unknown type %d", i, d.type);
+    }
+    l.out_elems = (size_t)l.oh * l.ow * l.oc;
+    if (l.has_gemm() && n->prec == PREC_BF16) { l.off_W_bf = off_bf; off_bf += l.n_W; l.off_Wt_bf = off_bf; off_bf += l.n_W; off_bf = (off_bf + 63) / 64 * 64; }
+    h = l.oh; w = l.ow; ch = l.oc;
+    n->L.push_back(l);
+  }
+  // fuse BatchNormalization + ActivationLayer (north_star's BN+ReLU / BN+LeakyReLU)
+  for (size_t i = 0; i + 1 < n->L.size(); ++i)
+    if (n->L[i].d.type == B2G_LAYER_BATCHNORM && n->L[i + 1].d.type == B2G_LAYER_ACTIVATION) {
+      n->L[i].fused_act = n->L[i + 1].d.act; n->L[i].fused_alpha = n->L[i + 1].d.act_alpha; n->L[i + 1].act_fused_into_prev = true;
+    }
+  int last = n->L.back().d.type;
+  (void)last;
+  n->n_params = off; n->n_shadow = off_bf;
+  return 0;
+}
+
+static int32_t net_alloc(b2g_net* n) {
+  const int R = n->cfg.max_batch; n->max_rows = R;
+  const size_t ts = prec_size(n->prec);
+  const int G = std::max(1, n->cfg.bn_groups);
+  B2(dalloc(n, &n->params, sizeof(float) * n->n_params)); B2(dalloc(n, &n->grads, sizeof(float) * n->n_params));
+  B2(dalloc(n, &n->st0, sizeof(float) * n->n_params)); B2(dalloc(n, &n->st1, sizeof(float) * n->n_params));
+  if (n->n_shadow) B2(dalloc(n, &n->shadow, sizeof(__nv_bfloat16) * n->n_shadow));
+  B2(dalloc(n, &n->step_dev, sizeof(int))); B2(dalloc(n, &n->loss_dev, sizeof(float) * 8)); B2(dalloc(n, &n->l2_dev, sizeof(double)));
+  B2(dalloc(n, &n->labels_dev, sizeof(float) * R));
+  B2(dalloc(n, (char**)&n->input, ts * R * n->in_elems));
+  size_t max_act = n->in_elems, scratch = 1 << 16, max_w = 0;
+  for (auto& l : n->L) {
+    max_act = std::max(max_act, std::max(l.in_elems, l.out_elems));
+    bool alias = l.act_fused_into_prev || l.d.type == B2G_LAYER_LOSS ||
+                 (l.d.type == B2G_LAYER_FF_TO_CNN && (l.oc == 1 || l.oh * l.ow == 1)) ||
+                 (l.d.type == B2G_LAYER_CNN_TO_FF && (l.ic == 1 || l.ih * l.iw == 1));
+    l.out_alias = alias;
+    if (!alias) B2(dalloc(n, (char**)&l.out, ts * R * l.out_elems));
+    if (l.d.type == B2G_LAYER_OUTPUT || l.d.type == B2G_LAYER_LOSS) B2(dalloc(n, (char**)&l.probs, ts * R * l.out_elems));
+    if (l.d.type == B2G_LAYER_MAXPOOL) B2(dalloc(n, &l.argmax, (size_t)R * l.out_elems));
+    if (l.d.type == B2G_LAYER_BATCHNORM) { B2(dalloc(n, &l.bn_mean, sizeof(float) * G * l.oc)); B2(dalloc(n, &l.bn_invstd, sizeof(float) * G * l.oc)); scratch = std::max(scratch, k_bn_scratch_floats(l.oc, G)); }
+    if (l.has_gemm()) {
+      ConvGeom g = l.geom; g.N = R;
+      scratch = std::max(scratch, std::max(k_simt_wgrad_scratch_floats(g), k_tc_wgrad_scratch_floats(g)));
+      scratch = std::max(scratch, k_colsum_scratch_floats(std::max(l.oc, l.ic)));
+      max_w = std::max(max_w, (size_t)l.n_W);
+    }
+  }
+  n->eps_elems = (size_t)R * max_act;
+  B2(dalloc(n, (char**)&n->epsA, ts * n->eps_elems)); B2(dalloc(n, (char**)&n->epsB, ts * n->eps_elems));
+  n->scratch_floats = scratch; B2(dalloc(n, &n->scratch, sizeof(float) * scratch));
+  n->stage_floats = std::max((size_t)R * max_act, std::max((size_t)n->n_params, max_w)); B2(dalloc(n, &n->stage_f32, sizeof(float) * n->stage_floats));
+  return 0;
+}
+
+static int updater_kind(int u) { return u == B2G_UPD_SGD ? 0 : u == B2G_UPD_RMSPROP ? 1 : u == B2G_UPD_ADAM ? 2 : 3; }
+
+static int32_t net_init_params_and_updater(b2g_net* n) {
+  cudaStream_t s = n->ctx->stream;
+  std::vector<float> hp(n->n_params, 0.f), h0(n->n_params, 0.f);
+  uint64_t seed = n->cfg.seed ? n->cfg.seed : 666;
+  std::vector<int64_t> l2o, l2l; std::vector<float> l2c;
+  for (auto& l : n->L) {
+    const b2g_layer_desc& d = l.d;
+    auto add_seg = [&](int64_t off, int64_t len, bool weight, bool noop) {
+      UpdSeg sg{}; sg.off = off; sg.len = len; sg.kind = noop ? 3 : updater_kind(d.updater);
+      sg.lr = d.lr; sg.b1 = d.beta1; sg.b2 = d.beta2; sg.eps = d.eps; sg.l2 = weight ? d.l2 : 0.f; sg.clip = n->cfg.grad_clip; sg.div_mb = noop ? 0 : 1;
+      sg.off_bf = -1; sg.off_bft = -1; n->segs.push_back(sg);
+      if (!noop && sg.kind == 1) for (int64_t i = 0; i < len; ++i) h0[off + i] = d.eps;     // RmsPropUpdater cache initialised to epsilon
+      if (weight && d.l2 != 0.f) { l2o.push_back(off); l2l.push_back(len); l2c.push_back(0.5f * d.l2); }
+    };
+    if (l.has_gemm()) {
+      // WeightInit.XAVIER (J:127): N(0, 2/(fanIn+fanOut)); conv fanIn = nIn*kH*kW, fanOut = nOut*kH*kW/(sH*sW)
+      double fi = (double)d.n_in * l.wTaps, fo = (double)d.n_out * l.wTaps / ((d.type == B2G_LAYER_CONV2D || d.type == B2G_LAYER_DECONV2D) ? (double)(d.s_h * d.s_w) : 1.0);
+      float sd = (float)sqrt(2.0 / (fi + fo));
+      for (int64_t i = 0; i < l.n_W; ++i) hp[l.off_W + i] = sd * nrand(seed);
+      if (l.off_b >= 0 && l.off_b < l.off_W) add_seg(l.off_b, d.n_out, false, false);
+      add_seg(l.off_W, l.n_W, true, false);
+      if (l.off_b >= 0 && l.off_b > l.off_W) add_seg(l.off_b, d.n_out, false, false);
+    } else if (d.type == B2G_LAYER_BATCHNORM) {
+      for (int c = 0; c < l.oc; ++c) { hp[l.off_gamma + c] = 1.f; hp[l.off_var + c] = 1.f; }
+      add_seg(l.off_gamma, l.oc, false, false); add_seg(l.off_beta, l.oc, false, false);
+      add_seg(l.off_mean, l.oc, false, true); add_seg(l.off_var, l.oc, false, true);
+    }
+  }
+  CU(cudaMemcpyAsync(n->params, hp.data(), sizeof(float) * n->n_params, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(n->st0, h0.data(), sizeof(float) * n->n_params, cudaMemcpyHostToDevice, s));
+  CU(cudaMemsetAsync(n->st1, 0, sizeof(float) * n->n_params, s)); CU(cudaMemsetAsync(n->grads, 0, sizeof(float) * n->n_params, s));
+  CU(cudaMemsetAsync(n->step_dev, 0, sizeof(int), s));
+  std::vector<int32_t> cs; std::vector<int64_t> co;
+  for (size_t i = 0; i < n->segs.size(); ++i) for (int64_t o = n->segs[i].off; o < n->segs[i].off + n->segs[i].len; o += UPD_CHUNK) { cs.push_back((int32_t)i); co.push_back(o); }
+  n->nchunks = (int)cs.size();
+  B2(dalloc(n, &n->segs_dev, sizeof(UpdSeg) * std::max<size_t>(1, n->segs.size()))); B2(dalloc(n, &n->chunk_seg_dev, sizeof(int32_t) * std::max(1, n->nchunks))); B2(dalloc(n, &n->chunk_off_dev, sizeof(int64_t) * std::max(1, n->nchunks)));
+  CU(cudaMemcpyAsync(n->segs_dev, n->segs.data(), sizeof(UpdSeg) * n->segs.size(), cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(n->chunk_seg_dev, cs.data(), sizeof(int32_t) * cs.size(), cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(n->chunk_off_dev, co.data(), sizeof(int64_t) * co.size(), cudaMemcpyHostToDevice, s));
+  n->n_l2 = (int)l2o.size();
+  if (n->n_l2) {
+    B2(dalloc(n, &n->l2_off_dev, sizeof(int64_t) * n->n_l2)); B2(dalloc(n, &n->l2_len_dev, sizeof(int64_t) * n->n_l2)); B2(dalloc(n, &n->l2_coef_dev, sizeof(float) * n->n_l2));
+    CU(cudaMemcpyAsync(n->l2_off_dev, l2o.data(), sizeof(int64_t) * n->n_l2, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(n->l2_len_dev, l2l.data(), sizeof(int64_t) * n->n_l2, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(n->l2_coef_dev, l2c.data(), sizeof(float) * n->n_l2, cudaMemcpyHostToDevice, s));
+  }
+  CU(cudaStreamSynchronize(s));
+  return 0;
+}
+
+// bf16 operand copies of every GEMM weight (straight + transposed); no-op in FP32 mode
+static void net_refresh_shadow(b2g_net* n, int only_layer = -1) {
+  if (n->prec != PREC_BF16) return;
+  for (size_t i = 0; i < n->L.size(); ++i) { auto& l = n->L[i];
+    if (!l.has_gemm() || (only_layer >= 0 && (int)i != only_layer)) continue;
+    k_weight_shadow(n->params + l.off_W, n->shadow + l.off_W_bf, n->shadow + l.off_Wt_bf, l.wA, l.wTaps, l.wB, n->ctx->stream);
+  }
+}
+
+// ------------------------------------------------------------------ forward / backward -------------------
+struct FwdOpts { int rows; int groups; bool train; bool update_running; void* out_override; };
+
+static const void* w_ptr(const b2g_net* n, const LayerRT& l, int* wprec) {
+  if (n->prec == PREC_BF16) { *wprec = PREC_BF16; return n->shadow + l.off_W_bf; }
+  *wprec = PREC_F32; return n->params + l.off_W;
+}
+
+static int32_t gemm_fprop(b2g_net* n, const LayerRT& l, const ConvGeom& g, const void* x, const float* bias, void* out, int act, float alpha) {
+  cudaStream_t s = n->ctx->stream; int wp; const void* w = w_ptr(n, l, &wp);
+  if (n->prec == PREC_BF16 && n->ctx->tc_ok && tc_fprop_supported(g)) {
+    if (k_tc_fprop(g, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)out, act, alpha, s) == 0) return 0;
+    return fail(B2G_ERR_CUDA, "tcgen05 fprop launch failed");
+  }
+  k_simt_fprop(n->prec, wp, g, x, w, bias, out, act, alpha, s); return 0;
+}
+static int32_t gemm_dgrad(b2g_net* n, const LayerRT& l, const ConvGeom& g, const void* dy, const float* bias, void* dx, int act, float alpha) {
+  cudaStream_t s = n->ctx->stream; int wp; const void* w = w_ptr(n, l, &wp);
+  if (n->prec == PREC_BF16 && n->ctx->tc_ok && tc_dgrad_supported(g)) {
+    if (k_tc_dgrad(g, (const __nv_bfloat16*)dy, n->shadow + l.off_Wt_bf, bias, (__nv_bfloat16*)dx, act, alpha, s) == 0) return 0;
+    return fail(B2G_ERR_CUDA, "tcgen05 dgrad launch failed");
+  }
+  k_simt_dgrad(n->prec, wp, g, dy, w, bias, dx, act, alpha, s); return 0;
+}
+static int32_t gemm_wgrad(b2g_net* n, const LayerRT& l, const ConvGeom& g, const void* x, const void* dy, float* dw) {
+  cudaStream_t s = n->ctx->stream;
+  if (n->prec == PREC_BF16 && n->ctx->tc_ok && tc_wgrad_supported(g)) {
+    if (k_tc_wgrad(g, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw, n->scratch, n->scratch_floats, 0, s) == 0) return 0;
+    return fail(B2G_ERR_CUDA, "tcgen05 wgrad launch failed");
+  }
+  k_simt_wgrad(n->prec, g, x, dy, dw, n->scratch, n->scratch_floats, 0, s); return 0;
+}
+
+// Runs layers [0, L) on `in` (T NHWC, rows examples). Returns pointer to the final activations.
+static int32_t net_forward(b2g_net* n, const void* in, const FwdOpts& o, const void** result) {
+  cudaStream_t s = n->ctx->stream;
+  if (o.rows > n->max_rows || o.rows < 1) return fail(B2G_ERR_SHAPE, "batch %d outside [1, max_batch=%d]", o.rows, n->max_rows);
+  if (o.groups < 1 || o.rows % o.groups) return fail(B2G_ERR_SHAPE, "batch %d not divisible into %d groups", o.rows, o.groups);
+  const int R = o.rows; const void* cur = in;
+  n->last_rows = R;
+  for (size_t i = 0; i < n->L.size(); ++i) {
+    LayerRT& l = n->L[i]; const b2g_layer_desc& d = l.d;
+    void* out = l.out;
+    if (i + 1 == n->L.size() && o.out_override && !l.out_alias) out = o.out_override;
+    const float* bias = l.off_b >= 0 ? n->params + l.off_b : nullptr;
+    switch (d.type) {
+      case B2G_LAYER_CONV2D: case B2G_LAYER_DENSE: case B2G_LAYER_OUTPUT: { ConvGeom g = l.geom; g.N = R; B2(gemm_fprop(n, l, g, cur, bias, out, d.act, d.act_alpha)); } break;
+      case B2G_LAYER_DECONV2D: { ConvGeom g = l.geom; g.N = R; B2(gemm_dgrad(n, l, g, cur, bias, out, d.act, d.act_alpha)); } break;
+      case B2G_LAYER_BATCHNORM: {
+        int rows_pg = (R / o.groups) * l.oh * l.ow;
+        if (o.train) k_bn_stats(n->prec, cur, rows_pg, l.oc, o.groups, n->scratch, l.bn_mean, l.bn_invstd, d.bn_eps, n->params + l.off_mean, n->params + l.off_var,
+                                o.update_running ? n->grads + l.off_mean : nullptr, o.update_running ? n->grads + l.off_var : nullptr, d.bn_decay, s);
+        else k_bn_prep_infer(n->params + l.off_mean, n->params + l.off_var, l.oc, o.groups, d.bn_eps, l.bn_mean, l.bn_invstd, s);
+        k_bn_apply(n->prec, cur, out, rows_pg, l.oc, o.groups, l.bn_mean, l.bn_invstd, n->params + l.off_gamma, n->params + l.off_beta, l.fused_act, l.fused_alpha, s);
+      } break;
+      case B2G_LAYER_ACTIVATION: if (l.act_fused_into_prev) out = (void*)cur; else k_act_fwd(n->prec, cur, out, (size_t)R * l.out_elems, d.act, d.act_alpha, s); break;
+      case B2G_LAYER_MAXPOOL: k_maxpool_fwd(n->prec, cur, out, l.argmax, R, l.ih, l.iw, l.ic, l.oh, l.ow, d.k_h, d.k_w, d.s_h, d.s_w, s); break;
+      case B2G_LAYER_UPSAMPLE2D: k_upsample_fwd(n->prec, cur, out, R, l.ih, l.iw, l.ic, d.k_h, s); break;
+      case B2G_LAYER_LOSS: out = (void*)cur; break;
+      case B2G_LAYER_FF_TO_CNN: if (l.out_alias) out = (void*)cur; else k_permute(n->prec, cur, out, R, l.oc, l.oh * l.ow, 1, s); break;
+      case B2G_LAYER_CNN_TO_FF: if (l.out_alias) out = (void*)cur; else k_permute(n->prec, cur, out, R, l.ic, l.ih * l.iw, 0, s); break;
+    }
+    if (l.out_alias) l.out = out;
+    cur = out;
+  }
+  CHECK_KERNELS();
+  if (result) *result = cur;
+  return 0;
+}
+
+// Back-propagates eps (T, w.r.t. the logits when the last layer is OUTPUT/LOSS: dz from k_xent) through the net.
+// `eps` must live in n->epsA or be an external buffer; uses epsA/epsB ping-pong.
+static int32_t net_backward(b2g_net* n, const void* net_in, void* eps, int rows, int groups, bool want_wgrad, bool need_input_grad) {
+  cudaStream_t s = n->ctx->stream; const int R = rows;
+  void* cur = eps;
+  auto other = [&](void* p) { return p == n->epsA ? n->epsB : n->epsA; };
+  for (int i = (int)n->L.size() - 1; i >= 0; --i) {
+    LayerRT& l = n->L[i]; const b2g_layer_desc& d = l.d;
+    const void* lin = i == 0 ? net_in : n->L[i - 1].out;
+    // the epsilon w.r.t. this layer's input is needed only if a trainable layer sits below it (or the caller wants d/d input)
+    bool need_in = need_input_grad;
+    if (!need_in) for (int j = 0; j < i; ++j) if (n->L[j].has_gemm() || n->L[j].d.type == B2G_LAYER_BATCHNORM) need_in = true;
+    switch (d.type) {
+      case B2G_LAYER_LOSS: break;
+      case B2G_LAYER_CONV2D: case B2G_LAYER_DENSE: case B2G_LAYER_OUTPUT: {
+        ConvGeom g = l.geom; g.N = R;
+        if (d.act != B2G_ACT_IDENTITY) k_act_bwd_from_output(n->prec, l.out, cur, cur, (size_t)R * l.out_elems, d.act, d.act_alpha, s);
+        if (want_wgrad) {
+          B2(gemm_wgrad(n, l, g, lin, cur, n->grads + l.off_W));
+          if (l.off_b >= 0) k_colsum(n->prec, cur, R * l.oh * l.ow, l.oc, n->scratch, n->grads + l.off_b, 0, s);
+        }
+        if (need_in) { void* nx = other(cur); B2(gemm_dgrad(n, l, g, cur, nullptr, nx, ACT_IDENTITY, 0.f)); cur = nx; }
+      } break;
+      case B2G_LAYER_DECONV2D: {
+        ConvGeom g = l.geom; g.N = R;
+        if (d.act != B2G_ACT_IDENTITY) k_act_bwd_from_output(n->prec, l.out, cur, cur, (size_t)R * l.out_elems, d.act, d.act_alpha, s);
+        if (want_wgrad) {
+          B2(gemm_wgrad(n, l, g, /*conv input = deconv out grad*/ cur, /*conv dy = deconv input*/ lin, n->grads + l.off_W));
+          if (l.off_b >= 0) k_colsum(n->prec, cur, R * l.oh * l.ow, l.oc, n->scratch, n->grads + l.off_b, 0, s);
+        }
+        if (need_in) { void* nx = other(cur); B2(gemm_fprop(n, l, g, cur, nullptr, nx, ACT_IDENTITY, 0.f)); cur = nx; }
+      } break;
+      case B2G_LAYER_BATCHNORM: {
+        int rows_pg = (R / groups) * l.oh * l.ow; void* nx = need_in ? other(cur) : nullptr;
+        k_bn_bwd(n->prec, lin, cur, nx, rows_pg, l.oc, groups, l.bn_mean, l.bn_invstd, n->params + l.off_gamma, n->params + l.off_beta, l.fused_act, l.fused_alpha,
+                 n->scratch, n->grads + l.off_gamma, n->grads + l.off_beta, want_wgrad ? 1 : 0, s);
+        if (need_in) cur = nx;
+      } break;
+      case B2G_LAYER_ACTIVATION: if (!l.act_fused_into_prev) k_act_bwd_from_output(n->prec, l.out, cur, cur, (size_t)R * l.out_elems, d.act, d.act_alpha, s); break;
+      case B2G_LAYER_MAXPOOL: if (need_in) { void* nx = other(cur); k_maxpool_bwd(n->prec, cur, l.argmax, nx, R, l.ih, l.iw, l.ic, l.oh, l.ow, d.k_h, d.k_w, d.s_h, d.s_w, s); cur = nx; } break;
+      case B2G_LAYER_UPSAMPLE2D: if (need_in) { void* nx = other(cur); k_upsample_bwd(n->prec, cur, nx, R, l.ih, l.iw, l.ic, d.k_h, s); cur = nx; } break;
+      case B2G_LAYER_FF_TO_CNN: if (!l.out_alias && need_in) { void* nx = other(cur); k_permute(n->prec, cur, nx, R, l.oc, l.oh * l.ow, 0, s); cur = nx; } break;
+      case B2G_LAYER_CNN_TO_FF: if (!l.out_alias && need_in) { void* nx = other(cur); k_permute(n->prec, cur, nx, R, l.ic, l.ih * l.iw, 1, s); cur = nx; } break;
+    }
+    if (!need_in) { cur = nullptr; break; }
+  }
+  n->input_grad = cur;
+  CHECK_KERNELS();
+  return 0;
+}
+
+static int32_t net_allreduce_grads(b2g_net* n) {
+  b2g_ctx* c = n->ctx; if (!c->comm || c->world == 1) return 0;
+  NC(g_nccl.ar(n->grads, n->grads, (size_t)n->n_params, /*ncclFloat32*/ 7, /*ncclSum*/ 0, c->comm, c->stream));
+  return 0;
+}
+static int32_t net_update(b2g_net* n, int mb_local) {
+  cudaStream_t s = n->ctx->stream; int W = n->ctx->comm ? n->ctx->world : 1;
+  // BN running-stat pseudo-gradients are exempt from the minibatch division; under DP they are averaged over ranks
+  k_updater(n->params, n->grads, n->st0, n->st1, n->segs_dev, n->chunk_seg_dev, n->chunk_off_dev, n->nchunks, 1.0f / ((float)mb_local * W), 1.0f / (float)W, n->step_dev, nullptr, s);
+  k_inc_int(n->step_dev, s);
+  net_refresh_shadow(n);
+  CHECK_KERNELS();
+  return 0;
+}
+
+// ------------------------------------------------------------------ C-ABI: context ----------------------
+extern "C" int32_t b2g_version(void) { return B2G_VERSION; }
+extern "C" const char* b2g_last_error(void) { return g_err; }
+
+extern "C" int32_t b2g_ctx_create(int32_t device, b2g_ctx** out) {
+  if (!out) return fail(B2G_ERR_ARG, "null out");
+  int count = 0; cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) return fail(B2G_ERR_NO_DEVICE, "no CUDA device (%s); libb200gan has no CPU fallback", e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(B2G_ERR_ARG, "device %d of %d", device, count);
+  CU(cudaSetDevice(device));
+  b2g_ctx* c = new b2g_ctx(); c->device = device;
+  CU(cudaGetDeviceProperties(&c->prop, device));
+  if (c->prop.major != 10) { int mj = c->prop.major, mn = c->prop.minor; delete c; return fail(B2G_ERR_NO_DEVICE, "device is sm_%d%d; this library is built for sm_100a (B200) only", mj, mn); }
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->tc_ok = tc_init() == 0;
+  *out = c; return 0;
+}
+extern "C" int32_t b2g_ctx_destroy(b2g_ctx* c) {
+  if (!c) return 0; cudaSetDevice(c->device);
+  if (c->comm && g_nccl.destroy) g_nccl.destroy(c->comm);
+  if (c->t0) { cudaEventDestroy(c->t0); cudaEventDestroy(c->t1); } if (c->flush_buf) cudaFree(c->flush_buf);
+  if (c->stream) cudaStreamDestroy(c->stream); delete c; return 0;
+}
+extern "C" int32_t b2g_timer_start(b2g_ctx* c) {
+  if (!c) return fail(B2G_ERR_ARG, "null ctx"); CU(cudaSetDevice(c->device));
+  if (!c->t0) { CU(cudaEventCreate(&c->t0)); CU(cudaEventCreate(&c->t1)); }
+  CU(cudaEventRecord(c->t0, c->stream)); return 0;
+}
+extern "C" int32_t b2g_timer_stop_ms(b2g_ctx* c, float* ms) {
+  if (!c || !ms || !c->t0) return fail(B2G_ERR_ARG, "timer not started"); CU(cudaSetDevice(c->device));
+  CU(cudaEventRecord(c->t1, c->stream)); CU(cudaEventSynchronize(c->t1)); CU(cudaEventElapsedTime(ms, c->t0, c->t1)); return 0;
+}
+extern "C" int32_t b2g_flush_l2(b2g_ctx* c) {
+  if (!c) return fail(B2G_ERR_ARG, "null ctx"); CU(cudaSetDevice(c->device));
+  if (!c->flush_buf) { c->flush_bytes = (size_t)256 << 20; CU(cudaMalloc(&c->flush_buf, c->flush_bytes)); }
+  CU(cudaMemsetAsync(c->flush_buf, 0, c->flush_bytes, c->stream)); return 0;
+}
+extern "C" int32_t b2g_sync(b2g_ctx* c) { if (!c) return fail(B2G_ERR_ARG, "null ctx"); CU(cudaSetDevice(c->device)); CU(cudaStreamSynchronize(c->stream)); return 0; }
+extern "C" int32_t b2g_launch_count(b2g_ctx* c, uint64_t* out) { if (!c || !out) return fail(B2G_ERR_ARG, "null"); *out = g_launch_count; return 0; }
+extern "C" int32_t b2g_device_info(b2g_ctx* c, int32_t* sm, int32_t* mj, int32_t* mn, uint64_t* mem) {
+  if (!c) return fail(B2G_ERR_ARG, "null ctx");
+  if (sm) *sm = c->prop.multiProcessorCount; if (mj) *mj = c->prop.major; if (mn) *mn = c->prop.minor; if (mem) *mem = c->prop.totalGlobalMem; return 0;
+}
+
+// ------------------------------------------------------------------ C-ABI: nets --------------------------
+extern "C" int32_t b2g_net_create(b2g_ctx* ctx, const b2g_net_config* cfg, const b2g_layer_desc* layers, int32_t nl, b2g_net** out) {
+  if (!ctx || !cfg || !layers || nl < 1 || !out) return fail(B2G_ERR_ARG, "b2g_net_create: null/empty argument");
+  if (cfg->max_batch < 1 || cfg->in_h < 1 || cfg->in_w < 1 || cfg->in_c < 1) return fail(B2G_ERR_ARG, "b2g_net_create: bad input type / max_batch");
+  if (cfg->precision != B2G_PREC_FP32 && cfg->precision != B2G_PREC_BF16) return fail(B2G_ERR_ARG, "b2g_net_create: precision %d", cfg->precision);
+  CU(cudaSetDevice(ctx->device));
+  b2g_net* n = new b2g_net(); n->ctx = ctx; n->cfg = *cfg; n->prec = cfg->precision == B2G_PREC_BF16 ? PREC_BF16 : PREC_F32;
+  if (n->cfg.bn_groups < 1) n->cfg.bn_groups = 1;
+  int32_t r = net_build(n, layers, nl); if (!r) r = net_alloc(n); if (!r) r = net_init_params_and_updater(n);
+  if (!r) { net_refresh_shadow(n); cudaError_t e = cudaStreamSynchronize(ctx->stream); if (e != cudaSuccess) r = fail(B2G_ERR_CUDA, "init: %s", cudaGetErrorString(e)); }
+  if (r) { for (void* p : n->allocs) cudaFree(p); delete n; return r; }
+  *out = n; return 0;
+}
+extern "C" int32_t b2g_net_destroy(b2g_net* n) { if (!n) return 0; cudaSetDevice(n->ctx->device); cudaStreamSynchronize(n->ctx->stream); for (void* p : n->allocs) cudaFree(p); delete n; return 0; }
+extern "C" int32_t b2g_net_num_params(b2g_net* n, int64_t* out) { if (!n || !out) return fail(B2G_ERR_ARG, "null"); *out = n->n_params; return 0; }
+extern "C" int32_t b2g_net_output_size(b2g_net* n, int64_t* out) { if (!n || !out) return fail(B2G_ERR_ARG, "null"); *out = (int64_t)n->L.back().out_elems; return 0; }
+extern "C" int32_t b2g_net_layer_output_size(b2g_net* n, int32_t layer, int64_t* out) {
+  if (!n || !out || layer < 0 || layer >= (int)n->L.size()) return fail(B2G_ERR_ARG, "bad layer index"); *out = (int64_t)n->L[layer].out_elems; return 0;
+}
+
+struct ParamRef { int64_t off, len; bool conv_w; int A, B, taps; int layer; };
+static int32_t find_param(b2g_net* n, const char* layer, const char* param, ParamRef* r) {
+  for (size_t i = 0; i < n->L.size(); ++i) { LayerRT& l = n->L[i];
+    if (strncmp(l.d.name, layer, B2G_NAME_LEN)) continue;
+    r->conv_w = false; r->layer = (int)i;
+    if (!strcmp(param, "W") && l.off_W >= 0) { r->off = l.off_W; r->len = l.n_W; r->conv_w = l.wTaps > 1; r->A = l.wA; r->B = l.wB; r->taps = l.wTaps; return 0; }
+    if (!strcmp(param, "b") && l.off_b >= 0) { r->off = l.off_b; r->len = l.d.n_out; return 0; }
+    if (l.d.type == B2G_LAYER_BATCHNORM) {
+      if (!strcmp(param, "gamma")) { r->off = l.off_gamma; r->len = l.oc; return 0; }
+      if (!strcmp(param, "beta")) { r->off = l.off_beta; r->len = l.oc; return 0; }
+      if (!strcmp(param, "mean")) { r->off = l.off_mean; r->len = l.oc; return 0; }
+      if (!strcmp(param, "var")) { r->off = l.off_var; r->len = l.oc; return 0; }
+    }
+    return fail(B2G_ERR_ARG, "layer %s has no parameter %s", layer, param);
+  }
+  return fail(B2G_ERR_ARG, "no layer named %s", layer);
+}
+extern "C" int32_t b2g_net_set_param(b2g_net* n, const char* layer, const char* param, const float* host, int64_t cnt) {
+  if (!n || !layer || !param || !host) return fail(B2G_ERR_ARG, "null"); CU(cudaSetDevice(n->ctx->device));
+  ParamRef r; B2(find_param(n, layer, param, &r));
+  if (cnt != r.len) return fail(B2G_ERR_SHAPE, "%s.%s has %lld elements, got %lld", layer, param, (long long)r.len, (long long)cnt);
+  std::vector<float> tmp; const float* src = host;
+  if (r.conv_w) { tmp.resize(r.len); w_dl4j_to_internal(host, tmp.data(), r.A, r.B, r.taps); src = tmp.data(); }
+  CU(cudaMemcpyAsync(n->params + r.off, src, sizeof(float) * r.len, cudaMemcpyHostToDevice, n->ctx->stream));
+  CU(cudaStreamSynchronize(n->ctx->stream));
+  if (!strcmp(param, "W")) { net_refresh_shadow(n, r.layer); CU(cudaStreamSynchronize(n->ctx->stream)); }
+  return 0;
+}
+static int32_t read_flat(b2g_net* n, const float* dev, float* host, int64_t cnt) {
+  if (cnt != n->n_params) return fail(B2G_ERR_SHAPE, "net has %lld parameters, got %lld", (long long)n->n_params, (long long)cnt);
+  std::vector<float> tmp(n->n_params);
+  CU(cudaMemcpyAsync(tmp.data(), dev, sizeof(float) * n->n_params, cudaMemcpyDeviceToHost, n->ctx->stream)); CU(cudaStreamSynchronize(n->ctx->stream));
+  memcpy(host, tmp.data(), sizeof(float) * n->n_params);
+  for (auto& l : n->L) if (l.has_gemm() && l.wTaps > 1) w_internal_to_dl4j(tmp.data() + l.off_W, host + l.off_W, l.wA, l.wB, l.wTaps);
+  return 0;
+}
+static int32_t write_flat(b2g_net* n, float* dev, const float* host, int64_t cnt) {
+  if (cnt != n->n_params) return fail(B2G_ERR_SHAPE, "net has %lld parameters, got %lld", (long long)n->n_params, (long long)cnt);
+  std::vector<float> tmp(host, host + n->n_params);
+  for (auto& l : n->L) if (l.has_gemm() && l.wTaps > 1) w_dl4j_to_internal(host + l.off_W, tmp.data() + l.off_W, l.wA, l.wB, l.wTaps);
+  CU(cudaMemcpyAsync(dev, tmp.data(), sizeof(float) * n->n_params, cudaMemcpyHostToDevice, n->ctx->stream)); CU(cudaStreamSynchronize(n->ctx->stream));
+  return 0;
+}
+extern "C" int32_t b2g_net_get_param(b2g_net* n, const char* layer, const char* param, float* host, int64_t cnt) {
+  if (!n || !layer || !param || !host) return fail(B2G_ERR_ARG, "null"); CU(cudaSetDevice(n->ctx->device));
+  ParamRef r; B2(find_param(n, layer, param, &r));
+  if (cnt != r.len) return fail(B2G_ERR_SHAPE, "%s.%s has %lld elements, got %lld", layer, param, (long long)r.len, (long long)cnt);
+  std::vector<float> tmp(r.len);
+  CU(cudaMemcpyAsync(tmp.data(), n->params + r.off, sizeof(float) * r.len, cudaMemcpyDeviceToHost, n->ctx->stream)); CU(cudaStreamSynchronize(n->ctx->stream));
+  if (r.conv_w) w_internal_to_dl4j(tmp.data(), host, r.A, r.B, r.taps); else memcpy(host, tmp.data(), sizeof(float) * r.len);
+  return 0;
+}
+extern "C" int32_t b2g_net_get_params(b2g_net* n, float* host, int64_t cnt) { if (!n || !host) return fail(B2G_ERR_ARG, "null"); CU(cudaSetDevice(n->ctx->device)); return read_flat(n, n->params, host, cnt); }
+extern "C" int32_t b2g_net_set_params(b2g_net* n, const float* host, int64_t cnt) {
+  if (!n || !host) return fail(B2G_ERR_ARG, "null"); CU(cudaSetDevice(n->ctx->device)); B2(write_flat(n, n->params, host, cnt)); net_refresh_shadow(n); CU(cudaStreamSynchronize(n->ctx->stream)); return 0;
+}
+extern "C" int32_t b2g_net_get_gradients(b2g_net* n, float* host, int64_t cnt) { if (!n || !host) return fail(B2G_ERR_ARG, "null"); CU(cudaSetDevice(n->ctx->device)); return read_flat(n, n->grads, host, cnt); }
+extern "C" int32_t b2g_net_get_updater_state(b2g_net* n, float* host, int64_t cnt) {
+  if (!n || !host) return fail(B2G_ERR_ARG, "null"); CU(cudaSetDevice(n->ctx->device));
+  if (cnt != 2 * n->n_params) return fail(B2G_ERR_SHAPE, "updater state has %lld elements", (long long)(2 * n->n_params));
+  B2(read_flat(n, n->st0, host, n->n_params)); return read_flat(n, n->st1, host + n->n_params, n->n_params);
+}
+extern "C" int32_t b2g_net_set_updater_state(b2g_net* n, const float* host, int64_t cnt) {
+  if (!n || !host) return fail(B2G_ERR_ARG, "null"); CU(cudaSetDevice(n->ctx->device));
+  if (cnt != 2 * n->n_params) return fail(B2G_ERR_SHAPE, "updater state has %lld elements", (long long)(2 * n->n_params));
+  B2(write_flat(n, n->st0, host, n->n_params)); return write_flat(n, n->st1, host + n->n_params, n->n_params);
+}
+
+// host NCHW fp32 -> device input buffer (T NHWC)
+static int32_t upload_input(b2g_net* n, const float* x, int rows, void* dst) {
+  cudaStream_t s = n->ctx->stream; size_t cnt = (size_t)rows * n->in_elems;
+  if (cnt > n->stage_floats) return fail(B2G_ERR_SHAPE, "input larger than staging");
+  CU(cudaMemcpyAsync(n->stage_f32, x, sizeof(float) * cnt, cudaMemcpyHostToDevice, s));
+  k_nchw_f32_to_nhwc(n->prec, n->stage_f32, dst, rows, n->cfg.in_c, n->cfg.in_h * n->cfg.in_w, s);
+  return 0;
+}
+static int32_t download_act(b2g_net* n, const void* src, int rows, int C, int HW, float* host) {
+  cudaStream_t s = n->ctx->stream; size_t cnt = (size_t)rows * C * HW;
+  if (cnt > n->stage_floats) return fail(B2G_ERR_SHAPE, "activation larger than staging");
+  k_nhwc_to_nchw_f32(n->prec, src, n->stage_f32, rows, C, HW, s);
+  CU(cudaMemcpyAsync(host, n->stage_f32, sizeof(float) * cnt, cudaMemcpyDeviceToHost, s)); CU(cudaStreamSynchronize(s));
+  return 0;
+}
+
+extern "C" int32_t b2g_net_output(b2g_net* n, const float* x, int32_t batch, int32_t train, float* out) {
+  if (!n || !x || !out) return fail(B2G_ERR_ARG, "null"); CU(cudaSetDevice(n->ctx->device));
+  if (batch < 1 || batch > n->max_rows) return fail(B2G_ERR_SHAPE, "batch %d outside [1,%d]", batch, n->max_rows);
+  B2(upload_input(n, x, batch, n->input));
+  const void* res = nullptr; FwdOpts o{batch, 1, train != 0, false, nullptr};
+  B2(net_forward(n, n->input, o, &res));
+  LayerRT& l = n->L.back();
+  if (l.d.type == B2G_LAYER_OUTPUT || l.d.type == B2G_LAYER_LOSS) { k_sigmoid_out(n->prec, res, l.probs, (size_t)batch * l.out_elems, n->ctx->stream); res = l.probs; }
+  return download_act(n, res, batch, l.oc, l.oh * l.ow, out);
+}
+extern "C" int32_t b2g_net_get_activation(b2g_net* n, int32_t layer, int32_t batch, float* host) {
+  if (!n || !host || layer < 0 || layer >= (int)n->L.size()) return fail(B2G_ERR_ARG, "bad layer index"); CU(cudaSetDevice(n->ctx->device));
+  LayerRT& l = n->L[layer]; if (!l.out) return fail(B2G_ERR_ARG, "layer %d has not run", layer);
+  return download_act(n, l.out, batch, l.oc, l.oh * l.ow, host);
+}
+
+static int32_t train_pass(b2g_net* n, const float* x, const float* y, int batch, bool do_update, float* score) {
+  cudaStream_t s = n->ctx->stream;
+  if (batch < 1 || batch > n->max_rows) return fail(B2G_ERR_SHAPE, "batch %d outside [1,%d]", batch, n->max_rows);
+  int lt = n->L.back().d.type;
+  if (lt != B2G_LAYER_OUTPUT && lt != B2G_LAYER_LOSS) return fail(B2G_ERR_UNSUPPORTED, "fit needs a net ending in OutputLayer/LossLayer (XENT)");
+  B2(upload_input(n, x, batch, n->input));
+  CU(cudaMemcpyAsync(n->labels_dev, y, sizeof(float) * batch, cudaMemcpyHostToDevice, s));
+  CU(cudaMemsetAsync(n->grads, 0, sizeof(float) * n->n_params, s));
+  const void* logits = nullptr; FwdOpts o{batch, 1, true, true, nullptr};
+  B2(net_forward(n, n->input, o, &logits));
+  k_xent(n->prec, logits, n->labels_dev, n->epsA, n->loss_dev, batch, 1, n->cfg.xent_clip_eps, s);
+  B2(net_backward(n, n->input, n->epsA, batch, 1, true, false));
+  if (score) {
+    double l2 = 0.0; float ls = 0.f;
+    if (n->n_l2) { k_sumsq_segments(n->params, n->l2_off_dev, n->l2_len_dev, n->l2_coef_dev, n->n_l2, n->l2_dev, s); CU(cudaMemcpyAsync(&l2, n->l2_dev, sizeof(double), cudaMemcpyDeviceToHost, s)); }
+    CU(cudaMemcpyAsync(&ls, n->loss_dev, sizeof(float), cudaMemcpyDeviceToHost, s)); CU(cudaStreamSynchronize(s));
+    *score = ls / batch + (float)l2;
+  }
+  if (do_update) { B2(net_allreduce_grads(n)); B2(net_update(n, batch)); }
+  return 0;
+}
+extern "C" int32_t b2g_net_compute_gradient_and_score(b2g_net* n, const float* x, const float* y, int32_t batch, float* score) {
+  if (!n || !x || !y) return fail(B2G_ERR_ARG, "null"); CU(cudaSetDevice(n->ctx->device)); B2(train_pass(n, x, y, batch, false, score)); CU(cudaStreamSynchronize(n->ctx->stream)); return 0;
+}
+extern "C" int32_t b2g_net_fit(b2g_net* n, const float* x, const float* y, int32_t batch, float* score) {
+  if (!n || !x || !y) return fail(B2G_ERR_ARG, "null"); CU(cudaSetDevice(n->ctx->device)); B2(train_pass(n, x, y, batch, true, score)); CU(cudaStreamSynchronize(n->ctx->stream)); return 0;
+}
+extern "C" int32_t b2g_net_get_input_gradient(b2g_net* n, int32_t batch, float* host) {
+  if (!n || !host) return fail(B2G_ERR_ARG, "null"); CU(cudaSetDevice(n->ctx->device));
+  if (!n->input_grad) return fail(B2G_ERR_ARG, "no input gradient available (run b2g_gan_step or a backward that requests it)");
+  return download_act(n, n->input_grad, batch, n->cfg.in_c, n->cfg.in_h * n->cfg.in_w, host);
+}
+
+// ------------------------------------------------------------------ the fused GAN step -------------------
+struct b2g_gan {
+  b2g_net *G = nullptr, *D = nullptr; b2g_gan_config cfg{};
+  int N = 0;                              // per-step batch (D sees 2N)
+  void *z_d = nullptr, *z_g = nullptr;    // T [N][z]
+  float *y_d = nullptr, *y_g = nullptr;   // [2N] = y_real | y_fake ; [N]
+  float* loss_dev = nullptr;              // [4]: d_real_sum, d_fake_sum, g_sum
+  float* stage = nullptr; size_t stage_floats = 0;
+  cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; int graph_batch = 0; uint64_t graph_launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr; float last_ms = 0.f; int last_batch = 1;
+  std::vector<void*> allocs;
+};
+
+static int32_t gan_step_body(b2g_gan* g, int N) {
+  b2g_net *G = g->G, *D = g->D; cudaStream_t s = G->ctx->stream;
+  const size_t ts = prec_size(D->prec);
+  // 1. x_fake = gen.output(z_d)  (J:420) written straight into the second half of D's input batch
+  void* fake_dst = (char*)D->input + ts * (size_t)N * D->in_elems;
+  FwdOpts og{N, 1, g->cfg.fake_bn_train != 0, false, fake_dst};
+  B2(net_forward(G, g->z_d, og, nullptr));
+  // 2. D update on (x_real, y_real) | (x_fake, y_fake): two BN groups, one batched pass (J:414-426)
+  CU(cudaMemsetAsync(D->grads, 0, sizeof(float) * D->n_params, s));
+  const void* logits = nullptr; FwdOpts od{2 * N, 2, true, true, nullptr};
+  B2(net_forward(D, D->input, od, &logits));
+  k_xent(D->prec, logits, g->y_d, D->epsA, g->loss_dev, N, 2, D->cfg.xent_clip_eps, s);
+  B2(net_backward(D, D->input, D->epsA, 2 * N, 2, true, false));
+  B2(net_allreduce_grads(D));
+  B2(net_update(D, 2 * N));
+  // 3. G update through D on (z_g, y_gen) (J:465-471); D's parameters / running stats / updater state untouched
+  CU(cudaMemsetAsync(G->grads, 0, sizeof(float) * G->n_params, s));
+  const void* xg = nullptr; FwdOpts og2{N, 1, true, true, nullptr};
+  B2(net_forward(G, g->z_g, og2, &xg));
+  FwdOpts od2{N, 1, true, false, nullptr};
+  B2(net_forward(D, xg, od2, &logits));
+  k_xent(D->prec, logits, g->y_g, D->epsA, g->loss_dev + 2, N, 1, D->cfg.xent_clip_eps, s);
+  B2(net_backward(D, xg, D->epsA, N, 1, false, true));
+  B2(net_backward(G, g->z_g, D->input_grad, N, 1, true, false));
+  B2(net_allreduce_grads(G));
+  B2(net_update(G, N));
+  return 0;
+}
+
+extern "C" int32_t b2g_gan_create(b2g_net* gen, b2g_net* dis, const b2g_gan_config* cfg, b2g_gan** out) {
+  if (!gen || !dis || !out) return fail(B2G_ERR_ARG, "null");
+  if (gen->ctx != dis->ctx) return fail(B2G_ERR_ARG, "generator and discriminator live on different contexts");
+  if (gen->prec != dis->prec) return fail(B2G_ERR_ARG, "generator and discriminator use different precisions");
+  if (gen->L.back().out_elems != dis->in_elems) return fail(B2G_ERR_SHAPE, "generator output (%zu) != discriminator input (%zu)", gen->L.back().out_elems, dis->in_elems);
+  if (gen->L.back().out_alias) return fail(B2G_ERR_UNSUPPORTED, "generator must end in a layer that owns its output");
+  if (dis->cfg.bn_groups < 2 || dis->max_rows < 2) return fail(B2G_ERR_ARG, "discriminator must be created with bn_groups>=2 and max_batch = 2*N");
+  int N = std::min(gen->max_rows, dis->max_rows / 2);
+  CU(cudaSetDevice(gen->ctx->device));
+  b2g_gan* g = new b2g_gan(); g->G = gen; g->D = dis; if (cfg) g->cfg = *cfg; g->N = N;
+  const size_t ts = prec_size(gen->prec);
+  auto al = [&](void** p, size_t bytes) -> int32_t { cudaError_t e = cudaMalloc(p, bytes ? bytes : 16); if (e != cudaSuccess) return fail(B2G_ERR_OOM, "cudaMalloc: %s", cudaGetErrorString(e)); g->allocs.push_back(*p); return 0; };
+  int32_t r = al(&g->z_d, ts * N * gen->in_elems); if (!r) r = al(&g->z_g, ts * N * gen->in_elems);
+  if (!r) r = al((void**)&g->y_d, sizeof(float) * 2 * N); if (!r) r = al((void**)&g->y_g, sizeof(float) * N); if (!r) r = al((void**)&g->loss_dev, sizeof(float) * 4);
+  g->stage_floats = (size_t)N * std::max(dis->in_elems, gen->in_elems); if (!r) r = al((void**)&g->stage, sizeof(float) * g->stage_floats);
+  if (!r) { if (cudaEventCreate(&g->ev0) != cudaSuccess || cudaEventCreate(&g->ev1) != cudaSuccess) r = fail(B2G_ERR_CUDA, "cudaEventCreate failed"); }
+  if (r) { for (void* p : g->allocs) cudaFree(p); delete g; return r; }
+  *out = g; return 0;
+}
+extern "C" int32_t b2g_gan_destroy(b2g_gan* g) {
+  if (!g) return 0; cudaSetDevice(g->G->ctx->device); cudaStreamSynchronize(g->G->ctx->stream);
+  if (g->exec) cudaGraphExecDestroy(g->exec); if (g->graph) cudaGraphDestroy(g->graph);
+  if (g->ev0) cudaEventDestroy(g->ev0); if (g->ev1) cudaEventDestroy(g->ev1);
+  for (void* p : g->allocs) cudaFree(p); delete g; return 0;
+}
+extern "C" int32_t b2g_gan_upload(b2g_gan* g, const float* x_real, const float* z_d, const float* z_g, const float* y_real, const float* y_fake, const float* y_gen, int32_t batch) {
+  if (!g || !x_real || !z_d || !z_g || !y_real || !y_fake || !y_gen) return fail(B2G_ERR_ARG, "null");
+  if (batch < 1 || batch > g->N) return fail(B2G_ERR_SHAPE, "batch %d outside [1,%d]", batch, g->N);
+  b2g_net *G = g->G, *D = g->D; cudaStream_t s = G->ctx->stream; CU(cudaSetDevice(G->ctx->device));
+  size_t nx = (size_t)batch * D->in_elems, nz = (size_t)batch * G->in_elems;
+  CU(cudaMemcpyAsync(g->stage, x_real, sizeof(float) * nx, cudaMemcpyHostToDevice, s));
+  k_nchw_f32_to_nhwc(D->prec, g->stage, D->input, batch, D->cfg.in_c, D->cfg.in_h * D->cfg.in_w, s);
+  CU(cudaMemcpyAsync(G->stage_f32, z_d, sizeof(float) * nz, cudaMemcpyHostToDevice, s));
+  k_nchw_f32_to_nhwc(G->prec, G->stage_f32, g->z_d, batch, G->cfg.in_c, G->cfg.in_h * G->cfg.in_w, s);
+  CU(cudaMemcpyAsync(D->stage_f32, z_g, sizeof(float) * nz, cudaMemcpyHostToDevice, s));
+  k_nchw_f32_to_nhwc(G->prec, D->stage_f32, g->z_g, batch, G->cfg.in_c, G->cfg.in_h * G->cfg.in_w, s);
+  CU(cudaMemcpyAsync(g->y_d, y_real, sizeof(float) * batch, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(g->y_d + batch, y_fake, sizeof(float) * batch, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(g->y_g, y_gen, sizeof(float) * batch, cudaMemcpyHostToDevice, s));
+  CHECK_KERNELS();
+  return 0;
+}
+extern "C" int32_t b2g_gan_step_resident(b2g_gan* g, int32_t batch) {
+  if (!g) return fail(B2G_ERR_ARG, "null"); if (batch < 1 || batch > g->N) return fail(B2G_ERR_SHAPE, "batch %d outside [1,%d]", batch, g->N);
+  b2g_ctx* c = g->G->ctx; cudaStream_t s = c->stream; CU(cudaSetDevice(c->device));
+  bool use_graph = g->cfg.use_cuda_graph && !c->comm;
+  g->last_batch = batch;
+  CU(cudaEventRecord(g->ev0, s));
+  if (!use_graph) { B2(gan_step_body(g, batch)); }
+  else {
+    if (!g->exec || g->graph_batch != batch) {
+      if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; } if (g->graph) { cudaGraphDestroy(g->graph); g->graph = nullptr; }
+      uint64_t before = g_launch_count;
+      CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      int32_t r = gan_step_body(g, batch);
+      cudaError_t e = cudaStreamEndCapture(s, &g->graph);
+      g->graph_launches = g_launch_count - before; g_launch_count = before;
+      if (r) return r; if (e != cudaSuccess) return fail(B2G_ERR_CUDA, "graph capture: %s", cudaGetErrorString(e));
+      CU(cudaGraphInstantiate(&g->exec, g->graph, 0)); g->graph_batch = batch;
+    }
+    CU(cudaGraphLaunch(g->exec, s)); g_launch_count += g->graph_launches;
+  }
+  CU(cudaEventRecord(g->ev1, s));
+  return 0;
+}
+extern "C" int32_t b2g_gan_read_losses(b2g_gan* g, float* losses) {
+  if (!g || !losses) return fail(B2G_ERR_ARG, "null"); cudaStream_t s = g->G->ctx->stream; CU(cudaSetDevice(g->G->ctx->device));
+  float h[4]; CU(cudaMemcpyAsync(h, g->loss_dev, sizeof(h), cudaMemcpyDeviceToHost, s)); CU(cudaStreamSynchronize(s));
+  int N = g->last_batch;
+  losses[0] = h[0] / N; losses[1] = h[1] / N; losses[2] = h[2] / N; return 0;
+}
+extern "C" int32_t b2g_gan_last_step_ms(b2g_gan* g, float* ms) {
+  if (!g || !ms) return fail(B2G_ERR_ARG, "null"); CU(cudaEventSynchronize(g->ev1)); CU(cudaEventElapsedTime(ms, g->ev0, g->ev1)); return 0;
+}
+extern "C" int32_t b2g_gan_step(b2g_gan* g, const float* x_real, const float* z_d, const float* z_g, const float* y_real, const float* y_fake, const float* y_gen, int32_t batch, float* losses) {
+  B2(b2g_gan_upload(g, x_real, z_d, z_g, y_real, y_fake, y_gen, batch));
+  B2(b2g_gan_step_resident(g, batch));
+  if (losses) return b2g_gan_read_losses(g, losses);
+  return 0;
+}
+
+// ------------------------------------------------------------------ data parallel ------------------------
+extern "C" int32_t b2g_comm_unique_id(void* id128) { if (!id128) return fail(B2G_ERR_ARG, "null"); B2(nccl_load()); NcclId id; NC(g_nccl.uid(&id)); memcpy(id128, &id, sizeof(id)); return 0; }
+extern "C" int32_t b2g_ctx_comm_init(b2g_ctx* c, int32_t world, int32_t rank, const void* id128) {
+  if (!c || !id128 || world < 1 || rank < 0 || rank >= world) return fail(B2G_ERR_ARG, "bad communicator arguments");
+  B2(nccl_load()); CU(cudaSetDevice(c->device));
+  NcclId id; memcpy(&id, id128, sizeof(id));
+  NC(g_nccl.init(&c->comm, world, id, rank)); c->world = world; c->rank = rank; return 0;
+}
+extern "C" int32_t b2g_ctx_comm_destroy(b2g_ctx* c) { if (c && c->comm) { g_nccl.destroy(c->comm); c->comm = nullptr; c->world = 1; c->rank = 0; } return 0; }
+extern "C" int32_t b2g_ctx_allreduce_test(b2g_ctx* c, float* host, int64_t n) {
+  if (!c || !host || n < 1) return fail(B2G_ERR_ARG, "null"); if (!c->comm) return fail(B2G_ERR_NCCL, "no communicator"); CU(cudaSetDevice(c->device));
+  float* d = nullptr; CU(cudaMalloc(&d, sizeof(float) * n));
+  CU(cudaMemcpyAsync(d, host, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+  NC(g_nccl.ar(d, d, (size_t)n, 7, 0, c->comm, c->stream));
+  CU(cudaMemcpyAsync(host, d, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream)); CU(cudaStreamSynchronize(c->stream)); cudaFree(d); return 0;
+}
+
+// ------------------------------------------------------------------ kernel-level test hook ----------------
+extern "C" int32_t b2g_test_conv(b2g_ctx* c, int32_t kind, int32_t impl, int32_t precision, const b2g_conv_geom* gg, const float* a_host, const float* b_host, float* out, int32_t iters, float* ms_per_iter) {
+  if (!c || !gg || !a_host || !b_host || !out) return fail(B2G_ERR_ARG, "null"); CU(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream; int prec = precision == B2G_PREC_BF16 ? PREC_BF16 : PREC_F32; size_t ts = prec_size(prec);
+  ConvGeom g{gg->n, gg->h, gg->w, gg->c, gg->oh, gg->ow, gg->o, gg->kh, gg->kw, gg->sh, gg->sw, gg->ph, gg->pw};
+  size_t nx = (size_t)g.N * g.H * g.W * g.C, ny = (size_t)g.N * g.OH * g.OW * g.O, nw = (size_t)g.O * g.KH * g.KW * g.C;
+  // operands: kind 0: a = x (NHWC), b = w [O][KH][KW][C] -> out y ; kind 1: a = dy, b = w -> out dx ; kind 2: a = x, b = dy -> out dw (fp32)
+  size_t na = kind == 1 ? ny : nx, nb = kind == 2 ? ny : nw, no = kind == 0 ? ny : kind == 1 ? nx : nw;
+  if (impl == 1) {
+    if (prec != PREC_BF16 || !c->tc_ok) return fail(B2G_ERR_UNSUPPORTED, "tcgen05 kernels need BF16 precision and a working tensor-map encoder");
+    bool ok = kind == 0 ? tc_fprop_supported(g) : kind == 1 ? tc_dgrad_supported(g) : tc_wgrad_supported(g);
+    if (!ok) return fail(B2G_ERR_UNSUPPORTED, "no tcgen05 kernel for this shape");
+  }
+  float *fa = nullptr, *fb = nullptr, *fo = nullptr, *scratch = nullptr; void *ta = nullptr, *tb = nullptr, *tbt = nullptr, *to = nullptr;
+  size_t sc = std::max(k_simt_wgrad_scratch_floats(g), k_tc_wgrad_scratch_floats(g)) + 16;
+  CU(cudaMalloc(&fa, 4 * na)); CU(cudaMalloc(&fb, 4 * nb)); CU(cudaMalloc(&fo, 4 * no)); CU(cudaMalloc(&scratch, 4 * sc));
+  CU(cudaMalloc(&ta, ts * na)); CU(cudaMalloc(&tb, ts * nb)); CU(cudaMalloc(&tbt, ts * nb)); CU(cudaMalloc(&to, ts * no));
+  CU(cudaMemcpyAsync(fa, a_host, 4 * na, cudaMemcpyHostToDevice, s)); CU(cudaMemcpyAsync(fb, b_host, 4 * nb, cudaMemcpyHostToDevice, s));
+  if (prec == PREC_BF16) {
+    k_cast_f32_to_bf16(fa, (__nv_bfloat16*)ta, na, s);
+    if (kind == 2) k_cast_f32_to_bf16(fb, (__nv_bfloat16*)tb, nb, s); else k_weight_shadow(fb, (__nv_bfloat16*)tb, (__nv_bfloat16*)tbt, g.O, g.KH * g.KW, g.C, s);
+  } else { CU(cudaMemcpyAsync(ta, fa, 4 * na, cudaMemcpyDeviceToDevice, s)); CU(cudaMemcpyAsync(tb, fb, 4 * nb, cudaMemcpyDeviceToDevice, s)); }
+  cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  int reps = iters < 1 ? 1 : iters; int rc = 0;
+  for (int it = -1; it < reps; ++it) {       // it = -1: warm-up
+    if (it == 0) CU(cudaEventRecord(e0, s));
+    if (kind == 0) { if (impl) rc = k_tc_fprop(g, (const __nv_bfloat16*)ta, (const __nv_bfloat16*)tb, nullptr, (__nv_bfloat16*)to, 0, 0.f, s); else k_simt_fprop(prec, prec, g, ta, tb, nullptr, to, 0, 0.f, s); }
+    else if (kind == 1) { if (impl) rc = k_tc_dgrad(g, (const __nv_bfloat16*)ta, (const __nv_bfloat16*)tbt, nullptr, (__nv_bfloat16*)to, 0, 0.f, s); else k_simt_dgrad(prec, prec, g, ta, tb, nullptr, to, 0, 0.f, s); }
+    else { if (impl) rc = k_tc_wgrad(g, (const __nv_bfloat16*)ta, (const __nv_bfloat16*)tb, fo, scratch, sc, 0, s); else k_simt_wgrad(prec, g, ta, tb, fo, scratch, sc, 0, s); }
+    if (rc) break;
+  }
+  CU(cudaEventRecord(e1, s));
+  if (rc) return fail(B2G_ERR_CUDA, "tensor-core kernel launch failed (%d)", rc);
+  if (kind != 2) { if (prec == PREC_BF16) { /* widen */ k_nhwc_to_nchw_f32(prec, to, fo, 1, 1, (int)no, s); } else CU(cudaMemcpyAsync(fo, to, 4 * no, cudaMemcpyDeviceToDevice, s)); }
+  CU(cudaMemcpyAsync(out, fo, 4 * no, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s)); CHECK_KERNELS();
+  float ms = 0.f; CU(cudaEventElapsedTime(&ms, e0, e1)); if (ms_per_iter) *ms_per_iter = ms / reps;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(fa); cudaFree(fb); cudaFree(fo); cudaFree(scratch); cudaFree(ta); cudaFree(tb); cudaFree(tbt); cudaFree(to);
+  return 0;
+}

@@ -1,0 +1,114 @@
+// kernels.h -- launch wrappers of every CUDA kernel in libb200gan.so (sm_100a only).
+// Host-callable, stream-ordered, no allocation.  "prec" selects the activation storage type
+// (PREC_F32 = DL4J-parity mode, PREC_BF16 = tensor-core mode); statistics, parameters, gradients and
+// updater state are always fp32.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace b2g {
+
+enum Prec { PREC_F32 = 0, PREC_BF16 = 1 };
+enum Act { ACT_IDENTITY = 0, ACT_TANH = 1, ACT_SIGMOID = 2, ACT_RELU = 3, ACT_LRELU = 4 };
+
+inline size_t prec_size(int prec) { return prec == PREC_F32 ? 4 : 2; }
+
+// Convolution geometry, NHWC.  A dense layer is the 1x1 conv on a 1x1 image; a deconvolution is the
+// transposed problem (its forward is this geometry's dgrad, its input-gradient this geometry's fprop).
+struct ConvGeom {
+  int N, H, W, C;        // conv input
+  int OH, OW, O;         // conv output
+  int KH, KW, SH, SW, PH, PW;
+};
+
+extern uint64_t g_launch_count;   // every kernel launch of this library bumps it (bench evidence)
+
+// ---- layout ------------------------------------------------------------------------------------
+void k_nchw_f32_to_nhwc(int prec, const float* src, void* dst, int N, int C, int HW, cudaStream_t s);
+void k_nhwc_to_nchw_f32(int prec, const void* src, float* dst, int N, int C, int HW, cudaStream_t s);
+void k_permute(int prec, const void* src, void* dst, int N, int C, int HW, int to_nhwc, cudaStream_t s);
+void k_cast_f32_to_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t s);
+// w [A][KH*KW][B] fp32 -> bf16 same layout, plus transposed copy [B][KH*KW][A] (dgrad operand)
+void k_weight_shadow(const float* w, __nv_bfloat16* w_bf, __nv_bfloat16* wt_bf, int A, int taps, int B, cudaStream_t s);
+
+// ---- batch norm --------------------------------------------------------------------------------
+// Train-mode statistics per (group, channel): mean, invstd = 1/sqrt(var_biased+eps); optional DL4J running-stat
+// pseudo-gradients g_mean += w*(1-decay)*(run_mean-mean) (w = 1/groups so groups average).
+void k_bn_stats(int prec, const void* x, int rows_per_group, int C, int groups, float* scratch,
+                float* mean, float* invstd, float eps,
+                const float* run_mean, const float* run_var, float* g_mean, float* g_var, float decay, cudaStream_t s);
+size_t k_bn_scratch_floats(int C, int groups);
+// inference mode: mean <- run_mean, invstd <- rsqrt(run_var+eps) for every group
+void k_bn_prep_infer(const float* run_mean, const float* run_var, int C, int groups, float eps, float* mean, float* invstd, cudaStream_t s);
+// y = act(gamma*(x-mean)*invstd+beta)
+void k_bn_apply(int prec, const void* x, void* y, int rows_per_group, int C, int groups, const float* mean, const float* invstd,
+                const float* gamma, const float* beta, int act, float alpha, cudaStream_t s);
+// backward of y=act(bn(x)): reduce then apply.  dgamma/dbeta are ACCUMULATED over groups into g_gamma/g_beta (+=).
+void k_bn_bwd(int prec, const void* x, const void* eps_out, void* eps_in, int rows_per_group, int C, int groups,
+              const float* mean, const float* invstd, const float* gamma, const float* beta, int act, float alpha,
+              float* scratch, float* g_gamma, float* g_beta, int want_param_grads, cudaStream_t s);
+
+// ---- activations / pooling / upsampling -----------------------------------------------------------
+void k_act_fwd(int prec, const void* x, void* y, size_t n, int act, float alpha, cudaStream_t s);
+// eps_in = eps_out * f'(.) evaluated from the layer OUTPUT a (tanh: 1-a^2, sigmoid: a(1-a), relu/lrelu: sign of a)
+void k_act_bwd_from_output(int prec, const void* a, const void* eps_out, void* eps_in, size_t n, int act, float alpha, cudaStream_t s);
+void k_maxpool_fwd(int prec, const void* x, void* y, uint8_t* argmax, int N, int H, int W, int C, int OH, int OW, int KH, int KW, int SH, int SW, cudaStream_t s);
+void k_maxpool_bwd(int prec, const void* eps_out, const uint8_t* argmax, void* eps_in, int N, int H, int W, int C, int OH, int OW, int KH, int KW, int SH, int SW, cudaStream_t s);
+void k_upsample_fwd(int prec, const void* x, void* y, int N, int H, int W, int C, int f, cudaStream_t s);
+void k_upsample_bwd(int prec, const void* eps_out, void* eps_in, int N, int H, int W, int C, int f, cudaStream_t s);
+
+// ---- loss ----------------------------------------------------------------------------------------------
+// LossBinaryXENT on logits z[rows] with labels y[rows]: dz = dL/dz (sum form, not /mb), loss_sums[g] = sum of losses per group.
+void k_xent(int prec, const void* z, const float* y, void* dz, float* loss_sums, int rows_per_group, int groups, float clip_eps, cudaStream_t s);
+void k_sigmoid_out(int prec, const void* z, void* p, size_t n, cudaStream_t s);
+
+// ---- reductions ------------------------------------------------------------------------------------
+// out[c] (+)= sum_rows x[row][c]
+void k_colsum(int prec, const void* x, int rows, int C, float* scratch, float* out, int accumulate, cudaStream_t s);
+size_t k_colsum_scratch_floats(int C);
+// out[0] = sum_i coef[i] * x[i]^2 over the listed segments (l2 score)
+void k_sumsq_segments(const float* p, const int64_t* seg_off, const int64_t* seg_len, const float* seg_coef, int nseg, double* out, cudaStream_t s);
+// dst[i] = sum_s src[s*stride + i]
+void k_reduce_splits(const float* src, float* dst, size_t n, int splits, size_t stride, int accumulate, cudaStream_t s);
+
+// ---- updater (BaseMultiLayerUpdater + UpdaterBlock + params.subi, one pass) -----------------------------
+struct UpdSeg {            // one parameter tensor
+  int64_t off, len;
+  int kind;                // 0 sgd, 1 rmsprop, 2 adam, 3 noop
+  float lr, b1, b2, eps;   // rmsprop: b1 = rmsDecay
+  float l2;                // post-updater, not lr-scaled (pre-beta4)
+  float clip;              // elementwise clip threshold, 0 = off
+  int div_mb;              // 0 for BN mean/var pseudo-gradients
+  // bf16 shadow of a conv/deconv/dense weight: w_bf[off_bf..] same layout; wt_bf transposed [B][taps][A]
+  int64_t off_bf, off_bft;
+  int A, taps, B;
+};
+void k_updater(float* params, const float* grads, float* st0, float* st1, const UpdSeg* segs_dev, const int32_t* chunk_seg_dev,
+               const int64_t* chunk_off_dev, int nchunks, float inv_mb, float inv_world, const int* step_dev /* t = *step_dev + 1 */,
+               __nv_bfloat16* shadow, cudaStream_t s);
+static const int UPD_CHUNK = 4096;
+void k_inc_int(int* p, cudaStream_t s);          // *p += 1 (iteration counters live on the device so CUDA graphs replay)
+void k_fill_f32(float* p, float v, size_t n, cudaStream_t s);
+
+// ---- GEMM-shaped kernels, SIMT (fp32 FMA) -----------------------------------------------------------------
+// fprop:  out[m][o] = act(sum_k A[m][k] w[o][k] + bias[o]),  m=(n,oy,ox), k=(r,s,c);  w layout [O][KH][KW][C]
+void k_simt_fprop(int prec, int wprec, const ConvGeom& g, const void* x, const void* w, const float* bias, void* out, int act, float alpha, cudaStream_t s);
+// dgrad:  dx[m][c] = act(sum_k dy[..][o] w[o][r][s][c] + bias[c]),  m=(n,iy,ix)   (also the deconvolution forward)
+void k_simt_dgrad(int prec, int wprec, const ConvGeom& g, const void* dy, const void* w, const float* bias, void* dx, int act, float alpha, cudaStream_t s);
+// wgrad:  dw[o][r][s][c] = sum_pixels dy[pix][o] x[pix(r,s)][c]   (fp32 out, split-K scratch of k_simt_wgrad_scratch floats)
+void k_simt_wgrad(int prec, const ConvGeom& g, const void* x, const void* dy, float* dw, float* scratch, size_t scratch_floats, int accumulate, cudaStream_t s);
+size_t k_simt_wgrad_scratch_floats(const ConvGeom& g);
+
+// ---- GEMM-shaped kernels, tcgen05 tensor cores (bf16 in, fp32 accumulate in TMEM) -------------------------
+bool tc_fprop_supported(const ConvGeom& g);
+bool tc_dgrad_supported(const ConvGeom& g);
+bool tc_wgrad_supported(const ConvGeom& g);
+int  tc_init();   // resolves cuTensorMapEncodeTiled; 0 on success
+// stats: optional per-(group,channel) sum / sum-of-squares of the fp32 accumulators, fused in the epilogue
+int k_tc_fprop(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out, int act, float alpha, cudaStream_t s);
+int k_tc_dgrad(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat16* wt, const float* bias, __nv_bfloat16* dx, int act, float alpha, cudaStream_t s);
+int k_tc_wgrad(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* scratch, size_t scratch_floats, int accumulate, cudaStream_t s);
+size_t k_tc_wgrad_scratch_floats(const ConvGeom& g);
+
+}  // namespace b2g

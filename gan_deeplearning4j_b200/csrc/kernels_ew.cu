@@ -1,0 +1,432 @@
+// kernels_ew.cu -- the HBM-bound kernels of the GAN step: layout conversion, BatchNorm statistics /
+// apply / backward, activations, max-pool, upsampling, binary cross-entropy, column sums, and the
+// one-pass updater (divide-by-minibatch -> clip -> RmsProp/Adam -> +l2*W -> theta -= g).
+//
+// Semantics follow DL4J 1.0.0-beta3 as restated in oracle/dl4j_oracle.py (SURVEY.md section 8a rows
+// a3-a6, a8, a9); the reference call sites are J:123-125,132-134,141-144,159-163,201-202 where
+// J = /root/reference/Java/src/main/java/org/deeplearning4j/dl4jGANComputerVision.java.
+//
+// All of these are bandwidth-bound: threads are mapped so that a warp touches consecutive channels
+// (NHWC innermost), reductions are fixed-order two-stage (deterministic), nothing allocates.
+#include "kernels.h"
+#include "common.cuh"
+
+namespace b2g {
+
+uint64_t g_launch_count = 0;
+
+// ---------------------------------------------------------------- layout -----------------------------
+template <typename T>
+__global__ void nchw_f32_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int N, int C, int HW) {
+  // one thread per destination element (coalesced writes; reads strided by HW, served by L2)
+  size_t total = (size_t)N * C * HW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int c = i % C; size_t t = i / C; int p = t % HW; size_t n = t / HW;
+    stf(dst, i, src[(n * C + c) * HW + p]);
+  }
+}
+template <typename T>
+__global__ void nhwc_to_nchw_f32_kernel(const T* __restrict__ src, float* __restrict__ dst, int N, int C, int HW) {
+  size_t total = (size_t)N * C * HW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int p = i % HW; size_t t = i / HW; int c = t % C; size_t n = t / C;
+    dst[i] = ldf(src, (n * HW + p) * C + c);
+  }
+}
+template <typename T>
+__global__ void permute_kernel(const T* __restrict__ src, T* __restrict__ dst, int N, int C, int HW, int to_nhwc) {
+  size_t total = (size_t)N * C * HW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    if (to_nhwc) { int c = i % C; size_t t = i / C; int p = t % HW; size_t n = t / HW; dst[i] = src[(n * C + c) * HW + p]; }
+    else         { int p = i % HW; size_t t = i / HW; int c = t % C; size_t n = t / C; dst[i] = src[(n * HW + p) * C + c]; }
+  }
+}
+static inline int ew_blocks(size_t n, int per = 256) { size_t b = (n + per - 1) / per; if (b > 148 * 16) b = 148 * 16; if (b < 1) b = 1; return (int)b; }
+
+void k_nchw_f32_to_nhwc(int prec, const float* src, void* dst, int N, int C, int HW, cudaStream_t s) {
+  size_t n = (size_t)N * C * HW; if (!n) return;
+  DISPATCH_PREC(prec, T, (nchw_f32_to_nhwc_kernel<T><<<ew_blocks(n), 256, 0, s>>>(src, (T*)dst, N, C, HW))); LAUNCHED();
+}
+void k_nhwc_to_nchw_f32(int prec, const void* src, float* dst, int N, int C, int HW, cudaStream_t s) {
+  size_t n = (size_t)N * C * HW; if (!n) return;
+  DISPATCH_PREC(prec, T, (nhwc_to_nchw_f32_kernel<T><<<ew_blocks(n), 256, 0, s>>>((const T*)src, dst, N, C, HW))); LAUNCHED();
+}
+void k_permute(int prec, const void* src, void* dst, int N, int C, int HW, int to_nhwc, cudaStream_t s) {
+  size_t n = (size_t)N * C * HW; if (!n) return;
+  DISPATCH_PREC(prec, T, (permute_kernel<T><<<ew_blocks(n), 256, 0, s>>>((const T*)src, (T*)dst, N, C, HW, to_nhwc))); LAUNCHED();
+}
+__global__ void cast_f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = __float2bfloat16_rn(src[i]);
+}
+void k_cast_f32_to_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t s) {
+  if (!n) return; cast_f32_to_bf16_kernel<<<ew_blocks(n), 256, 0, s>>>(src, dst, n); LAUNCHED();
+}
+// w [A][taps][B] -> w_bf same layout, wt_bf [B][taps][A]; 32x32 smem-tiled transpose per tap
+__global__ void weight_shadow_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ w_bf, __nv_bfloat16* __restrict__ wt_bf, int A, int taps, int B) {
+  __shared__ float tile[32][33];
+  int tap = blockIdx.z, a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int a = a0 + i, b = b0 + threadIdx.x;
+    float v = 0.f;
+    if (a < A && b < B) { size_t idx = ((size_t)a * taps + tap) * B + b; v = w[idx]; if (w_bf) w_bf[idx] = __float2bfloat16_rn(v); }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (wt_bf) for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int b = b0 + i, a = a0 + threadIdx.x;
+    if (a < A && b < B) wt_bf[((size_t)b * taps + tap) * A + a] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+void k_weight_shadow(const float* w, __nv_bfloat16* w_bf, __nv_bfloat16* wt_bf, int A, int taps, int B, cudaStream_t s) {
+  dim3 grid((B + 31) / 32, (A + 31) / 32, taps);
+  weight_shadow_kernel<<<grid, dim3(32, 8), 0, s>>>(w, w_bf, wt_bf, A, taps, B); LAUNCHED();
+}
+
+// ---------------------------------------------------------------- sliced column reductions ---------------
+// Thread idx -> (slice s = idx / C, channel c = idx % C); it sums rows s, s+S, s+2S, ... so that a warp
+// reads consecutive addresses.  partial[(g*S + s)*C + c].  Stage 2: one warp per channel, fixed order.
+static inline int pick_slices(int rows, int C) {
+  int cap = 65536 / (C > 0 ? C : 1); if (cap < 1) cap = 1; if (cap > 2048) cap = 2048;
+  int S = rows / 8; if (S < 1) S = 1; if (S > cap) S = cap; return S;
+}
+size_t k_bn_scratch_floats(int C, int groups) { return (size_t)2 * groups * (65536 + 2 * (size_t)C) + 64; }
+size_t k_colsum_scratch_floats(int C) { return (size_t)(65536 + C) + 64; }
+
+template <typename T>
+__global__ void bn_stats_partial_kernel(const T* __restrict__ x, int rows, int C, int S, float* __restrict__ psum, float* __restrict__ psq) {
+  int g = blockIdx.y;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= S * C) return;
+  int c = idx % C, sl = idx / C;
+  const T* xg = x + (size_t)g * rows * C;
+  float a = 0.f, b = 0.f;
+  for (int r = sl; r < rows; r += S) { float v = ldf(xg, (size_t)r * C + c); a += v; b = fmaf(v, v, b); }
+  psum[((size_t)g * S + sl) * C + c] = a; psq[((size_t)g * S + sl) * C + c] = b;
+}
+__global__ void bn_stats_final_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int rows, int C, int S, int groups, float eps,
+                                      float* __restrict__ mean, float* __restrict__ invstd,
+                                      const float* __restrict__ run_mean, const float* __restrict__ run_var, float* g_mean, float* g_var, float decay) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
+  if (warp >= C) return;
+  int c = warp;
+  double acc_gm = 0.0, acc_gv = 0.0;
+  for (int g = 0; g < groups; ++g) {
+    double a = 0.0, b = 0.0;
+    for (int sl = lane; sl < S; sl += 32) { a += psum[((size_t)g * S + sl) * C + c]; b += psq[((size_t)g * S + sl) * C + c]; }
+    for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    double mu = a / rows, var = b / rows - mu * mu; if (var < 0) var = 0;
+    if (lane == 0) { mean[g * C + c] = (float)mu; invstd[g * C + c] = (float)(1.0 / sqrt(var + (double)eps)); }
+    if (g_mean) { acc_gm += (1.0 - decay) * ((double)run_mean[c] - mu); acc_gv += (1.0 - decay) * ((double)run_var[c] - var); }
+  }
+  // BatchNormalization running stats as pseudo-gradients through a NoOp updater; groups (the two D minibatches) averaged
+  if (g_mean && lane == 0) { g_mean[c] = (float)(acc_gm / groups); g_var[c] = (float)(acc_gv / groups); }
+}
+void k_bn_stats(int prec, const void* x, int rows, int C, int groups, float* scratch, float* mean, float* invstd, float eps,
+                const float* run_mean, const float* run_var, float* g_mean, float* g_var, float decay, cudaStream_t s) {
+  int S = pick_slices(rows, C);
+  float* psum = scratch; float* psq = scratch + (size_t)groups * S * C;
+  dim3 grid((S * C + 255) / 256, groups);
+  DISPATCH_PREC(prec, T, (bn_stats_partial_kernel<T><<<grid, 256, 0, s>>>((const T*)x, rows, C, S, psum, psq))); LAUNCHED();
+  bn_stats_final_kernel<<<(C * 32 + 255) / 256, 256, 0, s>>>(psum, psq, rows, C, S, groups, eps, mean, invstd, run_mean, run_var, g_mean, g_var, decay); LAUNCHED();
+}
+__global__ void bn_prep_infer_kernel(const float* __restrict__ rm, const float* __restrict__ rv, int C, int groups, float eps, float* mean, float* invstd) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= C * groups) return;
+  int c = i % C; mean[i] = rm[c]; invstd[i] = 1.0f / sqrtf(rv[c] + eps);
+}
+void k_bn_prep_infer(const float* run_mean, const float* run_var, int C, int groups, float eps, float* mean, float* invstd, cudaStream_t s) {
+  bn_prep_infer_kernel<<<(C * groups + 255) / 256, 256, 0, s>>>(run_mean, run_var, C, groups, eps, mean, invstd); LAUNCHED();
+}
+
+template <typename T>
+__global__ void bn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, int rows, int C, int groups, const float* __restrict__ mean,
+                                const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int act, float alpha) {
+  size_t per_group = (size_t)rows * C, total = per_group * groups;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int c = i % C; int g = i / per_group;
+    float v = (ldf(x, i) - mean[g * C + c]) * invstd[g * C + c];
+    stf(y, i, act_fwd(act, fmaf(gamma[c], v, beta[c]), alpha));
+  }
+}
+// bf16, C % 8 == 0: 16-byte vectors
+__global__ void bn_apply_bf16x8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int rows, int C, int groups, const float* __restrict__ mean,
+                                       const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int act, float alpha) {
+  size_t per_group = (size_t)rows * C / 8, total = per_group * groups; int C8 = C / 8;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int c0 = (i % C8) * 8; int g = i / per_group;
+    uint4 v = x[i]; __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = __bfloat1622float2(h[j]); int c = c0 + 2 * j;
+      f.x = act_fwd(act, fmaf(gamma[c], (f.x - mean[g * C + c]) * invstd[g * C + c], beta[c]), alpha);
+      f.y = act_fwd(act, fmaf(gamma[c + 1], (f.y - mean[g * C + c + 1]) * invstd[g * C + c + 1], beta[c + 1]), alpha);
+      h[j] = __floats2bfloat162_rn(f.x, f.y);
+    }
+    y[i] = v;
+  }
+}
+void k_bn_apply(int prec, const void* x, void* y, int rows, int C, int groups, const float* mean, const float* invstd,
+                const float* gamma, const float* beta, int act, float alpha, cudaStream_t s) {
+  size_t n = (size_t)rows * C * groups; if (!n) return;
+  if (prec == PREC_BF16 && C % 8 == 0) {
+    bn_apply_bf16x8_kernel<<<ew_blocks(n / 8), 256, 0, s>>>((const uint4*)x, (uint4*)y, rows, C, groups, mean, invstd, gamma, beta, act, alpha);
+  } else {
+    DISPATCH_PREC(prec, T, (bn_apply_kernel<T><<<ew_blocks(n), 256, 0, s>>>((const T*)x, (T*)y, rows, C, groups, mean, invstd, gamma, beta, act, alpha)));
+  }
+  LAUNCHED();
+}
+
+// backward of a = act(y), y = gamma*xhat + beta
+template <typename T>
+__global__ void bn_bwd_partial_kernel(const T* __restrict__ x, const T* __restrict__ eo, int rows, int C, int S, const float* __restrict__ mean,
+                                      const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int act, float alpha,
+                                      float* __restrict__ p1, float* __restrict__ p2) {
+  int g = blockIdx.y;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= S * C) return;
+  int c = idx % C, sl = idx / C;
+  const T* xg = x + (size_t)g * rows * C; const T* eg = eo + (size_t)g * rows * C;
+  float mu = mean[g * C + c], is = invstd[g * C + c], ga = gamma[c], be = beta[c];
+  float a = 0.f, b = 0.f;
+  for (int r = sl; r < rows; r += S) {
+    float xh = (ldf(xg, (size_t)r * C + c) - mu) * is;
+    float dy = ldf(eg, (size_t)r * C + c) * act_grad_from_pre(act, fmaf(ga, xh, be), alpha);
+    a += dy; b = fmaf(dy, xh, b);
+  }
+  p1[((size_t)g * S + sl) * C + c] = a; p2[((size_t)g * S + sl) * C + c] = b;
+}
+__global__ void bn_bwd_final_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int rows, int C, int S, int groups,
+                                    float* __restrict__ c1, float* __restrict__ c2, float* g_gamma, float* g_beta, int want) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
+  if (warp >= C) return;
+  int c = warp; double tg = 0.0, tb = 0.0;
+  for (int g = 0; g < groups; ++g) {
+    double a = 0.0, b = 0.0;
+    for (int sl = lane; sl < S; sl += 32) { a += p1[((size_t)g * S + sl) * C + c]; b += p2[((size_t)g * S + sl) * C + c]; }
+    for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    if (lane == 0) { c1[g * C + c] = (float)(a / rows); c2[g * C + c] = (float)(b / rows); }
+    tb += a; tg += b;
+  }
+  if (want && lane == 0) { g_beta[c] += (float)tb; g_gamma[c] += (float)tg; }
+}
+template <typename T>
+__global__ void bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ eo, T* __restrict__ ei, int rows, int C, int groups,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, int act, float alpha, const float* __restrict__ c1, const float* __restrict__ c2) {
+  size_t per_group = (size_t)rows * C, total = per_group * groups;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int c = i % C; int g = i / per_group; int k = g * C + c;
+    float xh = (ldf(x, i) - mean[k]) * invstd[k];
+    float dy = ldf(eo, i) * act_grad_from_pre(act, fmaf(gamma[c], xh, beta[c]), alpha);
+    stf(ei, i, gamma[c] * invstd[k] * (dy - c1[k] - xh * c2[k]));
+  }
+}
+void k_bn_bwd(int prec, const void* x, const void* eps_out, void* eps_in, int rows, int C, int groups,
+              const float* mean, const float* invstd, const float* gamma, const float* beta, int act, float alpha,
+              float* scratch, float* g_gamma, float* g_beta, int want, cudaStream_t s) {
+  int S = pick_slices(rows, C);
+  float* p1 = scratch; float* p2 = p1 + (size_t)groups * S * C; float* c1 = p2 + (size_t)groups * S * C; float* c2 = c1 + (size_t)groups * C;
+  dim3 grid((S * C + 255) / 256, groups);
+  DISPATCH_PREC(prec, T, (bn_bwd_partial_kernel<T><<<grid, 256, 0, s>>>((const T*)x, (const T*)eps_out, rows, C, S, mean, invstd, gamma, beta, act, alpha, p1, p2))); LAUNCHED();
+  bn_bwd_final_kernel<<<(C * 32 + 255) / 256, 256, 0, s>>>(p1, p2, rows, C, S, groups, c1, c2, g_gamma, g_beta, want); LAUNCHED();
+  if (eps_in) {
+    size_t n = (size_t)rows * C * groups;
+    DISPATCH_PREC(prec, T, (bn_bwd_apply_kernel<T><<<ew_blocks(n), 256, 0, s>>>((const T*)x, (const T*)eps_out, (T*)eps_in, rows, C, groups, mean, invstd, gamma, beta, act, alpha, c1, c2))); LAUNCHED();
+  }
+}
+
+// ---------------------------------------------------------------- activations ---------------------------
+template <typename T>
+__global__ void act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, size_t n, int act, float alpha) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) stf(y, i, act_fwd(act, ldf(x, i), alpha));
+}
+template <typename T>
+__global__ void act_bwd_out_kernel(const T* __restrict__ a, const T* __restrict__ eo, T* __restrict__ ei, size_t n, int act, float alpha) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    stf(ei, i, ldf(eo, i) * act_grad_from_out(act, ldf(a, i), alpha));
+}
+void k_act_fwd(int prec, const void* x, void* y, size_t n, int act, float alpha, cudaStream_t s) {
+  if (!n) return; DISPATCH_PREC(prec, T, (act_fwd_kernel<T><<<ew_blocks(n), 256, 0, s>>>((const T*)x, (T*)y, n, act, alpha))); LAUNCHED();
+}
+void k_act_bwd_from_output(int prec, const void* a, const void* eo, void* ei, size_t n, int act, float alpha, cudaStream_t s) {
+  if (!n) return; DISPATCH_PREC(prec, T, (act_bwd_out_kernel<T><<<ew_blocks(n), 256, 0, s>>>((const T*)a, (const T*)eo, (T*)ei, n, act, alpha))); LAUNCHED();
+}
+void k_sigmoid_out(int prec, const void* z, void* p, size_t n, cudaStream_t s) { k_act_fwd(prec, z, p, n, ACT_SIGMOID, 0.f, s); }
+
+// ---------------------------------------------------------------- max-pool / upsample ---------------------
+template <typename T>
+__global__ void maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint8_t* __restrict__ arg, int N, int H, int W, int C, int OH, int OW, int KH, int KW, int SH, int SW) {
+  size_t total = (size_t)N * OH * OW * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int c = i % C; size_t t = i / C; int ox = t % OW; t /= OW; int oy = t % OH; size_t n = t / OH;
+    float best = -INFINITY; int bi = 0;
+    for (int r = 0; r < KH; ++r) for (int q = 0; q < KW; ++q) {   // row-major window order; first max wins (DL4J tie rule)
+      float v = ldf(x, ((n * H + oy * SH + r) * W + ox * SW + q) * C + c);
+      if (v > best) { best = v; bi = r * KW + q; }
+    }
+    stf(y, i, best); arg[i] = (uint8_t)bi;
+  }
+}
+template <typename T>
+__global__ void maxpool_bwd_kernel(const T* __restrict__ eo, const uint8_t* __restrict__ arg, T* __restrict__ ei, int N, int H, int W, int C, int OH, int OW, int KH, int KW, int SH, int SW) {
+  // gather form (deterministic): each input pixel sums the eps of the windows whose arg-max it is
+  size_t total = (size_t)N * H * W * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int c = i % C; size_t t = i / C; int ix = t % W; t /= W; int iy = t % H; size_t n = t / H;
+    float acc = 0.f;
+    for (int r = 0; r < KH; ++r) { int ty = iy - r; if (ty < 0 || ty % SH) continue; int oy = ty / SH; if (oy >= OH) continue;
+      for (int q = 0; q < KW; ++q) { int tx = ix - q; if (tx < 0 || tx % SW) continue; int ox = tx / SW; if (ox >= OW) continue;
+        size_t o = ((n * OH + oy) * OW + ox) * C + c;
+        if (arg[o] == r * KW + q) acc += ldf(eo, o);
+      } }
+    stf(ei, i, acc);
+  }
+}
+void k_maxpool_fwd(int prec, const void* x, void* y, uint8_t* arg, int N, int H, int W, int C, int OH, int OW, int KH, int KW, int SH, int SW, cudaStream_t s) {
+  size_t n = (size_t)N * OH * OW * C; if (!n) return;
+  DISPATCH_PREC(prec, T, (maxpool_fwd_kernel<T><<<ew_blocks(n), 256, 0, s>>>((const T*)x, (T*)y, arg, N, H, W, C, OH, OW, KH, KW, SH, SW))); LAUNCHED();
+}
+void k_maxpool_bwd(int prec, const void* eo, const uint8_t* arg, void* ei, int N, int H, int W, int C, int OH, int OW, int KH, int KW, int SH, int SW, cudaStream_t s) {
+  size_t n = (size_t)N * H * W * C; if (!n) return;
+  DISPATCH_PREC(prec, T, (maxpool_bwd_kernel<T><<<ew_blocks(n), 256, 0, s>>>((const T*)eo, arg, (T*)ei, N, H, W, C, OH, OW, KH, KW, SH, SW))); LAUNCHED();
+}
+template <typename T>
+__global__ void upsample_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int f) {
+  size_t total = (size_t)N * H * f * W * f * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int c = i % C; size_t t = i / C; int ox = t % (W * f); t /= (W * f); int oy = t % (H * f); size_t n = t / (H * f);
+    y[i] = x[((n * H + oy / f) * W + ox / f) * C + c];
+  }
+}
+template <typename T>
+__global__ void upsample_bwd_kernel(const T* __restrict__ eo, T* __restrict__ ei, int N, int H, int W, int C, int f) {
+  size_t total = (size_t)N * H * W * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int c = i % C; size_t t = i / C; int ix = t % W; t /= W; int iy = t % H; size_t n = t / H;
+    float acc = 0.f;
+    for (int a = 0; a < f; ++a) for (int b = 0; b < f; ++b) acc += ldf(eo, ((n * H * f + iy * f + a) * (size_t)(W * f) + ix * f + b) * C + c);
+    stf(ei, i, acc);
+  }
+}
+void k_upsample_fwd(int prec, const void* x, void* y, int N, int H, int W, int C, int f, cudaStream_t s) {
+  size_t n = (size_t)N * H * f * W * f * C; if (!n) return;
+  DISPATCH_PREC(prec, T, (upsample_fwd_kernel<T><<<ew_blocks(n), 256, 0, s>>>((const T*)x, (T*)y, N, H, W, C, f))); LAUNCHED();
+}
+void k_upsample_bwd(int prec, const void* eo, void* ei, int N, int H, int W, int C, int f, cudaStream_t s) {
+  size_t n = (size_t)N * H * W * C; if (!n) return;
+  DISPATCH_PREC(prec, T, (upsample_bwd_kernel<T><<<ew_blocks(n), 256, 0, s>>>((const T*)eo, (T*)ei, N, H, W, C, f))); LAUNCHED();
+}
+
+// ---------------------------------------------------------------- XENT ---------------------------------
+// LossBinaryXENT + sigmoid on the logit (J:159-163): clip_eps>0 DL4J-exact, 0 = BCE-with-logits.
+template <typename T>
+__global__ void xent_kernel(const T* __restrict__ z, const float* __restrict__ y, T* __restrict__ dz, float* __restrict__ loss_sums, int rows, float clip) {
+  int g = blockIdx.x;
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+    size_t i = (size_t)g * rows + r;
+    float zi = ldf(z, i), yi = y[i], loss, grad;
+    float sg = 1.0f / (1.0f + expf(-zi));
+    if (clip > 0.f) {
+      float p = fminf(fmaxf(sg, clip), 1.0f - clip);
+      loss = -(yi * logf(p) + (1.0f - yi) * logf(1.0f - p));
+      grad = (p - yi) / (p * (1.0f - p)) * sg * (1.0f - sg);
+    } else {
+      loss = fmaxf(zi, 0.f) + log1pf(expf(-fabsf(zi))) - yi * zi;
+      grad = sg - yi;
+    }
+    acc += loss; stf(dz, i, grad);
+  }
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) { double t = 0; for (int w = 0; w < (blockDim.x + 31) / 32; ++w) t += red[w]; loss_sums[g] = (float)t; }
+}
+void k_xent(int prec, const void* z, const float* y, void* dz, float* loss_sums, int rows, int groups, float clip, cudaStream_t s) {
+  DISPATCH_PREC(prec, T, (xent_kernel<T><<<groups, 1024, 0, s>>>((const T*)z, y, (T*)dz, loss_sums, rows, clip))); LAUNCHED();
+}
+
+// ---------------------------------------------------------------- column sum / misc reductions -----------
+template <typename T>
+__global__ void colsum_partial_kernel(const T* __restrict__ x, int rows, int C, int S, float* __restrict__ p) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x; if (idx >= S * C) return;
+  int c = idx % C, sl = idx / C; float a = 0.f;
+  for (int r = sl; r < rows; r += S) a += ldf(x, (size_t)r * C + c);
+  p[(size_t)sl * C + c] = a;
+}
+__global__ void colsum_final_kernel(const float* __restrict__ p, int C, int S, float* out, int accumulate) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32; if (warp >= C) return;
+  double a = 0.0; for (int sl = lane; sl < S; sl += 32) a += p[(size_t)sl * C + warp];
+  for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) out[warp] = (accumulate ? out[warp] : 0.f) + (float)a;
+}
+void k_colsum(int prec, const void* x, int rows, int C, float* scratch, float* out, int accumulate, cudaStream_t s) {
+  int S = pick_slices(rows, C);
+  DISPATCH_PREC(prec, T, (colsum_partial_kernel<T><<<(S * C + 255) / 256, 256, 0, s>>>((const T*)x, rows, C, S, scratch))); LAUNCHED();
+  colsum_final_kernel<<<(C * 32 + 255) / 256, 256, 0, s>>>(scratch, C, S, out, accumulate); LAUNCHED();
+}
+__global__ void sumsq_segments_kernel(const float* __restrict__ p, const int64_t* off, const int64_t* len, const float* coef, int nseg, double* out) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int sgi = 0; sgi < nseg; ++sgi) {
+    const float* q = p + off[sgi]; double a = 0.0;
+    for (int64_t i = threadIdx.x; i < len[sgi]; i += blockDim.x) a += (double)q[i] * q[i];
+    acc += coef[sgi] * a;
+  }
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) { double t = 0; for (int w = 0; w < (blockDim.x + 31) / 32; ++w) t += red[w]; *out = t; }
+}
+void k_sumsq_segments(const float* p, const int64_t* so, const int64_t* sl, const float* sc, int nseg, double* out, cudaStream_t s) {
+  sumsq_segments_kernel<<<1, 1024, 0, s>>>(p, so, sl, sc, nseg, out); LAUNCHED();
+}
+__global__ void reduce_splits_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n, int splits, size_t stride, int accumulate) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float a = accumulate ? dst[i] : 0.f;
+    for (int k = 0; k < splits; ++k) a += src[(size_t)k * stride + i];
+    dst[i] = a;
+  }
+}
+void k_reduce_splits(const float* src, float* dst, size_t n, int splits, size_t stride, int accumulate, cudaStream_t s) {
+  if (!n) return; reduce_splits_kernel<<<ew_blocks(n), 256, 0, s>>>(src, dst, n, splits, stride, accumulate); LAUNCHED();
+}
+
+// ---------------------------------------------------------------- updater -------------------------------
+// One pass over params: 28 B/param for Adam (read p,g,m,v; write p,m,v), 20 B/param RmsProp, +2 B bf16 shadow.
+__global__ void __launch_bounds__(256) updater_kernel(float* __restrict__ params, const float* __restrict__ grads, float* __restrict__ st0, float* __restrict__ st1,
+                                                      const UpdSeg* __restrict__ segs, const int32_t* __restrict__ chunk_seg, const int64_t* __restrict__ chunk_off,
+                                                      float inv_mb, float inv_world, const int* __restrict__ step, __nv_bfloat16* __restrict__ shadow) {
+  const UpdSeg sg = segs[chunk_seg[blockIdx.x]];
+  const int64_t base = chunk_off[blockIdx.x];
+  const int64_t end = min(base + (int64_t)UPD_CHUNK, sg.off + sg.len);
+  const int t = *step + 1;
+  float alpha_t = 0.f;
+  if (sg.kind == 2) alpha_t = sg.lr * sqrtf(1.0f - powf(sg.b2, (float)t)) / (1.0f - powf(sg.b1, (float)t));
+  for (int64_t i = base + threadIdx.x; i < end; i += blockDim.x) {
+    float g = grads[i] * (sg.div_mb ? inv_mb : inv_world);   // BN running-stat pseudo-gradients: no /mb, mean over ranks
+    if (sg.clip > 0.f) g = fminf(fmaxf(g, -sg.clip), sg.clip);
+    float p = params[i], u;
+    if (sg.kind == 0) u = sg.lr * g;
+    else if (sg.kind == 1) { float c = sg.b1 * st0[i] + (1.0f - sg.b1) * g * g; st0[i] = c; u = sg.lr * g / (sqrtf(c) + sg.eps); }
+    else if (sg.kind == 2) { float m = sg.b1 * st0[i] + (1.0f - sg.b1) * g; float v = sg.b2 * st1[i] + (1.0f - sg.b2) * g * g; st0[i] = m; st1[i] = v; u = alpha_t * m / (sqrtf(v) + sg.eps); }
+    else u = g;
+    if (sg.l2 != 0.f) u = fmaf(sg.l2, p, u);
+    p -= u; params[i] = p;
+    if (shadow && sg.off_bf >= 0) shadow[sg.off_bf + (i - sg.off)] = __float2bfloat16_rn(p);
+  }
+}
+void k_updater(float* params, const float* grads, float* st0, float* st1, const UpdSeg* segs, const int32_t* chunk_seg, const int64_t* chunk_off,
+               int nchunks, float inv_mb, float inv_world, const int* step_dev, __nv_bfloat16* shadow, cudaStream_t s) {
+  if (!nchunks) return;
+  updater_kernel<<<nchunks, 256, 0, s>>>(params, grads, st0, st1, segs, chunk_seg, chunk_off, inv_mb, inv_world, step_dev, shadow); LAUNCHED();
+}
+
+__global__ void inc_int_kernel(int* p) { *p += 1; }
+void k_inc_int(int* p, cudaStream_t s) { inc_int_kernel<<<1, 1, 0, s>>>(p); LAUNCHED(); }
+__global__ void fill_f32_kernel(float* p, float v, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+void k_fill_f32(float* p, float v, size_t n, cudaStream_t s) { if (!n) return; fill_f32_kernel<<<ew_blocks(n), 256, 0, s>>>(p, v, n); LAUNCHED(); }
+
+}  // namespace b2g
