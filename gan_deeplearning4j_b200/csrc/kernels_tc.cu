@@ -1,12 +1,326 @@
-// kernels_tc.cu -- tcgen05 tensor-core kernels (placeholder while the SIMT path is brought up)
+// kernels_tc.cu -- the tensor-core hot path: implicit-GEMM convolution / transposed convolution on sm_100a
+// with TMA-staged shared-memory tiles, tcgen05.mma (bf16 x bf16 -> fp32 accumulators in TMEM) and a
+// tcgen05.ld epilogue.  Hand-written PTX; no CUTLASS, no cuDNN, no wgmma/mma.sync.
+//
+// Replaces DL4J's ConvolutionLayer.preOutput / backpropGradient (im2col buffer + OpenBLAS sgemm + separate bias
+// and activation passes; reference call sites J:135-150, 203-219) for the
+// DCGAN shapes of SURVEY.md Appendix B.
+//
+// One warp-specialised CTA computes a 128 x BN output tile:
+//   warp 0     TMA producer: per K-block one 4-D tensor-map box for the activations (the im2col gather is done by the
+//              TMA unit: traversal strides give the stride-2 sampling, out-of-bounds coordinates give the zero padding)
+//              and one 3-D box for the weights, both landing 128B-swizzled in a STAGES-deep smem ring (mbarrier expect_tx)
+//   warp 1     MMA issuer: one elected thread issues 4 x tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) per
+//              K-block straight from the swizzled smem tiles via matrix descriptors; tcgen05.commit frees the stage
+//   warps 2-5  epilogue: tcgen05.ld the fp32 accumulators (one TMEM lane = one output pixel), + bias, activation,
+//              convert to bf16, 16-byte stores of the contiguous NHWC channel run
+// Modes: fprop (conv forward; also the input-gradient of a transposed conv) and dgrad (conv input-gradient = transposed
+// conv forward) in sub-pixel phase form: a 4x4 stride-2 pad-1 transposed conv is four 2x2 stride-1 convs, one per output
+// parity class, so no MAC is spent on inserted zeros and nothing is scattered.
+#include <cuda.h>
+#include <stdio.h>
+
+#include "common.cuh"
 #include "kernels.h"
+
 namespace b2g {
-bool tc_fprop_supported(const ConvGeom&) { return false; }
-bool tc_dgrad_supported(const ConvGeom&) { return false; }
-bool tc_wgrad_supported(const ConvGeom&) { return false; }
-int tc_init() { return -1; }
-int k_tc_fprop(const ConvGeom&, const __nv_bfloat16*, const __nv_bfloat16*, const float*, __nv_bfloat16*, int, float, cudaStream_t) { return -1; }
-int k_tc_dgrad(const ConvGeom&, const __nv_bfloat16*, const __nv_bfloat16*, const float*, __nv_bfloat16*, int, float, cudaStream_t) { return -1; }
-int k_tc_wgrad(const ConvGeom&, const __nv_bfloat16*, const __nv_bfloat16*, float*, float*, size_t, int, cudaStream_t) { return -1; }
-size_t k_tc_wgrad_scratch_floats(const ConvGeom&) { return 0; }
+
+// ------------------------------------------------------------------ driver entry point (no -lcuda) ------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+
+int tc_init() {
+  if (g_encode) return 0;
+  void* fn = nullptr; cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn || q != cudaDriverEntryPointSuccess) return -1;
+  g_encode = (PFN_encodeTiled)fn; return 0;
 }
+
+static int make_map_bf16(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box, const cuuint32_t* estr) {
+  if (!g_encode) return -1;
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { fprintf(stderr, "[b200gan] cuTensorMapEncodeTiled failed: %d (rank %d)\n", (int)r, rank); return -1; }
+  return 0;
+}
+
+// ------------------------------------------------------------------ PTX wrappers --------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ int g_tc_timeout_flag = 0;
+// bounded wait: a wrong expect_tx byte count or a bad descriptor must not hang the GPU -- trap instead
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t it = 0; it < (1u << 26); ++it) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return;
+  }
+  g_tc_timeout_flag = 1; __trap();
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void prefetch_map(const CUtensorMap* map) { asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) { asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory"); }
+__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) { asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]),
+                 "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]),
+                 "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+               : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100 "version 1"): start address >> 4 in [0,14),
+// leading byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version in [46,48), layout type in [61,64)
+// (2 = SWIZZLE_128B).  K-major 128B-swizzled tile: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (1).
+__device__ __forceinline__ uint64_t desc_kmajor_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// MN-major 128B-swizzled tile (operand stored [K rows][64 MN elements]): 8-K-row groups 1024 B apart (SBO),
+// 64-element MN blocks `lbo_bytes` apart (LBO).
+__device__ __forceinline__ uint64_t desc_mnmajor_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) at [4,6), a/b format BF16 (1) at [7,10)/[10,13),
+// a_major [15], b_major [16] (0 = K-major, 1 = MN-major), N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------ conv fprop / dgrad-phase kernel -------
+struct TcConvParams {
+  int mode;                 // 0 = fprop, 1 = dgrad in sub-pixel phase form (4x4 s2 p1)
+  int Nt, Ht, Wt;           // A-tile rows = Nt images x Ht rows x Wt cols of the row grid (Nt*Ht*Wt = 128)
+  int GH, GW;               // row grid: conv output (fprop) / phase grid = dy spatial dims (dgrad)
+  int tiles_y;              // GH / Ht
+  int taps_h, taps_w;       // K-loop taps: KH,KW (fprop) / 2,2 (dgrad phase)
+  int chunks;               // reduction channels / 64
+  int KW, SH, SW, PH, PW;
+  int OC;                   // output channels = row length of `out`
+  int outH, outW;           // spatial dims of `out`
+  const float* bias; int act; float alpha;
+  __nv_bfloat16* out;
+};
+
+template <int BN, int STAGES>
+struct TcSmem {
+  static constexpr int A_BYTES = 128 * 128;        // 128 rows x 64 bf16
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;   // + barriers + alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcConvParams p) {
+  using S = TcSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_full = smem_base + S::BAR_OFF;                 // STAGES x 8 B
+  const uint32_t bar_empty = bar_full + 8 * STAGES;                 // STAGES x 8 B
+  const uint32_t bar_accum = bar_empty + 8 * STAGES;                // 8 B
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + S::BAR_OFF + 8 * (2 * STAGES + 1));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // tile coordinates
+  const int mt = blockIdx.x, nb0 = blockIdx.y * BN, phase = blockIdx.z;
+  const int py = phase >> 1, px = phase & 1;
+  int n0, y0;
+  if (p.Nt > 1) { n0 = mt * p.Nt; y0 = 0; } else { n0 = mt / p.tiles_y; y0 = (mt % p.tiles_y) * p.Ht; }
+  const int num_kb = p.taps_h * p.taps_w * p.chunks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_map(&tmA); prefetch_map(&tmB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_accum, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(smem_u32((const void*)tmem_slot), BN < 32 ? 32 : BN); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
+        const int ch = kb % p.chunks, tap = kb / p.chunks, ta = tap / p.taps_w, tb = tap % p.taps_w;
+        int ax, ay, wtap;
+        if (p.mode == 0) { ay = y0 * p.SH - p.PH + ta; ax = -p.PW + tb; wtap = ta * p.KW + tb; }
+        else {
+          // output row 2*q+py takes filter rows r with (py+1-r) even: py=0 -> r=1 (dy row q), r=3 (q-1); py=1 -> r=0 (q+1), r=2 (q)
+          const int r = py == 0 ? (ta == 0 ? 1 : 3) : (ta == 0 ? 0 : 2), dyr = py == 0 ? (ta == 0 ? 0 : -1) : (ta == 0 ? 1 : 0);
+          const int sx = px == 0 ? (tb == 0 ? 1 : 3) : (tb == 0 ? 0 : 2), dxc = px == 0 ? (tb == 0 ? 0 : -1) : (tb == 0 ? 1 : 0);
+          ay = y0 + dyr; ax = dxc; wtap = r * 4 + sx;
+        }
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        mbar_expect_tx(bar_full + 8 * s, S::STAGE_BYTES);
+        tma_load_4d(smem_base + s * S::STAGE_BYTES, &tmA, bar_full + 8 * s, ch * 64, ax, ay, n0);
+        tma_load_3d(smem_base + s * S::STAGE_BYTES + S::A_BYTES, &tmB, bar_full + 8 * s, ch * 64, wtap, nb0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(bar_full + 8 * s, ph);
+        tc_fence_after();
+        const uint64_t adesc = desc_kmajor_sw128(smem_base + s * S::STAGE_BYTES);
+        const uint64_t bdesc = desc_kmajor_sw128(smem_base + s * S::STAGE_BYTES + S::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)     // 4 x K=16 inside the 128-byte swizzle atom: +32 B = +2 in the (>>4) start-address field
+          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        umma_commit(bar_empty + 8 * s);
+      }
+      umma_commit(bar_accum);
+    }
+  } else {
+    // ===== epilogue: TMEM lane quadrant = warp % 4 =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int img = row / (p.Ht * p.Wt), rem = row % (p.Ht * p.Wt), yy = rem / p.Wt, xx = rem % p.Wt;
+    const int n = n0 + img, gy = y0 + yy, gx = xx;
+    size_t pix;
+    if (p.mode == 0) pix = ((size_t)n * p.outH + gy) * p.outW + gx;
+    else pix = ((size_t)n * p.outH + 2 * gy + py) * p.outW + 2 * gx + px;
+    __nv_bfloat16* orow = p.out + pix * p.OC + nb0;
+    mbar_wait(bar_accum, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld_wait();
+      uint32_t packed[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
+        if (p.bias) { a += p.bias[nb0 + c0 + 2 * j]; b += p.bias[nb0 + c0 + 2 * j + 1]; }
+        a = act_fwd(p.act, a, p.alpha); b = act_fwd(p.act, b, p.alpha);
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        packed[j] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      uint4* dst = reinterpret_cast<uint4*>(orow + c0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, BN < 32 ? 32 : BN); }
+}
+
+// ------------------------------------------------------------------ host side ------------------------------
+static bool pick_row_tile(int N, int GH, int GW, int rows, int* Nt, int* Ht, int* Wt) {
+  const int P = GH * GW;
+  if (GW > rows || rows % GW) return false;
+  if (P >= rows) { if (P % rows) return false; *Nt = 1; *Ht = rows / GW; *Wt = GW; return GH % *Ht == 0; }
+  if (rows % P || N % (rows / P)) return false;
+  *Nt = rows / P; *Ht = GH; *Wt = GW; return true;
+}
+static int pick_bn(int OC) { return OC % 256 == 0 ? 256 : OC % 128 == 0 ? 128 : OC % 64 == 0 ? 64 : 0; }
+
+bool tc_fprop_supported(const ConvGeom& g) {
+  int a, b, c;
+  return g.C % 64 == 0 && pick_bn(g.O) != 0 && g.SH >= 1 && g.SH <= 2 && g.SW == g.SH && g.KH * g.KW * (g.C / 64) >= 1 &&
+         pick_row_tile(g.N, g.OH, g.OW, 128, &a, &b, &c) && c * g.SW <= 256 && b * g.SH <= 256 && g.N >= 1;
+}
+bool tc_dgrad_supported(const ConvGeom& g) {
+  int a, b, c;
+  return g.KH == 4 && g.KW == 4 && g.SH == 2 && g.SW == 2 && g.PH == 1 && g.PW == 1 && g.O % 64 == 0 && pick_bn(g.C) != 0 && g.H == 2 * g.OH && g.W == 2 * g.OW &&
+         pick_row_tile(g.N, g.OH, g.OW, 128, &a, &b, &c);
+}
+
+template <int BN, int STAGES>
+static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvParams& p, dim3 grid, cudaStream_t s) {
+  using S = TcSmem<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) { if (cudaFuncSetAttribute(tc_conv_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) return -2; attr_set = true; }
+  tc_conv_kernel<BN, STAGES><<<grid, 192, S::TOTAL, s>>>(tmA, tmB, p);
+  LAUNCHED();
+  return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
+}
+static int dispatch_conv(int BN, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvParams& p, dim3 grid, cudaStream_t s) {
+  switch (BN) {
+    case 64: return launch_conv<64, 4>(tmA, tmB, p, grid, s);
+    case 128: return launch_conv<128, 3>(tmA, tmB, p, grid, s);
+    case 256: return launch_conv<256, 4>(tmA, tmB, p, grid, s);
+  }
+  return -4;
+}
+
+// weights as a 3-D tensor [rows][taps][Kred] (bf16, Kred contiguous); box = 64 x 1 x BN
+static int weight_map(CUtensorMap* m, const __nv_bfloat16* w, int rows, int taps, int kred, int BN) {
+  cuuint64_t dims[3] = {(cuuint64_t)kred, (cuuint64_t)taps, (cuuint64_t)rows};
+  cuuint64_t strides[2] = {(cuuint64_t)kred * 2, (cuuint64_t)taps * kred * 2};
+  cuuint32_t box[3] = {64, 1, (cuuint32_t)BN}; cuuint32_t es[3] = {1, 1, 1};
+  return make_map_bf16(m, w, 3, dims, strides, box, es);
+}
+
+int k_tc_fprop(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out, int act, float alpha, cudaStream_t s) {
+  TcConvParams p{}; p.mode = 0;
+  if (!pick_row_tile(g.N, g.OH, g.OW, 128, &p.Nt, &p.Ht, &p.Wt)) return -1;
+  const int BN = pick_bn(g.O);
+  p.GH = g.OH; p.GW = g.OW; p.tiles_y = g.OH / p.Ht; p.taps_h = g.KH; p.taps_w = g.KW; p.chunks = g.C / 64; p.KW = g.KW;
+  p.SH = g.SH; p.SW = g.SW; p.PH = g.PH; p.PW = g.PW; p.OC = g.O; p.outH = g.OH; p.outW = g.OW; p.bias = bias; p.act = act; p.alpha = alpha; p.out = out;
+  CUtensorMap tmA, tmB;
+  cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
+  cuuint64_t strides[3] = {(cuuint64_t)g.C * 2, (cuuint64_t)g.W * g.C * 2, (cuuint64_t)g.H * g.W * g.C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)(p.Wt * g.SW), (cuuint32_t)(p.Ht * g.SH), (cuuint32_t)p.Nt};
+  cuuint32_t es[4] = {1, (cuuint32_t)g.SW, (cuuint32_t)g.SH, 1};
+  if (make_map_bf16(&tmA, x, 4, dims, strides, box, es)) return -1;
+  if (weight_map(&tmB, w, g.O, g.KH * g.KW, g.C, BN)) return -1;
+  dim3 grid((unsigned)(g.N * g.OH * g.OW / 128), (unsigned)(g.O / BN), 1);
+  return dispatch_conv(BN, tmA, tmB, p, grid, s);
+}
+
+int k_tc_dgrad(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat16* wt, const float* bias, __nv_bfloat16* dx, int act, float alpha, cudaStream_t s) {
+  TcConvParams p{}; p.mode = 1;
+  if (!pick_row_tile(g.N, g.OH, g.OW, 128, &p.Nt, &p.Ht, &p.Wt)) return -1;
+  const int BN = pick_bn(g.C);
+  p.GH = g.OH; p.GW = g.OW; p.tiles_y = g.OH / p.Ht; p.taps_h = 2; p.taps_w = 2; p.chunks = g.O / 64; p.KW = 4;
+  p.SH = 1; p.SW = 1; p.PH = 0; p.PW = 0; p.OC = g.C; p.outH = g.H; p.outW = g.W; p.bias = bias; p.act = act; p.alpha = alpha; p.out = dx;
+  CUtensorMap tmA, tmB;
+  cuuint64_t dims[4] = {(cuuint64_t)g.O, (cuuint64_t)g.OW, (cuuint64_t)g.OH, (cuuint64_t)g.N};
+  cuuint64_t strides[3] = {(cuuint64_t)g.O * 2, (cuuint64_t)g.OW * g.O * 2, (cuuint64_t)g.OH * g.OW * g.O * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)p.Wt, (cuuint32_t)p.Ht, (cuuint32_t)p.Nt};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  if (make_map_bf16(&tmA, dy, 4, dims, strides, box, es)) return -1;
+  if (weight_map(&tmB, wt, g.C, 16, g.O, BN)) return -1;       // transposed shadow [C][taps][O]
+  dim3 grid((unsigned)(g.N * g.OH * g.OW / 128), (unsigned)(g.C / BN), 4);
+  return dispatch_conv(BN, tmA, tmB, p, grid, s);
+}
+
+// ------------------------------------------------------------------ wgrad (to come: MN-major operands) ----
+bool tc_wgrad_supported(const ConvGeom&) { return false; }
+size_t k_tc_wgrad_scratch_floats(const ConvGeom&) { return 0; }
+int k_tc_wgrad(const ConvGeom&, const __nv_bfloat16*, const __nv_bfloat16*, float*, float*, size_t, int, cudaStream_t) { return -1; }
+
+}  // namespace b2g
