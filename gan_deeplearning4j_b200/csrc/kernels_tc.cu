@@ -318,9 +318,166 @@ int k_tc_dgrad(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat16* 
   return dispatch_conv(BN, tmA, tmB, p, grid, s);
 }
 
-// ------------------------------------------------------------------ wgrad (to come: MN-major operands) ----
-bool tc_wgrad_supported(const ConvGeom&) { return false; }
-size_t k_tc_wgrad_scratch_floats(const ConvGeom&) { return 0; }
-int k_tc_wgrad(const ConvGeom&, const __nv_bfloat16*, const __nv_bfloat16*, float*, float*, size_t, int, cudaStream_t) { return -1; }
+// ------------------------------------------------------------------ wgrad: MN-major operands --------------
+// dW[o][tap][c] = sum over pixels of dy[pix][o] * x[pix shifted by tap][c].  The reduction index (pixels) is the
+// slow dimension of both NHWC operands, so both are fed to tcgen05.mma as MN-major tiles: a TMA box of
+// {64 channels, 64 pixels} lands as [pixel rows][128 B], which IS the canonical 128B-swizzled MN-major layout
+// (8-pixel groups 1024 B apart = SBO, 64-channel blocks one box apart = LBO).  No transposes anywhere.
+// CTA tile: 128 output channels (o) x BNW input channels (c) for one filter tap, over a split of the pixel range;
+// fp32 partials go to scratch[split] and are summed in fixed order (deterministic).
+struct TcWgradParams {
+  int Nt, Ht, Wt;          // K-block = 64 pixels of the dy grid = Nt images x Ht rows x Wt cols
+  int tiles_y;             // OH / Ht
+  int KW, SH, SW, PH, PW;
+  int taps, C;             // row length of dw = taps*C
+  int kb_total, kb_per_split;
+  int c_tiles;
+  float* out; size_t split_stride;
+};
+
+template <int BNW, int STAGES>
+struct TcWgradSmem {
+  static constexpr int A_BYTES = 2 * 64 * 128;            // two 64-channel blocks of dy
+  static constexpr int B_BYTES = (BNW / 64) * 64 * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+
+template <int BNW, int STAGES>
+__global__ void __launch_bounds__(192) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, const TcWgradParams p) {
+  using S = TcWgradSmem<BNW, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_full = smem_base + S::BAR_OFF, bar_empty = bar_full + 8 * STAGES, bar_accum = bar_empty + 8 * STAGES;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + S::BAR_OFF + 8 * (2 * STAGES + 1));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x, tap = blockIdx.y / p.c_tiles, c0 = (blockIdx.y % p.c_tiles) * BNW, o0 = blockIdx.z * 128;
+  const int r = tap / p.KW, sx = tap % p.KW;
+  const int kb_beg = split * p.kb_per_split, kb_end = min(p.kb_total, kb_beg + p.kb_per_split);
+  const int num_kb = max(0, kb_end - kb_beg);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_map(&tmDy); prefetch_map(&tmX);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_accum, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(smem_u32((const void*)tmem_slot), BNW < 32 ? 32 : BNW); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int kb = kb_beg + i, s = i % STAGES; const uint32_t ph = (i / STAGES) & 1;
+        int n0, y0;
+        if (p.Nt > 1) { n0 = kb * p.Nt; y0 = 0; } else { n0 = kb / p.tiles_y; y0 = (kb % p.tiles_y) * p.Ht; }
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        mbar_expect_tx(bar_full + 8 * s, S::STAGE_BYTES);
+        const uint32_t a = smem_base + s * S::STAGE_BYTES, b = a + S::A_BYTES;
+        tma_load_2d(a, &tmDy, bar_full + 8 * s, o0, kb * 64);
+        tma_load_2d(a + 8192, &tmDy, bar_full + 8 * s, o0 + 64, kb * 64);
+#pragma unroll
+        for (int j = 0; j < BNW / 64; ++j)
+          tma_load_4d(b + j * 8192, &tmX, bar_full + 8 * s, c0 + j * 64, -p.PW + sx, y0 * p.SH - p.PH + r, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, BNW, 1, 1);
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % STAGES; const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(bar_full + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t a = smem_base + s * S::STAGE_BYTES, b = a + S::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)     // 16 pixel rows per MMA = 2048 B down the tile
+          umma_bf16(tmem_base, desc_mnmajor_sw128(a + k * 2048, 8192), desc_mnmajor_sw128(b + k * 2048, 8192), idesc, (i | k) != 0);
+        umma_commit(bar_empty + 8 * s);
+      }
+      umma_commit(bar_accum);
+    }
+  } else {
+    const int q = warp & 3, row = q * 32 + lane;
+    float* orow = p.out + (size_t)split * p.split_stride + ((size_t)(o0 + row) * p.taps + tap) * p.C + c0;
+    if (num_kb > 0) {
+      mbar_wait(bar_accum, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < BNW; cc += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
+        tmem_ld_wait();
+        float4* dst = reinterpret_cast<float4*>(orow + cc);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+      }
+    } else {
+      for (int cc = 0; cc < BNW; cc += 4) *reinterpret_cast<float4*>(orow + cc) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, BNW < 32 ? 32 : BNW); }
+}
+
+static int wgrad_bnw(int C) { return C % 256 == 0 ? 256 : C % 128 == 0 ? 128 : C % 64 == 0 ? 64 : 0; }
+static int tc_wgrad_splits(const ConvGeom& g) {
+  const int bnw = wgrad_bnw(g.C); if (!bnw) return 1;
+  long tiles = (long)(g.O / 128) * g.KH * g.KW * (g.C / bnw), kbt = (long)g.N * g.OH * g.OW / 64;
+  long sp = (296 + tiles - 1) / tiles, cap = kbt / 8; if (cap < 1) cap = 1; if (sp > cap) sp = cap; if (sp < 1) sp = 1; return (int)sp;
+}
+bool tc_wgrad_supported(const ConvGeom& g) {
+  int a, b, c;
+  return g.O % 128 == 0 && wgrad_bnw(g.C) != 0 && g.SH >= 1 && g.SH <= 2 && g.SW == g.SH && ((long)g.N * g.OH * g.OW) % 64 == 0 &&
+         pick_row_tile(g.N, g.OH, g.OW, 64, &a, &b, &c) && c * g.SW <= 256 && b * g.SH <= 256;
+}
+size_t k_tc_wgrad_scratch_floats(const ConvGeom& g) {
+  if (!tc_wgrad_supported(g)) return 0;
+  return (size_t)tc_wgrad_splits(g) * g.O * g.KH * g.KW * g.C;
+}
+
+template <int BNW, int STAGES>
+static int launch_wgrad(const CUtensorMap& tmDy, const CUtensorMap& tmX, const TcWgradParams& p, dim3 grid, cudaStream_t s) {
+  using S = TcWgradSmem<BNW, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) { if (cudaFuncSetAttribute(tc_wgrad_kernel<BNW, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) return -2; attr_set = true; }
+  tc_wgrad_kernel<BNW, STAGES><<<grid, 192, S::TOTAL, s>>>(tmDy, tmX, p);
+  LAUNCHED();
+  return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
+}
+
+int k_tc_wgrad(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* scratch, size_t scratch_floats, int accumulate, cudaStream_t s) {
+  TcWgradParams p{};
+  if (!pick_row_tile(g.N, g.OH, g.OW, 64, &p.Nt, &p.Ht, &p.Wt)) return -1;
+  const int BNW = wgrad_bnw(g.C); const size_t n = (size_t)g.O * g.KH * g.KW * g.C;
+  int splits = tc_wgrad_splits(g);
+  if ((size_t)splits * n > scratch_floats) return -5;
+  p.tiles_y = g.OH / p.Ht; p.KW = g.KW; p.SH = g.SH; p.SW = g.SW; p.PH = g.PH; p.PW = g.PW; p.taps = g.KH * g.KW; p.C = g.C;
+  p.kb_total = (int)((long)g.N * g.OH * g.OW / 64); p.kb_per_split = (p.kb_total + splits - 1) / splits; p.c_tiles = g.C / BNW;
+  p.out = scratch; p.split_stride = n;
+  CUtensorMap tmDy, tmX;
+  { cuuint64_t dims[2] = {(cuuint64_t)g.O, (cuuint64_t)g.N * g.OH * g.OW}; cuuint64_t strides[1] = {(cuuint64_t)g.O * 2};
+    cuuint32_t box[2] = {64, 64}; cuuint32_t es[2] = {1, 1};
+    if (make_map_bf16(&tmDy, dy, 2, dims, strides, box, es)) return -1; }
+  { cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
+    cuuint64_t strides[3] = {(cuuint64_t)g.C * 2, (cuuint64_t)g.W * g.C * 2, (cuuint64_t)g.H * g.W * g.C * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)(p.Wt * g.SW), (cuuint32_t)(p.Ht * g.SH), (cuuint32_t)p.Nt}; cuuint32_t es[4] = {1, (cuuint32_t)g.SW, (cuuint32_t)g.SH, 1};
+    if (make_map_bf16(&tmX, x, 4, dims, strides, box, es)) return -1; }
+  dim3 grid((unsigned)splits, (unsigned)(p.taps * p.c_tiles), (unsigned)(g.O / 128));
+  int rc;
+  switch (BNW) {
+    case 64: rc = launch_wgrad<64, 4>(tmDy, tmX, p, grid, s); break;
+    case 128: rc = launch_wgrad<128, 4>(tmDy, tmX, p, grid, s); break;
+    default: rc = launch_wgrad<256, 4>(tmDy, tmX, p, grid, s); break;
+  }
+  if (rc) return rc;
+  k_reduce_splits(scratch, dw, n, splits, n, accumulate, s);
+  return 0;
+}
 
 }  // namespace b2g

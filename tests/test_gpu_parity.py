@@ -344,3 +344,22 @@ def test_tc_dgrad_phase_form_matches_oracle(b200, case):
     dy_nhwc = dy.transpose(0, 2, 3, 1); w_int = wt.transpose(0, 2, 3, 1)
     out, _ = b.test_conv(ctx, 1, 1, b.BF16, geom, dy_nhwc, w_int, dx.size)
     assert rel_err(out.reshape(n, h, w, c), dx.transpose(0, 2, 3, 1)) < 1e-2
+
+
+TC_WGRAD_CASES = [
+    # n, h, w, c, o  (4x4 s2 p1)
+    (4, 16, 16, 64, 128),     # 8x8 dy grid: one image per 64-pixel K-block, BNW=64
+    (2, 32, 32, 128, 128),    # 16x16 grid: 4 rows per K-block, BNW=128
+    (16, 8, 8, 256, 256),     # 4x4 grid: four images per K-block, BNW=256, two o-tiles
+]
+
+
+@pytest.mark.parametrize("case", TC_WGRAD_CASES)
+def test_tc_wgrad_mn_major_matches_oracle(b200, case):
+    b, ctx = b200
+    n, h, w, c, oc = case
+    rng = np.random.default_rng(4)
+    x, wt, y, dy, dx, dw = _conv_ref(n, h, w, c, oc, 4, 2, 1, rng, bf16_round)
+    geom = dict(n=n, h=h, w=w, c=c, oh=h // 2, ow=w // 2, o=oc, kh=4, kw=4, sh=2, sw=2, ph=1, pw=1)
+    out, _ = b.test_conv(ctx, 2, 1, b.BF16, geom, x.transpose(0, 2, 3, 1), dy.transpose(0, 2, 3, 1), dw.size)
+    assert rel_err(out.reshape(oc, 4, 4, c), dw.transpose(0, 2, 3, 1)) < 1e-4     # fp32 accumulate, fp32 out: only summation order differs
