@@ -4,7 +4,7 @@ ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v
 SRC := gan_deeplearning4j_b200/csrc
 OUT := gan_deeplearning4j_b200/lib
-OBJS := $(OUT)/kernels_ew.o $(OUT)/kernels_simt.o $(OUT)/kernels_tc.o $(OUT)/engine.o $(OUT)/jni_shim.o
+OBJS := $(OUT)/kernels_ew.o $(OUT)/kernels_simt.o $(OUT)/kernels_tc.o $(OUT)/kernels_edge.o $(OUT)/engine.o $(OUT)/jni_shim.o
 
 all: $(OUT)/libb200gan.so
 

@@ -149,6 +149,8 @@ static int32_t net_build(b2g_net* n, const b2g_layer_desc* layers, int32_t nl) {
         l.oh = (h - d.k_h + 2 * d.p_h) / d.s_h + 1; l.ow = (w - d.k_w + 2 * d.p_w) / d.s_w + 1; l.oc = d.n_out;   // ConvolutionMode.Truncate
         if (l.oh < 1 || l.ow < 1) return fail(B2G_ERR_SHAPE, "layer %s: kernel larger than input", d.name);
         l.geom = ConvGeom{0, h, w, ch, l.oh, l.ow, d.n_out, d.k_h, d.k_w, d.s_h, d.s_w, d.p_h, d.p_w};
+        // a "valid" conv whose window is the whole input (DCGAN D-last) is a dense layer over the NHWC-flattened input
+        if (l.oh == 1 && l.ow == 1 && d.k_h == h && d.k_w == w && d.p_h == 0 && d.p_w == 0) l.geom = ConvGeom{0, 1, 1, h * w * ch, 1, 1, d.n_out, 1, 1, 1, 1, 0, 0};
         l.wA = d.n_out; l.wTaps = d.k_h * d.k_w; l.wB = d.n_in;
         if (d.has_bias) { l.off_b = off; off += d.n_out; }                 // ConvolutionParamInitializer: [b | W]
         l.off_W = off; l.n_W = (int64_t)l.wA * l.wTaps * l.wB; off += l.n_W;
@@ -159,6 +161,9 @@ static int32_t net_build(b2g_net* n, const b2g_layer_desc* layers, int32_t nl) {
         l.oh = d.s_h * (h - 1) + d.k_h - 2 * d.p_h; l.ow = d.s_w * (w - 1) + d.k_w - 2 * d.p_w; l.oc = d.n_out;
         // conv-equivalent: conv input = deconv output, conv output = deconv input
         l.geom = ConvGeom{0, l.oh, l.ow, d.n_out, h, w, d.n_in, d.k_h, d.k_w, d.s_h, d.s_w, d.p_h, d.p_w};
+        // a transposed conv of a 1x1 map (DCGAN G-first: z -> 4x4) is the 1x1 problem with taps*nOut output channels: out[n][tap][c] = sum_o z[n][o] W[o][tap][c]
+        if (h == 1 && w == 1 && d.s_h == 1 && d.s_w == 1 && d.p_h == 0 && d.p_w == 0 && !d.has_bias && d.act == B2G_ACT_IDENTITY)
+          l.geom = ConvGeom{0, 1, 1, d.k_h * d.k_w * d.n_out, 1, 1, d.n_in, 1, 1, 1, 1, 0, 0};
         l.wA = d.n_in; l.wTaps = d.k_h * d.k_w; l.wB = d.n_out;
         if (d.has_bias) { l.off_b = off; off += d.n_out; }
         l.off_W = off; l.n_W = (int64_t)l.wA * l.wTaps * l.wB; off += l.n_W;
@@ -232,6 +237,7 @@ static int32_t net_alloc(b2g_net* n) {
     if (l.has_gemm()) {
       ConvGeom g = l.geom; g.N = R;
       scratch = std::max(scratch, std::max(k_simt_wgrad_scratch_floats(g), k_tc_wgrad_scratch_floats(g)));
+      scratch = std::max(scratch, std::max(k_edge_wgrad_scratch_floats(g), k_dense_small_o_wgrad_scratch_floats(g)));
       scratch = std::max(scratch, k_colsum_scratch_floats(std::max(l.oc, l.ic)));
       max_w = std::max(max_w, (size_t)l.n_W);
     }
@@ -314,6 +320,8 @@ static const void* w_ptr(const b2g_net* n, const LayerRT& l, int* wprec) {
 
 static int32_t gemm_fprop(b2g_net* n, const LayerRT& l, const ConvGeom& g, const void* x, const float* bias, void* out, int act, float alpha) {
   cudaStream_t s = n->ctx->stream; int wp; const void* w = w_ptr(n, l, &wp);
+  if (edge_conv_small_cin_supported(g)) { k_edge_conv_small_cin(n->prec, wp, g, x, w, bias, out, act, alpha, s); return 0; }
+  if (dense_small_o_supported(g)) { k_dense_small_o_fwd(n->prec, wp, g, x, w, bias, out, act, alpha, s); return 0; }
   if (n->prec == PREC_BF16 && n->ctx->tc_ok && tc_fprop_supported(g)) {
     if (k_tc_fprop(g, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)out, act, alpha, s) == 0) return 0;
     return fail(B2G_ERR_CUDA, "tcgen05 fprop launch failed");
@@ -322,6 +330,8 @@ static int32_t gemm_fprop(b2g_net* n, const LayerRT& l, const ConvGeom& g, const
 }
 static int32_t gemm_dgrad(b2g_net* n, const LayerRT& l, const ConvGeom& g, const void* dy, const float* bias, void* dx, int act, float alpha) {
   cudaStream_t s = n->ctx->stream; int wp; const void* w = w_ptr(n, l, &wp);
+  if (edge_deconv_small_c_supported(g)) { k_edge_deconv_small_c(n->prec, wp, g, dy, w, bias, dx, act, alpha, s); return 0; }
+  if (dense_small_o_supported(g) && !bias && act == ACT_IDENTITY) { k_dense_small_o_dgrad(n->prec, wp, g, dy, w, dx, s); return 0; }
   if (n->prec == PREC_BF16 && n->ctx->tc_ok && tc_dgrad_supported(g)) {
     if (k_tc_dgrad(g, (const __nv_bfloat16*)dy, n->shadow + l.off_Wt_bf, bias, (__nv_bfloat16*)dx, act, alpha, s) == 0) return 0;
     return fail(B2G_ERR_CUDA, "tcgen05 dgrad launch failed");
@@ -330,6 +340,8 @@ static int32_t gemm_dgrad(b2g_net* n, const LayerRT& l, const ConvGeom& g, const
 }
 static int32_t gemm_wgrad(b2g_net* n, const LayerRT& l, const ConvGeom& g, const void* x, const void* dy, float* dw) {
   cudaStream_t s = n->ctx->stream;
+  if (edge_wgrad_small_cin_supported(g)) { k_edge_wgrad_small_cin(n->prec, g, x, dy, dw, n->scratch, 0, s); return 0; }
+  if (dense_small_o_supported(g)) { k_dense_small_o_wgrad(n->prec, g, x, dy, dw, n->scratch, 0, s); return 0; }
   if (n->prec == PREC_BF16 && n->ctx->tc_ok && tc_wgrad_supported(g)) {
     if (k_tc_wgrad(g, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw, n->scratch, n->scratch_floats, 0, s) == 0) return 0;
     return fail(B2G_ERR_CUDA, "tcgen05 wgrad launch failed");

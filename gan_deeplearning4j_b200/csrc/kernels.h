@@ -100,6 +100,20 @@ void k_simt_dgrad(int prec, int wprec, const ConvGeom& g, const void* dy, const 
 void k_simt_wgrad(int prec, const ConvGeom& g, const void* x, const void* dy, float* dw, float* scratch, size_t scratch_floats, int accumulate, cudaStream_t s);
 size_t k_simt_wgrad_scratch_floats(const ConvGeom& g);
 
+// ---- skinny layers (kernels_edge.cu): <=4 image channels on one side, or <=4 output units ------------------
+bool edge_deconv_small_c_supported(const ConvGeom& g);   // dgrad form, g.C <= 4
+bool edge_conv_small_cin_supported(const ConvGeom& g);   // fprop form, g.C <= 4
+bool edge_wgrad_small_cin_supported(const ConvGeom& g);
+bool dense_small_o_supported(const ConvGeom& g);         // 1x1 geometry, g.O <= 4
+void k_edge_deconv_small_c(int prec, int wprec, const ConvGeom& g, const void* dy, const void* w, const float* bias, void* dx, int act, float alpha, cudaStream_t s);
+void k_edge_conv_small_cin(int prec, int wprec, const ConvGeom& g, const void* x, const void* w, const float* bias, void* out, int act, float alpha, cudaStream_t s);
+void k_edge_wgrad_small_cin(int prec, const ConvGeom& g, const void* x, const void* dy, float* dw, float* scratch, int accumulate, cudaStream_t s);
+size_t k_edge_wgrad_scratch_floats(const ConvGeom& g);
+void k_dense_small_o_fwd(int prec, int wprec, const ConvGeom& g, const void* x, const void* w, const float* bias, void* out, int act, float alpha, cudaStream_t s);
+void k_dense_small_o_dgrad(int prec, int wprec, const ConvGeom& g, const void* dy, const void* w, void* dx, cudaStream_t s);
+void k_dense_small_o_wgrad(int prec, const ConvGeom& g, const void* x, const void* dy, float* dw, float* scratch, int accumulate, cudaStream_t s);
+size_t k_dense_small_o_wgrad_scratch_floats(const ConvGeom& g);
+
 // ---- GEMM-shaped kernels, tcgen05 tensor cores (bf16 in, fp32 accumulate in TMEM) -------------------------
 bool tc_fprop_supported(const ConvGeom& g);
 bool tc_dgrad_supported(const ConvGeom& g);

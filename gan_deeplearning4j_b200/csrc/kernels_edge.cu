@@ -1,0 +1,275 @@
+// kernels_edge.cu -- the "skinny" layers of the DCGAN stack, which are HBM/FMA-bound and not tensor-core shaped
+// (SURVEY.md section 7 "skinny layers": D1 with K=48, G-last with 3 output channels, D-last with one output):
+//
+//   edge_deconv_small_c   Deconvolution2D 4x4 s2 p1 with <=4 output channels (G-last forward; D1's input gradient)
+//   edge_conv_small_cin   ConvolutionLayer 4x4 s2 p1 with <=4 input channels (D1 forward; G-last's input gradient)
+//   edge_wgrad_small_cin  its weight gradient (D1 / G-last), a [O x 48] result reduced over every pixel of the batch
+//   dense_small_o_*       layers with <=4 output units (D-last 4x4 "valid" conv on a 4x4 map = a dot product per image;
+//                         the reference's OutputLayer 1024->1, J:159-163): forward, input gradient, weight gradient
+//
+// All are direct (no GEMM tiles): weights live in shared memory as fp32 and are read as broadcasts, activations are
+// read with 16-byte loads where the layout allows, every output element is written exactly once, reductions are
+// fixed-order (partials + k_reduce_splits), so results are deterministic.
+#include "kernels.h"
+#include "common.cuh"
+
+namespace b2g {
+
+template <typename T> __device__ __forceinline__ void load8(const T* p, float (&v)[8]);
+template <> __device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
+  float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+}
+template <typename TW> __device__ __forceinline__ float ldw(const TW* w, size_t i) { return ldf(w, i); }
+// parameters sit at arbitrary element offsets of the flattened fp32 vector: vector loads only when 16-byte aligned
+template <typename T> __device__ __forceinline__ void load8_any(const T* p, float (&v)[8]) {
+  if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) { load8(p, v); return; }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = ldf(p, j);
+}
+
+// ------------------------------------------------------------------ (a) transposed conv, <=4 output channels ----
+// dx[n, 2q+p] = bias + sum over the 2x2 taps of that parity class (sub-pixel phase form, as in kernels_tc.cu).
+// One thread per dy-grid position (n,qy,qx): reads its 3x3 neighbourhood once, writes the 2x2 output block.
+template <typename T, typename TW>
+__global__ void __launch_bounds__(128) edge_deconv_small_c_kernel(const T* __restrict__ dy, const TW* __restrict__ w, const float* __restrict__ bias, T* __restrict__ dx,
+                                                                   int N, int OH, int OW, int O, int C, int act, float alpha) {
+  extern __shared__ float4 ws4[];      // [16 taps][O] : (c0,c1,c2,c3)
+  for (int i = threadIdx.x; i < 16 * O; i += blockDim.x) {
+    int tap = i / O, o = i % O; float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const size_t base = ((size_t)o * 16 + tap) * C;
+    v.x = ldw(w, base); if (C > 1) v.y = ldw(w, base + 1); if (C > 2) v.z = ldw(w, base + 2); if (C > 3) v.w = ldw(w, base + 3);
+    ws4[i] = v;
+  }
+  __syncthreads();
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)N * OH * OW) return;
+  const int qx = idx % OW; long t = idx / OW; const int qy = t % OH; const int n = (int)(t / OH);
+  float4 acc[2][2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) acc[a][b] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int dyr = -1; dyr <= 1; ++dyr) {
+    const int iy = qy + dyr; if (iy < 0 || iy >= OH) continue;
+#pragma unroll
+    for (int dxc = -1; dxc <= 1; ++dxc) {
+      const int ix = qx + dxc; if (ix < 0 || ix >= OW) continue;
+      const T* src = dy + (((size_t)n * OH + iy) * OW + ix) * O;
+      for (int o8 = 0; o8 < O; o8 += 8) {
+        float v[8]; load8(src + o8, v);
+        // row offset dyr serves: -1 -> (py=0, r=3); 0 -> (py=0, r=1) and (py=1, r=2); +1 -> (py=1, r=0)
+#pragma unroll
+        for (int py = 0; py < 2; ++py) {
+          int r;
+          if (dyr == -1) { if (py != 0) continue; r = 3; } else if (dyr == 0) { r = py == 0 ? 1 : 2; } else { if (py != 1) continue; r = 0; }
+#pragma unroll
+          for (int px = 0; px < 2; ++px) {
+            int s;
+            if (dxc == -1) { if (px != 0) continue; s = 3; } else if (dxc == 0) { s = px == 0 ? 1 : 2; } else { if (px != 1) continue; s = 0; }
+            const float4* wt = ws4 + (r * 4 + s) * O + o8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float4 ww = wt[j]; acc[py][px].x = fmaf(v[j], ww.x, acc[py][px].x); acc[py][px].y = fmaf(v[j], ww.y, acc[py][px].y);
+              acc[py][px].z = fmaf(v[j], ww.z, acc[py][px].z); acc[py][px].w = fmaf(v[j], ww.w, acc[py][px].w); }
+          }
+        }
+      }
+    }
+  }
+  const int H = 2 * OH, W = 2 * OW;
+#pragma unroll
+  for (int py = 0; py < 2; ++py)
+#pragma unroll
+    for (int px = 0; px < 2; ++px) {
+      T* dst = dx + (((size_t)n * H + 2 * qy + py) * W + 2 * qx + px) * C;
+      const float a4[4] = {acc[py][px].x, acc[py][px].y, acc[py][px].z, acc[py][px].w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) if (c < C) stf(dst, c, act_fwd(act, a4[c] + (bias ? bias[c] : 0.f), alpha));
+    }
+}
+
+// ------------------------------------------------------------------ (b) conv 4x4 s2 p1, <=4 input channels ------
+// One thread per (output pixel, group of 16 output channels): 16 accumulators, the 48 inputs come from 4 contiguous
+// 12-element row segments, weights from smem as [k][O] so a warp's reads are broadcasts / conflict-free.
+template <typename T, typename TW>
+__global__ void __launch_bounds__(256) edge_conv_small_cin_kernel(const T* __restrict__ x, const TW* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out,
+                                                                   int N, int H, int W, int C, int OH, int OW, int O, int act, float alpha) {
+  extern __shared__ float wsf[];      // [16*C][O]
+  const int K = 16 * C;
+  for (int i = threadIdx.x; i < K * O; i += blockDim.x) { int k = i / O, o = i % O; wsf[i] = ldw(w, (size_t)o * K + k); }
+  __syncthreads();
+  const int groups = O / 16;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)N * OH * OW * groups) return;
+  const int og = idx % groups; long pix = idx / groups;
+  const int ox = pix % OW; long t = pix / OW; const int oy = t % OH; const int n = (int)(t / OH);
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = bias ? bias[og * 16 + j] : 0.f;
+  for (int r = 0; r < 4; ++r) {
+    const int iy = 2 * oy - 1 + r; if (iy < 0 || iy >= H) continue;
+    for (int s = 0; s < 4; ++s) {
+      const int ix = 2 * ox - 1 + s; if (ix < 0 || ix >= W) continue;
+      const T* src = x + (((size_t)n * H + iy) * W + ix) * C;
+      for (int c = 0; c < C; ++c) {
+        const float v = ldf(src, c);
+        const float4* wr = reinterpret_cast<const float4*>(wsf + ((r * 4 + s) * C + c) * O + og * 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float4 ww = wr[j]; acc[4 * j] = fmaf(v, ww.x, acc[4 * j]); acc[4 * j + 1] = fmaf(v, ww.y, acc[4 * j + 1]);
+          acc[4 * j + 2] = fmaf(v, ww.z, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(v, ww.w, acc[4 * j + 3]); }
+      }
+    }
+  }
+  T* dst = out + (size_t)pix * O + og * 16;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) stf(dst, j, act_fwd(act, acc[j], alpha));
+}
+
+// ------------------------------------------------------------------ (c) its weight gradient ---------------------
+// dw[o][r][s][c] = sum_pix dy[pix][o] * x[pix(r,s)][c].  CTA = 2*O threads: thread -> (pair of o, filter row r); per pixel it reads
+// one dy pair and the 4*C contiguous x values of its filter row from smem and does 2*4*C FMAs.  Each CTA reduces a contiguous pixel range;
+// partials [grid][O*16*C] are summed by k_reduce_splits.
+template <typename T>
+__global__ void edge_wgrad_small_cin_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ part, int N, int H, int W, int C, int OH, int OW, int O, int pix_per_cta) {
+  extern __shared__ float sm[];
+  const int TP = 32;                           // pixels per smem tile
+  float* sdy = sm;                             // [TP][O]
+  float* sx = sm + TP * O;                     // [TP][4 rows][16]  (4*C <= 16 values per row, zero padded)
+  const int o2 = threadIdx.x % (O / 2), r = threadIdx.x / (O / 2);
+  const long P = (long)N * OH * OW;
+  const long p_beg = (long)blockIdx.x * pix_per_cta, p_end = min(P, p_beg + pix_per_cta);
+  float acc0[16], acc1[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+  for (long p0 = p_beg; p0 < p_end; p0 += TP) {
+    const int np = (int)min((long)TP, p_end - p0);
+    for (int i = threadIdx.x; i < TP * O; i += blockDim.x) { int pp = i / O, o = i % O; sdy[i] = pp < np ? ldf(dy, (size_t)(p0 + pp) * O + o) : 0.f; }
+    for (int i = threadIdx.x; i < TP * 64; i += blockDim.x) {
+      int pp = i / 64, rr = (i % 64) / 16, e = i % 16; float v = 0.f;
+      if (pp < np && e < 4 * C) {
+        long pix = p0 + pp; int ox = pix % OW; long t = pix / OW; int oy = t % OH; int n = (int)(t / OH);
+        int s = e / C, c = e % C, iy = 2 * oy - 1 + rr, ix = 2 * ox - 1 + s;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = ldf(x, (((size_t)n * H + iy) * W + ix) * C + c);
+      }
+      sx[i] = v;
+    }
+    __syncthreads();
+    for (int pp = 0; pp < np; ++pp) {
+      const float d0 = sdy[pp * O + 2 * o2], d1 = sdy[pp * O + 2 * o2 + 1];
+      const float4* xr = reinterpret_cast<const float4*>(sx + pp * 64 + r * 16);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float4 xv = xr[j];
+        acc0[4 * j] = fmaf(d0, xv.x, acc0[4 * j]); acc0[4 * j + 1] = fmaf(d0, xv.y, acc0[4 * j + 1]); acc0[4 * j + 2] = fmaf(d0, xv.z, acc0[4 * j + 2]); acc0[4 * j + 3] = fmaf(d0, xv.w, acc0[4 * j + 3]);
+        acc1[4 * j] = fmaf(d1, xv.x, acc1[4 * j]); acc1[4 * j + 1] = fmaf(d1, xv.y, acc1[4 * j + 1]); acc1[4 * j + 2] = fmaf(d1, xv.z, acc1[4 * j + 2]); acc1[4 * j + 3] = fmaf(d1, xv.w, acc1[4 * j + 3]); }
+    }
+    __syncthreads();
+  }
+  float* dst = part + (size_t)blockIdx.x * O * 16 * C;
+#pragma unroll
+  for (int e = 0; e < 16; ++e) if (e < 4 * C) {       // dw[o][r][s][c], e = s*C + c
+    dst[((size_t)(2 * o2) * 4 + r) * 4 * C + e] = acc0[e];
+    dst[((size_t)(2 * o2 + 1) * 4 + r) * 4 * C + e] = acc1[e];
+  }
+}
+
+// ------------------------------------------------------------------ (d) layers with <=4 output units -------------
+template <typename T, typename TW>
+__global__ void __launch_bounds__(128) dense_small_o_fwd_kernel(const T* __restrict__ x, const TW* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out, int K, int O, int act, float alpha) {
+  const int n = blockIdx.x; __shared__ float red[4][4];
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const T* xr = x + (size_t)n * K;
+  for (int k = threadIdx.x * 8; k < K; k += blockDim.x * 8) {
+    float v[8]; load8(xr + k, v);
+    for (int o = 0; o < O; ++o) { float wv[8]; load8_any(w + (size_t)o * K + k, wv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[o] = fmaf(v[j], wv[j], acc[o]); }
+  }
+  for (int o = 0; o < O; ++o) { float a = acc[o]; for (int m = 16; m; m >>= 1) a += __shfl_xor_sync(0xffffffffu, a, m); if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][o] = a; }
+  __syncthreads();
+  if (threadIdx.x < O) { float a = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x]; stf(out, (size_t)n * O + threadIdx.x, act_fwd(act, a + (bias ? bias[threadIdx.x] : 0.f), alpha)); }
+}
+template <typename T, typename TW>
+__global__ void dense_small_o_dgrad_kernel(const T* __restrict__ dy, const TW* __restrict__ w, T* __restrict__ dx, int N, int K, int O) {
+  const size_t total = (size_t)N * K;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = i % K; const size_t n = i / K; float a = 0.f;
+    for (int o = 0; o < O; ++o) a = fmaf(ldf(dy, n * O + o), ldw(w, (size_t)o * K + k), a);
+    stf(dx, i, a);
+  }
+}
+template <typename T>
+__global__ void dense_small_o_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ part, int N, int K, int O, int rows_per_split) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x; if (k >= K) return;
+  const int n0 = blockIdx.y * rows_per_split, n1 = min(N, n0 + rows_per_split);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int n = n0; n < n1; ++n) { const float v = ldf(x, (size_t)n * K + k); for (int o = 0; o < O; ++o) acc[o] = fmaf(ldf(dy, (size_t)n * O + o), v, acc[o]); }
+  for (int o = 0; o < O; ++o) part[(size_t)blockIdx.y * O * K + (size_t)o * K + k] = acc[o];
+}
+
+// ------------------------------------------------------------------ host wrappers ---------------------------------
+static bool is_k4s2p1(const ConvGeom& g) { return g.KH == 4 && g.KW == 4 && g.SH == 2 && g.SW == 2 && g.PH == 1 && g.PW == 1 && g.H == 2 * g.OH && g.W == 2 * g.OW; }
+bool edge_deconv_small_c_supported(const ConvGeom& g) { return is_k4s2p1(g) && g.C <= 4 && g.O % 8 == 0 && g.O <= 128; }
+bool edge_conv_small_cin_supported(const ConvGeom& g) { return is_k4s2p1(g) && g.C <= 4 && g.O % 16 == 0 && 16 * g.C * g.O * 4 <= 48 * 1024; }
+bool edge_wgrad_small_cin_supported(const ConvGeom& g) { return is_k4s2p1(g) && g.C <= 4 && g.O % 2 == 0 && g.O <= 256; }
+bool dense_small_o_supported(const ConvGeom& g) { return g.KH == 1 && g.KW == 1 && g.H == 1 && g.W == 1 && g.O <= 4 && g.C % 8 == 0; }
+
+template <typename T, typename TW>
+static void launch_deconv_small_c(const ConvGeom& g, const void* dy, const void* w, const float* bias, void* dx, int act, float alpha, cudaStream_t s) {
+  long tot = (long)g.N * g.OH * g.OW;
+  edge_deconv_small_c_kernel<T, TW><<<(unsigned)((tot + 127) / 128), 128, 16 * g.O * sizeof(float4), s>>>((const T*)dy, (const TW*)w, bias, (T*)dx, g.N, g.OH, g.OW, g.O, g.C, act, alpha);
+}
+void k_edge_deconv_small_c(int prec, int wprec, const ConvGeom& g, const void* dy, const void* w, const float* bias, void* dx, int act, float alpha, cudaStream_t s) {
+  if (prec == PREC_F32) launch_deconv_small_c<float, float>(g, dy, w, bias, dx, act, alpha, s);
+  else if (wprec == PREC_F32) launch_deconv_small_c<__nv_bfloat16, float>(g, dy, w, bias, dx, act, alpha, s);
+  else launch_deconv_small_c<__nv_bfloat16, __nv_bfloat16>(g, dy, w, bias, dx, act, alpha, s);
+  LAUNCHED();
+}
+template <typename T, typename TW>
+static void launch_conv_small_cin(const ConvGeom& g, const void* x, const void* w, const float* bias, void* out, int act, float alpha, cudaStream_t s) {
+  long tot = (long)g.N * g.OH * g.OW * (g.O / 16);
+  edge_conv_small_cin_kernel<T, TW><<<(unsigned)((tot + 255) / 256), 256, 16 * g.C * g.O * sizeof(float), s>>>((const T*)x, (const TW*)w, bias, (T*)out, g.N, g.H, g.W, g.C, g.OH, g.OW, g.O, act, alpha);
+}
+void k_edge_conv_small_cin(int prec, int wprec, const ConvGeom& g, const void* x, const void* w, const float* bias, void* out, int act, float alpha, cudaStream_t s) {
+  if (prec == PREC_F32) launch_conv_small_cin<float, float>(g, x, w, bias, out, act, alpha, s);
+  else if (wprec == PREC_F32) launch_conv_small_cin<__nv_bfloat16, float>(g, x, w, bias, out, act, alpha, s);
+  else launch_conv_small_cin<__nv_bfloat16, __nv_bfloat16>(g, x, w, bias, out, act, alpha, s);
+  LAUNCHED();
+}
+static int edge_wgrad_ctas(const ConvGeom& g) { long P = (long)g.N * g.OH * g.OW; long c = 148 * 4; long cap = (P + 63) / 64; if (c > cap) c = cap; if (c < 1) c = 1; return (int)c; }
+size_t k_edge_wgrad_scratch_floats(const ConvGeom& g) { return edge_wgrad_small_cin_supported(g) ? (size_t)edge_wgrad_ctas(g) * g.O * 16 * g.C : 0; }
+void k_edge_wgrad_small_cin(int prec, const ConvGeom& g, const void* x, const void* dy, float* dw, float* scratch, int accumulate, cudaStream_t s) {
+  const int ctas = edge_wgrad_ctas(g); const long P = (long)g.N * g.OH * g.OW; const int ppc = (int)((P + ctas - 1) / ctas);
+  const size_t n = (size_t)g.O * 16 * g.C; const size_t smem = (32 * g.O + 32 * 64) * sizeof(float);
+  DISPATCH_PREC(prec, T, (edge_wgrad_small_cin_kernel<T><<<ctas, 2 * g.O, smem, s>>>((const T*)x, (const T*)dy, scratch, g.N, g.H, g.W, g.C, g.OH, g.OW, g.O, ppc))); LAUNCHED();
+  k_reduce_splits(scratch, dw, n, ctas, n, accumulate, s);
+}
+void k_dense_small_o_fwd(int prec, int wprec, const ConvGeom& g, const void* x, const void* w, const float* bias, void* out, int act, float alpha, cudaStream_t s) {
+  if (prec == PREC_F32) dense_small_o_fwd_kernel<float, float><<<g.N, 128, 0, s>>>((const float*)x, (const float*)w, bias, (float*)out, g.C, g.O, act, alpha);
+  else if (wprec == PREC_F32) dense_small_o_fwd_kernel<__nv_bfloat16, float><<<g.N, 128, 0, s>>>((const __nv_bfloat16*)x, (const float*)w, bias, (__nv_bfloat16*)out, g.C, g.O, act, alpha);
+  else dense_small_o_fwd_kernel<__nv_bfloat16, __nv_bfloat16><<<g.N, 128, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)out, g.C, g.O, act, alpha);
+  LAUNCHED();
+}
+void k_dense_small_o_dgrad(int prec, int wprec, const ConvGeom& g, const void* dy, const void* w, void* dx, cudaStream_t s) {
+  size_t tot = (size_t)g.N * g.C; int blocks = (int)((tot + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+  if (prec == PREC_F32) dense_small_o_dgrad_kernel<float, float><<<blocks, 256, 0, s>>>((const float*)dy, (const float*)w, (float*)dx, g.N, g.C, g.O);
+  else if (wprec == PREC_F32) dense_small_o_dgrad_kernel<__nv_bfloat16, float><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)dy, (const float*)w, (__nv_bfloat16*)dx, g.N, g.C, g.O);
+  else dense_small_o_dgrad_kernel<__nv_bfloat16, __nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)w, (__nv_bfloat16*)dx, g.N, g.C, g.O);
+  LAUNCHED();
+}
+static int dense_wgrad_splits(const ConvGeom& g) { int sp = (g.N + 31) / 32; if (sp > 16) sp = 16; if (sp < 1) sp = 1; return sp; }
+size_t k_dense_small_o_wgrad_scratch_floats(const ConvGeom& g) { return dense_small_o_supported(g) ? (size_t)dense_wgrad_splits(g) * g.O * g.C : 0; }
+void k_dense_small_o_wgrad(int prec, const ConvGeom& g, const void* x, const void* dy, float* dw, float* scratch, int accumulate, cudaStream_t s) {
+  const int sp = dense_wgrad_splits(g), rps = (g.N + sp - 1) / sp; const size_t n = (size_t)g.O * g.C;
+  dim3 grid((g.C + 127) / 128, sp);
+  DISPATCH_PREC(prec, T, (dense_small_o_wgrad_kernel<T><<<grid, 128, 0, s>>>((const T*)x, (const T*)dy, scratch, g.N, g.C, g.O, rps))); LAUNCHED();
+  k_reduce_splits(scratch, dw, n, sp, n, accumulate, s);
+}
+
+}  // namespace b2g

@@ -363,3 +363,55 @@ def test_tc_wgrad_mn_major_matches_oracle(b200, case):
     geom = dict(n=n, h=h, w=w, c=c, oh=h // 2, ow=w // 2, o=oc, kh=4, kw=4, sh=2, sw=2, ph=1, pw=1)
     out, _ = b.test_conv(ctx, 2, 1, b.BF16, geom, x.transpose(0, 2, 3, 1), dy.transpose(0, 2, 3, 1), dw.size)
     assert rel_err(out.reshape(oc, 4, 4, c), dw.transpose(0, 2, 3, 1)) < 1e-4     # fp32 accumulate, fp32 out: only summation order differs
+
+
+# ------------------------------------------------------------------------------------------------
+# skinny-layer kernels (kernels_edge.cu) are reached through the engine: layer-level parity in both precisions
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_edge_layers_dcgan_ends(b200, prec):
+    """D1 (3->64 conv), G-last (64->3 transposed conv + tanh), D-last (full-window conv -> 1 logit), G-first (z -> 4x4)
+    at a size where every specialised kernel engages; fp32 vs oracle to TOL, bf16 vs oracle loosely."""
+    b, ctx = b200
+    from gan_deeplearning4j_b200 import models as m
+    P = b.BF16 if prec == "bf16" else b.FP32
+    tol = 4e-2 if prec == "bf16" else TOL
+    size, z, nf, n = 32, 16, 64, 8          # G: z->(4x4x256)->8x8x128->16x16x64->32x32x3 ; D: 32->16x16x64->8x8x128->4x4x256->1
+    gs, ds = m.dcgan_generator(size, z, nf, 3, lr=1e-3), m.dcgan_discriminator(size, nf, 3, lr=1e-3)
+    q = o.Quirks(xent_clip_eps=0.0)
+    rng = np.random.default_rng(11)
+    G = oracle_from_specs(gs, (z,), quirks=q, seed=1); D = oracle_from_specs(ds, (3, size, size), quirks=q, seed=2)
+    randomize(G, rng); randomize(D, rng)
+    bG = b.Net(ctx, gs, (z,), max_batch=n, precision=P, xent_clip_eps=0.0)
+    bD = b.Net(ctx, ds, (3, size, size), max_batch=2 * n, precision=P, xent_clip_eps=0.0, bn_groups=2)
+    push_params(G, bG); push_params(D, bD)
+    x, z_d, z_g, y_r, y_f, y_g = [a.astype(np.float64) for a in o.synthetic_batch(n, size, 3, z, seed=5)]
+    # forward of both nets (train mode)
+    xg_o = G.forward(z_g, True); xg_b = bG.output(z_g, train=True)
+    assert rel_err(xg_b, xg_o.reshape(n, -1)) < tol
+    # D gradients on the real batch (exercises D1 fprop/wgrad, D-last fwd/dgrad/wgrad)
+    s_o = D.compute_gradient_and_score(x, y_r); s_b = bD.compute_gradient_and_score(x, y_r)
+    assert abs(s_b - s_o) < tol * max(1.0, abs(s_o))
+    g_b, g_o = bD.gradients(), D.grads_flat(); off = 0
+    for li, name, p, shape, _ in D.param_table():
+        k = int(np.prod(shape))
+        if p not in ("mean", "var"):
+            assert rel_err(g_b[off:off + k], g_o[off:off + k]) < (tol if prec == "fp32" else 0.1), (name, p)
+        off += k
+    # full step: exercises G-last forward/wgrad/input-grad, D1 input-grad, G-first forward/wgrad
+    gan = b.Gan(bG, bD, use_cuda_graph=False)
+    r = o.gan_step(G, D, x, z_d, z_g, y_r, y_f, y_g)
+    losses = gan.step(x, z_d, z_g, y_r, y_f, y_g)
+    want = np.array([r["loss_d_real"], r["loss_d_fake"], r["loss_g"]])
+    assert np.all(np.abs(losses - want) < (tol if prec == "fp32" else 0.1) * np.maximum(1.0, np.abs(want))), (losses, want)
+    if prec == "fp32":
+        for onet, bnet in ((D, bD), (G, bG)):
+            p_b, p_o = bnet.params(), onet.params_flat(); off = 0
+            for li, name, p, shape, _ in onet.param_table():
+                k = int(np.prod(shape))
+                if p in ("mean", "var"):
+                    assert rel_err(p_b[off:off + k], p_o[off:off + k]) < 2 * TOL, (name, p)
+                else:     # Adam's first step is lr*g/(|g|+eps'): elements with a numerically-zero gradient may land one step apart
+                    _assert_close_up_to_sign_flips(p_b[off:off + k], p_o[off:off + k], lr=1e-3)
+                off += k
+    gan.close(); bG.close(); bD.close()
