@@ -81,6 +81,7 @@ struct LayerRT {
   float* bn_mean = nullptr; float* bn_invstd = nullptr;
   int fused_act = ACT_IDENTITY; float fused_alpha = 0.f;       // BN followed by an ActivationLayer
   bool act_fused_into_prev = false;
+  bool needs_wt = false;                                       // a tcgen05 dgrad kernel reads the transposed bf16 copy
   bool has_gemm() const { return d.type == B2G_LAYER_CONV2D || d.type == B2G_LAYER_DECONV2D || d.type == B2G_LAYER_DENSE || d.type == B2G_LAYER_OUTPUT; }
 };
 
@@ -240,6 +241,7 @@ static int32_t net_alloc(b2g_net* n) {
       scratch = std::max(scratch, std::max(k_edge_wgrad_scratch_floats(g), k_dense_small_o_wgrad_scratch_floats(g)));
       scratch = std::max(scratch, k_colsum_scratch_floats(std::max(l.oc, l.ic)));
       max_w = std::max(max_w, (size_t)l.n_W);
+      l.needs_wt = n->prec == PREC_BF16 && n->ctx->tc_ok && tc_dgrad_supported(g) && !edge_deconv_small_c_supported(g);
     }
   }
   n->eps_elems = (size_t)R * max_act;
@@ -261,7 +263,7 @@ static int32_t net_init_params_and_updater(b2g_net* n) {
     auto add_seg = [&](int64_t off, int64_t len, bool weight, bool noop) {
       UpdSeg sg{}; sg.off = off; sg.len = len; sg.kind = noop ? 3 : updater_kind(d.updater);
       sg.lr = d.lr; sg.b1 = d.beta1; sg.b2 = d.beta2; sg.eps = d.eps; sg.l2 = weight ? d.l2 : 0.f; sg.clip = n->cfg.grad_clip; sg.div_mb = noop ? 0 : 1;
-      sg.off_bf = -1; sg.off_bft = -1; n->segs.push_back(sg);
+      sg.off_bf = (weight && l.off_W_bf >= 0) ? l.off_W_bf : -1; sg.off_bft = -1; n->segs.push_back(sg);
       if (!noop && sg.kind == 1) for (int64_t i = 0; i < len; ++i) h0[off + i] = d.eps;     // RmsPropUpdater cache initialised to epsilon
       if (weight && d.l2 != 0.f) { l2o.push_back(off); l2l.push_back(len); l2c.push_back(0.5f * d.l2); }
     };
@@ -301,12 +303,14 @@ static int32_t net_init_params_and_updater(b2g_net* n) {
   return 0;
 }
 
-// bf16 operand copies of every GEMM weight (straight + transposed); no-op in FP32 mode
-static void net_refresh_shadow(b2g_net* n, int only_layer = -1) {
+// bf16 operand copies of every GEMM weight (straight, and transposed where a tcgen05 dgrad reads it); no-op in FP32 mode.
+// After an updater pass the straight copy has already been written by the updater kernel itself.
+static void net_refresh_shadow(b2g_net* n, int only_layer = -1, bool straight_done = false) {
   if (n->prec != PREC_BF16) return;
   for (size_t i = 0; i < n->L.size(); ++i) { auto& l = n->L[i];
     if (!l.has_gemm() || (only_layer >= 0 && (int)i != only_layer)) continue;
-    k_weight_shadow(n->params + l.off_W, n->shadow + l.off_W_bf, n->shadow + l.off_Wt_bf, l.wA, l.wTaps, l.wB, n->ctx->stream);
+    if (straight_done && !l.needs_wt) continue;
+    k_weight_shadow(n->params + l.off_W, straight_done ? nullptr : n->shadow + l.off_W_bf, l.needs_wt ? n->shadow + l.off_Wt_bf : nullptr, l.wA, l.wTaps, l.wB, n->ctx->stream);
   }
 }
 
@@ -332,7 +336,7 @@ static int32_t gemm_dgrad(b2g_net* n, const LayerRT& l, const ConvGeom& g, const
   cudaStream_t s = n->ctx->stream; int wp; const void* w = w_ptr(n, l, &wp);
   if (edge_deconv_small_c_supported(g)) { k_edge_deconv_small_c(n->prec, wp, g, dy, w, bias, dx, act, alpha, s); return 0; }
   if (dense_small_o_supported(g) && !bias && act == ACT_IDENTITY) { k_dense_small_o_dgrad(n->prec, wp, g, dy, w, dx, s); return 0; }
-  if (n->prec == PREC_BF16 && n->ctx->tc_ok && tc_dgrad_supported(g)) {
+  if (n->prec == PREC_BF16 && n->ctx->tc_ok && l.needs_wt && tc_dgrad_supported(g)) {
     if (k_tc_dgrad(g, (const __nv_bfloat16*)dy, n->shadow + l.off_Wt_bf, bias, (__nv_bfloat16*)dx, act, alpha, s) == 0) return 0;
     return fail(B2G_ERR_CUDA, "tcgen05 dgrad launch failed");
   }
@@ -445,9 +449,9 @@ static int32_t net_allreduce_grads(b2g_net* n) {
 static int32_t net_update(b2g_net* n, int mb_local) {
   cudaStream_t s = n->ctx->stream; int W = n->ctx->comm ? n->ctx->world : 1;
   // BN running-stat pseudo-gradients are exempt from the minibatch division; under DP they are averaged over ranks
-  k_updater(n->params, n->grads, n->st0, n->st1, n->segs_dev, n->chunk_seg_dev, n->chunk_off_dev, n->nchunks, 1.0f / ((float)mb_local * W), 1.0f / (float)W, n->step_dev, nullptr, s);
+  k_updater(n->params, n->grads, n->st0, n->st1, n->segs_dev, n->chunk_seg_dev, n->chunk_off_dev, n->nchunks, 1.0f / ((float)mb_local * W), 1.0f / (float)W, n->step_dev, n->shadow, s);
   k_inc_int(n->step_dev, s);
-  net_refresh_shadow(n);
+  net_refresh_shadow(n, -1, true);
   CHECK_KERNELS();
   return 0;
 }

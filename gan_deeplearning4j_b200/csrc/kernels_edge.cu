@@ -48,8 +48,7 @@ __global__ void __launch_bounds__(128) edge_deconv_small_c_kernel(const T* __res
     ws4[i] = v;
   }
   __syncthreads();
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long)N * OH * OW) return;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < (long)N * OH * OW; idx += (long)gridDim.x * blockDim.x) {
   const int qx = idx % OW; long t = idx / OW; const int qy = t % OH; const int n = (int)(t / OH);
   float4 acc[2][2];
 #pragma unroll
@@ -93,43 +92,65 @@ __global__ void __launch_bounds__(128) edge_deconv_small_c_kernel(const T* __res
 #pragma unroll
       for (int c = 0; c < 4; ++c) if (c < C) stf(dst, c, act_fwd(act, a4[c] + (bias ? bias[c] : 0.f), alpha));
     }
+  }
 }
 
+__device__ __forceinline__ void store16(float* dst, const float (&a)[16]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(dst)[j] = make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
+}
+__device__ __forceinline__ void store16(__nv_bfloat16* dst, const float (&a)[16]) {
+  uint32_t pk[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { __nv_bfloat162 h = __floats2bfloat162_rn(a[2 * j], a[2 * j + 1]); pk[j] = *reinterpret_cast<uint32_t*>(&h); }
+  reinterpret_cast<uint4*>(dst)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]); reinterpret_cast<uint4*>(dst)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+}
 // ------------------------------------------------------------------ (b) conv 4x4 s2 p1, <=4 input channels ------
 // One thread per (output pixel, group of 16 output channels): 16 accumulators, the 48 inputs come from 4 contiguous
 // 12-element row segments, weights from smem as [k][O] so a warp's reads are broadcasts / conflict-free.
 template <typename T, typename TW>
-__global__ void __launch_bounds__(256) edge_conv_small_cin_kernel(const T* __restrict__ x, const TW* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out,
+__global__ void __launch_bounds__(128) edge_conv_small_cin_kernel(const T* __restrict__ x, const TW* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out,
                                                                    int N, int H, int W, int C, int OH, int OW, int O, int act, float alpha) {
   extern __shared__ float wsf[];      // [16*C][O]
   const int K = 16 * C;
-  for (int i = threadIdx.x; i < K * O; i += blockDim.x) { int k = i / O, o = i % O; wsf[i] = ldw(w, (size_t)o * K + k); }
+  for (int i = threadIdx.x; i < K * O; i += blockDim.x) { int o = i / K, k = i % K; wsf[k * O + o] = ldw(w, (size_t)i); }   // coalesced global read
   __syncthreads();
-  const int groups = O / 16;
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long)N * OH * OW * groups) return;
-  const int og = idx % groups; long pix = idx / groups;
-  const int ox = pix % OW; long t = pix / OW; const int oy = t % OH; const int n = (int)(t / OH);
-  float acc[16];
+  // work item = (4 adjacent output pixels of one row, 16 output channels): every weight vector fetched from smem feeds 4 pixels
+  const int groups = O / 16, OW4 = OW / 4;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < (long)N * OH * OW4 * groups; idx += (long)gridDim.x * blockDim.x) {
+    const int og = idx % groups; long q = idx / groups;
+    const int ox0 = (int)(q % OW4) * 4; long t = q / OW4; const int oy = t % OH; const int n = (int)(t / OH);
+    float acc[4][16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j] = bias ? bias[og * 16 + j] : 0.f;
-  for (int r = 0; r < 4; ++r) {
-    const int iy = 2 * oy - 1 + r; if (iy < 0 || iy >= H) continue;
-    for (int s = 0; s < 4; ++s) {
-      const int ix = 2 * ox - 1 + s; if (ix < 0 || ix >= W) continue;
-      const T* src = x + (((size_t)n * H + iy) * W + ix) * C;
-      for (int c = 0; c < C; ++c) {
-        const float v = ldf(src, c);
-        const float4* wr = reinterpret_cast<const float4*>(wsf + ((r * 4 + s) * C + c) * O + og * 16);
+    for (int p = 0; p < 4; ++p)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { const float4 ww = wr[j]; acc[4 * j] = fmaf(v, ww.x, acc[4 * j]); acc[4 * j + 1] = fmaf(v, ww.y, acc[4 * j + 1]);
-          acc[4 * j + 2] = fmaf(v, ww.z, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(v, ww.w, acc[4 * j + 3]); }
+      for (int j = 0; j < 16; ++j) acc[p][j] = bias ? bias[og * 16 + j] : 0.f;
+    for (int r = 0; r < 4; ++r) {
+      const int iy = 2 * oy - 1 + r; if (iy < 0 || iy >= H) continue;
+      const T* row = x + ((size_t)n * H + iy) * W * C;
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        for (int c = 0; c < C; ++c) {
+          float v[4];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) { const int ix = 2 * (ox0 + p) - 1 + s; v[p] = (ix >= 0 && ix < W) ? ldf(row, (size_t)ix * C + c) : 0.f; }
+          const float4* wr = reinterpret_cast<const float4*>(wsf + ((r * 4 + s) * C + c) * O + og * 16);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { const float4 ww = wr[j];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) { acc[p][4 * j] = fmaf(v[p], ww.x, acc[p][4 * j]); acc[p][4 * j + 1] = fmaf(v[p], ww.y, acc[p][4 * j + 1]);
+              acc[p][4 * j + 2] = fmaf(v[p], ww.z, acc[p][4 * j + 2]); acc[p][4 * j + 3] = fmaf(v[p], ww.w, acc[p][4 * j + 3]); } }
+        }
       }
     }
-  }
-  T* dst = out + (size_t)pix * O + og * 16;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) stf(dst, j, act_fwd(act, acc[j], alpha));
+    for (int p = 0; p < 4; ++p) {
+      T* dst = out + ((((size_t)n * OH + oy) * OW + ox0 + p)) * O + og * 16;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[p][j] = act_fwd(act, acc[p][j], alpha);
+      store16(dst, acc[p]);
+    }
+  }
 }
 
 // ------------------------------------------------------------------ (c) its weight gradient ---------------------
@@ -139,7 +160,7 @@ __global__ void __launch_bounds__(256) edge_conv_small_cin_kernel(const T* __res
 template <typename T>
 __global__ void edge_wgrad_small_cin_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ part, int N, int H, int W, int C, int OH, int OW, int O, int pix_per_cta) {
   extern __shared__ float sm[];
-  const int TP = 32;                           // pixels per smem tile
+  const int TP = 64;                           // pixels per smem tile
   float* sdy = sm;                             // [TP][O]
   float* sx = sm + TP * O;                     // [TP][4 rows][16]  (4*C <= 16 values per row, zero padded)
   const int o2 = threadIdx.x % (O / 2), r = threadIdx.x / (O / 2);
@@ -150,24 +171,38 @@ __global__ void edge_wgrad_small_cin_kernel(const T* __restrict__ x, const T* __
   for (int j = 0; j < 16; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
   for (long p0 = p_beg; p0 < p_end; p0 += TP) {
     const int np = (int)min((long)TP, p_end - p0);
-    for (int i = threadIdx.x; i < TP * O; i += blockDim.x) { int pp = i / O, o = i % O; sdy[i] = pp < np ? ldf(dy, (size_t)(p0 + pp) * O + o) : 0.f; }
-    for (int i = threadIdx.x; i < TP * 64; i += blockDim.x) {
-      int pp = i / 64, rr = (i % 64) / 16, e = i % 16; float v = 0.f;
-      if (pp < np && e < 4 * C) {
-        long pix = p0 + pp; int ox = pix % OW; long t = pix / OW; int oy = t % OH; int n = (int)(t / OH);
-        int s = e / C, c = e % C, iy = 2 * oy - 1 + rr, ix = 2 * ox - 1 + s;
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = ldf(x, (((size_t)n * H + iy) * W + ix) * C + c);
+    // dy tile: 16-byte (bf16) / 32-byte (fp32) loads, 8 channels at a time
+    for (int i = threadIdx.x; i < TP * (O / 8); i += blockDim.x) {
+      const int pp = i / (O / 8), o8 = (i % (O / 8)) * 8; float v[8];
+      if (pp < np) load8(dy + (size_t)(p0 + pp) * O + o8, v); else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f; }
+      *reinterpret_cast<float4*>(sdy + pp * O + o8) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(sdy + pp * O + o8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    // x rows: one (pixel, filter row) pair per work item; its 4 taps x C channels are contiguous in memory
+    for (int i = threadIdx.x; i < TP * 4; i += blockDim.x) {
+      const int pp = i >> 2, rr = i & 3; float* dstx = sx + pp * 64 + rr * 16;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) dstx[e] = 0.f;
+      if (pp < np) {
+        const long pix = p0 + pp; const int ox = pix % OW; const long t = pix / OW; const int oy = t % OH; const int n = (int)(t / OH);
+        const int iy = 2 * oy - 1 + rr;
+        if (iy >= 0 && iy < H) {
+          const T* row = x + ((size_t)n * H + iy) * W * C;
+          for (int sx_ = 0; sx_ < 4; ++sx_) { const int ix = 2 * ox - 1 + sx_; if (ix < 0 || ix >= W) continue;
+            for (int c = 0; c < C; ++c) dstx[sx_ * C + c] = ldf(row, (size_t)ix * C + c); }
+        }
       }
-      sx[i] = v;
     }
     __syncthreads();
     for (int pp = 0; pp < np; ++pp) {
-      const float d0 = sdy[pp * O + 2 * o2], d1 = sdy[pp * O + 2 * o2 + 1];
+      const float2 d = *reinterpret_cast<const float2*>(sdy + pp * O + 2 * o2);
       const float4* xr = reinterpret_cast<const float4*>(sx + pp * 64 + r * 16);
 #pragma unroll
       for (int j = 0; j < 4; ++j) { const float4 xv = xr[j];
-        acc0[4 * j] = fmaf(d0, xv.x, acc0[4 * j]); acc0[4 * j + 1] = fmaf(d0, xv.y, acc0[4 * j + 1]); acc0[4 * j + 2] = fmaf(d0, xv.z, acc0[4 * j + 2]); acc0[4 * j + 3] = fmaf(d0, xv.w, acc0[4 * j + 3]);
-        acc1[4 * j] = fmaf(d1, xv.x, acc1[4 * j]); acc1[4 * j + 1] = fmaf(d1, xv.y, acc1[4 * j + 1]); acc1[4 * j + 2] = fmaf(d1, xv.z, acc1[4 * j + 2]); acc1[4 * j + 3] = fmaf(d1, xv.w, acc1[4 * j + 3]); }
+        acc0[4 * j] = fmaf(d.x, xv.x, acc0[4 * j]); acc0[4 * j + 1] = fmaf(d.x, xv.y, acc0[4 * j + 1]); acc0[4 * j + 2] = fmaf(d.x, xv.z, acc0[4 * j + 2]); acc0[4 * j + 3] = fmaf(d.x, xv.w, acc0[4 * j + 3]);
+        acc1[4 * j] = fmaf(d.y, xv.x, acc1[4 * j]); acc1[4 * j + 1] = fmaf(d.y, xv.y, acc1[4 * j + 1]); acc1[4 * j + 2] = fmaf(d.y, xv.z, acc1[4 * j + 2]); acc1[4 * j + 3] = fmaf(d.y, xv.w, acc1[4 * j + 3]); }
     }
     __syncthreads();
   }
@@ -216,14 +251,14 @@ __global__ void dense_small_o_wgrad_kernel(const T* __restrict__ x, const T* __r
 // ------------------------------------------------------------------ host wrappers ---------------------------------
 static bool is_k4s2p1(const ConvGeom& g) { return g.KH == 4 && g.KW == 4 && g.SH == 2 && g.SW == 2 && g.PH == 1 && g.PW == 1 && g.H == 2 * g.OH && g.W == 2 * g.OW; }
 bool edge_deconv_small_c_supported(const ConvGeom& g) { return is_k4s2p1(g) && g.C <= 4 && g.O % 8 == 0 && g.O <= 128; }
-bool edge_conv_small_cin_supported(const ConvGeom& g) { return is_k4s2p1(g) && g.C <= 4 && g.O % 16 == 0 && 16 * g.C * g.O * 4 <= 48 * 1024; }
-bool edge_wgrad_small_cin_supported(const ConvGeom& g) { return is_k4s2p1(g) && g.C <= 4 && g.O % 2 == 0 && g.O <= 256; }
+bool edge_conv_small_cin_supported(const ConvGeom& g) { return is_k4s2p1(g) && g.C <= 4 && g.O % 16 == 0 && g.OW % 4 == 0 && 16 * g.C * g.O * 4 <= 48 * 1024; }
+bool edge_wgrad_small_cin_supported(const ConvGeom& g) { return is_k4s2p1(g) && g.C <= 4 && g.O % 8 == 0 && g.O <= 256; }
 bool dense_small_o_supported(const ConvGeom& g) { return g.KH == 1 && g.KW == 1 && g.H == 1 && g.W == 1 && g.O <= 4 && g.C % 8 == 0; }
 
 template <typename T, typename TW>
 static void launch_deconv_small_c(const ConvGeom& g, const void* dy, const void* w, const float* bias, void* dx, int act, float alpha, cudaStream_t s) {
-  long tot = (long)g.N * g.OH * g.OW;
-  edge_deconv_small_c_kernel<T, TW><<<(unsigned)((tot + 127) / 128), 128, 16 * g.O * sizeof(float4), s>>>((const T*)dy, (const TW*)w, bias, (T*)dx, g.N, g.OH, g.OW, g.O, g.C, act, alpha);
+  long tot = (long)g.N * g.OH * g.OW; long blocks = (tot + 127) / 128; if (blocks > 148 * 8) blocks = 148 * 8;
+  edge_deconv_small_c_kernel<T, TW><<<(unsigned)blocks, 128, 16 * g.O * sizeof(float4), s>>>((const T*)dy, (const TW*)w, bias, (T*)dx, g.N, g.OH, g.OW, g.O, g.C, act, alpha);
 }
 void k_edge_deconv_small_c(int prec, int wprec, const ConvGeom& g, const void* dy, const void* w, const float* bias, void* dx, int act, float alpha, cudaStream_t s) {
   if (prec == PREC_F32) launch_deconv_small_c<float, float>(g, dy, w, bias, dx, act, alpha, s);
@@ -233,8 +268,8 @@ void k_edge_deconv_small_c(int prec, int wprec, const ConvGeom& g, const void* d
 }
 template <typename T, typename TW>
 static void launch_conv_small_cin(const ConvGeom& g, const void* x, const void* w, const float* bias, void* out, int act, float alpha, cudaStream_t s) {
-  long tot = (long)g.N * g.OH * g.OW * (g.O / 16);
-  edge_conv_small_cin_kernel<T, TW><<<(unsigned)((tot + 255) / 256), 256, 16 * g.C * g.O * sizeof(float), s>>>((const T*)x, (const TW*)w, bias, (T*)out, g.N, g.H, g.W, g.C, g.OH, g.OW, g.O, act, alpha);
+  long tot = (long)g.N * g.OH * (g.OW / 4) * (g.O / 16); long blocks = (tot + 127) / 128; if (blocks > 148 * 8) blocks = 148 * 8;
+  edge_conv_small_cin_kernel<T, TW><<<(unsigned)blocks, 128, 16 * g.C * g.O * sizeof(float), s>>>((const T*)x, (const TW*)w, bias, (T*)out, g.N, g.H, g.W, g.C, g.OH, g.OW, g.O, act, alpha);
 }
 void k_edge_conv_small_cin(int prec, int wprec, const ConvGeom& g, const void* x, const void* w, const float* bias, void* out, int act, float alpha, cudaStream_t s) {
   if (prec == PREC_F32) launch_conv_small_cin<float, float>(g, x, w, bias, out, act, alpha, s);
@@ -242,11 +277,11 @@ void k_edge_conv_small_cin(int prec, int wprec, const ConvGeom& g, const void* x
   else launch_conv_small_cin<__nv_bfloat16, __nv_bfloat16>(g, x, w, bias, out, act, alpha, s);
   LAUNCHED();
 }
-static int edge_wgrad_ctas(const ConvGeom& g) { long P = (long)g.N * g.OH * g.OW; long c = 148 * 4; long cap = (P + 63) / 64; if (c > cap) c = cap; if (c < 1) c = 1; return (int)c; }
+static int edge_wgrad_ctas(const ConvGeom& g) { long P = (long)g.N * g.OH * g.OW; long c = 148 * 2; long cap = (P + 63) / 64; if (c > cap) c = cap; if (c < 1) c = 1; return (int)c; }
 size_t k_edge_wgrad_scratch_floats(const ConvGeom& g) { return edge_wgrad_small_cin_supported(g) ? (size_t)edge_wgrad_ctas(g) * g.O * 16 * g.C : 0; }
 void k_edge_wgrad_small_cin(int prec, const ConvGeom& g, const void* x, const void* dy, float* dw, float* scratch, int accumulate, cudaStream_t s) {
   const int ctas = edge_wgrad_ctas(g); const long P = (long)g.N * g.OH * g.OW; const int ppc = (int)((P + ctas - 1) / ctas);
-  const size_t n = (size_t)g.O * 16 * g.C; const size_t smem = (32 * g.O + 32 * 64) * sizeof(float);
+  const size_t n = (size_t)g.O * 16 * g.C; const size_t smem = (64 * g.O + 64 * 64) * sizeof(float);
   DISPATCH_PREC(prec, T, (edge_wgrad_small_cin_kernel<T><<<ctas, 2 * g.O, smem, s>>>((const T*)x, (const T*)dy, scratch, g.N, g.H, g.W, g.C, g.OH, g.OW, g.O, ppc))); LAUNCHED();
   k_reduce_splits(scratch, dw, n, ctas, n, accumulate, s);
 }

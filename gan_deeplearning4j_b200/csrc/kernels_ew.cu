@@ -85,12 +85,25 @@ void k_weight_shadow(const float* w, __nv_bfloat16* w_bf, __nv_bfloat16* wt_bf, 
 // ---------------------------------------------------------------- sliced column reductions ---------------
 // Thread idx -> (slice s = idx / C, channel c = idx % C); it sums rows s, s+S, s+2S, ... so that a warp
 // reads consecutive addresses.  partial[(g*S + s)*C + c].  Stage 2: one warp per channel, fixed order.
+static const int SLICE_ELEMS = 262144;     // S*C partial sums per group at most
 static inline int pick_slices(int rows, int C) {
-  int cap = 65536 / (C > 0 ? C : 1); if (cap < 1) cap = 1; if (cap > 2048) cap = 2048;
+  int cap = SLICE_ELEMS / (C > 0 ? C : 1); if (cap < 1) cap = 1; if (cap > 2048) cap = 2048;
   int S = rows / 8; if (S < 1) S = 1; if (S > cap) S = cap; return S;
 }
-size_t k_bn_scratch_floats(int C, int groups) { return (size_t)2 * groups * (65536 + 2 * (size_t)C) + 64; }
-size_t k_colsum_scratch_floats(int C) { return (size_t)(65536 + C) + 64; }
+size_t k_bn_scratch_floats(int C, int groups) { return (size_t)2 * groups * (SLICE_ELEMS + 2 * (size_t)C) + 64; }
+size_t k_colsum_scratch_floats(int C) { return (size_t)(SLICE_ELEMS + C) + 64; }
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  uint4 u; __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+  return u;
+}
 
 template <typename T>
 __global__ void bn_stats_partial_kernel(const T* __restrict__ x, int rows, int C, int S, float* __restrict__ psum, float* __restrict__ psq) {
@@ -103,31 +116,74 @@ __global__ void bn_stats_partial_kernel(const T* __restrict__ x, int rows, int C
   for (int r = sl; r < rows; r += S) { float v = ldf(xg, (size_t)r * C + c); a += v; b = fmaf(v, v, b); }
   psum[((size_t)g * S + sl) * C + c] = a; psq[((size_t)g * S + sl) * C + c] = b;
 }
-__global__ void bn_stats_final_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int rows, int C, int S, int groups, float eps,
+// bf16, C % 8 == 0, C <= 2048: a 256-thread block = (C/8 channel-octets) x TY row lanes reduces a contiguous chunk of rows
+// with 16-byte loads, folds its TY lanes in shared memory and writes ONE partial row per block: many threads in stage 1,
+// few partials for stage 2.
+static inline int vec_ty(int C) { int c8 = C / 8; int ty = 256 / c8; return ty < 1 ? 1 : ty; }
+static inline bool vec_ok(int prec, int C) { return prec == PREC_BF16 && C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0; }
+static inline int vec_blocks(int rows, int C) { int ty = vec_ty(C); int b = rows / (ty * 4); int cap = SLICE_ELEMS / C; if (cap > 512) cap = 512; if (b > cap) b = cap; if (b < 1) b = 1; return b; }
+template <int NV>
+__device__ __forceinline__ void block_fold_write(float (&acc)[NV][8], int C, int C8, int c8, int ty, int TY, float* const (&dst)[NV], size_t row_off) {
+  __shared__ float sred[NV][2048];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sred[v][ty * C + c8 * 8 + j] = acc[v][j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) { float a = 0.f; for (int k = 0; k < TY; ++k) a += sred[v][k * C + c]; dst[v][row_off + c] = a; }
+  }
+}
+__global__ void __launch_bounds__(256) bn_stats_partial_bf16x8_kernel(const uint4* __restrict__ x, int rows, int C, int S, float* __restrict__ psum, float* __restrict__ psq) {
+  const int g = blockIdx.y, C8 = C / 8, TY = 256 / C8, c8 = threadIdx.x % C8, ty = threadIdx.x / C8, sl = blockIdx.x;
+  const int chunk = (rows + S - 1) / S, r0 = sl * chunk, r1 = min(rows, r0 + chunk);
+  const uint4* xg = x + (size_t)g * rows * C8;
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
+  for (int r = r0 + ty; r < r1; r += TY) { float v[8]; unpack8(xg[(size_t)r * C8 + c8], v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc[0][j] += v[j]; acc[1][j] = fmaf(v[j], v[j], acc[1][j]); } }
+  float* const dst[2] = {psum, psq};
+  block_fold_write<2>(acc, C, C8, c8, ty, TY, dst, ((size_t)g * S + sl) * C);
+}
+// stage 2: block = 32 adjacent channels x 16 slice lanes (coalesced 128-byte rows of the partial arrays), fixed-order tree in double
+__global__ void __launch_bounds__(512) bn_stats_final_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int rows, int C, int S, int groups, float eps,
                                       float* __restrict__ mean, float* __restrict__ invstd,
                                       const float* __restrict__ run_mean, const float* __restrict__ run_var, float* g_mean, float* g_var, float decay) {
-  int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
-  if (warp >= C) return;
-  int c = warp;
+  __shared__ double sa[16][33], sb[16][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, c = blockIdx.x * 32 + tx;
   double acc_gm = 0.0, acc_gv = 0.0;
   for (int g = 0; g < groups; ++g) {
     double a = 0.0, b = 0.0;
-    for (int sl = lane; sl < S; sl += 32) { a += psum[((size_t)g * S + sl) * C + c]; b += psq[((size_t)g * S + sl) * C + c]; }
-    for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-    double mu = a / rows, var = b / rows - mu * mu; if (var < 0) var = 0;
-    if (lane == 0) { mean[g * C + c] = (float)mu; invstd[g * C + c] = (float)(1.0 / sqrt(var + (double)eps)); }
-    if (g_mean) { acc_gm += (1.0 - decay) * ((double)run_mean[c] - mu); acc_gv += (1.0 - decay) * ((double)run_var[c] - var); }
+    if (c < C) for (int sl = ty; sl < S; sl += 16) { a += psum[((size_t)g * S + sl) * C + c]; b += psq[((size_t)g * S + sl) * C + c]; }
+    sa[ty][tx] = a; sb[ty][tx] = b;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+      for (int k = 1; k < 16; ++k) { a += sa[k][tx]; b += sb[k][tx]; }
+      const double mu = a / rows; double var = b / rows - mu * mu; if (var < 0) var = 0;
+      mean[g * C + c] = (float)mu; invstd[g * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+      if (g_mean) { acc_gm += (1.0 - decay) * ((double)run_mean[c] - mu); acc_gv += (1.0 - decay) * ((double)run_var[c] - var); }
+    }
+    __syncthreads();
   }
   // BatchNormalization running stats as pseudo-gradients through a NoOp updater; groups (the two D minibatches) averaged
-  if (g_mean && lane == 0) { g_mean[c] = (float)(acc_gm / groups); g_var[c] = (float)(acc_gv / groups); }
+  if (g_mean && ty == 0 && c < C) { g_mean[c] = (float)(acc_gm / groups); g_var[c] = (float)(acc_gv / groups); }
 }
 void k_bn_stats(int prec, const void* x, int rows, int C, int groups, float* scratch, float* mean, float* invstd, float eps,
                 const float* run_mean, const float* run_var, float* g_mean, float* g_var, float decay, cudaStream_t s) {
-  int S = pick_slices(rows, C);
+  const bool vec = vec_ok(prec, C);
+  int S = vec ? vec_blocks(rows, C) : pick_slices(rows, C);
   float* psum = scratch; float* psq = scratch + (size_t)groups * S * C;
-  dim3 grid((S * C + 255) / 256, groups);
-  DISPATCH_PREC(prec, T, (bn_stats_partial_kernel<T><<<grid, 256, 0, s>>>((const T*)x, rows, C, S, psum, psq))); LAUNCHED();
-  bn_stats_final_kernel<<<(C * 32 + 255) / 256, 256, 0, s>>>(psum, psq, rows, C, S, groups, eps, mean, invstd, run_mean, run_var, g_mean, g_var, decay); LAUNCHED();
+  if (vec) {
+    bn_stats_partial_bf16x8_kernel<<<dim3(S, groups), 256, 0, s>>>((const uint4*)x, rows, C, S, psum, psq);
+  } else {
+    dim3 grid((S * C + 255) / 256, groups);
+    DISPATCH_PREC(prec, T, (bn_stats_partial_kernel<T><<<grid, 256, 0, s>>>((const T*)x, rows, C, S, psum, psq)));
+  }
+  LAUNCHED();
+  bn_stats_final_kernel<<<(C + 31) / 32, 512, 0, s>>>(psum, psq, rows, C, S, groups, eps, mean, invstd, run_mean, run_var, g_mean, g_var, decay); LAUNCHED();
 }
 __global__ void bn_prep_infer_kernel(const float* __restrict__ rm, const float* __restrict__ rv, int C, int groups, float eps, float* mean, float* invstd) {
   int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= C * groups) return;
@@ -194,19 +250,53 @@ __global__ void bn_bwd_partial_kernel(const T* __restrict__ x, const T* __restri
   }
   p1[((size_t)g * S + sl) * C + c] = a; p2[((size_t)g * S + sl) * C + c] = b;
 }
-__global__ void bn_bwd_final_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int rows, int C, int S, int groups,
+__global__ void __launch_bounds__(256) bn_bwd_partial_bf16x8_kernel(const uint4* __restrict__ x, const uint4* __restrict__ eo, int rows, int C, int S, const float* __restrict__ mean,
+                                             const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int act, float alpha,
+                                             float* __restrict__ p1, float* __restrict__ p2) {
+  const int g = blockIdx.y, C8 = C / 8, TY = 256 / C8, c8 = threadIdx.x % C8, ty = threadIdx.x / C8, sl = blockIdx.x;
+  const int chunk = (rows + S - 1) / S, r0 = sl * chunk, r1 = min(rows, r0 + chunk);
+  const uint4* xg = x + (size_t)g * rows * C8; const uint4* eg = eo + (size_t)g * rows * C8;
+  float mu[8], is[8], ga[8], be[8], acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { const int c = c8 * 8 + j; mu[j] = mean[g * C + c]; is[j] = invstd[g * C + c]; ga[j] = gamma[c]; be[j] = beta[c]; acc[0][j] = 0.f; acc[1][j] = 0.f; }
+  for (int r = r0 + ty; r < r1; r += TY) {
+    float xv[8], ev[8]; unpack8(xg[(size_t)r * C8 + c8], xv); unpack8(eg[(size_t)r * C8 + c8], ev);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float xh = (xv[j] - mu[j]) * is[j]; const float dy = ev[j] * act_grad_from_pre(act, fmaf(ga[j], xh, be[j]), alpha); acc[0][j] += dy; acc[1][j] = fmaf(dy, xh, acc[1][j]); }
+  }
+  float* const dst[2] = {p1, p2};
+  block_fold_write<2>(acc, C, C8, c8, ty, TY, dst, ((size_t)g * S + sl) * C);
+}
+__global__ void bn_bwd_apply_bf16x8_kernel(const uint4* __restrict__ x, const uint4* __restrict__ eo, uint4* __restrict__ ei, int rows, int C, int groups,
+                                           const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                           const float* __restrict__ beta, int act, float alpha, const float* __restrict__ c1, const float* __restrict__ c2) {
+  const int C8 = C / 8; const size_t per_group = (size_t)rows * C8, total = per_group * groups;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % C8) * 8; const int g = (int)(i / per_group);
+    float xv[8], ev[8], o[8]; unpack8(x[i], xv); unpack8(eo[i], ev);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const int c = c0 + j, k = g * C + c; const float xh = (xv[j] - mean[k]) * invstd[k];
+      const float dy = ev[j] * act_grad_from_pre(act, fmaf(gamma[c], xh, beta[c]), alpha); o[j] = gamma[c] * invstd[k] * (dy - c1[k] - xh * c2[k]); }
+    ei[i] = pack8(o);
+  }
+}
+__global__ void __launch_bounds__(512) bn_bwd_final_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int rows, int C, int S, int groups,
                                     float* __restrict__ c1, float* __restrict__ c2, float* g_gamma, float* g_beta, int want) {
-  int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
-  if (warp >= C) return;
-  int c = warp; double tg = 0.0, tb = 0.0;
+  __shared__ double sa[16][33], sb[16][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, c = blockIdx.x * 32 + tx;
+  double tg = 0.0, tb = 0.0;
   for (int g = 0; g < groups; ++g) {
     double a = 0.0, b = 0.0;
-    for (int sl = lane; sl < S; sl += 32) { a += p1[((size_t)g * S + sl) * C + c]; b += p2[((size_t)g * S + sl) * C + c]; }
-    for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-    if (lane == 0) { c1[g * C + c] = (float)(a / rows); c2[g * C + c] = (float)(b / rows); }
-    tb += a; tg += b;
+    if (c < C) for (int sl = ty; sl < S; sl += 16) { a += p1[((size_t)g * S + sl) * C + c]; b += p2[((size_t)g * S + sl) * C + c]; }
+    sa[ty][tx] = a; sb[ty][tx] = b;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+      for (int k = 1; k < 16; ++k) { a += sa[k][tx]; b += sb[k][tx]; }
+      c1[g * C + c] = (float)(a / rows); c2[g * C + c] = (float)(b / rows); tb += a; tg += b;
+    }
+    __syncthreads();
   }
-  if (want && lane == 0) { g_beta[c] += (float)tb; g_gamma[c] += (float)tg; }
+  if (want && ty == 0 && c < C) { g_beta[c] += (float)tb; g_gamma[c] += (float)tg; }
 }
 template <typename T>
 __global__ void bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ eo, T* __restrict__ ei, int rows, int C, int groups,
@@ -223,14 +313,22 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict
 void k_bn_bwd(int prec, const void* x, const void* eps_out, void* eps_in, int rows, int C, int groups,
               const float* mean, const float* invstd, const float* gamma, const float* beta, int act, float alpha,
               float* scratch, float* g_gamma, float* g_beta, int want, cudaStream_t s) {
-  int S = pick_slices(rows, C);
+  const bool vec = vec_ok(prec, C);
+  int S = vec ? vec_blocks(rows, C) : pick_slices(rows, C);
   float* p1 = scratch; float* p2 = p1 + (size_t)groups * S * C; float* c1 = p2 + (size_t)groups * S * C; float* c2 = c1 + (size_t)groups * C;
-  dim3 grid((S * C + 255) / 256, groups);
-  DISPATCH_PREC(prec, T, (bn_bwd_partial_kernel<T><<<grid, 256, 0, s>>>((const T*)x, (const T*)eps_out, rows, C, S, mean, invstd, gamma, beta, act, alpha, p1, p2))); LAUNCHED();
-  bn_bwd_final_kernel<<<(C * 32 + 255) / 256, 256, 0, s>>>(p1, p2, rows, C, S, groups, c1, c2, g_gamma, g_beta, want); LAUNCHED();
+  if (vec) {
+    bn_bwd_partial_bf16x8_kernel<<<dim3(S, groups), 256, 0, s>>>((const uint4*)x, (const uint4*)eps_out, rows, C, S, mean, invstd, gamma, beta, act, alpha, p1, p2);
+  } else {
+    dim3 grid((S * C + 255) / 256, groups);
+    DISPATCH_PREC(prec, T, (bn_bwd_partial_kernel<T><<<grid, 256, 0, s>>>((const T*)x, (const T*)eps_out, rows, C, S, mean, invstd, gamma, beta, act, alpha, p1, p2)));
+  }
+  LAUNCHED();
+  bn_bwd_final_kernel<<<(C + 31) / 32, 512, 0, s>>>(p1, p2, rows, C, S, groups, c1, c2, g_gamma, g_beta, want); LAUNCHED();
   if (eps_in) {
     size_t n = (size_t)rows * C * groups;
-    DISPATCH_PREC(prec, T, (bn_bwd_apply_kernel<T><<<ew_blocks(n), 256, 0, s>>>((const T*)x, (const T*)eps_out, (T*)eps_in, rows, C, groups, mean, invstd, gamma, beta, act, alpha, c1, c2))); LAUNCHED();
+    if (vec) bn_bwd_apply_bf16x8_kernel<<<ew_blocks(n / 8), 256, 0, s>>>((const uint4*)x, (const uint4*)eps_out, (uint4*)eps_in, rows, C, groups, mean, invstd, gamma, beta, act, alpha, c1, c2);
+    else DISPATCH_PREC(prec, T, (bn_bwd_apply_kernel<T><<<ew_blocks(n), 256, 0, s>>>((const T*)x, (const T*)eps_out, (T*)eps_in, rows, C, groups, mean, invstd, gamma, beta, act, alpha, c1, c2)));
+    LAUNCHED();
   }
 }
 
@@ -354,16 +452,34 @@ __global__ void colsum_partial_kernel(const T* __restrict__ x, int rows, int C, 
   for (int r = sl; r < rows; r += S) a += ldf(x, (size_t)r * C + c);
   p[(size_t)sl * C + c] = a;
 }
-__global__ void colsum_final_kernel(const float* __restrict__ p, int C, int S, float* out, int accumulate) {
-  int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32; if (warp >= C) return;
-  double a = 0.0; for (int sl = lane; sl < S; sl += 32) a += p[(size_t)sl * C + warp];
-  for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-  if (lane == 0) out[warp] = (accumulate ? out[warp] : 0.f) + (float)a;
+__global__ void __launch_bounds__(256) colsum_partial_bf16x8_kernel(const uint4* __restrict__ x, int rows, int C, int S, float* __restrict__ p) {
+  const int C8 = C / 8, TY = 256 / C8, c8 = threadIdx.x % C8, ty = threadIdx.x / C8, sl = blockIdx.x;
+  const int chunk = (rows + S - 1) / S, r0 = sl * chunk, r1 = min(rows, r0 + chunk);
+  float acc[1][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
+  for (int r = r0 + ty; r < r1; r += TY) { float v[8]; unpack8(x[(size_t)r * C8 + c8], v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[0][j] += v[j]; }
+  float* const dst[1] = {p};
+  block_fold_write<1>(acc, C, C8, c8, ty, TY, dst, (size_t)sl * C);
+}
+__global__ void __launch_bounds__(512) colsum_final_kernel(const float* __restrict__ p, int C, int S, float* out, int accumulate) {
+  __shared__ double sa[16][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, c = blockIdx.x * 32 + tx;
+  double a = 0.0;
+  if (c < C) for (int sl = ty; sl < S; sl += 16) a += p[(size_t)sl * C + c];
+  sa[ty][tx] = a;
+  __syncthreads();
+  if (ty == 0 && c < C) { for (int k = 1; k < 16; ++k) a += sa[k][tx]; out[c] = (accumulate ? out[c] : 0.f) + (float)a; }
 }
 void k_colsum(int prec, const void* x, int rows, int C, float* scratch, float* out, int accumulate, cudaStream_t s) {
-  int S = pick_slices(rows, C);
-  DISPATCH_PREC(prec, T, (colsum_partial_kernel<T><<<(S * C + 255) / 256, 256, 0, s>>>((const T*)x, rows, C, S, scratch))); LAUNCHED();
-  colsum_final_kernel<<<(C * 32 + 255) / 256, 256, 0, s>>>(scratch, C, S, out, accumulate); LAUNCHED();
+  const bool vec = vec_ok(prec, C);
+  int S = vec ? vec_blocks(rows, C) : pick_slices(rows, C);
+  if (vec) colsum_partial_bf16x8_kernel<<<S, 256, 0, s>>>((const uint4*)x, rows, C, S, scratch);
+  else DISPATCH_PREC(prec, T, (colsum_partial_kernel<T><<<(S * C + 255) / 256, 256, 0, s>>>((const T*)x, rows, C, S, scratch)));
+  LAUNCHED();
+  colsum_final_kernel<<<(C + 31) / 32, 512, 0, s>>>(scratch, C, S, out, accumulate); LAUNCHED();
 }
 __global__ void sumsq_segments_kernel(const float* __restrict__ p, const int64_t* off, const int64_t* len, const float* coef, int nseg, double* out) {
   __shared__ double red[32];

@@ -396,7 +396,11 @@ def test_edge_layers_dcgan_ends(b200, prec):
     for li, name, p, shape, _ in D.param_table():
         k = int(np.prod(shape))
         if p not in ("mean", "var"):
-            assert rel_err(g_b[off:off + k], g_o[off:off + k]) < (tol if prec == "fp32" else 0.1), (name, p)
+            if prec == "fp32":
+                assert rel_err(g_b[off:off + k], g_o[off:off + k]) < tol, (name, p)
+            else:   # bf16 activations through train-mode BN on 8 images: compare in the Frobenius norm
+                d = np.linalg.norm(g_b[off:off + k] - g_o[off:off + k]) / (np.linalg.norm(g_o[off:off + k]) + 1e-30)
+                assert d < 0.1, (name, p, d)
         off += k
     # full step: exercises G-last forward/wgrad/input-grad, D1 input-grad, G-first forward/wgrad
     gan = b.Gan(bG, bD, use_cuda_graph=False)
