@@ -104,6 +104,7 @@ struct b2g_net {
   void *epsA = nullptr, *epsB = nullptr; size_t eps_elems = 0;
   float* scratch = nullptr; size_t scratch_floats = 0;
   float* loss_dev = nullptr;           // [8]
+  unsigned* barrier_dev = nullptr;     // grid-barrier counter of the cooperative BN kernels
   double* l2_dev = nullptr;
   void* input_grad = nullptr;          // where the last backward left d(loss)/d(input), or null
   int last_rows = 0;
@@ -221,6 +222,7 @@ static int32_t net_alloc(b2g_net* n) {
   B2(dalloc(n, &n->params, sizeof(float) * n->n_params)); B2(dalloc(n, &n->grads, sizeof(float) * n->n_params));
   B2(dalloc(n, &n->st0, sizeof(float) * n->n_params)); B2(dalloc(n, &n->st1, sizeof(float) * n->n_params));
   if (n->n_shadow) B2(dalloc(n, &n->shadow, sizeof(__nv_bfloat16) * n->n_shadow));
+  B2(dalloc(n, &n->barrier_dev, sizeof(unsigned)));
   B2(dalloc(n, &n->step_dev, sizeof(int))); B2(dalloc(n, &n->loss_dev, sizeof(float) * 8)); B2(dalloc(n, &n->l2_dev, sizeof(double)));
   B2(dalloc(n, &n->labels_dev, sizeof(float) * R));
   B2(dalloc(n, (char**)&n->input, ts * R * n->in_elems));
@@ -370,6 +372,10 @@ static int32_t net_forward(b2g_net* n, const void* in, const FwdOpts& o, const v
       case B2G_LAYER_DECONV2D: { ConvGeom g = l.geom; g.N = R; B2(gemm_dgrad(n, l, g, cur, bias, out, d.act, d.act_alpha)); } break;
       case B2G_LAYER_BATCHNORM: {
         int rows_pg = (R / o.groups) * l.oh * l.ow;
+        if (o.train && k_bn_fused_ok(n->prec, l.oc, o.groups) &&
+            k_bn_fwd_fused(cur, out, rows_pg, l.oc, o.groups, n->scratch, l.bn_mean, l.bn_invstd, n->params + l.off_gamma, n->params + l.off_beta, l.fused_act, l.fused_alpha, d.bn_eps,
+                           n->params + l.off_mean, n->params + l.off_var, o.update_running ? n->grads + l.off_mean : nullptr, o.update_running ? n->grads + l.off_var : nullptr, d.bn_decay,
+                           n->barrier_dev, s) == 0) break;
         if (o.train) k_bn_stats(n->prec, cur, rows_pg, l.oc, o.groups, n->scratch, l.bn_mean, l.bn_invstd, d.bn_eps, n->params + l.off_mean, n->params + l.off_var,
                                 o.update_running ? n->grads + l.off_mean : nullptr, o.update_running ? n->grads + l.off_var : nullptr, d.bn_decay, s);
         else k_bn_prep_infer(n->params + l.off_mean, n->params + l.off_var, l.oc, o.groups, d.bn_eps, l.bn_mean, l.bn_invstd, s);
@@ -424,6 +430,9 @@ static int32_t net_backward(b2g_net* n, const void* net_in, void* eps, int rows,
       } break;
       case B2G_LAYER_BATCHNORM: {
         int rows_pg = (R / groups) * l.oh * l.ow; void* nx = need_in ? other(cur) : nullptr;
+        if (k_bn_fused_ok(n->prec, l.oc, groups) &&
+            k_bn_bwd_fused(lin, cur, nx, rows_pg, l.oc, groups, l.bn_mean, l.bn_invstd, n->params + l.off_gamma, n->params + l.off_beta, l.fused_act, l.fused_alpha, n->scratch,
+                           n->grads + l.off_gamma, n->grads + l.off_beta, want_wgrad ? 1 : 0, n->barrier_dev, s) == 0) { if (need_in) cur = nx; break; }
         k_bn_bwd(n->prec, lin, cur, nx, rows_pg, l.oc, groups, l.bn_mean, l.bn_invstd, n->params + l.off_gamma, n->params + l.off_beta, l.fused_act, l.fused_alpha,
                  n->scratch, n->grads + l.off_gamma, n->grads + l.off_beta, want_wgrad ? 1 : 0, s);
         if (need_in) cur = nx;

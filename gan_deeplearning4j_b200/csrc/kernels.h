@@ -49,6 +49,13 @@ void k_bn_bwd(int prec, const void* x, const void* eps_out, void* eps_in, int ro
               const float* mean, const float* invstd, const float* gamma, const float* beta, int act, float alpha,
               float* scratch, float* g_gamma, float* g_beta, int want_param_grads, cudaStream_t s);
 
+// fused cooperative variants (bf16, C % 8 == 0): one launch for statistics + apply / reduce + apply; return 0 on success
+bool k_bn_fused_ok(int prec, int C, int groups);
+int k_bn_fwd_fused(const void* x, void* y, int rows_per_group, int C, int groups, float* scratch, float* mean, float* invstd, const float* gamma, const float* beta,
+                   int act, float alpha, float eps, const float* run_mean, const float* run_var, float* g_mean, float* g_var, float decay, unsigned* counter, cudaStream_t s);
+int k_bn_bwd_fused(const void* x, const void* eps_out, void* eps_in, int rows_per_group, int C, int groups, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                   int act, float alpha, float* scratch, float* g_gamma, float* g_beta, int want_param_grads, unsigned* counter, cudaStream_t s);
+
 // ---- activations / pooling / upsampling -----------------------------------------------------------
 void k_act_fwd(int prec, const void* x, void* y, size_t n, int act, float alpha, cudaStream_t s);
 // eps_in = eps_out * f'(.) evaluated from the layer OUTPUT a (tanh: 1-a^2, sigmoid: a(1-a), relu/lrelu: sign of a)

@@ -8,6 +8,7 @@
 //
 // All of these are bandwidth-bound: threads are mapped so that a warp touches consecutive channels
 // (NHWC innermost), reductions are fixed-order two-stage (deterministic), nothing allocates.
+#include <stdlib.h>
 #include "kernels.h"
 #include "common.cuh"
 
@@ -85,7 +86,7 @@ void k_weight_shadow(const float* w, __nv_bfloat16* w_bf, __nv_bfloat16* wt_bf, 
 // ---------------------------------------------------------------- sliced column reductions ---------------
 // Thread idx -> (slice s = idx / C, channel c = idx % C); it sums rows s, s+S, s+2S, ... so that a warp
 // reads consecutive addresses.  partial[(g*S + s)*C + c].  Stage 2: one warp per channel, fixed order.
-static const int SLICE_ELEMS = 262144;     // S*C partial sums per group at most
+static const int SLICE_ELEMS = 1 << 20;     // S*C partial sums per group at most
 static inline int pick_slices(int rows, int C) {
   int cap = SLICE_ELEMS / (C > 0 ? C : 1); if (cap < 1) cap = 1; if (cap > 2048) cap = 2048;
   int S = rows / 8; if (S < 1) S = 1; if (S > cap) S = cap; return S;
@@ -330,6 +331,221 @@ void k_bn_bwd(int prec, const void* x, const void* eps_out, void* eps_in, int ro
     else DISPATCH_PREC(prec, T, (bn_bwd_apply_kernel<T><<<ew_blocks(n), 256, 0, s>>>((const T*)x, (const T*)eps_out, (T*)eps_in, rows, C, groups, mean, invstd, gamma, beta, act, alpha, c1, c2)));
     LAUNCHED();
   }
+}
+
+
+// ---------------------------------------------------------------- fused (cooperative) BatchNorm --------------------
+// One cooperative launch per BatchNorm forward / backward instead of three kernels: every CTA is co-resident, so the
+// batch-wide reduction is a software grid barrier between the phases of ONE kernel:
+//   phase 1   per-CTA partial sums over a contiguous chunk of rows (16-byte loads, block fold)       -> scratch[g][cta][C]
+//   phase 1.5 channel (g,c) summed over the CTAs in fixed order, in double -> mean/invstd (fwd) or c1/c2 + dgamma/dbeta (bwd)
+//   phase 2   elementwise apply; the tensor (<= tens of MB) is re-read from L2, not HBM
+// Deterministic (fixed partition, fixed order).  bf16, C % 8 == 0, C <= 2048.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned v;
+    do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory"); } while (v < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256, 3) bn_fwd_fused_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int rows, int C, int groups, float* __restrict__ scratch,
+                                                           float* __restrict__ mean, float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           int act, float alpha, float eps, const float* __restrict__ run_mean, const float* __restrict__ run_var,
+                                                           float* g_mean, float* g_var, float decay, unsigned* counter) {
+  const int C8 = C / 8, TY = 256 / C8, c8 = threadIdx.x % C8, ty = threadIdx.x / C8, S = gridDim.x, sl = blockIdx.x;
+  float* psum = scratch; float* psq = scratch + (size_t)groups * S * C;
+  const int chunk = (rows + S - 1) / S, r0 = sl * chunk, r1 = min(rows, r0 + chunk);
+  for (int g = 0; g < groups; ++g) {
+    const uint4* xg = x + (size_t)g * rows * C8;
+    float acc[2][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
+    int r = r0 + ty;
+    for (; r + 3 * TY < r1; r += 4 * TY) {     // 4 independent 16-byte loads in flight per thread
+      uint4 u[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) u[q] = xg[(size_t)(r + q * TY) * C8 + c8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { float v[8]; unpack8(u[q], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc[0][j] += v[j]; acc[1][j] = fmaf(v[j], v[j], acc[1][j]); } }
+    }
+    for (; r < r1; r += TY) { float v[8]; unpack8(xg[(size_t)r * C8 + c8], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { acc[0][j] += v[j]; acc[1][j] = fmaf(v[j], v[j], acc[1][j]); } }
+    float* const dst[2] = {psum, psq};
+    block_fold_write<2>(acc, C, C8, c8, ty, TY, dst, ((size_t)g * S + sl) * C);
+    __syncthreads();
+  }
+  grid_barrier(counter, gridDim.x);
+  {  // phase 1.5: 128 threads per channel (two channels per CTA pass), <=5 partial rows per thread all in flight, fixed-order tree in double
+    __shared__ double swa[8], swb[8];
+    const int half = threadIdx.x >> 7, t = threadIdx.x & 127, lane = threadIdx.x & 31, wih = (threadIdx.x >> 5) & 3;
+    for (int cb = blockIdx.x * 2; cb < C; cb += gridDim.x * 2) {
+      const int c = cb + half; double agm = 0.0, agv = 0.0;
+      for (int g = 0; g < groups; ++g) {
+        double a = 0.0, b = 0.0;
+        if (c < C) { float va[5], vb[5];
+#pragma unroll
+          for (int q = 0; q < 5; ++q) { const int k = t + 128 * q; va[q] = k < S ? __ldcg(psum + ((size_t)g * S + k) * C + c) : 0.f; vb[q] = k < S ? __ldcg(psq + ((size_t)g * S + k) * C + c) : 0.f; }
+#pragma unroll
+          for (int q = 0; q < 5; ++q) { a += va[q]; b += vb[q]; } }
+        for (int m = 16; m; m >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, m); b += __shfl_xor_sync(0xffffffffu, b, m); }
+        __syncthreads();
+        if (lane == 0) { swa[half * 4 + wih] = a; swb[half * 4 + wih] = b; }
+        __syncthreads();
+        if (t == 0 && c < C) {
+          a = swa[half * 4] + swa[half * 4 + 1] + swa[half * 4 + 2] + swa[half * 4 + 3]; b = swb[half * 4] + swb[half * 4 + 1] + swb[half * 4 + 2] + swb[half * 4 + 3];
+          const double mu = a / rows; double var = b / rows - mu * mu; if (var < 0) var = 0;
+          mean[g * C + c] = (float)mu; invstd[g * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+          if (g_mean) { agm += (1.0 - decay) * ((double)run_mean[c] - mu); agv += (1.0 - decay) * ((double)run_var[c] - var); }
+        }
+      }
+      if (g_mean && t == 0 && c < C) { g_mean[c] = (float)(agm / groups); g_var[c] = (float)(agv / groups); }
+    }
+  }
+  grid_barrier(counter, 2 * gridDim.x);
+  const size_t per_group = (size_t)rows * C8, total = per_group * groups;
+  // phase 2: blockDim (256) is a multiple of C/8, so a thread keeps the same 8 channels for every element it touches:
+  // fold (mean, invstd, gamma, beta) into one scale/shift pair per channel, once per group
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  (void)total;
+  for (int g = 0; g < groups; ++g) {
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const int c = c8 * 8 + j; const float is = __ldcg(invstd + g * C + c); sc[j] = gamma[c] * is; sh[j] = fmaf(-__ldcg(mean + g * C + c), sc[j], beta[c]); }
+    const uint4* xg = x + (size_t)g * per_group; uint4* yg = y + (size_t)g * per_group;
+    for (size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i0 < per_group; i0 += 4 * stride) {
+      uint4 u[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const size_t i = i0 + q * stride; if (i < per_group) u[q] = xg[i]; }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const size_t i = i0 + q * stride; if (i >= per_group) break;
+        float v[8]; unpack8(u[q], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = act_fwd(act, fmaf(v[j], sc[j], sh[j]), alpha);
+        yg[i] = pack8(v); }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(const uint4* __restrict__ x, const uint4* __restrict__ eo, uint4* __restrict__ ei, int rows, int C, int groups,
+                                                           const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           int act, float alpha, float* __restrict__ scratch, float* g_gamma, float* g_beta, int want, unsigned* counter) {
+  const int C8 = C / 8, TY = 256 / C8, c8 = threadIdx.x % C8, ty = threadIdx.x / C8, S = gridDim.x, sl = blockIdx.x;
+  float* p1 = scratch; float* p2 = p1 + (size_t)groups * S * C; float* c1 = p2 + (size_t)groups * S * C; float* c2 = c1 + (size_t)groups * C;
+  const int chunk = (rows + S - 1) / S, r0 = sl * chunk, r1 = min(rows, r0 + chunk);
+  for (int g = 0; g < groups; ++g) {
+    const uint4* xg = x + (size_t)g * rows * C8; const uint4* eg = eo + (size_t)g * rows * C8;
+    float mu[8], is[8], ga[8], be[8], acc[2][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const int c = c8 * 8 + j; mu[j] = mean[g * C + c]; is[j] = invstd[g * C + c]; ga[j] = gamma[c]; be[j] = beta[c]; acc[0][j] = 0.f; acc[1][j] = 0.f; }
+    int r = r0 + ty;
+    for (; r + 3 * TY < r1; r += 4 * TY) {
+      uint4 ux[4], ue[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { ux[q] = xg[(size_t)(r + q * TY) * C8 + c8]; ue[q] = eg[(size_t)(r + q * TY) * C8 + c8]; }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { float xv[8], ev[8]; unpack8(ux[q], xv); unpack8(ue[q], ev);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float xh = (xv[j] - mu[j]) * is[j]; const float dy = ev[j] * act_grad_from_pre(act, fmaf(ga[j], xh, be[j]), alpha); acc[0][j] += dy; acc[1][j] = fmaf(dy, xh, acc[1][j]); } }
+    }
+    for (; r < r1; r += TY) {
+      float xv[8], ev[8]; unpack8(xg[(size_t)r * C8 + c8], xv); unpack8(eg[(size_t)r * C8 + c8], ev);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float xh = (xv[j] - mu[j]) * is[j]; const float dy = ev[j] * act_grad_from_pre(act, fmaf(ga[j], xh, be[j]), alpha); acc[0][j] += dy; acc[1][j] = fmaf(dy, xh, acc[1][j]); }
+    }
+    float* const dst[2] = {p1, p2};
+    block_fold_write<2>(acc, C, C8, c8, ty, TY, dst, ((size_t)g * S + sl) * C);
+    __syncthreads();
+  }
+  grid_barrier(counter, gridDim.x);
+  {
+    __shared__ double swa[8], swb[8];
+    const int half = threadIdx.x >> 7, t = threadIdx.x & 127, lane = threadIdx.x & 31, wih = (threadIdx.x >> 5) & 3;
+    for (int cb = blockIdx.x * 2; cb < C; cb += gridDim.x * 2) {
+      const int c = cb + half; double tg = 0.0, tb = 0.0;
+      for (int g = 0; g < groups; ++g) {
+        double a = 0.0, b = 0.0;
+        if (c < C) { float va[5], vb[5];
+#pragma unroll
+          for (int q = 0; q < 5; ++q) { const int k = t + 128 * q; va[q] = k < S ? __ldcg(p1 + ((size_t)g * S + k) * C + c) : 0.f; vb[q] = k < S ? __ldcg(p2 + ((size_t)g * S + k) * C + c) : 0.f; }
+#pragma unroll
+          for (int q = 0; q < 5; ++q) { a += va[q]; b += vb[q]; } }
+        for (int m = 16; m; m >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, m); b += __shfl_xor_sync(0xffffffffu, b, m); }
+        __syncthreads();
+        if (lane == 0) { swa[half * 4 + wih] = a; swb[half * 4 + wih] = b; }
+        __syncthreads();
+        if (t == 0 && c < C) {
+          a = swa[half * 4] + swa[half * 4 + 1] + swa[half * 4 + 2] + swa[half * 4 + 3]; b = swb[half * 4] + swb[half * 4 + 1] + swb[half * 4 + 2] + swb[half * 4 + 3];
+          c1[g * C + c] = (float)(a / rows); c2[g * C + c] = (float)(b / rows); tb += a; tg += b;
+        }
+      }
+      if (want && t == 0 && c < C) { g_beta[c] += (float)tb; g_gamma[c] += (float)tg; }
+    }
+  }
+  if (!ei) return;
+  grid_barrier(counter, 2 * gridDim.x);
+  const size_t per_group = (size_t)rows * C8, total = per_group * groups;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  (void)total;
+  for (int g = 0; g < groups; ++g) {
+    float mu[8], is[8], ga[8], be[8], k1[8], k2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const int c = c8 * 8 + j, k = g * C + c; mu[j] = mean[k]; is[j] = invstd[k]; ga[j] = gamma[c]; be[j] = beta[c]; k1[j] = __ldcg(c1 + k); k2[j] = __ldcg(c2 + k); }
+    const uint4* xg = x + (size_t)g * per_group; const uint4* eg = eo + (size_t)g * per_group; uint4* og = ei + (size_t)g * per_group;
+    for (size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i0 < per_group; i0 += 4 * stride) {
+      uint4 ux[4], ue[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const size_t i = i0 + q * stride; if (i < per_group) { ux[q] = xg[i]; ue[q] = eg[i]; } }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const size_t i = i0 + q * stride; if (i >= per_group) break;
+        float xv[8], ev[8], o[8]; unpack8(ux[q], xv); unpack8(ue[q], ev);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float xh = (xv[j] - mu[j]) * is[j];
+          const float dy = ev[j] * act_grad_from_pre(act, fmaf(ga[j], xh, be[j]), alpha); o[j] = ga[j] * is[j] * (dy - k1[j] - xh * k2[j]); }
+        og[i] = pack8(o); }
+    }
+  }
+}
+
+static int coop_grid(const void* fn, int rows) {
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  int per_sm = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0);
+  if (per_sm < 1) return 0; if (per_sm > 3) per_sm = 3;
+  int g = sms * per_sm; int cap = rows / 8; if (cap < 1) cap = 1; if (g > cap) g = cap;
+  return g;
+}
+// Measured on B200 (round 1): the two software grid barriers + the serial channel pass cost ~15-20 us per launch, which is no better
+// than three small graph nodes (2.43-2.49 ms/step vs 2.31 ms), so the cooperative path is opt-in (B2G_FUSED_BN=1) until it is.
+bool k_bn_fused_ok(int prec, int C, int groups) {
+  static int on = -1; if (on < 0) { const char* e = getenv("B2G_FUSED_BN"); on = (e && e[0] == '1') ? 1 : 0; }
+  return on && vec_ok(prec, C) && (size_t)148 * 4 * C <= (size_t)SLICE_ELEMS;
+}
+// returns 0 on success
+int k_bn_fwd_fused(const void* x, void* y, int rows, int C, int groups, float* scratch, float* mean, float* invstd, const float* gamma, const float* beta,
+                   int act, float alpha, float eps, const float* run_mean, const float* run_var, float* g_mean, float* g_var, float decay, unsigned* counter, cudaStream_t s) {
+  int grid = coop_grid((const void*)bn_fwd_fused_kernel, rows); if (grid < 1) return -1;
+  if (cudaMemsetAsync(counter, 0, sizeof(unsigned), s) != cudaSuccess) return -1;
+  void* args[] = {(void*)&x, (void*)&y, (void*)&rows, (void*)&C, (void*)&groups, (void*)&scratch, (void*)&mean, (void*)&invstd, (void*)&gamma, (void*)&beta, (void*)&act, (void*)&alpha,
+                  (void*)&eps, (void*)&run_mean, (void*)&run_var, (void*)&g_mean, (void*)&g_var, (void*)&decay, (void*)&counter};
+  if (cudaLaunchCooperativeKernel((const void*)bn_fwd_fused_kernel, dim3(grid), dim3(256), args, 0, s) != cudaSuccess) return -1;
+  LAUNCHED(); return 0;
+}
+int k_bn_bwd_fused(const void* x, const void* eo, void* ei, int rows, int C, int groups, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                   int act, float alpha, float* scratch, float* g_gamma, float* g_beta, int want, unsigned* counter, cudaStream_t s) {
+  int grid = coop_grid((const void*)bn_bwd_fused_kernel, rows); if (grid < 1) return -1;
+  if (cudaMemsetAsync(counter, 0, sizeof(unsigned), s) != cudaSuccess) return -1;
+  void* args[] = {(void*)&x, (void*)&eo, (void*)&ei, (void*)&rows, (void*)&C, (void*)&groups, (void*)&mean, (void*)&invstd, (void*)&gamma, (void*)&beta, (void*)&act, (void*)&alpha,
+                  (void*)&scratch, (void*)&g_gamma, (void*)&g_beta, (void*)&want, (void*)&counter};
+  if (cudaLaunchCooperativeKernel((const void*)bn_bwd_fused_kernel, dim3(grid), dim3(256), args, 0, s) != cudaSuccess) return -1;
+  LAUNCHED(); return 0;
 }
 
 // ---------------------------------------------------------------- activations ---------------------------
