@@ -34,7 +34,25 @@ CONFIGS = {
     # name: (image size, z, nf, nc, per-GPU batch)
     "c2": dict(size=64, z=100, nf=64, nc=3, batch=128, desc="64x64x3 DCGAN z=100 (4-layer G/D) bf16 batch 128 per GPU"),
     "c4": dict(size=128, z=100, nf=64, nc=3, batch=32, desc="128x128x3 DCGAN (5-layer G/D) bf16 batch 32 per GPU"),
+    # BASELINE configs[4]: the README names no architecture; z=128 (tensor-core friendly; SURVEY assumed 100), hidden 1024-1024, d=256
+    "c5": dict(mlp=True, z=128, hidden=1024, d=256, batch=8192, desc="MLP-GAN d=256 z=128 hidden 1024-1024 bf16 batch 8192 per GPU"),
 }
+
+
+def build_specs(cfg):
+    from gan_deeplearning4j_b200 import models as m
+    if cfg.get("mlp"):
+        return m.mlp_generator(cfg["z"], cfg["hidden"], cfg["d"]), m.mlp_discriminator(cfg["d"], cfg["hidden"]), (cfg["z"],), (cfg["d"],)
+    return (m.dcgan_generator(cfg["size"], cfg["z"], cfg["nf"], cfg["nc"]), m.dcgan_discriminator(cfg["size"], cfg["nf"], cfg["nc"]),
+            (cfg["z"],), (cfg["nc"], cfg["size"], cfg["size"]))
+
+
+def synthetic(cfg, n, seed):
+    rng = np.random.default_rng(seed)
+    xshape = (n, cfg["d"]) if cfg.get("mlp") else (n, cfg["nc"], cfg["size"], cfg["size"])
+    f = np.float32
+    return [rng.uniform(-1, 1, xshape).astype(f), rng.uniform(-1, 1, (n, cfg["z"])).astype(f), rng.uniform(-1, 1, (n, cfg["z"])).astype(f),
+            (1 + 0.05 * rng.standard_normal((n, 1))).astype(f), (0.05 * rng.standard_normal((n, 1))).astype(f), np.ones((n, 1), f)]
 
 
 def load_peaks():
@@ -92,8 +110,8 @@ class ClockSampler:
 
 def algorithmic_flops_per_image(cfg):
     from gan_deeplearning4j_b200 import models as m
-    gf = m.forward_macs(m.dcgan_generator(cfg["size"], cfg["z"], cfg["nf"], cfg["nc"]), (cfg["z"],))
-    df = m.forward_macs(m.dcgan_discriminator(cfg["size"], cfg["nf"], cfg["nc"]), (cfg["nc"], cfg["size"], cfg["size"]))
+    gs, ds, gin, din = build_specs(cfg)
+    gf = m.forward_macs(gs, gin); df = m.forward_macs(ds, din)
     return 2.0 * (4 * gf + 8 * df), gf, df        # F = 2*(4*G_f + 8*D_f)
 
 
@@ -103,9 +121,12 @@ def algorithmic_flops_per_image(cfg):
 def cpu_step_rate(cfg, sample_batch, steps, warmup):
     from oracle import dl4j_oracle as o        # bench.py's cpu_baseline / reference legs may execute oracle/
     q = o.Quirks(xent_clip_eps=0.0)
-    G = o.dcgan_generator(cfg["size"], cfg["z"], cfg["nf"], cfg["nc"], dtype=np.float32, quirks=q)
-    D = o.dcgan_discriminator(cfg["size"], cfg["nf"], cfg["nc"], dtype=np.float32, quirks=q)
-    data = o.synthetic_batch(sample_batch, cfg["size"], cfg["nc"], cfg["z"], seed=666)
+    if cfg.get("mlp"):
+        G = o.mlp_generator(cfg["z"], cfg["hidden"], cfg["d"], dtype=np.float32, quirks=q); D = o.mlp_discriminator(cfg["d"], cfg["hidden"], dtype=np.float32, quirks=q)
+    else:
+        G = o.dcgan_generator(cfg["size"], cfg["z"], cfg["nf"], cfg["nc"], dtype=np.float32, quirks=q)
+        D = o.dcgan_discriminator(cfg["size"], cfg["nf"], cfg["nc"], dtype=np.float32, quirks=q)
+    data = synthetic(cfg, sample_batch, 666)
     for _ in range(warmup):
         o.gan_step(G, D, *data)
     t0 = time.perf_counter()
@@ -120,7 +141,7 @@ def run_reference(args, cfg, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = 32
+    sample = 2048 if cfg.get("mlp") else 32
     steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))
     ips, sec = cpu_step_rate(cfg, sample, steps, warmup)
     line = {
@@ -181,12 +202,11 @@ def run_ours(args, cfg, rank, world, local_rank):
         dist.broadcast_object_list(ids, src=0)
         ctx.comm_init(world, rank, ids[0])
     n = cfg["batch"]
-    gs = m.dcgan_generator(cfg["size"], cfg["z"], cfg["nf"], cfg["nc"])
-    ds = m.dcgan_discriminator(cfg["size"], cfg["nf"], cfg["nc"])
-    G = b.Net(ctx, gs, (cfg["z"],), max_batch=n, precision=b.BF16, xent_clip_eps=0.0, seed=666)
-    D = b.Net(ctx, ds, (cfg["nc"], cfg["size"], cfg["size"]), max_batch=2 * n, precision=b.BF16, xent_clip_eps=0.0, bn_groups=2, seed=667)
+    gs, ds, gin, din = build_specs(cfg)
+    G = b.Net(ctx, gs, gin, max_batch=n, precision=b.BF16, xent_clip_eps=0.0, seed=666)
+    D = b.Net(ctx, ds, din, max_batch=2 * n, precision=b.BF16, xent_clip_eps=0.0, bn_groups=2, seed=667)
     gan = b.Gan(G, D, fake_bn_train=False, use_cuda_graph=True)
-    data = o.synthetic_batch(n, cfg["size"], cfg["nc"], cfg["z"], seed=666 + rank)    # each rank draws its own slice
+    data = synthetic(cfg, n, 666 + rank)    # each rank draws its own slice
     pinned = [torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).pin_memory() for a in data]
     ptrs = [t.data_ptr() for t in pinned]
     h2d = int(sum(t.numel() * 4 for t in pinned)); d2h = 16
@@ -238,10 +258,11 @@ def run_ours(args, cfg, rank, world, local_rank):
         global_batch = n * world
         ips = global_batch * args.steps / (total_ms * 1e-3)
         e2e_ips = global_batch * args.steps / e2e_s
-        roof = dominant_kernel_roofline(b, ctx, cfg, n, peaks)
+        roof = dominant_kernel_roofline(b, ctx, CONFIGS["c2"] if cfg.get("mlp") else cfg, n if not cfg.get("mlp") else 128, peaks)
         step_tf = F * ips / world / 1e12
         cores = os.cpu_count() or 1
-        cpu_ips, cpu_sec = cpu_step_rate(cfg, 32, 4, 1)
+        cpu_sample = 2048 if cfg.get("mlp") else 32
+        cpu_ips, cpu_sec = cpu_step_rate(cfg, cpu_sample, 4, 1)
         line = {
             "metric": "images/sec (full G+D step)", "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -251,7 +272,7 @@ def run_ours(args, cfg, rank, world, local_rank):
             "step_roofline": {"algorithmic_gflop_per_image": F / 1e9, "achieved_tflops_per_gpu": step_tf, "peak": peaks["bf16_tflops_sustained"], "frac": step_tf / peaks["bf16_tflops_sustained"],
                               "peak_source": peaks["source"] + " (sustained cuBLAS bf16)"},
             "cpu_baseline": {"value": cpu_ips, "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": f"4 steps x batch 32 of the same workload, fp32 NumPy/OpenBLAS im2col+SGEMM restatement of DL4J nd4j-native, {cores} host threads"},
+                             "sample": f"4 steps x batch {cpu_sample} of the same workload, fp32 NumPy/OpenBLAS im2col+SGEMM restatement of DL4J nd4j-native, {cores} host threads"},
             "e2e": {"value": e2e_ips, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall,
             "losses": [float(v) for v in losses],

@@ -244,6 +244,10 @@ static int32_t net_alloc(b2g_net* n) {
       scratch = std::max(scratch, k_colsum_scratch_floats(std::max(l.oc, l.ic)));
       max_w = std::max(max_w, (size_t)l.n_W);
       l.needs_wt = n->prec == PREC_BF16 && n->ctx->tc_ok && tc_dgrad_supported(g) && !edge_deconv_small_c_supported(g);
+      // dense layers (1x1 geometry): the input gradient dx = dy . W is the tcgen05 fprop kernel on the transposed weight copy
+      if (n->prec == PREC_BF16 && n->ctx->tc_ok && g.KH == 1 && g.KW == 1 && g.H == 1 && g.W == 1 && !dense_small_o_supported(g)) {
+        ConvGeom t = g; t.C = g.O; t.O = g.C; if (tc_fprop_supported(t)) l.needs_wt = true;
+      }
     }
   }
   n->eps_elems = (size_t)R * max_act;
@@ -338,6 +342,13 @@ static int32_t gemm_dgrad(b2g_net* n, const LayerRT& l, const ConvGeom& g, const
   cudaStream_t s = n->ctx->stream; int wp; const void* w = w_ptr(n, l, &wp);
   if (edge_deconv_small_c_supported(g)) { k_edge_deconv_small_c(n->prec, wp, g, dy, w, bias, dx, act, alpha, s); return 0; }
   if (dense_small_o_supported(g) && !bias && act == ACT_IDENTITY) { k_dense_small_o_dgrad(n->prec, wp, g, dy, w, dx, s); return 0; }
+  if (n->prec == PREC_BF16 && n->ctx->tc_ok && l.needs_wt && g.KH == 1 && g.KW == 1 && g.H == 1 && g.W == 1) {
+    ConvGeom t = g; t.C = g.O; t.O = g.C;
+    if (tc_fprop_supported(t)) {
+      if (k_tc_fprop(t, (const __nv_bfloat16*)dy, n->shadow + l.off_Wt_bf, bias, (__nv_bfloat16*)dx, act, alpha, s) == 0) return 0;
+      return fail(B2G_ERR_CUDA, "tcgen05 dense dgrad launch failed");
+    }
+  }
   if (n->prec == PREC_BF16 && n->ctx->tc_ok && l.needs_wt && tc_dgrad_supported(g)) {
     if (k_tc_dgrad(g, (const __nv_bfloat16*)dy, n->shadow + l.off_Wt_bf, bias, (__nv_bfloat16*)dx, act, alpha, s) == 0) return 0;
     return fail(B2G_ERR_CUDA, "tcgen05 dgrad launch failed");

@@ -419,3 +419,65 @@ def test_edge_layers_dcgan_ends(b200, prec):
                     _assert_close_up_to_sign_flips(p_b[off:off + k], p_o[off:off + k], lr=1e-3)
                 off += k
     gan.close(); bG.close(); bD.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# C5: MLP-GAN (dense / OutputLayer path) and C4 (128x128, 5-stage) 
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_mlp_gan_step_matches_oracle(b200, prec):
+    """Dense layers + OutputLayer(XENT): fp32 to TOL; bf16 at tensor-core-eligible sizes (batch 128, widths multiple of 128) loosely."""
+    b, ctx = b200
+    from gan_deeplearning4j_b200 import models as m
+    P = b.BF16 if prec == "bf16" else b.FP32
+    n, z, hid, d = 128, 128, 256, 128
+    gs, ds = m.mlp_generator(z, hid, d, lr=1e-3), m.mlp_discriminator(d, hid, lr=1e-3)
+    q = o.Quirks(xent_clip_eps=0.0)
+    rng = np.random.default_rng(21)
+    G = oracle_from_specs(gs, (z,), quirks=q, seed=1); D = oracle_from_specs(ds, (d,), quirks=q, seed=2)
+    randomize(G, rng); randomize(D, rng)
+    bG = b.Net(ctx, gs, (z,), max_batch=n, precision=P, xent_clip_eps=0.0)
+    bD = b.Net(ctx, ds, (d,), max_batch=2 * n, precision=P, xent_clip_eps=0.0, bn_groups=2)
+    push_params(G, bG); push_params(D, bD)
+    x = rng.uniform(-1, 1, (n, d)); z_d = rng.uniform(-1, 1, (n, z)); z_g = rng.uniform(-1, 1, (n, z))
+    y_r = 1 + 0.05 * rng.standard_normal((n, 1)); y_f = 0.05 * rng.standard_normal((n, 1)); y_g = np.ones((n, 1))
+    # gradients of D on the real batch
+    s_o = D.compute_gradient_and_score(x, y_r); s_b = bD.compute_gradient_and_score(x, y_r)
+    tol = TOL if prec == "fp32" else 3e-2
+    assert abs(s_b - s_o) < tol * max(1.0, abs(s_o))
+    g_b, g_o = bD.gradients(), D.grads_flat()
+    err = np.linalg.norm(g_b - g_o) / np.linalg.norm(g_o)
+    assert err < (TOL if prec == "fp32" else 3e-2), err
+    gan = b.Gan(bG, bD, use_cuda_graph=False)
+    r = o.gan_step(G, D, x, z_d, z_g, y_r, y_f, y_g)
+    losses = gan.step(x, z_d, z_g, y_r, y_f, y_g)
+    want = np.array([r["loss_d_real"], r["loss_d_fake"], r["loss_g"]])
+    assert np.all(np.abs(losses - want) < tol * np.maximum(1.0, np.abs(want))), (losses, want)
+    if prec == "fp32":
+        _assert_close_up_to_sign_flips(bD.params(), D.params_flat(), lr=1e-3)
+        _assert_close_up_to_sign_flips(bG.params(), G.params_flat(), lr=1e-3)
+    gan.close(); bG.close(); bD.close()
+
+
+def test_full_size_c4_and_c5_steps_run(b200):
+    """BASELINE configs[3] (128x128x3, 32 per GPU) and configs[4] (MLP-GAN d=256, batch 8192) at full size: finite, learning, in range."""
+    b, ctx = b200
+    from gan_deeplearning4j_b200 import models as m
+    for name, gs, ds, gin, din, n in (("c4", m.dcgan_generator(128), m.dcgan_discriminator(128), (100,), (3, 128, 128), 32),
+                                     ("c5", m.mlp_generator(128, 1024, 256), m.mlp_discriminator(256, 1024), (128,), (256,), 8192)):
+        bG = b.Net(ctx, gs, gin, max_batch=n, precision=b.BF16, xent_clip_eps=0.0)
+        bD = b.Net(ctx, ds, din, max_batch=2 * n, precision=b.BF16, xent_clip_eps=0.0, bn_groups=2)
+        if name == "c4":
+            assert m.forward_macs(gs, gin) == 551092224 and m.forward_macs(ds, din) == 549470208      # SURVEY.md 8d
+        gan = b.Gan(bG, bD, use_cuda_graph=True)
+        rng = np.random.default_rng(1)
+        data = [rng.uniform(-1, 1, (n,) + din), rng.uniform(-1, 1, (n,) + gin), rng.uniform(-1, 1, (n,) + gin),
+                1 + 0.05 * rng.standard_normal((n, 1)), 0.05 * rng.standard_normal((n, 1)), np.ones((n, 1))]
+        gan.upload(*data)
+        first = None
+        for _ in range(5):
+            gan.step_resident(n); l = gan.losses(); assert np.all(np.isfinite(l)), (name, l)
+            first = l if first is None else first
+        assert l[0] + l[1] < first[0] + first[1], (name, first, l)
+        out = bG.output(data[1][:4]); assert np.all(np.isfinite(out)) and np.abs(out).max() <= 1.0
+        gan.close(); bG.close(); bD.close()
