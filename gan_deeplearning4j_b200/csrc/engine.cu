@@ -61,6 +61,7 @@ static int32_t nccl_load() {
 struct b2g_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;          // weight-gradient kernels run here, concurrently with the input-gradient chain
   cudaDeviceProp prop;
   void* comm = nullptr; int world = 1, rank = 0;
   bool tc_ok = false;
@@ -101,7 +102,9 @@ struct b2g_net {
   void* input = nullptr;               // T NHWC [max_rows][in_elems]
   float* stage_f32 = nullptr; size_t stage_floats = 0;   // host<->device fp32 staging (inputs, outputs, params)
   float* labels_dev = nullptr;         // [max_rows]
-  void *epsA = nullptr, *epsB = nullptr; size_t eps_elems = 0;
+  void *epsA = nullptr, *epsB = nullptr, *epsC = nullptr; size_t eps_elems = 0;
+  float* scratch2 = nullptr;           // split-K / colsum partials of the side stream
+  std::vector<cudaEvent_t> ev_fork, ev_done; cudaEvent_t ev_join = nullptr;
   float* scratch = nullptr; size_t scratch_floats = 0;
   float* loss_dev = nullptr;           // [8]
   unsigned* barrier_dev = nullptr;     // grid-barrier counter of the cooperative BN kernels
@@ -251,8 +254,11 @@ static int32_t net_alloc(b2g_net* n) {
     }
   }
   n->eps_elems = (size_t)R * max_act;
-  B2(dalloc(n, (char**)&n->epsA, ts * n->eps_elems)); B2(dalloc(n, (char**)&n->epsB, ts * n->eps_elems));
-  n->scratch_floats = scratch; B2(dalloc(n, &n->scratch, sizeof(float) * scratch));
+  B2(dalloc(n, (char**)&n->epsA, ts * n->eps_elems)); B2(dalloc(n, (char**)&n->epsB, ts * n->eps_elems)); B2(dalloc(n, (char**)&n->epsC, ts * n->eps_elems));
+  n->scratch_floats = scratch; B2(dalloc(n, &n->scratch, sizeof(float) * scratch)); B2(dalloc(n, &n->scratch2, sizeof(float) * scratch));
+  n->ev_fork.resize(n->L.size()); n->ev_done.resize(n->L.size());
+  for (size_t i = 0; i < n->L.size(); ++i) { CU(cudaEventCreateWithFlags(&n->ev_fork[i], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&n->ev_done[i], cudaEventDisableTiming)); }
+  CU(cudaEventCreateWithFlags(&n->ev_join, cudaEventDisableTiming));
   n->stage_floats = std::max((size_t)R * max_act, std::max((size_t)n->n_params, max_w)); B2(dalloc(n, &n->stage_f32, sizeof(float) * n->stage_floats));
   return 0;
 }
@@ -355,15 +361,14 @@ static int32_t gemm_dgrad(b2g_net* n, const LayerRT& l, const ConvGeom& g, const
   }
   k_simt_dgrad(n->prec, wp, g, dy, w, bias, dx, act, alpha, s); return 0;
 }
-static int32_t gemm_wgrad(b2g_net* n, const LayerRT& l, const ConvGeom& g, const void* x, const void* dy, float* dw) {
-  cudaStream_t s = n->ctx->stream;
-  if (edge_wgrad_small_cin_supported(g)) { k_edge_wgrad_small_cin(n->prec, g, x, dy, dw, n->scratch, 0, s); return 0; }
-  if (dense_small_o_supported(g)) { k_dense_small_o_wgrad(n->prec, g, x, dy, dw, n->scratch, 0, s); return 0; }
+static int32_t gemm_wgrad(b2g_net* n, const LayerRT& l, const ConvGeom& g, const void* x, const void* dy, float* dw, cudaStream_t s, float* scratch) {
+  if (edge_wgrad_small_cin_supported(g)) { k_edge_wgrad_small_cin(n->prec, g, x, dy, dw, scratch, 0, s); return 0; }
+  if (dense_small_o_supported(g)) { k_dense_small_o_wgrad(n->prec, g, x, dy, dw, scratch, 0, s); return 0; }
   if (n->prec == PREC_BF16 && n->ctx->tc_ok && tc_wgrad_supported(g)) {
-    if (k_tc_wgrad(g, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw, n->scratch, n->scratch_floats, 0, s) == 0) return 0;
+    if (k_tc_wgrad(g, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw, scratch, n->scratch_floats, 0, s) == 0) return 0;
     return fail(B2G_ERR_CUDA, "tcgen05 wgrad launch failed");
   }
-  k_simt_wgrad(n->prec, g, x, dy, dw, n->scratch, n->scratch_floats, 0, s); return 0;
+  k_simt_wgrad(n->prec, g, x, dy, dw, scratch, n->scratch_floats, 0, s); return 0;
 }
 
 // Runs layers [0, L) on `in` (T NHWC, rows examples). Returns pointer to the final activations.
@@ -410,9 +415,26 @@ static int32_t net_forward(b2g_net* n, const void* in, const FwdOpts& o, const v
 // Back-propagates eps (T, w.r.t. the logits when the last layer is OUTPUT/LOSS: dz from k_xent) through the net.
 // `eps` must live in n->epsA or be an external buffer; uses epsA/epsB ping-pong.
 static int32_t net_backward(b2g_net* n, const void* net_in, void* eps, int rows, int groups, bool want_wgrad, bool need_input_grad) {
-  cudaStream_t s = n->ctx->stream; const int R = rows;
+  cudaStream_t s = n->ctx->stream, s2 = n->ctx->side; const int R = rows;
   void* cur = eps;
-  auto other = [&](void* p) { return p == n->epsA ? n->epsB : n->epsA; };
+  // Three epsilon buffers in rotation.  Weight gradients are forked to the side stream (they only READ delta and the layer
+  // input), so the input-gradient chain -- the critical path -- never waits for them; a buffer still being read by a
+  // forked wgrad is not overwritten before that wgrad's event has fired.
+  void* bufs[3] = {n->epsA, n->epsB, n->epsC}; cudaEvent_t reader[3] = {nullptr, nullptr, nullptr}; bool forked = false;
+  auto other = [&](void* p) -> void* {
+    int pick = -1;
+    for (int k = 0; k < 3; ++k) if (bufs[k] != p && !reader[k]) { pick = k; break; }
+    if (pick < 0) for (int k = 0; k < 3; ++k) if (bufs[k] != p) { pick = k; break; }
+    if (reader[pick]) { cudaStreamWaitEvent(s, reader[pick], 0); reader[pick] = nullptr; }
+    return bufs[pick];
+  };
+  auto fork_wgrad = [&](int li, const void* delta) {      // side stream starts once delta is final
+    cudaEventRecord(n->ev_fork[li], s); cudaStreamWaitEvent(s2, n->ev_fork[li], 0); forked = true; (void)delta;
+  };
+  auto mark_reader = [&](int li, const void* delta) {
+    cudaEventRecord(n->ev_done[li], s2);
+    for (int k = 0; k < 3; ++k) if (bufs[k] == delta) reader[k] = n->ev_done[li];
+  };
   for (int i = (int)n->L.size() - 1; i >= 0; --i) {
     LayerRT& l = n->L[i]; const b2g_layer_desc& d = l.d;
     const void* lin = i == 0 ? net_in : n->L[i - 1].out;
@@ -425,8 +447,10 @@ static int32_t net_backward(b2g_net* n, const void* net_in, void* eps, int rows,
         ConvGeom g = l.geom; g.N = R;
         if (d.act != B2G_ACT_IDENTITY) k_act_bwd_from_output(n->prec, l.out, cur, cur, (size_t)R * l.out_elems, d.act, d.act_alpha, s);
         if (want_wgrad) {
-          B2(gemm_wgrad(n, l, g, lin, cur, n->grads + l.off_W));
-          if (l.off_b >= 0) k_colsum(n->prec, cur, R * l.oh * l.ow, l.oc, n->scratch, n->grads + l.off_b, 0, s);
+          fork_wgrad(i, cur);
+          B2(gemm_wgrad(n, l, g, lin, cur, n->grads + l.off_W, s2, n->scratch2));
+          if (l.off_b >= 0) k_colsum(n->prec, cur, R * l.oh * l.ow, l.oc, n->scratch2, n->grads + l.off_b, 0, s2);
+          mark_reader(i, cur);
         }
         if (need_in) { void* nx = other(cur); B2(gemm_dgrad(n, l, g, cur, nullptr, nx, ACT_IDENTITY, 0.f)); cur = nx; }
       } break;
@@ -434,8 +458,10 @@ static int32_t net_backward(b2g_net* n, const void* net_in, void* eps, int rows,
         ConvGeom g = l.geom; g.N = R;
         if (d.act != B2G_ACT_IDENTITY) k_act_bwd_from_output(n->prec, l.out, cur, cur, (size_t)R * l.out_elems, d.act, d.act_alpha, s);
         if (want_wgrad) {
-          B2(gemm_wgrad(n, l, g, /*conv input = deconv out grad*/ cur, /*conv dy = deconv input*/ lin, n->grads + l.off_W));
-          if (l.off_b >= 0) k_colsum(n->prec, cur, R * l.oh * l.ow, l.oc, n->scratch, n->grads + l.off_b, 0, s);
+          fork_wgrad(i, cur);
+          B2(gemm_wgrad(n, l, g, /*conv input = deconv out grad*/ cur, /*conv dy = deconv input*/ lin, n->grads + l.off_W, s2, n->scratch2));
+          if (l.off_b >= 0) k_colsum(n->prec, cur, R * l.oh * l.ow, l.oc, n->scratch2, n->grads + l.off_b, 0, s2);
+          mark_reader(i, cur);
         }
         if (need_in) { void* nx = other(cur); B2(gemm_fprop(n, l, g, cur, nullptr, nx, ACT_IDENTITY, 0.f)); cur = nx; }
       } break;
@@ -457,6 +483,7 @@ static int32_t net_backward(b2g_net* n, const void* net_in, void* eps, int rows,
     if (!need_in) { cur = nullptr; break; }
   }
   n->input_grad = cur;
+  if (forked) { cudaEventRecord(n->ev_join, s2); cudaStreamWaitEvent(s, n->ev_join, 0); }   // join before all-reduce / updater
   CHECK_KERNELS();
   return 0;
 }
@@ -490,6 +517,7 @@ extern "C" int32_t b2g_ctx_create(int32_t device, b2g_ctx** out) {
   CU(cudaGetDeviceProperties(&c->prop, device));
   if (c->prop.major != 10) { int mj = c->prop.major, mn = c->prop.minor; delete c; return fail(B2G_ERR_NO_DEVICE, "device is sm_%d%d; this library is built for sm_100a (B200) only", mj, mn); }
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
   c->tc_ok = tc_init() == 0;
   *out = c; return 0;
 }
@@ -497,6 +525,7 @@ extern "C" int32_t b2g_ctx_destroy(b2g_ctx* c) {
   if (!c) return 0; cudaSetDevice(c->device);
   if (c->comm && g_nccl.destroy) g_nccl.destroy(c->comm);
   if (c->t0) { cudaEventDestroy(c->t0); cudaEventDestroy(c->t1); } if (c->flush_buf) cudaFree(c->flush_buf);
+  if (c->side) cudaStreamDestroy(c->side);
   if (c->stream) cudaStreamDestroy(c->stream); delete c; return 0;
 }
 extern "C" int32_t b2g_timer_start(b2g_ctx* c) {
@@ -533,7 +562,11 @@ extern "C" int32_t b2g_net_create(b2g_ctx* ctx, const b2g_net_config* cfg, const
   if (r) { for (void* p : n->allocs) cudaFree(p); delete n; return r; }
   *out = n; return 0;
 }
-extern "C" int32_t b2g_net_destroy(b2g_net* n) { if (!n) return 0; cudaSetDevice(n->ctx->device); cudaStreamSynchronize(n->ctx->stream); for (void* p : n->allocs) cudaFree(p); delete n; return 0; }
+extern "C" int32_t b2g_net_destroy(b2g_net* n) {
+  if (!n) return 0; cudaSetDevice(n->ctx->device); cudaStreamSynchronize(n->ctx->stream); cudaStreamSynchronize(n->ctx->side);
+  for (auto e : n->ev_fork) if (e) cudaEventDestroy(e); for (auto e : n->ev_done) if (e) cudaEventDestroy(e); if (n->ev_join) cudaEventDestroy(n->ev_join);
+  for (void* p : n->allocs) cudaFree(p); delete n; return 0;
+}
 extern "C" int32_t b2g_net_num_params(b2g_net* n, int64_t* out) { if (!n || !out) return fail(B2G_ERR_ARG, "null"); *out = n->n_params; return 0; }
 extern "C" int32_t b2g_net_output_size(b2g_net* n, int64_t* out) { if (!n || !out) return fail(B2G_ERR_ARG, "null"); *out = (int64_t)n->L.back().out_elems; return 0; }
 extern "C" int32_t b2g_net_layer_output_size(b2g_net* n, int32_t layer, int64_t* out) {
