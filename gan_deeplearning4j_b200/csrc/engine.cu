@@ -62,6 +62,8 @@ struct b2g_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t side = nullptr;          // weight-gradient kernels run here, concurrently with the input-gradient chain
+  cudaStream_t side2 = nullptr;         // the generator's train-mode forward of the G step runs here, under the D step
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
   cudaDeviceProp prop;
   void* comm = nullptr; int world = 1, rank = 0;
   bool tc_ok = false;
@@ -111,6 +113,7 @@ struct b2g_net {
   double* l2_dev = nullptr;
   void* input_grad = nullptr;          // where the last backward left d(loss)/d(input), or null
   int last_rows = 0;
+  cudaStream_t fwd_stream = nullptr;   // when set, net_forward launches here instead of ctx->stream
   std::vector<void*> allocs;
 };
 
@@ -334,8 +337,9 @@ static const void* w_ptr(const b2g_net* n, const LayerRT& l, int* wprec) {
   *wprec = PREC_F32; return n->params + l.off_W;
 }
 
+static inline cudaStream_t fstream(const b2g_net* n) { return n->fwd_stream ? n->fwd_stream : n->ctx->stream; }
 static int32_t gemm_fprop(b2g_net* n, const LayerRT& l, const ConvGeom& g, const void* x, const float* bias, void* out, int act, float alpha) {
-  cudaStream_t s = n->ctx->stream; int wp; const void* w = w_ptr(n, l, &wp);
+  cudaStream_t s = fstream(n); int wp; const void* w = w_ptr(n, l, &wp);
   if (edge_conv_small_cin_supported(g)) { k_edge_conv_small_cin(n->prec, wp, g, x, w, bias, out, act, alpha, s); return 0; }
   if (dense_small_o_supported(g)) { k_dense_small_o_fwd(n->prec, wp, g, x, w, bias, out, act, alpha, s); return 0; }
   if (n->prec == PREC_BF16 && n->ctx->tc_ok && tc_fprop_supported(g)) {
@@ -345,7 +349,7 @@ static int32_t gemm_fprop(b2g_net* n, const LayerRT& l, const ConvGeom& g, const
   k_simt_fprop(n->prec, wp, g, x, w, bias, out, act, alpha, s); return 0;
 }
 static int32_t gemm_dgrad(b2g_net* n, const LayerRT& l, const ConvGeom& g, const void* dy, const float* bias, void* dx, int act, float alpha) {
-  cudaStream_t s = n->ctx->stream; int wp; const void* w = w_ptr(n, l, &wp);
+  cudaStream_t s = fstream(n); int wp; const void* w = w_ptr(n, l, &wp);
   if (edge_deconv_small_c_supported(g)) { k_edge_deconv_small_c(n->prec, wp, g, dy, w, bias, dx, act, alpha, s); return 0; }
   if (dense_small_o_supported(g) && !bias && act == ACT_IDENTITY) { k_dense_small_o_dgrad(n->prec, wp, g, dy, w, dx, s); return 0; }
   if (n->prec == PREC_BF16 && n->ctx->tc_ok && l.needs_wt && g.KH == 1 && g.KW == 1 && g.H == 1 && g.W == 1) {
@@ -373,7 +377,7 @@ static int32_t gemm_wgrad(b2g_net* n, const LayerRT& l, const ConvGeom& g, const
 
 // Runs layers [0, L) on `in` (T NHWC, rows examples). Returns pointer to the final activations.
 static int32_t net_forward(b2g_net* n, const void* in, const FwdOpts& o, const void** result) {
-  cudaStream_t s = n->ctx->stream;
+  cudaStream_t s = fstream(n);
   if (o.rows > n->max_rows || o.rows < 1) return fail(B2G_ERR_SHAPE, "batch %d outside [1, max_batch=%d]", o.rows, n->max_rows);
   if (o.groups < 1 || o.rows % o.groups) return fail(B2G_ERR_SHAPE, "batch %d not divisible into %d groups", o.rows, o.groups);
   const int R = o.rows; const void* cur = in;
@@ -517,7 +521,8 @@ extern "C" int32_t b2g_ctx_create(int32_t device, b2g_ctx** out) {
   CU(cudaGetDeviceProperties(&c->prop, device));
   if (c->prop.major != 10) { int mj = c->prop.major, mn = c->prop.minor; delete c; return fail(B2G_ERR_NO_DEVICE, "device is sm_%d%d; this library is built for sm_100a (B200) only", mj, mn); }
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking)); CU(cudaStreamCreateWithFlags(&c->side2, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
   c->tc_ok = tc_init() == 0;
   *out = c; return 0;
 }
@@ -525,7 +530,7 @@ extern "C" int32_t b2g_ctx_destroy(b2g_ctx* c) {
   if (!c) return 0; cudaSetDevice(c->device);
   if (c->comm && g_nccl.destroy) g_nccl.destroy(c->comm);
   if (c->t0) { cudaEventDestroy(c->t0); cudaEventDestroy(c->t1); } if (c->flush_buf) cudaFree(c->flush_buf);
-  if (c->side) cudaStreamDestroy(c->side);
+  if (c->side) cudaStreamDestroy(c->side); if (c->side2) cudaStreamDestroy(c->side2); if (c->ev_a) cudaEventDestroy(c->ev_a); if (c->ev_b) cudaEventDestroy(c->ev_b);
   if (c->stream) cudaStreamDestroy(c->stream); delete c; return 0;
 }
 extern "C" int32_t b2g_timer_start(b2g_ctx* c) {
@@ -726,6 +731,14 @@ static int32_t gan_step_body(b2g_gan* g, int N) {
   void* fake_dst = (char*)D->input + ts * (size_t)N * D->in_elems;
   FwdOpts og{N, 1, g->cfg.fake_bn_train != 0, false, fake_dst};
   B2(net_forward(G, g->z_d, og, nullptr));
+  // 3a (hoisted). The generator's train-mode forward on z_g depends only on G's parameters, which the D step does not touch:
+  // run it on a second stream underneath the whole D step.
+  cudaStream_t s3 = G->ctx->side2;
+  CU(cudaEventRecord(G->ctx->ev_a, s)); CU(cudaStreamWaitEvent(s3, G->ctx->ev_a, 0));
+  CU(cudaMemsetAsync(G->grads, 0, sizeof(float) * G->n_params, s3));
+  const void* xg = nullptr; FwdOpts og2{N, 1, true, true, nullptr};
+  G->fwd_stream = s3; int32_t rg = net_forward(G, g->z_g, og2, &xg); G->fwd_stream = nullptr; B2(rg);
+  CU(cudaEventRecord(G->ctx->ev_b, s3));
   // 2. D update on (x_real, y_real) | (x_fake, y_fake): two BN groups, one batched pass (J:414-426)
   CU(cudaMemsetAsync(D->grads, 0, sizeof(float) * D->n_params, s));
   const void* logits = nullptr; FwdOpts od{2 * N, 2, true, true, nullptr};
@@ -735,9 +748,7 @@ static int32_t gan_step_body(b2g_gan* g, int N) {
   B2(net_allreduce_grads(D));
   B2(net_update(D, 2 * N));
   // 3. G update through D on (z_g, y_gen) (J:465-471); D's parameters / running stats / updater state untouched
-  CU(cudaMemsetAsync(G->grads, 0, sizeof(float) * G->n_params, s));
-  const void* xg = nullptr; FwdOpts og2{N, 1, true, true, nullptr};
-  B2(net_forward(G, g->z_g, og2, &xg));
+  CU(cudaStreamWaitEvent(s, G->ctx->ev_b, 0));
   FwdOpts od2{N, 1, true, false, nullptr};
   B2(net_forward(D, xg, od2, &logits));
   k_xent(D->prec, logits, g->y_g, D->epsA, g->loss_dev + 2, N, 1, D->cfg.xent_clip_eps, s);
