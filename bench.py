@@ -267,7 +267,7 @@ def run_ours(args, cfg, rank, world, local_rank):
             "metric": "images/sec (full G+D step)", "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": cfg["desc"], "global_batch": global_batch, "parallelism": f"dp{world}", "l2": "flushed between steps (256 MiB memset, outside the per-step CUDA-event brackets)",
-                       "fake_bn": "inference (gen.output, J:420)", "cuda_graph": world == 1, "step": "G(z_d) -> D update on real|fake -> G update through D"},
+                       "fake_bn": "inference (gen.output, J:420)", "cuda_graph": os.environ.get("B2G_GRAPH_NCCL", "1") != "0" or world == 1, "step": "G(z_d) -> D update on real|fake -> G update through D"},
             "roofline": roof,
             "step_roofline": {"algorithmic_gflop_per_image": F / 1e9, "achieved_tflops_per_gpu": step_tf, "peak": peaks["bf16_tflops_sustained"], "frac": step_tf / peaks["bf16_tflops_sustained"],
                               "peak_source": peaks["source"] + " (sustained cuBLAS bf16)"},

@@ -14,6 +14,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -720,7 +721,7 @@ struct b2g_gan {
   float* loss_dev = nullptr;              // [4]: d_real_sum, d_fake_sum, g_sum
   float* stage = nullptr; size_t stage_floats = 0;
   cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; int graph_batch = 0; uint64_t graph_launches = 0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr; float last_ms = 0.f; int last_batch = 1;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr; float last_ms = 0.f; int last_batch = 1; bool nccl_warm = false;
   std::vector<void*> allocs;
 };
 
@@ -804,7 +805,11 @@ extern "C" int32_t b2g_gan_upload(b2g_gan* g, const float* x_real, const float* 
 extern "C" int32_t b2g_gan_step_resident(b2g_gan* g, int32_t batch) {
   if (!g) return fail(B2G_ERR_ARG, "null"); if (batch < 1 || batch > g->N) return fail(B2G_ERR_SHAPE, "batch %d outside [1,%d]", batch, g->N);
   b2g_ctx* c = g->G->ctx; cudaStream_t s = c->stream; CU(cudaSetDevice(c->device));
-  bool use_graph = g->cfg.use_cuda_graph && !c->comm;
+  // With a communicator the first step runs eagerly (NCCL connects lazily on its first collective); after that the whole step,
+  // the two ncclAllReduce calls included, is captured and replayed like the single-GPU one.  B2G_GRAPH_NCCL=0 keeps it eager.
+  static int graph_nccl = -1; if (graph_nccl < 0) { const char* e = getenv("B2G_GRAPH_NCCL"); graph_nccl = (e && e[0] == '0') ? 0 : 1; }
+  bool use_graph = g->cfg.use_cuda_graph && (!c->comm || (graph_nccl && g->nccl_warm));
+  if (c->comm) g->nccl_warm = true;
   g->last_batch = batch;
   CU(cudaEventRecord(g->ev0, s));
   if (!use_graph) { B2(gan_step_body(g, batch)); }

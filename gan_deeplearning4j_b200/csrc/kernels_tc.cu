@@ -323,8 +323,9 @@ int k_tc_dgrad(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat16* 
 // slow dimension of both NHWC operands, so both are fed to tcgen05.mma as MN-major tiles: a TMA box of
 // {64 channels, 64 pixels} lands as [pixel rows][128 B], which IS the canonical 128B-swizzled MN-major layout
 // (8-pixel groups 1024 B apart = SBO, 64-channel blocks one box apart = LBO).  No transposes anywhere.
-// CTA tile: 128 output channels (o) x BNW input channels (c) for one filter tap, over a split of the pixel range;
-// fp32 partials go to scratch[split] and are summed in fixed order (deterministic).
+// CTA tile: 128 output channels (o) x BNW columns of the flattened (tap, c) axis -- i.e. BNW/64 sixty-four-channel blocks that may
+// belong to different filter taps, so one dy tile in smem feeds several taps (halves / quarters the L2 traffic of dy) -- over a
+// split of the pixel range; fp32 partials go to scratch[split] and are summed in fixed order (deterministic).
 struct TcWgradParams {
   int Nt, Ht, Wt;          // K-block = 64 pixels of the dy grid = Nt images x Ht rows x Wt cols
   int tiles_y;             // OH / Ht
@@ -353,8 +354,7 @@ __global__ void __launch_bounds__(192) tc_wgrad_kernel(const __grid_constant__ C
   const uint32_t bar_full = smem_base + S::BAR_OFF, bar_empty = bar_full + 8 * STAGES, bar_accum = bar_empty + 8 * STAGES;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + S::BAR_OFF + 8 * (2 * STAGES + 1));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int split = blockIdx.x, tap = blockIdx.y / p.c_tiles, c0 = (blockIdx.y % p.c_tiles) * BNW, o0 = blockIdx.z * 128;
-  const int r = tap / p.KW, sx = tap % p.KW;
+  const int split = blockIdx.x, col0 = blockIdx.y * BNW, o0 = blockIdx.z * 128;     // col = tap*C + c
   const int kb_beg = split * p.kb_per_split, kb_end = min(p.kb_total, kb_beg + p.kb_per_split);
   const int num_kb = max(0, kb_end - kb_beg);
 
@@ -382,8 +382,10 @@ __global__ void __launch_bounds__(192) tc_wgrad_kernel(const __grid_constant__ C
         tma_load_2d(a, &tmDy, bar_full + 8 * s, o0, kb * 64);
         tma_load_2d(a + 8192, &tmDy, bar_full + 8 * s, o0 + 64, kb * 64);
 #pragma unroll
-        for (int j = 0; j < BNW / 64; ++j)
-          tma_load_4d(b + j * 8192, &tmX, bar_full + 8 * s, c0 + j * 64, -p.PW + sx, y0 * p.SH - p.PH + r, n0);
+        for (int j = 0; j < BNW / 64; ++j) {
+          const int col = col0 + j * 64, tap = col / p.C, c0 = col % p.C, r = tap / p.KW, sx = tap % p.KW;
+          tma_load_4d(b + j * 8192, &tmX, bar_full + 8 * s, c0, -p.PW + sx, y0 * p.SH - p.PH + r, n0);
+        }
       }
     }
   } else if (warp == 1) {
@@ -403,7 +405,7 @@ __global__ void __launch_bounds__(192) tc_wgrad_kernel(const __grid_constant__ C
     }
   } else {
     const int q = warp & 3, row = q * 32 + lane;
-    float* orow = p.out + (size_t)split * p.split_stride + ((size_t)(o0 + row) * p.taps + tap) * p.C + c0;
+    float* orow = p.out + (size_t)split * p.split_stride + (size_t)(o0 + row) * p.taps * p.C + col0;
     if (num_kb > 0) {
       mbar_wait(bar_accum, 0);
       tc_fence_after();
@@ -425,15 +427,15 @@ __global__ void __launch_bounds__(192) tc_wgrad_kernel(const __grid_constant__ C
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, BNW < 32 ? 32 : BNW); }
 }
 
-static int wgrad_bnw(int C) { return C % 256 == 0 ? 256 : C % 128 == 0 ? 128 : C % 64 == 0 ? 64 : 0; }
+static int wgrad_bnw(const ConvGeom& g) { if (g.C % 64) return 0; const long cols = (long)g.KH * g.KW * g.C; return cols % 256 == 0 ? 256 : cols % 128 == 0 ? 128 : 64; }
 static int tc_wgrad_splits(const ConvGeom& g) {
-  const int bnw = wgrad_bnw(g.C); if (!bnw) return 1;
-  long tiles = (long)(g.O / 128) * g.KH * g.KW * (g.C / bnw), kbt = (long)g.N * g.OH * g.OW / 64;
+  const int bnw = wgrad_bnw(g); if (!bnw) return 1;
+  long tiles = (long)(g.O / 128) * (g.KH * g.KW * g.C / bnw), kbt = (long)g.N * g.OH * g.OW / 64;
   long sp = (296 + tiles - 1) / tiles, cap = kbt / 8; if (cap < 1) cap = 1; if (sp > cap) sp = cap; if (sp < 1) sp = 1; return (int)sp;
 }
 bool tc_wgrad_supported(const ConvGeom& g) {
   int a, b, c;
-  return g.O % 128 == 0 && wgrad_bnw(g.C) != 0 && g.SH >= 1 && g.SH <= 2 && g.SW == g.SH && ((long)g.N * g.OH * g.OW) % 64 == 0 &&
+  return g.O % 128 == 0 && wgrad_bnw(g) != 0 && g.SH >= 1 && g.SH <= 2 && g.SW == g.SH && ((long)g.N * g.OH * g.OW) % 64 == 0 &&
          pick_row_tile(g.N, g.OH, g.OW, 64, &a, &b, &c) && c * g.SW <= 256 && b * g.SH <= 256;
 }
 size_t k_tc_wgrad_scratch_floats(const ConvGeom& g) {
@@ -454,11 +456,11 @@ static int launch_wgrad(const CUtensorMap& tmDy, const CUtensorMap& tmX, const T
 int k_tc_wgrad(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* scratch, size_t scratch_floats, int accumulate, cudaStream_t s) {
   TcWgradParams p{};
   if (!pick_row_tile(g.N, g.OH, g.OW, 64, &p.Nt, &p.Ht, &p.Wt)) return -1;
-  const int BNW = wgrad_bnw(g.C); const size_t n = (size_t)g.O * g.KH * g.KW * g.C;
+  const int BNW = wgrad_bnw(g); const size_t n = (size_t)g.O * g.KH * g.KW * g.C;
   int splits = tc_wgrad_splits(g);
   if ((size_t)splits * n > scratch_floats) return -5;
   p.tiles_y = g.OH / p.Ht; p.KW = g.KW; p.SH = g.SH; p.SW = g.SW; p.PH = g.PH; p.PW = g.PW; p.taps = g.KH * g.KW; p.C = g.C;
-  p.kb_total = (int)((long)g.N * g.OH * g.OW / 64); p.kb_per_split = (p.kb_total + splits - 1) / splits; p.c_tiles = g.C / BNW;
+  p.kb_total = (int)((long)g.N * g.OH * g.OW / 64); p.kb_per_split = (p.kb_total + splits - 1) / splits; p.c_tiles = 0;
   p.out = scratch; p.split_stride = n;
   CUtensorMap tmDy, tmX;
   { cuuint64_t dims[2] = {(cuuint64_t)g.O, (cuuint64_t)g.N * g.OH * g.OW}; cuuint64_t strides[1] = {(cuuint64_t)g.O * 2};
@@ -468,7 +470,7 @@ int k_tc_wgrad(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* d
     cuuint64_t strides[3] = {(cuuint64_t)g.C * 2, (cuuint64_t)g.W * g.C * 2, (cuuint64_t)g.H * g.W * g.C * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)(p.Wt * g.SW), (cuuint32_t)(p.Ht * g.SH), (cuuint32_t)p.Nt}; cuuint32_t es[4] = {1, (cuuint32_t)g.SW, (cuuint32_t)g.SH, 1};
     if (make_map_bf16(&tmX, x, 4, dims, strides, box, es)) return -1; }
-  dim3 grid((unsigned)splits, (unsigned)(p.taps * p.c_tiles), (unsigned)(g.O / 128));
+  dim3 grid((unsigned)splits, (unsigned)(p.taps * g.C / BNW), (unsigned)(g.O / 128));
   int rc;
   switch (BNW) {
     case 64: rc = launch_wgrad<64, 4>(tmDy, tmX, p, grid, s); break;
