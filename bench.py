@@ -72,7 +72,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -180,7 +180,12 @@ def dominant_kernel_roofline(b, ctx, cfg, batch, peaks):
             res[name + "_error"] = str(e)[:120]
     ms = res.get("tcgen05") or res.get("simt")
     ach = flops / (ms * 1e-3) / 1e12
-    return {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": None,
+    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the committed `ncu --set full` capture
+    # (profiles/r01_ncu_tc_conv.md, tc_conv_kernel<128,3> grid (512,1,1)): 33.87 MB read + 0.004 MB written per launch (the bf16 output
+    # stays in L2); algorithmic bytes = 33.55 MB input + 16.78 MB output + 0.26 MB weights.
+    traffic = 33.865472e6 + 3.84e3 if (res.get("tcgen05") and n == 256 and size == 64 and nf == 64) else None
+    return {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": traffic,
+            "traffic_unit": "bytes/launch (ncu dram read+write)", "algorithmic_bytes": n * h * h * nf * 2 + out_size * 2 + 2 * nf * 16 * nf * 2,
             "kernel": ("tcgen05 " if res.get("tcgen05") else "SIMT ") + f"conv fprop {n}x{h}x{h}x{nf} -> {2 * nf}, 4x4 s2 p1 (D2, D-step batch)",
             "flops_per_launch": flops, "ms_per_launch": ms, "peak_source": peaks["source"] + " (burst cuBLAS bf16)", "detail_ms": res}
 
@@ -286,7 +291,7 @@ def run_ours(args, cfg, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))

@@ -115,6 +115,7 @@ struct b2g_net {
   void* input_grad = nullptr;          // where the last backward left d(loss)/d(input), or null
   int last_rows = 0;
   cudaStream_t fwd_stream = nullptr;   // when set, net_forward launches here instead of ctx->stream
+  bool grad_allreduce = true;          // false: parameter-averaging mode (b2g_net_average_parameters)
   std::vector<void*> allocs;
 };
 
@@ -494,13 +495,14 @@ static int32_t net_backward(b2g_net* n, const void* net_in, void* eps, int rows,
 }
 
 static int32_t net_allreduce_grads(b2g_net* n) {
-  b2g_ctx* c = n->ctx; if (!c->comm || c->world == 1) return 0;
+  b2g_ctx* c = n->ctx; if (!c->comm || c->world == 1 || !n->grad_allreduce) return 0;
   NC(g_nccl.ar(n->grads, n->grads, (size_t)n->n_params, /*ncclFloat32*/ 7, /*ncclSum*/ 0, c->comm, c->stream));
   return 0;
 }
 static int32_t net_update(b2g_net* n, int mb_local) {
   cudaStream_t s = n->ctx->stream; int W = n->ctx->comm ? n->ctx->world : 1;
   // BN running-stat pseudo-gradients are exempt from the minibatch division; under DP they are averaged over ranks
+  if (!n->grad_allreduce) W = 1;     // parameter-averaging mode: purely local update
   k_updater(n->params, n->grads, n->st0, n->st1, n->segs_dev, n->chunk_seg_dev, n->chunk_off_dev, n->nchunks, 1.0f / ((float)mb_local * W), 1.0f / (float)W, n->step_dev, n->shadow, s);
   k_inc_int(n->step_dev, s);
   net_refresh_shadow(n, -1, true);
@@ -854,6 +856,16 @@ extern "C" int32_t b2g_ctx_comm_init(b2g_ctx* c, int32_t world, int32_t rank, co
   NC(g_nccl.init(&c->comm, world, id, rank)); c->world = world; c->rank = rank; return 0;
 }
 extern "C" int32_t b2g_ctx_comm_destroy(b2g_ctx* c) { if (c && c->comm) { g_nccl.destroy(c->comm); c->comm = nullptr; c->world = 1; c->rank = 0; } return 0; }
+extern "C" int32_t b2g_net_set_grad_allreduce(b2g_net* n, int32_t enabled) { if (!n) return fail(B2G_ERR_ARG, "null"); n->grad_allreduce = enabled != 0; return 0; }
+extern "C" int32_t b2g_net_average_parameters(b2g_net* n) {
+  if (!n) return fail(B2G_ERR_ARG, "null"); b2g_ctx* c = n->ctx; CU(cudaSetDevice(c->device));
+  if (!c->comm || c->world == 1) return 0;
+  const float inv = 1.0f / (float)c->world; cudaStream_t s = c->stream;
+  float* bufs[3] = {n->params, n->st0, n->st1};
+  for (float* b : bufs) { NC(g_nccl.ar(b, b, (size_t)n->n_params, 7, 0, c->comm, s)); k_scale_f32(b, inv, (size_t)n->n_params, s); }
+  net_refresh_shadow(n);
+  CU(cudaStreamSynchronize(s)); return 0;
+}
 extern "C" int32_t b2g_ctx_allreduce_test(b2g_ctx* c, float* host, int64_t n) {
   if (!c || !host || n < 1) return fail(B2G_ERR_ARG, "null"); if (!c->comm) return fail(B2G_ERR_NCCL, "no communicator"); CU(cudaSetDevice(c->device));
   float* d = nullptr; CU(cudaMalloc(&d, sizeof(float) * n));

@@ -97,6 +97,7 @@ void k_updater(float* params, const float* grads, float* st0, float* st1, const 
 static const int UPD_CHUNK = 4096;
 void k_inc_int(int* p, cudaStream_t s);          // *p += 1 (iteration counters live on the device so CUDA graphs replay)
 void k_fill_f32(float* p, float v, size_t n, cudaStream_t s);
+void k_scale_f32(float* p, float v, size_t n, cudaStream_t s);
 
 // ---- GEMM-shaped kernels, SIMT (fp32 FMA) -----------------------------------------------------------------
 // fprop:  out[m][o] = act(sum_k A[m][k] w[o][k] + bias[o]),  m=(n,oy,ox), k=(r,s,c);  w layout [O][KH][KW][C]

@@ -759,6 +759,10 @@ void k_inc_int(int* p, cudaStream_t s) { inc_int_kernel<<<1, 1, 0, s>>>(p); LAUN
 __global__ void fill_f32_kernel(float* p, float v, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
+__global__ void scale_f32_kernel(float* p, float v, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] *= v;
+}
+void k_scale_f32(float* p, float v, size_t n, cudaStream_t s) { if (!n) return; scale_f32_kernel<<<ew_blocks(n), 256, 0, s>>>(p, v, n); LAUNCHED(); }
 void k_fill_f32(float* p, float v, size_t n, cudaStream_t s) { if (!n) return; fill_f32_kernel<<<ew_blocks(n), 256, 0, s>>>(p, v, n); LAUNCHED(); }
 
 }  // namespace b2g

@@ -196,6 +196,14 @@ class Net:
         check(self.lib.b2g_net_fit(self.h, _fp(x), _fp(y), x.shape[0], C.byref(s)))
         return s.value
 
+    def set_grad_allreduce(self, enabled: bool):
+        """False = the reference's parameter-averaging mode: fit() updates locally, average_parameters() synchronises."""
+        check(self.lib.b2g_net_set_grad_allreduce(self.h, int(enabled)))
+
+    def average_parameters(self):
+        """ParameterAveragingTrainingMaster: params and updater state <- mean over ranks (J:325-330)."""
+        check(self.lib.b2g_net_average_parameters(self.h))
+
     def input_gradient(self, batch: int) -> np.ndarray:
         out = np.empty((batch, int(np.prod(self.input_shape))), np.float32)
         check(self.lib.b2g_net_get_input_gradient(self.h, batch, _fp(out)))

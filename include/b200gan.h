@@ -181,6 +181,12 @@ int32_t b2g_gan_last_step_ms(b2g_gan* gan, float* ms);
 int32_t b2g_comm_unique_id(void* id128);
 int32_t b2g_ctx_comm_init(b2g_ctx* ctx, int32_t world, int32_t rank, const void* id128);
 int32_t b2g_ctx_comm_destroy(b2g_ctx* ctx);
+/* ParameterAveragingTrainingMaster semantics (J:325-330; Python/gan.ipynb:182-186): Theta <- mean over ranks of theta_i, and
+ * likewise the updater state.  The host calls it every `averagingFrequency` local b2g_net_fit minibatches on nets whose gradient
+ * all-reduce is switched off (b2g_net_set_grad_allreduce(net, 0)) -- the reference's own data-parallel rule, kept as an option
+ * next to the per-update gradient all-reduce north_star mandates. */
+int32_t b2g_net_set_grad_allreduce(b2g_net* net, int32_t enabled);
+int32_t b2g_net_average_parameters(b2g_net* net);
 /* all-reduce an arbitrary device float buffer on the ctx stream (tests) */
 int32_t b2g_ctx_allreduce_test(b2g_ctx* ctx, float* host_inout, int64_t n);
 

@@ -54,5 +54,7 @@ FN(ganStep)(JNIEnv_*, jclass, jlong gan, jlong xReal, jlong zD, jlong zG, jlong 
   return b2g_gan_step(P(b2g_gan*, gan), P(const float*, xReal), P(const float*, zD), P(const float*, zG), P(const float*, yReal), P(const float*, yFake),
                       P(const float*, yGen), batch, P(float*, lossesAddr));
 }
+FN(netSetGradAllreduce)(JNIEnv_*, jclass, jlong net, jint enabled) { return b2g_net_set_grad_allreduce(P(b2g_net*, net), enabled); }
+FN(netAverageParameters)(JNIEnv_*, jclass, jlong net) { return b2g_net_average_parameters(P(b2g_net*, net)); }
 FN(commUniqueId)(JNIEnv_*, jclass, jlong id128Addr) { return b2g_comm_unique_id(P(void*, id128Addr)); }
 FN(ctxCommInit)(JNIEnv_*, jclass, jlong ctx, jint world, jint rank, jlong id128Addr) { return b2g_ctx_comm_init(P(b2g_ctx*, ctx), world, rank, P(const void*, id128Addr)); }

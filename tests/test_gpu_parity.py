@@ -481,3 +481,40 @@ def test_full_size_c4_and_c5_steps_run(b200):
         assert l[0] + l[1] < first[0] + first[1], (name, first, l)
         out = bG.output(data[1][:4]); assert np.all(np.isfinite(out)) and np.abs(out).max() <= 1.0
         gan.close(); bG.close(); bD.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# error behaviour at the boundary (DL4J throws; the C-ABI returns codes that the mirrors raise)
+# ------------------------------------------------------------------------------------------------
+def test_boundary_error_codes(b200):
+    b, ctx = b200
+    from gan_deeplearning4j_b200 import models as m
+    specs = m.dcgan_discriminator(16, 8, 3)
+    net = b.Net(ctx, specs, (3, 16, 16), max_batch=4, precision=b.FP32)
+    with pytest.raises(b.B200GanError) as e:                     # batch larger than max_batch
+        net.output(np.zeros((5, 3, 16, 16), np.float32))
+    assert e.value.code == -2
+    with pytest.raises(b.B200GanError) as e:                     # unknown layer
+        net.set_param("no_such_layer", "W", np.zeros(3, np.float32))
+    assert e.value.code == -1
+    with pytest.raises(b.B200GanError) as e:                     # wrong element count (DL4J: shape mismatch on setParam)
+        net.set_param("dis_conv_1", "W", np.zeros(7, np.float32))
+    assert e.value.code == -2
+    with pytest.raises(b.B200GanError) as e:                     # BN has no "W"
+        net.get_param("dis_bn_2", "W", 4)
+    assert e.value.code == -1
+    with pytest.raises(b.B200GanError) as e:                     # nIn that contradicts the incoming shape
+        b.Net(ctx, [{"type": "conv2d", "name": "c", "n_in": 5, "n_out": 4, "kernel": (3, 3)}], (3, 8, 8), max_batch=2)
+    assert e.value.code == -2
+    with pytest.raises(b.B200GanError) as e:                     # dense on a convolutional activation without CnnToFeedForward
+        b.Net(ctx, [{"type": "dense", "name": "d", "n_out": 4}], (3, 8, 8), max_batch=2)
+    assert e.value.code == -2
+    with pytest.raises(b.B200GanError) as e:                     # fit needs a loss-bearing last layer
+        b.Net(ctx, [{"type": "dense", "name": "d", "n_out": 4}], (8,), max_batch=2).fit(np.zeros((2, 8)), np.zeros((2, 1)))
+    assert e.value.code == -6
+    # ragged batches: every batch size from 1 up to max works and matches the oracle (falls back to non-tiled kernels)
+    onet = oracle_from_specs(specs, (3, 16, 16)); push_params(onet, net)
+    for bs in (1, 3, 4):
+        x = np.random.default_rng(bs).uniform(-1, 1, (bs, 3, 16, 16))
+        assert rel_err(net.output(x), onet.output(x).reshape(bs, -1)) < TOL
+    net.close()

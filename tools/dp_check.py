@@ -69,6 +69,20 @@ for prec, name in ((b.FP32, "fp32"), (b.BF16, "bf16")):
         out[f"sharded_{name}_{tag}_identical"] = bool(torch.equal(lo, hi))
         assert torch.equal(lo, hi), tag
     gan.close(); G.close(); D.close()
+# (4) the reference's own rule: local fits, then parameters AND updater state averaged over ranks (J:325-330)
+dspec = m.dcgan_discriminator(32, 64, 3, lr=1e-3)
+net = b.Net(ctx, dspec, (3, 32, 32), max_batch=16, precision=b.FP32, xent_clip_eps=0.0, seed=2)
+net.set_grad_allreduce(False)
+rng = np.random.default_rng(500 + rank)
+net.fit(rng.uniform(-1, 1, (16, 3, 32, 32)), rng.uniform(0, 1, (16, 1)))
+before = torch.from_numpy(np.concatenate([net.params(), net.updater_state()])).cuda()
+mean = before.clone(); dist.all_reduce(mean, op=dist.ReduceOp.SUM); mean /= world
+net.average_parameters()
+after = np.concatenate([net.params(), net.updater_state()])
+err = float(np.abs(after - mean.cpu().numpy()).max())
+out["parameter_averaging_max_abs_err"] = err
+assert err < 1e-6, err
+net.close()
 if rank == 0:
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "dp_check_rank0.json"), "w"), indent=1)
