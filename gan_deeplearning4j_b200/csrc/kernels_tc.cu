@@ -19,6 +19,7 @@
 // parity class, so no MAC is spent on inserted zeros and nothing is scattered.
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -72,6 +73,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// multicast variant: the box lands at the same CTA-relative smem offset of every CTA in `mask`, and signals the same-offset mbarrier there
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, uint16_t mask) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() { asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_map(const CUtensorMap* map) { asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -133,9 +144,14 @@ struct TcSmem {
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;   // + barriers + alignment slack
 };
 
-template <int BN, int STAGES>
+// CL > 1: a thread-block cluster of CL CTAs that are adjacent along M (same weight tile): each CTA fetches only BN/CL rows of the
+// weight tile and TMA-multicasts them into every CTA of the cluster, so the weight traffic out of L2 drops by CL; a stage is
+// refilled only after all CL MMA issuers have committed it (tcgen05.commit multicast onto every CTA's "empty" barrier).
+template <int BN, int STAGES, int CL>
 __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcConvParams p) {
   using S = TcSmem<BN, STAGES>;
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t cmask = (uint16_t)((1u << CL) - 1u);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -154,13 +170,14 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ CU
 
   if (warp == 0 && lane == 0) {
     prefetch_map(&tmA); prefetch_map(&tmB);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL); }
     mbar_init(bar_accum, 1);
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(smem_u32((const void*)tmem_slot), BN < 32 ? 32 : BN); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();      // every CTA's barriers exist before any peer multicasts into / arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -181,7 +198,8 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ CU
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
         mbar_expect_tx(bar_full + 8 * s, S::STAGE_BYTES);
         tma_load_4d(smem_base + s * S::STAGE_BYTES, &tmA, bar_full + 8 * s, ch * 64, ax, ay, n0);
-        tma_load_3d(smem_base + s * S::STAGE_BYTES + S::A_BYTES, &tmB, bar_full + 8 * s, ch * 64, wtap, nb0);
+        if (CL == 1) tma_load_3d(smem_base + s * S::STAGE_BYTES + S::A_BYTES, &tmB, bar_full + 8 * s, ch * 64, wtap, nb0);
+        else tma_load_3d_mc(smem_base + s * S::STAGE_BYTES + S::A_BYTES + crank * (BN / CL) * 128, &tmB, bar_full + 8 * s, ch * 64, wtap, nb0 + (int)crank * (BN / CL), cmask);
       }
     }
   } else if (warp == 1) {
@@ -197,7 +215,7 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ CU
 #pragma unroll
         for (int k = 0; k < 4; ++k)     // 4 x K=16 inside the 128-byte swizzle atom: +32 B = +2 in the (>>4) start-address field
           umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-        umma_commit(bar_empty + 8 * s);
+        if (CL == 1) umma_commit(bar_empty + 8 * s); else umma_commit_mc(bar_empty + 8 * s, cmask);
       }
       umma_commit(bar_accum);
     }
@@ -234,6 +252,7 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ CU
     tc_fence_before();
   }
   __syncthreads();
+  if (CL > 1) cluster_sync_all();      // no CTA leaves while a peer may still multicast into its smem or arrive on its barriers
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, BN < 32 ? 32 : BN); }
 }
 
@@ -258,26 +277,46 @@ bool tc_dgrad_supported(const ConvGeom& g) {
          pick_row_tile(g.N, g.OH, g.OW, 128, &a, &b, &c);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CL>
 static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvParams& p, dim3 grid, cudaStream_t s) {
   using S = TcSmem<BN, STAGES>;
   static bool attr_set = false;
-  if (!attr_set) { if (cudaFuncSetAttribute(tc_conv_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) return -2; attr_set = true; }
-  tc_conv_kernel<BN, STAGES><<<grid, 192, S::TOTAL, s>>>(tmA, tmB, p);
+  if (!attr_set) { if (cudaFuncSetAttribute(tc_conv_kernel<BN, STAGES, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) return -2; attr_set = true; }
+  if (CL == 1) {
+    tc_conv_kernel<BN, STAGES, CL><<<grid, 192, S::TOTAL, s>>>(tmA, tmB, p);
+  } else {
+    cudaLaunchConfig_t cfg{}; cfg.gridDim = grid; cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = S::TOTAL; cfg.stream = s;
+    cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, tc_conv_kernel<BN, STAGES, CL>, tmA, tmB, p) != cudaSuccess) return -3;
+  }
   LAUNCHED();
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
 }
-static int dispatch_conv(int BN, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvParams& p, dim3 grid, cudaStream_t s) {
+static int g_tc_cluster = -1;     // B2G_TC_CLUSTER=1|2|4 caps the cluster size. Default 1: measured on B200 the 2- and 4-CTA multicast variants are 5-20 % SLOWER (profiles/r01_kernel_bench_cluster.txt) -- consistent with the microarchitecture note that TMA multicast only dedups L2 reads at cluster size 8
+static int pick_cluster(unsigned grid_x) {
+  if (g_tc_cluster < 0) { const char* e = getenv("B2G_TC_CLUSTER"); g_tc_cluster = e ? atoi(e) : 1; if (g_tc_cluster != 1 && g_tc_cluster != 2 && g_tc_cluster != 4) g_tc_cluster = 1; }
+  if (g_tc_cluster >= 4 && grid_x % 4 == 0) return 4;
+  if (g_tc_cluster >= 2 && grid_x % 2 == 0) return 2;
+  return 1;
+}
+template <int BN, int STAGES>
+static int launch_conv_cl(int CL, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvParams& p, dim3 grid, cudaStream_t s) {
+  switch (CL) { case 4: return launch_conv<BN, STAGES, 4>(tmA, tmB, p, grid, s); case 2: return launch_conv<BN, STAGES, 2>(tmA, tmB, p, grid, s); }
+  return launch_conv<BN, STAGES, 1>(tmA, tmB, p, grid, s);
+}
+static int dispatch_conv(int BN, int CL, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvParams& p, dim3 grid, cudaStream_t s) {
   switch (BN) {
-    case 64: return launch_conv<64, 4>(tmA, tmB, p, grid, s);
-    case 128: return launch_conv<128, 3>(tmA, tmB, p, grid, s);
-    case 256: return launch_conv<256, 4>(tmA, tmB, p, grid, s);
+    case 64: return launch_conv_cl<64, 4>(CL, tmA, tmB, p, grid, s);
+    case 128: return launch_conv_cl<128, 3>(CL, tmA, tmB, p, grid, s);
+    case 256: return launch_conv_cl<256, 4>(CL, tmA, tmB, p, grid, s);
   }
   return -4;
 }
 
 // weights as a 3-D tensor [rows][taps][Kred] (bf16, Kred contiguous); box = 64 x 1 x BN
-static int weight_map(CUtensorMap* m, const __nv_bfloat16* w, int rows, int taps, int kred, int BN) {
+static int weight_map(CUtensorMap* m, const __nv_bfloat16* w, int rows, int taps, int kred, int box_rows) {
+  const int BN = box_rows;
   cuuint64_t dims[3] = {(cuuint64_t)kred, (cuuint64_t)taps, (cuuint64_t)rows};
   cuuint64_t strides[2] = {(cuuint64_t)kred * 2, (cuuint64_t)taps * kred * 2};
   cuuint32_t box[3] = {64, 1, (cuuint32_t)BN}; cuuint32_t es[3] = {1, 1, 1};
@@ -296,9 +335,10 @@ int k_tc_fprop(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* w
   cuuint32_t box[4] = {64, (cuuint32_t)(p.Wt * g.SW), (cuuint32_t)(p.Ht * g.SH), (cuuint32_t)p.Nt};
   cuuint32_t es[4] = {1, (cuuint32_t)g.SW, (cuuint32_t)g.SH, 1};
   if (make_map_bf16(&tmA, x, 4, dims, strides, box, es)) return -1;
-  if (weight_map(&tmB, w, g.O, g.KH * g.KW, g.C, BN)) return -1;
   dim3 grid((unsigned)(g.N * g.OH * g.OW / 128), (unsigned)(g.O / BN), 1);
-  return dispatch_conv(BN, tmA, tmB, p, grid, s);
+  const int CL = pick_cluster(grid.x);
+  if (weight_map(&tmB, w, g.O, g.KH * g.KW, g.C, BN / CL)) return -1;
+  return dispatch_conv(BN, CL, tmA, tmB, p, grid, s);
 }
 
 int k_tc_dgrad(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat16* wt, const float* bias, __nv_bfloat16* dx, int act, float alpha, cudaStream_t s) {
@@ -313,9 +353,10 @@ int k_tc_dgrad(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat16* 
   cuuint32_t box[4] = {64, (cuuint32_t)p.Wt, (cuuint32_t)p.Ht, (cuuint32_t)p.Nt};
   cuuint32_t es[4] = {1, 1, 1, 1};
   if (make_map_bf16(&tmA, dy, 4, dims, strides, box, es)) return -1;
-  if (weight_map(&tmB, wt, g.C, 16, g.O, BN)) return -1;       // transposed shadow [C][taps][O]
   dim3 grid((unsigned)(g.N * g.OH * g.OW / 128), (unsigned)(g.C / BN), 4);
-  return dispatch_conv(BN, tmA, tmB, p, grid, s);
+  const int CL = pick_cluster(grid.x);
+  if (weight_map(&tmB, wt, g.C, 16, g.O, BN / CL)) return -1;       // transposed shadow [C][taps][O]
+  return dispatch_conv(BN, CL, tmA, tmB, p, grid, s);
 }
 
 // ------------------------------------------------------------------ wgrad: MN-major operands --------------
