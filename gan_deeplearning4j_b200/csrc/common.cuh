@@ -3,12 +3,33 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 #include <stdint.h>
 #include "kernels.h"
 
 namespace b2g {
 
 #define LAUNCHED() do { ++::b2g::g_launch_count; } while (0)
+
+// Programmatic dependent launch: every kernel lets its successor's CTAs be scheduled as soon as SM resources free up
+// (griddepcontrol.launch_dependents) and then waits for its predecessor to have fully completed and flushed
+// (griddepcontrol.wait) before touching memory -- the launch latency of ~100 dependent kernels per step overlaps the tail of
+// the kernel in front.  Both instructions are no-ops for a launch without the attribute.  Measured on B200 (round 1): with the
+// attribute on every launch the graph-replayed step is 5 % SLOWER (2.16 vs 2.05 ms; waiting successor CTAs hold SM slots), so it is
+// opt-in: B2G_PDL=1.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+extern int g_pdl_enabled;     // -1 unknown, 0 off, 1 on
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  if (g_pdl_enabled < 0) { const char* e = getenv("B2G_PDL"); g_pdl_enabled = (e && e[0] == '1') ? 1 : 0; }
+  cudaLaunchConfig_t cfg{}; cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_pdl_enabled ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 #define DISPATCH_PREC(prec, T, ...)                                   \
   do {                                                                \

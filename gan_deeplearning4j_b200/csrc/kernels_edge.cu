@@ -39,7 +39,7 @@ template <typename T> __device__ __forceinline__ void load8_any(const T* p, floa
 // One thread per dy-grid position (n,qy,qx): reads its 3x3 neighbourhood once, writes the 2x2 output block.
 template <typename T, typename TW>
 __global__ void __launch_bounds__(128) edge_deconv_small_c_kernel(const T* __restrict__ dy, const TW* __restrict__ w, const float* __restrict__ bias, T* __restrict__ dx,
-                                                                   int N, int OH, int OW, int O, int C, int act, float alpha) {
+                                                                   int N, int OH, int OW, int O, int C, int act, float alpha) { pdl_prologue();
   extern __shared__ float4 ws4[];      // [16 taps][O] : (c0,c1,c2,c3)
   for (int i = threadIdx.x; i < 16 * O; i += blockDim.x) {
     int tap = i / O, o = i % O; float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -110,7 +110,7 @@ __device__ __forceinline__ void store16(__nv_bfloat16* dst, const float (&a)[16]
 // 12-element row segments, weights from smem as [k][O] so a warp's reads are broadcasts / conflict-free.
 template <typename T, typename TW>
 __global__ void __launch_bounds__(128) edge_conv_small_cin_kernel(const T* __restrict__ x, const TW* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out,
-                                                                   int N, int H, int W, int C, int OH, int OW, int O, int act, float alpha) {
+                                                                   int N, int H, int W, int C, int OH, int OW, int O, int act, float alpha) { pdl_prologue();
   extern __shared__ float wsf[];      // [16*C][O]
   const int K = 16 * C;
   for (int i = threadIdx.x; i < K * O; i += blockDim.x) { int o = i / K, k = i % K; wsf[k * O + o] = ldw(w, (size_t)i); }   // coalesced global read
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(128) edge_conv_small_cin_kernel(const T* __res
 // one dy pair and the 4*C contiguous x values of its filter row from smem and does 2*4*C FMAs.  Each CTA reduces a contiguous pixel range;
 // partials [grid][O*16*C] are summed by k_reduce_splits.
 template <typename T>
-__global__ void edge_wgrad_small_cin_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ part, int N, int H, int W, int C, int OH, int OW, int O, int pix_per_cta) {
+__global__ void edge_wgrad_small_cin_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ part, int N, int H, int W, int C, int OH, int OW, int O, int pix_per_cta) { pdl_prologue();
   extern __shared__ float sm[];
   const int TP = 64;                           // pixels per smem tile
   float* sdy = sm;                             // [TP][O]
@@ -224,7 +224,7 @@ __global__ void edge_wgrad_small_cin_kernel(const T* __restrict__ x, const T* __
 
 // ------------------------------------------------------------------ (d) layers with <=4 output units -------------
 template <typename T, typename TW>
-__global__ void __launch_bounds__(128) dense_small_o_fwd_kernel(const T* __restrict__ x, const TW* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out, int K, int O, int act, float alpha) {
+__global__ void __launch_bounds__(128) dense_small_o_fwd_kernel(const T* __restrict__ x, const TW* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out, int K, int O, int act, float alpha) { pdl_prologue();
   const int n = blockIdx.x; __shared__ float red[4][4];
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   const T* xr = x + (size_t)n * K;
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(128) dense_small_o_fwd_kernel(const T* __restr
   if (threadIdx.x < O) { float a = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x]; stf(out, (size_t)n * O + threadIdx.x, act_fwd(act, a + (bias ? bias[threadIdx.x] : 0.f), alpha)); }
 }
 template <typename T, typename TW>
-__global__ void dense_small_o_dgrad_kernel(const T* __restrict__ dy, const TW* __restrict__ w, T* __restrict__ dx, int N, int K, int O) {
+__global__ void dense_small_o_dgrad_kernel(const T* __restrict__ dy, const TW* __restrict__ w, T* __restrict__ dx, int N, int K, int O) { pdl_prologue();
   const size_t total = (size_t)N * K;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int k = i % K; const size_t n = i / K; float a = 0.f;
@@ -248,7 +248,7 @@ __global__ void dense_small_o_dgrad_kernel(const T* __restrict__ dy, const TW* _
   }
 }
 template <typename T>
-__global__ void dense_small_o_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ part, int N, int K, int O, int rows_per_split) {
+__global__ void dense_small_o_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ part, int N, int K, int O, int rows_per_split) { pdl_prologue();
   const int k = blockIdx.x * blockDim.x + threadIdx.x; if (k >= K) return;
   const int n0 = blockIdx.y * rows_per_split, n1 = min(N, n0 + rows_per_split);
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -266,7 +266,7 @@ bool dense_small_o_supported(const ConvGeom& g) { return g.KH == 1 && g.KW == 1 
 template <typename T, typename TW>
 static void launch_deconv_small_c(const ConvGeom& g, const void* dy, const void* w, const float* bias, void* dx, int act, float alpha, cudaStream_t s) {
   long tot = (long)g.N * g.OH * g.OW; long blocks = (tot + 127) / 128; if (blocks > 148 * 8) blocks = 148 * 8;
-  edge_deconv_small_c_kernel<T, TW><<<(unsigned)blocks, 128, 16 * g.O * sizeof(float4), s>>>((const T*)dy, (const TW*)w, bias, (T*)dx, g.N, g.OH, g.OW, g.O, g.C, act, alpha);
+  launch_pdl(edge_deconv_small_c_kernel<T, TW>, dim3((unsigned)blocks), dim3(128), (size_t)(16 * g.O * sizeof(float4)), s, (const T*)dy, (const TW*)w, bias, (T*)dx, g.N, g.OH, g.OW, g.O, g.C, act, alpha);
 }
 void k_edge_deconv_small_c(int prec, int wprec, const ConvGeom& g, const void* dy, const void* w, const float* bias, void* dx, int act, float alpha, cudaStream_t s) {
   if (prec == PREC_F32) launch_deconv_small_c<float, float>(g, dy, w, bias, dx, act, alpha, s);
@@ -277,7 +277,7 @@ void k_edge_deconv_small_c(int prec, int wprec, const ConvGeom& g, const void* d
 template <typename T, typename TW>
 static void launch_conv_small_cin(const ConvGeom& g, const void* x, const void* w, const float* bias, void* out, int act, float alpha, cudaStream_t s) {
   long tot = (long)g.N * g.OH * (g.OW / 4) * (g.O / 16); long blocks = (tot + 127) / 128; if (blocks > 148 * 8) blocks = 148 * 8;
-  edge_conv_small_cin_kernel<T, TW><<<(unsigned)blocks, 128, 16 * g.C * g.O * sizeof(float), s>>>((const T*)x, (const TW*)w, bias, (T*)out, g.N, g.H, g.W, g.C, g.OH, g.OW, g.O, act, alpha);
+  launch_pdl(edge_conv_small_cin_kernel<T, TW>, dim3((unsigned)blocks), dim3(128), (size_t)(16 * g.C * g.O * sizeof(float)), s, (const T*)x, (const TW*)w, bias, (T*)out, g.N, g.H, g.W, g.C, g.OH, g.OW, g.O, act, alpha);
 }
 void k_edge_conv_small_cin(int prec, int wprec, const ConvGeom& g, const void* x, const void* w, const float* bias, void* out, int act, float alpha, cudaStream_t s) {
   if (prec == PREC_F32) launch_conv_small_cin<float, float>(g, x, w, bias, out, act, alpha, s);
@@ -290,20 +290,20 @@ size_t k_edge_wgrad_scratch_floats(const ConvGeom& g) { return edge_wgrad_small_
 void k_edge_wgrad_small_cin(int prec, const ConvGeom& g, const void* x, const void* dy, float* dw, float* scratch, int accumulate, cudaStream_t s) {
   const int ctas = edge_wgrad_ctas(g); const long P = (long)g.N * g.OH * g.OW; const int ppc = (int)((P + ctas - 1) / ctas);
   const size_t n = (size_t)g.O * 16 * g.C; const size_t smem = (64 * g.O + 64 * 64) * sizeof(float);
-  DISPATCH_PREC(prec, T, (edge_wgrad_small_cin_kernel<T><<<ctas, 2 * g.O, smem, s>>>((const T*)x, (const T*)dy, scratch, g.N, g.H, g.W, g.C, g.OH, g.OW, g.O, ppc))); LAUNCHED();
+  DISPATCH_PREC(prec, T, (launch_pdl(edge_wgrad_small_cin_kernel<T>, dim3(ctas), dim3(2 * g.O), (size_t)(smem), s, (const T*)x, (const T*)dy, scratch, g.N, g.H, g.W, g.C, g.OH, g.OW, g.O, ppc))); LAUNCHED();
   k_reduce_splits(scratch, dw, n, ctas, n, accumulate, s);
 }
 void k_dense_small_o_fwd(int prec, int wprec, const ConvGeom& g, const void* x, const void* w, const float* bias, void* out, int act, float alpha, cudaStream_t s) {
-  if (prec == PREC_F32) dense_small_o_fwd_kernel<float, float><<<g.N, 128, 0, s>>>((const float*)x, (const float*)w, bias, (float*)out, g.C, g.O, act, alpha);
-  else if (wprec == PREC_F32) dense_small_o_fwd_kernel<__nv_bfloat16, float><<<g.N, 128, 0, s>>>((const __nv_bfloat16*)x, (const float*)w, bias, (__nv_bfloat16*)out, g.C, g.O, act, alpha);
-  else dense_small_o_fwd_kernel<__nv_bfloat16, __nv_bfloat16><<<g.N, 128, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)out, g.C, g.O, act, alpha);
+  if (prec == PREC_F32) launch_pdl(dense_small_o_fwd_kernel<float, float>, dim3(g.N), dim3(128), (size_t)(0), s, (const float*)x, (const float*)w, bias, (float*)out, g.C, g.O, act, alpha);
+  else if (wprec == PREC_F32) launch_pdl(dense_small_o_fwd_kernel<__nv_bfloat16, float>, dim3(g.N), dim3(128), (size_t)(0), s, (const __nv_bfloat16*)x, (const float*)w, bias, (__nv_bfloat16*)out, g.C, g.O, act, alpha);
+  else launch_pdl(dense_small_o_fwd_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(g.N), dim3(128), (size_t)(0), s, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)out, g.C, g.O, act, alpha);
   LAUNCHED();
 }
 void k_dense_small_o_dgrad(int prec, int wprec, const ConvGeom& g, const void* dy, const void* w, void* dx, cudaStream_t s) {
   size_t tot = (size_t)g.N * g.C; int blocks = (int)((tot + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
-  if (prec == PREC_F32) dense_small_o_dgrad_kernel<float, float><<<blocks, 256, 0, s>>>((const float*)dy, (const float*)w, (float*)dx, g.N, g.C, g.O);
-  else if (wprec == PREC_F32) dense_small_o_dgrad_kernel<__nv_bfloat16, float><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)dy, (const float*)w, (__nv_bfloat16*)dx, g.N, g.C, g.O);
-  else dense_small_o_dgrad_kernel<__nv_bfloat16, __nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)w, (__nv_bfloat16*)dx, g.N, g.C, g.O);
+  if (prec == PREC_F32) launch_pdl(dense_small_o_dgrad_kernel<float, float>, dim3(blocks), dim3(256), (size_t)(0), s, (const float*)dy, (const float*)w, (float*)dx, g.N, g.C, g.O);
+  else if (wprec == PREC_F32) launch_pdl(dense_small_o_dgrad_kernel<__nv_bfloat16, float>, dim3(blocks), dim3(256), (size_t)(0), s, (const __nv_bfloat16*)dy, (const float*)w, (__nv_bfloat16*)dx, g.N, g.C, g.O);
+  else launch_pdl(dense_small_o_dgrad_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(blocks), dim3(256), (size_t)(0), s, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)w, (__nv_bfloat16*)dx, g.N, g.C, g.O);
   LAUNCHED();
 }
 static int dense_wgrad_splits(const ConvGeom& g) { int sp = (g.N + 31) / 32; if (sp > 16) sp = 16; if (sp < 1) sp = 1; return sp; }
@@ -311,7 +311,7 @@ size_t k_dense_small_o_wgrad_scratch_floats(const ConvGeom& g) { return dense_sm
 void k_dense_small_o_wgrad(int prec, const ConvGeom& g, const void* x, const void* dy, float* dw, float* scratch, int accumulate, cudaStream_t s) {
   const int sp = dense_wgrad_splits(g), rps = (g.N + sp - 1) / sp; const size_t n = (size_t)g.O * g.C;
   dim3 grid((g.C + 127) / 128, sp);
-  DISPATCH_PREC(prec, T, (dense_small_o_wgrad_kernel<T><<<grid, 128, 0, s>>>((const T*)x, (const T*)dy, scratch, g.N, g.C, g.O, rps))); LAUNCHED();
+  DISPATCH_PREC(prec, T, (launch_pdl(dense_small_o_wgrad_kernel<T>, dim3(grid), dim3(128), (size_t)(0), s, (const T*)x, (const T*)dy, scratch, g.N, g.C, g.O, rps))); LAUNCHED();
   k_reduce_splits(scratch, dw, n, sp, n, accumulate, s);
 }
 

@@ -15,10 +15,11 @@
 namespace b2g {
 
 uint64_t g_launch_count = 0;
+int g_pdl_enabled = -1;
 
 // ---------------------------------------------------------------- layout -----------------------------
 template <typename T>
-__global__ void nchw_f32_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int N, int C, int HW) {
+__global__ void nchw_f32_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int N, int C, int HW) { pdl_prologue();
   // one thread per destination element (coalesced writes; reads strided by HW, served by L2)
   size_t total = (size_t)N * C * HW;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -27,7 +28,7 @@ __global__ void nchw_f32_to_nhwc_kernel(const float* __restrict__ src, T* __rest
   }
 }
 template <typename T>
-__global__ void nhwc_to_nchw_f32_kernel(const T* __restrict__ src, float* __restrict__ dst, int N, int C, int HW) {
+__global__ void nhwc_to_nchw_f32_kernel(const T* __restrict__ src, float* __restrict__ dst, int N, int C, int HW) { pdl_prologue();
   size_t total = (size_t)N * C * HW;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int p = i % HW; size_t t = i / HW; int c = t % C; size_t n = t / C;
@@ -35,7 +36,7 @@ __global__ void nhwc_to_nchw_f32_kernel(const T* __restrict__ src, float* __rest
   }
 }
 template <typename T>
-__global__ void permute_kernel(const T* __restrict__ src, T* __restrict__ dst, int N, int C, int HW, int to_nhwc) {
+__global__ void permute_kernel(const T* __restrict__ src, T* __restrict__ dst, int N, int C, int HW, int to_nhwc) { pdl_prologue();
   size_t total = (size_t)N * C * HW;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     if (to_nhwc) { int c = i % C; size_t t = i / C; int p = t % HW; size_t n = t / HW; dst[i] = src[(n * C + c) * HW + p]; }
@@ -46,24 +47,24 @@ static inline int ew_blocks(size_t n, int per = 256) { size_t b = (n + per - 1) 
 
 void k_nchw_f32_to_nhwc(int prec, const float* src, void* dst, int N, int C, int HW, cudaStream_t s) {
   size_t n = (size_t)N * C * HW; if (!n) return;
-  DISPATCH_PREC(prec, T, (nchw_f32_to_nhwc_kernel<T><<<ew_blocks(n), 256, 0, s>>>(src, (T*)dst, N, C, HW))); LAUNCHED();
+  DISPATCH_PREC(prec, T, (launch_pdl(nchw_f32_to_nhwc_kernel<T>, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, src, (T*)dst, N, C, HW))); LAUNCHED();
 }
 void k_nhwc_to_nchw_f32(int prec, const void* src, float* dst, int N, int C, int HW, cudaStream_t s) {
   size_t n = (size_t)N * C * HW; if (!n) return;
-  DISPATCH_PREC(prec, T, (nhwc_to_nchw_f32_kernel<T><<<ew_blocks(n), 256, 0, s>>>((const T*)src, dst, N, C, HW))); LAUNCHED();
+  DISPATCH_PREC(prec, T, (launch_pdl(nhwc_to_nchw_f32_kernel<T>, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, (const T*)src, dst, N, C, HW))); LAUNCHED();
 }
 void k_permute(int prec, const void* src, void* dst, int N, int C, int HW, int to_nhwc, cudaStream_t s) {
   size_t n = (size_t)N * C * HW; if (!n) return;
-  DISPATCH_PREC(prec, T, (permute_kernel<T><<<ew_blocks(n), 256, 0, s>>>((const T*)src, (T*)dst, N, C, HW, to_nhwc))); LAUNCHED();
+  DISPATCH_PREC(prec, T, (launch_pdl(permute_kernel<T>, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, (const T*)src, (T*)dst, N, C, HW, to_nhwc))); LAUNCHED();
 }
-__global__ void cast_f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+__global__ void cast_f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) { pdl_prologue();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = __float2bfloat16_rn(src[i]);
 }
 void k_cast_f32_to_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t s) {
-  if (!n) return; cast_f32_to_bf16_kernel<<<ew_blocks(n), 256, 0, s>>>(src, dst, n); LAUNCHED();
+  if (!n) return; launch_pdl(cast_f32_to_bf16_kernel, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, src, dst, n); LAUNCHED();
 }
 // w [A][taps][B] -> w_bf same layout, wt_bf [B][taps][A]; 32x32 smem-tiled transpose per tap
-__global__ void weight_shadow_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ w_bf, __nv_bfloat16* __restrict__ wt_bf, int A, int taps, int B) {
+__global__ void weight_shadow_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ w_bf, __nv_bfloat16* __restrict__ wt_bf, int A, int taps, int B) { pdl_prologue();
   __shared__ float tile[32][33];
   int tap = blockIdx.z, a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -80,7 +81,7 @@ __global__ void weight_shadow_kernel(const float* __restrict__ w, __nv_bfloat16*
 }
 void k_weight_shadow(const float* w, __nv_bfloat16* w_bf, __nv_bfloat16* wt_bf, int A, int taps, int B, cudaStream_t s) {
   dim3 grid((B + 31) / 32, (A + 31) / 32, taps);
-  weight_shadow_kernel<<<grid, dim3(32, 8), 0, s>>>(w, w_bf, wt_bf, A, taps, B); LAUNCHED();
+  launch_pdl(weight_shadow_kernel, dim3(grid), dim3(dim3(32, 8)), (size_t)(0), s, w, w_bf, wt_bf, A, taps, B); LAUNCHED();
 }
 
 // ---------------------------------------------------------------- sliced column reductions ---------------
@@ -107,7 +108,7 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
 }
 
 template <typename T>
-__global__ void bn_stats_partial_kernel(const T* __restrict__ x, int rows, int C, int S, float* __restrict__ psum, float* __restrict__ psq) {
+__global__ void bn_stats_partial_kernel(const T* __restrict__ x, int rows, int C, int S, float* __restrict__ psum, float* __restrict__ psq) { pdl_prologue();
   int g = blockIdx.y;
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= S * C) return;
@@ -122,7 +123,7 @@ __global__ void bn_stats_partial_kernel(const T* __restrict__ x, int rows, int C
 // few partials for stage 2.
 static inline int vec_ty(int C) { int c8 = C / 8; int ty = 256 / c8; return ty < 1 ? 1 : ty; }
 static inline bool vec_ok(int prec, int C) { return prec == PREC_BF16 && C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0; }
-static inline int vec_blocks(int rows, int C) { int ty = vec_ty(C); int b = rows / (ty * 4); int cap = SLICE_ELEMS / C; if (cap > 512) cap = 512; if (b > cap) b = cap; if (b < 1) b = 1; return b; }
+static inline int vec_blocks(int rows, int C) { int ty = vec_ty(C); int b = rows / (ty * 4); int cap = SLICE_ELEMS / C; if (cap > 256) cap = 256; if (b > cap) b = cap; if (b < 1) b = 1; return b; }
 template <int NV>
 __device__ __forceinline__ void block_fold_write(float (&acc)[NV][8], int C, int C8, int c8, int ty, int TY, float* const (&dst)[NV], size_t row_off) {
   __shared__ float sred[NV][2048];
@@ -136,7 +137,7 @@ __device__ __forceinline__ void block_fold_write(float (&acc)[NV][8], int C, int
     for (int v = 0; v < NV; ++v) { float a = 0.f; for (int k = 0; k < TY; ++k) a += sred[v][k * C + c]; dst[v][row_off + c] = a; }
   }
 }
-__global__ void __launch_bounds__(256) bn_stats_partial_bf16x8_kernel(const uint4* __restrict__ x, int rows, int C, int S, float* __restrict__ psum, float* __restrict__ psq) {
+__global__ void __launch_bounds__(256) bn_stats_partial_bf16x8_kernel(const uint4* __restrict__ x, int rows, int C, int S, float* __restrict__ psum, float* __restrict__ psq) { pdl_prologue();
   const int g = blockIdx.y, C8 = C / 8, TY = 256 / C8, c8 = threadIdx.x % C8, ty = threadIdx.x / C8, sl = blockIdx.x;
   const int chunk = (rows + S - 1) / S, r0 = sl * chunk, r1 = min(rows, r0 + chunk);
   const uint4* xg = x + (size_t)g * rows * C8;
@@ -152,13 +153,19 @@ __global__ void __launch_bounds__(256) bn_stats_partial_bf16x8_kernel(const uint
 // stage 2: block = 32 adjacent channels x 16 slice lanes (coalesced 128-byte rows of the partial arrays), fixed-order tree in double
 __global__ void __launch_bounds__(512) bn_stats_final_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int rows, int C, int S, int groups, float eps,
                                       float* __restrict__ mean, float* __restrict__ invstd,
-                                      const float* __restrict__ run_mean, const float* __restrict__ run_var, float* g_mean, float* g_var, float decay) {
+                                      const float* __restrict__ run_mean, const float* __restrict__ run_var, float* g_mean, float* g_var, float decay) { pdl_prologue();
   __shared__ double sa[16][33], sb[16][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, c = blockIdx.x * 32 + tx;
   double acc_gm = 0.0, acc_gv = 0.0;
   for (int g = 0; g < groups; ++g) {
     double a = 0.0, b = 0.0;
-    if (c < C) for (int sl = ty; sl < S; sl += 16) { a += psum[((size_t)g * S + sl) * C + c]; b += psq[((size_t)g * S + sl) * C + c]; }
+    if (c < C) for (int sl0 = ty; sl0 < S; sl0 += 16 * 8) {      // 16 independent loads in flight per thread: one L2 round trip per batch
+      float va[8], vb[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { const int sl = sl0 + 16 * q; va[q] = sl < S ? psum[((size_t)g * S + sl) * C + c] : 0.f; vb[q] = sl < S ? psq[((size_t)g * S + sl) * C + c] : 0.f; }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { a += va[q]; b += vb[q]; }
+    }
     sa[ty][tx] = a; sb[ty][tx] = b;
     __syncthreads();
     if (ty == 0 && c < C) {
@@ -178,25 +185,25 @@ void k_bn_stats(int prec, const void* x, int rows, int C, int groups, float* scr
   int S = vec ? vec_blocks(rows, C) : pick_slices(rows, C);
   float* psum = scratch; float* psq = scratch + (size_t)groups * S * C;
   if (vec) {
-    bn_stats_partial_bf16x8_kernel<<<dim3(S, groups), 256, 0, s>>>((const uint4*)x, rows, C, S, psum, psq);
+    launch_pdl(bn_stats_partial_bf16x8_kernel, dim3(dim3(S, groups)), dim3(256), (size_t)(0), s, (const uint4*)x, rows, C, S, psum, psq);
   } else {
     dim3 grid((S * C + 255) / 256, groups);
-    DISPATCH_PREC(prec, T, (bn_stats_partial_kernel<T><<<grid, 256, 0, s>>>((const T*)x, rows, C, S, psum, psq)));
+    DISPATCH_PREC(prec, T, (launch_pdl(bn_stats_partial_kernel<T>, dim3(grid), dim3(256), (size_t)(0), s, (const T*)x, rows, C, S, psum, psq)));
   }
   LAUNCHED();
-  bn_stats_final_kernel<<<(C + 31) / 32, 512, 0, s>>>(psum, psq, rows, C, S, groups, eps, mean, invstd, run_mean, run_var, g_mean, g_var, decay); LAUNCHED();
+  launch_pdl(bn_stats_final_kernel, dim3((C + 31) / 32), dim3(512), (size_t)(0), s, psum, psq, rows, C, S, groups, eps, mean, invstd, run_mean, run_var, g_mean, g_var, decay); LAUNCHED();
 }
-__global__ void bn_prep_infer_kernel(const float* __restrict__ rm, const float* __restrict__ rv, int C, int groups, float eps, float* mean, float* invstd) {
+__global__ void bn_prep_infer_kernel(const float* __restrict__ rm, const float* __restrict__ rv, int C, int groups, float eps, float* mean, float* invstd) { pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= C * groups) return;
   int c = i % C; mean[i] = rm[c]; invstd[i] = 1.0f / sqrtf(rv[c] + eps);
 }
 void k_bn_prep_infer(const float* run_mean, const float* run_var, int C, int groups, float eps, float* mean, float* invstd, cudaStream_t s) {
-  bn_prep_infer_kernel<<<(C * groups + 255) / 256, 256, 0, s>>>(run_mean, run_var, C, groups, eps, mean, invstd); LAUNCHED();
+  launch_pdl(bn_prep_infer_kernel, dim3((C * groups + 255) / 256), dim3(256), (size_t)(0), s, run_mean, run_var, C, groups, eps, mean, invstd); LAUNCHED();
 }
 
 template <typename T>
 __global__ void bn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, int rows, int C, int groups, const float* __restrict__ mean,
-                                const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int act, float alpha) {
+                                const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int act, float alpha) { pdl_prologue();
   size_t per_group = (size_t)rows * C, total = per_group * groups;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int c = i % C; int g = i / per_group;
@@ -206,7 +213,7 @@ __global__ void bn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, int 
 }
 // bf16, C % 8 == 0: 16-byte vectors
 __global__ void bn_apply_bf16x8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int rows, int C, int groups, const float* __restrict__ mean,
-                                       const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int act, float alpha) {
+                                       const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int act, float alpha) { pdl_prologue();
   size_t per_group = (size_t)rows * C / 8, total = per_group * groups; int C8 = C / 8;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int c0 = (i % C8) * 8; int g = i / per_group;
@@ -225,9 +232,9 @@ void k_bn_apply(int prec, const void* x, void* y, int rows, int C, int groups, c
                 const float* gamma, const float* beta, int act, float alpha, cudaStream_t s) {
   size_t n = (size_t)rows * C * groups; if (!n) return;
   if (prec == PREC_BF16 && C % 8 == 0) {
-    bn_apply_bf16x8_kernel<<<ew_blocks(n / 8), 256, 0, s>>>((const uint4*)x, (uint4*)y, rows, C, groups, mean, invstd, gamma, beta, act, alpha);
+    launch_pdl(bn_apply_bf16x8_kernel, dim3(ew_blocks(n / 8)), dim3(256), (size_t)(0), s, (const uint4*)x, (uint4*)y, rows, C, groups, mean, invstd, gamma, beta, act, alpha);
   } else {
-    DISPATCH_PREC(prec, T, (bn_apply_kernel<T><<<ew_blocks(n), 256, 0, s>>>((const T*)x, (T*)y, rows, C, groups, mean, invstd, gamma, beta, act, alpha)));
+    DISPATCH_PREC(prec, T, (launch_pdl(bn_apply_kernel<T>, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, (const T*)x, (T*)y, rows, C, groups, mean, invstd, gamma, beta, act, alpha)));
   }
   LAUNCHED();
 }
@@ -236,7 +243,7 @@ void k_bn_apply(int prec, const void* x, void* y, int rows, int C, int groups, c
 template <typename T>
 __global__ void bn_bwd_partial_kernel(const T* __restrict__ x, const T* __restrict__ eo, int rows, int C, int S, const float* __restrict__ mean,
                                       const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int act, float alpha,
-                                      float* __restrict__ p1, float* __restrict__ p2) {
+                                      float* __restrict__ p1, float* __restrict__ p2) { pdl_prologue();
   int g = blockIdx.y;
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= S * C) return;
@@ -253,7 +260,7 @@ __global__ void bn_bwd_partial_kernel(const T* __restrict__ x, const T* __restri
 }
 __global__ void __launch_bounds__(256) bn_bwd_partial_bf16x8_kernel(const uint4* __restrict__ x, const uint4* __restrict__ eo, int rows, int C, int S, const float* __restrict__ mean,
                                              const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int act, float alpha,
-                                             float* __restrict__ p1, float* __restrict__ p2) {
+                                             float* __restrict__ p1, float* __restrict__ p2) { pdl_prologue();
   const int g = blockIdx.y, C8 = C / 8, TY = 256 / C8, c8 = threadIdx.x % C8, ty = threadIdx.x / C8, sl = blockIdx.x;
   const int chunk = (rows + S - 1) / S, r0 = sl * chunk, r1 = min(rows, r0 + chunk);
   const uint4* xg = x + (size_t)g * rows * C8; const uint4* eg = eo + (size_t)g * rows * C8;
@@ -270,7 +277,7 @@ __global__ void __launch_bounds__(256) bn_bwd_partial_bf16x8_kernel(const uint4*
 }
 __global__ void bn_bwd_apply_bf16x8_kernel(const uint4* __restrict__ x, const uint4* __restrict__ eo, uint4* __restrict__ ei, int rows, int C, int groups,
                                            const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                           const float* __restrict__ beta, int act, float alpha, const float* __restrict__ c1, const float* __restrict__ c2) {
+                                           const float* __restrict__ beta, int act, float alpha, const float* __restrict__ c1, const float* __restrict__ c2) { pdl_prologue();
   const int C8 = C / 8; const size_t per_group = (size_t)rows * C8, total = per_group * groups;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c0 = (int)(i % C8) * 8; const int g = (int)(i / per_group);
@@ -282,13 +289,19 @@ __global__ void bn_bwd_apply_bf16x8_kernel(const uint4* __restrict__ x, const ui
   }
 }
 __global__ void __launch_bounds__(512) bn_bwd_final_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int rows, int C, int S, int groups,
-                                    float* __restrict__ c1, float* __restrict__ c2, float* g_gamma, float* g_beta, int want) {
+                                    float* __restrict__ c1, float* __restrict__ c2, float* g_gamma, float* g_beta, int want) { pdl_prologue();
   __shared__ double sa[16][33], sb[16][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, c = blockIdx.x * 32 + tx;
   double tg = 0.0, tb = 0.0;
   for (int g = 0; g < groups; ++g) {
     double a = 0.0, b = 0.0;
-    if (c < C) for (int sl = ty; sl < S; sl += 16) { a += p1[((size_t)g * S + sl) * C + c]; b += p2[((size_t)g * S + sl) * C + c]; }
+    if (c < C) for (int sl0 = ty; sl0 < S; sl0 += 16 * 8) {
+      float va[8], vb[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { const int sl = sl0 + 16 * q; va[q] = sl < S ? p1[((size_t)g * S + sl) * C + c] : 0.f; vb[q] = sl < S ? p2[((size_t)g * S + sl) * C + c] : 0.f; }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { a += va[q]; b += vb[q]; }
+    }
     sa[ty][tx] = a; sb[ty][tx] = b;
     __syncthreads();
     if (ty == 0 && c < C) {
@@ -302,7 +315,7 @@ __global__ void __launch_bounds__(512) bn_bwd_final_kernel(const float* __restri
 template <typename T>
 __global__ void bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ eo, T* __restrict__ ei, int rows, int C, int groups,
                                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                    const float* __restrict__ beta, int act, float alpha, const float* __restrict__ c1, const float* __restrict__ c2) {
+                                    const float* __restrict__ beta, int act, float alpha, const float* __restrict__ c1, const float* __restrict__ c2) { pdl_prologue();
   size_t per_group = (size_t)rows * C, total = per_group * groups;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int c = i % C; int g = i / per_group; int k = g * C + c;
@@ -318,17 +331,17 @@ void k_bn_bwd(int prec, const void* x, const void* eps_out, void* eps_in, int ro
   int S = vec ? vec_blocks(rows, C) : pick_slices(rows, C);
   float* p1 = scratch; float* p2 = p1 + (size_t)groups * S * C; float* c1 = p2 + (size_t)groups * S * C; float* c2 = c1 + (size_t)groups * C;
   if (vec) {
-    bn_bwd_partial_bf16x8_kernel<<<dim3(S, groups), 256, 0, s>>>((const uint4*)x, (const uint4*)eps_out, rows, C, S, mean, invstd, gamma, beta, act, alpha, p1, p2);
+    launch_pdl(bn_bwd_partial_bf16x8_kernel, dim3(dim3(S, groups)), dim3(256), (size_t)(0), s, (const uint4*)x, (const uint4*)eps_out, rows, C, S, mean, invstd, gamma, beta, act, alpha, p1, p2);
   } else {
     dim3 grid((S * C + 255) / 256, groups);
-    DISPATCH_PREC(prec, T, (bn_bwd_partial_kernel<T><<<grid, 256, 0, s>>>((const T*)x, (const T*)eps_out, rows, C, S, mean, invstd, gamma, beta, act, alpha, p1, p2)));
+    DISPATCH_PREC(prec, T, (launch_pdl(bn_bwd_partial_kernel<T>, dim3(grid), dim3(256), (size_t)(0), s, (const T*)x, (const T*)eps_out, rows, C, S, mean, invstd, gamma, beta, act, alpha, p1, p2)));
   }
   LAUNCHED();
-  bn_bwd_final_kernel<<<(C + 31) / 32, 512, 0, s>>>(p1, p2, rows, C, S, groups, c1, c2, g_gamma, g_beta, want); LAUNCHED();
+  launch_pdl(bn_bwd_final_kernel, dim3((C + 31) / 32), dim3(512), (size_t)(0), s, p1, p2, rows, C, S, groups, c1, c2, g_gamma, g_beta, want); LAUNCHED();
   if (eps_in) {
     size_t n = (size_t)rows * C * groups;
-    if (vec) bn_bwd_apply_bf16x8_kernel<<<ew_blocks(n / 8), 256, 0, s>>>((const uint4*)x, (const uint4*)eps_out, (uint4*)eps_in, rows, C, groups, mean, invstd, gamma, beta, act, alpha, c1, c2);
-    else DISPATCH_PREC(prec, T, (bn_bwd_apply_kernel<T><<<ew_blocks(n), 256, 0, s>>>((const T*)x, (const T*)eps_out, (T*)eps_in, rows, C, groups, mean, invstd, gamma, beta, act, alpha, c1, c2)));
+    if (vec) launch_pdl(bn_bwd_apply_bf16x8_kernel, dim3(ew_blocks(n / 8)), dim3(256), (size_t)(0), s, (const uint4*)x, (const uint4*)eps_out, (uint4*)eps_in, rows, C, groups, mean, invstd, gamma, beta, act, alpha, c1, c2);
+    else DISPATCH_PREC(prec, T, (launch_pdl(bn_bwd_apply_kernel<T>, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, (const T*)x, (const T*)eps_out, (T*)eps_in, rows, C, groups, mean, invstd, gamma, beta, act, alpha, c1, c2)));
     LAUNCHED();
   }
 }
@@ -356,7 +369,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target)
 __global__ void __launch_bounds__(256, 3) bn_fwd_fused_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int rows, int C, int groups, float* __restrict__ scratch,
                                                            float* __restrict__ mean, float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            int act, float alpha, float eps, const float* __restrict__ run_mean, const float* __restrict__ run_var,
-                                                           float* g_mean, float* g_var, float decay, unsigned* counter) {
+                                                           float* g_mean, float* g_var, float decay, unsigned* counter) { pdl_prologue();
   const int C8 = C / 8, TY = 256 / C8, c8 = threadIdx.x % C8, ty = threadIdx.x / C8, S = gridDim.x, sl = blockIdx.x;
   float* psum = scratch; float* psq = scratch + (size_t)groups * S * C;
   const int chunk = (rows + S - 1) / S, r0 = sl * chunk, r1 = min(rows, r0 + chunk);
@@ -436,7 +449,7 @@ __global__ void __launch_bounds__(256, 3) bn_fwd_fused_kernel(const uint4* __res
 
 __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(const uint4* __restrict__ x, const uint4* __restrict__ eo, uint4* __restrict__ ei, int rows, int C, int groups,
                                                            const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                           int act, float alpha, float* __restrict__ scratch, float* g_gamma, float* g_beta, int want, unsigned* counter) {
+                                                           int act, float alpha, float* __restrict__ scratch, float* g_gamma, float* g_beta, int want, unsigned* counter) { pdl_prologue();
   const int C8 = C / 8, TY = 256 / C8, c8 = threadIdx.x % C8, ty = threadIdx.x / C8, S = gridDim.x, sl = blockIdx.x;
   float* p1 = scratch; float* p2 = p1 + (size_t)groups * S * C; float* c1 = p2 + (size_t)groups * S * C; float* c2 = c1 + (size_t)groups * C;
   const int chunk = (rows + S - 1) / S, r0 = sl * chunk, r1 = min(rows, r0 + chunk);
@@ -550,25 +563,25 @@ int k_bn_bwd_fused(const void* x, const void* eo, void* ei, int rows, int C, int
 
 // ---------------------------------------------------------------- activations ---------------------------
 template <typename T>
-__global__ void act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, size_t n, int act, float alpha) {
+__global__ void act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, size_t n, int act, float alpha) { pdl_prologue();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) stf(y, i, act_fwd(act, ldf(x, i), alpha));
 }
 template <typename T>
-__global__ void act_bwd_out_kernel(const T* __restrict__ a, const T* __restrict__ eo, T* __restrict__ ei, size_t n, int act, float alpha) {
+__global__ void act_bwd_out_kernel(const T* __restrict__ a, const T* __restrict__ eo, T* __restrict__ ei, size_t n, int act, float alpha) { pdl_prologue();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     stf(ei, i, ldf(eo, i) * act_grad_from_out(act, ldf(a, i), alpha));
 }
 void k_act_fwd(int prec, const void* x, void* y, size_t n, int act, float alpha, cudaStream_t s) {
-  if (!n) return; DISPATCH_PREC(prec, T, (act_fwd_kernel<T><<<ew_blocks(n), 256, 0, s>>>((const T*)x, (T*)y, n, act, alpha))); LAUNCHED();
+  if (!n) return; DISPATCH_PREC(prec, T, (launch_pdl(act_fwd_kernel<T>, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, (const T*)x, (T*)y, n, act, alpha))); LAUNCHED();
 }
 void k_act_bwd_from_output(int prec, const void* a, const void* eo, void* ei, size_t n, int act, float alpha, cudaStream_t s) {
-  if (!n) return; DISPATCH_PREC(prec, T, (act_bwd_out_kernel<T><<<ew_blocks(n), 256, 0, s>>>((const T*)a, (const T*)eo, (T*)ei, n, act, alpha))); LAUNCHED();
+  if (!n) return; DISPATCH_PREC(prec, T, (launch_pdl(act_bwd_out_kernel<T>, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, (const T*)a, (const T*)eo, (T*)ei, n, act, alpha))); LAUNCHED();
 }
 void k_sigmoid_out(int prec, const void* z, void* p, size_t n, cudaStream_t s) { k_act_fwd(prec, z, p, n, ACT_SIGMOID, 0.f, s); }
 
 // ---------------------------------------------------------------- max-pool / upsample ---------------------
 template <typename T>
-__global__ void maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint8_t* __restrict__ arg, int N, int H, int W, int C, int OH, int OW, int KH, int KW, int SH, int SW) {
+__global__ void maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint8_t* __restrict__ arg, int N, int H, int W, int C, int OH, int OW, int KH, int KW, int SH, int SW) { pdl_prologue();
   size_t total = (size_t)N * OH * OW * C;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int c = i % C; size_t t = i / C; int ox = t % OW; t /= OW; int oy = t % OH; size_t n = t / OH;
@@ -581,7 +594,7 @@ __global__ void maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, u
   }
 }
 template <typename T>
-__global__ void maxpool_bwd_kernel(const T* __restrict__ eo, const uint8_t* __restrict__ arg, T* __restrict__ ei, int N, int H, int W, int C, int OH, int OW, int KH, int KW, int SH, int SW) {
+__global__ void maxpool_bwd_kernel(const T* __restrict__ eo, const uint8_t* __restrict__ arg, T* __restrict__ ei, int N, int H, int W, int C, int OH, int OW, int KH, int KW, int SH, int SW) { pdl_prologue();
   // gather form (deterministic): each input pixel sums the eps of the windows whose arg-max it is
   size_t total = (size_t)N * H * W * C;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -597,14 +610,14 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ eo, const uint8_t* __re
 }
 void k_maxpool_fwd(int prec, const void* x, void* y, uint8_t* arg, int N, int H, int W, int C, int OH, int OW, int KH, int KW, int SH, int SW, cudaStream_t s) {
   size_t n = (size_t)N * OH * OW * C; if (!n) return;
-  DISPATCH_PREC(prec, T, (maxpool_fwd_kernel<T><<<ew_blocks(n), 256, 0, s>>>((const T*)x, (T*)y, arg, N, H, W, C, OH, OW, KH, KW, SH, SW))); LAUNCHED();
+  DISPATCH_PREC(prec, T, (launch_pdl(maxpool_fwd_kernel<T>, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, (const T*)x, (T*)y, arg, N, H, W, C, OH, OW, KH, KW, SH, SW))); LAUNCHED();
 }
 void k_maxpool_bwd(int prec, const void* eo, const uint8_t* arg, void* ei, int N, int H, int W, int C, int OH, int OW, int KH, int KW, int SH, int SW, cudaStream_t s) {
   size_t n = (size_t)N * H * W * C; if (!n) return;
-  DISPATCH_PREC(prec, T, (maxpool_bwd_kernel<T><<<ew_blocks(n), 256, 0, s>>>((const T*)eo, arg, (T*)ei, N, H, W, C, OH, OW, KH, KW, SH, SW))); LAUNCHED();
+  DISPATCH_PREC(prec, T, (launch_pdl(maxpool_bwd_kernel<T>, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, (const T*)eo, arg, (T*)ei, N, H, W, C, OH, OW, KH, KW, SH, SW))); LAUNCHED();
 }
 template <typename T>
-__global__ void upsample_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int f) {
+__global__ void upsample_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int f) { pdl_prologue();
   size_t total = (size_t)N * H * f * W * f * C;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int c = i % C; size_t t = i / C; int ox = t % (W * f); t /= (W * f); int oy = t % (H * f); size_t n = t / (H * f);
@@ -612,7 +625,7 @@ __global__ void upsample_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, 
   }
 }
 template <typename T>
-__global__ void upsample_bwd_kernel(const T* __restrict__ eo, T* __restrict__ ei, int N, int H, int W, int C, int f) {
+__global__ void upsample_bwd_kernel(const T* __restrict__ eo, T* __restrict__ ei, int N, int H, int W, int C, int f) { pdl_prologue();
   size_t total = (size_t)N * H * W * C;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int c = i % C; size_t t = i / C; int ix = t % W; t /= W; int iy = t % H; size_t n = t / H;
@@ -623,17 +636,17 @@ __global__ void upsample_bwd_kernel(const T* __restrict__ eo, T* __restrict__ ei
 }
 void k_upsample_fwd(int prec, const void* x, void* y, int N, int H, int W, int C, int f, cudaStream_t s) {
   size_t n = (size_t)N * H * f * W * f * C; if (!n) return;
-  DISPATCH_PREC(prec, T, (upsample_fwd_kernel<T><<<ew_blocks(n), 256, 0, s>>>((const T*)x, (T*)y, N, H, W, C, f))); LAUNCHED();
+  DISPATCH_PREC(prec, T, (launch_pdl(upsample_fwd_kernel<T>, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, (const T*)x, (T*)y, N, H, W, C, f))); LAUNCHED();
 }
 void k_upsample_bwd(int prec, const void* eo, void* ei, int N, int H, int W, int C, int f, cudaStream_t s) {
   size_t n = (size_t)N * H * W * C; if (!n) return;
-  DISPATCH_PREC(prec, T, (upsample_bwd_kernel<T><<<ew_blocks(n), 256, 0, s>>>((const T*)eo, (T*)ei, N, H, W, C, f))); LAUNCHED();
+  DISPATCH_PREC(prec, T, (launch_pdl(upsample_bwd_kernel<T>, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, (const T*)eo, (T*)ei, N, H, W, C, f))); LAUNCHED();
 }
 
 // ---------------------------------------------------------------- XENT ---------------------------------
 // LossBinaryXENT + sigmoid on the logit (J:159-163): clip_eps>0 DL4J-exact, 0 = BCE-with-logits.
 template <typename T>
-__global__ void xent_kernel(const T* __restrict__ z, const float* __restrict__ y, T* __restrict__ dz, float* __restrict__ loss_sums, int rows, float clip) {
+__global__ void xent_kernel(const T* __restrict__ z, const float* __restrict__ y, T* __restrict__ dz, float* __restrict__ loss_sums, int rows, float clip) { pdl_prologue();
   int g = blockIdx.x;
   __shared__ double red[32];
   double acc = 0.0;
@@ -657,18 +670,18 @@ __global__ void xent_kernel(const T* __restrict__ z, const float* __restrict__ y
   if (threadIdx.x == 0) { double t = 0; for (int w = 0; w < (blockDim.x + 31) / 32; ++w) t += red[w]; loss_sums[g] = (float)t; }
 }
 void k_xent(int prec, const void* z, const float* y, void* dz, float* loss_sums, int rows, int groups, float clip, cudaStream_t s) {
-  DISPATCH_PREC(prec, T, (xent_kernel<T><<<groups, 1024, 0, s>>>((const T*)z, y, (T*)dz, loss_sums, rows, clip))); LAUNCHED();
+  DISPATCH_PREC(prec, T, (launch_pdl(xent_kernel<T>, dim3(groups), dim3(1024), (size_t)(0), s, (const T*)z, y, (T*)dz, loss_sums, rows, clip))); LAUNCHED();
 }
 
 // ---------------------------------------------------------------- column sum / misc reductions -----------
 template <typename T>
-__global__ void colsum_partial_kernel(const T* __restrict__ x, int rows, int C, int S, float* __restrict__ p) {
+__global__ void colsum_partial_kernel(const T* __restrict__ x, int rows, int C, int S, float* __restrict__ p) { pdl_prologue();
   int idx = blockIdx.x * blockDim.x + threadIdx.x; if (idx >= S * C) return;
   int c = idx % C, sl = idx / C; float a = 0.f;
   for (int r = sl; r < rows; r += S) a += ldf(x, (size_t)r * C + c);
   p[(size_t)sl * C + c] = a;
 }
-__global__ void __launch_bounds__(256) colsum_partial_bf16x8_kernel(const uint4* __restrict__ x, int rows, int C, int S, float* __restrict__ p) {
+__global__ void __launch_bounds__(256) colsum_partial_bf16x8_kernel(const uint4* __restrict__ x, int rows, int C, int S, float* __restrict__ p) { pdl_prologue();
   const int C8 = C / 8, TY = 256 / C8, c8 = threadIdx.x % C8, ty = threadIdx.x / C8, sl = blockIdx.x;
   const int chunk = (rows + S - 1) / S, r0 = sl * chunk, r1 = min(rows, r0 + chunk);
   float acc[1][8];
@@ -680,11 +693,17 @@ __global__ void __launch_bounds__(256) colsum_partial_bf16x8_kernel(const uint4*
   float* const dst[1] = {p};
   block_fold_write<1>(acc, C, C8, c8, ty, TY, dst, (size_t)sl * C);
 }
-__global__ void __launch_bounds__(512) colsum_final_kernel(const float* __restrict__ p, int C, int S, float* out, int accumulate) {
+__global__ void __launch_bounds__(512) colsum_final_kernel(const float* __restrict__ p, int C, int S, float* out, int accumulate) { pdl_prologue();
   __shared__ double sa[16][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, c = blockIdx.x * 32 + tx;
   double a = 0.0;
-  if (c < C) for (int sl = ty; sl < S; sl += 16) a += p[(size_t)sl * C + c];
+  if (c < C) for (int sl0 = ty; sl0 < S; sl0 += 16 * 8) {
+    float va[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { const int sl = sl0 + 16 * q; va[q] = sl < S ? p[(size_t)sl * C + c] : 0.f; }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a += va[q];
+  }
   sa[ty][tx] = a;
   __syncthreads();
   if (ty == 0 && c < C) { for (int k = 1; k < 16; ++k) a += sa[k][tx]; out[c] = (accumulate ? out[c] : 0.f) + (float)a; }
@@ -692,12 +711,12 @@ __global__ void __launch_bounds__(512) colsum_final_kernel(const float* __restri
 void k_colsum(int prec, const void* x, int rows, int C, float* scratch, float* out, int accumulate, cudaStream_t s) {
   const bool vec = vec_ok(prec, C);
   int S = vec ? vec_blocks(rows, C) : pick_slices(rows, C);
-  if (vec) colsum_partial_bf16x8_kernel<<<S, 256, 0, s>>>((const uint4*)x, rows, C, S, scratch);
-  else DISPATCH_PREC(prec, T, (colsum_partial_kernel<T><<<(S * C + 255) / 256, 256, 0, s>>>((const T*)x, rows, C, S, scratch)));
+  if (vec) launch_pdl(colsum_partial_bf16x8_kernel, dim3(S), dim3(256), (size_t)(0), s, (const uint4*)x, rows, C, S, scratch);
+  else DISPATCH_PREC(prec, T, (launch_pdl(colsum_partial_kernel<T>, dim3((S * C + 255) / 256), dim3(256), (size_t)(0), s, (const T*)x, rows, C, S, scratch)));
   LAUNCHED();
-  colsum_final_kernel<<<(C + 31) / 32, 512, 0, s>>>(scratch, C, S, out, accumulate); LAUNCHED();
+  launch_pdl(colsum_final_kernel, dim3((C + 31) / 32), dim3(512), (size_t)(0), s, scratch, C, S, out, accumulate); LAUNCHED();
 }
-__global__ void sumsq_segments_kernel(const float* __restrict__ p, const int64_t* off, const int64_t* len, const float* coef, int nseg, double* out) {
+__global__ void sumsq_segments_kernel(const float* __restrict__ p, const int64_t* off, const int64_t* len, const float* coef, int nseg, double* out) { pdl_prologue();
   __shared__ double red[32];
   double acc = 0.0;
   for (int sgi = 0; sgi < nseg; ++sgi) {
@@ -711,9 +730,9 @@ __global__ void sumsq_segments_kernel(const float* __restrict__ p, const int64_t
   if (threadIdx.x == 0) { double t = 0; for (int w = 0; w < (blockDim.x + 31) / 32; ++w) t += red[w]; *out = t; }
 }
 void k_sumsq_segments(const float* p, const int64_t* so, const int64_t* sl, const float* sc, int nseg, double* out, cudaStream_t s) {
-  sumsq_segments_kernel<<<1, 1024, 0, s>>>(p, so, sl, sc, nseg, out); LAUNCHED();
+  launch_pdl(sumsq_segments_kernel, dim3(1), dim3(1024), (size_t)(0), s, p, so, sl, sc, nseg, out); LAUNCHED();
 }
-__global__ void reduce_splits_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n, int splits, size_t stride, int accumulate) {
+__global__ void reduce_splits_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n, int splits, size_t stride, int accumulate) { pdl_prologue();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float a = accumulate ? dst[i] : 0.f;
     for (int k = 0; k < splits; ++k) a += src[(size_t)k * stride + i];
@@ -721,14 +740,14 @@ __global__ void reduce_splits_kernel(const float* __restrict__ src, float* __res
   }
 }
 void k_reduce_splits(const float* src, float* dst, size_t n, int splits, size_t stride, int accumulate, cudaStream_t s) {
-  if (!n) return; reduce_splits_kernel<<<ew_blocks(n), 256, 0, s>>>(src, dst, n, splits, stride, accumulate); LAUNCHED();
+  if (!n) return; launch_pdl(reduce_splits_kernel, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, src, dst, n, splits, stride, accumulate); LAUNCHED();
 }
 
 // ---------------------------------------------------------------- updater -------------------------------
 // One pass over params: 28 B/param for Adam (read p,g,m,v; write p,m,v), 20 B/param RmsProp, +2 B bf16 shadow.
 __global__ void __launch_bounds__(256) updater_kernel(float* __restrict__ params, const float* __restrict__ grads, float* __restrict__ st0, float* __restrict__ st1,
                                                       const UpdSeg* __restrict__ segs, const int32_t* __restrict__ chunk_seg, const int64_t* __restrict__ chunk_off,
-                                                      float inv_mb, float inv_world, const int* __restrict__ step, __nv_bfloat16* __restrict__ shadow) {
+                                                      float inv_mb, float inv_world, const int* __restrict__ step, __nv_bfloat16* __restrict__ shadow) { pdl_prologue();
   const UpdSeg sg = segs[chunk_seg[blockIdx.x]];
   const int64_t base = chunk_off[blockIdx.x];
   const int64_t end = min(base + (int64_t)UPD_CHUNK, sg.off + sg.len);
@@ -751,18 +770,18 @@ __global__ void __launch_bounds__(256) updater_kernel(float* __restrict__ params
 void k_updater(float* params, const float* grads, float* st0, float* st1, const UpdSeg* segs, const int32_t* chunk_seg, const int64_t* chunk_off,
                int nchunks, float inv_mb, float inv_world, const int* step_dev, __nv_bfloat16* shadow, cudaStream_t s) {
   if (!nchunks) return;
-  updater_kernel<<<nchunks, 256, 0, s>>>(params, grads, st0, st1, segs, chunk_seg, chunk_off, inv_mb, inv_world, step_dev, shadow); LAUNCHED();
+  launch_pdl(updater_kernel, dim3(nchunks), dim3(256), (size_t)(0), s, params, grads, st0, st1, segs, chunk_seg, chunk_off, inv_mb, inv_world, step_dev, shadow); LAUNCHED();
 }
 
-__global__ void inc_int_kernel(int* p) { *p += 1; }
-void k_inc_int(int* p, cudaStream_t s) { inc_int_kernel<<<1, 1, 0, s>>>(p); LAUNCHED(); }
-__global__ void fill_f32_kernel(float* p, float v, size_t n) {
+__global__ void inc_int_kernel(int* p) { pdl_prologue(); *p += 1; }
+void k_inc_int(int* p, cudaStream_t s) { launch_pdl(inc_int_kernel, dim3(1), dim3(1), (size_t)(0), s, p); LAUNCHED(); }
+__global__ void fill_f32_kernel(float* p, float v, size_t n) { pdl_prologue();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
-__global__ void scale_f32_kernel(float* p, float v, size_t n) {
+__global__ void scale_f32_kernel(float* p, float v, size_t n) { pdl_prologue();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] *= v;
 }
-void k_scale_f32(float* p, float v, size_t n, cudaStream_t s) { if (!n) return; scale_f32_kernel<<<ew_blocks(n), 256, 0, s>>>(p, v, n); LAUNCHED(); }
-void k_fill_f32(float* p, float v, size_t n, cudaStream_t s) { if (!n) return; fill_f32_kernel<<<ew_blocks(n), 256, 0, s>>>(p, v, n); LAUNCHED(); }
+void k_scale_f32(float* p, float v, size_t n, cudaStream_t s) { if (!n) return; launch_pdl(scale_f32_kernel, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, p, v, n); LAUNCHED(); }
+void k_fill_f32(float* p, float v, size_t n, cudaStream_t s) { if (!n) return; launch_pdl(fill_f32_kernel, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, p, v, n); LAUNCHED(); }
 
 }  // namespace b2g

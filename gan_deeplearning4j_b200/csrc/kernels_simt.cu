@@ -126,7 +126,7 @@ struct WgradProb {
 };
 
 template <class Prob>
-__global__ void __launch_bounds__(256) simt_gemm_kernel(Prob p, int k_per_split) {
+__global__ void __launch_bounds__(256) simt_gemm_kernel(Prob p, int k_per_split) { pdl_prologue();
   __shared__ float As[TK][TM + 4];
   __shared__ float Bs[TK][TN + 4];
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
@@ -159,13 +159,13 @@ template <typename T, typename TW>
 static void launch_fprop(const ConvGeom& g, const void* x, const void* w, const float* bias, void* out, int act, float alpha, cudaStream_t s) {
   FpropProb<T, TW> p{g, (const T*)x, (const TW*)w, bias, (T*)out, act, alpha, g.N * g.OH * g.OW, g.O, g.KH * g.KW * g.C};
   dim3 grid((p.Ncols + TN - 1) / TN, (p.M + TM - 1) / TM, 1);
-  simt_gemm_kernel<<<grid, 256, 0, s>>>(p, p.K); LAUNCHED();
+  launch_pdl(simt_gemm_kernel<FpropProb<T, TW>>, dim3(grid), dim3(256), (size_t)(0), s, p, p.K); LAUNCHED();
 }
 template <typename T, typename TW>
 static void launch_dgrad(const ConvGeom& g, const void* dy, const void* w, const float* bias, void* dx, int act, float alpha, cudaStream_t s) {
   DgradProb<T, TW> p{g, (const T*)dy, (const TW*)w, bias, (T*)dx, act, alpha, g.N * g.H * g.W, g.C, g.KH * g.KW * g.O};
   dim3 grid((p.Ncols + TN - 1) / TN, (p.M + TM - 1) / TM, 1);
-  simt_gemm_kernel<<<grid, 256, 0, s>>>(p, p.K); LAUNCHED();
+  launch_pdl(simt_gemm_kernel<DgradProb<T, TW>>, dim3(grid), dim3(256), (size_t)(0), s, p, p.K); LAUNCHED();
 }
 
 void k_simt_fprop(int prec, int wprec, const ConvGeom& g, const void* x, const void* w, const float* bias, void* out, int act, float alpha, cudaStream_t s) {
@@ -197,7 +197,7 @@ void k_simt_wgrad(int prec, const ConvGeom& g, const void* x, const void* dy, fl
   float* dst = (sp > 1 || accumulate) ? scratch : dw;
   if (sp == 1 && accumulate && scratch_floats < n) { dst = dw; accumulate = 0; }   // caller guarantees scratch when accumulating
   dim3 grid((int)((g.KH * g.KW * g.C + TN - 1) / TN), (g.O + TM - 1) / TM, sp);
-  DISPATCH_PREC(prec, T, (simt_gemm_kernel<<<grid, 256, 0, s>>>(WgradProb<T>{g, (const T*)x, (const T*)dy, dst, n, g.O, g.KH * g.KW * g.C, P}, kps))); LAUNCHED();
+  DISPATCH_PREC(prec, T, (launch_pdl(simt_gemm_kernel<WgradProb<T>>, dim3(grid), dim3(256), (size_t)(0), s, WgradProb<T>{g, (const T*)x, (const T*)dy, dst, n, g.O, g.KH * g.KW * g.C, P}, kps))); LAUNCHED();
   if (dst != dw) k_reduce_splits(dst, dw, n, sp, n, accumulate, s);
 }
 

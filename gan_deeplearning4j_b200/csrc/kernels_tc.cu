@@ -148,7 +148,7 @@ struct TcSmem {
 // weight tile and TMA-multicasts them into every CTA of the cluster, so the weight traffic out of L2 drops by CL; a stage is
 // refilled only after all CL MMA issuers have committed it (tcgen05.commit multicast onto every CTA's "empty" barrier).
 template <int BN, int STAGES, int CL>
-__global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcConvParams p) {
+__global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcConvParams p) { pdl_prologue();
   using S = TcSmem<BN, STAGES>;
   const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
   constexpr uint16_t cmask = (uint16_t)((1u << CL) - 1u);
@@ -283,7 +283,7 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcC
   static bool attr_set = false;
   if (!attr_set) { if (cudaFuncSetAttribute(tc_conv_kernel<BN, STAGES, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) return -2; attr_set = true; }
   if (CL == 1) {
-    tc_conv_kernel<BN, STAGES, CL><<<grid, 192, S::TOTAL, s>>>(tmA, tmB, p);
+    launch_pdl(tc_conv_kernel<BN, STAGES, CL>, dim3(grid), dim3(192), (size_t)(S::TOTAL), s, tmA, tmB, p);
   } else {
     cudaLaunchConfig_t cfg{}; cfg.gridDim = grid; cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = S::TOTAL; cfg.stream = s;
     cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -387,7 +387,7 @@ struct TcWgradSmem {
 };
 
 template <int BNW, int STAGES>
-__global__ void __launch_bounds__(192) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, const TcWgradParams p) {
+__global__ void __launch_bounds__(192) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, const TcWgradParams p) { pdl_prologue();
   using S = TcWgradSmem<BNW, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -489,7 +489,7 @@ static int launch_wgrad(const CUtensorMap& tmDy, const CUtensorMap& tmX, const T
   using S = TcWgradSmem<BNW, STAGES>;
   static bool attr_set = false;
   if (!attr_set) { if (cudaFuncSetAttribute(tc_wgrad_kernel<BNW, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) return -2; attr_set = true; }
-  tc_wgrad_kernel<BNW, STAGES><<<grid, 192, S::TOTAL, s>>>(tmDy, tmX, p);
+  launch_pdl(tc_wgrad_kernel<BNW, STAGES>, dim3(grid), dim3(192), (size_t)(S::TOTAL), s, tmDy, tmX, p);
   LAUNCHED();
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
 }
