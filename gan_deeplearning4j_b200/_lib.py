@@ -24,7 +24,8 @@ class LayerDesc(C.Structure):
                 ("k_h", C.c_int32), ("k_w", C.c_int32), ("s_h", C.c_int32), ("s_w", C.c_int32), ("p_h", C.c_int32), ("p_w", C.c_int32),
                 ("has_bias", C.c_int32), ("act", C.c_int32), ("act_alpha", C.c_float), ("updater", C.c_int32),
                 ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("l2", C.c_float),
-                ("bn_decay", C.c_float), ("bn_eps", C.c_float), ("pre_h", C.c_int32), ("pre_w", C.c_int32), ("pre_c", C.c_int32)]
+                ("bn_decay", C.c_float), ("bn_eps", C.c_float), ("pre_h", C.c_int32), ("pre_w", C.c_int32), ("pre_c", C.c_int32),
+                ("loss", C.c_int32), ("frozen", C.c_int32)]
 
 
 class NetConfig(C.Structure):

@@ -186,7 +186,7 @@ static int32_t net_build(b2g_net* n, const b2g_layer_desc* layers, int32_t nl) {
         l.wA = d.n_out; l.wTaps = 1; l.wB = d.n_in;                        // 'f'-order [nIn,nOut] == row-major [nOut][nIn]
         l.off_W = off; l.n_W = (int64_t)d.n_in * d.n_out; off += l.n_W;    // DefaultParamInitializer: [W | b]
         if (d.has_bias) { l.off_b = off; off += d.n_out; }
-        if (d.type == B2G_LAYER_OUTPUT) { d.act = B2G_ACT_IDENTITY; if (d.n_out != 1) return fail(B2G_ERR_UNSUPPORTED, "layer %s: XENT output supports nOut=1", d.name); }
+        if (d.type == B2G_LAYER_OUTPUT) { d.act = B2G_ACT_IDENTITY; if (d.loss == B2G_LOSS_XENT && d.n_out != 1) return fail(B2G_ERR_UNSUPPORTED, "layer %s: XENT output supports nOut=1 (use MCXENT for nOut>1)", d.name); }
       } break;
       case B2G_LAYER_BATCHNORM: {
         d.n_in = d.n_out = ch; l.oh = h; l.ow = w; l.oc = ch;
@@ -232,7 +232,7 @@ static int32_t net_alloc(b2g_net* n) {
   if (n->n_shadow) B2(dalloc(n, &n->shadow, sizeof(__nv_bfloat16) * n->n_shadow));
   B2(dalloc(n, &n->barrier_dev, sizeof(unsigned)));
   B2(dalloc(n, &n->step_dev, sizeof(int))); B2(dalloc(n, &n->loss_dev, sizeof(float) * 8)); B2(dalloc(n, &n->l2_dev, sizeof(double)));
-  B2(dalloc(n, &n->labels_dev, sizeof(float) * R));
+  B2(dalloc(n, &n->labels_dev, sizeof(float) * R * std::max<size_t>(1, n->L.back().out_elems)));
   B2(dalloc(n, (char**)&n->input, ts * R * n->in_elems));
   size_t max_act = n->in_elems, scratch = 1 << 16, max_w = 0;
   for (auto& l : n->L) {
@@ -278,6 +278,7 @@ static int32_t net_init_params_and_updater(b2g_net* n) {
   for (auto& l : n->L) {
     const b2g_layer_desc& d = l.d;
     auto add_seg = [&](int64_t off, int64_t len, bool weight, bool noop) {
+      if (d.frozen) return;      // FrozenLayer: no update, no l2 decay, no l2 score (calcL2() == 0)
       UpdSeg sg{}; sg.off = off; sg.len = len; sg.kind = noop ? 3 : updater_kind(d.updater);
       sg.lr = d.lr; sg.b1 = d.beta1; sg.b2 = d.beta2; sg.eps = d.eps; sg.l2 = weight ? d.l2 : 0.f; sg.clip = n->cfg.grad_clip; sg.div_mb = noop ? 0 : 1;
       sg.off_bf = (weight && l.off_W_bf >= 0) ? l.off_W_bf : -1; sg.off_bft = -1; n->segs.push_back(sg);
@@ -394,11 +395,12 @@ static int32_t net_forward(b2g_net* n, const void* in, const FwdOpts& o, const v
       case B2G_LAYER_DECONV2D: { ConvGeom g = l.geom; g.N = R; B2(gemm_dgrad(n, l, g, cur, bias, out, d.act, d.act_alpha)); } break;
       case B2G_LAYER_BATCHNORM: {
         int rows_pg = (R / o.groups) * l.oh * l.ow;
-        if (o.train && k_bn_fused_ok(n->prec, l.oc, o.groups) &&
+        const bool bn_train = o.train && !d.frozen;      // FrozenLayer always activates in test mode
+        if (bn_train && k_bn_fused_ok(n->prec, l.oc, o.groups) &&
             k_bn_fwd_fused(cur, out, rows_pg, l.oc, o.groups, n->scratch, l.bn_mean, l.bn_invstd, n->params + l.off_gamma, n->params + l.off_beta, l.fused_act, l.fused_alpha, d.bn_eps,
                            n->params + l.off_mean, n->params + l.off_var, o.update_running ? n->grads + l.off_mean : nullptr, o.update_running ? n->grads + l.off_var : nullptr, d.bn_decay,
                            n->barrier_dev, s) == 0) break;
-        if (o.train) k_bn_stats(n->prec, cur, rows_pg, l.oc, o.groups, n->scratch, l.bn_mean, l.bn_invstd, d.bn_eps, n->params + l.off_mean, n->params + l.off_var,
+        if (bn_train) k_bn_stats(n->prec, cur, rows_pg, l.oc, o.groups, n->scratch, l.bn_mean, l.bn_invstd, d.bn_eps, n->params + l.off_mean, n->params + l.off_var,
                                 o.update_running ? n->grads + l.off_mean : nullptr, o.update_running ? n->grads + l.off_var : nullptr, d.bn_decay, s);
         else k_bn_prep_infer(n->params + l.off_mean, n->params + l.off_var, l.oc, o.groups, d.bn_eps, l.bn_mean, l.bn_invstd, s);
         k_bn_apply(n->prec, cur, out, rows_pg, l.oc, o.groups, l.bn_mean, l.bn_invstd, n->params + l.off_gamma, n->params + l.off_beta, l.fused_act, l.fused_alpha, s);
@@ -446,13 +448,14 @@ static int32_t net_backward(b2g_net* n, const void* net_in, void* eps, int rows,
     const void* lin = i == 0 ? net_in : n->L[i - 1].out;
     // the epsilon w.r.t. this layer's input is needed only if a trainable layer sits below it (or the caller wants d/d input)
     bool need_in = need_input_grad;
-    if (!need_in) for (int j = 0; j < i; ++j) if (n->L[j].has_gemm() || n->L[j].d.type == B2G_LAYER_BATCHNORM) need_in = true;
+    if (!need_in) for (int j = 0; j < i; ++j) if (!n->L[j].d.frozen && (n->L[j].has_gemm() || n->L[j].d.type == B2G_LAYER_BATCHNORM)) need_in = true;
+    const bool want_wgrad_l = want_wgrad && !d.frozen;
     switch (d.type) {
       case B2G_LAYER_LOSS: break;
       case B2G_LAYER_CONV2D: case B2G_LAYER_DENSE: case B2G_LAYER_OUTPUT: {
         ConvGeom g = l.geom; g.N = R;
         if (d.act != B2G_ACT_IDENTITY) k_act_bwd_from_output(n->prec, l.out, cur, cur, (size_t)R * l.out_elems, d.act, d.act_alpha, s);
-        if (want_wgrad) {
+        if (want_wgrad_l) {
           fork_wgrad(i, cur);
           B2(gemm_wgrad(n, l, g, lin, cur, n->grads + l.off_W, s2, n->scratch2));
           if (l.off_b >= 0) k_colsum(n->prec, cur, R * l.oh * l.ow, l.oc, n->scratch2, n->grads + l.off_b, 0, s2);
@@ -463,7 +466,7 @@ static int32_t net_backward(b2g_net* n, const void* net_in, void* eps, int rows,
       case B2G_LAYER_DECONV2D: {
         ConvGeom g = l.geom; g.N = R;
         if (d.act != B2G_ACT_IDENTITY) k_act_bwd_from_output(n->prec, l.out, cur, cur, (size_t)R * l.out_elems, d.act, d.act_alpha, s);
-        if (want_wgrad) {
+        if (want_wgrad_l) {
           fork_wgrad(i, cur);
           B2(gemm_wgrad(n, l, g, /*conv input = deconv out grad*/ cur, /*conv dy = deconv input*/ lin, n->grads + l.off_W, s2, n->scratch2));
           if (l.off_b >= 0) k_colsum(n->prec, cur, R * l.oh * l.ow, l.oc, n->scratch2, n->grads + l.off_b, 0, s2);
@@ -475,9 +478,9 @@ static int32_t net_backward(b2g_net* n, const void* net_in, void* eps, int rows,
         int rows_pg = (R / groups) * l.oh * l.ow; void* nx = need_in ? other(cur) : nullptr;
         if (k_bn_fused_ok(n->prec, l.oc, groups) &&
             k_bn_bwd_fused(lin, cur, nx, rows_pg, l.oc, groups, l.bn_mean, l.bn_invstd, n->params + l.off_gamma, n->params + l.off_beta, l.fused_act, l.fused_alpha, n->scratch,
-                           n->grads + l.off_gamma, n->grads + l.off_beta, want_wgrad ? 1 : 0, n->barrier_dev, s) == 0) { if (need_in) cur = nx; break; }
+                           n->grads + l.off_gamma, n->grads + l.off_beta, want_wgrad_l ? 1 : 0, n->barrier_dev, s) == 0) { if (need_in) cur = nx; break; }
         k_bn_bwd(n->prec, lin, cur, nx, rows_pg, l.oc, groups, l.bn_mean, l.bn_invstd, n->params + l.off_gamma, n->params + l.off_beta, l.fused_act, l.fused_alpha,
-                 n->scratch, n->grads + l.off_gamma, n->grads + l.off_beta, want_wgrad ? 1 : 0, s);
+                 n->scratch, n->grads + l.off_gamma, n->grads + l.off_beta, want_wgrad_l ? 1 : 0, s);
         if (need_in) cur = nx;
       } break;
       case B2G_LAYER_ACTIVATION: if (!l.act_fused_into_prev) k_act_bwd_from_output(n->prec, l.out, cur, cur, (size_t)R * l.out_elems, d.act, d.act_alpha, s); break;
@@ -672,7 +675,8 @@ extern "C" int32_t b2g_net_output(b2g_net* n, const float* x, int32_t batch, int
   const void* res = nullptr; FwdOpts o{batch, 1, train != 0, false, nullptr};
   B2(net_forward(n, n->input, o, &res));
   LayerRT& l = n->L.back();
-  if (l.d.type == B2G_LAYER_OUTPUT || l.d.type == B2G_LAYER_LOSS) { k_sigmoid_out(n->prec, res, l.probs, (size_t)batch * l.out_elems, n->ctx->stream); res = l.probs; }
+  if (l.d.type == B2G_LAYER_OUTPUT && l.d.loss == B2G_LOSS_MCXENT) { k_softmax_xent(n->prec, res, nullptr, nullptr, l.probs, nullptr, batch, l.oc, n->ctx->stream); res = l.probs; }
+  else if (l.d.type == B2G_LAYER_OUTPUT || l.d.type == B2G_LAYER_LOSS) { k_sigmoid_out(n->prec, res, l.probs, (size_t)batch * l.out_elems, n->ctx->stream); res = l.probs; }
   return download_act(n, res, batch, l.oc, l.oh * l.ow, out);
 }
 extern "C" int32_t b2g_net_get_activation(b2g_net* n, int32_t layer, int32_t batch, float* host) {
@@ -681,17 +685,22 @@ extern "C" int32_t b2g_net_get_activation(b2g_net* n, int32_t layer, int32_t bat
   return download_act(n, l.out, batch, l.oc, l.oh * l.ow, host);
 }
 
+static void net_loss(b2g_net* n, const void* logits, const float* labels, void* dz, float* loss_sums, int rows_per_group, int groups) {
+  const LayerRT& l = n->L.back();
+  if (l.d.type == B2G_LAYER_OUTPUT && l.d.loss == B2G_LOSS_MCXENT) k_softmax_xent(n->prec, logits, labels, dz, nullptr, loss_sums, rows_per_group * groups, l.oc, n->ctx->stream);
+  else k_xent(n->prec, logits, labels, dz, loss_sums, rows_per_group, groups, n->cfg.xent_clip_eps, n->ctx->stream);
+}
 static int32_t train_pass(b2g_net* n, const float* x, const float* y, int batch, bool do_update, float* score) {
   cudaStream_t s = n->ctx->stream;
   if (batch < 1 || batch > n->max_rows) return fail(B2G_ERR_SHAPE, "batch %d outside [1,%d]", batch, n->max_rows);
   int lt = n->L.back().d.type;
   if (lt != B2G_LAYER_OUTPUT && lt != B2G_LAYER_LOSS) return fail(B2G_ERR_UNSUPPORTED, "fit needs a net ending in OutputLayer/LossLayer (XENT)");
   B2(upload_input(n, x, batch, n->input));
-  CU(cudaMemcpyAsync(n->labels_dev, y, sizeof(float) * batch, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(n->labels_dev, y, sizeof(float) * batch * n->L.back().out_elems, cudaMemcpyHostToDevice, s));
   CU(cudaMemsetAsync(n->grads, 0, sizeof(float) * n->n_params, s));
   const void* logits = nullptr; FwdOpts o{batch, 1, true, true, nullptr};
   B2(net_forward(n, n->input, o, &logits));
-  k_xent(n->prec, logits, n->labels_dev, n->epsA, n->loss_dev, batch, 1, n->cfg.xent_clip_eps, s);
+  net_loss(n, logits, n->labels_dev, n->epsA, n->loss_dev, batch, 1);
   B2(net_backward(n, n->input, n->epsA, batch, 1, true, false));
   if (score) {
     double l2 = 0.0; float ls = 0.f;
@@ -768,6 +777,7 @@ extern "C" int32_t b2g_gan_create(b2g_net* gen, b2g_net* dis, const b2g_gan_conf
   if (gen->prec != dis->prec) return fail(B2G_ERR_ARG, "generator and discriminator use different precisions");
   if (gen->L.back().out_elems != dis->in_elems) return fail(B2G_ERR_SHAPE, "generator output (%zu) != discriminator input (%zu)", gen->L.back().out_elems, dis->in_elems);
   if (gen->L.back().out_alias) return fail(B2G_ERR_UNSUPPORTED, "generator must end in a layer that owns its output");
+  if (dis->L.back().d.type == B2G_LAYER_OUTPUT && dis->L.back().d.loss != B2G_LOSS_XENT) return fail(B2G_ERR_UNSUPPORTED, "the adversarial step needs a binary XENT discriminator");
   if (dis->cfg.bn_groups < 2 || dis->max_rows < 2) return fail(B2G_ERR_ARG, "discriminator must be created with bn_groups>=2 and max_batch = 2*N");
   int N = std::min(gen->max_rows, dis->max_rows / 2);
   CU(cudaSetDevice(gen->ctx->device));

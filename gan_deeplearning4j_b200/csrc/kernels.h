@@ -69,6 +69,8 @@ void k_upsample_bwd(int prec, const void* eps_out, void* eps_in, int N, int H, i
 // LossBinaryXENT on logits z[rows] with labels y[rows]: dz = dL/dz (sum form, not /mb), loss_sums[g] = sum of losses per group.
 void k_xent(int prec, const void* z, const float* y, void* dz, float* loss_sums, int rows_per_group, int groups, float clip_eps, cudaStream_t s);
 void k_sigmoid_out(int prec, const void* z, void* p, size_t n, cudaStream_t s);
+// LossMCXENT + softmax over K classes: dz = softmax(z) - y, loss_sums[0] = -sum y log clip(p, 1e-10); p_out optional (probabilities)
+void k_softmax_xent(int prec, const void* z, const float* y, void* dz, void* p_out, float* loss_sums, int rows, int K, cudaStream_t s);
 
 // ---- reductions ------------------------------------------------------------------------------------
 // out[c] (+)= sum_rows x[row][c]

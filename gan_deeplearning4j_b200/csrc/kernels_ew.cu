@@ -673,6 +673,29 @@ void k_xent(int prec, const void* z, const float* y, void* dz, float* loss_sums,
   DISPATCH_PREC(prec, T, (launch_pdl(xent_kernel<T>, dim3(groups), dim3(1024), (size_t)(0), s, (const T*)z, y, (T*)dz, loss_sums, rows, clip))); LAUNCHED();
 }
 
+// LossMCXENT with softmax (J:357-362), K classes per row: one thread per row, block-level loss sum
+template <typename T>
+__global__ void softmax_xent_kernel(const T* __restrict__ z, const float* __restrict__ y, T* __restrict__ dz, T* __restrict__ p_out, float* __restrict__ loss_sum, int rows, int K) { pdl_prologue();
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+    float m = -INFINITY; for (int k = 0; k < K; ++k) m = fmaxf(m, ldf(z, (size_t)r * K + k));
+    float den = 0.f; for (int k = 0; k < K; ++k) den += expf(ldf(z, (size_t)r * K + k) - m);
+    for (int k = 0; k < K; ++k) {
+      const float p = expf(ldf(z, (size_t)r * K + k) - m) / den;
+      if (p_out) stf(p_out, (size_t)r * K + k, p);
+      if (dz) { const float yk = y[(size_t)r * K + k]; stf(dz, (size_t)r * K + k, p - yk); acc -= (double)yk * log((double)fminf(fmaxf(p, 1e-10f), 1.0f - 1e-10f)); }
+    }
+  }
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0 && loss_sum) { double t = 0; for (int w = 0; w < (blockDim.x + 31) / 32; ++w) t += red[w]; loss_sum[0] = (float)t; }
+}
+void k_softmax_xent(int prec, const void* z, const float* y, void* dz, void* p_out, float* loss_sums, int rows, int K, cudaStream_t s) {
+  DISPATCH_PREC(prec, T, (launch_pdl(softmax_xent_kernel<T>, dim3(1), dim3(1024), (size_t)0, s, (const T*)z, y, (T*)dz, (T*)p_out, loss_sums, rows, K))); LAUNCHED();
+}
+
 // ---------------------------------------------------------------- column sum / misc reductions -----------
 template <typename T>
 __global__ void colsum_partial_kernel(const T* __restrict__ x, int rows, int C, int S, float* __restrict__ p) { pdl_prologue();

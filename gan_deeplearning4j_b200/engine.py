@@ -52,6 +52,8 @@ def layer_desc(spec: Dict) -> LayerDesc:
     d.bn_decay, d.bn_eps = spec.get("decay", 0.9), spec.get("eps", 1e-5)
     to = spec.get("to", (0, 0, 0))      # FeedForwardToCnnPreProcessor(h, w, c)
     d.pre_h, d.pre_w, d.pre_c = to
+    d.loss = {"xent": 0, "mcxent": 1}[spec.get("loss", "xent")]
+    d.frozen = 1 if spec.get("frozen", False) else 0
     return d
 
 

@@ -58,6 +58,15 @@ def reference_gan(gen_lr=0.004, z=2) -> List[Dict]:
     return reference_generator(gen_lr, z, "gan") + reference_discriminator(0.0, "gan_dis")
 
 
+def reference_computer_vision(lr=0.002, n_classes=10) -> List[Dict]:
+    """J:337-364: the discriminator trunk frozen up to dis_dense_layer_6 (setFeatureExtractor), its output layer replaced by
+    BatchNormalization(1024) "dis_batch" + OutputLayer(MCXENT, softmax, 10).  Input (1,28,28), grad_clip=1.0."""
+    trunk = [dict(s, frozen=True) for s in reference_discriminator(lr)[:-1]]
+    u = lambda: rmsprop(lr, 1e-8, 1e-8)
+    return trunk + [{"type": "batchnorm", "name": "dis_batch", "updater": u()},
+                    {"type": "output", "name": "dis_output_layer_7", "n_out": n_classes, "loss": "mcxent", "updater": u(), "l2": 1e-4}]
+
+
 # ------------------------------------------------------------------ C2-C4: DCGAN -----------------------
 def dcgan_generator(size=64, z=100, nf=64, nc=3, lr=2e-4, beta1=0.5) -> List[Dict]:
     """ConvolutionTranspose2D(4x4)+BatchNorm+ReLU stack, tanh output.  Input (z,)."""

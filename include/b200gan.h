@@ -74,6 +74,7 @@ typedef enum {               /* org.nd4j.linalg.learning.config.*  J:133 (RmsPro
 } b2g_updater;
 
 typedef enum { B2G_PREC_FP32 = 0, B2G_PREC_BF16 = 1 } b2g_precision;
+typedef enum { B2G_LOSS_XENT = 0, B2G_LOSS_MCXENT = 1 } b2g_loss;
 
 /* One layer of a chain-shaped ComputationGraph (every graph in the reference is a chain, J:118-310). */
 typedef struct {
@@ -89,6 +90,8 @@ typedef struct {
   float l2;                     /* .l2(1e-4) (J:125): weights only, applied AFTER the updater, not lr-scaled */
   float bn_decay, bn_eps;       /* BatchNormalization defaults 0.9 / 1e-5 */
   int32_t pre_h, pre_w, pre_c;  /* FF_TO_CNN target shape */
+  int32_t loss;                 /* OUTPUT layer: 0 = LossFunction.XENT + sigmoid (J:159-163), 1 = MCXENT + softmax (J:357-362) */
+  int32_t frozen;               /* TransferLearning.setFeatureExtractor (J:350): FrozenLayer = test-mode forward, no gradient, no update */
 } b2g_layer_desc;
 
 typedef struct {
@@ -143,7 +146,8 @@ int32_t b2g_net_output(b2g_net* net, const float* x, int32_t batch, int32_t trai
 /* Activations of one layer from the most recent forward (parity tests): NCHW fp32. */
 int32_t b2g_net_get_activation(b2g_net* net, int32_t layer, int32_t batch, float* host);
 /* computeGradientAndScore(): train-mode forward, XENT loss vs labels y [batch,1], backprop.
- * score = sum(loss)/batch + 0.5*l2*||W||^2 ; gradients stay on device (b2g_net_get_gradients). */
+ * score = sum(loss)/batch + 0.5*l2*||W||^2 ; gradients stay on device (b2g_net_get_gradients).
+ * Labels y are [batch, nOut] (nOut = 1 for XENT; one-hot rows for MCXENT). */
 int32_t b2g_net_compute_gradient_and_score(b2g_net* net, const float* x, const float* y, int32_t batch, float* score);
 /* epsilon w.r.t. the network input from the last backward (NCHW fp32; what the stacked gan graph feeds the generator). */
 int32_t b2g_net_get_input_gradient(b2g_net* net, int32_t batch, float* host);

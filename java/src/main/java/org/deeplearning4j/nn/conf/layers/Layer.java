@@ -6,8 +6,8 @@ import org.nd4j.linalg.activations.Activation;
 import org.nd4j.linalg.learning.config.IUpdater;
 
 public class Layer {
-    public static final int DESC_BYTES = 4 + 64 + 4 * 2 + 4 * 6 + 4 + 4 + 4 + 4 + 4 * 4 + 4 + 4 * 2 + 4 * 3;   // == sizeof(b2g_layer_desc) = 156
-    public int type, nIn, nOut, kH = 1, kW = 1, sH = 1, sW = 1, pH, pW, hasBias = 1, act = -1, preH, preW, preC;
+    public static final int DESC_BYTES = 4 + 64 + 4 * 2 + 4 * 6 + 4 + 4 + 4 + 4 + 4 * 4 + 4 + 4 * 2 + 4 * 3 + 4 * 2;   // == sizeof(b2g_layer_desc) = 164
+    public int type, nIn, nOut, kH = 1, kW = 1, sH = 1, sW = 1, pH, pW, hasBias = 1, act = -1, preH, preW, preC, loss, frozen;
     public float alpha = 0.01f, l2 = Float.NaN, bnDecay = 0.9f, bnEps = 1e-5f;
     public IUpdater updater; public String name = "";
 
@@ -17,8 +17,10 @@ public class Layer {
         b.putInt(nIn).putInt(nOut).putInt(kH).putInt(kW).putInt(sH).putInt(sW).putInt(pH).putInt(pW).putInt(hasBias);
         b.putInt(act >= 0 ? act : defaultAct(globalAct)).putFloat(alpha);
         b.putInt(updater == null ? 0 : updater.kind()).putFloat(updater == null ? 0f : updater.lr()).putFloat(updater == null ? 0f : updater.beta1()).putFloat(updater == null ? 0f : updater.beta2()).putFloat(updater == null ? 1e-8f : updater.eps());
-        b.putFloat(Float.isNaN(l2) ? globalL2 : l2).putFloat(bnDecay).putFloat(bnEps).putInt(preH).putInt(preW).putInt(preC);
+        b.putFloat(Float.isNaN(l2) ? globalL2 : l2).putFloat(bnDecay).putFloat(bnEps).putInt(preH).putInt(preW).putInt(preC).putInt(loss).putInt(frozen);
     }
+    public Layer copy() { Layer c = new Layer(); c.type = type; c.nIn = nIn; c.nOut = nOut; c.kH = kH; c.kW = kW; c.sH = sH; c.sW = sW; c.pH = pH; c.pW = pW; c.hasBias = hasBias; c.act = act;
+        c.preH = preH; c.preW = preW; c.preC = preC; c.loss = loss; c.frozen = frozen; c.alpha = alpha; c.l2 = l2; c.bnDecay = bnDecay; c.bnEps = bnEps; c.updater = updater; c.name = name; return c; }
     protected int defaultAct(Activation g) { return g.code; }   // conv / dense inherit the global .activation(..) (J:126)
 
     @SuppressWarnings("unchecked")

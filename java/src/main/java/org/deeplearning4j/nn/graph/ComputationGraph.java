@@ -26,6 +26,7 @@ public class ComputationGraph {
         net = h.getLong(0);
     }
     public long handle() { return net; }
+    public ComputationGraphConfiguration configuration() { return conf; }
     public long numParams() { ByteBuffer o = Native.direct(8); Native.check(Native.netNumParams(net, Native.address(o))); return o.getLong(0); }
     public String summary() { StringBuilder s = new StringBuilder("b200gan ComputationGraph, params=" + numParams() + "\n"); for (Layer l : layers) s.append("  ").append(l.name).append(" type=").append(l.type).append(" nOut=").append(l.nOut).append("\n"); return s.toString(); }
 
@@ -36,7 +37,7 @@ public class ComputationGraph {
         Native.check(Native.netOutput(net, Native.address(in), batch, 0, Native.address(out)));
         float[] d = new float[batch * per]; out.get(d); return new INDArray[] { new INDArray(d, batch, per) };
     }
-    private int outElems() { Layer last = layers.get(layers.size() - 1); return last.type == 7 || last.type == 8 ? 1 : Integer.getInteger("b200gan.outElems", 784); }
+    private int outElems() { Layer last = layers.get(layers.size() - 1); return last.type == 7 ? Math.max(1, last.nOut) : last.type == 8 ? 1 : Integer.getInteger("b200gan.outElems", 784); }
 
     /** fit(DataSet): one minibatch = computeGradientAndScore + updater + params.subi (what SparkComputationGraph.fit reaches, SURVEY.md 3.3). */
     public void fit(DataSet ds) {

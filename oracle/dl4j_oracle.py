@@ -541,6 +541,36 @@ class Output(Dense):
         return eps @ self.params["W"].T
 
 
+def mcxent_softmax_score_and_grad(z: np.ndarray, y: np.ndarray, clip_eps: float = 1e-10):
+    """LossMCXENT with a softmax activation (J:357-362): p = softmax(z) clipped to [eps, 1-eps] for the log
+    (softmaxClipEps default 1e-10); loss = -sum y log p; dL/dz = p - y (DL4J's softmax+MCXENT shortcut)."""
+    zs = z - z.max(1, keepdims=True)
+    e = np.exp(zs)
+    p = e / e.sum(1, keepdims=True)
+    pc = np.clip(p, clip_eps, 1 - clip_eps) if clip_eps > 0 else p
+    return float(-(y * np.log(pc)).sum()), p - y
+
+
+class OutputSoftmax(Dense):
+    """OutputLayer.Builder(LossFunction.MCXENT).activation(Activation.SOFTMAX).nOut(10) (J:357-362): the transfer-learning head."""
+
+    def __init__(self, n_in, n_out, updater=None, l2=0.0, name=""):
+        super().__init__(n_in, n_out, activation="identity", updater=updater, l2=l2, name=name)
+
+    def forward(self, x, train):
+        z = super().forward(x, train)
+        e = np.exp(z - z.max(1, keepdims=True))
+        return e / e.sum(1, keepdims=True)
+
+    def score_and_eps(self, y):
+        return mcxent_softmax_score_and_grad(self._z, y)
+
+    def backward(self, eps):
+        self.grads["W"] = self._x.T @ eps
+        self.grads["b"] = eps.sum(0)
+        return eps @ self.params["W"].T
+
+
 # --------------------------------------------------------------------------------------------------
 # Network = ComputationGraph restricted to a chain (every graph in the reference is a chain).
 # --------------------------------------------------------------------------------------------------
@@ -589,7 +619,9 @@ class Net:
             off += n
 
     def grads_flat(self):
-        return np.concatenate([self.layers[li].grads[p].ravel(order=o.upper()) for li, _, p, _, o in self.param_table()])
+        """ComputationGraph.gradient() flattened; frozen layers (no gradient) contribute zeros."""
+        return np.concatenate([(self.layers[li].grads[p] if p in self.layers[li].grads else np.zeros(sh, self.dtype)).ravel(order=o.upper())
+                               for li, _, p, sh, o in self.param_table()])
 
     def layer(self, name) -> Layer:
         for l in self.layers:
@@ -602,7 +634,8 @@ class Net:
         acts = []
         a = np.asarray(x, self.dtype)
         for l in self.layers:
-            a = l.forward(a, train)
+            # FrozenLayer (TransferLearning.setFeatureExtractor, J:350) always runs its layer in test mode
+            a = l.forward(a, train and not getattr(l, "frozen", False))
             if collect:
                 acts.append(a)
         return (a, acts) if collect else a
@@ -625,7 +658,7 @@ class Net:
     def l2_score(self):
         s = 0.0
         for l in self.layers:
-            if l.has_params and l.l2:
+            if l.has_params and l.l2 and not getattr(l, "frozen", False):     # FrozenLayer.calcL2() == 0
                 for p in l.l2_names():
                     s += 0.5 * l.l2 * float((l.params[p].astype(np.float64) ** 2).sum())
         return s
@@ -638,7 +671,7 @@ class Net:
         y = np.asarray(y, self.dtype)
         loss_sum, eps = last.score_and_eps(y)
         mb = x.shape[0]
-        if isinstance(last, Output):
+        if isinstance(last, (Output, OutputSoftmax)):
             eps_in = last.backward(eps)
             eps_in, epss = self.backward_from_prefix(eps_in, collect=True)
         else:
@@ -649,9 +682,11 @@ class Net:
         return score
 
     def backward_from_prefix(self, eps, collect=False):
-        """Backprop through all layers except the final loss-bearing one."""
+        """Backprop through all layers except the final loss-bearing one; stops at the frozen feature extractor."""
         epss = []
         for l in reversed(self.layers[:-1]):
+            if getattr(l, "frozen", False):
+                break
             eps = l.backward(eps)
             epss.append(eps)
         return (eps, epss[::-1]) if collect else eps
@@ -661,7 +696,7 @@ class Net:
         """g/=mb -> clip -> updater -> +l2*W -> theta -= g.  """
         t = self.iteration + 1
         for li, l in enumerate(self.layers):
-            if not l.has_params:
+            if not l.has_params or getattr(l, "frozen", False):     # FrozenLayer: no gradient, no update, no l2 decay
                 continue
             u = l.updater or UpdaterCfg("sgd", 0.0)
             for pname, shape, _ in l.param_specs():
@@ -844,6 +879,22 @@ def reference_gan(gen_lr=0.004, z=2, dtype=np.float64, seed=666, quirks=DEFAULT_
     d = reference_discriminator(0.0, dtype, seed, "gan_dis", quirks).layers
     # gen output is [N,1,28,28]; dis's ff2cnn reshape is a no-op on it
     return Net(g + d, seed=seed, dtype=dtype, grad_clip=1.0, quirks=quirks), len(g)
+
+
+def reference_computer_vision(dis: Net, lr=0.002, n_classes=10, seed=666, quirks=DEFAULT_QUIRKS) -> Net:
+    """J:337-364: TransferLearning.GraphBuilder(dis).setFeatureExtractor("dis_dense_layer_6").removeVertexKeepConnections(output)
+    .addLayer("dis_batch", BatchNormalization(1024)).addLayer("dis_output_layer_7", OutputLayer(MCXENT, softmax, 10)).
+    The trunk layers are shared objects' copies marked frozen (FrozenLayer); fine-tune config: l2 1e-4, clip 1.0, RmsProp(lr,1e-8,1e-8)."""
+    import copy
+    trunk = [copy.deepcopy(l) for l in dis.layers[:-1]]
+    for l in trunk:
+        l.frozen = True
+    u = lambda: RmsProp(lr, 1e-8, 1e-8)
+    head = [BatchNorm(1024, updater=u(), name="dis_batch"), OutputSoftmax(1024, n_classes, updater=u(), l2=1e-4, name="dis_output_layer_7")]
+    net = Net(head, seed=seed, dtype=dis.dtype, grad_clip=1.0, quirks=quirks)     # initialises only the new layers
+    net.layers = trunk + head
+    net.state = {(li + len(trunk), p): v for (li, p), v in net.state.items()}
+    return net
 
 
 def dcgan_generator(size=64, z=100, nf=64, nc=3, lr=2e-4, beta1=0.5, dtype=np.float64, seed=666, quirks=DEFAULT_QUIRKS) -> Net:

@@ -518,3 +518,47 @@ def test_boundary_error_codes(b200):
         x = np.random.default_rng(bs).uniform(-1, 1, (bs, 3, 16, 16))
         assert rel_err(net.output(x), onet.output(x).reshape(bs, -1)) < TOL
     net.close()
+
+
+def test_fp32_transfer_learning_head_matches_oracle(b200):
+    """SURVEY 8f #3 (J:337-364, 512-545): frozen D trunk + BatchNormalization(1024) + OutputLayer(MCXENT, softmax, 10)."""
+    b, ctx = b200
+    from gan_deeplearning4j_b200 import models as m
+    n = 8
+    odis = oracle_from_specs(m.reference_discriminator(), (1, 28, 28), 1.0, seed=1, flat_input=False)
+    rng = np.random.default_rng(3); randomize(odis, rng)
+    ocv = o.reference_computer_vision(odis)
+    specs = m.reference_computer_vision()
+    bcv = b.Net(ctx, specs, (1, 28, 28), max_batch=n, precision=b.FP32, grad_clip=1.0)
+    assert bcv.num_params() == ocv.num_params()
+    # the driver copies the trunk by name (J:516-542); the new layers get the oracle's init
+    for s in specs:
+        l = ocv.layer(s["name"]) if s["type"] in ("batchnorm", "conv2d", "dense", "output") else None
+        if l is not None:
+            for p, shape, order in l.param_specs():
+                bcv.set_param(s["name"], p, l.params[p].ravel(order=order.upper()))
+    np.testing.assert_allclose(bcv.params(), ocv.params_flat(), rtol=1e-6)
+    x = np.round(rng.uniform(0, 1, (n, 784)), 2); y = np.eye(10)[rng.integers(0, 10, n)]
+    xo = x.reshape(n, 1, 28, 28)
+    assert rel_err(bcv.output(x), ocv.output(xo)) < TOL                       # softmax probabilities, test-mode trunk
+    s_o = ocv.compute_gradient_and_score(xo, y); s_b = bcv.compute_gradient_and_score(x, y)
+    assert abs(s_b - s_o) < TOL * abs(s_o)
+    g_b, g_o = bcv.gradients(), ocv.grads_flat(); off = 0
+    for li, name, p, shape, _ in ocv.param_table():
+        k = int(np.prod(shape))
+        if name in ("dis_batch", "dis_output_layer_7"):
+            assert rel_err(g_b[off:off + k], g_o[off:off + k]) < TOL, (name, p)
+        else:
+            assert not np.any(g_b[off:off + k]), (name, p)                     # FrozenLayer: no gradient at all
+        off += k
+    p0 = bcv.params()
+    ocv.fit(xo, y); bcv.fit(x, y)
+    p1 = bcv.params(); off = 0
+    for li, name, p, shape, _ in ocv.param_table():
+        k = int(np.prod(shape))
+        if name in ("dis_batch", "dis_output_layer_7"):
+            _assert_close_up_to_sign_flips(p1[off:off + k], ocv.params_flat()[off:off + k], lr=0.002)
+        else:
+            assert np.array_equal(p1[off:off + k], p0[off:off + k]), (name, p)  # not even l2-decayed
+        off += k
+    bcv.close()

@@ -361,3 +361,41 @@ def test_parameter_averaging_equals_gradient_averaging_for_sgd():
         single.compute_gradient_and_score(x, y); g.append({(li, p): l.grads[p].copy() for li, l in enumerate(single.layers) for p in l.grads})
     single.apply_update(12, grads={k: g[0][k] + g[1][k] for k in g[0]})
     np.testing.assert_allclose(master.params_flat(), single.params_flat(), rtol=1e-12, atol=1e-14)
+
+
+def test_transfer_learning_head_frozen_trunk_and_softmax_mcxent():
+    """J:337-364 / J:512-545: frozen discriminator trunk (test-mode BN, no gradient, no update, no l2) + BN(1024) + softmax-10 MCXENT head."""
+    dis = o.reference_discriminator()
+    cv = o.reference_computer_vision(dis)
+    assert cv.num_params() == 1388293 - 1025 + 4 * 1024 + 1024 * 10 + 10
+    rng = np.random.default_rng(0)
+    x = np.round(rng.uniform(0, 1, (6, 784)), 2); y = np.eye(10)[rng.integers(0, 10, 6)]
+    # softmax + MCXENT gradient is p - y; cross-check with torch
+    head = cv.layers[-1]
+    z = rng.standard_normal((6, 10)); zt = torch.tensor(z, requires_grad=True)
+    F.cross_entropy(zt, torch.tensor(y), reduction="sum").backward()
+    s, g = o.mcxent_softmax_score_and_grad(z, y)
+    np.testing.assert_allclose(g, zt.grad.numpy(), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(s, float(F.cross_entropy(torch.tensor(z), torch.tensor(y), reduction="sum")), rtol=1e-10)
+    # finite differences on the trainable head only
+    table = cv.param_table(); p0 = cv.params_flat().copy()
+    cv.compute_gradient_and_score(x, y); g = cv.grads_flat() / 6
+    off = 0; idx = []
+    for li, name, p, shape, _ in table:
+        k = int(np.prod(shape))
+        if name in ("dis_batch", "dis_output_layer_7") and p not in ("mean", "var"):
+            idx += list(range(off, off + min(k, 12)))
+        off += k
+    for i in idx:
+        pp = p0.copy(); pp[i] += 1e-6; cv.set_params_flat(pp); sp = cv.compute_gradient_and_score(x, y)
+        pm = p0.copy(); pm[i] -= 1e-6; cv.set_params_flat(pm); sm = cv.compute_gradient_and_score(x, y)
+        num = (sp - sm) / 2e-6; l2 = 1e-4 * p0[i] if table and i >= len(p0) - 10250 and i < len(p0) - 10 else 0.0
+        ana = g[i] + l2
+        assert abs(num - ana) < 1e-8 or abs(num - ana) / (abs(num) + abs(ana)) < 1e-3, (i, num, ana)
+    cv.set_params_flat(p0)
+    # fit: only the new layers move; the trunk is bit-for-bit unchanged (not even l2-decayed, unlike an lr-0 layer)
+    cv.fit(x, y); p1 = cv.params_flat()
+    names = [(n, p) for li, n, p, sh, _ in table for _ in range(int(np.prod(sh)))]
+    changed = {names[i][0] for i in np.flatnonzero(p0 != p1)}
+    assert changed == {"dis_batch", "dis_output_layer_7"}
+    assert np.allclose(cv.output(x).sum(1), 1.0)
