@@ -562,3 +562,21 @@ def test_fp32_transfer_learning_head_matches_oracle(b200):
             assert np.array_equal(p1[off:off + k], p0[off:off + k]), (name, p)  # not even l2-decayed
         off += k
     bcv.close()
+
+
+def test_reference_program_replay_end_to_end(b200, tmp_path):
+    """examples/gan_computer_vision.py = the Java main replayed: CSV in, two iterations, sample + prediction CSVs and parameter dumps out."""
+    import subprocess, sys, os
+    from gan_deeplearning4j_b200 import data
+    rng = np.random.default_rng(0)
+    data.write_csv(str(tmp_path / "train.csv"), rng.uniform(0, 1, (48, 784)), rng.integers(0, 10, 48))
+    data.write_csv(str(tmp_path / "test.csv"), rng.uniform(0, 1, (30, 784)), rng.integers(0, 10, 30))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "examples", "gan_computer_vision.py"), "--train-csv", str(tmp_path / "train.csv"),
+                        "--test-csv", str(tmp_path / "test.csv"), "--out", str(tmp_path / "out"), "--iterations", "2", "--batch", "16"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "Completed Batch 2!" in r.stdout
+    out = np.loadtxt(tmp_path / "out" / "mnist_out_2.csv", delimiter=","); pred = np.loadtxt(tmp_path / "out" / "mnist_test_predictions_2.csv", delimiter=",")
+    assert out.shape == (100, 784) and np.all((out >= 0) & (out <= 1))            # sigmoid images of the 10x10 latent grid
+    assert pred.shape == (30, 10) and np.allclose(pred.sum(1), 1, atol=1e-4)
+    assert os.path.getsize(tmp_path / "out" / "dis_coefficients_2.bin") == 4 * 1388293
