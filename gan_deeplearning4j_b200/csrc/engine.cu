@@ -82,7 +82,7 @@ struct LayerRT {
   void* out = nullptr; bool out_alias = false;
   void* probs = nullptr;                                       // OUTPUT / LOSS: sigmoid(logits)
   uint8_t* argmax = nullptr;
-  float* bn_mean = nullptr; float* bn_invstd = nullptr;
+  float* bn_mean = nullptr; float* bn_invstd = nullptr; float* bn_fold = nullptr;   // bn_fold: [scale | shift] for the inference-mode epilogue fold
   int fused_act = ACT_IDENTITY; float fused_alpha = 0.f;       // BN followed by an ActivationLayer
   bool act_fused_into_prev = false;
   bool needs_wt = false;                                       // a tcgen05 dgrad kernel reads the transposed bf16 copy
@@ -244,7 +244,7 @@ static int32_t net_alloc(b2g_net* n) {
     if (!alias) B2(dalloc(n, (char**)&l.out, ts * R * l.out_elems));
     if (l.d.type == B2G_LAYER_OUTPUT || l.d.type == B2G_LAYER_LOSS) B2(dalloc(n, (char**)&l.probs, ts * R * l.out_elems));
     if (l.d.type == B2G_LAYER_MAXPOOL) B2(dalloc(n, &l.argmax, (size_t)R * l.out_elems));
-    if (l.d.type == B2G_LAYER_BATCHNORM) { B2(dalloc(n, &l.bn_mean, sizeof(float) * G * l.oc)); B2(dalloc(n, &l.bn_invstd, sizeof(float) * G * l.oc)); scratch = std::max(scratch, k_bn_scratch_floats(l.oc, G)); }
+    if (l.d.type == B2G_LAYER_BATCHNORM) { B2(dalloc(n, &l.bn_fold, sizeof(float) * 2 * l.oc)); B2(dalloc(n, &l.bn_mean, sizeof(float) * G * l.oc)); B2(dalloc(n, &l.bn_invstd, sizeof(float) * G * l.oc)); scratch = std::max(scratch, k_bn_scratch_floats(l.oc, G)); }
     if (l.has_gemm()) {
       ConvGeom g = l.geom; g.N = R;
       scratch = std::max(scratch, std::max(k_simt_wgrad_scratch_floats(g), k_tc_wgrad_scratch_floats(g)));
@@ -341,8 +341,12 @@ static const void* w_ptr(const b2g_net* n, const LayerRT& l, int* wprec) {
 }
 
 static inline cudaStream_t fstream(const b2g_net* n) { return n->fwd_stream ? n->fwd_stream : n->ctx->stream; }
-static int32_t gemm_fprop(b2g_net* n, const LayerRT& l, const ConvGeom& g, const void* x, const float* bias, void* out, int act, float alpha) {
+static int32_t gemm_fprop(b2g_net* n, const LayerRT& l, const ConvGeom& g, const void* x, const float* bias, void* out, int act, float alpha, const float* scale = nullptr) {
   cudaStream_t s = fstream(n); int wp; const void* w = w_ptr(n, l, &wp);
+  if (scale) {       // folded epilogue: tensor-core or SIMT GEMM kernels only
+    if (n->prec == PREC_BF16 && n->ctx->tc_ok && tc_fprop_supported(g)) return k_tc_fprop(g, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)out, act, alpha, s, scale) == 0 ? 0 : fail(B2G_ERR_CUDA, "tcgen05 fprop launch failed");
+    k_simt_fprop(n->prec, wp, g, x, w, bias, out, act, alpha, s, scale); return 0;
+  }
   if (edge_conv_small_cin_supported(g)) { k_edge_conv_small_cin(n->prec, wp, g, x, w, bias, out, act, alpha, s); return 0; }
   if (dense_small_o_supported(g)) { k_dense_small_o_fwd(n->prec, wp, g, x, w, bias, out, act, alpha, s); return 0; }
   if (n->prec == PREC_BF16 && n->ctx->tc_ok && tc_fprop_supported(g)) {
@@ -351,8 +355,12 @@ static int32_t gemm_fprop(b2g_net* n, const LayerRT& l, const ConvGeom& g, const
   }
   k_simt_fprop(n->prec, wp, g, x, w, bias, out, act, alpha, s); return 0;
 }
-static int32_t gemm_dgrad(b2g_net* n, const LayerRT& l, const ConvGeom& g, const void* dy, const float* bias, void* dx, int act, float alpha) {
+static int32_t gemm_dgrad(b2g_net* n, const LayerRT& l, const ConvGeom& g, const void* dy, const float* bias, void* dx, int act, float alpha, const float* scale = nullptr) {
   cudaStream_t s = fstream(n); int wp; const void* w = w_ptr(n, l, &wp);
+  if (scale) {
+    if (n->prec == PREC_BF16 && n->ctx->tc_ok && l.needs_wt && tc_dgrad_supported(g)) return k_tc_dgrad(g, (const __nv_bfloat16*)dy, n->shadow + l.off_Wt_bf, bias, (__nv_bfloat16*)dx, act, alpha, s, scale) == 0 ? 0 : fail(B2G_ERR_CUDA, "tcgen05 dgrad launch failed");
+    k_simt_dgrad(n->prec, wp, g, dy, w, bias, dx, act, alpha, s, scale); return 0;
+  }
   if (edge_deconv_small_c_supported(g)) { k_edge_deconv_small_c(n->prec, wp, g, dy, w, bias, dx, act, alpha, s); return 0; }
   if (dense_small_o_supported(g) && !bias && act == ACT_IDENTITY) { k_dense_small_o_dgrad(n->prec, wp, g, dy, w, dx, s); return 0; }
   if (n->prec == PREC_BF16 && n->ctx->tc_ok && l.needs_wt && g.KH == 1 && g.KW == 1 && g.H == 1 && g.W == 1) {
@@ -390,6 +398,20 @@ static int32_t net_forward(b2g_net* n, const void* in, const FwdOpts& o, const v
     void* out = l.out;
     if (i + 1 == n->L.size() && o.out_override && !l.out_alias) out = o.out_override;
     const float* bias = l.off_b >= 0 ? n->params + l.off_b : nullptr;
+    // inference-mode (or frozen) BatchNorm right after a linear conv / deconv / dense: fold it, and its activation, into that GEMM's epilogue
+    static int fold_bn = -1; if (fold_bn < 0) { const char* e = getenv("B2G_FOLD_BN"); fold_bn = (e && e[0] == '0') ? 0 : 1; }
+    if (fold_bn && (d.type == B2G_LAYER_CONV2D || d.type == B2G_LAYER_DECONV2D || d.type == B2G_LAYER_DENSE) && d.act == B2G_ACT_IDENTITY && i + 1 < n->L.size() &&
+        n->L[i + 1].d.type == B2G_LAYER_BATCHNORM && (!o.train || n->L[i + 1].d.frozen) && !(i + 2 == n->L.size() && o.out_override)) {
+      LayerRT& bn = n->L[i + 1];
+      ConvGeom g = l.geom; g.N = R;
+      const bool remapped = d.type == B2G_LAYER_DECONV2D && g.KH == 1 && g.C != l.oc;     // 1x1-input deconv viewed as taps*C channels: no fold
+      if (!remapped) {
+        k_bn_fold(n->params + bn.off_mean, n->params + bn.off_var, n->params + bn.off_gamma, n->params + bn.off_beta, bias, bn.oc, bn.d.bn_eps, bn.bn_fold, bn.bn_fold + bn.oc, s);
+        if (d.type == B2G_LAYER_DECONV2D) B2(gemm_dgrad(n, l, g, cur, bn.bn_fold + bn.oc, bn.out, bn.fused_act, bn.fused_alpha, bn.bn_fold));
+        else B2(gemm_fprop(n, l, g, cur, bn.bn_fold + bn.oc, bn.out, bn.fused_act, bn.fused_alpha, bn.bn_fold));
+        cur = bn.out; ++i; continue;
+      }
+    }
     switch (d.type) {
       case B2G_LAYER_CONV2D: case B2G_LAYER_DENSE: case B2G_LAYER_OUTPUT: { ConvGeom g = l.geom; g.N = R; B2(gemm_fprop(n, l, g, cur, bias, out, d.act, d.act_alpha)); } break;
       case B2G_LAYER_DECONV2D: { ConvGeom g = l.geom; g.N = R; B2(gemm_dgrad(n, l, g, cur, bias, out, d.act, d.act_alpha)); } break;

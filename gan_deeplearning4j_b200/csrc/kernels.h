@@ -40,6 +40,8 @@ void k_bn_stats(int prec, const void* x, int rows_per_group, int C, int groups, 
                 const float* run_mean, const float* run_var, float* g_mean, float* g_var, float decay, cudaStream_t s);
 size_t k_bn_scratch_floats(int C, int groups);
 // inference mode: mean <- run_mean, invstd <- rsqrt(run_var+eps) for every group
+// scale[c] = gamma*rsqrt(var+eps), shift[c] = beta - mean*scale (+ conv_bias*scale): inference-mode BN as a GEMM epilogue
+void k_bn_fold(const float* run_mean, const float* run_var, const float* gamma, const float* beta, const float* conv_bias, int C, float eps, float* scale, float* shift, cudaStream_t s);
 void k_bn_prep_infer(const float* run_mean, const float* run_var, int C, int groups, float eps, float* mean, float* invstd, cudaStream_t s);
 // y = act(gamma*(x-mean)*invstd+beta)
 void k_bn_apply(int prec, const void* x, void* y, int rows_per_group, int C, int groups, const float* mean, const float* invstd,
@@ -103,9 +105,10 @@ void k_scale_f32(float* p, float v, size_t n, cudaStream_t s);
 
 // ---- GEMM-shaped kernels, SIMT (fp32 FMA) -----------------------------------------------------------------
 // fprop:  out[m][o] = act(sum_k A[m][k] w[o][k] + bias[o]),  m=(n,oy,ox), k=(r,s,c);  w layout [O][KH][KW][C]
-void k_simt_fprop(int prec, int wprec, const ConvGeom& g, const void* x, const void* w, const float* bias, void* out, int act, float alpha, cudaStream_t s);
+// optional per-output-channel `scale`: out = act(acc * scale[c] + bias[c])  (inference-mode BatchNorm folded into the epilogue)
+void k_simt_fprop(int prec, int wprec, const ConvGeom& g, const void* x, const void* w, const float* bias, void* out, int act, float alpha, cudaStream_t s, const float* scale = nullptr);
 // dgrad:  dx[m][c] = act(sum_k dy[..][o] w[o][r][s][c] + bias[c]),  m=(n,iy,ix)   (also the deconvolution forward)
-void k_simt_dgrad(int prec, int wprec, const ConvGeom& g, const void* dy, const void* w, const float* bias, void* dx, int act, float alpha, cudaStream_t s);
+void k_simt_dgrad(int prec, int wprec, const ConvGeom& g, const void* dy, const void* w, const float* bias, void* dx, int act, float alpha, cudaStream_t s, const float* scale = nullptr);
 // wgrad:  dw[o][r][s][c] = sum_pixels dy[pix][o] x[pix(r,s)][c]   (fp32 out, split-K scratch of k_simt_wgrad_scratch floats)
 void k_simt_wgrad(int prec, const ConvGeom& g, const void* x, const void* dy, float* dw, float* scratch, size_t scratch_floats, int accumulate, cudaStream_t s);
 size_t k_simt_wgrad_scratch_floats(const ConvGeom& g);
@@ -130,8 +133,8 @@ bool tc_dgrad_supported(const ConvGeom& g);
 bool tc_wgrad_supported(const ConvGeom& g);
 int  tc_init();   // resolves cuTensorMapEncodeTiled; 0 on success
 // stats: optional per-(group,channel) sum / sum-of-squares of the fp32 accumulators, fused in the epilogue
-int k_tc_fprop(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out, int act, float alpha, cudaStream_t s);
-int k_tc_dgrad(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat16* wt, const float* bias, __nv_bfloat16* dx, int act, float alpha, cudaStream_t s);
+int k_tc_fprop(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out, int act, float alpha, cudaStream_t s, const float* scale = nullptr);
+int k_tc_dgrad(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat16* wt, const float* bias, __nv_bfloat16* dx, int act, float alpha, cudaStream_t s, const float* scale = nullptr);
 int k_tc_wgrad(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* scratch, size_t scratch_floats, int accumulate, cudaStream_t s);
 size_t k_tc_wgrad_scratch_floats(const ConvGeom& g);
 

@@ -197,6 +197,13 @@ __global__ void bn_prep_infer_kernel(const float* __restrict__ rm, const float* 
   int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= C * groups) return;
   int c = i % C; mean[i] = rm[c]; invstd[i] = 1.0f / sqrtf(rv[c] + eps);
 }
+__global__ void bn_fold_kernel(const float* __restrict__ rm, const float* __restrict__ rv, const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ cb, int C, float eps, float* scale, float* shift) { pdl_prologue();
+  int c = blockIdx.x * blockDim.x + threadIdx.x; if (c >= C) return;
+  const float sc = gamma[c] / sqrtf(rv[c] + eps); scale[c] = sc; shift[c] = beta[c] - rm[c] * sc + (cb ? cb[c] * sc : 0.f);
+}
+void k_bn_fold(const float* rm, const float* rv, const float* gamma, const float* beta, const float* cb, int C, float eps, float* scale, float* shift, cudaStream_t s) {
+  launch_pdl(bn_fold_kernel, dim3((C + 255) / 256), dim3(256), (size_t)0, s, rm, rv, gamma, beta, cb, C, eps, scale, shift); LAUNCHED();
+}
 void k_bn_prep_infer(const float* run_mean, const float* run_var, int C, int groups, float eps, float* mean, float* invstd, cudaStream_t s) {
   launch_pdl(bn_prep_infer_kernel, dim3((C * groups + 255) / 256), dim3(256), (size_t)(0), s, run_mean, run_var, C, groups, eps, mean, invstd); LAUNCHED();
 }

@@ -19,7 +19,7 @@ static const int TM = 64, TN = 64, TK = 16;
 
 template <typename T, typename TW>
 struct FpropProb {
-  ConvGeom g; const T* x; const TW* w; const float* bias; T* out; int act; float alpha;
+  ConvGeom g; const T* x; const TW* w; const float* bias; const float* scale; T* out; int act; float alpha;
   int M, Ncols, K;
   __device__ __forceinline__ void load(float (*As)[TM + 4], float (*Bs)[TN + 4], int m0, int n0, int k0, int kend) const {
     int t = threadIdx.x;
@@ -45,13 +45,13 @@ struct FpropProb {
     for (int i = 0; i < 4; ++i) { int m = m0 + ty * 4 + i; if (m >= M) continue;
 #pragma unroll
       for (int j = 0; j < 4; ++j) { int o = n0 + tx * 4 + j; if (o >= Ncols) continue;
-        stf(out, (size_t)m * Ncols + o, act_fwd(act, acc[i][j] + (bias ? bias[o] : 0.f), alpha)); } }
+        stf(out, (size_t)m * Ncols + o, act_fwd(act, acc[i][j] * (scale ? scale[o] : 1.f) + (bias ? bias[o] : 0.f), alpha)); } }
   }
 };
 
 template <typename T, typename TW>
 struct DgradProb {
-  ConvGeom g; const T* dy; const TW* w; const float* bias; T* dx; int act; float alpha;
+  ConvGeom g; const T* dy; const TW* w; const float* bias; const float* scale; T* dx; int act; float alpha;
   int M, Ncols, K;   // M = N*H*W, Ncols = C, K = KH*KW*O
   __device__ __forceinline__ void load(float (*As)[TM + 4], float (*Bs)[TN + 4], int m0, int n0, int k0, int kend) const {
     int t = threadIdx.x;
@@ -89,7 +89,7 @@ struct DgradProb {
     for (int i = 0; i < 4; ++i) { int m = m0 + ty * 4 + i; if (m >= M) continue;
 #pragma unroll
       for (int j = 0; j < 4; ++j) { int c = n0 + tx * 4 + j; if (c >= Ncols) continue;
-        stf(dx, (size_t)m * Ncols + c, act_fwd(act, acc[i][j] + (bias ? bias[c] : 0.f), alpha)); } }
+        stf(dx, (size_t)m * Ncols + c, act_fwd(act, acc[i][j] * (scale ? scale[c] : 1.f) + (bias ? bias[c] : 0.f), alpha)); } }
   }
 };
 
@@ -156,27 +156,27 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(Prob p, int k_per_split)
 }
 
 template <typename T, typename TW>
-static void launch_fprop(const ConvGeom& g, const void* x, const void* w, const float* bias, void* out, int act, float alpha, cudaStream_t s) {
-  FpropProb<T, TW> p{g, (const T*)x, (const TW*)w, bias, (T*)out, act, alpha, g.N * g.OH * g.OW, g.O, g.KH * g.KW * g.C};
+static void launch_fprop(const ConvGeom& g, const void* x, const void* w, const float* bias, const float* scale, void* out, int act, float alpha, cudaStream_t s) {
+  FpropProb<T, TW> p{g, (const T*)x, (const TW*)w, bias, scale, (T*)out, act, alpha, g.N * g.OH * g.OW, g.O, g.KH * g.KW * g.C};
   dim3 grid((p.Ncols + TN - 1) / TN, (p.M + TM - 1) / TM, 1);
   launch_pdl(simt_gemm_kernel<FpropProb<T, TW>>, dim3(grid), dim3(256), (size_t)(0), s, p, p.K); LAUNCHED();
 }
 template <typename T, typename TW>
-static void launch_dgrad(const ConvGeom& g, const void* dy, const void* w, const float* bias, void* dx, int act, float alpha, cudaStream_t s) {
-  DgradProb<T, TW> p{g, (const T*)dy, (const TW*)w, bias, (T*)dx, act, alpha, g.N * g.H * g.W, g.C, g.KH * g.KW * g.O};
+static void launch_dgrad(const ConvGeom& g, const void* dy, const void* w, const float* bias, const float* scale, void* dx, int act, float alpha, cudaStream_t s) {
+  DgradProb<T, TW> p{g, (const T*)dy, (const TW*)w, bias, scale, (T*)dx, act, alpha, g.N * g.H * g.W, g.C, g.KH * g.KW * g.O};
   dim3 grid((p.Ncols + TN - 1) / TN, (p.M + TM - 1) / TM, 1);
   launch_pdl(simt_gemm_kernel<DgradProb<T, TW>>, dim3(grid), dim3(256), (size_t)(0), s, p, p.K); LAUNCHED();
 }
 
-void k_simt_fprop(int prec, int wprec, const ConvGeom& g, const void* x, const void* w, const float* bias, void* out, int act, float alpha, cudaStream_t s) {
-  if (prec == PREC_F32) launch_fprop<float, float>(g, x, w, bias, out, act, alpha, s);
-  else if (wprec == PREC_F32) launch_fprop<__nv_bfloat16, float>(g, x, w, bias, out, act, alpha, s);
-  else launch_fprop<__nv_bfloat16, __nv_bfloat16>(g, x, w, bias, out, act, alpha, s);
+void k_simt_fprop(int prec, int wprec, const ConvGeom& g, const void* x, const void* w, const float* bias, void* out, int act, float alpha, cudaStream_t s, const float* scale) {
+  if (prec == PREC_F32) launch_fprop<float, float>(g, x, w, bias, scale, out, act, alpha, s);
+  else if (wprec == PREC_F32) launch_fprop<__nv_bfloat16, float>(g, x, w, bias, scale, out, act, alpha, s);
+  else launch_fprop<__nv_bfloat16, __nv_bfloat16>(g, x, w, bias, scale, out, act, alpha, s);
 }
-void k_simt_dgrad(int prec, int wprec, const ConvGeom& g, const void* dy, const void* w, const float* bias, void* dx, int act, float alpha, cudaStream_t s) {
-  if (prec == PREC_F32) launch_dgrad<float, float>(g, dy, w, bias, dx, act, alpha, s);
-  else if (wprec == PREC_F32) launch_dgrad<__nv_bfloat16, float>(g, dy, w, bias, dx, act, alpha, s);
-  else launch_dgrad<__nv_bfloat16, __nv_bfloat16>(g, dy, w, bias, dx, act, alpha, s);
+void k_simt_dgrad(int prec, int wprec, const ConvGeom& g, const void* dy, const void* w, const float* bias, void* dx, int act, float alpha, cudaStream_t s, const float* scale) {
+  if (prec == PREC_F32) launch_dgrad<float, float>(g, dy, w, bias, scale, dx, act, alpha, s);
+  else if (wprec == PREC_F32) launch_dgrad<__nv_bfloat16, float>(g, dy, w, bias, scale, dx, act, alpha, s);
+  else launch_dgrad<__nv_bfloat16, __nv_bfloat16>(g, dy, w, bias, scale, dx, act, alpha, s);
 }
 
 static int wgrad_splits(const ConvGeom& g) {

@@ -131,7 +131,7 @@ struct TcConvParams {
   int KW, SH, SW, PH, PW;
   int OC;                   // output channels = row length of `out`
   int outH, outW;           // spatial dims of `out`
-  const float* bias; int act; float alpha;
+  const float* bias; const float* scale; int act; float alpha;     // out = act(acc * scale[c] + bias[c]); scale may be null
   __nv_bfloat16* out;
 };
 
@@ -147,7 +147,9 @@ struct TcSmem {
 // CL > 1: a thread-block cluster of CL CTAs that are adjacent along M (same weight tile): each CTA fetches only BN/CL rows of the
 // weight tile and TMA-multicasts them into every CTA of the cluster, so the weight traffic out of L2 drops by CL; a stage is
 // refilled only after all CL MMA issuers have committed it (tcgen05.commit multicast onto every CTA's "empty" barrier).
-template <int BN, int STAGES, int CL>
+// AFFINE: the epilogue is act(acc * scale[c] + bias[c]) with both arrays present (inference-mode BatchNorm folded in); otherwise
+// act(acc + bias[c]) with an optional bias.  Two instantiations keep the common path free of the extra loads.
+template <int BN, int STAGES, int CL, bool AFFINE>
 __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcConvParams p) { pdl_prologue();
   using S = TcSmem<BN, STAGES>;
   const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
@@ -240,7 +242,8 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ CU
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
-        if (p.bias) { a += p.bias[nb0 + c0 + 2 * j]; b += p.bias[nb0 + c0 + 2 * j + 1]; }
+        if (AFFINE) { a = fmaf(a, p.scale[nb0 + c0 + 2 * j], p.bias[nb0 + c0 + 2 * j]); b = fmaf(b, p.scale[nb0 + c0 + 2 * j + 1], p.bias[nb0 + c0 + 2 * j + 1]); }
+        else if (p.bias) { a += p.bias[nb0 + c0 + 2 * j]; b += p.bias[nb0 + c0 + 2 * j + 1]; }
         a = act_fwd(p.act, a, p.alpha); b = act_fwd(p.act, b, p.alpha);
         __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
         packed[j] = *reinterpret_cast<uint32_t*>(&h);
@@ -277,21 +280,25 @@ bool tc_dgrad_supported(const ConvGeom& g) {
          pick_row_tile(g.N, g.OH, g.OW, 128, &a, &b, &c);
 }
 
-template <int BN, int STAGES, int CL>
-static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvParams& p, dim3 grid, cudaStream_t s) {
+template <int BN, int STAGES, int CL, bool AFFINE>
+static int launch_conv_a(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvParams& p, dim3 grid, cudaStream_t s) {
   using S = TcSmem<BN, STAGES>;
   static bool attr_set = false;
-  if (!attr_set) { if (cudaFuncSetAttribute(tc_conv_kernel<BN, STAGES, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) return -2; attr_set = true; }
+  if (!attr_set) { if (cudaFuncSetAttribute(tc_conv_kernel<BN, STAGES, CL, AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) return -2; attr_set = true; }
   if (CL == 1) {
-    launch_pdl(tc_conv_kernel<BN, STAGES, CL>, dim3(grid), dim3(192), (size_t)(S::TOTAL), s, tmA, tmB, p);
+    launch_pdl(tc_conv_kernel<BN, STAGES, CL, AFFINE>, dim3(grid), dim3(192), (size_t)(S::TOTAL), s, tmA, tmB, p);
   } else {
     cudaLaunchConfig_t cfg{}; cfg.gridDim = grid; cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = S::TOTAL; cfg.stream = s;
     cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    if (cudaLaunchKernelEx(&cfg, tc_conv_kernel<BN, STAGES, CL>, tmA, tmB, p) != cudaSuccess) return -3;
+    if (cudaLaunchKernelEx(&cfg, tc_conv_kernel<BN, STAGES, CL, AFFINE>, tmA, tmB, p) != cudaSuccess) return -3;
   }
   LAUNCHED();
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
+}
+template <int BN, int STAGES, int CL>
+static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvParams& p, dim3 grid, cudaStream_t s) {
+  return (p.scale && p.bias) ? launch_conv_a<BN, STAGES, CL, true>(tmA, tmB, p, grid, s) : launch_conv_a<BN, STAGES, CL, false>(tmA, tmB, p, grid, s);
 }
 static int g_tc_cluster = -1;     // B2G_TC_CLUSTER=1|2|4 caps the cluster size. Default 1: measured on B200 the 2- and 4-CTA multicast variants are 5-20 % SLOWER (profiles/r01_kernel_bench_cluster.txt) -- consistent with the microarchitecture note that TMA multicast only dedups L2 reads at cluster size 8
 static int pick_cluster(unsigned grid_x) {
@@ -323,8 +330,8 @@ static int weight_map(CUtensorMap* m, const __nv_bfloat16* w, int rows, int taps
   return make_map_bf16(m, w, 3, dims, strides, box, es);
 }
 
-int k_tc_fprop(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out, int act, float alpha, cudaStream_t s) {
-  TcConvParams p{}; p.mode = 0;
+int k_tc_fprop(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out, int act, float alpha, cudaStream_t s, const float* scale) {
+  TcConvParams p{}; p.mode = 0; p.scale = scale;
   if (!pick_row_tile(g.N, g.OH, g.OW, 128, &p.Nt, &p.Ht, &p.Wt)) return -1;
   const int BN = pick_bn(g.O);
   p.GH = g.OH; p.GW = g.OW; p.tiles_y = g.OH / p.Ht; p.taps_h = g.KH; p.taps_w = g.KW; p.chunks = g.C / 64; p.KW = g.KW;
@@ -341,8 +348,8 @@ int k_tc_fprop(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* w
   return dispatch_conv(BN, CL, tmA, tmB, p, grid, s);
 }
 
-int k_tc_dgrad(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat16* wt, const float* bias, __nv_bfloat16* dx, int act, float alpha, cudaStream_t s) {
-  TcConvParams p{}; p.mode = 1;
+int k_tc_dgrad(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat16* wt, const float* bias, __nv_bfloat16* dx, int act, float alpha, cudaStream_t s, const float* scale) {
+  TcConvParams p{}; p.mode = 1; p.scale = scale;
   if (!pick_row_tile(g.N, g.OH, g.OW, 128, &p.Nt, &p.Ht, &p.Wt)) return -1;
   const int BN = pick_bn(g.C);
   p.GH = g.OH; p.GW = g.OW; p.tiles_y = g.OH / p.Ht; p.taps_h = 2; p.taps_w = 2; p.chunks = g.O / 64; p.KW = 4;
