@@ -239,15 +239,22 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ CU
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
       tmem_ld_wait();
       uint32_t packed[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
-        if (AFFINE) { a = fmaf(a, p.scale[nb0 + c0 + 2 * j], p.bias[nb0 + c0 + 2 * j]); b = fmaf(b, p.scale[nb0 + c0 + 2 * j + 1], p.bias[nb0 + c0 + 2 * j + 1]); }
-        else if (p.bias) { a += p.bias[nb0 + c0 + 2 * j]; b += p.bias[nb0 + c0 + 2 * j + 1]; }
-        a = act_fwd(p.act, a, p.alpha); b = act_fwd(p.act, b, p.alpha);
-        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-        packed[j] = *reinterpret_cast<uint32_t*>(&h);
-      }
+      // the activation switch is hoisted out of the 32-column loop: one uniform branch per chunk instead of one per element
+#define B2G_EPI_LOOP(ACTC)                                                                                                         \
+  _Pragma("unroll") for (int j = 0; j < 16; ++j) {                                                                                 \
+    float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);                                                        \
+    if (AFFINE) { a = fmaf(a, p.scale[nb0 + c0 + 2 * j], p.bias[nb0 + c0 + 2 * j]); b = fmaf(b, p.scale[nb0 + c0 + 2 * j + 1], p.bias[nb0 + c0 + 2 * j + 1]); } \
+    else if (has_bias) { a += p.bias[nb0 + c0 + 2 * j]; b += p.bias[nb0 + c0 + 2 * j + 1]; }                                      \
+    a = act_fwd(ACTC, a, p.alpha); b = act_fwd(ACTC, b, p.alpha);                                                                  \
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);                                                                                \
+    packed[j] = *reinterpret_cast<uint32_t*>(&h);                                                                                  \
+  }
+      const bool has_bias = p.bias != nullptr;
+      if (p.act == ACT_IDENTITY) { B2G_EPI_LOOP(ACT_IDENTITY) }
+      else if (p.act == ACT_LRELU) { B2G_EPI_LOOP(ACT_LRELU) }
+      else if (p.act == ACT_RELU) { B2G_EPI_LOOP(ACT_RELU) }
+      else { B2G_EPI_LOOP(p.act) }
+#undef B2G_EPI_LOOP
       uint4* dst = reinterpret_cast<uint4*>(orow + c0);
 #pragma unroll
       for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
@@ -268,6 +275,12 @@ static bool pick_row_tile(int N, int GH, int GW, int rows, int* Nt, int* Ht, int
   *Nt = rows / P; *Ht = GH; *Wt = GW; return true;
 }
 static int pick_bn(int OC) { return OC % 256 == 0 ? 256 : OC % 128 == 0 ? 128 : OC % 64 == 0 ? 64 : 0; }
+// Small layers (few M tiles) are latency-bound per CTA, not bandwidth-bound: prefer narrower N tiles until the grid covers the 148 SMs.
+static int pick_bn_fill(int OC, long m_tiles_x_phases) {
+  int bn = pick_bn(OC);
+  while (bn > 64 && m_tiles_x_phases * (OC / bn) < 148) bn /= 2;
+  return bn;
+}
 
 bool tc_fprop_supported(const ConvGeom& g) {
   int a, b, c;
@@ -333,7 +346,7 @@ static int weight_map(CUtensorMap* m, const __nv_bfloat16* w, int rows, int taps
 int k_tc_fprop(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out, int act, float alpha, cudaStream_t s, const float* scale) {
   TcConvParams p{}; p.mode = 0; p.scale = scale;
   if (!pick_row_tile(g.N, g.OH, g.OW, 128, &p.Nt, &p.Ht, &p.Wt)) return -1;
-  const int BN = pick_bn(g.O);
+  const int BN = pick_bn_fill(g.O, (long)g.N * g.OH * g.OW / 128);
   p.GH = g.OH; p.GW = g.OW; p.tiles_y = g.OH / p.Ht; p.taps_h = g.KH; p.taps_w = g.KW; p.chunks = g.C / 64; p.KW = g.KW;
   p.SH = g.SH; p.SW = g.SW; p.PH = g.PH; p.PW = g.PW; p.OC = g.O; p.outH = g.OH; p.outW = g.OW; p.bias = bias; p.act = act; p.alpha = alpha; p.out = out;
   CUtensorMap tmA, tmB;
@@ -351,7 +364,7 @@ int k_tc_fprop(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* w
 int k_tc_dgrad(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat16* wt, const float* bias, __nv_bfloat16* dx, int act, float alpha, cudaStream_t s, const float* scale) {
   TcConvParams p{}; p.mode = 1; p.scale = scale;
   if (!pick_row_tile(g.N, g.OH, g.OW, 128, &p.Nt, &p.Ht, &p.Wt)) return -1;
-  const int BN = pick_bn(g.C);
+  const int BN = pick_bn_fill(g.C, (long)g.N * g.OH * g.OW / 128 * 4);
   p.GH = g.OH; p.GW = g.OW; p.tiles_y = g.OH / p.Ht; p.taps_h = 2; p.taps_w = 2; p.chunks = g.O / 64; p.KW = 4;
   p.SH = 1; p.SW = 1; p.PH = 0; p.PW = 0; p.OC = g.C; p.outH = g.H; p.outW = g.W; p.bias = bias; p.act = act; p.alpha = alpha; p.out = dx;
   CUtensorMap tmA, tmB;
