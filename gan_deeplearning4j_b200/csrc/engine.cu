@@ -753,18 +753,27 @@ struct b2g_gan {
   float *y_d = nullptr, *y_g = nullptr;   // [2N] = y_real | y_fake ; [N]
   float* loss_dev = nullptr;              // [4]: d_real_sum, d_fake_sum, g_sum
   float* stage = nullptr; size_t stage_floats = 0;
-  cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; int graph_batch = 0; uint64_t graph_launches = 0;
+  cudaGraph_t graph = nullptr, graph1 = nullptr; cudaGraphExec_t exec = nullptr, exec1 = nullptr; int graph_batch = 0; uint64_t graph_launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr; float last_ms = 0.f; int last_batch = 1; bool nccl_warm = false;
+  cudaStream_t copy_stream = nullptr; cudaEvent_t ev_x = nullptr; bool ev1_valid = false;   // x_real's H2D runs under the generator's forward
   std::vector<void*> allocs;
 };
 
-static int32_t gan_step_body(b2g_gan* g, int N) {
-  b2g_net *G = g->G, *D = g->D; cudaStream_t s = G->ctx->stream;
+// part 1: x_fake = gen.output(z_d) -- needs nothing from the host but z_d.  part 2: everything that touches x_real.
+// They are two graphs so that the copy-stream event of x_real's H2D can be waited on between them (a captured stream may not
+// wait on work outside its capture).
+static int32_t gan_step_part1(b2g_gan* g, int N) {
+  b2g_net *G = g->G, *D = g->D;
   const size_t ts = prec_size(D->prec);
-  // 1. x_fake = gen.output(z_d)  (J:420) written straight into the second half of D's input batch
   void* fake_dst = (char*)D->input + ts * (size_t)N * D->in_elems;
   FwdOpts og{N, 1, g->cfg.fake_bn_train != 0, false, fake_dst};
-  B2(net_forward(G, g->z_d, og, nullptr));
+  return net_forward(G, g->z_d, og, nullptr);
+}
+static int32_t gan_step_part2(b2g_gan* g, int N) {
+  b2g_net *G = g->G, *D = g->D; cudaStream_t s = G->ctx->stream;
+  // 1. (part 1) x_fake = gen.output(z_d) (J:420) was written straight into the second half of D's input batch.
+  // x_real arrived on the copy stream meanwhile; only the discriminator needs it
+  k_nchw_f32_to_nhwc(D->prec, g->stage, D->input, N, D->cfg.in_c, D->cfg.in_h * D->cfg.in_w, s);
   // 3a (hoisted). The generator's train-mode forward on z_g depends only on G's parameters, which the D step does not touch:
   // run it on a second stream underneath the whole D step.
   cudaStream_t s3 = G->ctx->side2;
@@ -809,14 +818,15 @@ extern "C" int32_t b2g_gan_create(b2g_net* gen, b2g_net* dis, const b2g_gan_conf
   int32_t r = al(&g->z_d, ts * N * gen->in_elems); if (!r) r = al(&g->z_g, ts * N * gen->in_elems);
   if (!r) r = al((void**)&g->y_d, sizeof(float) * 2 * N); if (!r) r = al((void**)&g->y_g, sizeof(float) * N); if (!r) r = al((void**)&g->loss_dev, sizeof(float) * 4);
   g->stage_floats = (size_t)N * std::max(dis->in_elems, gen->in_elems); if (!r) r = al((void**)&g->stage, sizeof(float) * g->stage_floats);
-  if (!r) { if (cudaEventCreate(&g->ev0) != cudaSuccess || cudaEventCreate(&g->ev1) != cudaSuccess) r = fail(B2G_ERR_CUDA, "cudaEventCreate failed"); }
+  if (!r) { if (cudaEventCreate(&g->ev0) != cudaSuccess || cudaEventCreate(&g->ev1) != cudaSuccess || cudaEventCreateWithFlags(&g->ev_x, cudaEventDisableTiming) != cudaSuccess ||
+                cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking) != cudaSuccess) r = fail(B2G_ERR_CUDA, "cudaEventCreate failed"); }
   if (r) { for (void* p : g->allocs) cudaFree(p); delete g; return r; }
   *out = g; return 0;
 }
 extern "C" int32_t b2g_gan_destroy(b2g_gan* g) {
   if (!g) return 0; cudaSetDevice(g->G->ctx->device); cudaStreamSynchronize(g->G->ctx->stream);
-  if (g->exec) cudaGraphExecDestroy(g->exec); if (g->graph) cudaGraphDestroy(g->graph);
-  if (g->ev0) cudaEventDestroy(g->ev0); if (g->ev1) cudaEventDestroy(g->ev1);
+  if (g->exec) cudaGraphExecDestroy(g->exec); if (g->graph) cudaGraphDestroy(g->graph); if (g->exec1) cudaGraphExecDestroy(g->exec1); if (g->graph1) cudaGraphDestroy(g->graph1);
+  if (g->ev0) cudaEventDestroy(g->ev0); if (g->ev1) cudaEventDestroy(g->ev1); if (g->ev_x) cudaEventDestroy(g->ev_x); if (g->copy_stream) { cudaStreamSynchronize(g->copy_stream); cudaStreamDestroy(g->copy_stream); }
   for (void* p : g->allocs) cudaFree(p); delete g; return 0;
 }
 extern "C" int32_t b2g_gan_upload(b2g_gan* g, const float* x_real, const float* z_d, const float* z_g, const float* y_real, const float* y_fake, const float* y_gen, int32_t batch) {
@@ -824,8 +834,11 @@ extern "C" int32_t b2g_gan_upload(b2g_gan* g, const float* x_real, const float* 
   if (batch < 1 || batch > g->N) return fail(B2G_ERR_SHAPE, "batch %d outside [1,%d]", batch, g->N);
   b2g_net *G = g->G, *D = g->D; cudaStream_t s = G->ctx->stream; CU(cudaSetDevice(G->ctx->device));
   size_t nx = (size_t)batch * D->in_elems, nz = (size_t)batch * G->in_elems;
-  CU(cudaMemcpyAsync(g->stage, x_real, sizeof(float) * nx, cudaMemcpyHostToDevice, s));
-  k_nchw_f32_to_nhwc(D->prec, g->stage, D->input, batch, D->cfg.in_c, D->cfg.in_h * D->cfg.in_w, s);
+  // x_real (the only large input) goes over a separate copy stream and is converted inside the step, after the generator's forward;
+  // the staging buffer is free once the previous step's conversion has run (ev1 marks the end of that step)
+  if (g->ev1_valid) CU(cudaStreamWaitEvent(g->copy_stream, g->ev1, 0));
+  CU(cudaMemcpyAsync(g->stage, x_real, sizeof(float) * nx, cudaMemcpyHostToDevice, g->copy_stream));
+  CU(cudaEventRecord(g->ev_x, g->copy_stream));
   CU(cudaMemcpyAsync(G->stage_f32, z_d, sizeof(float) * nz, cudaMemcpyHostToDevice, s));
   k_nchw_f32_to_nhwc(G->prec, G->stage_f32, g->z_d, batch, G->cfg.in_c, G->cfg.in_h * G->cfg.in_w, s);
   CU(cudaMemcpyAsync(D->stage_f32, z_g, sizeof(float) * nz, cudaMemcpyHostToDevice, s));
@@ -846,21 +859,28 @@ extern "C" int32_t b2g_gan_step_resident(b2g_gan* g, int32_t batch) {
   if (c->comm) g->nccl_warm = true;
   g->last_batch = batch;
   CU(cudaEventRecord(g->ev0, s));
-  if (!use_graph) { B2(gan_step_body(g, batch)); }
+  if (!use_graph) { B2(gan_step_part1(g, batch)); CU(cudaStreamWaitEvent(s, g->ev_x, 0)); B2(gan_step_part2(g, batch)); }
   else {
     if (!g->exec || g->graph_batch != batch) {
       if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; } if (g->graph) { cudaGraphDestroy(g->graph); g->graph = nullptr; }
+      if (g->exec1) { cudaGraphExecDestroy(g->exec1); g->exec1 = nullptr; } if (g->graph1) { cudaGraphDestroy(g->graph1); g->graph1 = nullptr; }
       uint64_t before = g_launch_count;
       CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-      int32_t r = gan_step_body(g, batch);
-      cudaError_t e = cudaStreamEndCapture(s, &g->graph);
+      int32_t r = gan_step_part1(g, batch);
+      cudaError_t e = cudaStreamEndCapture(s, &g->graph1);
+      if (r) return r; if (e != cudaSuccess) return fail(B2G_ERR_CUDA, "graph capture (generator forward): %s", cudaGetErrorString(e));
+      CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      r = gan_step_part2(g, batch);
+      e = cudaStreamEndCapture(s, &g->graph);
       g->graph_launches = g_launch_count - before; g_launch_count = before;
       if (r) return r; if (e != cudaSuccess) return fail(B2G_ERR_CUDA, "graph capture: %s", cudaGetErrorString(e));
-      CU(cudaGraphInstantiate(&g->exec, g->graph, 0)); g->graph_batch = batch;
+      CU(cudaGraphInstantiate(&g->exec1, g->graph1, 0)); CU(cudaGraphInstantiate(&g->exec, g->graph, 0)); g->graph_batch = batch;
     }
+    CU(cudaGraphLaunch(g->exec1, s));
+    CU(cudaStreamWaitEvent(s, g->ev_x, 0));
     CU(cudaGraphLaunch(g->exec, s)); g_launch_count += g->graph_launches;
   }
-  CU(cudaEventRecord(g->ev1, s));
+  CU(cudaEventRecord(g->ev1, s)); g->ev1_valid = true;
   return 0;
 }
 extern "C" int32_t b2g_gan_read_losses(b2g_gan* g, float* losses) {
