@@ -133,6 +133,7 @@ struct TcConvParams {
   int outH, outW;           // spatial dims of `out`
   const float* bias; const float* scale; int act; float alpha;     // out = act(acc * scale[c] + bias[c]); scale may be null
   __nv_bfloat16* out;
+  int dbg;                  // timing experiments only (B2G_TC_DBG): 1 = MMAs without waiting for data (no TMA), 2 = TMA without MMAs
 };
 
 template <int BN, int STAGES>
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ CU
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = 0; kb < (p.dbg == 1 ? 0 : num_kb); ++kb) {
         const int s = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
         const int ch = kb % p.chunks, tap = kb / p.chunks, ta = tap / p.taps_w, tb = tap % p.taps_w;
         int ax, ay, wtap;
@@ -210,13 +211,15 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ CU
       constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(bar_full + 8 * s, ph);
+        if (p.dbg != 1) mbar_wait(bar_full + 8 * s, ph);
         tc_fence_after();
         const uint64_t adesc = desc_kmajor_sw128(smem_base + s * S::STAGE_BYTES);
         const uint64_t bdesc = desc_kmajor_sw128(smem_base + s * S::STAGE_BYTES + S::A_BYTES);
+        if (p.dbg != 2) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)     // 4 x K=16 inside the 128-byte swizzle atom: +32 B = +2 in the (>>4) start-address field
           umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        }
         if (CL == 1) umma_commit(bar_empty + 8 * s); else umma_commit_mc(bar_empty + 8 * s, cmask);
       }
       umma_commit(bar_accum);
@@ -266,6 +269,288 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ CU
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, BN < 32 ? 32 : BN); }
 }
 
+
+// ------------------------------------------------------------------ two M tiles per CTA ---------------------
+// Same pipeline, but one CTA owns TWO adjacent 128-row tiles that share every weight tile: per K-block it stages 2 x 16 KB of
+// activations + BN x 128 B of weights and issues 2 x 4 MMAs into two TMEM accumulators (2*BN <= 512 columns).  Bytes out of L2 per MAC
+// drop by 25 % (BN = 128) to 33 % (BN = 256) -- these kernels run at the L2->SM fabric limit, not the tensor pipe's.  Used when
+// the halved grid still covers the SMs.
+template <int BN, int STAGES>
+struct TcSmem2 {
+  static constexpr int A_BYTES = 2 * 128 * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+template <int BN, int STAGES, bool AFFINE>
+__global__ void __launch_bounds__(192) tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcConvParams p) { pdl_prologue();
+  using S = TcSmem2<BN, STAGES>;
+  constexpr uint32_t TCOLS = 2 * BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_full = smem_base + S::BAR_OFF, bar_empty = bar_full + 8 * STAGES, bar_accum = bar_empty + 8 * STAGES;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + S::BAR_OFF + 8 * (2 * STAGES + 1));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nb0 = blockIdx.y * BN, phase = blockIdx.z, py = phase >> 1, px = phase & 1;
+  int n0[2], y0[2];
+#pragma unroll
+  for (int m = 0; m < 2; ++m) { const int mt = blockIdx.x * 2 + m; if (p.Nt > 1) { n0[m] = mt * p.Nt; y0[m] = 0; } else { n0[m] = mt / p.tiles_y; y0[m] = (mt % p.tiles_y) * p.Ht; } }
+  const int num_kb = p.taps_h * p.taps_w * p.chunks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_map(&tmA); prefetch_map(&tmB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_accum, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(smem_u32((const void*)tmem_slot), TCOLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
+        const int ch = kb % p.chunks, tap = kb / p.chunks, ta = tap / p.taps_w, tb = tap % p.taps_w;
+        int ax, dy_, wtap;
+        if (p.mode == 0) { dy_ = -p.PH + ta; ax = -p.PW + tb; wtap = ta * p.KW + tb; }
+        else {
+          const int r = py == 0 ? (ta == 0 ? 1 : 3) : (ta == 0 ? 0 : 2), dyr = py == 0 ? (ta == 0 ? 0 : -1) : (ta == 0 ? 1 : 0);
+          const int sx = px == 0 ? (tb == 0 ? 1 : 3) : (tb == 0 ? 0 : 2), dxc = px == 0 ? (tb == 0 ? 0 : -1) : (tb == 0 ? 1 : 0);
+          dy_ = dyr; ax = dxc; wtap = r * 4 + sx;
+        }
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        mbar_expect_tx(bar_full + 8 * s, S::STAGE_BYTES);
+        const uint32_t st = smem_base + s * S::STAGE_BYTES;
+#pragma unroll
+        for (int m = 0; m < 2; ++m) tma_load_4d(st + m * 16384, &tmA, bar_full + 8 * s, ch * 64, ax, (p.mode == 0 ? y0[m] * p.SH : y0[m]) + dy_, n0[m]);
+        tma_load_3d(st + S::A_BYTES, &tmB, bar_full + 8 * s, ch * 64, wtap, nb0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(bar_full + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t st = smem_base + s * S::STAGE_BYTES;
+        const uint64_t bdesc = desc_kmajor_sw128(st + S::A_BYTES);
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          const uint64_t adesc = desc_kmajor_sw128(st + m * 16384);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + m * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        }
+        umma_commit(bar_empty + 8 * s);
+      }
+      umma_commit(bar_accum);
+    }
+  } else {
+    const int q = warp & 3, row = q * 32 + lane;
+    const int img = row / (p.Ht * p.Wt), rem = row % (p.Ht * p.Wt), yy = rem / p.Wt, xx = rem % p.Wt;
+    mbar_wait(bar_accum, 0);
+    tc_fence_after();
+    const bool has_bias = p.bias != nullptr;
+#pragma unroll 1
+    for (int m = 0; m < 2; ++m) {
+      const int n = n0[m] + img, gy = y0[m] + yy, gx = xx;
+      size_t pix;
+      if (p.mode == 0) pix = ((size_t)n * p.outH + gy) * p.outW + gx;
+      else pix = ((size_t)n * p.outH + 2 * gy + py) * p.outW + 2 * gx + px;
+      __nv_bfloat16* orow = p.out + pix * p.OC + nb0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * BN + c0), v);
+        tmem_ld_wait();
+        uint32_t packed[16];
+#define B2G_EPI_LOOP(ACTC)                                                                                                         \
+  _Pragma("unroll") for (int j = 0; j < 16; ++j) {                                                                                 \
+    float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);                                                        \
+    if (AFFINE) { a = fmaf(a, p.scale[nb0 + c0 + 2 * j], p.bias[nb0 + c0 + 2 * j]); b = fmaf(b, p.scale[nb0 + c0 + 2 * j + 1], p.bias[nb0 + c0 + 2 * j + 1]); } \
+    else if (has_bias) { a += p.bias[nb0 + c0 + 2 * j]; b += p.bias[nb0 + c0 + 2 * j + 1]; }                                      \
+    a = act_fwd(ACTC, a, p.alpha); b = act_fwd(ACTC, b, p.alpha);                                                                  \
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);                                                                                \
+    packed[j] = *reinterpret_cast<uint32_t*>(&h);                                                                                  \
+  }
+        if (p.act == ACT_IDENTITY) { B2G_EPI_LOOP(ACT_IDENTITY) }
+        else if (p.act == ACT_LRELU) { B2G_EPI_LOOP(ACT_LRELU) }
+        else if (p.act == ACT_RELU) { B2G_EPI_LOOP(ACT_RELU) }
+        else { B2G_EPI_LOOP(p.act) }
+#undef B2G_EPI_LOOP
+        uint4* dst = reinterpret_cast<uint4*>(orow + c0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TCOLS); }
+}
+
+
+// ------------------------------------------------------------------ persistent, double-buffered TMEM -----------------
+// Measured (B2G_TC_DBG experiments, round 1): with one short-lived CTA per tile the conv kernels are bounded twice over -- the
+// MMA path alone (no loads) costs ~0.5 of peak because every 2 us of MMAs pays ~4 us of per-CTA prologue + epilogue, and the load
+// path alone runs at the L2->SM limit.  This kernel attacks both: one resident CTA per SM walks a static list of work items
+// (MT adjacent 128-row tiles x one weight tile x one phase), the smem ring keeps flowing across items, and TWO TMEM accumulator
+// stages let the 4 epilogue warps drain item i while the MMA issuer already works on item i+1.  MT = 2 shares each weight tile
+// between two M tiles (25 % fewer bytes out of L2).
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+
+template <int BN, int STAGES, int MT>
+struct TcSmemP {
+  static constexpr int A_BYTES = MT * 128 * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+
+template <int BN, int STAGES, int MT, bool AFFINE>
+__global__ void __launch_bounds__(192) tc_conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcConvParams p,
+                                                                  int m_groups, int n_tiles, int phases) { pdl_prologue();
+  using S = TcSmemP<BN, STAGES, MT>;
+  constexpr uint32_t ACC_COLS = MT * BN, TCOLS = 2 * ACC_COLS;       // two accumulator stages
+  static_assert(TCOLS <= 512, "TMEM has 512 columns");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_full = smem_base + S::BAR_OFF, bar_empty = bar_full + 8 * STAGES;
+  const uint32_t bar_tfull = bar_empty + 8 * STAGES, bar_tempty = bar_tfull + 16;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + S::BAR_OFF + 8 * (2 * STAGES + 4));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_kb = p.taps_h * p.taps_w * p.chunks;
+  const int total_items = m_groups * n_tiles * phases;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_map(&tmA); prefetch_map(&tmB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }    // 4 epilogue warps release an accumulator
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(smem_u32((const void*)tmem_slot), TCOLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // item -> (m group, n tile, phase): m fastest so that concurrently running CTAs share the weight tile in L2
+  auto decode = [&](int item, int& mg, int& nb0, int& py, int& px) { mg = item % m_groups; const int r = item / m_groups; nb0 = (r % n_tiles) * BN; const int ph = r / n_tiles; py = ph >> 1; px = ph & 1; };
+  auto tile_origin = [&](int mt, int& n0, int& y0) { if (p.Nt > 1) { n0 = mt * p.Nt; y0 = 0; } else { n0 = mt / p.tiles_y; y0 = (mt % p.tiles_y) * p.Ht; } };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t kiter = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        int mg, nb0, py, px; decode(item, mg, nb0, py, px);
+        int n0[MT], y0[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) tile_origin(mg * MT + m, n0[m], y0[m]);
+        for (int kb = 0; kb < num_kb; ++kb, ++kiter) {
+          const int s = kiter % STAGES; const uint32_t ph = (kiter / STAGES) & 1;
+          const int ch = kb % p.chunks, tap = kb / p.chunks, ta = tap / p.taps_w, tb = tap % p.taps_w;
+          int ax, dy_, wtap;
+          if (p.mode == 0) { dy_ = -p.PH + ta; ax = -p.PW + tb; wtap = ta * p.KW + tb; }
+          else {
+            const int r = py == 0 ? (ta == 0 ? 1 : 3) : (ta == 0 ? 0 : 2), dyr = py == 0 ? (ta == 0 ? 0 : -1) : (ta == 0 ? 1 : 0);
+            const int sx = px == 0 ? (tb == 0 ? 1 : 3) : (tb == 0 ? 0 : 2), dxc = px == 0 ? (tb == 0 ? 0 : -1) : (tb == 0 ? 1 : 0);
+            dy_ = dyr; ax = dxc; wtap = r * 4 + sx;
+          }
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          mbar_expect_tx(bar_full + 8 * s, S::STAGE_BYTES);
+          const uint32_t st = smem_base + s * S::STAGE_BYTES;
+#pragma unroll
+          for (int m = 0; m < MT; ++m) tma_load_4d(st + m * 16384, &tmA, bar_full + 8 * s, ch * 64, ax, (p.mode == 0 ? y0[m] * p.SH : y0[m]) + dy_, n0[m]);
+          tma_load_3d(st + S::A_BYTES, &tmB, bar_full + 8 * s, ch * 64, wtap, nb0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+      uint32_t kiter = 0, it = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+        const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+        mbar_wait(bar_tempty + 8 * acc, aph ^ 1);          // the epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + acc * ACC_COLS;
+        for (int kb = 0; kb < num_kb; ++kb, ++kiter) {
+          const int s = kiter % STAGES; const uint32_t ph = (kiter / STAGES) & 1;
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t st = smem_base + s * S::STAGE_BYTES;
+          const uint64_t bdesc = desc_kmajor_sw128(st + S::A_BYTES);
+#pragma unroll
+          for (int m = 0; m < MT; ++m) {
+            const uint64_t adesc = desc_kmajor_sw128(st + m * 16384);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(tacc + m * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(bar_empty + 8 * s);
+        }
+        umma_commit(bar_tfull + 8 * acc);
+      }
+    }
+  } else {
+    const int q = warp & 3, row = q * 32 + lane;
+    const int img = row / (p.Ht * p.Wt), rem = row % (p.Ht * p.Wt), yy = rem / p.Wt, xx = rem % p.Wt;
+    const bool has_bias = p.bias != nullptr;
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+      int mg, nb0, py, px; decode(item, mg, nb0, py, px);
+      const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+      mbar_wait(bar_tfull + 8 * acc, aph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int m = 0; m < MT; ++m) {
+        int n0, y0; tile_origin(mg * MT + m, n0, y0);
+        const int n = n0 + img, gy = y0 + yy, gx = xx;
+        size_t pix;
+        if (p.mode == 0) pix = ((size_t)n * p.outH + gy) * p.outW + gx;
+        else pix = ((size_t)n * p.outH + 2 * gy + py) * p.outW + 2 * gx + px;
+        __nv_bfloat16* orow = p.out + pix * p.OC + nb0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + m * BN + c0), v);
+          tmem_ld_wait();
+          uint32_t packed[16];
+#define B2G_EPI_LOOP(ACTC)                                                                                                         \
+  _Pragma("unroll") for (int j = 0; j < 16; ++j) {                                                                                 \
+    float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);                                                        \
+    if (AFFINE) { a = fmaf(a, p.scale[nb0 + c0 + 2 * j], p.bias[nb0 + c0 + 2 * j]); b = fmaf(b, p.scale[nb0 + c0 + 2 * j + 1], p.bias[nb0 + c0 + 2 * j + 1]); } \
+    else if (has_bias) { a += p.bias[nb0 + c0 + 2 * j]; b += p.bias[nb0 + c0 + 2 * j + 1]; }                                      \
+    a = act_fwd(ACTC, a, p.alpha); b = act_fwd(ACTC, b, p.alpha);                                                                  \
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);                                                                                \
+    packed[j] = *reinterpret_cast<uint32_t*>(&h);                                                                                  \
+  }
+          if (p.act == ACT_IDENTITY) { B2G_EPI_LOOP(ACT_IDENTITY) }
+          else if (p.act == ACT_LRELU) { B2G_EPI_LOOP(ACT_LRELU) }
+          else if (p.act == ACT_RELU) { B2G_EPI_LOOP(ACT_RELU) }
+          else { B2G_EPI_LOOP(p.act) }
+#undef B2G_EPI_LOOP
+          uint4* dst = reinterpret_cast<uint4*>(orow + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        }
+      }
+      // all of this warp's TMEM reads of the stage have completed (tcgen05.wait::ld above): hand the accumulator back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+    }
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TCOLS); }
+}
+
 // ------------------------------------------------------------------ host side ------------------------------
 static bool pick_row_tile(int N, int GH, int GW, int rows, int* Nt, int* Ht, int* Wt) {
   const int P = GH * GW;
@@ -313,6 +598,7 @@ template <int BN, int STAGES, int CL>
 static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvParams& p, dim3 grid, cudaStream_t s) {
   return (p.scale && p.bias) ? launch_conv_a<BN, STAGES, CL, true>(tmA, tmB, p, grid, s) : launch_conv_a<BN, STAGES, CL, false>(tmA, tmB, p, grid, s);
 }
+static int tc_dbg() { static int d = -1; if (d < 0) { const char* e = getenv("B2G_TC_DBG"); d = e ? atoi(e) : 0; } return d; }
 static int g_tc_cluster = -1;     // B2G_TC_CLUSTER=1|2|4 caps the cluster size. Default 1: measured on B200 the 2- and 4-CTA multicast variants are 5-20 % SLOWER (profiles/r01_kernel_bench_cluster.txt) -- consistent with the microarchitecture note that TMA multicast only dedups L2 reads at cluster size 8
 static int pick_cluster(unsigned grid_x) {
   if (g_tc_cluster < 0) { const char* e = getenv("B2G_TC_CLUSTER"); g_tc_cluster = e ? atoi(e) : 1; if (g_tc_cluster != 1 && g_tc_cluster != 2 && g_tc_cluster != 4) g_tc_cluster = 1; }
@@ -325,7 +611,68 @@ static int launch_conv_cl(int CL, const CUtensorMap& tmA, const CUtensorMap& tmB
   switch (CL) { case 4: return launch_conv<BN, STAGES, 4>(tmA, tmB, p, grid, s); case 2: return launch_conv<BN, STAGES, 2>(tmA, tmB, p, grid, s); }
   return launch_conv<BN, STAGES, 1>(tmA, tmB, p, grid, s);
 }
+template <int BN, int STAGES, bool AFFINE>
+static int launch_conv2_a(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvParams& p, dim3 grid, cudaStream_t s) {
+  using S = TcSmem2<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) { if (cudaFuncSetAttribute(tc_conv2_kernel<BN, STAGES, AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) return -2; attr_set = true; }
+  launch_pdl(tc_conv2_kernel<BN, STAGES, AFFINE>, grid, dim3(192), (size_t)S::TOTAL, s, tmA, tmB, p);
+  LAUNCHED();
+  return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
+}
+template <int BN, int STAGES>
+static int launch_conv2(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvParams& p, dim3 grid, cudaStream_t s) {
+  return (p.scale && p.bias) ? launch_conv2_a<BN, STAGES, true>(tmA, tmB, p, grid, s) : launch_conv2_a<BN, STAGES, false>(tmA, tmB, p, grid, s);
+}
+static int g_tc_mt2 = -1;        // B2G_TC_MT2=0 disables the two-tile variant
+static bool use_mt2(dim3 grid, int CL) {
+  if (g_tc_mt2 < 0) { const char* e = getenv("B2G_TC_MT2"); g_tc_mt2 = (e && e[0] == '0') ? 0 : 1; }
+  return g_tc_mt2 && CL == 1 && grid.x % 2 == 0 && (long)(grid.x / 2) * grid.y * grid.z >= 148;
+}
+template <int BN, int STAGES, int MT, bool AFFINE>
+static int launch_convp_a(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvParams& p, int m_groups, int n_tiles, int phases, cudaStream_t s) {
+  using S = TcSmemP<BN, STAGES, MT>;
+  static bool attr_set = false; static int sms = 0;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(tc_conv_persistent_kernel<BN, STAGES, MT, AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) return -2;
+    int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); attr_set = true;
+  }
+  const int items = m_groups * n_tiles * phases; const int grid = items < sms ? items : sms;
+  launch_pdl(tc_conv_persistent_kernel<BN, STAGES, MT, AFFINE>, dim3(grid), dim3(192), (size_t)S::TOTAL, s, tmA, tmB, p, m_groups, n_tiles, phases);
+  LAUNCHED();
+  return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
+}
+template <int BN, int STAGES, int MT>
+static int launch_convp(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvParams& p, int m_groups, int n_tiles, int phases, cudaStream_t s) {
+  return (p.scale && p.bias) ? launch_convp_a<BN, STAGES, MT, true>(tmA, tmB, p, m_groups, n_tiles, phases, s) : launch_convp_a<BN, STAGES, MT, false>(tmA, tmB, p, m_groups, n_tiles, phases, s);
+}
+static int g_tc_persist = -1;     // B2G_TC_PERSIST=0 falls back to one CTA per tile
+// returns 1 if the persistent kernel took the launch, 0 if not applicable, <0 on error
+static int try_persistent(int BN, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvParams& p, dim3 grid, cudaStream_t s) {
+  if (g_tc_persist < 0) { const char* e = getenv("B2G_TC_PERSIST"); g_tc_persist = (e && e[0] == '0') ? 0 : 1; }
+  if (!g_tc_persist || p.dbg) return 0;
+  const int mt2 = (grid.x % 2 == 0 && (long)(grid.x / 2) * grid.y * grid.z >= 148) ? 2 : 1;
+  // measured (profiles/r01_kernel_bench_persistent.txt): a win only where two M tiles can share the weight tile AND the halved grid still
+  // covers the SMs (D2 fprop 27.3 -> 25.1 us, D2 dgrad / G4 forward 28.8 -> 24 us); with one tile per item the lone resident CTA hides
+  // load latency worse than two co-resident short-lived CTAs do (D3 fprop 23.7 -> 36 us), so those shapes keep one CTA per tile.
+  if (mt2 != 2 && !getenv("B2G_TC_PERSIST_ALL")) return 0;
+  int rc;
+  if (BN == 256) rc = launch_convp<256, 4, 1>(tmA, tmB, p, grid.x, grid.y, grid.z, s);
+  else if (BN == 128) rc = mt2 == 2 ? launch_convp<128, 4, 2>(tmA, tmB, p, grid.x / 2, grid.y, grid.z, s) : launch_convp<128, 6, 1>(tmA, tmB, p, grid.x, grid.y, grid.z, s);
+  else if (BN == 64) rc = mt2 == 2 ? launch_convp<64, 4, 2>(tmA, tmB, p, grid.x / 2, grid.y, grid.z, s) : launch_convp<64, 8, 1>(tmA, tmB, p, grid.x, grid.y, grid.z, s);
+  else return 0;
+  return rc == 0 ? 1 : rc;
+}
 static int dispatch_conv(int BN, int CL, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvParams& p, dim3 grid, cudaStream_t s) {
+  if (CL == 1) { const int r = try_persistent(BN, tmA, tmB, p, grid, s); if (r == 1) return 0; if (r < 0) return r; }
+  if (use_mt2(grid, CL)) {
+    dim3 g2(grid.x / 2, grid.y, grid.z);
+    switch (BN) {
+      case 64: return launch_conv2<64, 4>(tmA, tmB, p, g2, s);
+      case 128: return launch_conv2<128, 4>(tmA, tmB, p, g2, s);
+      case 256: return launch_conv2<256, 3>(tmA, tmB, p, g2, s);
+    }
+  }
   switch (BN) {
     case 64: return launch_conv_cl<64, 4>(CL, tmA, tmB, p, grid, s);
     case 128: return launch_conv_cl<128, 3>(CL, tmA, tmB, p, grid, s);
@@ -344,7 +691,7 @@ static int weight_map(CUtensorMap* m, const __nv_bfloat16* w, int rows, int taps
 }
 
 int k_tc_fprop(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out, int act, float alpha, cudaStream_t s, const float* scale) {
-  TcConvParams p{}; p.mode = 0; p.scale = scale;
+  TcConvParams p{}; p.mode = 0; p.scale = scale; p.dbg = tc_dbg();
   if (!pick_row_tile(g.N, g.OH, g.OW, 128, &p.Nt, &p.Ht, &p.Wt)) return -1;
   const int BN = pick_bn_fill(g.O, (long)g.N * g.OH * g.OW / 128);
   p.GH = g.OH; p.GW = g.OW; p.tiles_y = g.OH / p.Ht; p.taps_h = g.KH; p.taps_w = g.KW; p.chunks = g.C / 64; p.KW = g.KW;
@@ -362,7 +709,7 @@ int k_tc_fprop(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* w
 }
 
 int k_tc_dgrad(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat16* wt, const float* bias, __nv_bfloat16* dx, int act, float alpha, cudaStream_t s, const float* scale) {
-  TcConvParams p{}; p.mode = 1; p.scale = scale;
+  TcConvParams p{}; p.mode = 1; p.scale = scale; p.dbg = tc_dbg();
   if (!pick_row_tile(g.N, g.OH, g.OW, 128, &p.Nt, &p.Ht, &p.Wt)) return -1;
   const int BN = pick_bn_fill(g.C, (long)g.N * g.OH * g.OW / 128 * 4);
   p.GH = g.OH; p.GW = g.OW; p.tiles_y = g.OH / p.Ht; p.taps_h = 2; p.taps_w = 2; p.chunks = g.O / 64; p.KW = 4;
