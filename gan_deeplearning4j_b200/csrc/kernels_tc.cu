@@ -839,7 +839,9 @@ static int wgrad_bnw(const ConvGeom& g) { if (g.C % 64) return 0; const long col
 static int tc_wgrad_splits(const ConvGeom& g) {
   const int bnw = wgrad_bnw(g); if (!bnw) return 1;
   long tiles = (long)(g.O / 128) * (g.KH * g.KW * g.C / bnw), kbt = (long)g.N * g.OH * g.OW / 64;
-  long sp = (296 + tiles - 1) / tiles, cap = kbt / 8; if (cap < 1) cap = 1; if (sp > cap) sp = cap; if (sp < 1) sp = 1; return (int)sp;
+  // one CTA per SM (192 KB of smem): choose the split count so that the whole grid is ONE wave (<= 148 CTAs); measured: D2 wgrad 52 -> 39 us
+  static int target = -1; if (target < 0) { const char* e = getenv("B2G_WGRAD_CTAS"); target = e ? atoi(e) : 148; }
+  long sp = target / tiles, cap = kbt / 8; if (cap < 1) cap = 1; if (sp > cap) sp = cap; if (sp < 1) sp = 1; return (int)sp;
 }
 bool tc_wgrad_supported(const ConvGeom& g) {
   int a, b, c;
