@@ -769,7 +769,20 @@ __global__ void reduce_splits_kernel(const float* __restrict__ src, float* __res
     dst[i] = a;
   }
 }
+// many splits, few outputs (the 3-channel edge weight gradients: ~300 partials of 3072 values): one warp per output element, lanes
+// stride over the splits, fixed-order shuffle tree
+__global__ void reduce_splits_wide_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n, int splits, size_t stride, int accumulate) { pdl_prologue();
+  const size_t o = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5; const int lane = threadIdx.x & 31;
+  if (o >= n) return;
+  float a = 0.f;
+  for (int k = lane; k < splits; k += 32) a += src[(size_t)k * stride + o];
+  for (int m = 16; m; m >>= 1) a += __shfl_xor_sync(0xffffffffu, a, m);
+  if (lane == 0) dst[o] = (accumulate ? dst[o] : 0.f) + a;
+}
 void k_reduce_splits(const float* src, float* dst, size_t n, int splits, size_t stride, int accumulate, cudaStream_t s) {
+  if (n && splits >= 64 && n <= (1u << 16)) {
+    launch_pdl(reduce_splits_wide_kernel, dim3((unsigned)((n * 32 + 255) / 256)), dim3(256), (size_t)0, s, src, dst, n, splits, stride, accumulate); LAUNCHED(); return;
+  }
   if (!n) return; launch_pdl(reduce_splits_kernel, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, src, dst, n, splits, stride, accumulate); LAUNCHED();
 }
 
