@@ -78,6 +78,7 @@ struct LayerRT {
   ConvGeom geom{};                                             // conv-equivalent geometry (N filled per call)
   int64_t off_W = -1, n_W = 0, off_b = -1, off_gamma = -1, off_beta = -1, off_mean = -1, off_var = -1;
   int64_t off_W_bf = -1, off_Wt_bf = -1;
+  int64_t off_Wps_bf = -1;                                     // packed [16][9][O] weights of the tcgen05 pixel-shuffle transposed conv (<= 4 image channels)
   int wA = 0, wTaps = 0, wB = 0;                               // internal weight layout [A][taps][B]
   void* out = nullptr; bool out_alias = false;
   void* probs = nullptr;                                       // OUTPUT / LOSS: sigmoid(logits)
@@ -208,7 +209,8 @@ static int32_t net_build(b2g_net* n, const b2g_layer_desc* layers, int32_t nl) {
       default: return fail(B2G_ERR_ARG, "layer %d: unknown type %d", i, d.type);
     }
     l.out_elems = (size_t)l.oh * l.ow * l.oc;
-    if (l.has_gemm() && n->prec == PREC_BF16) { l.off_W_bf = off_bf; off_bf += l.n_W; l.off_Wt_bf = off_bf; off_bf += l.n_W; off_bf = (off_bf + 63) / 64 * 64; }
+    if (l.has_gemm() && n->prec == PREC_BF16) { l.off_W_bf = off_bf; off_bf += l.n_W; l.off_Wt_bf = off_bf; off_bf += l.n_W; off_bf = (off_bf + 63) / 64 * 64;
+      if (n->ctx->tc_ok && tc_deconv_ps_shape(l.geom) && !getenv("B2G_NO_TC_EDGE")) { l.off_Wps_bf = off_bf; off_bf += (int64_t)k_tc_deconv_ps_weight_elems(l.geom); off_bf = (off_bf + 63) / 64 * 64; } }
     h = l.oh; w = l.ow; ch = l.oc;
     n->L.push_back(l);
   }
@@ -249,6 +251,7 @@ static int32_t net_alloc(b2g_net* n) {
       ConvGeom g = l.geom; g.N = R;
       scratch = std::max(scratch, std::max(k_simt_wgrad_scratch_floats(g), k_tc_wgrad_scratch_floats(g)));
       scratch = std::max(scratch, std::max(k_edge_wgrad_scratch_floats(g), k_dense_small_o_wgrad_scratch_floats(g)));
+      scratch = std::max(scratch, k_tc_edge_wgrad_scratch_floats(g));
       scratch = std::max(scratch, k_colsum_scratch_floats(std::max(l.oc, l.ic)));
       max_w = std::max(max_w, (size_t)l.n_W);
       l.needs_wt = n->prec == PREC_BF16 && n->ctx->tc_ok && tc_dgrad_supported(g) && !edge_deconv_small_c_supported(g);
@@ -327,6 +330,7 @@ static void net_refresh_shadow(b2g_net* n, int only_layer = -1, bool straight_do
   if (n->prec != PREC_BF16) return;
   for (size_t i = 0; i < n->L.size(); ++i) { auto& l = n->L[i];
     if (!l.has_gemm() || (only_layer >= 0 && (int)i != only_layer)) continue;
+    if (l.off_Wps_bf >= 0) k_pack_deconv_ps(n->params + l.off_W, n->shadow + l.off_Wps_bf, l.geom.O, l.geom.C, n->ctx->stream);
     if (straight_done && !l.needs_wt) continue;
     k_weight_shadow(n->params + l.off_W, straight_done ? nullptr : n->shadow + l.off_W_bf, l.needs_wt ? n->shadow + l.off_Wt_bf : nullptr, l.wA, l.wTaps, l.wB, n->ctx->stream);
   }
@@ -340,6 +344,8 @@ static const void* w_ptr(const b2g_net* n, const LayerRT& l, int* wprec) {
   *wprec = PREC_F32; return n->params + l.off_W;
 }
 
+// tcgen05 versions of the <= 4-image-channel layers (B2G_NO_TC_EDGE=1 keeps the SIMT kernels of kernels_edge.cu)
+static bool tc_edge_on(const b2g_net* n) { static int on = -1; if (on < 0) on = getenv("B2G_NO_TC_EDGE") ? 0 : 1; return on && n->prec == PREC_BF16 && n->ctx->tc_ok; }
 static inline cudaStream_t fstream(const b2g_net* n) { return n->fwd_stream ? n->fwd_stream : n->ctx->stream; }
 static int32_t gemm_fprop(b2g_net* n, const LayerRT& l, const ConvGeom& g, const void* x, const float* bias, void* out, int act, float alpha, const float* scale = nullptr) {
   cudaStream_t s = fstream(n); int wp; const void* w = w_ptr(n, l, &wp);
@@ -347,6 +353,7 @@ static int32_t gemm_fprop(b2g_net* n, const LayerRT& l, const ConvGeom& g, const
     if (n->prec == PREC_BF16 && n->ctx->tc_ok && tc_fprop_supported(g)) return k_tc_fprop(g, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)out, act, alpha, s, scale) == 0 ? 0 : fail(B2G_ERR_CUDA, "tcgen05 fprop launch failed");
     k_simt_fprop(n->prec, wp, g, x, w, bias, out, act, alpha, s, scale); return 0;
   }
+  if (tc_edge_on(n) && tc_edge_conv_supported(g) && k_tc_edge_conv(g, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)out, act, alpha, s) == 0) return 0;
   if (edge_conv_small_cin_supported(g)) { k_edge_conv_small_cin(n->prec, wp, g, x, w, bias, out, act, alpha, s); return 0; }
   if (dense_small_o_supported(g)) { k_dense_small_o_fwd(n->prec, wp, g, x, w, bias, out, act, alpha, s); return 0; }
   if (n->prec == PREC_BF16 && n->ctx->tc_ok && tc_fprop_supported(g)) {
@@ -360,6 +367,10 @@ static int32_t gemm_dgrad(b2g_net* n, const LayerRT& l, const ConvGeom& g, const
   if (scale) {
     if (n->prec == PREC_BF16 && n->ctx->tc_ok && l.needs_wt && tc_dgrad_supported(g)) return k_tc_dgrad(g, (const __nv_bfloat16*)dy, n->shadow + l.off_Wt_bf, bias, (__nv_bfloat16*)dx, act, alpha, s, scale) == 0 ? 0 : fail(B2G_ERR_CUDA, "tcgen05 dgrad launch failed");
     k_simt_dgrad(n->prec, wp, g, dy, w, bias, dx, act, alpha, s, scale); return 0;
+  }
+  if (tc_edge_on(n) && l.off_Wps_bf >= 0 && tc_deconv_ps_supported(g)) {
+    if (k_tc_deconv_ps(g, (const __nv_bfloat16*)dy, n->shadow + l.off_Wps_bf, bias, (__nv_bfloat16*)dx, act, alpha, s) == 0) return 0;
+    return fail(B2G_ERR_CUDA, "tcgen05 pixel-shuffle deconv launch failed");
   }
   if (edge_deconv_small_c_supported(g)) { k_edge_deconv_small_c(n->prec, wp, g, dy, w, bias, dx, act, alpha, s); return 0; }
   if (dense_small_o_supported(g) && !bias && act == ACT_IDENTITY) { k_dense_small_o_dgrad(n->prec, wp, g, dy, w, dx, s); return 0; }
@@ -377,6 +388,7 @@ static int32_t gemm_dgrad(b2g_net* n, const LayerRT& l, const ConvGeom& g, const
   k_simt_dgrad(n->prec, wp, g, dy, w, bias, dx, act, alpha, s); return 0;
 }
 static int32_t gemm_wgrad(b2g_net* n, const LayerRT& l, const ConvGeom& g, const void* x, const void* dy, float* dw, cudaStream_t s, float* scratch) {
+  if (tc_edge_on(n) && tc_edge_wgrad_supported(g) && k_tc_edge_wgrad(g, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw, scratch, n->scratch_floats, 0, s) == 0) return 0;
   if (edge_wgrad_small_cin_supported(g)) { k_edge_wgrad_small_cin(n->prec, g, x, dy, dw, scratch, 0, s); return 0; }
   if (dense_small_o_supported(g)) { k_dense_small_o_wgrad(n->prec, g, x, dy, dw, scratch, 0, s); return 0; }
   if (n->prec == PREC_BF16 && n->ctx->tc_ok && tc_wgrad_supported(g)) {
@@ -939,8 +951,14 @@ extern "C" int32_t b2g_test_conv(b2g_ctx* c, int32_t kind, int32_t impl, int32_t
     bool ok = kind == 0 ? tc_fprop_supported(g) : kind == 1 ? tc_dgrad_supported(g) : tc_wgrad_supported(g);
     if (!ok) return fail(B2G_ERR_UNSUPPORTED, "no tcgen05 kernel for this shape");
   }
-  float *fa = nullptr, *fb = nullptr, *fo = nullptr, *scratch = nullptr; void *ta = nullptr, *tb = nullptr, *tbt = nullptr, *to = nullptr;
-  size_t sc = std::max(k_simt_wgrad_scratch_floats(g), k_tc_wgrad_scratch_floats(g)) + 16;
+  // impl 2 = the SIMT skinny-layer kernels (kernels_edge.cu), impl 3 = their tcgen05 counterparts; both need <= 4 image channels (g.C)
+  if (impl == 2 || impl == 3) {
+    bool ok = kind == 0 ? edge_conv_small_cin_supported(g) : kind == 1 ? edge_deconv_small_c_supported(g) : edge_wgrad_small_cin_supported(g);
+    if (impl == 3) ok = ok && prec == PREC_BF16 && c->tc_ok && (kind == 0 ? tc_edge_conv_supported(g) : kind == 1 ? tc_deconv_ps_supported(g) : tc_edge_wgrad_supported(g));
+    if (!ok) return fail(B2G_ERR_UNSUPPORTED, "no skinny-layer kernel (impl %d) for this shape", impl);
+  }
+  float *fa = nullptr, *fb = nullptr, *fo = nullptr, *scratch = nullptr; void *ta = nullptr, *tb = nullptr, *tbt = nullptr, *to = nullptr; __nv_bfloat16* wps = nullptr;
+  size_t sc = std::max(std::max(k_simt_wgrad_scratch_floats(g), k_tc_wgrad_scratch_floats(g)), std::max(k_edge_wgrad_scratch_floats(g), k_tc_edge_wgrad_scratch_floats(g))) + 16;
   CU(cudaMalloc(&fa, 4 * na)); CU(cudaMalloc(&fb, 4 * nb)); CU(cudaMalloc(&fo, 4 * no)); CU(cudaMalloc(&scratch, 4 * sc));
   CU(cudaMalloc(&ta, ts * na)); CU(cudaMalloc(&tb, ts * nb)); CU(cudaMalloc(&tbt, ts * nb)); CU(cudaMalloc(&to, ts * no));
   CU(cudaMemcpyAsync(fa, a_host, 4 * na, cudaMemcpyHostToDevice, s)); CU(cudaMemcpyAsync(fb, b_host, 4 * nb, cudaMemcpyHostToDevice, s));
@@ -948,11 +966,17 @@ extern "C" int32_t b2g_test_conv(b2g_ctx* c, int32_t kind, int32_t impl, int32_t
     k_cast_f32_to_bf16(fa, (__nv_bfloat16*)ta, na, s);
     if (kind == 2) k_cast_f32_to_bf16(fb, (__nv_bfloat16*)tb, nb, s); else k_weight_shadow(fb, (__nv_bfloat16*)tb, (__nv_bfloat16*)tbt, g.O, g.KH * g.KW, g.C, s);
   } else { CU(cudaMemcpyAsync(ta, fa, 4 * na, cudaMemcpyDeviceToDevice, s)); CU(cudaMemcpyAsync(tb, fb, 4 * nb, cudaMemcpyDeviceToDevice, s)); }
+  if (impl == 3 && kind == 1) { CU(cudaMalloc(&wps, 2 * k_tc_deconv_ps_weight_elems(g))); k_pack_deconv_ps(fb, wps, g.O, g.C, s); }
   cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
   int reps = iters < 1 ? 1 : iters; int rc = 0;
   for (int it = -1; it < reps; ++it) {       // it = -1: warm-up
     if (it == 0) CU(cudaEventRecord(e0, s));
-    if (kind == 0) { if (impl) rc = k_tc_fprop(g, (const __nv_bfloat16*)ta, (const __nv_bfloat16*)tb, nullptr, (__nv_bfloat16*)to, 0, 0.f, s); else k_simt_fprop(prec, prec, g, ta, tb, nullptr, to, 0, 0.f, s); }
+    if (impl >= 2) {
+      if (kind == 0) { if (impl == 3) rc = k_tc_edge_conv(g, (const __nv_bfloat16*)ta, (const __nv_bfloat16*)tb, nullptr, (__nv_bfloat16*)to, 0, 0.f, s); else k_edge_conv_small_cin(prec, prec, g, ta, tb, nullptr, to, 0, 0.f, s); }
+      else if (kind == 1) { if (impl == 3) rc = k_tc_deconv_ps(g, (const __nv_bfloat16*)ta, wps, nullptr, (__nv_bfloat16*)to, 0, 0.f, s); else k_edge_deconv_small_c(prec, prec, g, ta, tb, nullptr, to, 0, 0.f, s); }
+      else { if (impl == 3) rc = k_tc_edge_wgrad(g, (const __nv_bfloat16*)ta, (const __nv_bfloat16*)tb, fo, scratch, sc, 0, s); else k_edge_wgrad_small_cin(prec, g, ta, tb, fo, scratch, 0, s); }
+    }
+    else if (kind == 0) { if (impl) rc = k_tc_fprop(g, (const __nv_bfloat16*)ta, (const __nv_bfloat16*)tb, nullptr, (__nv_bfloat16*)to, 0, 0.f, s); else k_simt_fprop(prec, prec, g, ta, tb, nullptr, to, 0, 0.f, s); }
     else if (kind == 1) { if (impl) rc = k_tc_dgrad(g, (const __nv_bfloat16*)ta, (const __nv_bfloat16*)tbt, nullptr, (__nv_bfloat16*)to, 0, 0.f, s); else k_simt_dgrad(prec, prec, g, ta, tb, nullptr, to, 0, 0.f, s); }
     else { if (impl) rc = k_tc_wgrad(g, (const __nv_bfloat16*)ta, (const __nv_bfloat16*)tb, fo, scratch, sc, 0, s); else k_simt_wgrad(prec, g, ta, tb, fo, scratch, sc, 0, s); }
     if (rc) break;
@@ -964,6 +988,6 @@ extern "C" int32_t b2g_test_conv(b2g_ctx* c, int32_t kind, int32_t impl, int32_t
   CU(cudaStreamSynchronize(s)); CHECK_KERNELS();
   float ms = 0.f; CU(cudaEventElapsedTime(&ms, e0, e1)); if (ms_per_iter) *ms_per_iter = ms / reps;
   cudaEventDestroy(e0); cudaEventDestroy(e1);
-  cudaFree(fa); cudaFree(fb); cudaFree(fo); cudaFree(scratch); cudaFree(ta); cudaFree(tb); cudaFree(tbt); cudaFree(to);
+  cudaFree(fa); cudaFree(fb); cudaFree(fo); cudaFree(scratch); cudaFree(ta); cudaFree(tb); cudaFree(tbt); cudaFree(to); if (wps) cudaFree(wps);
   return 0;
 }

@@ -137,5 +137,17 @@ int k_tc_fprop(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* w
 int k_tc_dgrad(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat16* wt, const float* bias, __nv_bfloat16* dx, int act, float alpha, cudaStream_t s, const float* scale = nullptr);
 int k_tc_wgrad(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* scratch, size_t scratch_floats, int accumulate, cudaStream_t s);
 size_t k_tc_wgrad_scratch_floats(const ConvGeom& g);
+// transposed conv 4x4 s2 p1 onto <= 4 image channels as one 3x3 tcgen05 conv over the 2x2 output blocks (weights packed by k_pack_deconv_ps)
+bool tc_deconv_ps_shape(const ConvGeom& g);          // geometry only (allocation time)
+bool tc_deconv_ps_supported(const ConvGeom& g);      // + the batch tiles into 128-pixel rows
+size_t k_tc_deconv_ps_weight_elems(const ConvGeom& g);
+void k_pack_deconv_ps(const float* w, __nv_bfloat16* wps, int O, int C, cudaStream_t s);
+// conv 4x4 s2 p1 from <= 4 image channels (fprop form) and its weight gradient: im2col rows built in shared memory by the CTA, tcgen05 MMAs
+bool tc_edge_conv_supported(const ConvGeom& g);
+bool tc_edge_wgrad_supported(const ConvGeom& g);
+size_t k_tc_edge_wgrad_scratch_floats(const ConvGeom& g);
+int k_tc_edge_conv(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out, int act, float alpha, cudaStream_t s);
+int k_tc_edge_wgrad(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* scratch, size_t scratch_floats, int accumulate, cudaStream_t s);
+int k_tc_deconv_ps(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat16* wps, const float* bias, __nv_bfloat16* dx, int act, float alpha, cudaStream_t s);
 
 }  // namespace b2g

@@ -20,6 +20,7 @@
 #include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <algorithm>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -150,7 +151,11 @@ struct TcSmem {
 // refilled only after all CL MMA issuers have committed it (tcgen05.commit multicast onto every CTA's "empty" barrier).
 // AFFINE: the epilogue is act(acc * scale[c] + bias[c]) with both arrays present (inference-mode BatchNorm folded in); otherwise
 // act(acc + bias[c]) with an optional bias.  Two instantiations keep the common path free of the extra loads.
-template <int BN, int STAGES, int CL, bool AFFINE>
+// PS ("pixel shuffle", BN = 16): the 4x4 stride-2 pad-1 transposed conv onto <= 4 image channels (G-last forward, D1 input gradient) as ONE
+// 3x3 stride-1 pad-1 convolution whose 16 output columns are (py, px, c) = the 2x2 output block x 4 (padded) channels: the four
+// sub-pixel phases share every activation load (9 taps instead of 4 x 4), the packed weight [16][9][O] holds zeros where a
+// (tap, phase) pair does not meet; the epilogue scatters its 16 values to the 2x2 block of the NHWC image.
+template <int BN, int STAGES, int CL, bool AFFINE, bool PS = false>
 __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcConvParams p) { pdl_prologue();
   using S = TcSmem<BN, STAGES>;
   const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
@@ -236,6 +241,31 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ CU
     __nv_bfloat16* orow = p.out + pix * p.OC + nb0;
     mbar_wait(bar_accum, 0);
     tc_fence_after();
+    if constexpr (PS) {
+      uint32_t v[32];                       // 32 columns are allocated; [0,16) carry the tile
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16), v);
+      tmem_ld_wait();
+      const int C = p.OC;
+#pragma unroll
+      for (int ppy = 0; ppy < 2; ++ppy) {
+        __nv_bfloat16* dst = p.out + (((size_t)n * p.outH + 2 * gy + ppy) * p.outW + 2 * gx) * C;
+        float o[8];
+#pragma unroll
+        for (int ppx = 0; ppx < 2; ++ppx)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { float a = __uint_as_float(v[(ppy * 2 + ppx) * 4 + c]); if (p.bias && c < C) a += p.bias[c]; o[ppx * 4 + c] = act_fwd(p.act, a, p.alpha); }
+        if (C == 3) {         // 6 contiguous bf16 = three aligned 32-bit stores
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[4]), h2 = __floats2bfloat162_rn(o[5], o[6]);
+          uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+          d32[0] = *reinterpret_cast<uint32_t*>(&h0); d32[1] = *reinterpret_cast<uint32_t*>(&h1); d32[2] = *reinterpret_cast<uint32_t*>(&h2);
+        } else {
+#pragma unroll
+          for (int ppx = 0; ppx < 2; ++ppx)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) if (c < C) dst[ppx * C + c] = __float2bfloat16(o[ppx * 4 + c]);
+        }
+      }
+    } else {
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t v[32];
@@ -261,6 +291,7 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ CU
       uint4* dst = reinterpret_cast<uint4*>(orow + c0);
 #pragma unroll
       for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+    }
     }
     tc_fence_before();
   }
@@ -724,6 +755,258 @@ int k_tc_dgrad(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat16* 
   const int CL = pick_cluster(grid.x);
   if (weight_map(&tmB, wt, g.C, 16, g.O, BN / CL)) return -1;       // transposed shadow [C][taps][O]
   return dispatch_conv(BN, CL, tmA, tmB, p, grid, s);
+}
+
+// ------------------------------------------------------------------ transposed conv onto <= 4 channels ------
+static bool is_k4s2p1_geom(const ConvGeom& g) { return g.KH == 4 && g.KW == 4 && g.SH == 2 && g.SW == 2 && g.PH == 1 && g.PW == 1 && g.H == 2 * g.OH && g.W == 2 * g.OW; }
+bool tc_deconv_ps_shape(const ConvGeom& g) { return is_k4s2p1_geom(g) && g.C >= 1 && g.C <= 4 && g.O % 64 == 0; }
+bool tc_deconv_ps_supported(const ConvGeom& g) { int a, b, c; return tc_deconv_ps_shape(g) && pick_row_tile(g.N, g.OH, g.OW, 128, &a, &b, &c); }
+size_t k_tc_deconv_ps_weight_elems(const ConvGeom& g) { return tc_deconv_ps_shape(g) ? (size_t)16 * 9 * g.O : 0; }
+// w [O][4][4][C] fp32 master -> wps [(py,px,c4)][(dyr,dxc)][O] bf16; dy row offset dyr serves (py, filter row r): -1 -> (0,3); 0 -> (0,1),(1,2); +1 -> (1,0)
+__global__ void pack_deconv_ps_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wps, int O, int C) { pdl_prologue();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x; if (idx >= 16 * 9 * O) return;
+  const int o = idx % O, t = (idx / O) % 9, n = idx / (9 * O);
+  const int py = n >> 3, px = (n >> 2) & 1, c = n & 3, dyr = t / 3 - 1, dxc = t % 3 - 1;
+  const int r = dyr == -1 ? (py == 0 ? 3 : -1) : dyr == 0 ? (py == 0 ? 1 : 2) : (py == 1 ? 0 : -1);
+  const int sx = dxc == -1 ? (px == 0 ? 3 : -1) : dxc == 0 ? (px == 0 ? 1 : 2) : (px == 1 ? 0 : -1);
+  wps[idx] = __float2bfloat16((r >= 0 && sx >= 0 && c < C) ? w[((size_t)o * 16 + r * 4 + sx) * C + c] : 0.f);
+}
+void k_pack_deconv_ps(const float* w, __nv_bfloat16* wps, int O, int C, cudaStream_t s) {
+  launch_pdl(pack_deconv_ps_kernel, dim3((16 * 9 * O + 255) / 256), dim3(256), (size_t)0, s, w, wps, O, C); LAUNCHED();
+}
+int k_tc_deconv_ps(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat16* wps, const float* bias, __nv_bfloat16* dx, int act, float alpha, cudaStream_t s) {
+  TcConvParams p{}; p.mode = 0; p.dbg = 0;
+  if (!tc_deconv_ps_shape(g) || !pick_row_tile(g.N, g.OH, g.OW, 128, &p.Nt, &p.Ht, &p.Wt)) return -1;
+  p.GH = g.OH; p.GW = g.OW; p.tiles_y = g.OH / p.Ht; p.taps_h = 3; p.taps_w = 3; p.chunks = g.O / 64; p.KW = 3;
+  p.SH = 1; p.SW = 1; p.PH = 1; p.PW = 1; p.OC = g.C; p.outH = g.H; p.outW = g.W; p.bias = bias; p.act = act; p.alpha = alpha; p.out = dx;
+  CUtensorMap tmA, tmB;
+  cuuint64_t dims[4] = {(cuuint64_t)g.O, (cuuint64_t)g.OW, (cuuint64_t)g.OH, (cuuint64_t)g.N};
+  cuuint64_t strides[3] = {(cuuint64_t)g.O * 2, (cuuint64_t)g.OW * g.O * 2, (cuuint64_t)g.OH * g.OW * g.O * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)p.Wt, (cuuint32_t)p.Ht, (cuuint32_t)p.Nt}; cuuint32_t es[4] = {1, 1, 1, 1};
+  if (make_map_bf16(&tmA, dy, 4, dims, strides, box, es)) return -1;
+  if (weight_map(&tmB, wps, 16, 9, g.O, 16)) return -1;
+  using S = TcSmem<16, 4>;
+  static bool attr_set = false;
+  if (!attr_set) { if (cudaFuncSetAttribute(tc_conv_kernel<16, 4, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) return -2; attr_set = true; }
+  dim3 grid((unsigned)((long)g.N * g.OH * g.OW / 128), 1, 1);
+  launch_pdl(tc_conv_kernel<16, 4, 1, false, true>, grid, dim3(192), (size_t)S::TOTAL, s, tmA, tmB, p);
+  LAUNCHED();
+  return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
+}
+
+// ------------------------------------------------------------------ conv 4x4 s2 p1 FROM <= 4 image channels ------
+// D1 forward / G-last input gradient (fprop form) and their weight gradient.  K = 16 taps x C <= 64 is ONE 128-byte swizzle row per
+// output pixel, but a 3-channel NHWC image cannot be gathered by TMA (6-byte pixels), so the im2col tile is built by the CTA itself:
+// the (2*Ht+2) input rows a 128-pixel tile touches are one contiguous slab of the image; 128 threads copy it to shared memory with
+// 16-byte loads, each thread then writes its pixel's 4 x (4*C) window as the 128B-swizzled K-major row tcgen05.mma expects
+// (fence.proxy.async makes the generic-proxy writes visible to the tensor core), one thread issues the MMAs, and the 4 warps drain TMEM.
+// Many short CTAs per SM (31 KB smem, 64 TMEM columns each) overlap each other's load / transform / MMA / store phases.
+struct TcEdgeParams {
+  const __nv_bfloat16* x; const __nv_bfloat16* w; const __nv_bfloat16* dy; const float* bias; __nv_bfloat16* out; float* part;
+  int N, H, W, C, OH, OW, O, Ht, tiles_y, tiles_total, tiles_per_cta, act; float alpha;
+};
+static constexpr int EDGE_SLAB_BYTES = 6144;
+__device__ __forceinline__ uint32_t swz128(int row, int byte) { return (uint32_t)(row * 128 + ((((byte >> 4) ^ (row & 7)) << 4) | (byte & 15))); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// rows 2*oy0-1 .. 2*(oy0+Ht-1)+2 of image n -> slab (zero rows outside the image)
+__device__ __forceinline__ void edge_load_slab(const TcEdgeParams& p, int n, int oy0, uint8_t* slab) {
+  const int WC = p.W * p.C, cpr = WC >> 3, nrows = 2 * p.Ht + 2;
+  for (int i = threadIdx.x; i < nrows * cpr; i += blockDim.x) {
+    const int j = i / cpr, cc = i - j * cpr, iy = 2 * oy0 - 1 + j;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (iy >= 0 && iy < p.H) v = __ldg(reinterpret_cast<const uint4*>(p.x + ((size_t)n * p.H + iy) * WC) + cc);
+    reinterpret_cast<uint4*>(slab)[i] = v;
+  }
+}
+// thread = output pixel (oy_l, ox) of the tile: k = (r*4 + s)*C + c  <-  slab row 2*oy_l + r, elements (2*ox-1)*C + s*C + c
+__device__ __forceinline__ void edge_build_row(const TcEdgeParams& p, const uint8_t* slab, uint8_t* tile, int row) {
+  const int WC = p.W * p.C, oy_l = row / p.OW, ox = row - oy_l * p.OW, e0 = (2 * ox - 1) * p.C, K = 16 * p.C;
+  const uint16_t* s16 = reinterpret_cast<const uint16_t*>(slab);
+  for (int r = 0; r < 4; ++r) {
+    const uint16_t* srow = s16 + (2 * oy_l + r) * WC;
+    for (int jp = 0; jp < 2 * p.C; ++jp) {
+      const int e = e0 + 2 * jp;
+      const uint32_t lo = (e >= 0 && e < WC) ? srow[e] : 0u, hi = (e + 1 >= 0 && e + 1 < WC) ? srow[e + 1] : 0u;
+      *reinterpret_cast<uint32_t*>(tile + swz128(row, (r * 4 * p.C + 2 * jp) * 2)) = lo | (hi << 16);
+    }
+  }
+  for (int k = K; k < 64; k += 2) *reinterpret_cast<uint32_t*>(tile + swz128(row, k * 2)) = 0u;
+}
+
+__global__ void __launch_bounds__(128) tc_edge_conv_kernel(const TcEdgeParams p) { pdl_prologue();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (smem_base - smem_u32(smem_raw));
+  uint8_t* sA = sm; uint8_t* sB = sm + 16384; uint8_t* slab = sm + 24576;
+  const uint32_t bar = smem_base + 24576 + EDGE_SLAB_BYTES;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + 24576 + EDGE_SLAB_BYTES + 8);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int mt = blockIdx.x, nb0 = blockIdx.y * 64;
+  const int n = mt / p.tiles_y, oy0 = (mt % p.tiles_y) * p.Ht, K = 16 * p.C;
+  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  if (warp == 0) { tmem_alloc(smem_u32((const void*)tmem_slot), 64); tmem_relinquish(); }
+  edge_load_slab(p, n, oy0, slab);
+  for (int i = tid; i < 64 * 32; i += 128) {          // weight tile [64 o][64 k] K-major: row o = 16*C contiguous bf16 of the shadow, zero padded
+    const int o = i >> 5, kp = i & 31;
+    const uint32_t v = (2 * kp < K) ? *reinterpret_cast<const uint32_t*>(p.w + (size_t)(nb0 + o) * K + 2 * kp) : 0u;
+    *reinterpret_cast<uint32_t*>(sB + swz128(o, kp * 4)) = v;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  edge_build_row(p, slab, sA, tid);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) {
+    constexpr uint32_t idesc = make_idesc(128, 64, 0, 0);
+    const uint64_t adesc = desc_kmajor_sw128(smem_base), bdesc = desc_kmajor_sw128(smem_base + 16384);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, k != 0);
+    umma_commit(bar);
+  }
+  mbar_wait(bar, 0);
+  tc_fence_after();
+  {
+    const int oy_l = tid / p.OW, ox = tid - oy_l * p.OW;
+    __nv_bfloat16* orow = p.out + (((size_t)n * p.OH + oy0 + oy_l) * p.OW + ox) * p.O + nb0;
+    const bool has_bias = p.bias != nullptr;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld_wait();
+      uint32_t packed[16];
+#define B2G_EDGE_EPI(ACTC)                                                                                              \
+  _Pragma("unroll") for (int j = 0; j < 16; ++j) {                                                                      \
+    float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);                                             \
+    if (has_bias) { a += p.bias[nb0 + c0 + 2 * j]; b += p.bias[nb0 + c0 + 2 * j + 1]; }                                \
+    a = act_fwd(ACTC, a, p.alpha); b = act_fwd(ACTC, b, p.alpha);                                                       \
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);                                                                     \
+    packed[j] = *reinterpret_cast<uint32_t*>(&h);                                                                       \
+  }
+      if (p.act == ACT_IDENTITY) { B2G_EDGE_EPI(ACT_IDENTITY) }
+      else if (p.act == ACT_LRELU) { B2G_EDGE_EPI(ACT_LRELU) }
+      else { B2G_EDGE_EPI(p.act) }
+#undef B2G_EDGE_EPI
+      uint4* dst = reinterpret_cast<uint4*>(orow + c0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 64); }
+}
+
+// weight gradient of the same layers: dw[o][k] = sum_pix dy[pix][o] * xcol[pix][k].  Both operands are MN-major tiles [128 pixel rows][128 B]:
+// dy rows are copied as they are (64 channels = 128 B), xcol rows are built as above.  O = 64 fills half of the M = 128 instruction;
+// the second 64-row block of the A descriptor points at the xcol tile (LBO = 16 KB), those accumulator rows are never read.
+// Each CTA walks tiles_per_cta consecutive tiles (split over pixels), accumulating in TMEM, and writes one fp32 partial.
+__global__ void __launch_bounds__(128) tc_edge_wgrad_kernel(const TcEdgeParams p) { pdl_prologue();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (smem_base - smem_u32(smem_raw));
+  uint8_t* sDy = sm; uint8_t* sX = sm + 16384; uint8_t* slab = sm + 32768;
+  const uint32_t bar = smem_base + 32768 + EDGE_SLAB_BYTES;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + 32768 + EDGE_SLAB_BYTES + 8);
+  const int tid = threadIdx.x, warp = tid >> 5, K = 16 * p.C;
+  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  if (warp == 0) { tmem_alloc(smem_u32((const void*)tmem_slot), 64); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int t_beg = blockIdx.x * p.tiles_per_cta, t_end = min(p.tiles_total, t_beg + p.tiles_per_cta);
+  uint32_t ph = 0;
+  for (int t = t_beg; t < t_end; ++t) {
+    const int n = t / p.tiles_y, oy0 = (t % p.tiles_y) * p.Ht;
+    edge_load_slab(p, n, oy0, slab);
+    const uint4* dyt = reinterpret_cast<const uint4*>(p.dy + (((size_t)n * p.OH + oy0) * p.OW) * 64);     // the tile's 128 pixels are contiguous: 16 KB
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const int idx = tid + i * 128, r = idx >> 3, cc = idx & 7; *reinterpret_cast<uint4*>(sDy + r * 128 + ((cc ^ (r & 7)) << 4)) = __ldg(dyt + idx); }
+    __syncthreads();
+    edge_build_row(p, slab, sX, tid);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+      constexpr uint32_t idesc = make_idesc(128, 64, 1, 1);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)       // 16 pixel rows per MMA
+        umma_bf16(tmem_base, desc_mnmajor_sw128(smem_base + k * 2048, 16384), desc_mnmajor_sw128(smem_base + 16384 + k * 2048, 16384), idesc, (t != t_beg) || k != 0);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, ph); ph ^= 1u;       // the MMAs have consumed both tiles: shared memory may be overwritten
+    tc_fence_after();
+  }
+  if (warp < 2) {                         // accumulator rows 0..63 = output channel o
+    float* orow = p.part + ((size_t)blockIdx.x * 64 + tid) * K;
+    if (t_end > t_beg) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (c0 + 4 * j < K) *reinterpret_cast<float4*>(orow + c0 + 4 * j) = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+      }
+    } else {
+      for (int k = 0; k < K; ++k) orow[k] = 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 64); }
+}
+
+static bool edge_tile(const ConvGeom& g, int* Ht) {
+  if (!is_k4s2p1_geom(g) || g.C < 1 || g.C > 4 || g.OW > 128 || 128 % g.OW) return false;
+  const int ht = 128 / g.OW;
+  if (g.OH % ht || (g.W * g.C) % 8 || (2 * ht + 2) * g.W * g.C * 2 > EDGE_SLAB_BYTES) return false;
+  *Ht = ht; return true;
+}
+bool tc_edge_conv_supported(const ConvGeom& g) { int ht; return edge_tile(g, &ht) && g.O % 64 == 0; }
+bool tc_edge_wgrad_supported(const ConvGeom& g) { int ht; return edge_tile(g, &ht) && g.O == 64; }
+static int tc_edge_wgrad_target() { static int target = -1; if (target < 0) { const char* e = getenv("B2G_EDGE_WGRAD_CTAS"); target = e ? atoi(e) : 296; if (target < 1 || target > 1184) target = 296; } return target; }
+static int tc_edge_wgrad_ctas(const ConvGeom& g, int* tpc) {
+  int ht = 1; edge_tile(g, &ht);
+  const int tiles = g.N * (g.OH / ht), target = tc_edge_wgrad_target();
+  const int per = (tiles + target - 1) / target; *tpc = per < 1 ? 1 : per;
+  return (tiles + *tpc - 1) / *tpc;
+}
+size_t k_tc_edge_wgrad_scratch_floats(const ConvGeom& g) { return tc_edge_wgrad_supported(g) ? (size_t)tc_edge_wgrad_target() * 64 * 16 * g.C : 0; }
+int k_tc_edge_conv(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out, int act, float alpha, cudaStream_t s) {
+  TcEdgeParams p{}; if (!edge_tile(g, &p.Ht) || g.O % 64) return -1;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 3) || (reinterpret_cast<uintptr_t>(out) & 15)) return -1;
+  p.x = x; p.w = w; p.bias = bias; p.out = out; p.N = g.N; p.H = g.H; p.W = g.W; p.C = g.C; p.OH = g.OH; p.OW = g.OW; p.O = g.O; p.tiles_y = g.OH / p.Ht;
+  p.tiles_total = g.N * p.tiles_y; p.act = act; p.alpha = alpha;
+  const size_t smem = 1024 + 24576 + EDGE_SLAB_BYTES + 64;
+  static bool attr_set = false;
+  if (!attr_set) { if (cudaFuncSetAttribute(tc_edge_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2; attr_set = true; }
+  launch_pdl(tc_edge_conv_kernel, dim3((unsigned)p.tiles_total, (unsigned)(g.O / 64)), dim3(128), smem, s, p);
+  LAUNCHED();
+  return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
+}
+int k_tc_edge_wgrad(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* scratch, size_t scratch_floats, int accumulate, cudaStream_t s) {
+  TcEdgeParams p{}; if (!edge_tile(g, &p.Ht) || g.O != 64) return -1;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(dy) & 15)) return -1;
+  p.x = x; p.dy = dy; p.part = scratch; p.N = g.N; p.H = g.H; p.W = g.W; p.C = g.C; p.OH = g.OH; p.OW = g.OW; p.O = g.O; p.tiles_y = g.OH / p.Ht;
+  p.tiles_total = g.N * p.tiles_y;
+  const int ctas = tc_edge_wgrad_ctas(g, &p.tiles_per_cta); const size_t n = (size_t)64 * 16 * g.C;
+  if ((size_t)ctas * n > scratch_floats) return -5;
+  const size_t smem = 1024 + 32768 + EDGE_SLAB_BYTES + 64;
+  static bool attr_set = false;
+  if (!attr_set) { if (cudaFuncSetAttribute(tc_edge_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2; attr_set = true; }
+  launch_pdl(tc_edge_wgrad_kernel, dim3((unsigned)ctas), dim3(128), smem, s, p);
+  LAUNCHED();
+  if (cudaPeekAtLastError() != cudaSuccess) return -3;
+  k_reduce_splits(scratch, dw, n, ctas, n, accumulate, s);
+  return 0;
 }
 
 // ------------------------------------------------------------------ wgrad: MN-major operands --------------

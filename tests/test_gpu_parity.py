@@ -365,6 +365,39 @@ def test_tc_wgrad_mn_major_matches_oracle(b200, case):
     assert rel_err(out.reshape(oc, 4, 4, c), dw.transpose(0, 2, 3, 1)) < 1e-4     # fp32 accumulate, fp32 out: only summation order differs
 
 
+TC_EDGE_CASES = [
+    # conv geometry 4x4 s2 p1 with <= 4 image channels: n, h, w, c (image side), o (feature side)
+    (4, 64, 64, 3, 64),       # DCGAN D1 / G-last
+    (2, 128, 128, 3, 64),     # C4: 128x128 images
+    (8, 16, 16, 3, 128),      # two images per 128-pixel tile, two 64-channel K chunks
+    (2, 32, 32, 4, 64), (2, 32, 32, 1, 64),
+]
+
+
+@pytest.mark.parametrize("case", TC_EDGE_CASES)
+def test_tc_skinny_layer_kernels_match_oracle(b200, case):
+    """tcgen05 versions of the <= 4-image-channel layers: transposed conv as ONE 3x3 conv over 2x2 output blocks (pixel-shuffle epilogue)."""
+    b, ctx = b200
+    n, h, w, c, oc = case
+    rng = np.random.default_rng(5)
+    x, wt, y, dy, dx, dw = _conv_ref(n, h, w, c, oc, 4, 2, 1, rng, bf16_round)
+    geom = dict(n=n, h=h, w=w, c=c, oh=h // 2, ow=w // 2, o=oc, kh=4, kw=4, sh=2, sw=2, ph=1, pw=1)
+    dy_nhwc = dy.transpose(0, 2, 3, 1); w_int = wt.transpose(0, 2, 3, 1)
+    out, _ = b.test_conv(ctx, 1, 3, b.BF16, geom, dy_nhwc, w_int, dx.size)
+    assert rel_err(out.reshape(n, h, w, c), dx.transpose(0, 2, 3, 1)) < 1e-2
+    ref, _ = b.test_conv(ctx, 1, 2, b.BF16, geom, dy_nhwc, w_int, dx.size)           # SIMT skinny kernel, same operands
+    assert rel_err(out, ref) < 1e-2
+    # fprop: im2col rows built in shared memory (the 3-channel image cannot be gathered by TMA), one K = 64 MMA group per 128 pixels
+    if w // 2 < 16:
+        return        # 128-pixel tiles spanning several images are only implemented for the transposed-conv form
+    x_nhwc = x.transpose(0, 2, 3, 1)
+    out, _ = b.test_conv(ctx, 0, 3, b.BF16, geom, x_nhwc, w_int, y.size)
+    assert rel_err(out.reshape(n, h // 2, w // 2, oc), y.transpose(0, 2, 3, 1)) < 1e-2
+    if oc == 64:      # wgrad: MN-major operands, split over pixels, fp32 partials summed in fixed order
+        out, _ = b.test_conv(ctx, 2, 3, b.BF16, geom, x_nhwc, dy_nhwc, dw.size)
+        assert rel_err(out.reshape(oc, 4, 4, c), dw.transpose(0, 2, 3, 1)) < 1e-4
+
+
 # ------------------------------------------------------------------------------------------------
 # skinny-layer kernels (kernels_edge.cu) are reached through the engine: layer-level parity in both precisions
 # ------------------------------------------------------------------------------------------------
