@@ -374,6 +374,7 @@ static int32_t gemm_dgrad(b2g_net* n, const LayerRT& l, const ConvGeom& g, const
   }
   if (edge_deconv_small_c_supported(g)) { k_edge_deconv_small_c(n->prec, wp, g, dy, w, bias, dx, act, alpha, s); return 0; }
   if (dense_small_o_supported(g) && !bias && act == ACT_IDENTITY) { k_dense_small_o_dgrad(n->prec, wp, g, dy, w, dx, s); return 0; }
+  if (dense_small_k_supported(g) && !(n->prec == PREC_BF16 && n->ctx->tc_ok && g.O % 64 == 0)) { k_dense_small_k_dgrad(n->prec, wp, g, dy, w, bias, dx, act, alpha, s); return 0; }
   if (n->prec == PREC_BF16 && n->ctx->tc_ok && l.needs_wt && g.KH == 1 && g.KW == 1 && g.H == 1 && g.W == 1) {
     ConvGeom t = g; t.C = g.O; t.O = g.C;
     if (tc_fprop_supported(t)) {
@@ -387,10 +388,11 @@ static int32_t gemm_dgrad(b2g_net* n, const LayerRT& l, const ConvGeom& g, const
   }
   k_simt_dgrad(n->prec, wp, g, dy, w, bias, dx, act, alpha, s); return 0;
 }
-static int32_t gemm_wgrad(b2g_net* n, const LayerRT& l, const ConvGeom& g, const void* x, const void* dy, float* dw, cudaStream_t s, float* scratch) {
-  if (tc_edge_on(n) && tc_edge_wgrad_supported(g) && k_tc_edge_wgrad(g, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw, scratch, n->scratch_floats, 0, s) == 0) return 0;
+static int32_t gemm_wgrad(b2g_net* n, const LayerRT& l, const ConvGeom& g, const void* x, const void* dy, float* dw, cudaStream_t s, float* scratch, float* db = nullptr, bool* bias_done = nullptr) {
+  if (tc_edge_on(n) && tc_edge_wgrad_supported(g)) { const int r = k_tc_edge_wgrad(g, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw, db, scratch, n->scratch_floats, 0, s); if (r >= 0) { if (bias_done) *bias_done = r == 1; return 0; } }
   if (edge_wgrad_small_cin_supported(g)) { k_edge_wgrad_small_cin(n->prec, g, x, dy, dw, scratch, 0, s); return 0; }
   if (dense_small_o_supported(g)) { k_dense_small_o_wgrad(n->prec, g, x, dy, dw, scratch, 0, s); return 0; }
+  if (dense_small_k_supported(g) && !(n->prec == PREC_BF16 && n->ctx->tc_ok && tc_wgrad_supported(g))) { k_dense_small_k_wgrad(n->prec, g, x, dy, dw, s); return 0; }
   if (n->prec == PREC_BF16 && n->ctx->tc_ok && tc_wgrad_supported(g)) {
     if (k_tc_wgrad(g, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw, scratch, n->scratch_floats, 0, s) == 0) return 0;
     return fail(B2G_ERR_CUDA, "tcgen05 wgrad launch failed");
@@ -491,8 +493,9 @@ static int32_t net_backward(b2g_net* n, const void* net_in, void* eps, int rows,
         if (d.act != B2G_ACT_IDENTITY) k_act_bwd_from_output(n->prec, l.out, cur, cur, (size_t)R * l.out_elems, d.act, d.act_alpha, s);
         if (want_wgrad_l) {
           fork_wgrad(i, cur);
-          B2(gemm_wgrad(n, l, g, lin, cur, n->grads + l.off_W, s2, n->scratch2));
-          if (l.off_b >= 0) k_colsum(n->prec, cur, R * l.oh * l.ow, l.oc, n->scratch2, n->grads + l.off_b, 0, s2);
+          bool bias_done = false;
+          B2(gemm_wgrad(n, l, g, lin, cur, n->grads + l.off_W, s2, n->scratch2, l.off_b >= 0 ? n->grads + l.off_b : nullptr, &bias_done));
+          if (l.off_b >= 0 && !bias_done) k_colsum(n->prec, cur, R * l.oh * l.ow, l.oc, n->scratch2, n->grads + l.off_b, 0, s2);
           mark_reader(i, cur);
         }
         if (need_in) { void* nx = other(cur); B2(gemm_dgrad(n, l, g, cur, nullptr, nx, ACT_IDENTITY, 0.f)); cur = nx; }
@@ -974,7 +977,7 @@ extern "C" int32_t b2g_test_conv(b2g_ctx* c, int32_t kind, int32_t impl, int32_t
     if (impl >= 2) {
       if (kind == 0) { if (impl == 3) rc = k_tc_edge_conv(g, (const __nv_bfloat16*)ta, (const __nv_bfloat16*)tb, nullptr, (__nv_bfloat16*)to, 0, 0.f, s); else k_edge_conv_small_cin(prec, prec, g, ta, tb, nullptr, to, 0, 0.f, s); }
       else if (kind == 1) { if (impl == 3) rc = k_tc_deconv_ps(g, (const __nv_bfloat16*)ta, wps, nullptr, (__nv_bfloat16*)to, 0, 0.f, s); else k_edge_deconv_small_c(prec, prec, g, ta, tb, nullptr, to, 0, 0.f, s); }
-      else { if (impl == 3) rc = k_tc_edge_wgrad(g, (const __nv_bfloat16*)ta, (const __nv_bfloat16*)tb, fo, scratch, sc, 0, s); else k_edge_wgrad_small_cin(prec, g, ta, tb, fo, scratch, 0, s); }
+      else { if (impl == 3) rc = k_tc_edge_wgrad(g, (const __nv_bfloat16*)ta, (const __nv_bfloat16*)tb, fo, nullptr, scratch, sc, 0, s); else k_edge_wgrad_small_cin(prec, g, ta, tb, fo, scratch, 0, s); }
     }
     else if (kind == 0) { if (impl) rc = k_tc_fprop(g, (const __nv_bfloat16*)ta, (const __nv_bfloat16*)tb, nullptr, (__nv_bfloat16*)to, 0, 0.f, s); else k_simt_fprop(prec, prec, g, ta, tb, nullptr, to, 0, 0.f, s); }
     else if (kind == 1) { if (impl) rc = k_tc_dgrad(g, (const __nv_bfloat16*)ta, (const __nv_bfloat16*)tbt, nullptr, (__nv_bfloat16*)to, 0, 0.f, s); else k_simt_dgrad(prec, prec, g, ta, tb, nullptr, to, 0, 0.f, s); }

@@ -126,6 +126,9 @@ void k_dense_small_o_fwd(int prec, int wprec, const ConvGeom& g, const void* x, 
 void k_dense_small_o_dgrad(int prec, int wprec, const ConvGeom& g, const void* dy, const void* w, void* dx, cudaStream_t s);
 void k_dense_small_o_wgrad(int prec, const ConvGeom& g, const void* x, const void* dy, float* dw, float* scratch, int accumulate, cudaStream_t s);
 size_t k_dense_small_o_wgrad_scratch_floats(const ConvGeom& g);
+bool dense_small_k_supported(const ConvGeom& g);         // 1x1 geometry, reduction g.O <= 128, g.C % 256 == 0 (DCGAN G-first: z -> 4x4 map)
+void k_dense_small_k_dgrad(int prec, int wprec, const ConvGeom& g, const void* dy, const void* w, const float* bias, void* dx, int act, float alpha, cudaStream_t s);
+void k_dense_small_k_wgrad(int prec, const ConvGeom& g, const void* x, const void* dy, float* dw, cudaStream_t s);
 
 // ---- GEMM-shaped kernels, tcgen05 tensor cores (bf16 in, fp32 accumulate in TMEM) -------------------------
 bool tc_fprop_supported(const ConvGeom& g);
@@ -147,7 +150,8 @@ bool tc_edge_conv_supported(const ConvGeom& g);
 bool tc_edge_wgrad_supported(const ConvGeom& g);
 size_t k_tc_edge_wgrad_scratch_floats(const ConvGeom& g);
 int k_tc_edge_conv(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out, int act, float alpha, cudaStream_t s);
-int k_tc_edge_wgrad(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* scratch, size_t scratch_floats, int accumulate, cudaStream_t s);
+// db (optional, g.C < 4): also the column sums of dy (= the conv bias gradient) from a ones column of the im2col tile; returns 1 if db was written, 0 if not, < 0 on error
+int k_tc_edge_wgrad(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* db, float* scratch, size_t scratch_floats, int accumulate, cudaStream_t s);
 int k_tc_deconv_ps(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat16* wps, const float* bias, __nv_bfloat16* dx, int act, float alpha, cudaStream_t s);
 
 }  // namespace b2g

@@ -256,6 +256,87 @@ __global__ void dense_small_o_wgrad_kernel(const T* __restrict__ x, const T* __r
   for (int o = 0; o < O; ++o) part[(size_t)blockIdx.y * O * K + (size_t)o * K + k] = acc[o];
 }
 
+// ------------------------------------------------------------------ (e) 1x1 layers with a short reduction (G-first: z -> 4x4 map) -----
+// Transposed conv of a 1x1 input = out[n][c] = sum_o z[n][o] * W[o][c] with O = nIn (100) and C = taps*nOut (8192): the reduction is too
+// short (and not a multiple of 64) for the tensor-core tiles, the work is reading W / writing the map once.  Thread = 2 adjacent c
+// (one 32-bit weight load per o), 16 rows of n per CTA with z staged in smem as fp32 and read as float4 broadcasts (4 o at a time).
+template <typename T> __device__ __forceinline__ float2 ld2(const T* p);
+template <> __device__ __forceinline__ float2 ld2<float>(const float* p) { if ((reinterpret_cast<uintptr_t>(p) & 7) == 0) return *reinterpret_cast<const float2*>(p); return make_float2(p[0], p[1]); }   // fp32 parameters sit at arbitrary offsets
+template <> __device__ __forceinline__ float2 ld2<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p)); }
+__device__ __forceinline__ void st2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+__device__ __forceinline__ void st2(__nv_bfloat16* p, float a, float b) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b); }
+
+// The thread's weights for 16 o are fetched together, one chunk ahead of the FMAs (register double buffer): one global latency per 16 o.
+template <typename T, typename TW>
+__global__ void __launch_bounds__(128) dense_small_k_dgrad_kernel(const T* __restrict__ dy, const TW* __restrict__ w, const float* __restrict__ bias, T* __restrict__ dx,
+                                                                   int N, int C, int O, int act, float alpha) { pdl_prologue();
+  constexpr int OC = 16;                                  // o per chunk
+  __shared__ __align__(16) float sz[16][128];            // [n][o], zero padded to a multiple of OC
+  const int cb = blockIdx.x * 256, c = cb + threadIdx.x * 2, n0 = blockIdx.y * 16, OP = (O + OC - 1) / OC * OC;
+  for (int i = threadIdx.x; i < 16 * OP; i += 128) { const int r = i / OP, o = i - r * OP; sz[r][o] = (o < O && n0 + r < N) ? ldf(dy, (size_t)(n0 + r) * O + o) : 0.f; }
+  float acc[16][2];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; }
+  float2 pre[OC];                                         // thread's pair of columns for each o of the next chunk
+#pragma unroll
+  for (int j = 0; j < OC; ++j) pre[j] = (j < O) ? ld2(w + (size_t)j * C + c) : make_float2(0.f, 0.f);
+  __syncthreads();
+  for (int o0 = 0; o0 < OP; o0 += OC) {
+    float2 cur[OC];
+#pragma unroll
+    for (int j = 0; j < OC; ++j) { cur[j] = pre[j]; pre[j] = (o0 + OC + j < O) ? ld2(w + (size_t)(o0 + OC + j) * C + c) : make_float2(0.f, 0.f); }
+#pragma unroll
+    for (int j4 = 0; j4 < OC / 4; ++j4) {
+      const float2* wv = cur + 4 * j4;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const float4 z = *reinterpret_cast<const float4*>(&sz[r][o0 + 4 * j4]);
+        acc[r][0] = fmaf(z.x, wv[0].x, acc[r][0]); acc[r][1] = fmaf(z.x, wv[0].y, acc[r][1]);
+        acc[r][0] = fmaf(z.y, wv[1].x, acc[r][0]); acc[r][1] = fmaf(z.y, wv[1].y, acc[r][1]);
+        acc[r][0] = fmaf(z.z, wv[2].x, acc[r][0]); acc[r][1] = fmaf(z.z, wv[2].y, acc[r][1]);
+        acc[r][0] = fmaf(z.w, wv[3].x, acc[r][0]); acc[r][1] = fmaf(z.w, wv[3].y, acc[r][1]);
+      }
+    }
+  }
+  const float b0 = bias ? bias[c] : 0.f, b1 = bias ? bias[c + 1] : 0.f;
+#pragma unroll
+  for (int r = 0; r < 16; ++r) if (n0 + r < N) st2(dx + (size_t)(n0 + r) * C + c, act_fwd(act, acc[r][0] + b0, alpha), act_fwd(act, acc[r][1] + b1, alpha));
+}
+// dw[o][c] = sum_n dy[n][o] * x[n][c]: thread = 2 adjacent c x 16 o, the whole batch reduced in the CTA (no split, deterministic);
+// rows are consumed 8 at a time so that eight global loads are in flight per thread
+template <typename T>
+__global__ void __launch_bounds__(128) dense_small_k_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw, int N, int C, int O) { pdl_prologue();
+  __shared__ __align__(16) float sd[128][16];            // [n][o local]
+  const int c = (blockIdx.x * 128 + threadIdx.x) * 2, o0 = blockIdx.y * 16;
+  float acc[16][2];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; }
+  for (int nb = 0; nb < N; nb += 128) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 128 * 16; i += 128) { const int r = i >> 4, o = i & 15; sd[r][o] = (nb + r < N && o0 + o < O) ? ldf(dy, (size_t)(nb + r) * O + o0 + o) : 0.f; }
+    __syncthreads();
+    const int rows = min(128, N - nb);
+    for (int r0 = 0; r0 < rows; r0 += 8) {
+      float2 xv[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) xv[q] = (r0 + q < rows) ? ld2(x + (size_t)(nb + r0 + q) * C + c) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 d = *reinterpret_cast<const float4*>(&sd[r0 + q][4 * j4]);
+          acc[4 * j4][0] = fmaf(d.x, xv[q].x, acc[4 * j4][0]); acc[4 * j4][1] = fmaf(d.x, xv[q].y, acc[4 * j4][1]);
+          acc[4 * j4 + 1][0] = fmaf(d.y, xv[q].x, acc[4 * j4 + 1][0]); acc[4 * j4 + 1][1] = fmaf(d.y, xv[q].y, acc[4 * j4 + 1][1]);
+          acc[4 * j4 + 2][0] = fmaf(d.z, xv[q].x, acc[4 * j4 + 2][0]); acc[4 * j4 + 2][1] = fmaf(d.z, xv[q].y, acc[4 * j4 + 2][1]);
+          acc[4 * j4 + 3][0] = fmaf(d.w, xv[q].x, acc[4 * j4 + 3][0]); acc[4 * j4 + 3][1] = fmaf(d.w, xv[q].y, acc[4 * j4 + 3][1]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) if (o0 + j < O) st2(dw + (size_t)(o0 + j) * C + c, acc[j][0], acc[j][1]);
+}
+
 // ------------------------------------------------------------------ host wrappers ---------------------------------
 static bool is_k4s2p1(const ConvGeom& g) { return g.KH == 4 && g.KW == 4 && g.SH == 2 && g.SW == 2 && g.PH == 1 && g.PW == 1 && g.H == 2 * g.OH && g.W == 2 * g.OW; }
 bool edge_deconv_small_c_supported(const ConvGeom& g) { return is_k4s2p1(g) && g.C <= 4 && g.O % 8 == 0 && g.O <= 128; }
@@ -292,6 +373,18 @@ void k_edge_wgrad_small_cin(int prec, const ConvGeom& g, const void* x, const vo
   const size_t n = (size_t)g.O * 16 * g.C; const size_t smem = (64 * g.O + 64 * 64) * sizeof(float);
   DISPATCH_PREC(prec, T, (launch_pdl(edge_wgrad_small_cin_kernel<T>, dim3(ctas), dim3(2 * g.O), (size_t)(smem), s, (const T*)x, (const T*)dy, scratch, g.N, g.H, g.W, g.C, g.OH, g.OW, g.O, ppc))); LAUNCHED();
   k_reduce_splits(scratch, dw, n, ctas, n, accumulate, s);
+}
+bool dense_small_k_supported(const ConvGeom& g) { return g.KH == 1 && g.KW == 1 && g.H == 1 && g.W == 1 && g.O >= 1 && g.O <= 128 && g.C % 256 == 0 && g.C >= 256; }
+void k_dense_small_k_dgrad(int prec, int wprec, const ConvGeom& g, const void* dy, const void* w, const float* bias, void* dx, int act, float alpha, cudaStream_t s) {
+  dim3 grid(g.C / 256, (g.N + 15) / 16);
+  if (prec == PREC_F32) launch_pdl(dense_small_k_dgrad_kernel<float, float>, grid, dim3(128), (size_t)0, s, (const float*)dy, (const float*)w, bias, (float*)dx, g.N, g.C, g.O, act, alpha);
+  else if (wprec == PREC_F32) launch_pdl(dense_small_k_dgrad_kernel<__nv_bfloat16, float>, grid, dim3(128), (size_t)0, s, (const __nv_bfloat16*)dy, (const float*)w, bias, (__nv_bfloat16*)dx, g.N, g.C, g.O, act, alpha);
+  else launch_pdl(dense_small_k_dgrad_kernel<__nv_bfloat16, __nv_bfloat16>, grid, dim3(128), (size_t)0, s, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)dx, g.N, g.C, g.O, act, alpha);
+  LAUNCHED();
+}
+void k_dense_small_k_wgrad(int prec, const ConvGeom& g, const void* x, const void* dy, float* dw, cudaStream_t s) {
+  dim3 grid(g.C / 256, (g.O + 15) / 16);
+  DISPATCH_PREC(prec, T, (launch_pdl(dense_small_k_wgrad_kernel<T>, grid, dim3(128), (size_t)0, s, (const T*)x, (const T*)dy, dw, g.N, g.C, g.O))); LAUNCHED();
 }
 void k_dense_small_o_fwd(int prec, int wprec, const ConvGeom& g, const void* x, const void* w, const float* bias, void* out, int act, float alpha, cudaStream_t s) {
   if (prec == PREC_F32) launch_pdl(dense_small_o_fwd_kernel<float, float>, dim3(g.N), dim3(128), (size_t)(0), s, (const float*)x, (const float*)w, bias, (float*)out, g.C, g.O, act, alpha);

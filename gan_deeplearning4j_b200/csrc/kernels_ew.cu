@@ -9,6 +9,7 @@
 // All of these are bandwidth-bound: threads are mapped so that a warp touches consecutive channels
 // (NHWC innermost), reductions are fixed-order two-stage (deterministic), nothing allocates.
 #include <stdlib.h>
+#include <algorithm>
 #include "kernels.h"
 #include "common.cuh"
 
@@ -43,6 +44,7 @@ __global__ void permute_kernel(const T* __restrict__ src, T* __restrict__ dst, i
     else         { int p = i % HW; size_t t = i / HW; int c = t % C; size_t n = t / C; dst[i] = src[(n * HW + p) * C + c]; }
   }
 }
+static inline int vec4_blocks(size_t n_vec) { size_t b = (n_vec + 1023) / 1024; if (b > 148 * 4) b = 148 * 4; if (b < 1) b = 1; return (int)b; }
 static inline int ew_blocks(size_t n, int per = 256) { size_t b = (n + per - 1) / per; if (b > 148 * 16) b = 148 * 16; if (b < 1) b = 1; return (int)b; }
 
 void k_nchw_f32_to_nhwc(int prec, const float* src, void* dst, int N, int C, int HW, cudaStream_t s) {
@@ -144,6 +146,7 @@ __global__ void __launch_bounds__(256) bn_stats_partial_bf16x8_kernel(const uint
   float acc[2][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
+#pragma unroll 4
   for (int r = r0 + ty; r < r1; r += TY) { float v[8]; unpack8(xg[(size_t)r * C8 + c8], v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) { acc[0][j] += v[j]; acc[1][j] = fmaf(v[j], v[j], acc[1][j]); } }
@@ -218,28 +221,37 @@ __global__ void bn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, int 
     stf(y, i, act_fwd(act, fmaf(gamma[c], v, beta[c]), alpha));
   }
 }
-// bf16, C % 8 == 0: 16-byte vectors
-__global__ void bn_apply_bf16x8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int rows, int C, int groups, const float* __restrict__ mean,
+// bf16, C % 8 == 0 and 256 % (C/8) == 0: 16-byte vectors.  The grid stride (gridDim.x * 256 vectors) is a multiple of C/8, so a thread always
+// meets the same 8 channels: their coefficients are loaded once per group instead of 4-6 scalar loads per element.
+__global__ void __launch_bounds__(256) bn_apply_bf16x8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int rows, int C, int groups, const float* __restrict__ mean,
                                        const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int act, float alpha) { pdl_prologue();
-  size_t per_group = (size_t)rows * C / 8, total = per_group * groups; int C8 = C / 8;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    int c0 = (i % C8) * 8; int g = i / per_group;
-    uint4 v = x[i]; __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+  const int C8 = C / 8; const size_t per_group = (size_t)rows * C8;
+  const size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  const int c0 = (int)(t0 % C8) * 8;
+  for (int g = 0; g < groups; ++g) {
+    float mu[8], is[8], ga[8], be[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float2 f = __bfloat1622float2(h[j]); int c = c0 + 2 * j;
-      f.x = act_fwd(act, fmaf(gamma[c], (f.x - mean[g * C + c]) * invstd[g * C + c], beta[c]), alpha);
-      f.y = act_fwd(act, fmaf(gamma[c + 1], (f.y - mean[g * C + c + 1]) * invstd[g * C + c + 1], beta[c + 1]), alpha);
-      h[j] = __floats2bfloat162_rn(f.x, f.y);
+    for (int j = 0; j < 8; ++j) { mu[j] = mean[g * C + c0 + j]; is[j] = invstd[g * C + c0 + j]; ga[j] = gamma[c0 + j]; be[j] = beta[c0 + j]; }
+    const uint4* xg = x + g * per_group; uint4* yg = y + g * per_group;
+    for (size_t i = t0; i < per_group; i += 4 * stride) {        // four independent 16-byte loads in flight per thread
+      uint4 xa[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) if (i + q * stride < per_group) xa[q] = xg[i + q * stride];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) if (i + q * stride < per_group) {
+        float v[8]; unpack8(xa[q], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = act_fwd(act, fmaf(ga[j], (v[j] - mu[j]) * is[j], be[j]), alpha);
+        yg[i + q * stride] = pack8(v);
+      }
     }
-    y[i] = v;
   }
 }
 void k_bn_apply(int prec, const void* x, void* y, int rows, int C, int groups, const float* mean, const float* invstd,
                 const float* gamma, const float* beta, int act, float alpha, cudaStream_t s) {
   size_t n = (size_t)rows * C * groups; if (!n) return;
-  if (prec == PREC_BF16 && C % 8 == 0) {
-    launch_pdl(bn_apply_bf16x8_kernel, dim3(ew_blocks(n / 8)), dim3(256), (size_t)(0), s, (const uint4*)x, (uint4*)y, rows, C, groups, mean, invstd, gamma, beta, act, alpha);
+  if (vec_ok(prec, C)) {
+    launch_pdl(bn_apply_bf16x8_kernel, dim3(vec4_blocks((size_t)rows * C / 8)), dim3(256), (size_t)(0), s, (const uint4*)x, (uint4*)y, rows, C, groups, mean, invstd, gamma, beta, act, alpha);
   } else {
     DISPATCH_PREC(prec, T, (launch_pdl(bn_apply_kernel<T>, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, (const T*)x, (T*)y, rows, C, groups, mean, invstd, gamma, beta, act, alpha)));
   }
@@ -274,6 +286,7 @@ __global__ void __launch_bounds__(256) bn_bwd_partial_bf16x8_kernel(const uint4*
   float mu[8], is[8], ga[8], be[8], acc[2][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { const int c = c8 * 8 + j; mu[j] = mean[g * C + c]; is[j] = invstd[g * C + c]; ga[j] = gamma[c]; be[j] = beta[c]; acc[0][j] = 0.f; acc[1][j] = 0.f; }
+#pragma unroll 4
   for (int r = r0 + ty; r < r1; r += TY) {
     float xv[8], ev[8]; unpack8(xg[(size_t)r * C8 + c8], xv); unpack8(eg[(size_t)r * C8 + c8], ev);
 #pragma unroll
@@ -282,17 +295,31 @@ __global__ void __launch_bounds__(256) bn_bwd_partial_bf16x8_kernel(const uint4*
   float* const dst[2] = {p1, p2};
   block_fold_write<2>(acc, C, C8, c8, ty, TY, dst, ((size_t)g * S + sl) * C);
 }
-__global__ void bn_bwd_apply_bf16x8_kernel(const uint4* __restrict__ x, const uint4* __restrict__ eo, uint4* __restrict__ ei, int rows, int C, int groups,
+__global__ void __launch_bounds__(256) bn_bwd_apply_bf16x8_kernel(const uint4* __restrict__ x, const uint4* __restrict__ eo, uint4* __restrict__ ei, int rows, int C, int groups,
                                            const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                                            const float* __restrict__ beta, int act, float alpha, const float* __restrict__ c1, const float* __restrict__ c2) { pdl_prologue();
-  const int C8 = C / 8; const size_t per_group = (size_t)rows * C8, total = per_group * groups;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % C8) * 8; const int g = (int)(i / per_group);
-    float xv[8], ev[8], o[8]; unpack8(x[i], xv); unpack8(eo[i], ev);
+  // same hoisting as bn_apply_bf16x8_kernel: one thread, one channel octet
+  const int C8 = C / 8; const size_t per_group = (size_t)rows * C8;
+  const size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  const int c0 = (int)(t0 % C8) * 8;
+  for (int g = 0; g < groups; ++g) {
+    float mu[8], is[8], ga[8], be[8], k1[8], k2[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { const int c = c0 + j, k = g * C + c; const float xh = (xv[j] - mean[k]) * invstd[k];
-      const float dy = ev[j] * act_grad_from_pre(act, fmaf(gamma[c], xh, beta[c]), alpha); o[j] = gamma[c] * invstd[k] * (dy - c1[k] - xh * c2[k]); }
-    ei[i] = pack8(o);
+    for (int j = 0; j < 8; ++j) { const int k = g * C + c0 + j; mu[j] = mean[k]; is[j] = invstd[k]; ga[j] = gamma[c0 + j]; be[j] = beta[c0 + j]; k1[j] = c1[k]; k2[j] = c2[k]; }
+    const uint4* xg = x + g * per_group; const uint4* eg = eo + g * per_group; uint4* ig = ei + g * per_group;
+    for (size_t i = t0; i < per_group; i += 4 * stride) {
+      uint4 xa[4], ea[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) if (i + q * stride < per_group) { xa[q] = xg[i + q * stride]; ea[q] = eg[i + q * stride]; }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) if (i + q * stride < per_group) {
+        float xv[8], ev[8], o[8]; unpack8(xa[q], xv); unpack8(ea[q], ev);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float xh = (xv[j] - mu[j]) * is[j];
+          const float dy = ev[j] * act_grad_from_pre(act, fmaf(ga[j], xh, be[j]), alpha); o[j] = ga[j] * is[j] * (dy - k1[j] - xh * k2[j]); }
+        ig[i + q * stride] = pack8(o);
+      }
+    }
   }
 }
 __global__ void __launch_bounds__(512) bn_bwd_final_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int rows, int C, int S, int groups,
@@ -347,7 +374,7 @@ void k_bn_bwd(int prec, const void* x, const void* eps_out, void* eps_in, int ro
   launch_pdl(bn_bwd_final_kernel, dim3((C + 31) / 32), dim3(512), (size_t)(0), s, p1, p2, rows, C, S, groups, c1, c2, g_gamma, g_beta, want); LAUNCHED();
   if (eps_in) {
     size_t n = (size_t)rows * C * groups;
-    if (vec) launch_pdl(bn_bwd_apply_bf16x8_kernel, dim3(ew_blocks(n / 8)), dim3(256), (size_t)(0), s, (const uint4*)x, (const uint4*)eps_out, (uint4*)eps_in, rows, C, groups, mean, invstd, gamma, beta, act, alpha, c1, c2);
+    if (vec) launch_pdl(bn_bwd_apply_bf16x8_kernel, dim3(vec4_blocks((size_t)rows * C / 8)), dim3(256), (size_t)(0), s, (const uint4*)x, (const uint4*)eps_out, (uint4*)eps_in, rows, C, groups, mean, invstd, gamma, beta, act, alpha, c1, c2);
     else DISPATCH_PREC(prec, T, (launch_pdl(bn_bwd_apply_kernel<T>, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, (const T*)x, (const T*)eps_out, (T*)eps_in, rows, C, groups, mean, invstd, gamma, beta, act, alpha, c1, c2)));
     LAUNCHED();
   }
@@ -581,8 +608,28 @@ __global__ void act_bwd_out_kernel(const T* __restrict__ a, const T* __restrict_
 void k_act_fwd(int prec, const void* x, void* y, size_t n, int act, float alpha, cudaStream_t s) {
   if (!n) return; DISPATCH_PREC(prec, T, (launch_pdl(act_fwd_kernel<T>, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, (const T*)x, (T*)y, n, act, alpha))); LAUNCHED();
 }
+// bf16, 16-byte vectors (n % 8 == 0): the D1 / G-last activation derivative runs over the largest tensors of the step
+__global__ void act_bwd_out_bf16x8_kernel(const uint4* __restrict__ a, const uint4* __restrict__ eo, uint4* __restrict__ ei, size_t n8, int act, float alpha) { pdl_prologue();
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += 4 * stride) {
+    uint4 aa[4], ea[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) if (i + q * stride < n8) { aa[q] = a[i + q * stride]; ea[q] = eo[i + q * stride]; }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) if (i + q * stride < n8) {
+      float av[8], ev[8], o[8]; unpack8(aa[q], av); unpack8(ea[q], ev);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = ev[j] * act_grad_from_out(act, av[j], alpha);
+      ei[i + q * stride] = pack8(o);
+    }
+  }
+}
 void k_act_bwd_from_output(int prec, const void* a, const void* eo, void* ei, size_t n, int act, float alpha, cudaStream_t s) {
-  if (!n) return; DISPATCH_PREC(prec, T, (launch_pdl(act_bwd_out_kernel<T>, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, (const T*)a, (const T*)eo, (T*)ei, n, act, alpha))); LAUNCHED();
+  if (!n) return;
+  if (prec == PREC_BF16 && n % 8 == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(eo) | reinterpret_cast<uintptr_t>(ei)) & 15) == 0) {
+    launch_pdl(act_bwd_out_bf16x8_kernel, dim3(vec4_blocks(n / 8)), dim3(256), (size_t)0, s, (const uint4*)a, (const uint4*)eo, (uint4*)ei, n / 8, act, alpha); LAUNCHED(); return;
+  }
+  DISPATCH_PREC(prec, T, (launch_pdl(act_bwd_out_kernel<T>, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, (const T*)a, (const T*)eo, (T*)ei, n, act, alpha))); LAUNCHED();
 }
 void k_sigmoid_out(int prec, const void* z, void* p, size_t n, cudaStream_t s) { k_act_fwd(prec, z, p, n, ACT_SIGMOID, 0.f, s); }
 
@@ -738,7 +785,41 @@ __global__ void __launch_bounds__(512) colsum_final_kernel(const float* __restri
   __syncthreads();
   if (ty == 0 && c < C) { for (int k = 1; k < 16; ++k) a += sa[k][tx]; out[c] = (accumulate ? out[c] : 0.f) + (float)a; }
 }
+// bf16, C <= 4 (the G-last bias gradient: 3 channels x every pixel of the batch), rows % 8 == 0: a thread walks groups of 8 pixels = C 16-byte
+// vectors (element k of a group belongs to channel k % C), block-folds its C sums and writes one partial row; <= 256 partial rows
+template <int C>
+__global__ void __launch_bounds__(256) colsum_small_c_kernel(const uint4* __restrict__ x, size_t groups8, float* __restrict__ p) { pdl_prologue();
+  float acc[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) acc[c] = 0.f;
+  for (size_t gidx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; gidx < groups8; gidx += (size_t)gridDim.x * blockDim.x) {
+    uint4 u[C];
+#pragma unroll
+    for (int q = 0; q < C; ++q) u[q] = x[gidx * C + q];
+#pragma unroll
+    for (int q = 0; q < C; ++q) { float v[8]; unpack8(u[q], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[(q * 8 + j) % C] += v[j]; }
+  }
+  __shared__ float red[8][C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) { float a = acc[c]; for (int m = 16; m; m >>= 1) a += __shfl_xor_sync(0xffffffffu, a, m); if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][c] = a; }
+  __syncthreads();
+  if (threadIdx.x < C) { float a = 0.f; for (int w = 0; w < 8; ++w) a += red[w][threadIdx.x]; p[(size_t)blockIdx.x * C + threadIdx.x] = a; }
+}
 void k_colsum(int prec, const void* x, int rows, int C, float* scratch, float* out, int accumulate, cudaStream_t s) {
+  if (prec == PREC_BF16 && C >= 1 && C <= 4 && rows % 8 == 0 && rows >= 4096 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const size_t groups8 = (size_t)rows / 8; int S = (int)std::min<size_t>(256, (groups8 + 255) / 256);
+    switch (C) {
+      case 1: launch_pdl(colsum_small_c_kernel<1>, dim3(S), dim3(256), (size_t)0, s, (const uint4*)x, groups8, scratch); break;
+      case 2: launch_pdl(colsum_small_c_kernel<2>, dim3(S), dim3(256), (size_t)0, s, (const uint4*)x, groups8, scratch); break;
+      case 3: launch_pdl(colsum_small_c_kernel<3>, dim3(S), dim3(256), (size_t)0, s, (const uint4*)x, groups8, scratch); break;
+      default: launch_pdl(colsum_small_c_kernel<4>, dim3(S), dim3(256), (size_t)0, s, (const uint4*)x, groups8, scratch); break;
+    }
+    LAUNCHED();
+    launch_pdl(colsum_final_kernel, dim3(1), dim3(512), (size_t)(0), s, scratch, C, S, out, accumulate); LAUNCHED();
+    return;
+  }
   const bool vec = vec_ok(prec, C);
   int S = vec ? vec_blocks(rows, C) : pick_slices(rows, C);
   if (vec) launch_pdl(colsum_partial_bf16x8_kernel, dim3(S), dim3(256), (size_t)(0), s, (const uint4*)x, rows, C, S, scratch);

@@ -802,36 +802,68 @@ int k_tc_deconv_ps(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat
 // (fence.proxy.async makes the generic-proxy writes visible to the tensor core), one thread issues the MMAs, and the 4 warps drain TMEM.
 // Many short CTAs per SM (31 KB smem, 64 TMEM columns each) overlap each other's load / transform / MMA / store phases.
 struct TcEdgeParams {
-  const __nv_bfloat16* x; const __nv_bfloat16* w; const __nv_bfloat16* dy; const float* bias; __nv_bfloat16* out; float* part;
+  const __nv_bfloat16* x; const __nv_bfloat16* w; const __nv_bfloat16* dy; const float* bias; __nv_bfloat16* out; float* part; float* part_b;
   int N, H, W, C, OH, OW, O, Ht, tiles_y, tiles_total, tiles_per_cta, act; float alpha;
 };
 static constexpr int EDGE_SLAB_BYTES = 6144;
 __device__ __forceinline__ uint32_t swz128(int row, int byte) { return (uint32_t)(row * 128 + ((((byte >> 4) ^ (row & 7)) << 4) | (byte & 15))); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// rows 2*oy0-1 .. 2*(oy0+Ht-1)+2 of image n -> slab (zero rows outside the image)
-__device__ __forceinline__ void edge_load_slab(const TcEdgeParams& p, int n, int oy0, uint8_t* slab) {
-  const int WC = p.W * p.C, cpr = WC >> 3, nrows = 2 * p.Ht + 2;
-  for (int i = threadIdx.x; i < nrows * cpr; i += blockDim.x) {
-    const int j = i / cpr, cc = i - j * cpr, iy = 2 * oy0 - 1 + j;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (iy >= 0 && iy < p.H) v = __ldg(reinterpret_cast<const uint4*>(p.x + ((size_t)n * p.H + iy) * WC) + cc);
-    reinterpret_cast<uint4*>(slab)[i] = v;
+// rows 2*oy0-1 .. 2*(oy0+Ht-1)+2 of image n (zero rows outside the image), <= 3 x 16 B per thread: fetched into registers one tile ahead so
+// that the global-memory latency overlaps the previous tile's transform / MMA / epilogue, then parked in the slab
+struct EdgeSlabRegs { uint4 v[3]; };
+__device__ __forceinline__ void edge_fetch_slab(const TcEdgeParams& p, int n, int oy0, EdgeSlabRegs& r) {
+  const int WC = p.W * p.C, cpr = WC >> 3, total = (2 * p.Ht + 2) * cpr;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const int i = threadIdx.x + q * 128; r.v[q] = make_uint4(0u, 0u, 0u, 0u);
+    if (i < total) { const int j = i / cpr, cc = i - j * cpr, iy = 2 * oy0 - 1 + j;
+      if (iy >= 0 && iy < p.H) r.v[q] = __ldg(reinterpret_cast<const uint4*>(p.x + ((size_t)n * p.H + iy) * WC) + cc); }
   }
 }
-// thread = output pixel (oy_l, ox) of the tile: k = (r*4 + s)*C + c  <-  slab row 2*oy_l + r, elements (2*ox-1)*C + s*C + c
-__device__ __forceinline__ void edge_build_row(const TcEdgeParams& p, const uint8_t* slab, uint8_t* tile, int row) {
-  const int WC = p.W * p.C, oy_l = row / p.OW, ox = row - oy_l * p.OW, e0 = (2 * ox - 1) * p.C, K = 16 * p.C;
-  const uint16_t* s16 = reinterpret_cast<const uint16_t*>(slab);
+__device__ __forceinline__ void edge_store_slab(const TcEdgeParams& p, const EdgeSlabRegs& r, uint8_t* slab) {
+  const int total = (2 * p.Ht + 2) * ((p.W * p.C) >> 3);
+#pragma unroll
+  for (int q = 0; q < 3; ++q) { const int i = threadIdx.x + q * 128; if (i < total) reinterpret_cast<uint4*>(slab)[i] = r.v[q]; }
+}
+// thread = output pixel (oy_l, ox) of the tile: k = (r*4 + s)*C + c  <-  slab row 2*oy_l + r, elements (2*ox-1)*C + s*C + c, i.e. 4*C contiguous
+// bf16 per filter row.  The window starts 2 bytes off a 32-bit boundary when C is odd: aligned 32-bit loads + a 16-bit funnel shift.  The
+// whole 128-byte row (zero padded past k = 16*C) is assembled in registers and written as eight conflict-free 16-byte swizzled stores.
+template <int C>
+__device__ __forceinline__ void edge_build_row_c(const TcEdgeParams& p, const uint8_t* slab, uint8_t* tile, int row, bool ones) {
+  const int WC = p.W * C, oy_l = row / p.OW, ox = row - oy_l * p.OW;
+  const int lo = ox == 0 ? C : 0, hi = ox == p.OW - 1 ? 3 * C : 4 * C;       // window elements outside [lo, hi) fall left / right of the image
+  uint32_t out[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) out[i] = 0u;
+#pragma unroll
   for (int r = 0; r < 4; ++r) {
-    const uint16_t* srow = s16 + (2 * oy_l + r) * WC;
-    for (int jp = 0; jp < 2 * p.C; ++jp) {
-      const int e = e0 + 2 * jp;
-      const uint32_t lo = (e >= 0 && e < WC) ? srow[e] : 0u, hi = (e + 1 >= 0 && e + 1 < WC) ? srow[e + 1] : 0u;
-      *reinterpret_cast<uint32_t*>(tile + swz128(row, (r * 4 * p.C + 2 * jp) * 2)) = lo | (hi << 16);
+    const int b0 = ((2 * oy_l + r) * WC + (2 * ox - 1) * C) * 2;
+    if (C & 1) {
+      const uint32_t* wp = reinterpret_cast<const uint32_t*>(slab + b0 - 2);
+      uint32_t w[2 * C + 1];
+#pragma unroll
+      for (int i = 0; i <= 2 * C; ++i) w[i] = wp[i];
+#pragma unroll
+      for (int i = 0; i < 2 * C; ++i) out[r * 2 * C + i] = __funnelshift_r(w[i], w[i + 1], 16);
+    } else {
+      const uint32_t* wp = reinterpret_cast<const uint32_t*>(slab + b0);
+#pragma unroll
+      for (int i = 0; i < 2 * C; ++i) out[r * 2 * C + i] = wp[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 2 * C; ++i) {
+      const uint32_t m = ((2 * i >= lo && 2 * i < hi) ? 0xFFFFu : 0u) | ((2 * i + 1 >= lo && 2 * i + 1 < hi) ? 0xFFFF0000u : 0u);
+      out[r * 2 * C + i] &= m;
     }
   }
-  for (int k = K; k < 64; k += 2) *reinterpret_cast<uint32_t*>(tile + swz128(row, k * 2)) = 0u;
+  if (C < 4 && ones) out[8 * C] = 0x3F80u;       // column 16*C = 1.0 (bf16): the weight-gradient MMA then also yields sum_pix dy[pix][o] = the bias gradient
+#pragma unroll
+  for (int cc = 0; cc < 8; ++cc) *reinterpret_cast<uint4*>(tile + row * 128 + ((cc ^ (row & 7)) << 4)) = make_uint4(out[4 * cc], out[4 * cc + 1], out[4 * cc + 2], out[4 * cc + 3]);
+}
+__device__ __forceinline__ void edge_build_row(const TcEdgeParams& p, const uint8_t* slab, uint8_t* tile, int row, bool ones = false) {
+  switch (p.C) { case 1: edge_build_row_c<1>(p, slab, tile, row, ones); break; case 2: edge_build_row_c<2>(p, slab, tile, row, ones); break;
+                 case 3: edge_build_row_c<3>(p, slab, tile, row, ones); break; default: edge_build_row_c<4>(p, slab, tile, row, ones); break; }
 }
 
 __global__ void __launch_bounds__(128) tc_edge_conv_kernel(const TcEdgeParams p) { pdl_prologue();
@@ -842,38 +874,48 @@ __global__ void __launch_bounds__(128) tc_edge_conv_kernel(const TcEdgeParams p)
   const uint32_t bar = smem_base + 24576 + EDGE_SLAB_BYTES;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + 24576 + EDGE_SLAB_BYTES + 8);
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int mt = blockIdx.x, nb0 = blockIdx.y * 64;
-  const int n = mt / p.tiles_y, oy0 = (mt % p.tiles_y) * p.Ht, K = 16 * p.C;
+  const int nb0 = blockIdx.y * 64, K = 16 * p.C;
+  const int t_beg = blockIdx.x * p.tiles_per_cta, t_end = min(p.tiles_total, t_beg + p.tiles_per_cta);
   if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
   if (warp == 0) { tmem_alloc(smem_u32((const void*)tmem_slot), 64); tmem_relinquish(); }
-  edge_load_slab(p, n, oy0, slab);
-  for (int i = tid; i < 64 * 32; i += 128) {          // weight tile [64 o][64 k] K-major: row o = 16*C contiguous bf16 of the shadow, zero padded
-    const int o = i >> 5, kp = i & 31;
-    const uint32_t v = (2 * kp < K) ? *reinterpret_cast<const uint32_t*>(p.w + (size_t)(nb0 + o) * K + 2 * kp) : 0u;
-    *reinterpret_cast<uint32_t*>(sB + swz128(o, kp * 4)) = v;
+  EdgeSlabRegs pre;
+  if (t_beg < t_end) edge_fetch_slab(p, t_beg / p.tiles_y, (t_beg % p.tiles_y) * p.Ht, pre);
+  {   // weight tile [64 o][64 k] K-major, once per CTA: row o = 16*C contiguous bf16 of the shadow = 2*C 16-byte chunks, zero padded to 8
+    uint4 wv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const int i = tid + q * 128, o = i >> 3, cc = i & 7;
+      wv[q] = cc < 2 * p.C ? __ldg(reinterpret_cast<const uint4*>(p.w + (size_t)(nb0 + o) * K) + cc) : make_uint4(0u, 0u, 0u, 0u); }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const int i = tid + q * 128, o = i >> 3, cc = i & 7; *reinterpret_cast<uint4*>(sB + o * 128 + ((cc ^ (o & 7)) << 4)) = wv[q]; }
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  edge_build_row(p, slab, sA, tid);
-  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (tid == 0) {
-    constexpr uint32_t idesc = make_idesc(128, 64, 0, 0);
-    const uint64_t adesc = desc_kmajor_sw128(smem_base), bdesc = desc_kmajor_sw128(smem_base + 16384);
+  const int oy_l = tid / p.OW, ox = tid - oy_l * p.OW;
+  const bool has_bias = p.bias != nullptr;
+  uint32_t ph = 0;
+  for (int t = t_beg; t < t_end; ++t) {
+    const int n = t / p.tiles_y, oy0 = (t % p.tiles_y) * p.Ht;
+    edge_store_slab(p, pre, slab);
+    tc_fence_before();          // the previous tile's tcgen05.ld (epilogue) precede the next MMA
+    __syncthreads();
+    if (t + 1 < t_end) edge_fetch_slab(p, (t + 1) / p.tiles_y, ((t + 1) % p.tiles_y) * p.Ht, pre);
+    edge_build_row(p, slab, sA, tid);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+      constexpr uint32_t idesc = make_idesc(128, 64, 0, 0);
+      const uint64_t adesc = desc_kmajor_sw128(smem_base), bdesc = desc_kmajor_sw128(smem_base + 16384);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, k != 0);
-    umma_commit(bar);
-  }
-  mbar_wait(bar, 0);
-  tc_fence_after();
-  {
-    const int oy_l = tid / p.OW, ox = tid - oy_l * p.OW;
+      for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, k != 0);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, ph); ph ^= 1u;
+    tc_fence_after();
     __nv_bfloat16* orow = p.out + (((size_t)n * p.OH + oy0 + oy_l) * p.OW + ox) * p.O + nb0;
-    const bool has_bias = p.bias != nullptr;
 #pragma unroll 1
     for (int c0 = 0; c0 < 64; c0 += 32) {
       uint32_t v[32];
@@ -922,14 +964,22 @@ __global__ void __launch_bounds__(128) tc_edge_wgrad_kernel(const TcEdgeParams p
   const uint32_t tmem_base = *tmem_slot;
   const int t_beg = blockIdx.x * p.tiles_per_cta, t_end = min(p.tiles_total, t_beg + p.tiles_per_cta);
   uint32_t ph = 0;
-  for (int t = t_beg; t < t_end; ++t) {
+  EdgeSlabRegs pre; uint4 dyr[8];
+  auto fetch = [&](int t) {
     const int n = t / p.tiles_y, oy0 = (t % p.tiles_y) * p.Ht;
-    edge_load_slab(p, n, oy0, slab);
+    edge_fetch_slab(p, n, oy0, pre);
     const uint4* dyt = reinterpret_cast<const uint4*>(p.dy + (((size_t)n * p.OH + oy0) * p.OW) * 64);     // the tile's 128 pixels are contiguous: 16 KB
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { const int idx = tid + i * 128, r = idx >> 3, cc = idx & 7; *reinterpret_cast<uint4*>(sDy + r * 128 + ((cc ^ (r & 7)) << 4)) = __ldg(dyt + idx); }
+    for (int i = 0; i < 8; ++i) dyr[i] = __ldg(dyt + tid + i * 128);
+  };
+  if (t_beg < t_end) fetch(t_beg);
+  for (int t = t_beg; t < t_end; ++t) {
+    edge_store_slab(p, pre, slab);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const int idx = tid + i * 128, r = idx >> 3, cc = idx & 7; *reinterpret_cast<uint4*>(sDy + r * 128 + ((cc ^ (r & 7)) << 4)) = dyr[i]; }
     __syncthreads();
-    edge_build_row(p, slab, sX, tid);
+    if (t + 1 < t_end) fetch(t + 1);      // next tile's global loads fly during this tile's transform + MMAs
+    edge_build_row(p, slab, sX, tid, p.part_b != nullptr);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -954,9 +1004,16 @@ __global__ void __launch_bounds__(128) tc_edge_wgrad_kernel(const TcEdgeParams p
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 8; ++j) if (c0 + 4 * j < K) *reinterpret_cast<float4*>(orow + c0 + 4 * j) = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        if (p.part_b && K >= c0 && K < c0 + 32) {
+          float bsum = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (c0 + j == K) bsum = __uint_as_float(v[j]);
+          p.part_b[(size_t)blockIdx.x * 64 + tid] = bsum;
+        }
       }
     } else {
       for (int k = 0; k < K; ++k) orow[k] = 0.f;
+      if (p.part_b) p.part_b[(size_t)blockIdx.x * 64 + tid] = 0.f;
     }
   }
   tc_fence_before();
@@ -979,7 +1036,7 @@ static int tc_edge_wgrad_ctas(const ConvGeom& g, int* tpc) {
   const int per = (tiles + target - 1) / target; *tpc = per < 1 ? 1 : per;
   return (tiles + *tpc - 1) / *tpc;
 }
-size_t k_tc_edge_wgrad_scratch_floats(const ConvGeom& g) { return tc_edge_wgrad_supported(g) ? (size_t)tc_edge_wgrad_target() * 64 * 16 * g.C : 0; }
+size_t k_tc_edge_wgrad_scratch_floats(const ConvGeom& g) { return tc_edge_wgrad_supported(g) ? (size_t)tc_edge_wgrad_target() * (64 * 16 * g.C + 64) : 0; }
 int k_tc_edge_conv(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out, int act, float alpha, cudaStream_t s) {
   TcEdgeParams p{}; if (!edge_tile(g, &p.Ht) || g.O % 64) return -1;
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 3) || (reinterpret_cast<uintptr_t>(out) & 15)) return -1;
@@ -988,17 +1045,20 @@ int k_tc_edge_conv(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat1
   const size_t smem = 1024 + 24576 + EDGE_SLAB_BYTES + 64;
   static bool attr_set = false;
   if (!attr_set) { if (cudaFuncSetAttribute(tc_edge_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2; attr_set = true; }
-  launch_pdl(tc_edge_conv_kernel, dim3((unsigned)p.tiles_total, (unsigned)(g.O / 64)), dim3(128), smem, s, p);
+  static int target = -1; if (target < 0) { const char* e = getenv("B2G_EDGE_CONV_CTAS"); target = e ? atoi(e) : 592; if (target < 1) target = 592; }
+  p.tiles_per_cta = (p.tiles_total + target - 1) / target;
+  launch_pdl(tc_edge_conv_kernel, dim3((unsigned)((p.tiles_total + p.tiles_per_cta - 1) / p.tiles_per_cta), (unsigned)(g.O / 64)), dim3(128), smem, s, p);
   LAUNCHED();
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
 }
-int k_tc_edge_wgrad(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* scratch, size_t scratch_floats, int accumulate, cudaStream_t s) {
+int k_tc_edge_wgrad(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* db, float* scratch, size_t scratch_floats, int accumulate, cudaStream_t s) {
   TcEdgeParams p{}; if (!edge_tile(g, &p.Ht) || g.O != 64) return -1;
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(dy) & 15)) return -1;
   p.x = x; p.dy = dy; p.part = scratch; p.N = g.N; p.H = g.H; p.W = g.W; p.C = g.C; p.OH = g.OH; p.OW = g.OW; p.O = g.O; p.tiles_y = g.OH / p.Ht;
   p.tiles_total = g.N * p.tiles_y;
   const int ctas = tc_edge_wgrad_ctas(g, &p.tiles_per_cta); const size_t n = (size_t)64 * 16 * g.C;
-  if ((size_t)ctas * n > scratch_floats) return -5;
+  if ((size_t)ctas * (n + 64) > scratch_floats) return -5;
+  if (db && g.C < 4) p.part_b = scratch + (size_t)ctas * n;
   const size_t smem = 1024 + 32768 + EDGE_SLAB_BYTES + 64;
   static bool attr_set = false;
   if (!attr_set) { if (cudaFuncSetAttribute(tc_edge_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2; attr_set = true; }
@@ -1006,7 +1066,8 @@ int k_tc_edge_wgrad(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat
   LAUNCHED();
   if (cudaPeekAtLastError() != cudaSuccess) return -3;
   k_reduce_splits(scratch, dw, n, ctas, n, accumulate, s);
-  return 0;
+  if (p.part_b) k_reduce_splits(p.part_b, db, 64, ctas, 64, accumulate, s);
+  return p.part_b ? 1 : 0;      // 1: the bias gradient (column sums of dy) was produced as well
 }
 
 // ------------------------------------------------------------------ wgrad: MN-major operands --------------

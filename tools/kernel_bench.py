@@ -10,7 +10,9 @@ import numpy as np
 
 import gan_deeplearning4j_b200 as b
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+edge_only = "--edge-only" in sys.argv
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+n = int(args[0]) if args else 128
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1590.0
 ctx = b.Context(0)
 rng = np.random.default_rng(0)
@@ -39,7 +41,7 @@ for name, kind, bt in edge:
             t.append(float("nan"))
     edge_rows.append((name, 2.0 * bt * (h // 2) * (w // 2) * o * 16 * c / 1e9, (nx + ny) * 2 / 1e6, t[0], t[1]))
 rows = []
-for name, kind, bt, h, w, c, o in shapes:
+for name, kind, bt, h, w, c, o in ([] if edge_only else shapes):
     g = dict(n=bt, h=h, w=w, c=c, oh=h // 2, ow=w // 2, o=o, kh=4, kw=4, sh=2, sw=2, ph=1, pw=1)
     nx, ny, nw = bt * h * w * c, bt * (h // 2) * (w // 2) * o, o * 16 * c
     a = rng.standard_normal(ny if kind == 1 else nx, dtype=np.float32)
@@ -54,7 +56,7 @@ for name, kind, bt, h, w, c, o in shapes:
 print(f"| kernel (batch N={n}) | GFLOP | us | TFLOP/s | of measured peak ({peak:.0f}) |\n|---|---|---|---|---|")
 for r in rows:
     print(f"| {r[0]} | {r[1]:.2f} | {r[2]:.1f} | {r[3]:.0f} | {r[4]:.2f} |")
-tot_f = sum(r[1] for r in rows); tot_t = sum(r[2] for r in rows if r[2] == r[2])
+tot_f = sum(r[1] for r in rows); tot_t = sum(r[2] for r in rows if r[2] == r[2]) or 1.0
 print(f"| all | {tot_f:.1f} | {tot_t:.0f} | {tot_f / tot_t * 1e3:.0f} | {tot_f / tot_t * 1e3 / peak:.2f} |")
 print(f"\n| skinny layer (batch N={n}) | GFLOP | activation MB | SIMT us | tcgen05 us |\n|---|---|---|---|---|")
 for r in edge_rows:
