@@ -273,6 +273,7 @@ __global__ void __launch_bounds__(128) dense_small_k_dgrad_kernel(const T* __res
   constexpr int OC = 16;                                  // o per chunk
   __shared__ __align__(16) float sz[16][128];            // [n][o], zero padded to a multiple of OC
   const int cb = blockIdx.x * 256, c = cb + threadIdx.x * 2, n0 = blockIdx.y * 16, OP = (O + OC - 1) / OC * OC;
+#pragma unroll 8
   for (int i = threadIdx.x; i < 16 * OP; i += 128) { const int r = i / OP, o = i - r * OP; sz[r][o] = (o < O && n0 + r < N) ? ldf(dy, (size_t)(n0 + r) * O + o) : 0.f; }
   float acc[16][2];
 #pragma unroll

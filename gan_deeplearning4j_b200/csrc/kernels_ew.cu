@@ -44,6 +44,14 @@ __global__ void permute_kernel(const T* __restrict__ src, T* __restrict__ dst, i
     else         { int p = i % HW; size_t t = i / HW; int c = t % C; size_t n = t / C; dst[i] = src[(n * HW + p) * C + c]; }
   }
 }
+// activation resolved at compile time for the common cases (the per-element switch costs more than the arithmetic in these kernels)
+#define DISPATCH_ACT(act, ACTC, ...)                                                            \
+  switch (act) {                                                                                \
+    case ACT_IDENTITY: { constexpr int ACTC = ACT_IDENTITY; __VA_ARGS__; } break;               \
+    case ACT_RELU: { constexpr int ACTC = ACT_RELU; __VA_ARGS__; } break;                       \
+    case ACT_LRELU: { constexpr int ACTC = ACT_LRELU; __VA_ARGS__; } break;                     \
+    default: { constexpr int ACTC = -1; __VA_ARGS__; } break;                                   \
+  }
 static inline int vec4_blocks(size_t n_vec) { size_t b = (n_vec + 1023) / 1024; if (b > 148 * 4) b = 148 * 4; if (b < 1) b = 1; return (int)b; }
 static inline int ew_blocks(size_t n, int per = 256) { size_t b = (n + per - 1) / per; if (b > 148 * 16) b = 148 * 16; if (b < 1) b = 1; return (int)b; }
 
@@ -223,7 +231,8 @@ __global__ void bn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, int 
 }
 // bf16, C % 8 == 0 and 256 % (C/8) == 0: 16-byte vectors.  The grid stride (gridDim.x * 256 vectors) is a multiple of C/8, so a thread always
 // meets the same 8 channels: their coefficients are loaded once per group instead of 4-6 scalar loads per element.
-__global__ void __launch_bounds__(256) bn_apply_bf16x8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int rows, int C, int groups, const float* __restrict__ mean,
+template <int ACTC>
+__global__ void __launch_bounds__(256, 3) bn_apply_bf16x8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int rows, int C, int groups, const float* __restrict__ mean,
                                        const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int act, float alpha) { pdl_prologue();
   const int C8 = C / 8; const size_t per_group = (size_t)rows * C8;
   const size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
@@ -241,7 +250,7 @@ __global__ void __launch_bounds__(256) bn_apply_bf16x8_kernel(const uint4* __res
       for (int q = 0; q < 4; ++q) if (i + q * stride < per_group) {
         float v[8]; unpack8(xa[q], v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = act_fwd(act, fmaf(ga[j], (v[j] - mu[j]) * is[j], be[j]), alpha);
+        for (int j = 0; j < 8; ++j) v[j] = act_fwd(ACTC < 0 ? act : ACTC, fmaf(ga[j], (v[j] - mu[j]) * is[j], be[j]), alpha);
         yg[i + q * stride] = pack8(v);
       }
     }
@@ -251,7 +260,7 @@ void k_bn_apply(int prec, const void* x, void* y, int rows, int C, int groups, c
                 const float* gamma, const float* beta, int act, float alpha, cudaStream_t s) {
   size_t n = (size_t)rows * C * groups; if (!n) return;
   if (vec_ok(prec, C)) {
-    launch_pdl(bn_apply_bf16x8_kernel, dim3(vec4_blocks((size_t)rows * C / 8)), dim3(256), (size_t)(0), s, (const uint4*)x, (uint4*)y, rows, C, groups, mean, invstd, gamma, beta, act, alpha);
+    DISPATCH_ACT(act, ACTC, launch_pdl(bn_apply_bf16x8_kernel<ACTC>, dim3(vec4_blocks((size_t)rows * C / 8)), dim3(256), (size_t)(0), s, (const uint4*)x, (uint4*)y, rows, C, groups, mean, invstd, gamma, beta, act, alpha));
   } else {
     DISPATCH_PREC(prec, T, (launch_pdl(bn_apply_kernel<T>, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, (const T*)x, (T*)y, rows, C, groups, mean, invstd, gamma, beta, act, alpha)));
   }
@@ -277,7 +286,8 @@ __global__ void bn_bwd_partial_kernel(const T* __restrict__ x, const T* __restri
   }
   p1[((size_t)g * S + sl) * C + c] = a; p2[((size_t)g * S + sl) * C + c] = b;
 }
-__global__ void __launch_bounds__(256) bn_bwd_partial_bf16x8_kernel(const uint4* __restrict__ x, const uint4* __restrict__ eo, int rows, int C, int S, const float* __restrict__ mean,
+template <int ACTC>
+__global__ void __launch_bounds__(256, 3) bn_bwd_partial_bf16x8_kernel(const uint4* __restrict__ x, const uint4* __restrict__ eo, int rows, int C, int S, const float* __restrict__ mean,
                                              const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int act, float alpha,
                                              float* __restrict__ p1, float* __restrict__ p2) { pdl_prologue();
   const int g = blockIdx.y, C8 = C / 8, TY = 256 / C8, c8 = threadIdx.x % C8, ty = threadIdx.x / C8, sl = blockIdx.x;
@@ -290,12 +300,13 @@ __global__ void __launch_bounds__(256) bn_bwd_partial_bf16x8_kernel(const uint4*
   for (int r = r0 + ty; r < r1; r += TY) {
     float xv[8], ev[8]; unpack8(xg[(size_t)r * C8 + c8], xv); unpack8(eg[(size_t)r * C8 + c8], ev);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { const float xh = (xv[j] - mu[j]) * is[j]; const float dy = ev[j] * act_grad_from_pre(act, fmaf(ga[j], xh, be[j]), alpha); acc[0][j] += dy; acc[1][j] = fmaf(dy, xh, acc[1][j]); }
+    for (int j = 0; j < 8; ++j) { const float xh = (xv[j] - mu[j]) * is[j]; const float dy = ev[j] * act_grad_from_pre(ACTC < 0 ? act : ACTC, fmaf(ga[j], xh, be[j]), alpha); acc[0][j] += dy; acc[1][j] = fmaf(dy, xh, acc[1][j]); }
   }
   float* const dst[2] = {p1, p2};
   block_fold_write<2>(acc, C, C8, c8, ty, TY, dst, ((size_t)g * S + sl) * C);
 }
-__global__ void __launch_bounds__(256) bn_bwd_apply_bf16x8_kernel(const uint4* __restrict__ x, const uint4* __restrict__ eo, uint4* __restrict__ ei, int rows, int C, int groups,
+template <int ACTC>
+__global__ void __launch_bounds__(256, 2) bn_bwd_apply_bf16x8_kernel(const uint4* __restrict__ x, const uint4* __restrict__ eo, uint4* __restrict__ ei, int rows, int C, int groups,
                                            const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                                            const float* __restrict__ beta, int act, float alpha, const float* __restrict__ c1, const float* __restrict__ c2) { pdl_prologue();
   // same hoisting as bn_apply_bf16x8_kernel: one thread, one channel octet
@@ -316,7 +327,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_bf16x8_kernel(const uint4* _
         float xv[8], ev[8], o[8]; unpack8(xa[q], xv); unpack8(ea[q], ev);
 #pragma unroll
         for (int j = 0; j < 8; ++j) { const float xh = (xv[j] - mu[j]) * is[j];
-          const float dy = ev[j] * act_grad_from_pre(act, fmaf(ga[j], xh, be[j]), alpha); o[j] = ga[j] * is[j] * (dy - k1[j] - xh * k2[j]); }
+          const float dy = ev[j] * act_grad_from_pre(ACTC < 0 ? act : ACTC, fmaf(ga[j], xh, be[j]), alpha); o[j] = ga[j] * is[j] * (dy - k1[j] - xh * k2[j]); }
         ig[i + q * stride] = pack8(o);
       }
     }
@@ -365,7 +376,7 @@ void k_bn_bwd(int prec, const void* x, const void* eps_out, void* eps_in, int ro
   int S = vec ? vec_blocks(rows, C) : pick_slices(rows, C);
   float* p1 = scratch; float* p2 = p1 + (size_t)groups * S * C; float* c1 = p2 + (size_t)groups * S * C; float* c2 = c1 + (size_t)groups * C;
   if (vec) {
-    launch_pdl(bn_bwd_partial_bf16x8_kernel, dim3(dim3(S, groups)), dim3(256), (size_t)(0), s, (const uint4*)x, (const uint4*)eps_out, rows, C, S, mean, invstd, gamma, beta, act, alpha, p1, p2);
+    DISPATCH_ACT(act, ACTC, launch_pdl(bn_bwd_partial_bf16x8_kernel<ACTC>, dim3(dim3(S, groups)), dim3(256), (size_t)(0), s, (const uint4*)x, (const uint4*)eps_out, rows, C, S, mean, invstd, gamma, beta, act, alpha, p1, p2));
   } else {
     dim3 grid((S * C + 255) / 256, groups);
     DISPATCH_PREC(prec, T, (launch_pdl(bn_bwd_partial_kernel<T>, dim3(grid), dim3(256), (size_t)(0), s, (const T*)x, (const T*)eps_out, rows, C, S, mean, invstd, gamma, beta, act, alpha, p1, p2)));
@@ -374,7 +385,7 @@ void k_bn_bwd(int prec, const void* x, const void* eps_out, void* eps_in, int ro
   launch_pdl(bn_bwd_final_kernel, dim3((C + 31) / 32), dim3(512), (size_t)(0), s, p1, p2, rows, C, S, groups, c1, c2, g_gamma, g_beta, want); LAUNCHED();
   if (eps_in) {
     size_t n = (size_t)rows * C * groups;
-    if (vec) launch_pdl(bn_bwd_apply_bf16x8_kernel, dim3(vec4_blocks((size_t)rows * C / 8)), dim3(256), (size_t)(0), s, (const uint4*)x, (const uint4*)eps_out, (uint4*)eps_in, rows, C, groups, mean, invstd, gamma, beta, act, alpha, c1, c2);
+    if (vec) { DISPATCH_ACT(act, ACTC, launch_pdl(bn_bwd_apply_bf16x8_kernel<ACTC>, dim3(vec4_blocks((size_t)rows * C / 8)), dim3(256), (size_t)(0), s, (const uint4*)x, (const uint4*)eps_out, (uint4*)eps_in, rows, C, groups, mean, invstd, gamma, beta, act, alpha, c1, c2)); }
     else DISPATCH_PREC(prec, T, (launch_pdl(bn_bwd_apply_kernel<T>, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, (const T*)x, (const T*)eps_out, (T*)eps_in, rows, C, groups, mean, invstd, gamma, beta, act, alpha, c1, c2)));
     LAUNCHED();
   }
@@ -609,7 +620,8 @@ void k_act_fwd(int prec, const void* x, void* y, size_t n, int act, float alpha,
   if (!n) return; DISPATCH_PREC(prec, T, (launch_pdl(act_fwd_kernel<T>, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, (const T*)x, (T*)y, n, act, alpha))); LAUNCHED();
 }
 // bf16, 16-byte vectors (n % 8 == 0): the D1 / G-last activation derivative runs over the largest tensors of the step
-__global__ void act_bwd_out_bf16x8_kernel(const uint4* __restrict__ a, const uint4* __restrict__ eo, uint4* __restrict__ ei, size_t n8, int act, float alpha) { pdl_prologue();
+template <int ACTC>
+__global__ void __launch_bounds__(256, 4) act_bwd_out_bf16x8_kernel(const uint4* __restrict__ a, const uint4* __restrict__ eo, uint4* __restrict__ ei, size_t n8, int act, float alpha) { pdl_prologue();
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += 4 * stride) {
     uint4 aa[4], ea[4];
@@ -619,7 +631,7 @@ __global__ void act_bwd_out_bf16x8_kernel(const uint4* __restrict__ a, const uin
     for (int q = 0; q < 4; ++q) if (i + q * stride < n8) {
       float av[8], ev[8], o[8]; unpack8(aa[q], av); unpack8(ea[q], ev);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = ev[j] * act_grad_from_out(act, av[j], alpha);
+      for (int j = 0; j < 8; ++j) o[j] = ev[j] * act_grad_from_out(ACTC < 0 ? act : ACTC, av[j], alpha);
       ei[i + q * stride] = pack8(o);
     }
   }
@@ -627,7 +639,7 @@ __global__ void act_bwd_out_bf16x8_kernel(const uint4* __restrict__ a, const uin
 void k_act_bwd_from_output(int prec, const void* a, const void* eo, void* ei, size_t n, int act, float alpha, cudaStream_t s) {
   if (!n) return;
   if (prec == PREC_BF16 && n % 8 == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(eo) | reinterpret_cast<uintptr_t>(ei)) & 15) == 0) {
-    launch_pdl(act_bwd_out_bf16x8_kernel, dim3(vec4_blocks(n / 8)), dim3(256), (size_t)0, s, (const uint4*)a, (const uint4*)eo, (uint4*)ei, n / 8, act, alpha); LAUNCHED(); return;
+    DISPATCH_ACT(act, ACTC, launch_pdl(act_bwd_out_bf16x8_kernel<ACTC>, dim3(vec4_blocks(n / 8)), dim3(256), (size_t)0, s, (const uint4*)a, (const uint4*)eo, (uint4*)ei, n / 8, act, alpha)); LAUNCHED(); return;
   }
   DISPATCH_PREC(prec, T, (launch_pdl(act_bwd_out_kernel<T>, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, (const T*)a, (const T*)eo, (T*)ei, n, act, alpha))); LAUNCHED();
 }
