@@ -109,6 +109,8 @@ struct b2g_net {
   void *epsA = nullptr, *epsB = nullptr, *epsC = nullptr; size_t eps_elems = 0;
   float* scratch2 = nullptr;           // split-K / colsum partials of the side stream
   std::vector<cudaEvent_t> ev_fork, ev_done; cudaEvent_t ev_join = nullptr;
+  cudaEvent_t ev_shadow = nullptr; bool shadow_pending = false;   // transposed / packed bf16 weight copies being refreshed on the side stream
+  bool fwd_reads_wt = false;                                       // some layer's FORWARD reads a transposed / packed copy (transposed convs)
   float* scratch = nullptr; size_t scratch_floats = 0;
   float* loss_dev = nullptr;           // [8]
   unsigned* barrier_dev = nullptr;     // grid-barrier counter of the cooperative BN kernels
@@ -266,7 +268,8 @@ static int32_t net_alloc(b2g_net* n) {
   n->scratch_floats = scratch; B2(dalloc(n, &n->scratch, sizeof(float) * scratch)); B2(dalloc(n, &n->scratch2, sizeof(float) * scratch));
   n->ev_fork.resize(n->L.size()); n->ev_done.resize(n->L.size());
   for (size_t i = 0; i < n->L.size(); ++i) { CU(cudaEventCreateWithFlags(&n->ev_fork[i], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&n->ev_done[i], cudaEventDisableTiming)); }
-  CU(cudaEventCreateWithFlags(&n->ev_join, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&n->ev_join, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&n->ev_shadow, cudaEventDisableTiming));
+  for (auto& l : n->L) if (l.d.type == B2G_LAYER_DECONV2D && (l.needs_wt || l.off_Wps_bf >= 0)) n->fwd_reads_wt = true;
   n->stage_floats = std::max((size_t)R * max_act, std::max((size_t)n->n_params, max_w)); B2(dalloc(n, &n->stage_f32, sizeof(float) * n->stage_floats));
   return 0;
 }
@@ -326,15 +329,19 @@ static int32_t net_init_params_and_updater(b2g_net* n) {
 
 // bf16 operand copies of every GEMM weight (straight, and transposed where a tcgen05 dgrad reads it); no-op in FP32 mode.
 // After an updater pass the straight copy has already been written by the updater kernel itself.
-static void net_refresh_shadow(b2g_net* n, int only_layer = -1, bool straight_done = false) {
+static void net_refresh_shadow(b2g_net* n, int only_layer = -1, bool straight_done = false, cudaStream_t st = nullptr) {
   if (n->prec != PREC_BF16) return;
+  if (!st) st = n->ctx->stream;
+  if (n->shadow_pending && st == n->ctx->stream) { cudaStreamWaitEvent(st, n->ev_shadow, 0); n->shadow_pending = false; }     // never two refreshes in flight
   for (size_t i = 0; i < n->L.size(); ++i) { auto& l = n->L[i];
     if (!l.has_gemm() || (only_layer >= 0 && (int)i != only_layer)) continue;
-    if (l.off_Wps_bf >= 0) k_pack_deconv_ps(n->params + l.off_W, n->shadow + l.off_Wps_bf, l.geom.O, l.geom.C, n->ctx->stream);
+    if (l.off_Wps_bf >= 0) k_pack_deconv_ps(n->params + l.off_W, n->shadow + l.off_Wps_bf, l.geom.O, l.geom.C, st);
     if (straight_done && !l.needs_wt) continue;
-    k_weight_shadow(n->params + l.off_W, straight_done ? nullptr : n->shadow + l.off_W_bf, l.needs_wt ? n->shadow + l.off_Wt_bf : nullptr, l.wA, l.wTaps, l.wB, n->ctx->stream);
+    k_weight_shadow(n->params + l.off_W, straight_done ? nullptr : n->shadow + l.off_W_bf, l.needs_wt ? n->shadow + l.off_Wt_bf : nullptr, l.wA, l.wTaps, l.wB, st);
   }
 }
+// consumers of the transposed / packed copies order themselves after a refresh that is still running on the side stream
+static inline void wait_shadow(b2g_net* n, cudaStream_t consumer) { if (n->shadow_pending) { cudaStreamWaitEvent(consumer, n->ev_shadow, 0); n->shadow_pending = false; } }
 
 // ------------------------------------------------------------------ forward / backward -------------------
 struct FwdOpts { int rows; int groups; bool train; bool update_running; void* out_override; };
@@ -403,6 +410,7 @@ static int32_t gemm_wgrad(b2g_net* n, const LayerRT& l, const ConvGeom& g, const
 // Runs layers [0, L) on `in` (T NHWC, rows examples). Returns pointer to the final activations.
 static int32_t net_forward(b2g_net* n, const void* in, const FwdOpts& o, const void** result) {
   cudaStream_t s = fstream(n);
+  if (n->fwd_reads_wt) wait_shadow(n, s);
   if (o.rows > n->max_rows || o.rows < 1) return fail(B2G_ERR_SHAPE, "batch %d outside [1, max_batch=%d]", o.rows, n->max_rows);
   if (o.groups < 1 || o.rows % o.groups) return fail(B2G_ERR_SHAPE, "batch %d not divisible into %d groups", o.rows, o.groups);
   const int R = o.rows; const void* cur = in;
@@ -460,6 +468,7 @@ static int32_t net_forward(b2g_net* n, const void* in, const FwdOpts& o, const v
 // `eps` must live in n->epsA or be an external buffer; uses epsA/epsB ping-pong.
 static int32_t net_backward(b2g_net* n, const void* net_in, void* eps, int rows, int groups, bool want_wgrad, bool need_input_grad) {
   cudaStream_t s = n->ctx->stream, s2 = n->ctx->side; const int R = rows;
+  wait_shadow(n, s);
   void* cur = eps;
   // Three epsilon buffers in rotation.  Weight gradients are forked to the side stream (they only READ delta and the layer
   // input), so the input-gradient chain -- the critical path -- never waits for them; a buffer still being read by a
@@ -539,13 +548,20 @@ static int32_t net_allreduce_grads(b2g_net* n) {
   NC(g_nccl.ar(n->grads, n->grads, (size_t)n->n_params, /*ncclFloat32*/ 7, /*ncclSum*/ 0, c->comm, c->stream));
   return 0;
 }
-static int32_t net_update(b2g_net* n, int mb_local) {
+static int32_t net_update(b2g_net* n, int mb_local, bool async_shadow = false) {
   cudaStream_t s = n->ctx->stream; int W = n->ctx->comm ? n->ctx->world : 1;
   // BN running-stat pseudo-gradients are exempt from the minibatch division; under DP they are averaged over ranks
   if (!n->grad_allreduce) W = 1;     // parameter-averaging mode: purely local update
   k_updater(n->params, n->grads, n->st0, n->st1, n->segs_dev, n->chunk_seg_dev, n->chunk_off_dev, n->nchunks, 1.0f / ((float)mb_local * W), 1.0f / (float)W, n->step_dev, n->shadow, s);
   k_inc_int(n->step_dev, s);
-  net_refresh_shadow(n, -1, true);
+  if (async_shadow && n->prec == PREC_BF16) {
+    // the straight copies were written by the updater itself; the transposed / packed ones are first needed by the next backward pass
+    // (or, for a net with transposed convs, its next forward): refresh them beside whatever the main stream does until then
+    cudaStream_t s2 = n->ctx->side;
+    cudaEventRecord(n->ev_fork[0], s); cudaStreamWaitEvent(s2, n->ev_fork[0], 0);
+    net_refresh_shadow(n, -1, true, s2);
+    cudaEventRecord(n->ev_shadow, s2); n->shadow_pending = true;
+  } else net_refresh_shadow(n, -1, true);
   CHECK_KERNELS();
   return 0;
 }
@@ -612,7 +628,7 @@ extern "C" int32_t b2g_net_create(b2g_ctx* ctx, const b2g_net_config* cfg, const
 }
 extern "C" int32_t b2g_net_destroy(b2g_net* n) {
   if (!n) return 0; cudaSetDevice(n->ctx->device); cudaStreamSynchronize(n->ctx->stream); cudaStreamSynchronize(n->ctx->side);
-  for (auto e : n->ev_fork) if (e) cudaEventDestroy(e); for (auto e : n->ev_done) if (e) cudaEventDestroy(e); if (n->ev_join) cudaEventDestroy(n->ev_join);
+  for (auto e : n->ev_fork) if (e) cudaEventDestroy(e); for (auto e : n->ev_done) if (e) cudaEventDestroy(e); if (n->ev_join) cudaEventDestroy(n->ev_join); if (n->ev_shadow) cudaEventDestroy(n->ev_shadow);
   for (void* p : n->allocs) cudaFree(p); delete n; return 0;
 }
 extern "C" int32_t b2g_net_num_params(b2g_net* n, int64_t* out) { if (!n || !out) return fail(B2G_ERR_ARG, "null"); *out = n->n_params; return 0; }
@@ -804,7 +820,7 @@ static int32_t gan_step_part2(b2g_gan* g, int N) {
   k_xent(D->prec, logits, g->y_d, D->epsA, g->loss_dev, N, 2, D->cfg.xent_clip_eps, s);
   B2(net_backward(D, D->input, D->epsA, 2 * N, 2, true, false));
   B2(net_allreduce_grads(D));
-  B2(net_update(D, 2 * N));
+  B2(net_update(D, 2 * N, /*async_shadow=*/true));     // joined by the G step's backward pass through D
   // 3. G update through D on (z_g, y_gen) (J:465-471); D's parameters / running stats / updater state untouched
   CU(cudaStreamWaitEvent(s, G->ctx->ev_b, 0));
   FwdOpts od2{N, 1, true, false, nullptr};

@@ -162,25 +162,25 @@ __global__ void __launch_bounds__(256) bn_stats_partial_bf16x8_kernel(const uint
   block_fold_write<2>(acc, C, C8, c8, ty, TY, dst, ((size_t)g * S + sl) * C);
 }
 // stage 2: block = 32 adjacent channels x 16 slice lanes (coalesced 128-byte rows of the partial arrays), fixed-order tree in double
-__global__ void __launch_bounds__(512) bn_stats_final_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int rows, int C, int S, int groups, float eps,
+__global__ void __launch_bounds__(1024) bn_stats_final_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int rows, int C, int S, int groups, float eps,
                                       float* __restrict__ mean, float* __restrict__ invstd,
                                       const float* __restrict__ run_mean, const float* __restrict__ run_var, float* g_mean, float* g_var, float decay) { pdl_prologue();
-  __shared__ double sa[16][33], sb[16][33];
+  __shared__ double sa[32][33], sb[32][33];      // 32 channels x 32 slice lanes: S <= 256 partial rows in ONE batch of 8 loads per thread
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, c = blockIdx.x * 32 + tx;
   double acc_gm = 0.0, acc_gv = 0.0;
   for (int g = 0; g < groups; ++g) {
     double a = 0.0, b = 0.0;
-    if (c < C) for (int sl0 = ty; sl0 < S; sl0 += 16 * 8) {      // 16 independent loads in flight per thread: one L2 round trip per batch
+    if (c < C) for (int sl0 = ty; sl0 < S; sl0 += 32 * 8) {      // 16 independent loads in flight per thread: one L2 round trip per batch
       float va[8], vb[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) { const int sl = sl0 + 16 * q; va[q] = sl < S ? psum[((size_t)g * S + sl) * C + c] : 0.f; vb[q] = sl < S ? psq[((size_t)g * S + sl) * C + c] : 0.f; }
+      for (int q = 0; q < 8; ++q) { const int sl = sl0 + 32 * q; va[q] = sl < S ? psum[((size_t)g * S + sl) * C + c] : 0.f; vb[q] = sl < S ? psq[((size_t)g * S + sl) * C + c] : 0.f; }
 #pragma unroll
       for (int q = 0; q < 8; ++q) { a += va[q]; b += vb[q]; }
     }
     sa[ty][tx] = a; sb[ty][tx] = b;
     __syncthreads();
     if (ty == 0 && c < C) {
-      for (int k = 1; k < 16; ++k) { a += sa[k][tx]; b += sb[k][tx]; }
+      for (int k = 1; k < 32; ++k) { a += sa[k][tx]; b += sb[k][tx]; }
       const double mu = a / rows; double var = b / rows - mu * mu; if (var < 0) var = 0;
       mean[g * C + c] = (float)mu; invstd[g * C + c] = (float)(1.0 / sqrt(var + (double)eps));
       if (g_mean) { acc_gm += (1.0 - decay) * ((double)run_mean[c] - mu); acc_gv += (1.0 - decay) * ((double)run_var[c] - var); }
@@ -202,7 +202,7 @@ void k_bn_stats(int prec, const void* x, int rows, int C, int groups, float* scr
     DISPATCH_PREC(prec, T, (launch_pdl(bn_stats_partial_kernel<T>, dim3(grid), dim3(256), (size_t)(0), s, (const T*)x, rows, C, S, psum, psq)));
   }
   LAUNCHED();
-  launch_pdl(bn_stats_final_kernel, dim3((C + 31) / 32), dim3(512), (size_t)(0), s, psum, psq, rows, C, S, groups, eps, mean, invstd, run_mean, run_var, g_mean, g_var, decay); LAUNCHED();
+  launch_pdl(bn_stats_final_kernel, dim3((C + 31) / 32), dim3(1024), (size_t)(0), s, psum, psq, rows, C, S, groups, eps, mean, invstd, run_mean, run_var, g_mean, g_var, decay); LAUNCHED();
 }
 __global__ void bn_prep_infer_kernel(const float* __restrict__ rm, const float* __restrict__ rv, int C, int groups, float eps, float* mean, float* invstd) { pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= C * groups) return;
@@ -333,24 +333,24 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_bf16x8_kernel(const uint4
     }
   }
 }
-__global__ void __launch_bounds__(512) bn_bwd_final_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int rows, int C, int S, int groups,
+__global__ void __launch_bounds__(1024) bn_bwd_final_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int rows, int C, int S, int groups,
                                     float* __restrict__ c1, float* __restrict__ c2, float* g_gamma, float* g_beta, int want) { pdl_prologue();
-  __shared__ double sa[16][33], sb[16][33];
+  __shared__ double sa[32][33], sb[32][33];      // 32 channels x 32 slice lanes: S <= 256 partial rows in ONE batch of 8 loads per thread
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, c = blockIdx.x * 32 + tx;
   double tg = 0.0, tb = 0.0;
   for (int g = 0; g < groups; ++g) {
     double a = 0.0, b = 0.0;
-    if (c < C) for (int sl0 = ty; sl0 < S; sl0 += 16 * 8) {
+    if (c < C) for (int sl0 = ty; sl0 < S; sl0 += 32 * 8) {
       float va[8], vb[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) { const int sl = sl0 + 16 * q; va[q] = sl < S ? p1[((size_t)g * S + sl) * C + c] : 0.f; vb[q] = sl < S ? p2[((size_t)g * S + sl) * C + c] : 0.f; }
+      for (int q = 0; q < 8; ++q) { const int sl = sl0 + 32 * q; va[q] = sl < S ? p1[((size_t)g * S + sl) * C + c] : 0.f; vb[q] = sl < S ? p2[((size_t)g * S + sl) * C + c] : 0.f; }
 #pragma unroll
       for (int q = 0; q < 8; ++q) { a += va[q]; b += vb[q]; }
     }
     sa[ty][tx] = a; sb[ty][tx] = b;
     __syncthreads();
     if (ty == 0 && c < C) {
-      for (int k = 1; k < 16; ++k) { a += sa[k][tx]; b += sb[k][tx]; }
+      for (int k = 1; k < 32; ++k) { a += sa[k][tx]; b += sb[k][tx]; }
       c1[g * C + c] = (float)(a / rows); c2[g * C + c] = (float)(b / rows); tb += a; tg += b;
     }
     __syncthreads();
@@ -382,7 +382,7 @@ void k_bn_bwd(int prec, const void* x, const void* eps_out, void* eps_in, int ro
     DISPATCH_PREC(prec, T, (launch_pdl(bn_bwd_partial_kernel<T>, dim3(grid), dim3(256), (size_t)(0), s, (const T*)x, (const T*)eps_out, rows, C, S, mean, invstd, gamma, beta, act, alpha, p1, p2)));
   }
   LAUNCHED();
-  launch_pdl(bn_bwd_final_kernel, dim3((C + 31) / 32), dim3(512), (size_t)(0), s, p1, p2, rows, C, S, groups, c1, c2, g_gamma, g_beta, want); LAUNCHED();
+  launch_pdl(bn_bwd_final_kernel, dim3((C + 31) / 32), dim3(1024), (size_t)(0), s, p1, p2, rows, C, S, groups, c1, c2, g_gamma, g_beta, want); LAUNCHED();
   if (eps_in) {
     size_t n = (size_t)rows * C * groups;
     if (vec) { DISPATCH_ACT(act, ACTC, launch_pdl(bn_bwd_apply_bf16x8_kernel<ACTC>, dim3(vec4_blocks((size_t)rows * C / 8)), dim3(256), (size_t)(0), s, (const uint4*)x, (const uint4*)eps_out, (uint4*)eps_in, rows, C, groups, mean, invstd, gamma, beta, act, alpha, c1, c2)); }
