@@ -259,7 +259,7 @@ __global__ void dense_small_o_wgrad_kernel(const T* __restrict__ x, const T* __r
 // ------------------------------------------------------------------ (e) 1x1 layers with a short reduction (G-first: z -> 4x4 map) -----
 // Transposed conv of a 1x1 input = out[n][c] = sum_o z[n][o] * W[o][c] with O = nIn (100) and C = taps*nOut (8192): the reduction is too
 // short (and not a multiple of 64) for the tensor-core tiles, the work is reading W / writing the map once.  Thread = 2 adjacent c
-// (one 32-bit weight load per o), 16 rows of n per CTA with z staged in smem as fp32 and read as float4 broadcasts (4 o at a time).
+// (one 32-bit weight load per o), 8 rows of n per CTA with z staged in smem as fp32 and read as float4 broadcasts (4 o at a time).
 template <typename T> __device__ __forceinline__ float2 ld2(const T* p);
 template <> __device__ __forceinline__ float2 ld2<float>(const float* p) { if ((reinterpret_cast<uintptr_t>(p) & 7) == 0) return *reinterpret_cast<const float2*>(p); return make_float2(p[0], p[1]); }   // fp32 parameters sit at arbitrary offsets
 template <> __device__ __forceinline__ float2 ld2<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p)); }
@@ -271,13 +271,13 @@ template <typename T, typename TW>
 __global__ void __launch_bounds__(128) dense_small_k_dgrad_kernel(const T* __restrict__ dy, const TW* __restrict__ w, const float* __restrict__ bias, T* __restrict__ dx,
                                                                    int N, int C, int O, int act, float alpha) { pdl_prologue();
   constexpr int OC = 16;                                  // o per chunk
-  __shared__ __align__(16) float sz[16][128];            // [n][o], zero padded to a multiple of OC
-  const int cb = blockIdx.x * 256, c = cb + threadIdx.x * 2, n0 = blockIdx.y * 16, OP = (O + OC - 1) / OC * OC;
+  __shared__ __align__(16) float sz[8][128];             // [n][o], zero padded to a multiple of OC
+  const int cb = blockIdx.x * 256, c = cb + threadIdx.x * 2, n0 = blockIdx.y * 8, OP = (O + OC - 1) / OC * OC;
 #pragma unroll 8
-  for (int i = threadIdx.x; i < 16 * OP; i += 128) { const int r = i / OP, o = i - r * OP; sz[r][o] = (o < O && n0 + r < N) ? ldf(dy, (size_t)(n0 + r) * O + o) : 0.f; }
-  float acc[16][2];
+  for (int i = threadIdx.x; i < 8 * OP; i += 128) { const int r = i / OP, o = i - r * OP; sz[r][o] = (o < O && n0 + r < N) ? ldf(dy, (size_t)(n0 + r) * O + o) : 0.f; }
+  float acc[8][2];
 #pragma unroll
-  for (int r = 0; r < 16; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; }
+  for (int r = 0; r < 8; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; }
   float2 pre[OC];                                         // thread's pair of columns for each o of the next chunk
 #pragma unroll
   for (int j = 0; j < OC; ++j) pre[j] = (j < O) ? ld2(w + (size_t)j * C + c) : make_float2(0.f, 0.f);
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(128) dense_small_k_dgrad_kernel(const T* __res
     for (int j4 = 0; j4 < OC / 4; ++j4) {
       const float2* wv = cur + 4 * j4;
 #pragma unroll
-      for (int r = 0; r < 16; ++r) {
+      for (int r = 0; r < 8; ++r) {
         const float4 z = *reinterpret_cast<const float4*>(&sz[r][o0 + 4 * j4]);
         acc[r][0] = fmaf(z.x, wv[0].x, acc[r][0]); acc[r][1] = fmaf(z.x, wv[0].y, acc[r][1]);
         acc[r][0] = fmaf(z.y, wv[1].x, acc[r][0]); acc[r][1] = fmaf(z.y, wv[1].y, acc[r][1]);
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(128) dense_small_k_dgrad_kernel(const T* __res
   }
   const float b0 = bias ? bias[c] : 0.f, b1 = bias ? bias[c + 1] : 0.f;
 #pragma unroll
-  for (int r = 0; r < 16; ++r) if (n0 + r < N) st2(dx + (size_t)(n0 + r) * C + c, act_fwd(act, acc[r][0] + b0, alpha), act_fwd(act, acc[r][1] + b1, alpha));
+  for (int r = 0; r < 8; ++r) if (n0 + r < N) st2(dx + (size_t)(n0 + r) * C + c, act_fwd(act, acc[r][0] + b0, alpha), act_fwd(act, acc[r][1] + b1, alpha));
 }
 // dw[o][c] = sum_n dy[n][o] * x[n][c]: thread = 2 adjacent c x 16 o, the whole batch reduced in the CTA (no split, deterministic);
 // rows are consumed 8 at a time so that eight global loads are in flight per thread
@@ -377,7 +377,7 @@ void k_edge_wgrad_small_cin(int prec, const ConvGeom& g, const void* x, const vo
 }
 bool dense_small_k_supported(const ConvGeom& g) { return g.KH == 1 && g.KW == 1 && g.H == 1 && g.W == 1 && g.O >= 1 && g.O <= 128 && g.C % 256 == 0 && g.C >= 256; }
 void k_dense_small_k_dgrad(int prec, int wprec, const ConvGeom& g, const void* dy, const void* w, const float* bias, void* dx, int act, float alpha, cudaStream_t s) {
-  dim3 grid(g.C / 256, (g.N + 15) / 16);
+  dim3 grid(g.C / 256, (g.N + 7) / 8);
   if (prec == PREC_F32) launch_pdl(dense_small_k_dgrad_kernel<float, float>, grid, dim3(128), (size_t)0, s, (const float*)dy, (const float*)w, bias, (float*)dx, g.N, g.C, g.O, act, alpha);
   else if (wprec == PREC_F32) launch_pdl(dense_small_k_dgrad_kernel<__nv_bfloat16, float>, grid, dim3(128), (size_t)0, s, (const __nv_bfloat16*)dy, (const float*)w, bias, (__nv_bfloat16*)dx, g.N, g.C, g.O, act, alpha);
   else launch_pdl(dense_small_k_dgrad_kernel<__nv_bfloat16, __nv_bfloat16>, grid, dim3(128), (size_t)0, s, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)dx, g.N, g.C, g.O, act, alpha);

@@ -890,17 +890,26 @@ __global__ void __launch_bounds__(256) updater_kernel(float* __restrict__ params
   const int t = *step + 1;
   float alpha_t = 0.f;
   if (sg.kind == 2) alpha_t = sg.lr * sqrtf(1.0f - powf(sg.b2, (float)t)) / (1.0f - powf(sg.b1, (float)t));
-  for (int64_t i = base + threadIdx.x; i < end; i += blockDim.x) {
-    float g = grads[i] * (sg.div_mb ? inv_mb : inv_world);   // BN running-stat pseudo-gradients: no /mb, mean over ranks
-    if (sg.clip > 0.f) g = fminf(fmaxf(g, -sg.clip), sg.clip);
-    float p = params[i], u;
-    if (sg.kind == 0) u = sg.lr * g;
-    else if (sg.kind == 1) { float c = sg.b1 * st0[i] + (1.0f - sg.b1) * g * g; st0[i] = c; u = sg.lr * g / (sqrtf(c) + sg.eps); }
-    else if (sg.kind == 2) { float m = sg.b1 * st0[i] + (1.0f - sg.b1) * g; float v = sg.b2 * st1[i] + (1.0f - sg.b2) * g * g; st0[i] = m; st1[i] = v; u = alpha_t * m / (sqrtf(v) + sg.eps); }
-    else u = g;
-    if (sg.l2 != 0.f) u = fmaf(sg.l2, p, u);
-    p -= u; params[i] = p;
-    if (shadow && sg.off_bf >= 0) shadow[sg.off_bf + (i - sg.off)] = __float2bfloat16_rn(p);
+  // four elements per thread per pass, every load issued before the first use: the kernel is latency-, not bandwidth-bound otherwise
+  const float gscale = sg.div_mb ? inv_mb : inv_world;     // BN running-stat pseudo-gradients: no /mb, mean over ranks
+  for (int64_t i0 = base + threadIdx.x; i0 < end; i0 += 4 * blockDim.x) {
+    float gv[4], pv[4], s0[4], s1[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const int64_t i = i0 + q * (int64_t)blockDim.x; const bool ok = i < end;
+      gv[q] = ok ? grads[i] : 0.f; pv[q] = ok ? params[i] : 0.f; s0[q] = (ok && (sg.kind == 1 || sg.kind == 2)) ? st0[i] : 0.f; s1[q] = (ok && sg.kind == 2) ? st1[i] : 0.f; }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const int64_t i = i0 + q * (int64_t)blockDim.x; if (i >= end) continue;
+      float g = gv[q] * gscale;
+      if (sg.clip > 0.f) g = fminf(fmaxf(g, -sg.clip), sg.clip);
+      float p = pv[q], u;
+      if (sg.kind == 0) u = sg.lr * g;
+      else if (sg.kind == 1) { float c = sg.b1 * s0[q] + (1.0f - sg.b1) * g * g; st0[i] = c; u = sg.lr * g / (sqrtf(c) + sg.eps); }
+      else if (sg.kind == 2) { float m = sg.b1 * s0[q] + (1.0f - sg.b1) * g; float v = sg.b2 * s1[q] + (1.0f - sg.b2) * g * g; st0[i] = m; st1[i] = v; u = alpha_t * m / (sqrtf(v) + sg.eps); }
+      else u = g;
+      if (sg.l2 != 0.f) u = fmaf(sg.l2, p, u);
+      p -= u; params[i] = p;
+      if (shadow && sg.off_bf >= 0) shadow[sg.off_bf + (i - sg.off)] = __float2bfloat16_rn(p);
+    }
   }
 }
 void k_updater(float* params, const float* grads, float* st0, float* st1, const UpdSeg* segs, const int32_t* chunk_seg, const int64_t* chunk_off,

@@ -1039,7 +1039,7 @@ static int tc_edge_wgrad_ctas(const ConvGeom& g, int* tpc) {
 size_t k_tc_edge_wgrad_scratch_floats(const ConvGeom& g) { return tc_edge_wgrad_supported(g) ? (size_t)tc_edge_wgrad_target() * (64 * 16 * g.C + 64) : 0; }
 int k_tc_edge_conv(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out, int act, float alpha, cudaStream_t s) {
   TcEdgeParams p{}; if (!edge_tile(g, &p.Ht) || g.O % 64) return -1;
-  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 3) || (reinterpret_cast<uintptr_t>(out) & 15)) return -1;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return -1;
   p.x = x; p.w = w; p.bias = bias; p.out = out; p.N = g.N; p.H = g.H; p.W = g.W; p.C = g.C; p.OH = g.OH; p.OW = g.OW; p.O = g.O; p.tiles_y = g.OH / p.Ht;
   p.tiles_total = g.N * p.tiles_y; p.act = act; p.alpha = alpha;
   const size_t smem = 1024 + 24576 + EDGE_SLAB_BYTES + 64;
