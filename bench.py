@@ -12,7 +12,9 @@ Workload at N=1: BASELINE configs[1] = 64x64x3 DCGAN, z=100, bf16, batch 128 per
 `e2e`     : the same metric through the host-buffer C-ABI call b2g_gan_step (H2D of x_real/z/labels from pinned memory and
             D2H of the three losses inside the timed region) -- the call the Java driver makes per iteration.
 `roofline`: the dominant tensor-core kernel timed live (CUDA events, on the library's stream) against MEASURED_PEAKS.json.
-`cpu_baseline`: the oracle port (NumPy/OpenBLAS im2col+SGEMM restatement of DL4J's nd4j-native algorithm) on this box's cores.
+`cpu_baseline`: the oracle port on this box's cores -- the same step as oracle/dl4j_oracle.py::gan_step (pinned to it to 1e-16 in fp64 by
+            tests/test_oracle.py) executed on torch's CPU kernels (oneDNN convolutions + MKL GEMM, every host thread), i.e. the libraries
+            DL4J's nd4j-native backend itself calls; the NumPy im2col+SGEMM oracle is ~10x slower and is only the fallback.
 --impl reference: that CPU restatement IS the reference arm (DL4J itself cannot run: no JVM in the image).
 """
 from __future__ import annotations
@@ -118,23 +120,45 @@ def algorithmic_flops_per_image(cfg):
 # ------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port timed on the host cores (cpu_baseline leg and --impl reference)
 # ------------------------------------------------------------------------------------------------------
-def cpu_step_rate(cfg, sample_batch, steps, warmup):
+def _oracle_nets(cfg):
     from oracle import dl4j_oracle as o        # bench.py's cpu_baseline / reference legs may execute oracle/
     q = o.Quirks(xent_clip_eps=0.0)
     if cfg.get("mlp"):
-        G = o.mlp_generator(cfg["z"], cfg["hidden"], cfg["d"], dtype=np.float32, quirks=q); D = o.mlp_discriminator(cfg["d"], cfg["hidden"], dtype=np.float32, quirks=q)
-    else:
-        G = o.dcgan_generator(cfg["size"], cfg["z"], cfg["nf"], cfg["nc"], dtype=np.float32, quirks=q)
-        D = o.dcgan_discriminator(cfg["size"], cfg["nf"], cfg["nc"], dtype=np.float32, quirks=q)
+        return o.mlp_generator(cfg["z"], cfg["hidden"], cfg["d"], dtype=np.float32, quirks=q), o.mlp_discriminator(cfg["d"], cfg["hidden"], dtype=np.float32, quirks=q)
+    return (o.dcgan_generator(cfg["size"], cfg["z"], cfg["nf"], cfg["nc"], dtype=np.float32, quirks=q),
+            o.dcgan_discriminator(cfg["size"], cfg["nf"], cfg["nc"], dtype=np.float32, quirks=q))
+
+
+def cpu_stepper(cfg):
+    """Returns (step(data) -> result dict, engine description).  Preferred: the oracle step on torch CPU kernels; fallback: NumPy oracle."""
+    from oracle import dl4j_oracle as o
+    G, D = _oracle_nets(cfg)
+    try:
+        import torch
+        from oracle import torch_cpu
+        torch.set_num_threads(os.cpu_count() or 1)
+        t = torch_cpu.TorchCpuGan(G, D, dtype=torch.float32)
+        return (lambda data: t.step(*data)), f"fp32 torch-CPU (oneDNN/MKL) port of oracle gan_step, {torch.get_num_threads()} threads"
+    except Exception as e:      # noqa: BLE001 -- any import / runtime problem: fall back to the NumPy oracle
+        sys.stderr.write(f"[bench] torch CPU port unavailable ({e}); timing the NumPy oracle\n")
+        return (lambda data: o.gan_step(G, D, *data)), "fp32 NumPy/OpenBLAS im2col+SGEMM oracle"
+
+
+def cpu_step_rate(cfg, sample_batch, steps, warmup, budget_s=None):
+    """Times `steps` CPU steps of `sample_batch` examples.  With a budget, the sample batch is halved until the projected run fits."""
+    step, engine = cpu_stepper(cfg)
     data = synthetic(cfg, sample_batch, 666)
-    for _ in range(warmup):
-        o.gan_step(G, D, *data)
+    for _ in range(max(1, warmup)):
+        t0 = time.perf_counter(); step(data); one = time.perf_counter() - t0
+    while budget_s and one * steps > budget_s and sample_batch > 4:
+        sample_batch //= 2; data = synthetic(cfg, sample_batch, 666)
+        t0 = time.perf_counter(); step(data); one = time.perf_counter() - t0
     t0 = time.perf_counter()
     for _ in range(steps):
-        r = o.gan_step(G, D, *data)
+        r = step(data)
     dt = time.perf_counter() - t0
     assert np.isfinite(r["loss_g"])
-    return sample_batch * steps / dt, dt / steps
+    return sample_batch * steps / dt, dt / steps, sample_batch, engine
 
 
 def run_reference(args, cfg, rank, world):
@@ -142,14 +166,14 @@ def run_reference(args, cfg, rank, world):
         return
     cores = os.cpu_count() or 1
     sample = 2048 if cfg.get("mlp") else 32
-    steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))
-    ips, sec = cpu_step_rate(cfg, sample, steps, warmup)
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
+    ips, sec, sample, engine = cpu_step_rate(cfg, sample, steps, warmup, budget_s=180.0)     # exactly K timed steps; the per-step sample shrinks if K of them would not fit
     line = {
         "impl": "reference", "metric": "images/sec (full G+D step)", "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg["desc"], "global_batch": sample, "note": "bounded sample: batch 32 per step on the host CPU; DL4J 1.0.0-beta3 cannot run here (no JVM), "
-                   "this is the im2col+SGEMM (OpenBLAS) restatement of its nd4j-native algorithm (oracle/dl4j_oracle.py)"},
-        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": f"{steps} steps x batch {sample}, fp32 NumPy/OpenBLAS, all {cores} host threads"},
+        "config": {"workload": cfg["desc"], "global_batch": sample, "note": f"bounded sample: batch {sample} per step on the host CPU; DL4J 1.0.0-beta3 cannot run here (no JVM); "
+                   f"engine: {engine} (the step of oracle/dl4j_oracle.py, the restatement of DL4J's algorithm)"},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": f"{steps} steps x batch {sample}, {engine}"},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -267,7 +291,7 @@ def run_ours(args, cfg, rank, world, local_rank):
         step_tf = F * ips / world / 1e12
         cores = os.cpu_count() or 1
         cpu_sample = 2048 if cfg.get("mlp") else 32
-        cpu_ips, cpu_sec = cpu_step_rate(cfg, cpu_sample, 4, 1)
+        cpu_ips, cpu_sec, cpu_sample, cpu_engine = cpu_step_rate(cfg, cpu_sample, 4, 1, budget_s=30.0)
         line = {
             "metric": "images/sec (full G+D step)", "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -277,7 +301,7 @@ def run_ours(args, cfg, rank, world, local_rank):
             "step_roofline": {"algorithmic_gflop_per_image": F / 1e9, "achieved_tflops_per_gpu": step_tf, "peak": peaks["bf16_tflops_sustained"], "frac": step_tf / peaks["bf16_tflops_sustained"],
                               "peak_source": peaks["source"] + " (sustained cuBLAS bf16)"},
             "cpu_baseline": {"value": cpu_ips, "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": f"4 steps x batch {cpu_sample} of the same workload, fp32 NumPy/OpenBLAS im2col+SGEMM restatement of DL4J nd4j-native, {cores} host threads"},
+                             "sample": f"4 steps x batch {cpu_sample} of the same workload, {cpu_engine}"},
             "e2e": {"value": e2e_ips, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall,
             "losses": [float(v) for v in losses],

@@ -399,3 +399,36 @@ def test_transfer_learning_head_frozen_trunk_and_softmax_mcxent():
     changed = {names[i][0] for i in np.flatnonzero(p0 != p1)}
     assert changed == {"dis_batch", "dis_output_layer_7"}
     assert np.allclose(cv.output(x).sum(1), 1.0)
+
+
+def test_torch_cpu_step_matches_numpy_oracle():
+    """oracle/torch_cpu.py (the CPU arm bench.py times) is the same step as dl4j_oracle.gan_step: fp64, two iterations, DCGAN with
+    BatchNorm + LeakyReLU + transposed convs, Adam -- losses and every parameter to round-off; and the MLP-GAN (dense path)."""
+    import copy
+    import torch
+    from oracle import torch_cpu as tc
+    q = o.Quirks(xent_clip_eps=0.0)
+    cases = [(o.dcgan_generator(16, 12, 8, 3, dtype=np.float64, quirks=q), o.dcgan_discriminator(16, 8, 3, dtype=np.float64, quirks=q), o.synthetic_batch(8, 16, 3, 12, seed=3)),
+             (o.mlp_generator(10, 32, 24, dtype=np.float64, quirks=q), o.mlp_discriminator(24, 32, dtype=np.float64, quirks=q), None)]
+    rng = np.random.default_rng(3)
+    for G, D, data in cases:
+        for net in (G, D):
+            for l in net.layers:
+                if l.has_params:
+                    for p in l.params:
+                        l.params[p] = l.params[p] * (1 + 0.2 * rng.random(l.params[p].shape)) if p == "var" else l.params[p] + 0.1 * rng.standard_normal(l.params[p].shape)
+        if data is None:
+            n = 16
+            data = (rng.standard_normal((n, 24)), rng.uniform(-1, 1, (n, 10)), rng.uniform(-1, 1, (n, 10)),
+                    1 + 0.05 * rng.standard_normal((n, 1)), 0.05 * rng.standard_normal((n, 1)), np.ones((n, 1)))
+        data = [np.asarray(a, np.float64) for a in data]
+        G2, D2 = copy.deepcopy(G), copy.deepcopy(D)
+        t = tc.TorchCpuGan(G2, D2, dtype=torch.float64)
+        for _ in range(2):
+            r, r2 = o.gan_step(G, D, *data), t.step(*data)
+            for k in ("loss_d_real", "loss_d_fake", "loss_g"):
+                assert abs(r[k] - r2[k]) < 1e-10 * max(1.0, abs(r[k])), (k, r[k], r2[k])
+            assert np.abs(r["x_fake"] - r2["x_fake"].reshape(r["x_fake"].shape)).max() < 1e-10
+        t.G.export(); t.D.export()
+        assert np.abs(G.params_flat() - G2.params_flat()).max() < 1e-9
+        assert np.abs(D.params_flat() - D2.params_flat()).max() < 1e-9
