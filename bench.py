@@ -129,24 +129,22 @@ def _oracle_nets(cfg):
             o.dcgan_discriminator(cfg["size"], cfg["nf"], cfg["nc"], dtype=np.float32, quirks=q))
 
 
-def cpu_stepper(cfg):
-    """Returns (step(data) -> result dict, engine description).  Preferred: the oracle step on torch CPU kernels; fallback: NumPy oracle."""
+def cpu_stepper(cfg, engine):
+    """Returns (step(data) -> result dict, engine description).  engine "torch": the oracle step on torch CPU kernels; "numpy": the NumPy oracle."""
     from oracle import dl4j_oracle as o
     G, D = _oracle_nets(cfg)
-    try:
+    if engine == "torch":
         import torch
         from oracle import torch_cpu
         torch.set_num_threads(os.cpu_count() or 1)
         t = torch_cpu.TorchCpuGan(G, D, dtype=torch.float32)
         return (lambda data: t.step(*data)), f"fp32 torch-CPU (oneDNN/MKL) port of oracle gan_step, {torch.get_num_threads()} threads"
-    except Exception as e:      # noqa: BLE001 -- any import / runtime problem: fall back to the NumPy oracle
-        sys.stderr.write(f"[bench] torch CPU port unavailable ({e}); timing the NumPy oracle\n")
-        return (lambda data: o.gan_step(G, D, *data)), "fp32 NumPy/OpenBLAS im2col+SGEMM oracle"
+    return (lambda data: o.gan_step(G, D, *data)), f"fp32 NumPy/OpenBLAS im2col+SGEMM oracle, {os.cpu_count()} host threads"
 
 
-def cpu_step_rate(cfg, sample_batch, steps, warmup, budget_s=None):
+def _cpu_step_rate_inproc(cfg, sample_batch, steps, warmup, budget_s, engine):
     """Times `steps` CPU steps of `sample_batch` examples.  With a budget, the sample batch is halved until the projected run fits."""
-    step, engine = cpu_stepper(cfg)
+    step, desc = cpu_stepper(cfg, engine)
     data = synthetic(cfg, sample_batch, 666)
     for _ in range(max(1, warmup)):
         t0 = time.perf_counter(); step(data); one = time.perf_counter() - t0
@@ -158,7 +156,30 @@ def cpu_step_rate(cfg, sample_batch, steps, warmup, budget_s=None):
         r = step(data)
     dt = time.perf_counter() - t0
     assert np.isfinite(r["loss_g"])
-    return sample_batch * steps / dt, dt / steps, sample_batch, engine
+    return sample_batch * steps / dt, dt / steps, sample_batch, desc
+
+
+def cpu_step_rate(cfg_name, sample_batch, steps, warmup, budget_s=None):
+    """The CPU arm.  The torch-CPU port runs in a CHILD process under a hard timeout (a cold `import torch` on a fresh box takes up to a
+    minute, and a wedged thread pool must not take the bench down with it); if it fails or times out the NumPy oracle is timed in-process."""
+    cfg = CONFIGS[cfg_name]
+    if os.environ.get("B2G_CPU_ENGINE", "torch") == "torch":
+        cmd = [sys.executable, os.path.abspath(__file__), "--_cpu_worker", json.dumps([cfg_name, sample_batch, steps, warmup, budget_s])]
+        try:
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=(budget_s or 60.0) + 150.0)
+            last = [l for l in out.stdout.splitlines() if l.startswith("{")]
+            if out.returncode == 0 and last:
+                d = json.loads(last[-1]); return d["ips"], d["sec"], d["sample"], d["engine"]
+            sys.stderr.write(f"[bench] torch CPU port failed (rc {out.returncode}): {out.stderr[-300:]}\n")
+        except subprocess.TimeoutExpired:
+            sys.stderr.write("[bench] torch CPU port timed out; timing the NumPy oracle instead\n")
+    return _cpu_step_rate_inproc(cfg, sample_batch, steps, warmup, budget_s, "numpy")
+
+
+def _cpu_worker(payload):
+    cfg_name, sample_batch, steps, warmup, budget_s = json.loads(payload)
+    ips, sec, sample, desc = _cpu_step_rate_inproc(CONFIGS[cfg_name], sample_batch, steps, warmup, budget_s, "torch")
+    print(json.dumps({"ips": ips, "sec": sec, "sample": sample, "engine": desc}), flush=True)
 
 
 def run_reference(args, cfg, rank, world):
@@ -167,7 +188,7 @@ def run_reference(args, cfg, rank, world):
     cores = os.cpu_count() or 1
     sample = 2048 if cfg.get("mlp") else 32
     steps, warmup = max(1, args.steps), max(1, args.warmup)
-    ips, sec, sample, engine = cpu_step_rate(cfg, sample, steps, warmup, budget_s=180.0)     # exactly K timed steps; the per-step sample shrinks if K of them would not fit
+    ips, sec, sample, engine = cpu_step_rate(args.config, sample, steps, warmup, budget_s=150.0)     # exactly K timed steps; the per-step sample shrinks if K of them would not fit
     line = {
         "impl": "reference", "metric": "images/sec (full G+D step)", "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -291,7 +312,10 @@ def run_ours(args, cfg, rank, world, local_rank):
         step_tf = F * ips / world / 1e12
         cores = os.cpu_count() or 1
         cpu_sample = 2048 if cfg.get("mlp") else 32
-        cpu_ips, cpu_sec, cpu_sample, cpu_engine = cpu_step_rate(cfg, cpu_sample, 4, 1, budget_s=30.0)
+        cpu_base = None       # the CPU leg runs on rank 0 at N=1 only (the other ranks would idle in the process group meanwhile)
+        if world == 1:
+            cpu_ips, cpu_sec, cpu_sample, cpu_engine = cpu_step_rate(args.config, cpu_sample, 4, 1, budget_s=30.0)
+            cpu_base = {"value": cpu_ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": f"4 steps x batch {cpu_sample} of the same workload, {cpu_engine}"}
         line = {
             "metric": "images/sec (full G+D step)", "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -300,8 +324,7 @@ def run_ours(args, cfg, rank, world, local_rank):
             "roofline": roof,
             "step_roofline": {"algorithmic_gflop_per_image": F / 1e9, "achieved_tflops_per_gpu": step_tf, "peak": peaks["bf16_tflops_sustained"], "frac": step_tf / peaks["bf16_tflops_sustained"],
                               "peak_source": peaks["source"] + " (sustained cuBLAS bf16)"},
-            "cpu_baseline": {"value": cpu_ips, "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": f"4 steps x batch {cpu_sample} of the same workload, {cpu_engine}"},
+            "cpu_baseline": cpu_base,
             "e2e": {"value": e2e_ips, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall,
             "losses": [float(v) for v in losses],
@@ -313,6 +336,8 @@ def run_ours(args, cfg, rank, world, local_rank):
 
 
 def main():
+    if len(sys.argv) == 3 and sys.argv[1] == "--_cpu_worker":
+        _cpu_worker(sys.argv[2]); return
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
