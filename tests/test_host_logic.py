@@ -1,0 +1,84 @@
+"""CPU-only checks of host-side logic that the GPU kernels rely on, and of bench.py's reference-arm contract line."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+from oracle import dl4j_oracle as o
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def pack_deconv_ps(w_int, O, C):
+    """NumPy mirror of pack_deconv_ps_kernel (kernels_tc.cu): w_int [O][4][4][C] -> wps [(py,px,c4)][(dyr,dxc)][O]."""
+    wps = np.zeros((16, 9, O), w_int.dtype)
+    for py in range(2):
+        for px in range(2):
+            for c in range(C):
+                n = (py * 2 + px) * 4 + c
+                for t in range(9):
+                    dyr, dxc = t // 3 - 1, t % 3 - 1
+                    r = {(-1, 0): 3, (0, 0): 1, (0, 1): 2, (1, 1): 0}.get((dyr, py), -1)
+                    s = {(-1, 0): 3, (0, 0): 1, (0, 1): 2, (1, 1): 0}.get((dxc, px), -1)
+                    if r >= 0 and s >= 0:
+                        wps[n, t, :] = w_int[:, r, s, c]
+    return wps
+
+
+def test_pixel_shuffle_form_of_the_transposed_conv_equals_deconvolution2d():
+    """The tcgen05 G-last forward computes ONE 3x3 s1 p1 conv with 16 = (py,px,c4) output columns over the deconv input and scatters
+    each pixel's 16 values to its 2x2 output block.  With the packed weights this must equal Deconvolution2D 4x4 s2 p1 (J:203-219 family)."""
+    rng = np.random.default_rng(0)
+    n, O, C, h = 2, 8, 3, 5                                  # deconv: O input channels on an h x h grid -> C channels on 2h x 2h
+    dec = o.Deconv2D(O, C, (4, 4), (2, 2), (1, 1), has_bias=False); dec.init(rng, np.float64)
+    x = rng.standard_normal((n, O, h, h))
+    want = dec.forward(x, True)                              # [n, C, 2h, 2h]
+    # internal weight layout of the engine for this layer: [O][taps][C] (conv-equivalent geometry: g.O = deconv nIn, g.C = deconv nOut)
+    w_int = dec.params["W"].transpose(0, 2, 3, 1)            # [nIn=O][kh][kw][nOut=C]
+    wps = pack_deconv_ps(w_int, O, C)                        # [16][9][O]
+    conv = o.Conv2D(O, 16, (3, 3), (1, 1), (1, 1), has_bias=False); conv.init(rng, np.float64)
+    conv.params["W"] = wps.reshape(16, 3, 3, O).transpose(0, 3, 1, 2).copy()      # [16][O][3][3]
+    y16 = conv.forward(x, True)                              # [n, 16, h, h]
+    got = np.zeros_like(want)
+    for py in range(2):
+        for px in range(2):
+            for c in range(C):
+                got[:, c, py::2, px::2] = y16[:, (py * 2 + px) * 4 + c]
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12)
+    # the padded channel slots stay zero
+    for py in range(2):
+        for px in range(2):
+            assert np.all(y16[:, (py * 2 + px) * 4 + 3] == 0)
+
+
+def test_edge_im2col_row_layout():
+    """tc_edge_conv builds, per output pixel, the row k = (r*4+s)*C + c from the 4 x (4*C) window starting at input (2oy-1, 2ox-1):
+    the same K ordering as the engine's weight rows [O][16 taps][C], so out = rows @ W_int^T must equal ConvolutionLayer 4x4 s2 p1."""
+    rng = np.random.default_rng(1)
+    n, C, O, H = 2, 3, 5, 8
+    conv = o.Conv2D(C, O, (4, 4), (2, 2), (1, 1), has_bias=False); conv.init(rng, np.float64)
+    x = rng.standard_normal((n, C, H, H)); want = conv.forward(x, True)
+    xh = np.pad(x.transpose(0, 2, 3, 1), ((0, 0), (1, 1), (1, 1), (0, 0)))          # NHWC with the zero border
+    w_int = conv.params["W"].transpose(0, 2, 3, 1).reshape(O, 16 * C)              # [O][(r,s,c)]
+    got = np.zeros((n, H // 2, H // 2, O))
+    for oy in range(H // 2):
+        for ox in range(H // 2):
+            rows = xh[:, 2 * oy:2 * oy + 4, 2 * ox:2 * ox + 4, :].reshape(n, 16 * C)   # k = (r*4+s)*C + c
+            got[:, oy, ox] = rows @ w_int.T
+    np.testing.assert_allclose(got.transpose(0, 3, 1, 2), want, rtol=1e-12, atol=1e-12)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    env = dict(os.environ, B2G_CPU_ENGINE="numpy")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "c5", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-500:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["steps"] == 2 and line["warmup"] == 1 and line["higher_is_better"] is True
+    for k in ("metric", "value", "unit", "n_gpus", "ms_per_step", "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"] and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["value"] > 0
