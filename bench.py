@@ -166,7 +166,8 @@ def cpu_step_rate(cfg_name, sample_batch, steps, warmup, budget_s=None):
     if os.environ.get("B2G_CPU_ENGINE", "torch") == "torch":
         cmd = [sys.executable, os.path.abspath(__file__), "--_cpu_worker", json.dumps([cfg_name, sample_batch, steps, warmup, budget_s])]
         try:
-            out = subprocess.run(cmd, capture_output=True, text=True, timeout=(budget_s or 60.0) + 150.0)
+            env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "MKL_NUM_THREADS")}     # torchrun pins these to 1
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=(budget_s or 60.0) + 150.0, env=env)
             last = [l for l in out.stdout.splitlines() if l.startswith("{")]
             if out.returncode == 0 and last:
                 d = json.loads(last[-1]); return d["ips"], d["sec"], d["sample"], d["engine"]
