@@ -704,6 +704,15 @@ static int dispatch_conv(int BN, int CL, const CUtensorMap& tmA, const CUtensorM
       case 256: return launch_conv2<256, 3>(tmA, tmB, p, g2, s);
     }
   }
+  // B2G_TC_DEEP=1 (experiment, not yet measured): a grid that cannot give every SM two CTAs anyway (<= 148 CTAs: D4, G2 -- 64..128 sequential
+  // K-blocks at ~0.5 us each, TMA-latency-bound with 3-4 stages in flight) takes the whole shared memory for a deeper ring instead
+  static int deep = -1; if (deep < 0) { const char* e = getenv("B2G_TC_DEEP"); deep = (e && e[0] == '1') ? 1 : 0; }
+  if (deep && CL == 1 && (long)grid.x * grid.y * grid.z <= 148) {
+    switch (BN) {
+      case 64: return launch_conv<64, 8, 1>(tmA, tmB, p, grid, s);
+      case 128: return launch_conv<128, 6, 1>(tmA, tmB, p, grid, s);
+    }
+  }
   switch (BN) {
     case 64: return launch_conv_cl<64, 4>(CL, tmA, tmB, p, grid, s);
     case 128: return launch_conv_cl<128, 3>(CL, tmA, tmB, p, grid, s);
