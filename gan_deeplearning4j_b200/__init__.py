@@ -3,4 +3,4 @@ step of hamaadshah/gan_deeplearning4j, executing in libb200gan.so (hand-written 
 No CPU fallback: compute entry points raise B200GanError when the CUDA library or a B200 is missing."""
 from ._lib import B200GanError, LIB_PATH, PROTOTYPES, load  # noqa: F401
 from .engine import BF16, FP32, Context, Gan, Net, comm_unique_id, test_conv  # noqa: F401
-from . import data, models, parallel  # noqa: F401
+from . import data, models, parallel, serializer  # noqa: F401

@@ -169,6 +169,16 @@ class Net:
         v = _f32(st).ravel()
         check(self.lib.b2g_net_set_updater_state(self.h, _fp(v), v.size))
 
+    # --- checkpoint / resume (ModelSerializer.writeModel, J:606-618; serializer.py) ---
+    def save(self, path, save_updater: bool = True):
+        from . import serializer
+        serializer.save_net(self, path, self.specs, self.input_shape, save_updater, {"precision": "bf16" if self.precision == BF16 else "fp32", "max_batch": self.max_batch})
+
+    def restore(self, path, load_updater: bool = True):
+        """Loads parameters (and updater state) of a checkpoint written by save() into this net (same architecture)."""
+        from . import serializer
+        return serializer.restore_into(self, path, load_updater)
+
     # --- execution ---
     def output(self, x, train: bool = False) -> np.ndarray:
         x = _f32(x)

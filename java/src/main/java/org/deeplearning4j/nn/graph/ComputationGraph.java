@@ -45,6 +45,14 @@ public class ComputationGraph {
         Native.check(Native.netFit(net, Native.address(Native.floats(ds.getFeatures().data)), Native.address(Native.floats(ds.getLabels().data)), batch, Native.address(score)));
     }
     public INDArray params() { int n = (int) numParams(); FloatBuffer b = Native.direct(4 * n).asFloatBuffer(); Native.check(Native.netGetParams(net, Native.address(b), n)); float[] d = new float[n]; b.get(d); return new INDArray(d, 1, n); }
+    /** Updater state in the library's [state0 | state1] order (RmsProp cache / Adam m, then Adam v), 2 x numParams values. */
+    public INDArray updaterState() { int n = 2 * (int) numParams(); FloatBuffer b = Native.direct(4 * n).asFloatBuffer(); Native.check(Native.netGetUpdaterState(net, Native.address(b), n)); float[] d = new float[n]; b.get(d); return new INDArray(d, 1, n); }
+    /** The layer list as JSON (this library's specification, not DL4J's Jackson schema) -- ModelSerializer's configuration.json entry. */
+    public String configurationJson() {
+        StringBuilder s = new StringBuilder("{\"format\": \"b200gan layer specs\", \"layers\": [");
+        for (int i = 0; i < layers.size(); ++i) { Layer l = layers.get(i); s.append(i == 0 ? "" : ", ").append("{\"name\": \"").append(l.name).append("\", \"type\": ").append(l.type).append(", \"nIn\": ").append(l.nIn).append(", \"nOut\": ").append(l.nOut).append("}"); }
+        return s.append("]}").toString();
+    }
     public void setParams(INDArray p) { Native.check(Native.netSetParams(net, Native.address(Native.floats(p.data)), p.length())); }
 
     public LayerView getLayer(String name) { return new LayerView(name); }

@@ -82,3 +82,45 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"] and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["value"] > 0
+
+
+def test_checkpoint_container_round_trip_and_nd4j_stream_layout(tmp_path):
+    """ModelSerializer-style zip (J:606-618): round trip, and the byte layout of the ND4J stream restated in serializer.py."""
+    import io
+    import struct
+    import zipfile
+    from gan_deeplearning4j_b200 import serializer as sz, models as m
+    rng = np.random.default_rng(0)
+    specs = m.dcgan_discriminator(16, 8, 3)
+    p = rng.standard_normal(1234).astype(np.float32); u = rng.standard_normal(2468).astype(np.float32)
+
+    class FakeNet:            # the part of the Net interface the wrappers use
+        def __init__(self): self.p, self.u = p.copy(), u.copy()
+        def params(self): return self.p
+        def updater_state(self): return self.u
+        def num_params(self): return self.p.size
+        def set_params(self, v): self.p = np.asarray(v, np.float32).copy()
+        def set_updater_state(self, v): self.u = np.asarray(v, np.float32).copy()
+    path = tmp_path / "dis.zip"
+    sz.save_net(FakeNet(), path, specs, (3, 16, 16), meta={"precision": "bf16", "iteration": 7})
+    with zipfile.ZipFile(path) as z:
+        assert {"configuration.json", "coefficients.bin", "updaterState.bin"} <= set(z.namelist())        # DL4J's entry names
+        raw = z.read("coefficients.bin")
+    # shape-info buffer: writeUTF("LONG_SHAPE") writeLong(8) writeUTF("LONG") {2,1,n,n,1,0,1,'c'}; data: writeUTF writeLong(n) writeUTF("FLOAT") big-endian floats
+    b = io.BytesIO(raw)
+    assert b.read(2) == struct.pack(">H", 10) and b.read(10) == b"LONG_SHAPE" and struct.unpack(">q", b.read(8))[0] == 8
+    assert b.read(2) == struct.pack(">H", 4) and b.read(4) == b"LONG"
+    assert list(struct.unpack(">8q", b.read(64))) == [2, 1, 1234, 1234, 1, 0, 1, 99]
+    assert b.read(2 + 10) == struct.pack(">H", 10) + b"LONG_SHAPE" and struct.unpack(">q", b.read(8))[0] == 1234
+    assert b.read(2 + 5) == struct.pack(">H", 5) + b"FLOAT"
+    assert struct.unpack(">f", b.read(4))[0] == p[0]
+    other = FakeNet(); other.p[:] = 0; other.u[:] = 0
+    got = sz.restore_into(other, path)
+    assert np.array_equal(other.p, p) and np.array_equal(other.u, u) and got["meta"]["iteration"] == 7 and got["input_shape"] == (3, 16, 16)
+    assert [l["type"] for l in got["specs"]] == [l["type"] for l in specs]
+    sz.save_net(FakeNet(), path, specs, (3, 16, 16), save_updater=False)
+    assert sz.read_model(path)["updater_state"] is None
+    # a legacy (int-length) header is still readable
+    legacy = io.BytesIO(); legacy.write(struct.pack(">H", 4) + b"HEAP" + struct.pack(">i", 8) + struct.pack(">H", 3) + b"INT" + np.array([2, 1, 3, 3, 1, 0, 1, 99], ">i4").tobytes())
+    legacy.write(struct.pack(">H", 4) + b"HEAP" + struct.pack(">i", 3) + struct.pack(">H", 5) + b"FLOAT" + np.array([1, 2, 3], ">f4").tobytes()); legacy.seek(0)
+    assert np.array_equal(sz.read_nd4j_array(legacy), np.array([[1, 2, 3]], np.float32))
