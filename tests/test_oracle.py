@@ -432,3 +432,16 @@ def test_torch_cpu_step_matches_numpy_oracle():
         t.G.export(); t.D.export()
         assert np.abs(G.params_flat() - G2.params_flat()).max() < 1e-9
         assert np.abs(D.params_flat() - D2.params_flat()).max() < 1e-9
+
+
+def test_golden_vectors_pin_the_oracle():
+    """tests/golden/*.npz (made by tests/golden/make_golden.py) are fixed bytes: the oracle must keep reproducing them."""
+    import importlib.util
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "make_golden.py")); mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    for fname, fresh in (("gan_step_dcgan16.npz", mg.gan_step_vectors()), ("layer_cases.npz", mg.layer_vectors())):
+        stored = np.load(os.path.join(here, fname))
+        assert set(stored.files) == set(fresh), fname
+        for k in stored.files:
+            np.testing.assert_allclose(fresh[k], stored[k], rtol=1e-9, atol=1e-12, err_msg=f"{fname}:{k}")
