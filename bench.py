@@ -314,7 +314,7 @@ def run_ours(args, cfg, rank, world, local_rank):
         cores = os.cpu_count() or 1
         cpu_sample = 2048 if cfg.get("mlp") else 32
         cpu_base = None       # the CPU leg runs on rank 0 at N=1 only (the other ranks would idle in the process group meanwhile)
-        if world == 1:
+        if world == 1 and not args.no_cpu:
             cpu_ips, cpu_sec, cpu_sample, cpu_engine = cpu_step_rate(args.config, cpu_sample, 4, 1, budget_s=30.0)
             cpu_base = {"value": cpu_ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": f"4 steps x batch {cpu_sample} of the same workload, {cpu_engine}"}
         line = {
@@ -345,6 +345,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--no-cpu", dest="no_cpu", action="store_true", help="skip the cpu_baseline leg (A/B runs of kernel switches; not for reported lines)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cfg = CONFIGS[args.config]

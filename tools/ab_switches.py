@@ -1,0 +1,31 @@
+"""A/B the library's experiment switches in ONE gpurun call: runs bench.py (short, no CPU leg) once per environment variant and prints a table.
+usage: python tools/ab_switches.py [--steps 100] [--config c2] "B2G_TC_DEEP=1" "B2G_WGRAD_CTAS=296" "B2G_TC_DEEP=1 B2G_AR_OVERLAP=1" ...
+The first row is always the default configuration.  Numbers are for comparison inside one call only (same box, same clocks)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+args = sys.argv[1:]
+steps, config = "100", "c2"
+while args and args[0].startswith("--"):
+    k = args.pop(0)
+    if k == "--steps": steps = args.pop(0)
+    elif k == "--config": config = args.pop(0)
+variants = [""] + args
+rows = []
+for v in variants:
+    env = dict(os.environ)
+    for kv in v.split():
+        k, _, val = kv.partition("="); env[k] = val
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", steps, "--config", config, "--no-cpu"], capture_output=True, text=True, env=env)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    if out.returncode or not lines:
+        rows.append((v or "(default)", float("nan"), float("nan"), out.stderr.strip().splitlines()[-1][:80] if out.stderr.strip() else "failed")); continue
+    d = json.loads(lines[-1])
+    rows.append((v or "(default)", d["ms_per_step"], d["value"], f"e2e {d['e2e']['value']:.0f}"))
+base = rows[0][1]
+print(f"| switches | ms/step | {json.loads(lines[-1])['unit'] if lines else 'rate'} | vs default | note |\n|---|---|---|---|---|")
+for v, ms, val, note in rows:
+    print(f"| {v} | {ms:.4f} | {val:.0f} | {ms / base:.3f} | {note} |")
