@@ -1188,10 +1188,104 @@ __global__ void __launch_bounds__(192) tc_wgrad_kernel(const __grid_constant__ C
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, BNW < 32 ? 32 : BNW); }
 }
 
+// Experiment (B2G_WGRAD_MT2=1, not yet measured): one CTA owns 256 output channels -- four dy blocks and two accumulators (2 x 256 = all 512
+// TMEM columns) -- so each activation (x) tile in shared memory feeds twice the MMAs: bytes out of L2 per MAC drop by a third for the
+// O >= 256 layers (D3, D4, G2, G3).  A separate kernel so that the measured tc_wgrad_kernel above stays untouched.
+struct TcWgrad2Smem {
+  static constexpr int A_BYTES = 4 * 64 * 128, B_BYTES = 4 * 64 * 128, STAGE_BYTES = A_BYTES + B_BYTES, STAGES = 3;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES, TOTAL = BAR_OFF + 256 + 1024;
+};
+__global__ void __launch_bounds__(192) tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, const TcWgradParams p) { pdl_prologue();
+  using S = TcWgrad2Smem; constexpr int STAGES = S::STAGES, BNW = 256;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_full = smem_base + S::BAR_OFF, bar_empty = bar_full + 8 * STAGES, bar_accum = bar_empty + 8 * STAGES;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + S::BAR_OFF + 8 * (2 * STAGES + 1));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x, col0 = blockIdx.y * BNW, o0 = blockIdx.z * 256;
+  const int kb_beg = split * p.kb_per_split, kb_end = min(p.kb_total, kb_beg + p.kb_per_split);
+  const int num_kb = max(0, kb_end - kb_beg);
+  if (warp == 0 && lane == 0) {
+    prefetch_map(&tmDy); prefetch_map(&tmX);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_accum, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(smem_u32((const void*)tmem_slot), 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int kb = kb_beg + i, s = i % STAGES; const uint32_t ph = (i / STAGES) & 1;
+        int n0, y0;
+        if (p.Nt > 1) { n0 = kb * p.Nt; y0 = 0; } else { n0 = kb / p.tiles_y; y0 = (kb % p.tiles_y) * p.Ht; }
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        mbar_expect_tx(bar_full + 8 * s, S::STAGE_BYTES);
+        const uint32_t a = smem_base + s * S::STAGE_BYTES, b = a + S::A_BYTES;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tma_load_2d(a + j * 8192, &tmDy, bar_full + 8 * s, o0 + 64 * j, kb * 64);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int col = col0 + j * 64, tap = col / p.C, c0 = col % p.C, r = tap / p.KW, sx = tap % p.KW;
+          tma_load_4d(b + j * 8192, &tmX, bar_full + 8 * s, c0, -p.PW + sx, y0 * p.SH - p.PH + r, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, BNW, 1, 1);
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % STAGES; const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(bar_full + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t a = smem_base + s * S::STAGE_BYTES, b = a + S::A_BYTES;
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + m * BNW, desc_mnmajor_sw128(a + m * 16384 + k * 2048, 8192), desc_mnmajor_sw128(b + k * 2048, 8192), idesc, (i | k) != 0);
+        umma_commit(bar_empty + 8 * s);
+      }
+      umma_commit(bar_accum);
+    }
+  } else {
+    const int q = warp & 3, row = q * 32 + lane;
+    if (num_kb > 0) { mbar_wait(bar_accum, 0); tc_fence_after(); }
+#pragma unroll 1
+    for (int m = 0; m < 2; ++m) {
+      float* orow = p.out + (size_t)split * p.split_stride + (size_t)(o0 + m * 128 + row) * p.taps * p.C + col0;
+      if (num_kb > 0) {
+#pragma unroll 1
+        for (int cc = 0; cc < BNW; cc += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * BNW + cc), v);
+          tmem_ld_wait();
+          float4* dst = reinterpret_cast<float4*>(orow + cc);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        }
+      } else {
+        for (int cc = 0; cc < BNW; cc += 4) *reinterpret_cast<float4*>(orow + cc) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
 static int wgrad_bnw(const ConvGeom& g) { if (g.C % 64) return 0; const long cols = (long)g.KH * g.KW * g.C; return cols % 256 == 0 ? 256 : cols % 128 == 0 ? 128 : 64; }
+static bool wgrad_mt2(const ConvGeom& g) {
+  static int on = -1; if (on < 0) { const char* e = getenv("B2G_WGRAD_MT2"); on = (e && e[0] == '1') ? 1 : 0; }
+  return on && g.O % 256 == 0 && wgrad_bnw(g) == 256;
+}
 static int tc_wgrad_splits(const ConvGeom& g) {
   const int bnw = wgrad_bnw(g); if (!bnw) return 1;
-  long tiles = (long)(g.O / 128) * (g.KH * g.KW * g.C / bnw), kbt = (long)g.N * g.OH * g.OW / 64;
+  long tiles = (long)(g.O / (wgrad_mt2(g) ? 256 : 128)) * (g.KH * g.KW * g.C / bnw), kbt = (long)g.N * g.OH * g.OW / 64;
   // one CTA per SM (192 KB of smem): choose the split count so that the whole grid is ONE wave (<= 148 CTAs); measured: D2 wgrad 52 -> 39 us
   static int target = -1; if (target < 0) { const char* e = getenv("B2G_WGRAD_CTAS"); target = e ? atoi(e) : 148; }
   long sp = target / tiles, cap = kbt / 8; if (cap < 1) cap = 1; if (sp > cap) sp = cap; if (sp < 1) sp = 1; return (int)sp;
@@ -1235,6 +1329,13 @@ int k_tc_wgrad(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* d
     if (make_map_bf16(&tmX, x, 4, dims, strides, box, es)) return -1; }
   dim3 grid((unsigned)splits, (unsigned)(p.taps * g.C / BNW), (unsigned)(g.O / 128));
   int rc;
+  if (wgrad_mt2(g)) {
+    static bool attr2 = false;
+    if (!attr2) { if (cudaFuncSetAttribute(tc_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcWgrad2Smem::TOTAL) != cudaSuccess) return -2; attr2 = true; }
+    grid.z = (unsigned)(g.O / 256);
+    launch_pdl(tc_wgrad2_kernel, dim3(grid), dim3(192), (size_t)TcWgrad2Smem::TOTAL, s, tmDy, tmX, p); LAUNCHED();
+    rc = cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
+  } else
   switch (BNW) {
     case 64: rc = launch_wgrad<64, 4>(tmDy, tmX, p, grid, s); break;
     case 128: rc = launch_wgrad<128, 4>(tmDy, tmX, p, grid, s); break;
