@@ -122,28 +122,6 @@ def test_fp32_gan_step_matches_oracle(b200, fake_bn_train):
     gan.close(); bG.close(); bD.close()
 
 
-def test_fp32_gan_step_matches_golden_fixture(b200):
-    """The same step against the committed fixture tests/golden/gan_step_dcgan16.npz (inputs, initial parameters, and the oracle's losses and
-    parameters after each of 3 steps; tests/golden/make_golden.py): the CUDA path is compared with fixed bytes, not with a live oracle run."""
-    import os
-    from gan_deeplearning4j_b200 import models as m
-    b, ctx = b200
-    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gan_step_dcgan16.npz"))
-    size, z, nf, n = 16, 12, 8, 8
-    gs, ds = m.dcgan_generator(size, z, nf, 3, lr=2e-3), m.dcgan_discriminator(size, nf, 3, lr=2e-3)
-    bG = b.Net(ctx, gs, (z,), max_batch=n, precision=b.FP32, xent_clip_eps=1e-5)
-    bD = b.Net(ctx, ds, (3, size, size), max_batch=2 * n, precision=b.FP32, xent_clip_eps=1e-5, bn_groups=2)
-    bG.set_params(gold["g_params0"].astype(np.float32)); bD.set_params(gold["d_params0"].astype(np.float32))
-    gan = b.Gan(bG, bD, use_cuda_graph=False)
-    data = [gold[k] for k in ("x_real", "z_d", "z_g", "y_real", "y_fake", "y_gen")]
-    for it in range(1, 4):
-        losses = gan.step(*data); want = gold[f"losses{it}"]
-        assert np.all(np.abs(losses - want) < TOL * np.maximum(1.0, np.abs(want))), (it, losses, want)
-        assert rel_err(bD.params(), gold[f"d_params{it}"]) < 2 * TOL, it
-        assert rel_err(bG.params(), gold[f"g_params{it}"]) < 2 * TOL, it
-    gan.close(); bG.close(); bD.close()
-
-
 def test_cuda_graph_replay_equals_eager(b200):
     b, ctx = b200
     size, z, nf, n = 16, 12, 8, 8
@@ -635,3 +613,28 @@ def test_reference_program_replay_end_to_end(b200, tmp_path):
     assert out.shape == (100, 784) and np.all((out >= 0) & (out <= 1))            # sigmoid images of the 10x10 latent grid
     assert pred.shape == (30, 10) and np.allclose(pred.sum(1), 1, atol=1e-4)
     assert os.path.getsize(tmp_path / "out" / "dis_coefficients_2.bin") == 4 * 1388293
+
+
+# ------------------------------------------------------------------------------------------------
+# committed golden fixture (tests/golden): the CUDA path against fixed bytes
+# ------------------------------------------------------------------------------------------------
+def test_fp32_gan_step_matches_golden_fixture(b200):
+    """The same step against the committed fixture tests/golden/gan_step_dcgan16.npz (inputs, initial parameters, and the oracle's losses and
+    parameters after each of 3 steps; tests/golden/make_golden.py): the CUDA path is compared with fixed bytes, not with a live oracle run."""
+    import os
+    from gan_deeplearning4j_b200 import models as m
+    b, ctx = b200
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gan_step_dcgan16.npz"))
+    size, z, nf, n = 16, 12, 8, 8
+    gs, ds = m.dcgan_generator(size, z, nf, 3, lr=2e-3), m.dcgan_discriminator(size, nf, 3, lr=2e-3)
+    bG = b.Net(ctx, gs, (z,), max_batch=n, precision=b.FP32, xent_clip_eps=1e-5)
+    bD = b.Net(ctx, ds, (3, size, size), max_batch=2 * n, precision=b.FP32, xent_clip_eps=1e-5, bn_groups=2)
+    bG.set_params(gold["g_params0"].astype(np.float32)); bD.set_params(gold["d_params0"].astype(np.float32))
+    gan = b.Gan(bG, bD, use_cuda_graph=False)
+    data = [gold[k] for k in ("x_real", "z_d", "z_g", "y_real", "y_fake", "y_gen")]
+    for it in range(1, 4):
+        losses = gan.step(*data); want = gold[f"losses{it}"]
+        assert np.all(np.abs(losses - want) < TOL * np.maximum(1.0, np.abs(want))), (it, losses, want)
+        assert rel_err(bD.params(), gold[f"d_params{it}"]) < 2 * TOL, it
+        assert rel_err(bG.params(), gold[f"g_params{it}"]) < 2 * TOL, it
+    gan.close(); bG.close(); bD.close()
