@@ -146,7 +146,7 @@ def _cpu_step_rate_inproc(cfg, sample_batch, steps, warmup, budget_s, engine):
     """Times `steps` CPU steps of `sample_batch` examples.  With a budget, the sample batch is halved until the projected run fits."""
     step, desc = cpu_stepper(cfg, engine)
     data = synthetic(cfg, sample_batch, 666)
-    for _ in range(max(1, warmup)):
+    for _ in range(max(2, warmup)):          # the first step pays one-off costs (oneDNN primitive creation, page faults): never size the sample from it
         t0 = time.perf_counter(); step(data); one = time.perf_counter() - t0
     while budget_s and one * steps > budget_s and sample_batch > 4:
         sample_batch //= 2; data = synthetic(cfg, sample_batch, 666)
