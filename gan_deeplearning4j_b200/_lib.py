@@ -41,6 +41,12 @@ class ConvGeom(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("n", "h", "w", "c", "oh", "ow", "o", "kh", "kw", "sh", "sw", "ph", "pw")]
 
 
+class TestConvOpts(C.Structure):
+    """b2g_test_conv_opts: the epilogue a kernel-level parity test asks for, and the name of the kernel that ran."""
+    _fields_ = [("epi", C.c_int32), ("act", C.c_int32), ("alpha", C.c_float), ("bias", C.POINTER(C.c_float)), ("scale", C.POINTER(C.c_float)),
+                ("groups", C.c_int32), ("aux", C.POINTER(C.c_float)), ("coef", C.POINTER(C.c_float)), ("stats", C.POINTER(C.c_double)), ("kernel", C.c_char * 64)]
+
+
 _vp, _i32, _i64, _fp = C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_float)
 _pvp = C.POINTER(C.c_void_p)
 
@@ -73,6 +79,9 @@ PROTOTYPES = {
     "b2g_net_compute_gradient_and_score": (_i32, [_vp, _fp, _fp, _i32, _fp]),
     "b2g_net_get_input_gradient": (_i32, [_vp, _i32, _fp]),
     "b2g_net_fit": (_i32, [_vp, _fp, _fp, _i32, _fp]),
+    "b2g_net_get_iteration": (_i32, [_vp, C.POINTER(_i64)]),
+    "b2g_net_set_iteration": (_i32, [_vp, _i64]),
+    "b2g_net_simt_gemm_calls": (_i32, [_vp, C.POINTER(C.c_uint64)]),
     "b2g_gan_create": (_i32, [_vp, _vp, C.POINTER(GanConfig), _pvp]),
     "b2g_gan_destroy": (_i32, [_vp]),
     "b2g_gan_step": (_i32, [_vp, _fp, _fp, _fp, _fp, _fp, _fp, _i32, _fp]),
@@ -87,6 +96,7 @@ PROTOTYPES = {
     "b2g_net_average_parameters": (_i32, [_vp]),
     "b2g_ctx_allreduce_test": (_i32, [_vp, _fp, _i64]),
     "b2g_test_conv": (_i32, [_vp, _i32, _i32, _i32, C.POINTER(ConvGeom), _fp, _fp, _fp, _i32, _fp]),
+    "b2g_test_conv_ex": (_i32, [_vp, _i32, _i32, _i32, C.POINTER(ConvGeom), _fp, _fp, _fp, _i32, _fp, C.POINTER(TestConvOpts)]),
 }
 
 _lib = None

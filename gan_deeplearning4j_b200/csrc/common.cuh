@@ -11,24 +11,26 @@ namespace b2g {
 
 #define LAUNCHED() do { ++::b2g::g_launch_count; } while (0)
 
-// Programmatic dependent launch: every kernel lets its successor's CTAs be scheduled as soon as SM resources free up
-// (griddepcontrol.launch_dependents) and then waits for its predecessor to have fully completed and flushed
-// (griddepcontrol.wait) before touching memory -- the launch latency of ~100 dependent kernels per step overlaps the tail of
-// the kernel in front.  Both instructions are no-ops for a launch without the attribute.  Measured on B200 (round 1): with the
-// attribute on every launch the graph-replayed step is 5 % SLOWER (2.16 vs 2.05 ms; waiting successor CTAs hold SM slots), so it is
-// opt-in: B2G_PDL=1.
-__device__ __forceinline__ void pdl_prologue() {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-}
-extern int g_pdl_enabled;     // -1 unknown, 0 off, 1 on
+// plain stream-ordered launch (round 1 measured programmatic dependent launch on every kernel as 5 % slower; removed in round 2)
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
-  if (g_pdl_enabled < 0) { const char* e = getenv("B2G_PDL"); g_pdl_enabled = (e && e[0] == '1') ? 1 : 0; }
-  cudaLaunchConfig_t cfg{}; cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-  cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = g_pdl_enabled ? 1 : 0;
+  cudaLaunchConfig_t cfg{}; cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream; cfg.attrs = nullptr; cfg.numAttrs = 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// 128-bit fixed-point accumulation of fp32 partial sums with two 64-bit integer atomics: hi counts units of 2^-10, lo the remainder in units
+// of 2^-60.  Integer addition commutes, so a sum of per-CTA partials is bit-identical whatever order the CTAs arrive in (fp32 / fp64 atomics
+// are not), it is exact to 2^-61 per addend, and it cannot overflow below |total| ~ 9e15.  hi_lo[idx] / hi_lo[stride + idx].
+__device__ __forceinline__ void sacc_add(unsigned long long* hi_lo, size_t stride, size_t idx, float s) {
+  const double d = (double)s;
+  const long long hi = __double2ll_rn(d * 1024.0);
+  const double r = d - (double)hi * (1.0 / 1024.0);
+  const long long lo = __double2ll_rn(r * 1152921504606846976.0);
+  atomicAdd(hi_lo + idx, (unsigned long long)hi);
+  atomicAdd(hi_lo + stride + idx, (unsigned long long)lo);
+}
+__device__ __forceinline__ double sacc_read(const unsigned long long* hi_lo, size_t stride, size_t idx) {
+  return (double)(long long)hi_lo[idx] * (1.0 / 1024.0) + (double)(long long)hi_lo[stride + idx] * (1.0 / 1152921504606846976.0);
 }
 
 #define DISPATCH_PREC(prec, T, ...)                                   \

@@ -79,16 +79,20 @@ struct LayerRT {
   size_t in_elems = 0, out_elems = 0;
   ConvGeom geom{};                                             // conv-equivalent geometry (N filled per call)
   int64_t off_W = -1, n_W = 0, off_b = -1, off_gamma = -1, off_beta = -1, off_mean = -1, off_var = -1;
-  int64_t off_W_bf = -1, off_Wt_bf = -1;
+  int64_t off_W_bf = -1;                                       // bf16 operand copy [A][taps][B] (written by the updater itself); serves fprop, dgrad (MN-major tiles) and wgrad
   int64_t off_Wps_bf = -1;                                     // packed [16][9][O] weights of the tcgen05 pixel-shuffle transposed conv (<= 4 image channels)
   int wA = 0, wTaps = 0, wB = 0;                               // internal weight layout [A][taps][B]
   void* out = nullptr; bool out_alias = false;
   void* probs = nullptr;                                       // OUTPUT / LOSS: sigmoid(logits)
   uint8_t* argmax = nullptr;
   float* bn_mean = nullptr; float* bn_invstd = nullptr; float* bn_fold = nullptr;   // bn_fold: [scale | shift] for the inference-mode epilogue fold
+  float* bn_coef = nullptr;                                    // fused path: [groups][4][C] = scale, shift, mean, invstd of the latest train-mode forward
+  unsigned long long *acc_fwd = nullptr, *acc_bwd = nullptr;   // fused path: 128-bit statistics accumulators (forward: sum x, sum x^2; backward: sum dy', sum dy'*xhat)
+  bool fwd_fused = false; int fwd_groups = 1;                  // the latest train-mode forward of this BatchNorm took the accumulator path (so must its backward)
+  bool stats_by_producer = false, bwd_premul = false;          // set per pass: the producing GEMM's epilogue has already filled acc_fwd / (acc_bwd and eps = dy')
   int fused_act = ACT_IDENTITY; float fused_alpha = 0.f;       // BN followed by an ActivationLayer
   bool act_fused_into_prev = false;
-  bool needs_wt = false;                                       // a tcgen05 dgrad kernel reads the transposed bf16 copy
+  float* wg_part = nullptr; size_t wg_part_floats = 0;         // split-K partials of this layer's tcgen05 weight gradient (reduced by ONE k_reduce_multi per pass)
   bool has_gemm() const { return d.type == B2G_LAYER_CONV2D || d.type == B2G_LAYER_DECONV2D || d.type == B2G_LAYER_DENSE || d.type == B2G_LAYER_OUTPUT; }
 };
 
@@ -111,11 +115,12 @@ struct b2g_net {
   void *epsA = nullptr, *epsB = nullptr, *epsC = nullptr; size_t eps_elems = 0;
   float* scratch2 = nullptr;           // split-K / colsum partials of the side stream
   std::vector<cudaEvent_t> ev_fork, ev_done; cudaEvent_t ev_join = nullptr;
-  cudaEvent_t ev_shadow = nullptr; bool shadow_pending = false;   // transposed / packed bf16 weight copies being refreshed on the side stream
-  bool fwd_reads_wt = false;                                       // some layer's FORWARD reads a transposed / packed copy (transposed convs)
+  unsigned long long* bn_acc = nullptr; size_t bn_acc_bytes = 0;  // every BatchNorm layer's accumulators, zeroed by one memset per train-mode forward
+  unsigned* upd_ticket = nullptr;                                  // block-completion counter of the updater kernel (the last block bumps step_dev)
+  ReduceList pending{};                                            // split-K partial sums queued by this backward pass
+  uint64_t simt_gemm_calls = 0;                                    // BF16 nets: GEMM-shaped ops that ran on the SIMT kernels (skinny / unsupported shapes) -- reported, never silent
   float* scratch = nullptr; size_t scratch_floats = 0;
   float* loss_dev = nullptr;           // [8]
-  unsigned* barrier_dev = nullptr;     // grid-barrier counter of the cooperative BN kernels
   double* l2_dev = nullptr;
   void* input_grad = nullptr;          // where the last backward left d(loss)/d(input), or null
   int last_rows = 0;
@@ -215,7 +220,7 @@ static int32_t net_build(b2g_net* n, const b2g_layer_desc* layers, int32_t nl) {
       default: return fail(B2G_ERR_ARG, "layer %d: unknown type %d", i, d.type);
     }
     l.out_elems = (size_t)l.oh * l.ow * l.oc;
-    if (l.has_gemm() && n->prec == PREC_BF16) { l.off_W_bf = off_bf; off_bf += l.n_W; l.off_Wt_bf = off_bf; off_bf += l.n_W; off_bf = (off_bf + 63) / 64 * 64;
+    if (l.has_gemm() && n->prec == PREC_BF16) { l.off_W_bf = off_bf; off_bf += l.n_W; off_bf = (off_bf + 63) / 64 * 64;
       if (n->ctx->tc_ok && tc_deconv_ps_shape(l.geom) && !getenv("B2G_NO_TC_EDGE")) { l.off_Wps_bf = off_bf; off_bf += (int64_t)k_tc_deconv_ps_weight_elems(l.geom); off_bf = (off_bf + 63) / 64 * 64; } }
     h = l.oh; w = l.ow; ch = l.oc;
     n->L.push_back(l);
@@ -238,11 +243,11 @@ static int32_t net_alloc(b2g_net* n) {
   B2(dalloc(n, &n->params, sizeof(float) * n->n_params)); B2(dalloc(n, &n->grads, sizeof(float) * n->n_params));
   B2(dalloc(n, &n->st0, sizeof(float) * n->n_params)); B2(dalloc(n, &n->st1, sizeof(float) * n->n_params));
   if (n->n_shadow) B2(dalloc(n, &n->shadow, sizeof(__nv_bfloat16) * n->n_shadow));
-  B2(dalloc(n, &n->barrier_dev, sizeof(unsigned)));
+  B2(dalloc(n, &n->upd_ticket, sizeof(unsigned))); CU(cudaMemsetAsync(n->upd_ticket, 0, sizeof(unsigned), n->ctx->stream));
   B2(dalloc(n, &n->step_dev, sizeof(int))); B2(dalloc(n, &n->loss_dev, sizeof(float) * 8)); B2(dalloc(n, &n->l2_dev, sizeof(double)));
   B2(dalloc(n, &n->labels_dev, sizeof(float) * R * std::max<size_t>(1, n->L.back().out_elems)));
   B2(dalloc(n, (char**)&n->input, ts * R * n->in_elems));
-  size_t max_act = n->in_elems, scratch = 1 << 16, max_w = 0;
+  size_t max_act = n->in_elems, scratch = 1 << 16, max_w = 0, bn_acc_words = 0;
   for (auto& l : n->L) {
     max_act = std::max(max_act, std::max(l.in_elems, l.out_elems));
     bool alias = l.act_fused_into_prev || l.d.type == B2G_LAYER_LOSS ||
@@ -252,7 +257,8 @@ static int32_t net_alloc(b2g_net* n) {
     if (!alias) B2(dalloc(n, (char**)&l.out, ts * R * l.out_elems));
     if (l.d.type == B2G_LAYER_OUTPUT || l.d.type == B2G_LAYER_LOSS) B2(dalloc(n, (char**)&l.probs, ts * R * l.out_elems));
     if (l.d.type == B2G_LAYER_MAXPOOL) B2(dalloc(n, &l.argmax, (size_t)R * l.out_elems));
-    if (l.d.type == B2G_LAYER_BATCHNORM) { B2(dalloc(n, &l.bn_fold, sizeof(float) * 2 * l.oc)); B2(dalloc(n, &l.bn_mean, sizeof(float) * G * l.oc)); B2(dalloc(n, &l.bn_invstd, sizeof(float) * G * l.oc)); scratch = std::max(scratch, k_bn_scratch_floats(l.oc, G)); }
+    if (l.d.type == B2G_LAYER_BATCHNORM) { B2(dalloc(n, &l.bn_fold, sizeof(float) * 2 * l.oc)); B2(dalloc(n, &l.bn_mean, sizeof(float) * G * l.oc)); B2(dalloc(n, &l.bn_invstd, sizeof(float) * G * l.oc)); scratch = std::max(scratch, k_bn_scratch_floats(l.oc, G));
+      if (k_bn_vec_ok(n->prec, l.oc)) { B2(dalloc(n, &l.bn_coef, sizeof(float) * 4 * G * l.oc)); bn_acc_words += 2 * k_bn_acc_elems(l.oc, G); } }
     if (l.has_gemm()) {
       ConvGeom g = l.geom; g.N = R;
       scratch = std::max(scratch, std::max(k_simt_wgrad_scratch_floats(g), k_tc_wgrad_scratch_floats(g)));
@@ -260,12 +266,17 @@ static int32_t net_alloc(b2g_net* n) {
       scratch = std::max(scratch, k_tc_edge_wgrad_scratch_floats(g));
       scratch = std::max(scratch, k_colsum_scratch_floats(std::max(l.oc, l.ic)));
       max_w = std::max(max_w, (size_t)l.n_W);
-      l.needs_wt = n->prec == PREC_BF16 && n->ctx->tc_ok && tc_dgrad_supported(g) && !edge_deconv_small_c_supported(g);
-      // dense layers (1x1 geometry): the input gradient dx = dy . W is the tcgen05 fprop kernel on the transposed weight copy
-      if (n->prec == PREC_BF16 && n->ctx->tc_ok && g.KH == 1 && g.KW == 1 && g.H == 1 && g.W == 1 && !dense_small_o_supported(g)) {
-        ConvGeom t = g; t.C = g.O; t.O = g.C; if (tc_fprop_supported(t)) l.needs_wt = true;
+      // split-K partials of the tcgen05 weight gradients stay in a per-layer region until the pass's single k_reduce_multi launch
+      if (n->prec == PREC_BF16 && n->ctx->tc_ok && !l.d.frozen) {
+        l.wg_part_floats = std::max(k_tc_wgrad_scratch_floats(g), k_tc_edge_wgrad_scratch_floats(g));
+        if (l.wg_part_floats) B2(dalloc(n, &l.wg_part, sizeof(float) * l.wg_part_floats));
       }
     }
+  }
+  if (bn_acc_words) {
+    n->bn_acc_bytes = sizeof(unsigned long long) * bn_acc_words; B2(dalloc(n, &n->bn_acc, n->bn_acc_bytes));
+    unsigned long long* q = n->bn_acc;
+    for (auto& l : n->L) if (l.bn_coef) { const size_t w = k_bn_acc_elems(l.oc, G); l.acc_fwd = q; l.acc_bwd = q + w; q += 2 * w; }
   }
   n->eps_elems = (size_t)R * max_act;
   B2(dalloc(n, (char**)&n->epsA, ts * n->eps_elems)); B2(dalloc(n, (char**)&n->epsB, ts * n->eps_elems)); B2(dalloc(n, (char**)&n->epsC, ts * n->eps_elems));
@@ -286,8 +297,7 @@ static int32_t net_alloc(b2g_net* n) {
   }
   n->ev_fork.resize(n->L.size()); n->ev_done.resize(n->L.size());
   for (size_t i = 0; i < n->L.size(); ++i) { CU(cudaEventCreateWithFlags(&n->ev_fork[i], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&n->ev_done[i], cudaEventDisableTiming)); }
-  CU(cudaEventCreateWithFlags(&n->ev_join, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&n->ev_shadow, cudaEventDisableTiming));
-  for (auto& l : n->L) if (l.d.type == B2G_LAYER_DECONV2D && (l.needs_wt || l.off_Wps_bf >= 0)) n->fwd_reads_wt = true;
+  CU(cudaEventCreateWithFlags(&n->ev_join, cudaEventDisableTiming));
   n->stage_floats = std::max((size_t)R * max_act, std::max((size_t)n->n_params, max_w)); B2(dalloc(n, &n->stage_f32, sizeof(float) * n->stage_floats));
   return 0;
 }
@@ -305,7 +315,7 @@ static int32_t net_init_params_and_updater(b2g_net* n) {
       if (d.frozen) return;      // FrozenLayer: no update, no l2 decay, no l2 score (calcL2() == 0)
       UpdSeg sg{}; sg.off = off; sg.len = len; sg.kind = noop ? 3 : updater_kind(d.updater);
       sg.lr = d.lr; sg.b1 = d.beta1; sg.b2 = d.beta2; sg.eps = d.eps; sg.l2 = weight ? d.l2 : 0.f; sg.clip = n->cfg.grad_clip; sg.div_mb = noop ? 0 : 1;
-      sg.off_bf = (weight && l.off_W_bf >= 0) ? l.off_W_bf : -1; sg.off_bft = -1; n->segs.push_back(sg);
+      sg.off_bf = (weight && l.off_W_bf >= 0) ? l.off_W_bf : -1; sg.off_ps = (weight && l.off_Wps_bf >= 0) ? l.off_Wps_bf : -1; sg.ps_O = l.geom.O; sg.ps_C = l.geom.C; n->segs.push_back(sg);
       if (!noop && sg.kind == 1) for (int64_t i = 0; i < len; ++i) h0[off + i] = d.eps;     // RmsPropUpdater cache initialised to epsilon
       if (weight && d.l2 != 0.f) { l2o.push_back(off); l2l.push_back(len); l2c.push_back(0.5f * d.l2); }
     };
@@ -345,21 +355,17 @@ static int32_t net_init_params_and_updater(b2g_net* n) {
   return 0;
 }
 
-// bf16 operand copies of every GEMM weight (straight, and transposed where a tcgen05 dgrad reads it); no-op in FP32 mode.
-// After an updater pass the straight copy has already been written by the updater kernel itself.
-static void net_refresh_shadow(b2g_net* n, int only_layer = -1, bool straight_done = false, cudaStream_t st = nullptr) {
+// bf16 operand copy of every GEMM weight (plus the packed pixel-shuffle operand of the <= 4-channel transposed conv); no-op in FP32 mode.
+// Only setParam / setParams / parameter averaging need it: after an updater pass both were written by the updater kernel itself.
+static void net_refresh_shadow(b2g_net* n, int only_layer = -1) {
   if (n->prec != PREC_BF16) return;
-  if (!st) st = n->ctx->stream;
-  if (n->shadow_pending && st == n->ctx->stream) { cudaStreamWaitEvent(st, n->ev_shadow, 0); n->shadow_pending = false; }     // never two refreshes in flight
+  cudaStream_t st = n->ctx->stream;
   for (size_t i = 0; i < n->L.size(); ++i) { auto& l = n->L[i];
     if (!l.has_gemm() || (only_layer >= 0 && (int)i != only_layer)) continue;
     if (l.off_Wps_bf >= 0) k_pack_deconv_ps(n->params + l.off_W, n->shadow + l.off_Wps_bf, l.geom.O, l.geom.C, st);
-    if (straight_done && !l.needs_wt) continue;
-    k_weight_shadow(n->params + l.off_W, straight_done ? nullptr : n->shadow + l.off_W_bf, l.needs_wt ? n->shadow + l.off_Wt_bf : nullptr, l.wA, l.wTaps, l.wB, st);
+    k_cast_f32_to_bf16(n->params + l.off_W, n->shadow + l.off_W_bf, (size_t)l.n_W, st);
   }
 }
-// consumers of the transposed / packed copies order themselves after a refresh that is still running on the side stream
-static inline void wait_shadow(b2g_net* n, cudaStream_t consumer) { if (n->shadow_pending) { cudaStreamWaitEvent(consumer, n->ev_shadow, 0); n->shadow_pending = false; } }
 
 // ------------------------------------------------------------------ forward / backward -------------------
 struct FwdOpts { int rows; int groups; bool train; bool update_running; void* out_override; };
@@ -370,98 +376,125 @@ static const void* w_ptr(const b2g_net* n, const LayerRT& l, int* wprec) {
 }
 
 // tcgen05 versions of the <= 4-image-channel layers (B2G_NO_TC_EDGE=1 keeps the SIMT kernels of kernels_edge.cu)
-static bool tc_edge_on(const b2g_net* n) { static int on = -1; if (on < 0) on = getenv("B2G_NO_TC_EDGE") ? 0 : 1; return on && n->prec == PREC_BF16 && n->ctx->tc_ok; }
+static inline bool tc_on(const b2g_net* n) { return n->prec == PREC_BF16 && n->ctx->tc_ok; }
+static bool tc_edge_on(const b2g_net* n) { static int on = -1; if (on < 0) on = getenv("B2G_NO_TC_EDGE") ? 0 : 1; return on && tc_on(n); }
 static inline cudaStream_t fstream(const b2g_net* n) { return n->fwd_stream ? n->fwd_stream : n->ctx->stream; }
-static int32_t gemm_fprop(b2g_net* n, const LayerRT& l, const ConvGeom& g, const void* x, const float* bias, void* out, int act, float alpha, const float* scale = nullptr) {
+// A BF16 net whose GEMM-shaped op has no tcgen05 kernel runs it on the SIMT kernels: counted (b2g_net_simt_gemm_calls, bench.py prints
+// it per step) so that a shape falling off the tensor-core path is visible, never silent.  The by-design skinny layers (<= 4 units on one
+// side, K = 100 G-first) are counted too.
+static inline void note_simt(b2g_net* n) { if (n->prec == PREC_BF16) ++n->simt_gemm_calls; }
+
+// `scale` (inference-mode BatchNorm folded into the epilogue) must be honoured; `fuse` (EPI_STATS / EPI_BNBWD / EPI_ACTBWD) is opportunistic:
+// *fused tells the caller whether the kernel that ran did it -- if not, the unfused elementwise kernels follow.
+static int32_t gemm_fprop(b2g_net* n, const LayerRT& l, const ConvGeom& g, const void* x, const float* bias, void* out, int act, float alpha,
+                          const float* scale = nullptr, const TcEpi* fuse = nullptr, bool* fused = nullptr) {
   cudaStream_t s = fstream(n); int wp; const void* w = w_ptr(n, l, &wp);
+  if (fused) *fused = false;
   if (scale) {       // folded epilogue: tensor-core or SIMT GEMM kernels only
-    if (n->prec == PREC_BF16 && n->ctx->tc_ok && tc_fprop_supported(g)) return k_tc_fprop(g, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)out, act, alpha, s, scale) == 0 ? 0 : fail(B2G_ERR_CUDA, "tcgen05 fprop launch failed");
-    k_simt_fprop(n->prec, wp, g, x, w, bias, out, act, alpha, s, scale); return 0;
+    if (tc_on(n) && tc_fprop_supported(g)) { TcEpi e{}; e.mode = EPI_PLAIN; e.scale = scale; return k_tc_fprop(g, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)out, act, alpha, s, &e) == 0 ? 0 : fail(B2G_ERR_CUDA, "tcgen05 fprop launch failed"); }
+    note_simt(n); k_simt_fprop(n->prec, wp, g, x, w, bias, out, act, alpha, s, scale); return 0;
   }
   if (tc_edge_on(n) && tc_edge_conv_supported(g) && k_tc_edge_conv(g, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)out, act, alpha, s) == 0) return 0;
-  if (edge_conv_small_cin_supported(g)) { k_edge_conv_small_cin(n->prec, wp, g, x, w, bias, out, act, alpha, s); return 0; }
-  if (dense_small_o_supported(g)) { k_dense_small_o_fwd(n->prec, wp, g, x, w, bias, out, act, alpha, s); return 0; }
-  if (n->prec == PREC_BF16 && n->ctx->tc_ok && tc_fprop_supported(g)) {
+  if (edge_conv_small_cin_supported(g)) { note_simt(n); k_edge_conv_small_cin(n->prec, wp, g, x, w, bias, out, act, alpha, s); return 0; }
+  if (dense_small_o_supported(g)) { note_simt(n); k_dense_small_o_fwd(n->prec, wp, g, x, w, bias, out, act, alpha, s); return 0; }
+  if (tc_on(n) && tc_fprop_supported(g)) {
+    if (fuse && k_tc_fprop(g, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)out, act, alpha, s, fuse) == 0) { if (fused) *fused = true; return 0; }
     if (k_tc_fprop(g, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)out, act, alpha, s) == 0) return 0;
     return fail(B2G_ERR_CUDA, "tcgen05 fprop launch failed");
   }
-  k_simt_fprop(n->prec, wp, g, x, w, bias, out, act, alpha, s); return 0;
+  note_simt(n); k_simt_fprop(n->prec, wp, g, x, w, bias, out, act, alpha, s); return 0;
 }
-static int32_t gemm_dgrad(b2g_net* n, const LayerRT& l, const ConvGeom& g, const void* dy, const float* bias, void* dx, int act, float alpha, const float* scale = nullptr) {
+static int32_t gemm_dgrad(b2g_net* n, const LayerRT& l, const ConvGeom& g, const void* dy, const float* bias, void* dx, int act, float alpha,
+                          const float* scale = nullptr, const TcEpi* fuse = nullptr, bool* fused = nullptr) {
   cudaStream_t s = fstream(n); int wp; const void* w = w_ptr(n, l, &wp);
+  if (fused) *fused = false;
   if (scale) {
-    if (n->prec == PREC_BF16 && n->ctx->tc_ok && l.needs_wt && tc_dgrad_supported(g)) return k_tc_dgrad(g, (const __nv_bfloat16*)dy, n->shadow + l.off_Wt_bf, bias, (__nv_bfloat16*)dx, act, alpha, s, scale) == 0 ? 0 : fail(B2G_ERR_CUDA, "tcgen05 dgrad launch failed");
-    k_simt_dgrad(n->prec, wp, g, dy, w, bias, dx, act, alpha, s, scale); return 0;
+    if (tc_on(n) && tc_dgrad_supported(g) && !edge_deconv_small_c_supported(g)) { TcEpi e{}; e.mode = EPI_PLAIN; e.scale = scale; return k_tc_dgrad(g, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)dx, act, alpha, s, &e) == 0 ? 0 : fail(B2G_ERR_CUDA, "tcgen05 dgrad launch failed"); }
+    note_simt(n); k_simt_dgrad(n->prec, wp, g, dy, w, bias, dx, act, alpha, s, scale); return 0;
   }
   if (tc_edge_on(n) && l.off_Wps_bf >= 0 && tc_deconv_ps_supported(g)) {
-    if (k_tc_deconv_ps(g, (const __nv_bfloat16*)dy, n->shadow + l.off_Wps_bf, bias, (__nv_bfloat16*)dx, act, alpha, s) == 0) return 0;
+    const TcEpi* f = (fuse && fuse->mode == EPI_ACTBWD) ? fuse : nullptr;
+    if (k_tc_deconv_ps(g, (const __nv_bfloat16*)dy, n->shadow + l.off_Wps_bf, bias, (__nv_bfloat16*)dx, act, alpha, s, f) == 0) { if (fused) *fused = f != nullptr; return 0; }
     return fail(B2G_ERR_CUDA, "tcgen05 pixel-shuffle deconv launch failed");
   }
-  if (edge_deconv_small_c_supported(g)) { k_edge_deconv_small_c(n->prec, wp, g, dy, w, bias, dx, act, alpha, s); return 0; }
-  if (dense_small_o_supported(g) && !bias && act == ACT_IDENTITY) { k_dense_small_o_dgrad(n->prec, wp, g, dy, w, dx, s); return 0; }
-  if (dense_small_k_supported(g) && !(n->prec == PREC_BF16 && n->ctx->tc_ok && g.O % 64 == 0)) { k_dense_small_k_dgrad(n->prec, wp, g, dy, w, bias, dx, act, alpha, s); return 0; }
-  if (n->prec == PREC_BF16 && n->ctx->tc_ok && l.needs_wt && g.KH == 1 && g.KW == 1 && g.H == 1 && g.W == 1) {
+  if (edge_deconv_small_c_supported(g)) { note_simt(n); k_edge_deconv_small_c(n->prec, wp, g, dy, w, bias, dx, act, alpha, s); return 0; }
+  if (dense_small_o_supported(g) && !bias && act == ACT_IDENTITY) { note_simt(n); k_dense_small_o_dgrad(n->prec, wp, g, dy, w, dx, s); return 0; }
+  if (dense_small_k_supported(g) && !(tc_on(n) && g.O % 64 == 0)) { note_simt(n); k_dense_small_k_dgrad(n->prec, wp, g, dy, w, bias, dx, act, alpha, s); return 0; }
+  if (tc_on(n) && g.KH == 1 && g.KW == 1 && g.H == 1 && g.W == 1) {
+    // dense layer: dx = dy . W is the fprop kernel reading the layer's own [nOut][nIn] weight as an MN-major operand (reduction over nOut)
     ConvGeom t = g; t.C = g.O; t.O = g.C;
     if (tc_fprop_supported(t)) {
-      if (k_tc_fprop(t, (const __nv_bfloat16*)dy, n->shadow + l.off_Wt_bf, bias, (__nv_bfloat16*)dx, act, alpha, s) == 0) return 0;
+      if (fuse && k_tc_fprop(t, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)dx, act, alpha, s, fuse, 1) == 0) { if (fused) *fused = true; return 0; }
+      if (k_tc_fprop(t, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)dx, act, alpha, s, nullptr, 1) == 0) return 0;
       return fail(B2G_ERR_CUDA, "tcgen05 dense dgrad launch failed");
     }
   }
-  if (n->prec == PREC_BF16 && n->ctx->tc_ok && l.needs_wt && tc_dgrad_supported(g)) {
-    if (k_tc_dgrad(g, (const __nv_bfloat16*)dy, n->shadow + l.off_Wt_bf, bias, (__nv_bfloat16*)dx, act, alpha, s) == 0) return 0;
+  if (tc_on(n) && tc_dgrad_supported(g)) {
+    if (fuse && k_tc_dgrad(g, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)dx, act, alpha, s, fuse) == 0) { if (fused) *fused = true; return 0; }
+    if (k_tc_dgrad(g, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)dx, act, alpha, s) == 0) return 0;
     return fail(B2G_ERR_CUDA, "tcgen05 dgrad launch failed");
   }
-  k_simt_dgrad(n->prec, wp, g, dy, w, bias, dx, act, alpha, s); return 0;
+  note_simt(n); k_simt_dgrad(n->prec, wp, g, dy, w, bias, dx, act, alpha, s); return 0;
 }
-static int32_t gemm_wgrad(b2g_net* n, const LayerRT& l, const ConvGeom& g, const void* x, const void* dy, float* dw, cudaStream_t s, float* scratch, float* db = nullptr, bool* bias_done = nullptr) {
-  if (tc_edge_on(n) && tc_edge_wgrad_supported(g)) { const int r = k_tc_edge_wgrad(g, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw, db, scratch, n->scratch_floats, 0, s); if (r >= 0) { if (bias_done) *bias_done = r == 1; return 0; } }
-  if (edge_wgrad_small_cin_supported(g)) { k_edge_wgrad_small_cin(n->prec, g, x, dy, dw, scratch, 0, s); return 0; }
-  if (dense_small_o_supported(g)) { k_dense_small_o_wgrad(n->prec, g, x, dy, dw, scratch, 0, s); return 0; }
-  if (dense_small_k_supported(g) && !(n->prec == PREC_BF16 && n->ctx->tc_ok && tc_wgrad_supported(g))) { k_dense_small_k_wgrad(n->prec, g, x, dy, dw, s); return 0; }
-  if (n->prec == PREC_BF16 && n->ctx->tc_ok && tc_wgrad_supported(g)) {
-    if (k_tc_wgrad(g, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw, scratch, n->scratch_floats, 0, s) == 0) return 0;
+static int32_t gemm_wgrad(b2g_net* n, LayerRT& l, const ConvGeom& g, const void* x, const void* dy, float* dw, cudaStream_t s, float* scratch, float* db = nullptr, bool* bias_done = nullptr) {
+  if (tc_edge_on(n) && tc_edge_wgrad_supported(g) && l.wg_part) { const int r = k_tc_edge_wgrad(g, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw, db, l.wg_part, l.wg_part_floats, 0, s, &n->pending); if (r >= 0) { if (bias_done) *bias_done = r == 1; return 0; } }
+  if (edge_wgrad_small_cin_supported(g)) { note_simt(n); k_edge_wgrad_small_cin(n->prec, g, x, dy, dw, scratch, 0, s); return 0; }
+  if (dense_small_o_supported(g)) { note_simt(n); k_dense_small_o_wgrad(n->prec, g, x, dy, dw, scratch, 0, s); return 0; }
+  if (dense_small_k_supported(g) && !(tc_on(n) && tc_wgrad_supported(g))) { note_simt(n); k_dense_small_k_wgrad(n->prec, g, x, dy, dw, s); return 0; }
+  if (tc_on(n) && tc_wgrad_supported(g) && l.wg_part) {
+    if (k_tc_wgrad(g, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw, l.wg_part, l.wg_part_floats, 0, s, &n->pending) == 0) return 0;
     return fail(B2G_ERR_CUDA, "tcgen05 wgrad launch failed");
   }
-  k_simt_wgrad(n->prec, g, x, dy, dw, scratch, n->scratch_floats, 0, s); return 0;
+  note_simt(n); k_simt_wgrad(n->prec, g, x, dy, dw, scratch, n->scratch_floats, 0, s); return 0;
 }
 
 // Runs layers [0, L) on `in` (T NHWC, rows examples). Returns pointer to the final activations.
 static int32_t net_forward(b2g_net* n, const void* in, const FwdOpts& o, const void** result) {
   cudaStream_t s = fstream(n);
-  if (n->fwd_reads_wt) wait_shadow(n, s);
   if (o.rows > n->max_rows || o.rows < 1) return fail(B2G_ERR_SHAPE, "batch %d outside [1, max_batch=%d]", o.rows, n->max_rows);
   if (o.groups < 1 || o.rows % o.groups) return fail(B2G_ERR_SHAPE, "batch %d not divisible into %d groups", o.rows, o.groups);
   const int R = o.rows; const void* cur = in;
   n->last_rows = R;
+  // every BatchNorm accumulator of the pass (forward statistics and the backward reductions that follow) starts from zero: one memset node
+  if (o.train && n->bn_acc) CU(cudaMemsetAsync(n->bn_acc, 0, n->bn_acc_bytes, s));
+  static int fold_bn = -1; if (fold_bn < 0) { const char* e = getenv("B2G_FOLD_BN"); fold_bn = (e && e[0] == '0') ? 0 : 1; }
+  static int fuse_bn = -1; if (fuse_bn < 0) { const char* e = getenv("B2G_FUSE_BN"); fuse_bn = (e && e[0] == '0') ? 0 : 1; }
   for (size_t i = 0; i < n->L.size(); ++i) {
     LayerRT& l = n->L[i]; const b2g_layer_desc& d = l.d;
     void* out = l.out;
     if (i + 1 == n->L.size() && o.out_override && !l.out_alias) out = o.out_override;
     const float* bias = l.off_b >= 0 ? n->params + l.off_b : nullptr;
+    const bool gemm_then_bn = (d.type == B2G_LAYER_CONV2D || d.type == B2G_LAYER_DECONV2D || d.type == B2G_LAYER_DENSE) && i + 1 < n->L.size() && n->L[i + 1].d.type == B2G_LAYER_BATCHNORM;
+    // a 1x1-input deconv is computed as the 1x1 problem with taps*C output channels: its columns are not the BatchNorm's channels
+    const bool remapped = d.type == B2G_LAYER_DECONV2D && l.geom.KH == 1 && l.geom.C != l.oc;
     // inference-mode (or frozen) BatchNorm right after a linear conv / deconv / dense: fold it, and its activation, into that GEMM's epilogue
-    static int fold_bn = -1; if (fold_bn < 0) { const char* e = getenv("B2G_FOLD_BN"); fold_bn = (e && e[0] == '0') ? 0 : 1; }
-    if (fold_bn && (d.type == B2G_LAYER_CONV2D || d.type == B2G_LAYER_DECONV2D || d.type == B2G_LAYER_DENSE) && d.act == B2G_ACT_IDENTITY && i + 1 < n->L.size() &&
-        n->L[i + 1].d.type == B2G_LAYER_BATCHNORM && (!o.train || n->L[i + 1].d.frozen) && !(i + 2 == n->L.size() && o.out_override)) {
+    if (fold_bn && gemm_then_bn && d.act == B2G_ACT_IDENTITY && (!o.train || n->L[i + 1].d.frozen) && !(i + 2 == n->L.size() && o.out_override) && !remapped) {
       LayerRT& bn = n->L[i + 1];
       ConvGeom g = l.geom; g.N = R;
-      const bool remapped = d.type == B2G_LAYER_DECONV2D && g.KH == 1 && g.C != l.oc;     // 1x1-input deconv viewed as taps*C channels: no fold
-      if (!remapped) {
-        k_bn_fold(n->params + bn.off_mean, n->params + bn.off_var, n->params + bn.off_gamma, n->params + bn.off_beta, bias, bn.oc, bn.d.bn_eps, bn.bn_fold, bn.bn_fold + bn.oc, s);
-        if (d.type == B2G_LAYER_DECONV2D) B2(gemm_dgrad(n, l, g, cur, bn.bn_fold + bn.oc, bn.out, bn.fused_act, bn.fused_alpha, bn.bn_fold));
-        else B2(gemm_fprop(n, l, g, cur, bn.bn_fold + bn.oc, bn.out, bn.fused_act, bn.fused_alpha, bn.bn_fold));
-        cur = bn.out; ++i; continue;
-      }
+      k_bn_fold(n->params + bn.off_mean, n->params + bn.off_var, n->params + bn.off_gamma, n->params + bn.off_beta, bias, bn.oc, bn.d.bn_eps, bn.bn_fold, bn.bn_fold + bn.oc, s);
+      if (d.type == B2G_LAYER_DECONV2D) B2(gemm_dgrad(n, l, g, cur, bn.bn_fold + bn.oc, bn.out, bn.fused_act, bn.fused_alpha, bn.bn_fold));
+      else B2(gemm_fprop(n, l, g, cur, bn.bn_fold + bn.oc, bn.out, bn.fused_act, bn.fused_alpha, bn.bn_fold));
+      cur = bn.out; ++i; continue;
+    }
+    // train-mode BatchNorm right after a GEMM: its batch statistics come out of the GEMM's epilogue (kernels_tc.cu EPI_STATS)
+    TcEpi st{}; const TcEpi* fuse = nullptr; bool fused = false;
+    if (fuse_bn && gemm_then_bn && o.train && !n->L[i + 1].d.frozen && n->L[i + 1].bn_coef && !remapped && tc_on(n)) {
+      st.mode = EPI_STATS; st.acc = n->L[i + 1].acc_fwd; st.imgs_per_group = R / o.groups; fuse = &st;
     }
     switch (d.type) {
-      case B2G_LAYER_CONV2D: case B2G_LAYER_DENSE: case B2G_LAYER_OUTPUT: { ConvGeom g = l.geom; g.N = R; B2(gemm_fprop(n, l, g, cur, bias, out, d.act, d.act_alpha)); } break;
-      case B2G_LAYER_DECONV2D: { ConvGeom g = l.geom; g.N = R; B2(gemm_dgrad(n, l, g, cur, bias, out, d.act, d.act_alpha)); } break;
+      case B2G_LAYER_CONV2D: case B2G_LAYER_DENSE: case B2G_LAYER_OUTPUT: { ConvGeom g = l.geom; g.N = R; B2(gemm_fprop(n, l, g, cur, bias, out, d.act, d.act_alpha, nullptr, fuse, &fused)); } break;
+      case B2G_LAYER_DECONV2D: { ConvGeom g = l.geom; g.N = R; B2(gemm_dgrad(n, l, g, cur, bias, out, d.act, d.act_alpha, nullptr, fuse, &fused)); } break;
       case B2G_LAYER_BATCHNORM: {
         int rows_pg = (R / o.groups) * l.oh * l.ow;
         const bool bn_train = o.train && !d.frozen;      // FrozenLayer always activates in test mode
-        if (bn_train && k_bn_fused_ok(n->prec, l.oc, o.groups) &&
-            k_bn_fwd_fused(cur, out, rows_pg, l.oc, o.groups, n->scratch, l.bn_mean, l.bn_invstd, n->params + l.off_gamma, n->params + l.off_beta, l.fused_act, l.fused_alpha, d.bn_eps,
-                           n->params + l.off_mean, n->params + l.off_var, o.update_running ? n->grads + l.off_mean : nullptr, o.update_running ? n->grads + l.off_var : nullptr, d.bn_decay,
-                           n->barrier_dev, s) == 0) break;
+        l.fwd_fused = false;
+        if (bn_train && l.bn_coef && fuse_bn) {
+          if (!l.stats_by_producer) k_bn_stats_acc(cur, rows_pg, l.oc, o.groups, l.acc_fwd, s);
+          k_bn_apply_acc(cur, out, rows_pg, l.oc, o.groups, l.acc_fwd, n->params + l.off_gamma, n->params + l.off_beta, l.fused_act, l.fused_alpha, d.bn_eps, l.bn_coef,
+                         n->params + l.off_mean, n->params + l.off_var, o.update_running ? n->grads + l.off_mean : nullptr, o.update_running ? n->grads + l.off_var : nullptr, d.bn_decay, s);
+          l.fwd_fused = true; l.stats_by_producer = false; l.fwd_groups = o.groups;
+          break;
+        }
         if (bn_train) k_bn_stats(n->prec, cur, rows_pg, l.oc, o.groups, n->scratch, l.bn_mean, l.bn_invstd, d.bn_eps, n->params + l.off_mean, n->params + l.off_var,
                                 o.update_running ? n->grads + l.off_mean : nullptr, o.update_running ? n->grads + l.off_var : nullptr, d.bn_decay, s);
         else k_bn_prep_infer(n->params + l.off_mean, n->params + l.off_var, l.oc, o.groups, d.bn_eps, l.bn_mean, l.bn_invstd, s);
@@ -474,6 +507,7 @@ static int32_t net_forward(b2g_net* n, const void* in, const FwdOpts& o, const v
       case B2G_LAYER_FF_TO_CNN: if (l.out_alias) out = (void*)cur; else k_permute(n->prec, cur, out, R, l.oc, l.oh * l.ow, 1, s); break;
       case B2G_LAYER_CNN_TO_FF: if (l.out_alias) out = (void*)cur; else k_permute(n->prec, cur, out, R, l.ic, l.ih * l.iw, 0, s); break;
     }
+    if (fuse) n->L[i + 1].stats_by_producer = fused;
     if (l.out_alias) l.out = out;
     cur = out;
   }
@@ -483,18 +517,26 @@ static int32_t net_forward(b2g_net* n, const void* in, const FwdOpts& o, const v
 }
 
 // B2G_AR_OVERLAP=1: two-bucket gradient all-reduce, the tail bucket (layers whose gradients are final first) travels on a comm stream while
-// backward continues.  Opt-in: measured on 2 x B200 it is bit-identical (tools/dp_check.py) but only 0.6 % faster (1.412 vs 1.421 ms per
-// step) -- the all-reduce cost at this size is launch / rank-skew latency, not transfer time -- and it was not exercised on 4 / 8 GPUs.
+// backward continues.
 static bool ar_overlap_on(const b2g_net* n) {
   static int on = -1; if (on < 0) { const char* e = getenv("B2G_AR_OVERLAP"); on = (e && e[0] == '1') ? 1 : 0; }
   return on && n->ctx->comm && n->ctx->world > 1 && n->grad_allreduce && n->ar_split_layer > 0;
 }
+static void flush_pending_reduce(b2g_net* n, cudaStream_t s2) { if (n->pending.count) { k_reduce_multi(n->pending, s2); n->pending.count = 0; } }
+
 // Back-propagates eps (T, w.r.t. the logits when the last layer is OUTPUT/LOSS: dz from k_xent) through the net.
-// `eps` must live in n->epsA or be an external buffer; uses epsA/epsB ping-pong.
-static int32_t net_backward(b2g_net* n, const void* net_in, void* eps, int rows, int groups, bool want_wgrad, bool need_input_grad, bool allreduce_follows = false) {
+// `eps` must live in n->epsA or be an external buffer; uses epsA/epsB/epsC in rotation.
+// input_act: when the caller will multiply the input gradient by act'(a) of the layer that FED this net (the generator's tanh in the stacked
+// gan graph, J:228-310), the first layer's dgrad epilogue can do it (EPI_ACTBWD): *input_act_done reports whether it did.
+// top_act_done: the epsilon handed in has already been multiplied by the last layer's act' (the mirror image of the above).
+static int32_t net_backward(b2g_net* n, const void* net_in, void* eps, int rows, int groups, bool want_wgrad, bool need_input_grad, bool allreduce_follows = false,
+                            const TcEpi* input_act = nullptr, bool* input_act_done = nullptr, bool top_act_done = false) {
   cudaStream_t s = n->ctx->stream, s2 = n->ctx->side; const int R = rows;
-  wait_shadow(n, s);
   void* cur = eps;
+  if (input_act_done) *input_act_done = false;
+  static int fuse_bn = -1; if (fuse_bn < 0) { const char* e = getenv("B2G_FUSE_BN"); fuse_bn = (e && e[0] == '0') ? 0 : 1; }
+  static int fuse_act = -1; if (fuse_act < 0) { const char* e = getenv("B2G_FUSE_ACTBWD"); fuse_act = (e && e[0] == '0') ? 0 : 1; }
+  n->pending.count = 0;
   // Three epsilon buffers in rotation.  Weight gradients are forked to the side stream (they only READ delta and the layer
   // input), so the input-gradient chain -- the critical path -- never waits for them; a buffer still being read by a
   // forked wgrad is not overwritten before that wgrad's event has fired.
@@ -513,6 +555,30 @@ static int32_t net_backward(b2g_net* n, const void* net_in, void* eps, int rows,
     cudaEventRecord(n->ev_done[li], s2);
     for (int k = 0; k < 3; ++k) if (bufs[k] == delta) reader[k] = n->ev_done[li];
   };
+  std::vector<char> act_done(n->L.size(), 0);        // layer i's own activation derivative was applied by the dgrad epilogue of the layer above
+  if (top_act_done) act_done.back() = 1;
+  // what the dgrad of GEMM layer i can fold into its epilogue: the BatchNorm-backward reductions of the BatchNorm(+activation) below it, or the
+  // activation derivative of the GEMM layer below it / of the layer that fed the net
+  auto pick_fuse = [&](int i, TcEpi* e, int* target) -> bool {
+    *target = -1;
+    if (!tc_on(n)) return false;
+    int k = i - 1; while (k >= 0 && n->L[k].act_fused_into_prev) --k;
+    if (k < 0) { if (input_act && fuse_act) { *e = *input_act; *target = -2; return true; } return false; }
+    LayerRT& b = n->L[k];
+    if (fuse_bn && b.d.type == B2G_LAYER_BATCHNORM && b.fwd_fused && !b.d.frozen && b.fwd_groups == groups) {
+      e->mode = EPI_BNBWD; e->acc = b.acc_bwd; e->imgs_per_group = R / groups; e->aux = (const __nv_bfloat16*)(k == 0 ? net_in : n->L[k - 1].out); e->coef = b.bn_coef;
+      e->act = b.fused_act; e->alpha = b.fused_alpha; *target = k; return true;
+    }
+    if (fuse_act && k == i - 1 && b.has_gemm() && b.d.act != B2G_ACT_IDENTITY && b.d.type != B2G_LAYER_OUTPUT) {
+      e->mode = EPI_ACTBWD; e->aux = (const __nv_bfloat16*)b.out; e->act = b.d.act; e->alpha = b.d.act_alpha; *target = k; return true;
+    }
+    return false;
+  };
+  auto note_fused = [&](int target, const TcEpi& e, bool fused) {
+    if (!fused || target == -1) return;
+    if (target == -2) { if (input_act_done) *input_act_done = true; return; }
+    if (e.mode == EPI_BNBWD) n->L[target].bwd_premul = true; else act_done[target] = 1;
+  };
   for (int i = (int)n->L.size() - 1; i >= 0; --i) {
     LayerRT& l = n->L[i]; const b2g_layer_desc& d = l.d;
     const void* lin = i == 0 ? net_in : n->L[i - 1].out;
@@ -524,7 +590,7 @@ static int32_t net_backward(b2g_net* n, const void* net_in, void* eps, int rows,
       case B2G_LAYER_LOSS: break;
       case B2G_LAYER_CONV2D: case B2G_LAYER_DENSE: case B2G_LAYER_OUTPUT: {
         ConvGeom g = l.geom; g.N = R;
-        if (d.act != B2G_ACT_IDENTITY) k_act_bwd_from_output(n->prec, l.out, cur, cur, (size_t)R * l.out_elems, d.act, d.act_alpha, s);
+        if (d.act != B2G_ACT_IDENTITY && !act_done[i]) k_act_bwd_from_output(n->prec, l.out, cur, cur, (size_t)R * l.out_elems, d.act, d.act_alpha, s);
         if (want_wgrad_l) {
           fork_wgrad(i, cur);
           bool bias_done = false;
@@ -532,24 +598,28 @@ static int32_t net_backward(b2g_net* n, const void* net_in, void* eps, int rows,
           if (l.off_b >= 0 && !bias_done) k_colsum(n->prec, cur, R * l.oh * l.ow, l.oc, n->scratch2, n->grads + l.off_b, 0, s2);
           mark_reader(i, cur);
         }
-        if (need_in) { void* nx = other(cur); B2(gemm_dgrad(n, l, g, cur, nullptr, nx, ACT_IDENTITY, 0.f)); cur = nx; }
+        if (need_in) { void* nx = other(cur); TcEpi e{}; int tgt; bool fused = false; const bool can = pick_fuse(i, &e, &tgt);
+          B2(gemm_dgrad(n, l, g, cur, nullptr, nx, ACT_IDENTITY, 0.f, nullptr, can ? &e : nullptr, &fused)); note_fused(tgt, e, fused); cur = nx; }
       } break;
       case B2G_LAYER_DECONV2D: {
         ConvGeom g = l.geom; g.N = R;
-        if (d.act != B2G_ACT_IDENTITY) k_act_bwd_from_output(n->prec, l.out, cur, cur, (size_t)R * l.out_elems, d.act, d.act_alpha, s);
+        if (d.act != B2G_ACT_IDENTITY && !act_done[i]) k_act_bwd_from_output(n->prec, l.out, cur, cur, (size_t)R * l.out_elems, d.act, d.act_alpha, s);
         if (want_wgrad_l) {
           fork_wgrad(i, cur);
           B2(gemm_wgrad(n, l, g, /*conv input = deconv out grad*/ cur, /*conv dy = deconv input*/ lin, n->grads + l.off_W, s2, n->scratch2));
           if (l.off_b >= 0) k_colsum(n->prec, cur, R * l.oh * l.ow, l.oc, n->scratch2, n->grads + l.off_b, 0, s2);
           mark_reader(i, cur);
         }
-        if (need_in) { void* nx = other(cur); B2(gemm_fprop(n, l, g, cur, nullptr, nx, ACT_IDENTITY, 0.f)); cur = nx; }
+        if (need_in) { void* nx = other(cur); TcEpi e{}; int tgt; bool fused = false; const bool can = pick_fuse(i, &e, &tgt);
+          B2(gemm_fprop(n, l, g, cur, nullptr, nx, ACT_IDENTITY, 0.f, nullptr, can ? &e : nullptr, &fused)); note_fused(tgt, e, fused); cur = nx; }
       } break;
       case B2G_LAYER_BATCHNORM: {
         int rows_pg = (R / groups) * l.oh * l.ow; void* nx = need_in ? other(cur) : nullptr;
-        if (k_bn_fused_ok(n->prec, l.oc, groups) &&
-            k_bn_bwd_fused(lin, cur, nx, rows_pg, l.oc, groups, l.bn_mean, l.bn_invstd, n->params + l.off_gamma, n->params + l.off_beta, l.fused_act, l.fused_alpha, n->scratch,
-                           n->grads + l.off_gamma, n->grads + l.off_beta, want_wgrad_l ? 1 : 0, n->barrier_dev, s) == 0) { if (need_in) cur = nx; break; }
+        if (l.fwd_fused && l.fwd_groups == groups) {
+          if (!l.bwd_premul) k_bn_bwd_stats_acc(lin, cur, rows_pg, l.oc, groups, l.bn_coef, l.fused_act, l.fused_alpha, l.acc_bwd, s);
+          k_bn_bwd_apply_acc(lin, cur, nx, rows_pg, l.oc, groups, l.bn_coef, l.fused_act, l.fused_alpha, l.bwd_premul ? 1 : 0, l.acc_bwd, n->grads + l.off_gamma, n->grads + l.off_beta, want_wgrad_l ? 1 : 0, s);
+          l.bwd_premul = false;
+        } else
         k_bn_bwd(n->prec, lin, cur, nx, rows_pg, l.oc, groups, l.bn_mean, l.bn_invstd, n->params + l.off_gamma, n->params + l.off_beta, l.fused_act, l.fused_alpha,
                  n->scratch, n->grads + l.off_gamma, n->grads + l.off_beta, want_wgrad_l ? 1 : 0, s);
         if (need_in) cur = nx;
@@ -564,14 +634,14 @@ static int32_t net_backward(b2g_net* n, const void* net_in, void* eps, int rows,
       // every gradient of layers >= i is queued (BN scale/shift on s, weights/biases on s2): all-reduce that tail on the comm stream now
       b2g_ctx* c = n->ctx;
       cudaEventRecord(c->ev_c0, s); cudaStreamWaitEvent(c->comm_stream, c->ev_c0, 0);
-      if (forked) { cudaEventRecord(c->ev_c1, s2); cudaStreamWaitEvent(c->comm_stream, c->ev_c1, 0); }
+      if (forked) { flush_pending_reduce(n, s2); cudaEventRecord(c->ev_c1, s2); cudaStreamWaitEvent(c->comm_stream, c->ev_c1, 0); }
       NC(g_nccl.ar(n->grads + n->ar_split_off, n->grads + n->ar_split_off, (size_t)(n->n_params - n->ar_split_off), /*ncclFloat32*/ 7, /*ncclSum*/ 0, c->comm, c->comm_stream));
       n->ar_tail_sent = true;
     }
     if (!need_in) { cur = nullptr; break; }
   }
   n->input_grad = cur;
-  if (forked) { cudaEventRecord(n->ev_join, s2); cudaStreamWaitEvent(s, n->ev_join, 0); }   // join before all-reduce / updater
+  if (forked) { flush_pending_reduce(n, s2); cudaEventRecord(n->ev_join, s2); cudaStreamWaitEvent(s, n->ev_join, 0); }   // join before all-reduce / updater
   CHECK_KERNELS();
   return 0;
 }
@@ -588,20 +658,12 @@ static int32_t net_allreduce_grads(b2g_net* n) {
   NC(g_nccl.ar(n->grads, n->grads, (size_t)n->n_params, /*ncclFloat32*/ 7, /*ncclSum*/ 0, c->comm, c->stream));
   return 0;
 }
-static int32_t net_update(b2g_net* n, int mb_local, bool async_shadow = false) {
+static int32_t net_update(b2g_net* n, int mb_local) {
   cudaStream_t s = n->ctx->stream; int W = n->ctx->comm ? n->ctx->world : 1;
   // BN running-stat pseudo-gradients are exempt from the minibatch division; under DP they are averaged over ranks
   if (!n->grad_allreduce) W = 1;     // parameter-averaging mode: purely local update
-  k_updater(n->params, n->grads, n->st0, n->st1, n->segs_dev, n->chunk_seg_dev, n->chunk_off_dev, n->nchunks, 1.0f / ((float)mb_local * W), 1.0f / (float)W, n->step_dev, n->shadow, s);
-  k_inc_int(n->step_dev, s);
-  if (async_shadow && n->prec == PREC_BF16) {
-    // the straight copies were written by the updater itself; the transposed / packed ones are first needed by the next backward pass
-    // (or, for a net with transposed convs, its next forward): refresh them beside whatever the main stream does until then
-    cudaStream_t s2 = n->ctx->side;
-    cudaEventRecord(n->ev_fork[0], s); cudaStreamWaitEvent(s2, n->ev_fork[0], 0);
-    net_refresh_shadow(n, -1, true, s2);
-    cudaEventRecord(n->ev_shadow, s2); n->shadow_pending = true;
-  } else net_refresh_shadow(n, -1, true);
+  // one pass: /mb -> clip -> updater -> +l2*W -> theta -= g, the bf16 operand copies (straight and packed) and the iteration counter
+  k_updater(n->params, n->grads, n->st0, n->st1, n->segs_dev, n->chunk_seg_dev, n->chunk_off_dev, n->nchunks, 1.0f / ((float)mb_local * W), 1.0f / (float)W, n->step_dev, n->upd_ticket, n->shadow, s);
   CHECK_KERNELS();
   return 0;
 }
@@ -671,7 +733,7 @@ extern "C" int32_t b2g_net_create(b2g_ctx* ctx, const b2g_net_config* cfg, const
 }
 extern "C" int32_t b2g_net_destroy(b2g_net* n) {
   if (!n) return 0; cudaSetDevice(n->ctx->device); cudaStreamSynchronize(n->ctx->stream); cudaStreamSynchronize(n->ctx->side);
-  for (auto e : n->ev_fork) if (e) cudaEventDestroy(e); for (auto e : n->ev_done) if (e) cudaEventDestroy(e); if (n->ev_join) cudaEventDestroy(n->ev_join); if (n->ev_shadow) cudaEventDestroy(n->ev_shadow);
+  for (auto e : n->ev_fork) if (e) cudaEventDestroy(e); for (auto e : n->ev_done) if (e) cudaEventDestroy(e); if (n->ev_join) cudaEventDestroy(n->ev_join);
   for (void* p : n->allocs) cudaFree(p); delete n; return 0;
 }
 extern "C" int32_t b2g_net_num_params(b2g_net* n, int64_t* out) { if (!n || !out) return fail(B2G_ERR_ARG, "null"); *out = n->n_params; return 0; }
@@ -863,14 +925,18 @@ static int32_t gan_step_part2(b2g_gan* g, int N) {
   k_xent(D->prec, logits, g->y_d, D->epsA, g->loss_dev, N, 2, D->cfg.xent_clip_eps, s);
   B2(net_backward(D, D->input, D->epsA, 2 * N, 2, true, false, /*allreduce_follows=*/true));
   B2(net_allreduce_grads(D));
-  B2(net_update(D, 2 * N, /*async_shadow=*/true));     // joined by the G step's backward pass through D
+  B2(net_update(D, 2 * N));
   // 3. G update through D on (z_g, y_gen) (J:465-471); D's parameters / running stats / updater state untouched
   CU(cudaStreamWaitEvent(s, G->ctx->ev_b, 0));
   FwdOpts od2{N, 1, true, false, nullptr};
   B2(net_forward(D, xg, od2, &logits));
   k_xent(D->prec, logits, g->y_g, D->epsA, g->loss_dev + 2, N, 1, D->cfg.xent_clip_eps, s);
-  B2(net_backward(D, xg, D->epsA, N, 1, false, true));
-  B2(net_backward(G, g->z_g, D->input_grad, N, 1, true, false, /*allreduce_follows=*/true));
+  // the generator's output activation (tanh) is differentiated inside D's last input-gradient kernel when that kernel can (EPI_ACTBWD)
+  TcEpi ga{}; const LayerRT& gl = G->L.back(); bool ga_done = false;
+  const bool ga_can = gl.has_gemm() && gl.d.act != B2G_ACT_IDENTITY && gl.d.type != B2G_LAYER_OUTPUT;
+  if (ga_can) { ga.mode = EPI_ACTBWD; ga.aux = (const __nv_bfloat16*)xg; ga.act = gl.d.act; ga.alpha = gl.d.act_alpha; }
+  B2(net_backward(D, xg, D->epsA, N, 1, false, true, false, ga_can ? &ga : nullptr, &ga_done));
+  B2(net_backward(G, g->z_g, D->input_grad, N, 1, true, false, /*allreduce_follows=*/true, nullptr, nullptr, ga_done));
   B2(net_allreduce_grads(G));
   B2(net_update(G, N));
   return 0;
@@ -973,6 +1039,19 @@ extern "C" int32_t b2g_gan_step(b2g_gan* g, const float* x_real, const float* z_
   return 0;
 }
 
+// ------------------------------------------------------------------ iteration counter / dispatch evidence ----
+// The updater's iteration counter (Adam's t, DL4J's BaseMultiLayerUpdater iteration) lives on the device so that CUDA graphs replay;
+// a checkpoint must carry it, or a resumed Adam restarts its bias correction at t = 1 with warm moments.
+extern "C" int32_t b2g_net_get_iteration(b2g_net* n, int64_t* out) {
+  if (!n || !out) return fail(B2G_ERR_ARG, "null"); CU(cudaSetDevice(n->ctx->device));
+  int v = 0; CU(cudaMemcpyAsync(&v, n->step_dev, sizeof(int), cudaMemcpyDeviceToHost, n->ctx->stream)); CU(cudaStreamSynchronize(n->ctx->stream)); *out = v; return 0;
+}
+extern "C" int32_t b2g_net_set_iteration(b2g_net* n, int64_t it) {
+  if (!n || it < 0 || it > 0x7fffffff) return fail(B2G_ERR_ARG, "bad iteration"); CU(cudaSetDevice(n->ctx->device));
+  int v = (int)it; CU(cudaMemcpyAsync(n->step_dev, &v, sizeof(int), cudaMemcpyHostToDevice, n->ctx->stream)); CU(cudaStreamSynchronize(n->ctx->stream)); return 0;
+}
+extern "C" int32_t b2g_net_simt_gemm_calls(b2g_net* n, uint64_t* out) { if (!n || !out) return fail(B2G_ERR_ARG, "null"); *out = n->simt_gemm_calls; return 0; }
+
 // ------------------------------------------------------------------ data parallel ------------------------
 extern "C" int32_t b2g_comm_unique_id(void* id128) { if (!id128) return fail(B2G_ERR_ARG, "null"); B2(nccl_load()); NcclId id; NC(g_nccl.uid(&id)); memcpy(id128, &id, sizeof(id)); return 0; }
 extern "C" int32_t b2g_ctx_comm_init(b2g_ctx* c, int32_t world, int32_t rank, const void* id128) {
@@ -1001,55 +1080,83 @@ extern "C" int32_t b2g_ctx_allreduce_test(b2g_ctx* c, float* host, int64_t n) {
 }
 
 // ------------------------------------------------------------------ kernel-level test hook ----------------
-extern "C" int32_t b2g_test_conv(b2g_ctx* c, int32_t kind, int32_t impl, int32_t precision, const b2g_conv_geom* gg, const float* a_host, const float* b_host, float* out, int32_t iters, float* ms_per_iter) {
+extern "C" int32_t b2g_test_conv_ex(b2g_ctx* c, int32_t kind, int32_t impl, int32_t precision, const b2g_conv_geom* gg, const float* a_host, const float* b_host, float* out, int32_t iters, float* ms_per_iter,
+                                    b2g_test_conv_opts* opt) {
   if (!c || !gg || !a_host || !b_host || !out) return fail(B2G_ERR_ARG, "null"); CU(cudaSetDevice(c->device));
   cudaStream_t s = c->stream; int prec = precision == B2G_PREC_BF16 ? PREC_BF16 : PREC_F32; size_t ts = prec_size(prec);
   ConvGeom g{gg->n, gg->h, gg->w, gg->c, gg->oh, gg->ow, gg->o, gg->kh, gg->kw, gg->sh, gg->sw, gg->ph, gg->pw};
   size_t nx = (size_t)g.N * g.H * g.W * g.C, ny = (size_t)g.N * g.OH * g.OW * g.O, nw = (size_t)g.O * g.KH * g.KW * g.C;
   // operands: kind 0: a = x (NHWC), b = w [O][KH][KW][C] -> out y ; kind 1: a = dy, b = w -> out dx ; kind 2: a = x, b = dy -> out dw (fp32)
   size_t na = kind == 1 ? ny : nx, nb = kind == 2 ? ny : nw, no = kind == 0 ? ny : kind == 1 ? nx : nw;
+  const int oc = kind == 0 ? g.O : g.C;       // channels of the result (kinds 0 / 1)
   if (impl == 1) {
     if (prec != PREC_BF16 || !c->tc_ok) return fail(B2G_ERR_UNSUPPORTED, "tcgen05 kernels need BF16 precision and a working tensor-map encoder");
     bool ok = kind == 0 ? tc_fprop_supported(g) : kind == 1 ? tc_dgrad_supported(g) : tc_wgrad_supported(g);
     if (!ok) return fail(B2G_ERR_UNSUPPORTED, "no tcgen05 kernel for this shape");
   }
+  if (opt && (impl != 1 || kind == 2) && (opt->epi || opt->bias || opt->scale || opt->act)) return fail(B2G_ERR_UNSUPPORTED, "epilogue options apply to the tcgen05 fprop / dgrad kernels (impl 1, kind 0 / 1)");
   // impl 2 = the SIMT skinny-layer kernels (kernels_edge.cu), impl 3 = their tcgen05 counterparts; both need <= 4 image channels (g.C)
   if (impl == 2 || impl == 3) {
     bool ok = kind == 0 ? edge_conv_small_cin_supported(g) : kind == 1 ? edge_deconv_small_c_supported(g) : edge_wgrad_small_cin_supported(g);
     if (impl == 3) ok = ok && prec == PREC_BF16 && c->tc_ok && (kind == 0 ? tc_edge_conv_supported(g) : kind == 1 ? tc_deconv_ps_supported(g) : tc_edge_wgrad_supported(g));
     if (!ok) return fail(B2G_ERR_UNSUPPORTED, "no skinny-layer kernel (impl %d) for this shape", impl);
   }
-  float *fa = nullptr, *fb = nullptr, *fo = nullptr, *scratch = nullptr; void *ta = nullptr, *tb = nullptr, *tbt = nullptr, *to = nullptr; __nv_bfloat16* wps = nullptr;
+  float *fa = nullptr, *fb = nullptr, *fo = nullptr, *scratch = nullptr; void *ta = nullptr, *tb = nullptr, *to = nullptr; __nv_bfloat16* wps = nullptr;
+  float *d_bias = nullptr, *d_scale = nullptr, *d_coef = nullptr, *d_auxf = nullptr; __nv_bfloat16* d_aux = nullptr; unsigned long long* d_acc = nullptr;
   size_t sc = std::max(std::max(k_simt_wgrad_scratch_floats(g), k_tc_wgrad_scratch_floats(g)), std::max(k_edge_wgrad_scratch_floats(g), k_tc_edge_wgrad_scratch_floats(g))) + 16;
   CU(cudaMalloc(&fa, 4 * na)); CU(cudaMalloc(&fb, 4 * nb)); CU(cudaMalloc(&fo, 4 * no)); CU(cudaMalloc(&scratch, 4 * sc));
-  CU(cudaMalloc(&ta, ts * na)); CU(cudaMalloc(&tb, ts * nb)); CU(cudaMalloc(&tbt, ts * nb)); CU(cudaMalloc(&to, ts * no));
+  CU(cudaMalloc(&ta, ts * na)); CU(cudaMalloc(&tb, ts * nb)); CU(cudaMalloc(&to, ts * no));
   CU(cudaMemcpyAsync(fa, a_host, 4 * na, cudaMemcpyHostToDevice, s)); CU(cudaMemcpyAsync(fb, b_host, 4 * nb, cudaMemcpyHostToDevice, s));
-  if (prec == PREC_BF16) {
-    k_cast_f32_to_bf16(fa, (__nv_bfloat16*)ta, na, s);
-    if (kind == 2) k_cast_f32_to_bf16(fb, (__nv_bfloat16*)tb, nb, s); else k_weight_shadow(fb, (__nv_bfloat16*)tb, (__nv_bfloat16*)tbt, g.O, g.KH * g.KW, g.C, s);
-  } else { CU(cudaMemcpyAsync(ta, fa, 4 * na, cudaMemcpyDeviceToDevice, s)); CU(cudaMemcpyAsync(tb, fb, 4 * nb, cudaMemcpyDeviceToDevice, s)); }
+  if (prec == PREC_BF16) { k_cast_f32_to_bf16(fa, (__nv_bfloat16*)ta, na, s); k_cast_f32_to_bf16(fb, (__nv_bfloat16*)tb, nb, s); }
+  else { CU(cudaMemcpyAsync(ta, fa, 4 * na, cudaMemcpyDeviceToDevice, s)); CU(cudaMemcpyAsync(tb, fb, 4 * nb, cudaMemcpyDeviceToDevice, s)); }
   if (impl == 3 && kind == 1) { CU(cudaMalloc(&wps, 2 * k_tc_deconv_ps_weight_elems(g))); k_pack_deconv_ps(fb, wps, g.O, g.C, s); }
+  TcEpi epi{}; const TcEpi* pe = nullptr; const float* bias = nullptr; int act = 0; float alpha = 0.f; int groups = 1;
+  if (opt && impl == 1 && kind != 2) {
+    groups = opt->groups > 0 ? opt->groups : 1; act = opt->act; alpha = opt->alpha;
+    if (opt->bias) { CU(cudaMalloc(&d_bias, 4 * oc)); CU(cudaMemcpyAsync(d_bias, opt->bias, 4 * oc, cudaMemcpyHostToDevice, s)); bias = d_bias; }
+    if (opt->scale) { CU(cudaMalloc(&d_scale, 4 * oc)); CU(cudaMemcpyAsync(d_scale, opt->scale, 4 * oc, cudaMemcpyHostToDevice, s)); }
+    epi.mode = opt->epi; epi.scale = d_scale; epi.imgs_per_group = g.N / groups; epi.act = opt->act; epi.alpha = opt->alpha;
+    if (opt->epi == EPI_STATS || opt->epi == EPI_BNBWD) { CU(cudaMalloc(&d_acc, 8 * k_bn_acc_elems(oc, groups))); epi.acc = d_acc; }
+    if (opt->epi == EPI_BNBWD || opt->epi == EPI_ACTBWD) {
+      if (!opt->aux) return fail(B2G_ERR_ARG, "epilogue %d needs aux", opt->epi);
+      CU(cudaMalloc(&d_auxf, 4 * no)); CU(cudaMalloc(&d_aux, 2 * no)); CU(cudaMemcpyAsync(d_auxf, opt->aux, 4 * no, cudaMemcpyHostToDevice, s)); k_cast_f32_to_bf16(d_auxf, d_aux, no, s); epi.aux = d_aux;
+    }
+    if (opt->epi == EPI_BNBWD) { if (!opt->coef) return fail(B2G_ERR_ARG, "epilogue 2 needs coef"); CU(cudaMalloc(&d_coef, 4 * 4 * groups * oc)); CU(cudaMemcpyAsync(d_coef, opt->coef, 4 * 4 * groups * oc, cudaMemcpyHostToDevice, s)); epi.coef = d_coef; }
+    if (opt->epi || opt->scale) pe = &epi;
+  }
   cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
   int reps = iters < 1 ? 1 : iters; int rc = 0;
+  g_tc_last_kernel = "";
   for (int it = -1; it < reps; ++it) {       // it = -1: warm-up
     if (it == 0) CU(cudaEventRecord(e0, s));
+    if (d_acc) CU(cudaMemsetAsync(d_acc, 0, 8 * k_bn_acc_elems(oc, groups), s));
     if (impl >= 2) {
       if (kind == 0) { if (impl == 3) rc = k_tc_edge_conv(g, (const __nv_bfloat16*)ta, (const __nv_bfloat16*)tb, nullptr, (__nv_bfloat16*)to, 0, 0.f, s); else k_edge_conv_small_cin(prec, prec, g, ta, tb, nullptr, to, 0, 0.f, s); }
       else if (kind == 1) { if (impl == 3) rc = k_tc_deconv_ps(g, (const __nv_bfloat16*)ta, wps, nullptr, (__nv_bfloat16*)to, 0, 0.f, s); else k_edge_deconv_small_c(prec, prec, g, ta, tb, nullptr, to, 0, 0.f, s); }
       else { if (impl == 3) rc = k_tc_edge_wgrad(g, (const __nv_bfloat16*)ta, (const __nv_bfloat16*)tb, fo, nullptr, scratch, sc, 0, s); else k_edge_wgrad_small_cin(prec, g, ta, tb, fo, scratch, 0, s); }
     }
-    else if (kind == 0) { if (impl) rc = k_tc_fprop(g, (const __nv_bfloat16*)ta, (const __nv_bfloat16*)tb, nullptr, (__nv_bfloat16*)to, 0, 0.f, s); else k_simt_fprop(prec, prec, g, ta, tb, nullptr, to, 0, 0.f, s); }
-    else if (kind == 1) { if (impl) rc = k_tc_dgrad(g, (const __nv_bfloat16*)ta, (const __nv_bfloat16*)tbt, nullptr, (__nv_bfloat16*)to, 0, 0.f, s); else k_simt_dgrad(prec, prec, g, ta, tb, nullptr, to, 0, 0.f, s); }
+    else if (kind == 0) { if (impl) rc = k_tc_fprop(g, (const __nv_bfloat16*)ta, (const __nv_bfloat16*)tb, bias, (__nv_bfloat16*)to, act, alpha, s, pe); else k_simt_fprop(prec, prec, g, ta, tb, nullptr, to, 0, 0.f, s); }
+    else if (kind == 1) { if (impl) rc = k_tc_dgrad(g, (const __nv_bfloat16*)ta, (const __nv_bfloat16*)tb, bias, (__nv_bfloat16*)to, act, alpha, s, pe); else k_simt_dgrad(prec, prec, g, ta, tb, nullptr, to, 0, 0.f, s); }
     else { if (impl) rc = k_tc_wgrad(g, (const __nv_bfloat16*)ta, (const __nv_bfloat16*)tb, fo, scratch, sc, 0, s); else k_simt_wgrad(prec, g, ta, tb, fo, scratch, sc, 0, s); }
     if (rc) break;
   }
   CU(cudaEventRecord(e1, s));
   if (rc) return fail(B2G_ERR_CUDA, "tensor-core kernel launch failed (%d)", rc);
+  if (opt) { strncpy(opt->kernel, g_tc_last_kernel, sizeof(opt->kernel) - 1); opt->kernel[sizeof(opt->kernel) - 1] = 0; }
   if (kind != 2) { if (prec == PREC_BF16) { /* widen */ k_nhwc_to_nchw_f32(prec, to, fo, 1, 1, (int)no, s); } else CU(cudaMemcpyAsync(fo, to, 4 * no, cudaMemcpyDeviceToDevice, s)); }
   CU(cudaMemcpyAsync(out, fo, 4 * no, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s)); CHECK_KERNELS();
+  if (d_acc && opt && opt->stats) {      // [groups][2][C] doubles from the [groups][2][2][C] hi | lo words
+    std::vector<long long> h(k_bn_acc_elems(oc, groups)); CU(cudaMemcpy(h.data(), d_acc, 8 * h.size(), cudaMemcpyDeviceToHost));
+    for (int gi = 0; gi < groups; ++gi) for (int st = 0; st < 2; ++st) for (int ch = 0; ch < oc; ++ch)
+      opt->stats[((size_t)gi * 2 + st) * oc + ch] = (double)h[((size_t)(gi * 2 + st) * 2 + 0) * oc + ch] / 1024.0 + (double)h[((size_t)(gi * 2 + st) * 2 + 1) * oc + ch] / 1152921504606846976.0;
+  }
   float ms = 0.f; CU(cudaEventElapsedTime(&ms, e0, e1)); if (ms_per_iter) *ms_per_iter = ms / reps;
   cudaEventDestroy(e0); cudaEventDestroy(e1);
-  cudaFree(fa); cudaFree(fb); cudaFree(fo); cudaFree(scratch); cudaFree(ta); cudaFree(tb); cudaFree(tbt); cudaFree(to); if (wps) cudaFree(wps);
+  cudaFree(fa); cudaFree(fb); cudaFree(fo); cudaFree(scratch); cudaFree(ta); cudaFree(tb); cudaFree(to); if (wps) cudaFree(wps);
+  if (d_bias) cudaFree(d_bias); if (d_scale) cudaFree(d_scale); if (d_coef) cudaFree(d_coef); if (d_auxf) cudaFree(d_auxf); if (d_aux) cudaFree(d_aux); if (d_acc) cudaFree(d_acc);
   return 0;
+}
+extern "C" int32_t b2g_test_conv(b2g_ctx* c, int32_t kind, int32_t impl, int32_t precision, const b2g_conv_geom* gg, const float* a_host, const float* b_host, float* out, int32_t iters, float* ms_per_iter) {
+  return b2g_test_conv_ex(c, kind, impl, precision, gg, a_host, b_host, out, iters, ms_per_iter, nullptr);
 }

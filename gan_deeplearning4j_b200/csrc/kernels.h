@@ -29,8 +29,6 @@ void k_nchw_f32_to_nhwc(int prec, const float* src, void* dst, int N, int C, int
 void k_nhwc_to_nchw_f32(int prec, const void* src, float* dst, int N, int C, int HW, cudaStream_t s);
 void k_permute(int prec, const void* src, void* dst, int N, int C, int HW, int to_nhwc, cudaStream_t s);
 void k_cast_f32_to_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t s);
-// w [A][KH*KW][B] fp32 -> bf16 same layout, plus transposed copy [B][KH*KW][A] (dgrad operand)
-void k_weight_shadow(const float* w, __nv_bfloat16* w_bf, __nv_bfloat16* wt_bf, int A, int taps, int B, cudaStream_t s);
 
 // ---- batch norm --------------------------------------------------------------------------------
 // Train-mode statistics per (group, channel): mean, invstd = 1/sqrt(var_biased+eps); optional DL4J running-stat
@@ -51,12 +49,22 @@ void k_bn_bwd(int prec, const void* x, const void* eps_out, void* eps_in, int ro
               const float* mean, const float* invstd, const float* gamma, const float* beta, int act, float alpha,
               float* scratch, float* g_gamma, float* g_beta, int want_param_grads, cudaStream_t s);
 
-// fused cooperative variants (bf16, C % 8 == 0): one launch for statistics + apply / reduce + apply; return 0 on success
-bool k_bn_fused_ok(int prec, int C, int groups);
-int k_bn_fwd_fused(const void* x, void* y, int rows_per_group, int C, int groups, float* scratch, float* mean, float* invstd, const float* gamma, const float* beta,
-                   int act, float alpha, float eps, const float* run_mean, const float* run_var, float* g_mean, float* g_var, float decay, unsigned* counter, cudaStream_t s);
-int k_bn_bwd_fused(const void* x, const void* eps_out, void* eps_in, int rows_per_group, int C, int groups, const float* mean, const float* invstd, const float* gamma, const float* beta,
-                   int act, float alpha, float* scratch, float* g_gamma, float* g_beta, int want_param_grads, unsigned* counter, cudaStream_t s);
+// Fused path (bf16, C % 8 == 0): the batch statistics live in 128-bit fixed-point accumulators acc[groups][2][2][C] (statistic, hi | lo,
+// channel; common.cuh sacc_add) that the producing tcgen05 GEMM fills from its epilogue (kernels_tc.cu EPI_STATS / EPI_BNBWD) or, where the
+// producer has no such epilogue, the *_stats_acc kernels below; the apply kernels derive mean / invstd (and the backward coefficients) from
+// them on the fly -- no partial buffers, no finalise launches.  The caller zeroes acc (one memset per pass).
+bool k_bn_vec_ok(int prec, int C);
+size_t k_bn_acc_elems(int C, int groups);                  // 64-bit words per accumulator set
+void k_bn_stats_acc(const void* x, int rows_per_group, int C, int groups, unsigned long long* acc, cudaStream_t s);
+// y = act(x*scale+shift); block 0 also leaves coef[groups][4][C] = {scale = gamma*invstd, shift = beta - mean*scale, mean, invstd} for the
+// backward pass and (g_mean != null) the DL4J running-stat pseudo-gradients averaged over groups
+void k_bn_apply_acc(const void* x, void* y, int rows_per_group, int C, int groups, const unsigned long long* acc, const float* gamma, const float* beta,
+                    int act, float alpha, float eps, float* coef, const float* run_mean, const float* run_var, float* g_mean, float* g_var, float decay, cudaStream_t s);
+// sum dy', sum dy'*xhat -> acc with dy' = eps_out * act'(x*scale+shift)   (producers without the EPI_BNBWD epilogue)
+void k_bn_bwd_stats_acc(const void* x, const void* eps_out, int rows_per_group, int C, int groups, const float* coef, int act, float alpha, unsigned long long* acc, cudaStream_t s);
+// eps_in = scale * (dy' - mean(dy') - xhat*mean(dy'*xhat)); premul != 0: eps_out already holds dy'.  Block 0 adds dgamma / dbeta (summed over groups).
+void k_bn_bwd_apply_acc(const void* x, const void* eps_out, void* eps_in, int rows_per_group, int C, int groups, const float* coef, int act, float alpha, int premul,
+                        const unsigned long long* acc, float* g_gamma, float* g_beta, int want_param_grads, cudaStream_t s);
 
 // ---- activations / pooling / upsampling -----------------------------------------------------------
 void k_act_fwd(int prec, const void* x, void* y, size_t n, int act, float alpha, cudaStream_t s);
@@ -82,6 +90,11 @@ size_t k_colsum_scratch_floats(int C);
 void k_sumsq_segments(const float* p, const int64_t* seg_off, const int64_t* seg_len, const float* seg_coef, int nseg, double* out, cudaStream_t s);
 // dst[i] = sum_s src[s*stride + i]
 void k_reduce_splits(const float* src, float* dst, size_t n, int splits, size_t stride, int accumulate, cudaStream_t s);
+// the same for a whole list of (src, dst) pairs in ONE launch: the split-K partials of every weight gradient of a backward pass
+struct ReduceJob { const float* src; float* dst; int64_t n, stride; int splits, blocks; };
+struct ReduceList { static const int MAX_JOBS = 24; ReduceJob jobs[MAX_JOBS]; int count; };
+void reduce_list_push(ReduceList* rl, const float* src, float* dst, int64_t n, int splits, int64_t stride);
+void k_reduce_multi(const ReduceList& rl, cudaStream_t s);
 
 // ---- updater (BaseMultiLayerUpdater + UpdaterBlock + params.subi, one pass) -----------------------------
 struct UpdSeg {            // one parameter tensor
@@ -91,15 +104,16 @@ struct UpdSeg {            // one parameter tensor
   float l2;                // post-updater, not lr-scaled (pre-beta4)
   float clip;              // elementwise clip threshold, 0 = off
   int div_mb;              // 0 for BN mean/var pseudo-gradients
-  // bf16 shadow of a conv/deconv/dense weight: w_bf[off_bf..] same layout; wt_bf transposed [B][taps][A]
-  int64_t off_bf, off_bft;
-  int A, taps, B;
+  // bf16 shadow of a conv/deconv/dense weight: shadow[off_bf..] same layout [A][taps][B]; off_ps >= 0: also the packed [16][9][ps_O] operand of
+  // the pixel-shuffle transposed conv (kernels_tc.cu k_pack_deconv_ps), every weight element has exactly one slot there
+  int64_t off_bf, off_ps;
+  int ps_O, ps_C;
 };
+// The last block to finish bumps *step_dev (Adam's t) and resets *ticket: no separate counter kernel.
 void k_updater(float* params, const float* grads, float* st0, float* st1, const UpdSeg* segs_dev, const int32_t* chunk_seg_dev,
-               const int64_t* chunk_off_dev, int nchunks, float inv_mb, float inv_world, const int* step_dev /* t = *step_dev + 1 */,
+               const int64_t* chunk_off_dev, int nchunks, float inv_mb, float inv_world, int* step_dev /* t = *step_dev + 1 */, unsigned* ticket,
                __nv_bfloat16* shadow, cudaStream_t s);
 static const int UPD_CHUNK = 4096;
-void k_inc_int(int* p, cudaStream_t s);          // *p += 1 (iteration counters live on the device so CUDA graphs replay)
 void k_fill_f32(float* p, float v, size_t n, cudaStream_t s);
 void k_scale_f32(float* p, float v, size_t n, cudaStream_t s);
 
@@ -135,10 +149,23 @@ bool tc_fprop_supported(const ConvGeom& g);
 bool tc_dgrad_supported(const ConvGeom& g);
 bool tc_wgrad_supported(const ConvGeom& g);
 int  tc_init();   // resolves cuTensorMapEncodeTiled; 0 on success
-// stats: optional per-(group,channel) sum / sum-of-squares of the fp32 accumulators, fused in the epilogue
-int k_tc_fprop(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out, int act, float alpha, cudaStream_t s, const float* scale = nullptr);
-int k_tc_dgrad(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat16* wt, const float* bias, __nv_bfloat16* dx, int act, float alpha, cudaStream_t s, const float* scale = nullptr);
-int k_tc_wgrad(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* scratch, size_t scratch_floats, int accumulate, cudaStream_t s);
+extern const char* g_tc_last_kernel;     // which tcgen05 kernel the most recent k_tc_* call dispatched (parity tests assert it)
+// epilogue of the fprop / dgrad kernels (kernels_tc.cu): what happens between the fp32 accumulator and the bf16 store
+enum { EPI_PLAIN = 0, EPI_STATS = 1, EPI_BNBWD = 2, EPI_ACTBWD = 3 };
+struct TcEpi {
+  int mode;                    // EPI_*
+  const float* scale;          // EPI_PLAIN / EPI_STATS: out = act(acc*scale[c] + bias[c]) (inference-mode BatchNorm folded in), may be null
+  unsigned long long* acc;     // EPI_STATS: sum / sum-of-squares of the outputs; EPI_BNBWD: sum dy', sum dy'*xhat   [groups][2][2][OC]
+  int imgs_per_group;          // statistics group = image index / imgs_per_group
+  const __nv_bfloat16* aux;    // EPI_BNBWD: the BatchNorm layer's input z; EPI_ACTBWD: the forward output a of the layer whose act' is applied
+  const float* coef;           // EPI_BNBWD: [groups][4][OC] from k_bn_apply_acc
+  int act; float alpha;        // EPI_BNBWD / EPI_ACTBWD: the activation whose derivative multiplies the result
+};
+// w: the bf16 weight copy [O][taps][C].  w_mn = 1 (1x1 geometry): w is [C][O], the dense layer's own weight as its input-gradient operand.
+int k_tc_fprop(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out, int act, float alpha, cudaStream_t s, const TcEpi* epi = nullptr, int w_mn = 0);
+// conv input gradient / transposed-conv forward (4x4 s2 p1, sub-pixel phases); w is the SAME straight copy [O][16][C] (MN-major weight tiles)
+int k_tc_dgrad(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* dx, int act, float alpha, cudaStream_t s, const TcEpi* epi = nullptr);
+int k_tc_wgrad(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* scratch, size_t scratch_floats, int accumulate, cudaStream_t s, ReduceList* defer = nullptr);
 size_t k_tc_wgrad_scratch_floats(const ConvGeom& g);
 // transposed conv 4x4 s2 p1 onto <= 4 image channels as one 3x3 tcgen05 conv over the 2x2 output blocks (weights packed by k_pack_deconv_ps)
 bool tc_deconv_ps_shape(const ConvGeom& g);          // geometry only (allocation time)
@@ -151,7 +178,7 @@ bool tc_edge_wgrad_supported(const ConvGeom& g);
 size_t k_tc_edge_wgrad_scratch_floats(const ConvGeom& g);
 int k_tc_edge_conv(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out, int act, float alpha, cudaStream_t s);
 // db (optional, g.C < 4): also the column sums of dy (= the conv bias gradient) from a ones column of the im2col tile; returns 1 if db was written, 0 if not, < 0 on error
-int k_tc_edge_wgrad(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* db, float* scratch, size_t scratch_floats, int accumulate, cudaStream_t s);
-int k_tc_deconv_ps(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat16* wps, const float* bias, __nv_bfloat16* dx, int act, float alpha, cudaStream_t s);
+int k_tc_edge_wgrad(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* db, float* scratch, size_t scratch_floats, int accumulate, cudaStream_t s, ReduceList* defer = nullptr);
+int k_tc_deconv_ps(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat16* wps, const float* bias, __nv_bfloat16* dx, int act, float alpha, cudaStream_t s, const TcEpi* epi = nullptr);
 
 }  // namespace b2g

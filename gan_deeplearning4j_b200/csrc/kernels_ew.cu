@@ -16,11 +16,10 @@
 namespace b2g {
 
 uint64_t g_launch_count = 0;
-int g_pdl_enabled = -1;
 
 // ---------------------------------------------------------------- layout -----------------------------
 template <typename T>
-__global__ void nchw_f32_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int N, int C, int HW) { pdl_prologue();
+__global__ void nchw_f32_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int N, int C, int HW) {
   // one thread per destination element (coalesced writes; reads strided by HW, served by L2)
   size_t total = (size_t)N * C * HW;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -29,7 +28,7 @@ __global__ void nchw_f32_to_nhwc_kernel(const float* __restrict__ src, T* __rest
   }
 }
 template <typename T>
-__global__ void nhwc_to_nchw_f32_kernel(const T* __restrict__ src, float* __restrict__ dst, int N, int C, int HW) { pdl_prologue();
+__global__ void nhwc_to_nchw_f32_kernel(const T* __restrict__ src, float* __restrict__ dst, int N, int C, int HW) {
   size_t total = (size_t)N * C * HW;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int p = i % HW; size_t t = i / HW; int c = t % C; size_t n = t / C;
@@ -37,7 +36,7 @@ __global__ void nhwc_to_nchw_f32_kernel(const T* __restrict__ src, float* __rest
   }
 }
 template <typename T>
-__global__ void permute_kernel(const T* __restrict__ src, T* __restrict__ dst, int N, int C, int HW, int to_nhwc) { pdl_prologue();
+__global__ void permute_kernel(const T* __restrict__ src, T* __restrict__ dst, int N, int C, int HW, int to_nhwc) {
   size_t total = (size_t)N * C * HW;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     if (to_nhwc) { int c = i % C; size_t t = i / C; int p = t % HW; size_t n = t / HW; dst[i] = src[(n * C + c) * HW + p]; }
@@ -67,33 +66,12 @@ void k_permute(int prec, const void* src, void* dst, int N, int C, int HW, int t
   size_t n = (size_t)N * C * HW; if (!n) return;
   DISPATCH_PREC(prec, T, (launch_pdl(permute_kernel<T>, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, (const T*)src, (T*)dst, N, C, HW, to_nhwc))); LAUNCHED();
 }
-__global__ void cast_f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) { pdl_prologue();
+__global__ void cast_f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = __float2bfloat16_rn(src[i]);
 }
 void k_cast_f32_to_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t s) {
   if (!n) return; launch_pdl(cast_f32_to_bf16_kernel, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, src, dst, n); LAUNCHED();
 }
-// w [A][taps][B] -> w_bf same layout, wt_bf [B][taps][A]; 32x32 smem-tiled transpose per tap
-__global__ void weight_shadow_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ w_bf, __nv_bfloat16* __restrict__ wt_bf, int A, int taps, int B) { pdl_prologue();
-  __shared__ float tile[32][33];
-  int tap = blockIdx.z, a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    int a = a0 + i, b = b0 + threadIdx.x;
-    float v = 0.f;
-    if (a < A && b < B) { size_t idx = ((size_t)a * taps + tap) * B + b; v = w[idx]; if (w_bf) w_bf[idx] = __float2bfloat16_rn(v); }
-    tile[i][threadIdx.x] = v;
-  }
-  __syncthreads();
-  if (wt_bf) for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    int b = b0 + i, a = a0 + threadIdx.x;
-    if (a < A && b < B) wt_bf[((size_t)b * taps + tap) * A + a] = __float2bfloat16_rn(tile[threadIdx.x][i]);
-  }
-}
-void k_weight_shadow(const float* w, __nv_bfloat16* w_bf, __nv_bfloat16* wt_bf, int A, int taps, int B, cudaStream_t s) {
-  dim3 grid((B + 31) / 32, (A + 31) / 32, taps);
-  launch_pdl(weight_shadow_kernel, dim3(grid), dim3(dim3(32, 8)), (size_t)(0), s, w, w_bf, wt_bf, A, taps, B); LAUNCHED();
-}
-
 // ---------------------------------------------------------------- sliced column reductions ---------------
 // Thread idx -> (slice s = idx / C, channel c = idx % C); it sums rows s, s+S, s+2S, ... so that a warp
 // reads consecutive addresses.  partial[(g*S + s)*C + c].  Stage 2: one warp per channel, fixed order.
@@ -118,7 +96,7 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
 }
 
 template <typename T>
-__global__ void bn_stats_partial_kernel(const T* __restrict__ x, int rows, int C, int S, float* __restrict__ psum, float* __restrict__ psq) { pdl_prologue();
+__global__ void bn_stats_partial_kernel(const T* __restrict__ x, int rows, int C, int S, float* __restrict__ psum, float* __restrict__ psq) {
   int g = blockIdx.y;
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= S * C) return;
@@ -147,7 +125,7 @@ __device__ __forceinline__ void block_fold_write(float (&acc)[NV][8], int C, int
     for (int v = 0; v < NV; ++v) { float a = 0.f; for (int k = 0; k < TY; ++k) a += sred[v][k * C + c]; dst[v][row_off + c] = a; }
   }
 }
-__global__ void __launch_bounds__(256) bn_stats_partial_bf16x8_kernel(const uint4* __restrict__ x, int rows, int C, int S, float* __restrict__ psum, float* __restrict__ psq) { pdl_prologue();
+__global__ void __launch_bounds__(256) bn_stats_partial_bf16x8_kernel(const uint4* __restrict__ x, int rows, int C, int S, float* __restrict__ psum, float* __restrict__ psq) {
   const int g = blockIdx.y, C8 = C / 8, TY = 256 / C8, c8 = threadIdx.x % C8, ty = threadIdx.x / C8, sl = blockIdx.x;
   const int chunk = (rows + S - 1) / S, r0 = sl * chunk, r1 = min(rows, r0 + chunk);
   const uint4* xg = x + (size_t)g * rows * C8;
@@ -164,7 +142,7 @@ __global__ void __launch_bounds__(256) bn_stats_partial_bf16x8_kernel(const uint
 // stage 2: block = 32 adjacent channels x 16 slice lanes (coalesced 128-byte rows of the partial arrays), fixed-order tree in double
 __global__ void __launch_bounds__(1024) bn_stats_final_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int rows, int C, int S, int groups, float eps,
                                       float* __restrict__ mean, float* __restrict__ invstd,
-                                      const float* __restrict__ run_mean, const float* __restrict__ run_var, float* g_mean, float* g_var, float decay) { pdl_prologue();
+                                      const float* __restrict__ run_mean, const float* __restrict__ run_var, float* g_mean, float* g_var, float decay) {
   __shared__ double sa[32][33], sb[32][33];      // 32 channels x 32 slice lanes: S <= 256 partial rows in ONE batch of 8 loads per thread
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, c = blockIdx.x * 32 + tx;
   double acc_gm = 0.0, acc_gv = 0.0;
@@ -204,11 +182,11 @@ void k_bn_stats(int prec, const void* x, int rows, int C, int groups, float* scr
   LAUNCHED();
   launch_pdl(bn_stats_final_kernel, dim3((C + 31) / 32), dim3(1024), (size_t)(0), s, psum, psq, rows, C, S, groups, eps, mean, invstd, run_mean, run_var, g_mean, g_var, decay); LAUNCHED();
 }
-__global__ void bn_prep_infer_kernel(const float* __restrict__ rm, const float* __restrict__ rv, int C, int groups, float eps, float* mean, float* invstd) { pdl_prologue();
+__global__ void bn_prep_infer_kernel(const float* __restrict__ rm, const float* __restrict__ rv, int C, int groups, float eps, float* mean, float* invstd) {
   int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= C * groups) return;
   int c = i % C; mean[i] = rm[c]; invstd[i] = 1.0f / sqrtf(rv[c] + eps);
 }
-__global__ void bn_fold_kernel(const float* __restrict__ rm, const float* __restrict__ rv, const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ cb, int C, float eps, float* scale, float* shift) { pdl_prologue();
+__global__ void bn_fold_kernel(const float* __restrict__ rm, const float* __restrict__ rv, const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ cb, int C, float eps, float* scale, float* shift) {
   int c = blockIdx.x * blockDim.x + threadIdx.x; if (c >= C) return;
   const float sc = gamma[c] / sqrtf(rv[c] + eps); scale[c] = sc; shift[c] = beta[c] - rm[c] * sc + (cb ? cb[c] * sc : 0.f);
 }
@@ -221,7 +199,7 @@ void k_bn_prep_infer(const float* run_mean, const float* run_var, int C, int gro
 
 template <typename T>
 __global__ void bn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, int rows, int C, int groups, const float* __restrict__ mean,
-                                const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int act, float alpha) { pdl_prologue();
+                                const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int act, float alpha) {
   size_t per_group = (size_t)rows * C, total = per_group * groups;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int c = i % C; int g = i / per_group;
@@ -233,7 +211,7 @@ __global__ void bn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, int 
 // meets the same 8 channels: their coefficients are loaded once per group instead of 4-6 scalar loads per element.
 template <int ACTC>
 __global__ void __launch_bounds__(256, 3) bn_apply_bf16x8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int rows, int C, int groups, const float* __restrict__ mean,
-                                       const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int act, float alpha) { pdl_prologue();
+                                       const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int act, float alpha) {
   const int C8 = C / 8; const size_t per_group = (size_t)rows * C8;
   const size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
   const int c0 = (int)(t0 % C8) * 8;
@@ -271,7 +249,7 @@ void k_bn_apply(int prec, const void* x, void* y, int rows, int C, int groups, c
 template <typename T>
 __global__ void bn_bwd_partial_kernel(const T* __restrict__ x, const T* __restrict__ eo, int rows, int C, int S, const float* __restrict__ mean,
                                       const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int act, float alpha,
-                                      float* __restrict__ p1, float* __restrict__ p2) { pdl_prologue();
+                                      float* __restrict__ p1, float* __restrict__ p2) {
   int g = blockIdx.y;
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= S * C) return;
@@ -289,7 +267,7 @@ __global__ void bn_bwd_partial_kernel(const T* __restrict__ x, const T* __restri
 template <int ACTC>
 __global__ void __launch_bounds__(256, 3) bn_bwd_partial_bf16x8_kernel(const uint4* __restrict__ x, const uint4* __restrict__ eo, int rows, int C, int S, const float* __restrict__ mean,
                                              const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int act, float alpha,
-                                             float* __restrict__ p1, float* __restrict__ p2) { pdl_prologue();
+                                             float* __restrict__ p1, float* __restrict__ p2) {
   const int g = blockIdx.y, C8 = C / 8, TY = 256 / C8, c8 = threadIdx.x % C8, ty = threadIdx.x / C8, sl = blockIdx.x;
   const int chunk = (rows + S - 1) / S, r0 = sl * chunk, r1 = min(rows, r0 + chunk);
   const uint4* xg = x + (size_t)g * rows * C8; const uint4* eg = eo + (size_t)g * rows * C8;
@@ -308,7 +286,7 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_partial_bf16x8_kernel(const uin
 template <int ACTC>
 __global__ void __launch_bounds__(256, 2) bn_bwd_apply_bf16x8_kernel(const uint4* __restrict__ x, const uint4* __restrict__ eo, uint4* __restrict__ ei, int rows, int C, int groups,
                                            const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                           const float* __restrict__ beta, int act, float alpha, const float* __restrict__ c1, const float* __restrict__ c2) { pdl_prologue();
+                                           const float* __restrict__ beta, int act, float alpha, const float* __restrict__ c1, const float* __restrict__ c2) {
   // same hoisting as bn_apply_bf16x8_kernel: one thread, one channel octet
   const int C8 = C / 8; const size_t per_group = (size_t)rows * C8;
   const size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
@@ -334,7 +312,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_bf16x8_kernel(const uint4
   }
 }
 __global__ void __launch_bounds__(1024) bn_bwd_final_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int rows, int C, int S, int groups,
-                                    float* __restrict__ c1, float* __restrict__ c2, float* g_gamma, float* g_beta, int want) { pdl_prologue();
+                                    float* __restrict__ c1, float* __restrict__ c2, float* g_gamma, float* g_beta, int want) {
   __shared__ double sa[32][33], sb[32][33];      // 32 channels x 32 slice lanes: S <= 256 partial rows in ONE batch of 8 loads per thread
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, c = blockIdx.x * 32 + tx;
   double tg = 0.0, tb = 0.0;
@@ -360,7 +338,7 @@ __global__ void __launch_bounds__(1024) bn_bwd_final_kernel(const float* __restr
 template <typename T>
 __global__ void bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ eo, T* __restrict__ ei, int rows, int C, int groups,
                                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                    const float* __restrict__ beta, int act, float alpha, const float* __restrict__ c1, const float* __restrict__ c2) { pdl_prologue();
+                                    const float* __restrict__ beta, int act, float alpha, const float* __restrict__ c1, const float* __restrict__ c2) {
   size_t per_group = (size_t)rows * C, total = per_group * groups;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int c = i % C; int g = i / per_group; int k = g * C + c;
@@ -392,227 +370,178 @@ void k_bn_bwd(int prec, const void* x, const void* eps_out, void* eps_in, int ro
 }
 
 
-// ---------------------------------------------------------------- fused (cooperative) BatchNorm --------------------
-// One cooperative launch per BatchNorm forward / backward instead of three kernels: every CTA is co-resident, so the
-// batch-wide reduction is a software grid barrier between the phases of ONE kernel:
-//   phase 1   per-CTA partial sums over a contiguous chunk of rows (16-byte loads, block fold)       -> scratch[g][cta][C]
-//   phase 1.5 channel (g,c) summed over the CTAs in fixed order, in double -> mean/invstd (fwd) or c1/c2 + dgamma/dbeta (bwd)
-//   phase 2   elementwise apply; the tensor (<= tens of MB) is re-read from L2, not HBM
-// Deterministic (fixed partition, fixed order).  bf16, C % 8 == 0, C <= 2048.
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
+// ---------------------------------------------------------------- BatchNorm on 128-bit accumulators ----------------
+// north_star's "BatchNorm fused with its producer": the batch statistics arrive in acc[groups][2][2][C] (common.cuh sacc_add) from the
+// tcgen05 GEMM epilogues (kernels_tc.cu EPI_STATS / EPI_BNBWD) or from the *_stats_acc kernels below; the apply kernels turn them into
+// per-channel coefficients in shared memory (once per block, in double) and stream the tensor once.  bf16, C % 8 == 0, 256 % (C/8) == 0.
+bool k_bn_vec_ok(int prec, int C) { return vec_ok(prec, C); }
+size_t k_bn_acc_elems(int C, int groups) { return (size_t)groups * 4 * C; }
+
+template <int NV>
+__device__ __forceinline__ void block_fold_acc(float (&acc)[NV][8], int C, int c8, int ty, int TY, unsigned long long* accbase /* statistic v at accbase + v*2*C */) {
+  __shared__ float sred[NV][2048];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sred[v][ty * C + c8 * 8 + j] = acc[v][j];
   __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(counter, 1u);
-    unsigned v;
-    do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory"); } while (v < target);
-    __threadfence();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) { float a = 0.f; for (int k = 0; k < TY; ++k) a += sred[v][k * C + c]; sacc_add(accbase + (size_t)v * 2 * C, (size_t)C, (size_t)c, a); }
   }
-  __syncthreads();
+}
+__global__ void __launch_bounds__(256) bn_stats_acc_kernel(const uint4* __restrict__ x, int rows, int C, int S, unsigned long long* __restrict__ accp) {
+  const int g = blockIdx.y, C8 = C / 8, TY = 256 / C8, c8 = threadIdx.x % C8, ty = threadIdx.x / C8, sl = blockIdx.x;
+  const int chunk = (rows + S - 1) / S, r0 = sl * chunk, r1 = min(rows, r0 + chunk);
+  const uint4* xg = x + (size_t)g * rows * C8;
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
+#pragma unroll 4
+  for (int r = r0 + ty; r < r1; r += TY) { float v[8]; unpack8(xg[(size_t)r * C8 + c8], v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc[0][j] += v[j]; acc[1][j] = fmaf(v[j], v[j], acc[1][j]); } }
+  block_fold_acc<2>(acc, C, c8, ty, TY, accp + (size_t)g * 4 * C);
+}
+void k_bn_stats_acc(const void* x, int rows, int C, int groups, unsigned long long* acc, cudaStream_t s) {
+  const int S = vec_blocks(rows, C);
+  launch_pdl(bn_stats_acc_kernel, dim3(S, groups), dim3(256), (size_t)0, s, (const uint4*)x, rows, C, S, acc); LAUNCHED();
 }
 
-__global__ void __launch_bounds__(256, 3) bn_fwd_fused_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int rows, int C, int groups, float* __restrict__ scratch,
-                                                           float* __restrict__ mean, float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                           int act, float alpha, float eps, const float* __restrict__ run_mean, const float* __restrict__ run_var,
-                                                           float* g_mean, float* g_var, float decay, unsigned* counter) { pdl_prologue();
-  const int C8 = C / 8, TY = 256 / C8, c8 = threadIdx.x % C8, ty = threadIdx.x / C8, S = gridDim.x, sl = blockIdx.x;
-  float* psum = scratch; float* psq = scratch + (size_t)groups * S * C;
-  const int chunk = (rows + S - 1) / S, r0 = sl * chunk, r1 = min(rows, r0 + chunk);
-  for (int g = 0; g < groups; ++g) {
-    const uint4* xg = x + (size_t)g * rows * C8;
-    float acc[2][8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
-    int r = r0 + ty;
-    for (; r + 3 * TY < r1; r += 4 * TY) {     // 4 independent 16-byte loads in flight per thread
-      uint4 u[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) u[q] = xg[(size_t)(r + q * TY) * C8 + c8];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) { float v[8]; unpack8(u[q], v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { acc[0][j] += v[j]; acc[1][j] = fmaf(v[j], v[j], acc[1][j]); } }
-    }
-    for (; r < r1; r += TY) { float v[8]; unpack8(xg[(size_t)r * C8 + c8], v);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { acc[0][j] += v[j]; acc[1][j] = fmaf(v[j], v[j], acc[1][j]); } }
-    float* const dst[2] = {psum, psq};
-    block_fold_write<2>(acc, C, C8, c8, ty, TY, dst, ((size_t)g * S + sl) * C);
-    __syncthreads();
-  }
-  grid_barrier(counter, gridDim.x);
-  {  // phase 1.5: 128 threads per channel (two channels per CTA pass), <=5 partial rows per thread all in flight, fixed-order tree in double
-    __shared__ double swa[8], swb[8];
-    const int half = threadIdx.x >> 7, t = threadIdx.x & 127, lane = threadIdx.x & 31, wih = (threadIdx.x >> 5) & 3;
-    for (int cb = blockIdx.x * 2; cb < C; cb += gridDim.x * 2) {
-      const int c = cb + half; double agm = 0.0, agv = 0.0;
-      for (int g = 0; g < groups; ++g) {
-        double a = 0.0, b = 0.0;
-        if (c < C) { float va[5], vb[5];
-#pragma unroll
-          for (int q = 0; q < 5; ++q) { const int k = t + 128 * q; va[q] = k < S ? __ldcg(psum + ((size_t)g * S + k) * C + c) : 0.f; vb[q] = k < S ? __ldcg(psq + ((size_t)g * S + k) * C + c) : 0.f; }
-#pragma unroll
-          for (int q = 0; q < 5; ++q) { a += va[q]; b += vb[q]; } }
-        for (int m = 16; m; m >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, m); b += __shfl_xor_sync(0xffffffffu, b, m); }
-        __syncthreads();
-        if (lane == 0) { swa[half * 4 + wih] = a; swb[half * 4 + wih] = b; }
-        __syncthreads();
-        if (t == 0 && c < C) {
-          a = swa[half * 4] + swa[half * 4 + 1] + swa[half * 4 + 2] + swa[half * 4 + 3]; b = swb[half * 4] + swb[half * 4 + 1] + swb[half * 4 + 2] + swb[half * 4 + 3];
-          const double mu = a / rows; double var = b / rows - mu * mu; if (var < 0) var = 0;
-          mean[g * C + c] = (float)mu; invstd[g * C + c] = (float)(1.0 / sqrt(var + (double)eps));
-          if (g_mean) { agm += (1.0 - decay) * ((double)run_mean[c] - mu); agv += (1.0 - decay) * ((double)run_var[c] - var); }
-        }
+// dynamic shared memory: [groups][2][C] floats = (scale, shift)
+template <int ACTC>
+__global__ void __launch_bounds__(256, 3) bn_apply_acc_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int rows, int C, int groups, const unsigned long long* __restrict__ accp,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta, int act, float alpha, float eps, float* __restrict__ coef,
+                                                             const float* __restrict__ run_mean, const float* __restrict__ run_var, float* g_mean, float* g_var, float decay) {
+  extern __shared__ float s_cf[];
+  const bool writer = blockIdx.x == 0;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double agm = 0.0, agv = 0.0;
+    for (int g = 0; g < groups; ++g) {
+      const unsigned long long* a = accp + (size_t)g * 4 * C;
+      const double mu = sacc_read(a, (size_t)C, (size_t)c) / rows; double var = sacc_read(a + 2 * (size_t)C, (size_t)C, (size_t)c) / rows - mu * mu; if (var < 0) var = 0;
+      const float is = (float)(1.0 / sqrt(var + (double)eps)), sc = gamma[c] * is, sh = fmaf(-(float)mu, sc, beta[c]);
+      s_cf[(g * 2 + 0) * C + c] = sc; s_cf[(g * 2 + 1) * C + c] = sh;
+      if (writer) {
+        coef[(size_t)(g * 4 + 0) * C + c] = sc; coef[(size_t)(g * 4 + 1) * C + c] = sh; coef[(size_t)(g * 4 + 2) * C + c] = (float)mu; coef[(size_t)(g * 4 + 3) * C + c] = is;
+        if (g_mean) { agm += (1.0 - decay) * ((double)run_mean[c] - mu); agv += (1.0 - decay) * ((double)run_var[c] - var); }
       }
-      if (g_mean && t == 0 && c < C) { g_mean[c] = (float)(agm / groups); g_var[c] = (float)(agv / groups); }
     }
+    // BatchNormalization running stats as pseudo-gradients through a NoOp updater; groups (the two D minibatches) averaged
+    if (writer && g_mean) { g_mean[c] = (float)(agm / groups); g_var[c] = (float)(agv / groups); }
   }
-  grid_barrier(counter, 2 * gridDim.x);
-  const size_t per_group = (size_t)rows * C8, total = per_group * groups;
-  // phase 2: blockDim (256) is a multiple of C/8, so a thread keeps the same 8 channels for every element it touches:
-  // fold (mean, invstd, gamma, beta) into one scale/shift pair per channel, once per group
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  (void)total;
+  __syncthreads();
+  const int C8 = C / 8; const size_t per_group = (size_t)rows * C8;
+  const size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  const int c0 = (int)(t0 % C8) * 8;
   for (int g = 0; g < groups; ++g) {
     float sc[8], sh[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { const int c = c8 * 8 + j; const float is = __ldcg(invstd + g * C + c); sc[j] = gamma[c] * is; sh[j] = fmaf(-__ldcg(mean + g * C + c), sc[j], beta[c]); }
-    const uint4* xg = x + (size_t)g * per_group; uint4* yg = y + (size_t)g * per_group;
-    for (size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i0 < per_group; i0 += 4 * stride) {
-      uint4 u[4];
+    for (int j = 0; j < 8; ++j) { sc[j] = s_cf[(g * 2 + 0) * C + c0 + j]; sh[j] = s_cf[(g * 2 + 1) * C + c0 + j]; }
+    const uint4* xg = x + g * per_group; uint4* yg = y + g * per_group;
+    for (size_t i = t0; i < per_group; i += 4 * stride) {        // four independent 16-byte loads in flight per thread
+      uint4 xa[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { const size_t i = i0 + q * stride; if (i < per_group) u[q] = xg[i]; }
+      for (int q = 0; q < 4; ++q) if (i + q * stride < per_group) xa[q] = xg[i + q * stride];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { const size_t i = i0 + q * stride; if (i >= per_group) break;
-        float v[8]; unpack8(u[q], v);
+      for (int q = 0; q < 4; ++q) if (i + q * stride < per_group) {
+        float v[8]; unpack8(xa[q], v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = act_fwd(act, fmaf(v[j], sc[j], sh[j]), alpha);
-        yg[i] = pack8(v); }
+        for (int j = 0; j < 8; ++j) v[j] = act_fwd(ACTC < 0 ? act : ACTC, fmaf(v[j], sc[j], sh[j]), alpha);
+        yg[i + q * stride] = pack8(v);
+      }
     }
   }
 }
+void k_bn_apply_acc(const void* x, void* y, int rows, int C, int groups, const unsigned long long* acc, const float* gamma, const float* beta, int act, float alpha, float eps,
+                    float* coef, const float* run_mean, const float* run_var, float* g_mean, float* g_var, float decay, cudaStream_t s) {
+  const size_t smem = sizeof(float) * 2 * groups * C;
+  DISPATCH_ACT(act, ACTC, launch_pdl(bn_apply_acc_kernel<ACTC>, dim3(vec4_blocks((size_t)rows * C / 8)), dim3(256), smem, s, (const uint4*)x, (uint4*)y, rows, C, groups, acc, gamma, beta, act, alpha, eps,
+                                     coef, run_mean, run_var, g_mean, g_var, decay));
+  LAUNCHED();
+}
 
-__global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(const uint4* __restrict__ x, const uint4* __restrict__ eo, uint4* __restrict__ ei, int rows, int C, int groups,
-                                                           const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                           int act, float alpha, float* __restrict__ scratch, float* g_gamma, float* g_beta, int want, unsigned* counter) { pdl_prologue();
-  const int C8 = C / 8, TY = 256 / C8, c8 = threadIdx.x % C8, ty = threadIdx.x / C8, S = gridDim.x, sl = blockIdx.x;
-  float* p1 = scratch; float* p2 = p1 + (size_t)groups * S * C; float* c1 = p2 + (size_t)groups * S * C; float* c2 = c1 + (size_t)groups * C;
+template <int ACTC>
+__global__ void __launch_bounds__(256, 3) bn_bwd_stats_acc_kernel(const uint4* __restrict__ x, const uint4* __restrict__ eo, int rows, int C, int S, const float* __restrict__ coef,
+                                                                 int act, float alpha, unsigned long long* __restrict__ accp) {
+  const int g = blockIdx.y, C8 = C / 8, TY = 256 / C8, c8 = threadIdx.x % C8, ty = threadIdx.x / C8, sl = blockIdx.x;
   const int chunk = (rows + S - 1) / S, r0 = sl * chunk, r1 = min(rows, r0 + chunk);
-  for (int g = 0; g < groups; ++g) {
-    const uint4* xg = x + (size_t)g * rows * C8; const uint4* eg = eo + (size_t)g * rows * C8;
-    float mu[8], is[8], ga[8], be[8], acc[2][8];
+  const uint4* xg = x + (size_t)g * rows * C8; const uint4* eg = eo + (size_t)g * rows * C8;
+  float sc[8], sh[8], mu[8], is[8], acc[2][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { const int c = c8 * 8 + j; mu[j] = mean[g * C + c]; is[j] = invstd[g * C + c]; ga[j] = gamma[c]; be[j] = beta[c]; acc[0][j] = 0.f; acc[1][j] = 0.f; }
-    int r = r0 + ty;
-    for (; r + 3 * TY < r1; r += 4 * TY) {
-      uint4 ux[4], ue[4];
+  for (int j = 0; j < 8; ++j) { const int c = c8 * 8 + j; sc[j] = coef[(size_t)(g * 4 + 0) * C + c]; sh[j] = coef[(size_t)(g * 4 + 1) * C + c]; mu[j] = coef[(size_t)(g * 4 + 2) * C + c]; is[j] = coef[(size_t)(g * 4 + 3) * C + c]; acc[0][j] = 0.f; acc[1][j] = 0.f; }
+#pragma unroll 4
+  for (int r = r0 + ty; r < r1; r += TY) {
+    float xv[8], ev[8]; unpack8(xg[(size_t)r * C8 + c8], xv); unpack8(eg[(size_t)r * C8 + c8], ev);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { ux[q] = xg[(size_t)(r + q * TY) * C8 + c8]; ue[q] = eg[(size_t)(r + q * TY) * C8 + c8]; }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) { float xv[8], ev[8]; unpack8(ux[q], xv); unpack8(ue[q], ev);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { const float xh = (xv[j] - mu[j]) * is[j]; const float dy = ev[j] * act_grad_from_pre(act, fmaf(ga[j], xh, be[j]), alpha); acc[0][j] += dy; acc[1][j] = fmaf(dy, xh, acc[1][j]); } }
-    }
-    for (; r < r1; r += TY) {
-      float xv[8], ev[8]; unpack8(xg[(size_t)r * C8 + c8], xv); unpack8(eg[(size_t)r * C8 + c8], ev);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { const float xh = (xv[j] - mu[j]) * is[j]; const float dy = ev[j] * act_grad_from_pre(act, fmaf(ga[j], xh, be[j]), alpha); acc[0][j] += dy; acc[1][j] = fmaf(dy, xh, acc[1][j]); }
-    }
-    float* const dst[2] = {p1, p2};
-    block_fold_write<2>(acc, C, C8, c8, ty, TY, dst, ((size_t)g * S + sl) * C);
-    __syncthreads();
+    for (int j = 0; j < 8; ++j) { const float xh = (xv[j] - mu[j]) * is[j]; const float dy = ev[j] * act_grad_from_pre(ACTC < 0 ? act : ACTC, fmaf(xv[j], sc[j], sh[j]), alpha); acc[0][j] += dy; acc[1][j] = fmaf(dy, xh, acc[1][j]); }
   }
-  grid_barrier(counter, gridDim.x);
-  {
-    __shared__ double swa[8], swb[8];
-    const int half = threadIdx.x >> 7, t = threadIdx.x & 127, lane = threadIdx.x & 31, wih = (threadIdx.x >> 5) & 3;
-    for (int cb = blockIdx.x * 2; cb < C; cb += gridDim.x * 2) {
-      const int c = cb + half; double tg = 0.0, tb = 0.0;
-      for (int g = 0; g < groups; ++g) {
-        double a = 0.0, b = 0.0;
-        if (c < C) { float va[5], vb[5];
-#pragma unroll
-          for (int q = 0; q < 5; ++q) { const int k = t + 128 * q; va[q] = k < S ? __ldcg(p1 + ((size_t)g * S + k) * C + c) : 0.f; vb[q] = k < S ? __ldcg(p2 + ((size_t)g * S + k) * C + c) : 0.f; }
-#pragma unroll
-          for (int q = 0; q < 5; ++q) { a += va[q]; b += vb[q]; } }
-        for (int m = 16; m; m >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, m); b += __shfl_xor_sync(0xffffffffu, b, m); }
-        __syncthreads();
-        if (lane == 0) { swa[half * 4 + wih] = a; swb[half * 4 + wih] = b; }
-        __syncthreads();
-        if (t == 0 && c < C) {
-          a = swa[half * 4] + swa[half * 4 + 1] + swa[half * 4 + 2] + swa[half * 4 + 3]; b = swb[half * 4] + swb[half * 4 + 1] + swb[half * 4 + 2] + swb[half * 4 + 3];
-          c1[g * C + c] = (float)(a / rows); c2[g * C + c] = (float)(b / rows); tb += a; tg += b;
-        }
-      }
-      if (want && t == 0 && c < C) { g_beta[c] += (float)tb; g_gamma[c] += (float)tg; }
+  block_fold_acc<2>(acc, C, c8, ty, TY, accp + (size_t)g * 4 * C);
+}
+void k_bn_bwd_stats_acc(const void* x, const void* eps_out, int rows, int C, int groups, const float* coef, int act, float alpha, unsigned long long* acc, cudaStream_t s) {
+  const int S = vec_blocks(rows, C);
+  DISPATCH_ACT(act, ACTC, launch_pdl(bn_bwd_stats_acc_kernel<ACTC>, dim3(S, groups), dim3(256), (size_t)0, s, (const uint4*)x, (const uint4*)eps_out, rows, C, S, coef, act, alpha, acc));
+  LAUNCHED();
+}
+
+// dynamic shared memory: [groups][2][C] floats = (mean of dy', mean of dy'*xhat)
+template <int ACTC, bool PREMUL>
+__global__ void __launch_bounds__(256, 2) bn_bwd_apply_acc_kernel(const uint4* __restrict__ x, const uint4* __restrict__ eo, uint4* __restrict__ ei, int rows, int C, int groups,
+                                                                 const float* __restrict__ coef, int act, float alpha, const unsigned long long* __restrict__ accp,
+                                                                 float* g_gamma, float* g_beta, int want) {
+  extern __shared__ float s_k[];
+  const bool writer = blockIdx.x == 0 && want;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double tb = 0.0, tg = 0.0;
+    for (int g = 0; g < groups; ++g) {
+      const unsigned long long* a = accp + (size_t)g * 4 * C;
+      const double s1 = sacc_read(a, (size_t)C, (size_t)c), s2 = sacc_read(a + 2 * (size_t)C, (size_t)C, (size_t)c);
+      s_k[(g * 2 + 0) * C + c] = (float)(s1 / rows); s_k[(g * 2 + 1) * C + c] = (float)(s2 / rows); tb += s1; tg += s2;
     }
+    if (writer) { g_beta[c] += (float)tb; g_gamma[c] += (float)tg; }
   }
+  __syncthreads();
   if (!ei) return;
-  grid_barrier(counter, 2 * gridDim.x);
-  const size_t per_group = (size_t)rows * C8, total = per_group * groups;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  (void)total;
+  const int C8 = C / 8; const size_t per_group = (size_t)rows * C8;
+  const size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  const int c0 = (int)(t0 % C8) * 8;
   for (int g = 0; g < groups; ++g) {
-    float mu[8], is[8], ga[8], be[8], k1[8], k2[8];
+    float sc[8], sh[8], mu[8], is[8], k1[8], k2[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { const int c = c8 * 8 + j, k = g * C + c; mu[j] = mean[k]; is[j] = invstd[k]; ga[j] = gamma[c]; be[j] = beta[c]; k1[j] = __ldcg(c1 + k); k2[j] = __ldcg(c2 + k); }
-    const uint4* xg = x + (size_t)g * per_group; const uint4* eg = eo + (size_t)g * per_group; uint4* og = ei + (size_t)g * per_group;
-    for (size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i0 < per_group; i0 += 4 * stride) {
-      uint4 ux[4], ue[4];
+    for (int j = 0; j < 8; ++j) { const int c = c0 + j; sc[j] = coef[(size_t)(g * 4 + 0) * C + c]; sh[j] = coef[(size_t)(g * 4 + 1) * C + c]; mu[j] = coef[(size_t)(g * 4 + 2) * C + c]; is[j] = coef[(size_t)(g * 4 + 3) * C + c];
+      k1[j] = s_k[(g * 2 + 0) * C + c]; k2[j] = s_k[(g * 2 + 1) * C + c]; }
+    const uint4* xg = x + g * per_group; const uint4* eg = eo + g * per_group; uint4* ig = ei + g * per_group;
+    for (size_t i = t0; i < per_group; i += 4 * stride) {
+      uint4 xa[4], ea[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { const size_t i = i0 + q * stride; if (i < per_group) { ux[q] = xg[i]; ue[q] = eg[i]; } }
+      for (int q = 0; q < 4; ++q) if (i + q * stride < per_group) { xa[q] = xg[i + q * stride]; ea[q] = eg[i + q * stride]; }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { const size_t i = i0 + q * stride; if (i >= per_group) break;
-        float xv[8], ev[8], o[8]; unpack8(ux[q], xv); unpack8(ue[q], ev);
+      for (int q = 0; q < 4; ++q) if (i + q * stride < per_group) {
+        float xv[8], ev[8], o[8]; unpack8(xa[q], xv); unpack8(ea[q], ev);
 #pragma unroll
         for (int j = 0; j < 8; ++j) { const float xh = (xv[j] - mu[j]) * is[j];
-          const float dy = ev[j] * act_grad_from_pre(act, fmaf(ga[j], xh, be[j]), alpha); o[j] = ga[j] * is[j] * (dy - k1[j] - xh * k2[j]); }
-        og[i] = pack8(o); }
+          const float dy = PREMUL ? ev[j] : ev[j] * act_grad_from_pre(ACTC < 0 ? act : ACTC, fmaf(xv[j], sc[j], sh[j]), alpha); o[j] = sc[j] * (dy - k1[j] - xh * k2[j]); }
+        ig[i + q * stride] = pack8(o);
+      }
     }
   }
 }
-
-static int coop_grid(const void* fn, int rows) {
-  static int sms = 0;
-  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-  int per_sm = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0);
-  if (per_sm < 1) return 0; if (per_sm > 3) per_sm = 3;
-  int g = sms * per_sm; int cap = rows / 8; if (cap < 1) cap = 1; if (g > cap) g = cap;
-  return g;
-}
-// Measured on B200 (round 1): the two software grid barriers + the serial channel pass cost ~15-20 us per launch, which is no better
-// than three small graph nodes (2.43-2.49 ms/step vs 2.31 ms), so the cooperative path is opt-in (B2G_FUSED_BN=1) until it is.
-bool k_bn_fused_ok(int prec, int C, int groups) {
-  static int on = -1; if (on < 0) { const char* e = getenv("B2G_FUSED_BN"); on = (e && e[0] == '1') ? 1 : 0; }
-  return on && vec_ok(prec, C) && (size_t)148 * 4 * C <= (size_t)SLICE_ELEMS;
-}
-// returns 0 on success
-int k_bn_fwd_fused(const void* x, void* y, int rows, int C, int groups, float* scratch, float* mean, float* invstd, const float* gamma, const float* beta,
-                   int act, float alpha, float eps, const float* run_mean, const float* run_var, float* g_mean, float* g_var, float decay, unsigned* counter, cudaStream_t s) {
-  int grid = coop_grid((const void*)bn_fwd_fused_kernel, rows); if (grid < 1) return -1;
-  if (cudaMemsetAsync(counter, 0, sizeof(unsigned), s) != cudaSuccess) return -1;
-  void* args[] = {(void*)&x, (void*)&y, (void*)&rows, (void*)&C, (void*)&groups, (void*)&scratch, (void*)&mean, (void*)&invstd, (void*)&gamma, (void*)&beta, (void*)&act, (void*)&alpha,
-                  (void*)&eps, (void*)&run_mean, (void*)&run_var, (void*)&g_mean, (void*)&g_var, (void*)&decay, (void*)&counter};
-  if (cudaLaunchCooperativeKernel((const void*)bn_fwd_fused_kernel, dim3(grid), dim3(256), args, 0, s) != cudaSuccess) return -1;
-  LAUNCHED(); return 0;
-}
-int k_bn_bwd_fused(const void* x, const void* eo, void* ei, int rows, int C, int groups, const float* mean, const float* invstd, const float* gamma, const float* beta,
-                   int act, float alpha, float* scratch, float* g_gamma, float* g_beta, int want, unsigned* counter, cudaStream_t s) {
-  int grid = coop_grid((const void*)bn_bwd_fused_kernel, rows); if (grid < 1) return -1;
-  if (cudaMemsetAsync(counter, 0, sizeof(unsigned), s) != cudaSuccess) return -1;
-  void* args[] = {(void*)&x, (void*)&eo, (void*)&ei, (void*)&rows, (void*)&C, (void*)&groups, (void*)&mean, (void*)&invstd, (void*)&gamma, (void*)&beta, (void*)&act, (void*)&alpha,
-                  (void*)&scratch, (void*)&g_gamma, (void*)&g_beta, (void*)&want, (void*)&counter};
-  if (cudaLaunchCooperativeKernel((const void*)bn_bwd_fused_kernel, dim3(grid), dim3(256), args, 0, s) != cudaSuccess) return -1;
-  LAUNCHED(); return 0;
+void k_bn_bwd_apply_acc(const void* x, const void* eps_out, void* eps_in, int rows, int C, int groups, const float* coef, int act, float alpha, int premul,
+                        const unsigned long long* acc, float* g_gamma, float* g_beta, int want, cudaStream_t s) {
+  const size_t smem = sizeof(float) * 2 * groups * C;
+  const dim3 grid(eps_in ? vec4_blocks((size_t)rows * C / 8) : 1);
+  if (premul) { launch_pdl(bn_bwd_apply_acc_kernel<ACT_IDENTITY, true>, grid, dim3(256), smem, s, (const uint4*)x, (const uint4*)eps_out, (uint4*)eps_in, rows, C, groups, coef, act, alpha, acc, g_gamma, g_beta, want); }
+  else { DISPATCH_ACT(act, ACTC, launch_pdl(bn_bwd_apply_acc_kernel<ACTC, false>, grid, dim3(256), smem, s, (const uint4*)x, (const uint4*)eps_out, (uint4*)eps_in, rows, C, groups, coef, act, alpha, acc, g_gamma, g_beta, want)); }
+  LAUNCHED();
 }
 
 // ---------------------------------------------------------------- activations ---------------------------
 template <typename T>
-__global__ void act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, size_t n, int act, float alpha) { pdl_prologue();
+__global__ void act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, size_t n, int act, float alpha) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) stf(y, i, act_fwd(act, ldf(x, i), alpha));
 }
 template <typename T>
-__global__ void act_bwd_out_kernel(const T* __restrict__ a, const T* __restrict__ eo, T* __restrict__ ei, size_t n, int act, float alpha) { pdl_prologue();
+__global__ void act_bwd_out_kernel(const T* __restrict__ a, const T* __restrict__ eo, T* __restrict__ ei, size_t n, int act, float alpha) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     stf(ei, i, ldf(eo, i) * act_grad_from_out(act, ldf(a, i), alpha));
 }
@@ -621,7 +550,7 @@ void k_act_fwd(int prec, const void* x, void* y, size_t n, int act, float alpha,
 }
 // bf16, 16-byte vectors (n % 8 == 0): the D1 / G-last activation derivative runs over the largest tensors of the step
 template <int ACTC>
-__global__ void __launch_bounds__(256, 4) act_bwd_out_bf16x8_kernel(const uint4* __restrict__ a, const uint4* __restrict__ eo, uint4* __restrict__ ei, size_t n8, int act, float alpha) { pdl_prologue();
+__global__ void __launch_bounds__(256, 4) act_bwd_out_bf16x8_kernel(const uint4* __restrict__ a, const uint4* __restrict__ eo, uint4* __restrict__ ei, size_t n8, int act, float alpha) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += 4 * stride) {
     uint4 aa[4], ea[4];
@@ -647,7 +576,7 @@ void k_sigmoid_out(int prec, const void* z, void* p, size_t n, cudaStream_t s) {
 
 // ---------------------------------------------------------------- max-pool / upsample ---------------------
 template <typename T>
-__global__ void maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint8_t* __restrict__ arg, int N, int H, int W, int C, int OH, int OW, int KH, int KW, int SH, int SW) { pdl_prologue();
+__global__ void maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint8_t* __restrict__ arg, int N, int H, int W, int C, int OH, int OW, int KH, int KW, int SH, int SW) {
   size_t total = (size_t)N * OH * OW * C;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int c = i % C; size_t t = i / C; int ox = t % OW; t /= OW; int oy = t % OH; size_t n = t / OH;
@@ -660,7 +589,7 @@ __global__ void maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, u
   }
 }
 template <typename T>
-__global__ void maxpool_bwd_kernel(const T* __restrict__ eo, const uint8_t* __restrict__ arg, T* __restrict__ ei, int N, int H, int W, int C, int OH, int OW, int KH, int KW, int SH, int SW) { pdl_prologue();
+__global__ void maxpool_bwd_kernel(const T* __restrict__ eo, const uint8_t* __restrict__ arg, T* __restrict__ ei, int N, int H, int W, int C, int OH, int OW, int KH, int KW, int SH, int SW) {
   // gather form (deterministic): each input pixel sums the eps of the windows whose arg-max it is
   size_t total = (size_t)N * H * W * C;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -683,7 +612,7 @@ void k_maxpool_bwd(int prec, const void* eo, const uint8_t* arg, void* ei, int N
   DISPATCH_PREC(prec, T, (launch_pdl(maxpool_bwd_kernel<T>, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, (const T*)eo, arg, (T*)ei, N, H, W, C, OH, OW, KH, KW, SH, SW))); LAUNCHED();
 }
 template <typename T>
-__global__ void upsample_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int f) { pdl_prologue();
+__global__ void upsample_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int f) {
   size_t total = (size_t)N * H * f * W * f * C;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int c = i % C; size_t t = i / C; int ox = t % (W * f); t /= (W * f); int oy = t % (H * f); size_t n = t / (H * f);
@@ -691,7 +620,7 @@ __global__ void upsample_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, 
   }
 }
 template <typename T>
-__global__ void upsample_bwd_kernel(const T* __restrict__ eo, T* __restrict__ ei, int N, int H, int W, int C, int f) { pdl_prologue();
+__global__ void upsample_bwd_kernel(const T* __restrict__ eo, T* __restrict__ ei, int N, int H, int W, int C, int f) {
   size_t total = (size_t)N * H * W * C;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int c = i % C; size_t t = i / C; int ix = t % W; t /= W; int iy = t % H; size_t n = t / H;
@@ -712,7 +641,7 @@ void k_upsample_bwd(int prec, const void* eo, void* ei, int N, int H, int W, int
 // ---------------------------------------------------------------- XENT ---------------------------------
 // LossBinaryXENT + sigmoid on the logit (J:159-163): clip_eps>0 DL4J-exact, 0 = BCE-with-logits.
 template <typename T>
-__global__ void xent_kernel(const T* __restrict__ z, const float* __restrict__ y, T* __restrict__ dz, float* __restrict__ loss_sums, int rows, float clip) { pdl_prologue();
+__global__ void xent_kernel(const T* __restrict__ z, const float* __restrict__ y, T* __restrict__ dz, float* __restrict__ loss_sums, int rows, float clip) {
   int g = blockIdx.x;
   __shared__ double red[32];
   double acc = 0.0;
@@ -741,7 +670,7 @@ void k_xent(int prec, const void* z, const float* y, void* dz, float* loss_sums,
 
 // LossMCXENT with softmax (J:357-362), K classes per row: one thread per row, block-level loss sum
 template <typename T>
-__global__ void softmax_xent_kernel(const T* __restrict__ z, const float* __restrict__ y, T* __restrict__ dz, T* __restrict__ p_out, float* __restrict__ loss_sum, int rows, int K) { pdl_prologue();
+__global__ void softmax_xent_kernel(const T* __restrict__ z, const float* __restrict__ y, T* __restrict__ dz, T* __restrict__ p_out, float* __restrict__ loss_sum, int rows, int K) {
   __shared__ double red[32];
   double acc = 0.0;
   for (int r = threadIdx.x; r < rows; r += blockDim.x) {
@@ -764,13 +693,13 @@ void k_softmax_xent(int prec, const void* z, const float* y, void* dz, void* p_o
 
 // ---------------------------------------------------------------- column sum / misc reductions -----------
 template <typename T>
-__global__ void colsum_partial_kernel(const T* __restrict__ x, int rows, int C, int S, float* __restrict__ p) { pdl_prologue();
+__global__ void colsum_partial_kernel(const T* __restrict__ x, int rows, int C, int S, float* __restrict__ p) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x; if (idx >= S * C) return;
   int c = idx % C, sl = idx / C; float a = 0.f;
   for (int r = sl; r < rows; r += S) a += ldf(x, (size_t)r * C + c);
   p[(size_t)sl * C + c] = a;
 }
-__global__ void __launch_bounds__(256) colsum_partial_bf16x8_kernel(const uint4* __restrict__ x, int rows, int C, int S, float* __restrict__ p) { pdl_prologue();
+__global__ void __launch_bounds__(256) colsum_partial_bf16x8_kernel(const uint4* __restrict__ x, int rows, int C, int S, float* __restrict__ p) {
   const int C8 = C / 8, TY = 256 / C8, c8 = threadIdx.x % C8, ty = threadIdx.x / C8, sl = blockIdx.x;
   const int chunk = (rows + S - 1) / S, r0 = sl * chunk, r1 = min(rows, r0 + chunk);
   float acc[1][8];
@@ -782,7 +711,7 @@ __global__ void __launch_bounds__(256) colsum_partial_bf16x8_kernel(const uint4*
   float* const dst[1] = {p};
   block_fold_write<1>(acc, C, C8, c8, ty, TY, dst, (size_t)sl * C);
 }
-__global__ void __launch_bounds__(512) colsum_final_kernel(const float* __restrict__ p, int C, int S, float* out, int accumulate) { pdl_prologue();
+__global__ void __launch_bounds__(512) colsum_final_kernel(const float* __restrict__ p, int C, int S, float* out, int accumulate) {
   __shared__ double sa[16][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, c = blockIdx.x * 32 + tx;
   double a = 0.0;
@@ -800,7 +729,7 @@ __global__ void __launch_bounds__(512) colsum_final_kernel(const float* __restri
 // bf16, C <= 4 (the G-last bias gradient: 3 channels x every pixel of the batch), rows % 8 == 0: a thread walks groups of 8 pixels = C 16-byte
 // vectors (element k of a group belongs to channel k % C), block-folds its C sums and writes one partial row; <= 256 partial rows
 template <int C>
-__global__ void __launch_bounds__(256) colsum_small_c_kernel(const uint4* __restrict__ x, size_t groups8, float* __restrict__ p) { pdl_prologue();
+__global__ void __launch_bounds__(256) colsum_small_c_kernel(const uint4* __restrict__ x, size_t groups8, float* __restrict__ p) {
   float acc[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) acc[c] = 0.f;
@@ -839,7 +768,7 @@ void k_colsum(int prec, const void* x, int rows, int C, float* scratch, float* o
   LAUNCHED();
   launch_pdl(colsum_final_kernel, dim3((C + 31) / 32), dim3(512), (size_t)(0), s, scratch, C, S, out, accumulate); LAUNCHED();
 }
-__global__ void sumsq_segments_kernel(const float* __restrict__ p, const int64_t* off, const int64_t* len, const float* coef, int nseg, double* out) { pdl_prologue();
+__global__ void sumsq_segments_kernel(const float* __restrict__ p, const int64_t* off, const int64_t* len, const float* coef, int nseg, double* out) {
   __shared__ double red[32];
   double acc = 0.0;
   for (int sgi = 0; sgi < nseg; ++sgi) {
@@ -855,7 +784,7 @@ __global__ void sumsq_segments_kernel(const float* __restrict__ p, const int64_t
 void k_sumsq_segments(const float* p, const int64_t* so, const int64_t* sl, const float* sc, int nseg, double* out, cudaStream_t s) {
   launch_pdl(sumsq_segments_kernel, dim3(1), dim3(1024), (size_t)(0), s, p, so, sl, sc, nseg, out); LAUNCHED();
 }
-__global__ void reduce_splits_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n, int splits, size_t stride, int accumulate) { pdl_prologue();
+__global__ void reduce_splits_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n, int splits, size_t stride, int accumulate) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float a = accumulate ? dst[i] : 0.f;
     for (int k = 0; k < splits; ++k) a += src[(size_t)k * stride + i];
@@ -864,7 +793,7 @@ __global__ void reduce_splits_kernel(const float* __restrict__ src, float* __res
 }
 // many splits, few outputs (the 3-channel edge weight gradients: ~300 partials of 3072 values): one warp per output element, lanes
 // stride over the splits, fixed-order shuffle tree
-__global__ void reduce_splits_wide_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n, int splits, size_t stride, int accumulate) { pdl_prologue();
+__global__ void reduce_splits_wide_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n, int splits, size_t stride, int accumulate) {
   const size_t o = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5; const int lane = threadIdx.x & 31;
   if (o >= n) return;
   float a = 0.f;
@@ -879,11 +808,50 @@ void k_reduce_splits(const float* src, float* dst, size_t n, int splits, size_t 
   if (!n) return; launch_pdl(reduce_splits_kernel, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, src, dst, n, splits, stride, accumulate); LAUNCHED();
 }
 
+// every split-K partial sum of a backward pass in ONE launch: block -> (job, chunk); few splits: a thread owns 4 consecutive outputs and walks
+// the splits with float4 loads; many splits, few outputs (the 3-channel edge layers: ~300 partials of 3072 values): one warp per output
+void reduce_list_push(ReduceList* rl, const float* src, float* dst, int64_t n, int splits, int64_t stride) {
+  if (!rl || rl->count >= ReduceList::MAX_JOBS || n <= 0) return;
+  ReduceJob& j = rl->jobs[rl->count++]; j.src = src; j.dst = dst; j.n = n; j.splits = splits; j.stride = stride;
+  const bool wide = splits >= 64 && n <= (1 << 16);
+  j.blocks = wide ? -(int)((n + 7) / 8) : (int)((n + 1023) / 1024);      // negative: warp-per-output mode
+}
+__global__ void __launch_bounds__(256) reduce_multi_kernel(const ReduceList rl) {
+  int b = blockIdx.x, ji = 0;
+  while (ji < rl.count) { const int nb = abs(rl.jobs[ji].blocks); if (b < nb) break; b -= nb; ++ji; }
+  if (ji >= rl.count) return;
+  const ReduceJob& jb = rl.jobs[ji];
+  if (jb.blocks < 0) {
+    const int64_t o = (int64_t)b * 8 + (threadIdx.x >> 5); const int lane = threadIdx.x & 31;
+    if (o >= jb.n) return;
+    float a = 0.f;
+    for (int k = lane; k < jb.splits; k += 32) a += jb.src[(int64_t)k * jb.stride + o];
+    for (int m = 16; m; m >>= 1) a += __shfl_xor_sync(0xffffffffu, a, m);
+    if (lane == 0) jb.dst[o] = a;
+    return;
+  }
+  const int64_t i = ((int64_t)b * 256 + threadIdx.x) * 4;
+  if (i >= jb.n) return;
+  if (i + 4 <= jb.n && (jb.stride & 3) == 0 && ((reinterpret_cast<uintptr_t>(jb.src) | reinterpret_cast<uintptr_t>(jb.dst)) & 15) == 0) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int k = 0; k < jb.splits; ++k) { const float4 v = *reinterpret_cast<const float4*>(jb.src + (int64_t)k * jb.stride + i); a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+    *reinterpret_cast<float4*>(jb.dst + i) = a;
+  } else {
+    for (int64_t e = i; e < jb.n && e < i + 4; ++e) { float a = 0.f; for (int k = 0; k < jb.splits; ++k) a += jb.src[(int64_t)k * jb.stride + e]; jb.dst[e] = a; }
+  }
+}
+void k_reduce_multi(const ReduceList& rl, cudaStream_t s) {
+  int blocks = 0; for (int i = 0; i < rl.count; ++i) blocks += abs(rl.jobs[i].blocks);
+  if (!blocks) return;
+  launch_pdl(reduce_multi_kernel, dim3(blocks), dim3(256), (size_t)0, s, rl); LAUNCHED();
+}
+
 // ---------------------------------------------------------------- updater -------------------------------
 // One pass over params: 28 B/param for Adam (read p,g,m,v; write p,m,v), 20 B/param RmsProp, +2 B bf16 shadow.
 __global__ void __launch_bounds__(256) updater_kernel(float* __restrict__ params, const float* __restrict__ grads, float* __restrict__ st0, float* __restrict__ st1,
                                                       const UpdSeg* __restrict__ segs, const int32_t* __restrict__ chunk_seg, const int64_t* __restrict__ chunk_off,
-                                                      float inv_mb, float inv_world, const int* __restrict__ step, __nv_bfloat16* __restrict__ shadow) { pdl_prologue();
+                                                      float inv_mb, float inv_world, int* __restrict__ step, unsigned* __restrict__ ticket, __nv_bfloat16* __restrict__ shadow) {
   const UpdSeg sg = segs[chunk_seg[blockIdx.x]];
   const int64_t base = chunk_off[blockIdx.x];
   const int64_t end = min(base + (int64_t)UPD_CHUNK, sg.off + sg.len);
@@ -908,22 +876,34 @@ __global__ void __launch_bounds__(256) updater_kernel(float* __restrict__ params
       else u = g;
       if (sg.l2 != 0.f) u = fmaf(sg.l2, p, u);
       p -= u; params[i] = p;
-      if (shadow && sg.off_bf >= 0) shadow[sg.off_bf + (i - sg.off)] = __float2bfloat16_rn(p);
+      if (shadow && sg.off_bf >= 0) {
+        const __nv_bfloat16 pb = __float2bfloat16_rn(p);
+        shadow[sg.off_bf + (i - sg.off)] = pb;
+        if (sg.off_ps >= 0) {       // [O][4][4][C] element -> its one slot of the packed [(py,px,c4)][(dyr,dxc)][O] pixel-shuffle operand (kernels_tc.cu pack_deconv_ps_kernel)
+          const int e = (int)(i - sg.off), c = e % sg.ps_C, tap = (e / sg.ps_C) % 16, o = e / (sg.ps_C * 16), r = tap >> 2, sx = tap & 3;
+          const int py = (r == 0 || r == 2) ? 1 : 0, dyr = r == 3 ? -1 : r == 0 ? 1 : 0, px = (sx == 0 || sx == 2) ? 1 : 0, dxc = sx == 3 ? -1 : sx == 0 ? 1 : 0;
+          shadow[sg.off_ps + ((int64_t)((py * 8 + px * 4 + c) * 9 + (dyr + 1) * 3 + (dxc + 1))) * sg.ps_O + o] = pb;
+        }
+      }
     }
+  }
+  // iteration counter (Adam's t): every block has read *step above; the last one to get here bumps it for the next launch
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned done = atomicAdd(ticket, 1u);
+    if (done == gridDim.x - 1) { *step = t; *ticket = 0u; __threadfence(); }
   }
 }
 void k_updater(float* params, const float* grads, float* st0, float* st1, const UpdSeg* segs, const int32_t* chunk_seg, const int64_t* chunk_off,
-               int nchunks, float inv_mb, float inv_world, const int* step_dev, __nv_bfloat16* shadow, cudaStream_t s) {
+               int nchunks, float inv_mb, float inv_world, int* step_dev, unsigned* ticket, __nv_bfloat16* shadow, cudaStream_t s) {
   if (!nchunks) return;
-  launch_pdl(updater_kernel, dim3(nchunks), dim3(256), (size_t)(0), s, params, grads, st0, st1, segs, chunk_seg, chunk_off, inv_mb, inv_world, step_dev, shadow); LAUNCHED();
+  launch_pdl(updater_kernel, dim3(nchunks), dim3(256), (size_t)(0), s, params, grads, st0, st1, segs, chunk_seg, chunk_off, inv_mb, inv_world, step_dev, ticket, shadow); LAUNCHED();
 }
-
-__global__ void inc_int_kernel(int* p) { pdl_prologue(); *p += 1; }
-void k_inc_int(int* p, cudaStream_t s) { launch_pdl(inc_int_kernel, dim3(1), dim3(1), (size_t)(0), s, p); LAUNCHED(); }
-__global__ void fill_f32_kernel(float* p, float v, size_t n) { pdl_prologue();
+__global__ void fill_f32_kernel(float* p, float v, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
-__global__ void scale_f32_kernel(float* p, float v, size_t n) { pdl_prologue();
+__global__ void scale_f32_kernel(float* p, float v, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] *= v;
 }
 void k_scale_f32(float* p, float v, size_t n, cudaStream_t s) { if (!n) return; launch_pdl(scale_f32_kernel, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, p, v, n); LAUNCHED(); }

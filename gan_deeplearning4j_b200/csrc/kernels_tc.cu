@@ -74,16 +74,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
-// multicast variant: the box lands at the same CTA-relative smem offset of every CTA in `mask`, and signals the same-offset mbarrier there
-__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, uint16_t mask) {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
-               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() { asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_map(const CUtensorMap* map) { asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -121,7 +111,21 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// ------------------------------------------------------------------ conv fprop / dgrad-phase kernel -------
+
+// ------------------------------------------------------------------ conv fprop / dgrad-phase kernels -------
+// Epilogue modes (runtime, warp-uniform):
+//   EPI_PLAIN   out = act(acc * scale[c] + bias[c])                 (scale / bias optional: inference-mode BatchNorm folded in)
+//   EPI_STATS   EPI_PLAIN + per-(group, channel) sum / sum of squares of the bf16-rounded outputs: the train-mode BatchNorm
+//               statistics of the layer that follows come out of the producing GEMM (SURVEY section 7 step 5, J:132-134,197-199)
+//   EPI_BNBWD   the GEMM produces the epsilon w.r.t. the OUTPUT of a BatchNorm(+activation) layer; the epilogue reads that
+//               layer's input z at the same pixel, out = eps * act'(gamma*xhat+beta) and accumulates sum(out), sum(out * xhat):
+//               the two reductions of BatchNorm backward fall out of the dgrad epilogue
+//   EPI_ACTBWD  out = eps * act'(a) with a = the forward output of the layer below (D1's LeakyReLU, G-last's tanh)
+// Statistics: 32 rows x 32 columns per warp are column-reduced by a shuffle butterfly (31 shuffles per statistic), the four
+// epilogue warps are folded through shared memory in fixed order, and one value per (tile, channel) is added into a 128-bit
+// fixed-point accumulator with two 64-bit integer atomics (common.cuh sacc_add): integer addition commutes, so the result is
+// bit-reproducible whatever order the CTAs arrive in, and there is no partial buffer and no finalise kernel.
+
 struct TcConvParams {
   int mode;                 // 0 = fprop, 1 = dgrad in sub-pixel phase form (4x4 s2 p1)
   int Nt, Ht, Wt;           // A-tile rows = Nt images x Ht rows x Wt cols of the row grid (Nt*Ht*Wt = 128)
@@ -132,34 +136,189 @@ struct TcConvParams {
   int KW, SH, SW, PH, PW;
   int OC;                   // output channels = row length of `out`
   int outH, outW;           // spatial dims of `out`
-  const float* bias; const float* scale; int act; float alpha;     // out = act(acc * scale[c] + bias[c]); scale may be null
+  int b_mn;                 // 1: the weight tile is MN-major (rows = reduction index, 64 output channels contiguous): the straight
+                            //    [O][taps][C] copy serves the dgrad form too, no transposed weight copy exists
+  const float* bias; const float* scale; int act; float alpha;     // EPI_PLAIN / EPI_STATS
   __nv_bfloat16* out;
-  int dbg;                  // timing experiments only (B2G_TC_DBG): 1 = MMAs without waiting for data (no TMA), 2 = TMA without MMAs
+  int epi;
+  unsigned long long* acc;  // EPI_STATS / EPI_BNBWD: [groups][2][2][OC] (statistic, hi | lo, channel)
+  int imgs_per_group;
+  const __nv_bfloat16* aux; // EPI_BNBWD: the BatchNorm input z; EPI_ACTBWD: the forward output a   (same NHWC shape as `out`)
+  const float* coef;        // EPI_BNBWD: [groups][4][OC] = scale (gamma*invstd), shift (beta - mean*scale), mean, invstd
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI = EPI_PLAIN>
 struct TcSmem {
   static constexpr int A_BYTES = 128 * 128;        // 128 rows x 64 bf16
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;   // + barriers + alignment slack
+  static constexpr int STAT_OFF = BAR_OFF + 256;
+  static constexpr int TOTAL = STAT_OFF + ((EPI == EPI_STATS || EPI == EPI_BNBWD) ? 4 * 2 * BN * 4 : 0) + 1024;   // + barriers + statistics + alignment slack
 };
 
-// CL > 1: a thread-block cluster of CL CTAs that are adjacent along M (same weight tile): each CTA fetches only BN/CL rows of the
-// weight tile and TMA-multicasts them into every CTA of the cluster, so the weight traffic out of L2 drops by CL; a stage is
-// refilled only after all CL MMA issuers have committed it (tcgen05.commit multicast onto every CTA's "empty" barrier).
-// AFFINE: the epilogue is act(acc * scale[c] + bias[c]) with both arrays present (inference-mode BatchNorm folded in); otherwise
-// act(acc + bias[c]) with an optional bias.  Two instantiations keep the common path free of the extra loads.
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }    // the four epilogue warps only
+
+// column sums over the 32 lanes of a warp: on return lane l holds sum_lanes a[l] in a[0]
+__device__ __forceinline__ void warp_colsum32(float (&a)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < off; ++j) {
+      const float lo = a[j], hi = a[j + off];
+      const float send = up ? lo : hi, keep = up ? hi : lo;
+      a[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
+
+// One 128-row x BN-column accumulator tile: TMEM -> registers -> epilogue arithmetic -> bf16 -> 16-byte stores of the NHWC channel run.
+// taddr = TMEM address of (this warp's lane quadrant, first column of the tile); roff = element offset of (pixel, first channel) in `out`.
+template <int BN, int EPI, bool AFFINE>
+__device__ __forceinline__ void epi_tile(const TcConvParams& p, uint32_t taddr, size_t roff, int nb0, int group, float* sst, int q, int lane, int ep_tid) {
+  constexpr bool stats = EPI == EPI_STATS || EPI == EPI_BNBWD;
+  __nv_bfloat16* orow = p.out + roff;
+  const bool has_bias = p.bias != nullptr;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    uint32_t v[32];
+    uint4 ax[4];
+    if constexpr (EPI >= EPI_BNBWD) {
+      const uint4* ap = reinterpret_cast<const uint4*>(p.aux + roff + c0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ax[i] = ap[i];
+    }
+    tmem_ld32(taddr + (uint32_t)c0, v);
+    tmem_ld_wait();
+    float o[32], s2[32];
+    if constexpr (EPI == EPI_BNBWD) {
+      const float4* cs = reinterpret_cast<const float4*>(p.coef + (size_t)group * 4 * p.OC + nb0 + c0);
+      const int q4 = p.OC >> 2;     // float4 stride between the four coefficient arrays
+      const __nv_bfloat162* zb = reinterpret_cast<const __nv_bfloat162*>(ax);
+#define B2G_BNBWD_LOOP(ACTC)                                                                                                   \
+  _Pragma("unroll") for (int j4 = 0; j4 < 8; ++j4) {                                                                           \
+    const float4 sc = cs[j4], sh = cs[q4 + j4], mu = cs[2 * q4 + j4], is = cs[3 * q4 + j4];                                    \
+    const float2 za = __bfloat1622float2(zb[2 * j4]), zc = __bfloat1622float2(zb[2 * j4 + 1]);                                 \
+    const float z4[4] = {za.x, za.y, zc.x, zc.y}, sc4[4] = {sc.x, sc.y, sc.z, sc.w}, sh4[4] = {sh.x, sh.y, sh.z, sh.w};        \
+    const float mu4[4] = {mu.x, mu.y, mu.z, mu.w}, is4[4] = {is.x, is.y, is.z, is.w};                                          \
+    _Pragma("unroll") for (int e = 0; e < 4; ++e) {                                                                            \
+      const int j = 4 * j4 + e;                                                                                                \
+      s2[j] = (z4[e] - mu4[e]) * is4[e];                                                                                       \
+      o[j] = __uint_as_float(v[j]) * act_grad_from_pre(ACTC, fmaf(z4[e], sc4[e], sh4[e]), p.alpha);                            \
+    }                                                                                                                          \
+  }
+      if (p.act == ACT_LRELU) { B2G_BNBWD_LOOP(ACT_LRELU) }
+      else if (p.act == ACT_RELU) { B2G_BNBWD_LOOP(ACT_RELU) }
+      else { B2G_BNBWD_LOOP(p.act) }
+#undef B2G_BNBWD_LOOP
+    } else if constexpr (EPI == EPI_ACTBWD) {
+      const __nv_bfloat162* ab = reinterpret_cast<const __nv_bfloat162*>(ax);
+#define B2G_ACTBWD_LOOP(ACTC)                                                                                                  \
+  _Pragma("unroll") for (int j = 0; j < 16; ++j) {                                                                             \
+    const float2 a2 = __bfloat1622float2(ab[j]);                                                                               \
+    o[2 * j] = __uint_as_float(v[2 * j]) * act_grad_from_out(ACTC, a2.x, p.alpha);                                             \
+    o[2 * j + 1] = __uint_as_float(v[2 * j + 1]) * act_grad_from_out(ACTC, a2.y, p.alpha);                                     \
+  }
+      if (p.act == ACT_LRELU) { B2G_ACTBWD_LOOP(ACT_LRELU) }
+      else if (p.act == ACT_TANH) { B2G_ACTBWD_LOOP(ACT_TANH) }
+      else { B2G_ACTBWD_LOOP(p.act) }
+#undef B2G_ACTBWD_LOOP
+    } else {
+      // the activation switch is hoisted out of the 32-column loop: one uniform branch per chunk instead of one per element
+#define B2G_EPI_LOOP(ACTC)                                                                                                     \
+  _Pragma("unroll") for (int j = 0; j < 32; ++j) {                                                                             \
+    float a = __uint_as_float(v[j]);                                                                                           \
+    if (AFFINE) a = fmaf(a, p.scale[nb0 + c0 + j], p.bias[nb0 + c0 + j]);                                                      \
+    else if (has_bias) a += p.bias[nb0 + c0 + j];                                                                              \
+    o[j] = act_fwd(ACTC, a, p.alpha);                                                                                          \
+  }
+      if (p.act == ACT_IDENTITY) { B2G_EPI_LOOP(ACT_IDENTITY) }
+      else if (p.act == ACT_LRELU) { B2G_EPI_LOOP(ACT_LRELU) }
+      else if (p.act == ACT_RELU) { B2G_EPI_LOOP(ACT_RELU) }
+      else { B2G_EPI_LOOP(p.act) }
+#undef B2G_EPI_LOOP
+    }
+    uint32_t packed[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
+      packed[j] = *reinterpret_cast<uint32_t*>(&h);
+      if constexpr (stats) { const float2 r = __bfloat1622float2(h); o[2 * j] = r.x; o[2 * j + 1] = r.y; }      // statistics of what is stored
+    }
+    uint4* dst = reinterpret_cast<uint4*>(orow + c0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+    if constexpr (stats) {
+      if constexpr (EPI == EPI_STATS) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) s2[j] = o[j] * o[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) s2[j] = o[j] * s2[j];
+      }
+      warp_colsum32(o, lane); warp_colsum32(s2, lane);
+      sst[(q * 2 + 0) * BN + c0 + lane] = o[0];
+      sst[(q * 2 + 1) * BN + c0 + lane] = s2[0];
+    }
+  }
+  if constexpr (stats) {
+    epi_bar_sync();
+    for (int col = ep_tid; col < BN; col += 128) {
+#pragma unroll
+      for (int st = 0; st < 2; ++st) {
+        const float s = ((sst[(0 * 2 + st) * BN + col] + sst[(1 * 2 + st) * BN + col]) + sst[(2 * 2 + st) * BN + col]) + sst[(3 * 2 + st) * BN + col];
+        sacc_add(p.acc + (size_t)(group * 2 + st) * 2 * p.OC, (size_t)p.OC, (size_t)(nb0 + col), s);
+      }
+    }
+    epi_bar_sync();       // the statistics area is free again (next tile of a persistent CTA)
+  }
+}
+
+// weight tile of one K-block: K-major = one 3-D box {64 k, 1 tap, BN rows}; MN-major = BN/64 boxes {64 n, 1 tap, 64 k rows}
+template <int BN>
+__device__ __forceinline__ void load_b_tile(const TcConvParams& p, const CUtensorMap* tmB, uint32_t dst, uint32_t bar, int ch, int wtap, int nb0) {
+  if (!p.b_mn) tma_load_3d(dst, tmB, bar, ch * 64, wtap, nb0);
+  else {
+#pragma unroll
+    for (int j = 0; j < (BN >= 64 ? BN / 64 : 1); ++j) tma_load_3d(dst + j * 8192, tmB, bar, nb0 + j * 64, wtap, ch * 64);
+  }
+}
+// the 4 x (K = 16) MMAs of one K-block
+template <int BN>
+__device__ __forceinline__ void mma_kblock(uint32_t tacc, uint32_t a_smem, uint32_t b_smem, int b_mn, uint32_t accumulate_first) {
+  const uint64_t adesc = desc_kmajor_sw128(a_smem);
+  if (!b_mn) {
+    constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+    const uint64_t bdesc = desc_kmajor_sw128(b_smem);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)     // 4 x K=16 inside the 128-byte swizzle atom: +32 B = +2 in the (>>4) start-address field
+      umma_bf16(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate_first | (uint32_t)k);
+  } else {
+    constexpr uint32_t idesc = make_idesc(128, BN, 0, 1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)     // 16 reduction rows per MMA = 2048 B down the MN-major tile, 64-column blocks 8 KB apart
+      umma_bf16(tacc, adesc + 2 * k, desc_mnmajor_sw128(b_smem + k * 2048, 8192), idesc, accumulate_first | (uint32_t)k);
+  }
+}
+__device__ __forceinline__ void tap_coords(const TcConvParams& p, int ta, int tb, int py, int px, int& ax, int& dy_, int& wtap) {
+  if (p.mode == 0) { dy_ = -p.PH + ta; ax = -p.PW + tb; wtap = ta * p.KW + tb; }
+  else {
+    // output row 2*q+py takes filter rows r with (py+1-r) even: py=0 -> r=1 (dy row q), r=3 (q-1); py=1 -> r=0 (q+1), r=2 (q)
+    const int r = py == 0 ? (ta == 0 ? 1 : 3) : (ta == 0 ? 0 : 2), dyr = py == 0 ? (ta == 0 ? 0 : -1) : (ta == 0 ? 1 : 0);
+    const int sx = px == 0 ? (tb == 0 ? 1 : 3) : (tb == 0 ? 0 : 2), dxc = px == 0 ? (tb == 0 ? 0 : -1) : (tb == 0 ? 1 : 0);
+    dy_ = dyr; ax = dxc; wtap = r * 4 + sx;
+  }
+}
+
+// One warp-specialised CTA per 128 x BN output tile.
 // PS ("pixel shuffle", BN = 16): the 4x4 stride-2 pad-1 transposed conv onto <= 4 image channels (G-last forward, D1 input gradient) as ONE
 // 3x3 stride-1 pad-1 convolution whose 16 output columns are (py, px, c) = the 2x2 output block x 4 (padded) channels: the four
 // sub-pixel phases share every activation load (9 taps instead of 4 x 4), the packed weight [16][9][O] holds zeros where a
 // (tap, phase) pair does not meet; the epilogue scatters its 16 values to the 2x2 block of the NHWC image.
-template <int BN, int STAGES, int CL, bool AFFINE, bool PS = false>
-__global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcConvParams p) { pdl_prologue();
-  using S = TcSmem<BN, STAGES>;
-  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
-  constexpr uint16_t cmask = (uint16_t)((1u << CL) - 1u);
+template <int BN, int STAGES, int EPI, bool AFFINE, bool PS = false>
+__global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcConvParams p) {
+  using S = TcSmem<BN, STAGES, EPI>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -167,6 +326,7 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ CU
   const uint32_t bar_empty = bar_full + 8 * STAGES;                 // STAGES x 8 B
   const uint32_t bar_accum = bar_empty + 8 * STAGES;                // 8 B
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + S::BAR_OFF + 8 * (2 * STAGES + 1));
+  float* sst = reinterpret_cast<float*>(smem_gen + S::STAT_OFF);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // tile coordinates
@@ -178,54 +338,38 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ CU
 
   if (warp == 0 && lane == 0) {
     prefetch_map(&tmA); prefetch_map(&tmB);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     mbar_init(bar_accum, 1);
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(smem_u32((const void*)tmem_slot), BN < 32 ? 32 : BN); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();      // every CTA's barriers exist before any peer multicasts into / arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
-      for (int kb = 0; kb < (p.dbg == 1 ? 0 : num_kb); ++kb) {
+      for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
         const int ch = kb % p.chunks, tap = kb / p.chunks, ta = tap / p.taps_w, tb = tap % p.taps_w;
-        int ax, ay, wtap;
-        if (p.mode == 0) { ay = y0 * p.SH - p.PH + ta; ax = -p.PW + tb; wtap = ta * p.KW + tb; }
-        else {
-          // output row 2*q+py takes filter rows r with (py+1-r) even: py=0 -> r=1 (dy row q), r=3 (q-1); py=1 -> r=0 (q+1), r=2 (q)
-          const int r = py == 0 ? (ta == 0 ? 1 : 3) : (ta == 0 ? 0 : 2), dyr = py == 0 ? (ta == 0 ? 0 : -1) : (ta == 0 ? 1 : 0);
-          const int sx = px == 0 ? (tb == 0 ? 1 : 3) : (tb == 0 ? 0 : 2), dxc = px == 0 ? (tb == 0 ? 0 : -1) : (tb == 0 ? 1 : 0);
-          ay = y0 + dyr; ax = dxc; wtap = r * 4 + sx;
-        }
+        int ax, dy_, wtap; tap_coords(p, ta, tb, py, px, ax, dy_, wtap);
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
         mbar_expect_tx(bar_full + 8 * s, S::STAGE_BYTES);
-        tma_load_4d(smem_base + s * S::STAGE_BYTES, &tmA, bar_full + 8 * s, ch * 64, ax, ay, n0);
-        if (CL == 1) tma_load_3d(smem_base + s * S::STAGE_BYTES + S::A_BYTES, &tmB, bar_full + 8 * s, ch * 64, wtap, nb0);
-        else tma_load_3d_mc(smem_base + s * S::STAGE_BYTES + S::A_BYTES + crank * (BN / CL) * 128, &tmB, bar_full + 8 * s, ch * 64, wtap, nb0 + (int)crank * (BN / CL), cmask);
+        tma_load_4d(smem_base + s * S::STAGE_BYTES, &tmA, bar_full + 8 * s, ch * 64, ax, (p.mode == 0 ? y0 * p.SH : y0) + dy_, n0);
+        load_b_tile<BN>(p, &tmB, smem_base + s * S::STAGE_BYTES + S::A_BYTES, bar_full + 8 * s, ch, wtap, nb0);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
-        if (p.dbg != 1) mbar_wait(bar_full + 8 * s, ph);
+        mbar_wait(bar_full + 8 * s, ph);
         tc_fence_after();
-        const uint64_t adesc = desc_kmajor_sw128(smem_base + s * S::STAGE_BYTES);
-        const uint64_t bdesc = desc_kmajor_sw128(smem_base + s * S::STAGE_BYTES + S::A_BYTES);
-        if (p.dbg != 2) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)     // 4 x K=16 inside the 128-byte swizzle atom: +32 B = +2 in the (>>4) start-address field
-          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-        }
-        if (CL == 1) umma_commit(bar_empty + 8 * s); else umma_commit_mc(bar_empty + 8 * s, cmask);
+        mma_kblock<BN>(tmem_base, smem_base + s * S::STAGE_BYTES, smem_base + s * S::STAGE_BYTES + S::A_BYTES, PS ? 0 : p.b_mn, (uint32_t)kb);
+        umma_commit(bar_empty + 8 * s);
       }
       umma_commit(bar_accum);
     }
@@ -238,7 +382,6 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ CU
     size_t pix;
     if (p.mode == 0) pix = ((size_t)n * p.outH + gy) * p.outW + gx;
     else pix = ((size_t)n * p.outH + 2 * gy + py) * p.outW + 2 * gx + px;
-    __nv_bfloat16* orow = p.out + pix * p.OC + nb0;
     mbar_wait(bar_accum, 0);
     tc_fence_after();
     if constexpr (PS) {
@@ -248,12 +391,18 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ CU
       const int C = p.OC;
 #pragma unroll
       for (int ppy = 0; ppy < 2; ++ppy) {
-        __nv_bfloat16* dst = p.out + (((size_t)n * p.outH + 2 * gy + ppy) * p.outW + 2 * gx) * C;
+        const size_t doff = (((size_t)n * p.outH + 2 * gy + ppy) * p.outW + 2 * gx) * C;
+        __nv_bfloat16* dst = p.out + doff;
         float o[8];
 #pragma unroll
         for (int ppx = 0; ppx < 2; ++ppx)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) { float a = __uint_as_float(v[(ppy * 2 + ppx) * 4 + c]); if (p.bias && c < C) a += p.bias[c]; o[ppx * 4 + c] = act_fwd(p.act, a, p.alpha); }
+          for (int c = 0; c < 4; ++c) {
+            float a = __uint_as_float(v[(ppy * 2 + ppx) * 4 + c]);
+            if constexpr (EPI == EPI_ACTBWD) { if (c < C) a *= act_grad_from_out(p.act, __bfloat162float(p.aux[doff + ppx * C + c]), p.alpha); }
+            else { if (p.bias && c < C) a += p.bias[c]; a = act_fwd(p.act, a, p.alpha); }
+            o[ppx * 4 + c] = a;
+          }
         if (C == 3) {         // 6 contiguous bf16 = three aligned 32-bit stores
           __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[4]), h2 = __floats2bfloat162_rn(o[5], o[6]);
           uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
@@ -266,188 +415,37 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ CU
         }
       }
     } else {
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      tmem_ld_wait();
-      uint32_t packed[16];
-      // the activation switch is hoisted out of the 32-column loop: one uniform branch per chunk instead of one per element
-#define B2G_EPI_LOOP(ACTC)                                                                                                         \
-  _Pragma("unroll") for (int j = 0; j < 16; ++j) {                                                                                 \
-    float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);                                                        \
-    if (AFFINE) { a = fmaf(a, p.scale[nb0 + c0 + 2 * j], p.bias[nb0 + c0 + 2 * j]); b = fmaf(b, p.scale[nb0 + c0 + 2 * j + 1], p.bias[nb0 + c0 + 2 * j + 1]); } \
-    else if (has_bias) { a += p.bias[nb0 + c0 + 2 * j]; b += p.bias[nb0 + c0 + 2 * j + 1]; }                                      \
-    a = act_fwd(ACTC, a, p.alpha); b = act_fwd(ACTC, b, p.alpha);                                                                  \
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);                                                                                \
-    packed[j] = *reinterpret_cast<uint32_t*>(&h);                                                                                  \
-  }
-      const bool has_bias = p.bias != nullptr;
-      if (p.act == ACT_IDENTITY) { B2G_EPI_LOOP(ACT_IDENTITY) }
-      else if (p.act == ACT_LRELU) { B2G_EPI_LOOP(ACT_LRELU) }
-      else if (p.act == ACT_RELU) { B2G_EPI_LOOP(ACT_RELU) }
-      else { B2G_EPI_LOOP(p.act) }
-#undef B2G_EPI_LOOP
-      uint4* dst = reinterpret_cast<uint4*>(orow + c0);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-    }
+      const int group = p.imgs_per_group > 0 ? n0 / p.imgs_per_group : 0;
+      epi_tile<BN, EPI, AFFINE>(p, tmem_base + ((uint32_t)(q * 32) << 16), pix * p.OC + nb0, nb0, group, sst, q, lane, (int)threadIdx.x - 64);
     }
     tc_fence_before();
   }
   __syncthreads();
-  if (CL > 1) cluster_sync_all();      // no CTA leaves while a peer may still multicast into its smem or arrive on its barriers
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, BN < 32 ? 32 : BN); }
 }
 
-
-// ------------------------------------------------------------------ two M tiles per CTA ---------------------
-// Same pipeline, but one CTA owns TWO adjacent 128-row tiles that share every weight tile: per K-block it stages 2 x 16 KB of
-// activations + BN x 128 B of weights and issues 2 x 4 MMAs into two TMEM accumulators (2*BN <= 512 columns).  Bytes out of L2 per MAC
-// drop by 25 % (BN = 128) to 33 % (BN = 256) -- these kernels run at the L2->SM fabric limit, not the tensor pipe's.  Used when
-// the halved grid still covers the SMs.
-template <int BN, int STAGES>
-struct TcSmem2 {
-  static constexpr int A_BYTES = 2 * 128 * 128;
-  static constexpr int B_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
-};
-template <int BN, int STAGES, bool AFFINE>
-__global__ void __launch_bounds__(192) tc_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcConvParams p) { pdl_prologue();
-  using S = TcSmem2<BN, STAGES>;
-  constexpr uint32_t TCOLS = 2 * BN;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_full = smem_base + S::BAR_OFF, bar_empty = bar_full + 8 * STAGES, bar_accum = bar_empty + 8 * STAGES;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + S::BAR_OFF + 8 * (2 * STAGES + 1));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nb0 = blockIdx.y * BN, phase = blockIdx.z, py = phase >> 1, px = phase & 1;
-  int n0[2], y0[2];
-#pragma unroll
-  for (int m = 0; m < 2; ++m) { const int mt = blockIdx.x * 2 + m; if (p.Nt > 1) { n0[m] = mt * p.Nt; y0[m] = 0; } else { n0[m] = mt / p.tiles_y; y0[m] = (mt % p.tiles_y) * p.Ht; } }
-  const int num_kb = p.taps_h * p.taps_w * p.chunks;
-
-  if (warp == 0 && lane == 0) {
-    prefetch_map(&tmA); prefetch_map(&tmB);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    mbar_init(bar_accum, 1);
-    fence_mbar_init();
-  }
-  if (warp == 1) { tmem_alloc(smem_u32((const void*)tmem_slot), TCOLS); tmem_relinquish(); }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
-        const int ch = kb % p.chunks, tap = kb / p.chunks, ta = tap / p.taps_w, tb = tap % p.taps_w;
-        int ax, dy_, wtap;
-        if (p.mode == 0) { dy_ = -p.PH + ta; ax = -p.PW + tb; wtap = ta * p.KW + tb; }
-        else {
-          const int r = py == 0 ? (ta == 0 ? 1 : 3) : (ta == 0 ? 0 : 2), dyr = py == 0 ? (ta == 0 ? 0 : -1) : (ta == 0 ? 1 : 0);
-          const int sx = px == 0 ? (tb == 0 ? 1 : 3) : (tb == 0 ? 0 : 2), dxc = px == 0 ? (tb == 0 ? 0 : -1) : (tb == 0 ? 1 : 0);
-          dy_ = dyr; ax = dxc; wtap = r * 4 + sx;
-        }
-        mbar_wait(bar_empty + 8 * s, ph ^ 1);
-        mbar_expect_tx(bar_full + 8 * s, S::STAGE_BYTES);
-        const uint32_t st = smem_base + s * S::STAGE_BYTES;
-#pragma unroll
-        for (int m = 0; m < 2; ++m) tma_load_4d(st + m * 16384, &tmA, bar_full + 8 * s, ch * 64, ax, (p.mode == 0 ? y0[m] * p.SH : y0[m]) + dy_, n0[m]);
-        tma_load_3d(st + S::A_BYTES, &tmB, bar_full + 8 * s, ch * 64, wtap, nb0);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(bar_full + 8 * s, ph);
-        tc_fence_after();
-        const uint32_t st = smem_base + s * S::STAGE_BYTES;
-        const uint64_t bdesc = desc_kmajor_sw128(st + S::A_BYTES);
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
-          const uint64_t adesc = desc_kmajor_sw128(st + m * 16384);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + m * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-        }
-        umma_commit(bar_empty + 8 * s);
-      }
-      umma_commit(bar_accum);
-    }
-  } else {
-    const int q = warp & 3, row = q * 32 + lane;
-    const int img = row / (p.Ht * p.Wt), rem = row % (p.Ht * p.Wt), yy = rem / p.Wt, xx = rem % p.Wt;
-    mbar_wait(bar_accum, 0);
-    tc_fence_after();
-    const bool has_bias = p.bias != nullptr;
-#pragma unroll 1
-    for (int m = 0; m < 2; ++m) {
-      const int n = n0[m] + img, gy = y0[m] + yy, gx = xx;
-      size_t pix;
-      if (p.mode == 0) pix = ((size_t)n * p.outH + gy) * p.outW + gx;
-      else pix = ((size_t)n * p.outH + 2 * gy + py) * p.outW + 2 * gx + px;
-      __nv_bfloat16* orow = p.out + pix * p.OC + nb0;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * BN + c0), v);
-        tmem_ld_wait();
-        uint32_t packed[16];
-#define B2G_EPI_LOOP(ACTC)                                                                                                         \
-  _Pragma("unroll") for (int j = 0; j < 16; ++j) {                                                                                 \
-    float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);                                                        \
-    if (AFFINE) { a = fmaf(a, p.scale[nb0 + c0 + 2 * j], p.bias[nb0 + c0 + 2 * j]); b = fmaf(b, p.scale[nb0 + c0 + 2 * j + 1], p.bias[nb0 + c0 + 2 * j + 1]); } \
-    else if (has_bias) { a += p.bias[nb0 + c0 + 2 * j]; b += p.bias[nb0 + c0 + 2 * j + 1]; }                                      \
-    a = act_fwd(ACTC, a, p.alpha); b = act_fwd(ACTC, b, p.alpha);                                                                  \
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);                                                                                \
-    packed[j] = *reinterpret_cast<uint32_t*>(&h);                                                                                  \
-  }
-        if (p.act == ACT_IDENTITY) { B2G_EPI_LOOP(ACT_IDENTITY) }
-        else if (p.act == ACT_LRELU) { B2G_EPI_LOOP(ACT_LRELU) }
-        else if (p.act == ACT_RELU) { B2G_EPI_LOOP(ACT_RELU) }
-        else { B2G_EPI_LOOP(p.act) }
-#undef B2G_EPI_LOOP
-        uint4* dst = reinterpret_cast<uint4*>(orow + c0);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-      }
-    }
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TCOLS); }
-}
-
-
 // ------------------------------------------------------------------ persistent, double-buffered TMEM -----------------
-// Measured (B2G_TC_DBG experiments, round 1): with one short-lived CTA per tile the conv kernels are bounded twice over -- the
-// MMA path alone (no loads) costs ~0.5 of peak because every 2 us of MMAs pays ~4 us of per-CTA prologue + epilogue, and the load
-// path alone runs at the L2->SM limit.  This kernel attacks both: one resident CTA per SM walks a static list of work items
-// (MT adjacent 128-row tiles x one weight tile x one phase), the smem ring keeps flowing across items, and TWO TMEM accumulator
-// stages let the 4 epilogue warps drain item i while the MMA issuer already works on item i+1.  MT = 2 shares each weight tile
-// between two M tiles (25 % fewer bytes out of L2).
+// Measured (round 1): with one short-lived CTA per tile the conv kernels are bounded twice over -- the MMA path alone (no loads) costs
+// ~0.5 of peak because every 2 us of MMAs pays ~4 us of per-CTA prologue + epilogue, and the load path alone runs at the L2->SM
+// limit.  This kernel attacks both: one resident CTA per SM walks a static list of work items (MT adjacent 128-row tiles x one
+// weight tile x one phase), the smem ring keeps flowing across items, and TWO TMEM accumulator stages let the 4 epilogue warps drain
+// item i while the MMA issuer already works on item i+1.  MT = 2 shares each weight tile between two M tiles (25 % fewer bytes out of L2).
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 
-template <int BN, int STAGES, int MT>
+template <int BN, int STAGES, int MT, int EPI = EPI_PLAIN>
 struct TcSmemP {
   static constexpr int A_BYTES = MT * 128 * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+  static constexpr int STAT_OFF = BAR_OFF + 256;
+  static constexpr int TOTAL = STAT_OFF + ((EPI == EPI_STATS || EPI == EPI_BNBWD) ? 4 * 2 * BN * 4 : 0) + 1024;
 };
 
-template <int BN, int STAGES, int MT, bool AFFINE>
+template <int BN, int STAGES, int MT, int EPI, bool AFFINE>
 __global__ void __launch_bounds__(192) tc_conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcConvParams p,
-                                                                  int m_groups, int n_tiles, int phases) { pdl_prologue();
-  using S = TcSmemP<BN, STAGES, MT>;
+                                                                  int m_groups, int n_tiles, int phases) {
+  using S = TcSmemP<BN, STAGES, MT, EPI>;
   constexpr uint32_t ACC_COLS = MT * BN, TCOLS = 2 * ACC_COLS;       // two accumulator stages
   static_assert(TCOLS <= 512, "TMEM has 512 columns");
   extern __shared__ uint8_t smem_raw[];
@@ -456,6 +454,7 @@ __global__ void __launch_bounds__(192) tc_conv_persistent_kernel(const __grid_co
   const uint32_t bar_full = smem_base + S::BAR_OFF, bar_empty = bar_full + 8 * STAGES;
   const uint32_t bar_tfull = bar_empty + 8 * STAGES, bar_tempty = bar_tfull + 16;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + S::BAR_OFF + 8 * (2 * STAGES + 4));
+  float* sst = reinterpret_cast<float*>(smem_gen + S::STAT_OFF);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = p.taps_h * p.taps_w * p.chunks;
   const int total_items = m_groups * n_tiles * phases;
@@ -487,25 +486,18 @@ __global__ void __launch_bounds__(192) tc_conv_persistent_kernel(const __grid_co
         for (int kb = 0; kb < num_kb; ++kb, ++kiter) {
           const int s = kiter % STAGES; const uint32_t ph = (kiter / STAGES) & 1;
           const int ch = kb % p.chunks, tap = kb / p.chunks, ta = tap / p.taps_w, tb = tap % p.taps_w;
-          int ax, dy_, wtap;
-          if (p.mode == 0) { dy_ = -p.PH + ta; ax = -p.PW + tb; wtap = ta * p.KW + tb; }
-          else {
-            const int r = py == 0 ? (ta == 0 ? 1 : 3) : (ta == 0 ? 0 : 2), dyr = py == 0 ? (ta == 0 ? 0 : -1) : (ta == 0 ? 1 : 0);
-            const int sx = px == 0 ? (tb == 0 ? 1 : 3) : (tb == 0 ? 0 : 2), dxc = px == 0 ? (tb == 0 ? 0 : -1) : (tb == 0 ? 1 : 0);
-            dy_ = dyr; ax = dxc; wtap = r * 4 + sx;
-          }
+          int ax, dy_, wtap; tap_coords(p, ta, tb, py, px, ax, dy_, wtap);
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
           mbar_expect_tx(bar_full + 8 * s, S::STAGE_BYTES);
           const uint32_t st = smem_base + s * S::STAGE_BYTES;
 #pragma unroll
           for (int m = 0; m < MT; ++m) tma_load_4d(st + m * 16384, &tmA, bar_full + 8 * s, ch * 64, ax, (p.mode == 0 ? y0[m] * p.SH : y0[m]) + dy_, n0[m]);
-          tma_load_3d(st + S::A_BYTES, &tmB, bar_full + 8 * s, ch * 64, wtap, nb0);
+          load_b_tile<BN>(p, &tmB, st + S::A_BYTES, bar_full + 8 * s, ch, wtap, nb0);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
       uint32_t kiter = 0, it = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
         const uint32_t acc = it & 1, aph = (it >> 1) & 1;
@@ -517,13 +509,8 @@ __global__ void __launch_bounds__(192) tc_conv_persistent_kernel(const __grid_co
           mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
           const uint32_t st = smem_base + s * S::STAGE_BYTES;
-          const uint64_t bdesc = desc_kmajor_sw128(st + S::A_BYTES);
 #pragma unroll
-          for (int m = 0; m < MT; ++m) {
-            const uint64_t adesc = desc_kmajor_sw128(st + m * 16384);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(tacc + m * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-          }
+          for (int m = 0; m < MT; ++m) mma_kblock<BN>(tacc + m * BN, st + m * 16384, st + S::A_BYTES, p.b_mn, (uint32_t)kb);
           umma_commit(bar_empty + 8 * s);
         }
         umma_commit(bar_tfull + 8 * acc);
@@ -532,7 +519,6 @@ __global__ void __launch_bounds__(192) tc_conv_persistent_kernel(const __grid_co
   } else {
     const int q = warp & 3, row = q * 32 + lane;
     const int img = row / (p.Ht * p.Wt), rem = row % (p.Ht * p.Wt), yy = rem / p.Wt, xx = rem % p.Wt;
-    const bool has_bias = p.bias != nullptr;
     uint32_t it = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
       int mg, nb0, py, px; decode(item, mg, nb0, py, px);
@@ -546,31 +532,8 @@ __global__ void __launch_bounds__(192) tc_conv_persistent_kernel(const __grid_co
         size_t pix;
         if (p.mode == 0) pix = ((size_t)n * p.outH + gy) * p.outW + gx;
         else pix = ((size_t)n * p.outH + 2 * gy + py) * p.outW + 2 * gx + px;
-        __nv_bfloat16* orow = p.out + pix * p.OC + nb0;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + m * BN + c0), v);
-          tmem_ld_wait();
-          uint32_t packed[16];
-#define B2G_EPI_LOOP(ACTC)                                                                                                         \
-  _Pragma("unroll") for (int j = 0; j < 16; ++j) {                                                                                 \
-    float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);                                                        \
-    if (AFFINE) { a = fmaf(a, p.scale[nb0 + c0 + 2 * j], p.bias[nb0 + c0 + 2 * j]); b = fmaf(b, p.scale[nb0 + c0 + 2 * j + 1], p.bias[nb0 + c0 + 2 * j + 1]); } \
-    else if (has_bias) { a += p.bias[nb0 + c0 + 2 * j]; b += p.bias[nb0 + c0 + 2 * j + 1]; }                                      \
-    a = act_fwd(ACTC, a, p.alpha); b = act_fwd(ACTC, b, p.alpha);                                                                  \
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);                                                                                \
-    packed[j] = *reinterpret_cast<uint32_t*>(&h);                                                                                  \
-  }
-          if (p.act == ACT_IDENTITY) { B2G_EPI_LOOP(ACT_IDENTITY) }
-          else if (p.act == ACT_LRELU) { B2G_EPI_LOOP(ACT_LRELU) }
-          else if (p.act == ACT_RELU) { B2G_EPI_LOOP(ACT_RELU) }
-          else { B2G_EPI_LOOP(p.act) }
-#undef B2G_EPI_LOOP
-          uint4* dst = reinterpret_cast<uint4*>(orow + c0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-        }
+        const int group = p.imgs_per_group > 0 ? n0 / p.imgs_per_group : 0;
+        epi_tile<BN, EPI, AFFINE>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + m * BN), pix * p.OC + nb0, nb0, group, sst, q, lane, (int)threadIdx.x - 64);
       }
       // all of this warp's TMEM reads of the stage have completed (tcgen05.wait::ld above): hand the accumulator back
       tc_fence_before();
@@ -583,6 +546,13 @@ __global__ void __launch_bounds__(192) tc_conv_persistent_kernel(const __grid_co
 }
 
 // ------------------------------------------------------------------ host side ------------------------------
+const char* g_tc_last_kernel = "";       // name of the tcgen05 kernel the most recent k_tc_* call dispatched (parity tests assert it)
+static int tc_device() { int dev = 0; cudaGetDevice(&dev); return dev < 0 || dev >= 64 ? 0 : dev; }
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per device: one flag per (kernel, device)
+#define TC_SET_SMEM_ONCE(kernel, bytes)                                                                                            \
+  do { static bool set_[64] = {}; const int d_ = tc_device();                                                                       \
+       if (!set_[d_]) { if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)) != cudaSuccess) return -2; set_[d_] = true; } } while (0)
+
 static bool pick_row_tile(int N, int GH, int GW, int rows, int* Nt, int* Ht, int* Wt) {
   const int P = GH * GW;
   if (GW > rows || rows % GW) return false;
@@ -608,134 +578,91 @@ bool tc_dgrad_supported(const ConvGeom& g) {
   return g.KH == 4 && g.KW == 4 && g.SH == 2 && g.SW == 2 && g.PH == 1 && g.PW == 1 && g.O % 64 == 0 && pick_bn(g.C) != 0 && g.H == 2 * g.OH && g.W == 2 * g.OW &&
          pick_row_tile(g.N, g.OH, g.OW, 128, &a, &b, &c);
 }
+// the fused BatchNorm epilogues need every 128-row tile inside one statistics group
+static bool tc_epi_ok(const TcEpi* e, int Nt) { return !e || e->mode == EPI_PLAIN || e->mode == EPI_ACTBWD || (e->imgs_per_group > 0 && e->imgs_per_group % Nt == 0 && e->acc); }
 
-template <int BN, int STAGES, int CL, bool AFFINE>
-static int launch_conv_a(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvParams& p, dim3 grid, cudaStream_t s) {
-  using S = TcSmem<BN, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) { if (cudaFuncSetAttribute(tc_conv_kernel<BN, STAGES, CL, AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) return -2; attr_set = true; }
-  if (CL == 1) {
-    launch_pdl(tc_conv_kernel<BN, STAGES, CL, AFFINE>, dim3(grid), dim3(192), (size_t)(S::TOTAL), s, tmA, tmB, p);
-  } else {
-    cudaLaunchConfig_t cfg{}; cfg.gridDim = grid; cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = S::TOTAL; cfg.stream = s;
-    cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    if (cudaLaunchKernelEx(&cfg, tc_conv_kernel<BN, STAGES, CL, AFFINE>, tmA, tmB, p) != cudaSuccess) return -3;
-  }
-  LAUNCHED();
-  return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
-}
-template <int BN, int STAGES, int CL>
-static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvParams& p, dim3 grid, cudaStream_t s) {
-  return (p.scale && p.bias) ? launch_conv_a<BN, STAGES, CL, true>(tmA, tmB, p, grid, s) : launch_conv_a<BN, STAGES, CL, false>(tmA, tmB, p, grid, s);
-}
-static int tc_dbg() { static int d = -1; if (d < 0) { const char* e = getenv("B2G_TC_DBG"); d = e ? atoi(e) : 0; } return d; }
-static int g_tc_cluster = -1;     // B2G_TC_CLUSTER=1|2|4 caps the cluster size. Default 1: measured on B200 the 2- and 4-CTA multicast variants are 5-20 % SLOWER (profiles/r01_kernel_bench_cluster.txt) -- consistent with the microarchitecture note that TMA multicast only dedups L2 reads at cluster size 8
-static int pick_cluster(unsigned grid_x) {
-  if (g_tc_cluster < 0) { const char* e = getenv("B2G_TC_CLUSTER"); g_tc_cluster = e ? atoi(e) : 1; if (g_tc_cluster != 1 && g_tc_cluster != 2 && g_tc_cluster != 4) g_tc_cluster = 1; }
-  if (g_tc_cluster >= 4 && grid_x % 4 == 0) return 4;
-  if (g_tc_cluster >= 2 && grid_x % 2 == 0) return 2;
-  return 1;
-}
-template <int BN, int STAGES>
-static int launch_conv_cl(int CL, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvParams& p, dim3 grid, cudaStream_t s) {
-  switch (CL) { case 4: return launch_conv<BN, STAGES, 4>(tmA, tmB, p, grid, s); case 2: return launch_conv<BN, STAGES, 2>(tmA, tmB, p, grid, s); }
-  return launch_conv<BN, STAGES, 1>(tmA, tmB, p, grid, s);
-}
-template <int BN, int STAGES, bool AFFINE>
-static int launch_conv2_a(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvParams& p, dim3 grid, cudaStream_t s) {
-  using S = TcSmem2<BN, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) { if (cudaFuncSetAttribute(tc_conv2_kernel<BN, STAGES, AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) return -2; attr_set = true; }
-  launch_pdl(tc_conv2_kernel<BN, STAGES, AFFINE>, grid, dim3(192), (size_t)S::TOTAL, s, tmA, tmB, p);
+template <int BN, int STAGES, int EPI, bool AFFINE>
+static int launch_conv_e(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvParams& p, dim3 grid, cudaStream_t s) {
+  using S = TcSmem<BN, STAGES, EPI>;
+  TC_SET_SMEM_ONCE((tc_conv_kernel<BN, STAGES, EPI, AFFINE, false>), S::TOTAL);
+  tc_conv_kernel<BN, STAGES, EPI, AFFINE, false><<<grid, 192, S::TOTAL, s>>>(tmA, tmB, p);
   LAUNCHED();
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
 }
 template <int BN, int STAGES>
-static int launch_conv2(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvParams& p, dim3 grid, cudaStream_t s) {
-  return (p.scale && p.bias) ? launch_conv2_a<BN, STAGES, true>(tmA, tmB, p, grid, s) : launch_conv2_a<BN, STAGES, false>(tmA, tmB, p, grid, s);
-}
-static int g_tc_mt2 = -1;        // B2G_TC_MT2=0 disables the two-tile variant
-static bool use_mt2(dim3 grid, int CL) {
-  if (g_tc_mt2 < 0) { const char* e = getenv("B2G_TC_MT2"); g_tc_mt2 = (e && e[0] == '0') ? 0 : 1; }
-  return g_tc_mt2 && CL == 1 && grid.x % 2 == 0 && (long)(grid.x / 2) * grid.y * grid.z >= 148;
-}
-template <int BN, int STAGES, int MT, bool AFFINE>
-static int launch_convp_a(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvParams& p, int m_groups, int n_tiles, int phases, cudaStream_t s) {
-  using S = TcSmemP<BN, STAGES, MT>;
-  static bool attr_set = false; static int sms = 0;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(tc_conv_persistent_kernel<BN, STAGES, MT, AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) return -2;
-    int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); attr_set = true;
+static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvParams& p, dim3 grid, cudaStream_t s, const char* name) {
+  g_tc_last_kernel = name;
+  switch (p.epi) {
+    case EPI_STATS: return launch_conv_e<BN, STAGES, EPI_STATS, false>(tmA, tmB, p, grid, s);
+    case EPI_BNBWD: return launch_conv_e<BN, STAGES, EPI_BNBWD, false>(tmA, tmB, p, grid, s);
+    case EPI_ACTBWD: return launch_conv_e<BN, STAGES, EPI_ACTBWD, false>(tmA, tmB, p, grid, s);
   }
+  return (p.scale && p.bias) ? launch_conv_e<BN, STAGES, EPI_PLAIN, true>(tmA, tmB, p, grid, s) : launch_conv_e<BN, STAGES, EPI_PLAIN, false>(tmA, tmB, p, grid, s);
+}
+template <int BN, int STAGES, int MT, int EPI, bool AFFINE>
+static int launch_convp_e(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvParams& p, int m_groups, int n_tiles, int phases, cudaStream_t s) {
+  using S = TcSmemP<BN, STAGES, MT, EPI>;
+  TC_SET_SMEM_ONCE((tc_conv_persistent_kernel<BN, STAGES, MT, EPI, AFFINE>), S::TOTAL);
+  static int sms = 0; if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, tc_device());
   const int items = m_groups * n_tiles * phases; const int grid = items < sms ? items : sms;
-  launch_pdl(tc_conv_persistent_kernel<BN, STAGES, MT, AFFINE>, dim3(grid), dim3(192), (size_t)S::TOTAL, s, tmA, tmB, p, m_groups, n_tiles, phases);
+  tc_conv_persistent_kernel<BN, STAGES, MT, EPI, AFFINE><<<grid, 192, S::TOTAL, s>>>(tmA, tmB, p, m_groups, n_tiles, phases);
   LAUNCHED();
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
 }
 template <int BN, int STAGES, int MT>
-static int launch_convp(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvParams& p, int m_groups, int n_tiles, int phases, cudaStream_t s) {
-  return (p.scale && p.bias) ? launch_convp_a<BN, STAGES, MT, true>(tmA, tmB, p, m_groups, n_tiles, phases, s) : launch_convp_a<BN, STAGES, MT, false>(tmA, tmB, p, m_groups, n_tiles, phases, s);
-}
-static int g_tc_persist = -1;     // B2G_TC_PERSIST=0 falls back to one CTA per tile
-// returns 1 if the persistent kernel took the launch, 0 if not applicable, <0 on error
-static int try_persistent(int BN, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvParams& p, dim3 grid, cudaStream_t s) {
-  if (g_tc_persist < 0) { const char* e = getenv("B2G_TC_PERSIST"); g_tc_persist = (e && e[0] == '0') ? 0 : 1; }
-  if (!g_tc_persist || p.dbg) return 0;
-  const int mt2 = (grid.x % 2 == 0 && (long)(grid.x / 2) * grid.y * grid.z >= 148) ? 2 : 1;
-  // measured (profiles/r01_kernel_bench_persistent.txt): a win only where two M tiles can share the weight tile AND the halved grid still
-  // covers the SMs (D2 fprop 27.3 -> 25.1 us, D2 dgrad / G4 forward 28.8 -> 24 us); with one tile per item the lone resident CTA hides
-  // load latency worse than two co-resident short-lived CTAs do (D3 fprop 23.7 -> 36 us), so those shapes keep one CTA per tile.
-  if (mt2 != 2 && !getenv("B2G_TC_PERSIST_ALL")) return 0;
-  int rc;
-  if (BN == 256) rc = launch_convp<256, 4, 1>(tmA, tmB, p, grid.x, grid.y, grid.z, s);
-  else if (BN == 128) rc = mt2 == 2 ? launch_convp<128, 4, 2>(tmA, tmB, p, grid.x / 2, grid.y, grid.z, s) : launch_convp<128, 6, 1>(tmA, tmB, p, grid.x, grid.y, grid.z, s);
-  else if (BN == 64) rc = mt2 == 2 ? launch_convp<64, 4, 2>(tmA, tmB, p, grid.x / 2, grid.y, grid.z, s) : launch_convp<64, 8, 1>(tmA, tmB, p, grid.x, grid.y, grid.z, s);
-  else return 0;
-  return rc == 0 ? 1 : rc;
-}
-static int dispatch_conv(int BN, int CL, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvParams& p, dim3 grid, cudaStream_t s) {
-  if (CL == 1) { const int r = try_persistent(BN, tmA, tmB, p, grid, s); if (r == 1) return 0; if (r < 0) return r; }
-  if (use_mt2(grid, CL)) {
-    dim3 g2(grid.x / 2, grid.y, grid.z);
-    switch (BN) {
-      case 64: return launch_conv2<64, 4>(tmA, tmB, p, g2, s);
-      case 128: return launch_conv2<128, 4>(tmA, tmB, p, g2, s);
-      case 256: return launch_conv2<256, 3>(tmA, tmB, p, g2, s);
-    }
+static int launch_convp(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvParams& p, int m_groups, int n_tiles, int phases, cudaStream_t s, const char* name) {
+  g_tc_last_kernel = name;
+  switch (p.epi) {
+    case EPI_STATS: return launch_convp_e<BN, STAGES, MT, EPI_STATS, false>(tmA, tmB, p, m_groups, n_tiles, phases, s);
+    case EPI_BNBWD: return launch_convp_e<BN, STAGES, MT, EPI_BNBWD, false>(tmA, tmB, p, m_groups, n_tiles, phases, s);
+    case EPI_ACTBWD: return launch_convp_e<BN, STAGES, MT, EPI_ACTBWD, false>(tmA, tmB, p, m_groups, n_tiles, phases, s);
   }
-  // B2G_TC_DEEP=1 (experiment, not yet measured): a grid that cannot give every SM two CTAs anyway (<= 148 CTAs: D4, G2 -- 64..128 sequential
-  // K-blocks at ~0.5 us each, TMA-latency-bound with 3-4 stages in flight) takes the whole shared memory for a deeper ring instead
-  static int deep = -1; if (deep < 0) { const char* e = getenv("B2G_TC_DEEP"); deep = (e && e[0] == '1') ? 1 : 0; }
-  if (deep && CL == 1 && (long)grid.x * grid.y * grid.z <= 148) {
-    switch (BN) {
-      case 64: return launch_conv<64, 8, 1>(tmA, tmB, p, grid, s);
-      case 128: return launch_conv<128, 6, 1>(tmA, tmB, p, grid, s);
-    }
+  return (p.scale && p.bias) ? launch_convp_e<BN, STAGES, MT, EPI_PLAIN, true>(tmA, tmB, p, m_groups, n_tiles, phases, s) : launch_convp_e<BN, STAGES, MT, EPI_PLAIN, false>(tmA, tmB, p, m_groups, n_tiles, phases, s);
+}
+static int g_tc_persist = -1;     // B2G_TC_PERSIST=0: one CTA per tile everywhere
+static int dispatch_conv(int BN, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvParams& p, dim3 grid, cudaStream_t s) {
+  if (g_tc_persist < 0) { const char* e = getenv("B2G_TC_PERSIST"); g_tc_persist = (e && e[0] == '0') ? 0 : 1; }
+  // measured (profiles/r01_kernel_bench_persistent.txt): the persistent kernel wins only where two M tiles can share the weight tile AND the
+  // halved grid still covers the SMs (D2 fprop 27.3 -> 25.1 us, D2 dgrad / G4 forward 28.8 -> 24 us); with one tile per item the lone
+  // resident CTA hides load latency worse than two co-resident short-lived CTAs do (D3 fprop 23.7 -> 36 us): those keep one CTA per tile
+  const bool mt2 = g_tc_persist && grid.x % 2 == 0 && (long)(grid.x / 2) * grid.y * grid.z >= 148 && BN <= 128;
+  if (mt2) {
+    if (BN == 128) return launch_convp<128, 4, 2>(tmA, tmB, p, grid.x / 2, grid.y, grid.z, s, "tc_conv_persistent_kernel<128,4,2>");
+    return launch_convp<64, 4, 2>(tmA, tmB, p, grid.x / 2, grid.y, grid.z, s, "tc_conv_persistent_kernel<64,4,2>");
   }
   switch (BN) {
-    case 64: return launch_conv_cl<64, 4>(CL, tmA, tmB, p, grid, s);
-    case 128: return launch_conv_cl<128, 3>(CL, tmA, tmB, p, grid, s);
-    case 256: return launch_conv_cl<256, 4>(CL, tmA, tmB, p, grid, s);
+    case 64: return launch_conv<64, 4>(tmA, tmB, p, grid, s, "tc_conv_kernel<64,4>");
+    case 128: return launch_conv<128, 3>(tmA, tmB, p, grid, s, "tc_conv_kernel<128,3>");
+    case 256: return launch_conv<256, 4>(tmA, tmB, p, grid, s, "tc_conv_kernel<256,4>");
   }
   return -4;
 }
 
-// weights as a 3-D tensor [rows][taps][Kred] (bf16, Kred contiguous); box = 64 x 1 x BN
-static int weight_map(CUtensorMap* m, const __nv_bfloat16* w, int rows, int taps, int kred, int box_rows) {
-  const int BN = box_rows;
-  cuuint64_t dims[3] = {(cuuint64_t)kred, (cuuint64_t)taps, (cuuint64_t)rows};
-  cuuint64_t strides[2] = {(cuuint64_t)kred * 2, (cuuint64_t)taps * kred * 2};
-  cuuint32_t box[3] = {64, 1, (cuuint32_t)BN}; cuuint32_t es[3] = {1, 1, 1};
+// weights as a 3-D tensor [rows][taps][inner] (bf16, inner contiguous)
+static int weight_map(CUtensorMap* m, const __nv_bfloat16* w, int rows, int taps, int inner, int box_rows) {
+  cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)taps, (cuuint64_t)rows};
+  cuuint64_t strides[2] = {(cuuint64_t)inner * 2, (cuuint64_t)taps * inner * 2};
+  cuuint32_t box[3] = {64, 1, (cuuint32_t)box_rows}; cuuint32_t es[3] = {1, 1, 1};
   return make_map_bf16(m, w, 3, dims, strides, box, es);
 }
+static void fill_epi(TcConvParams& p, const float* bias, int act, float alpha, const TcEpi* e) {
+  p.bias = bias; p.act = act; p.alpha = alpha; p.epi = EPI_PLAIN;
+  if (!e) return;
+  p.scale = e->scale; p.epi = e->mode; p.acc = e->acc; p.imgs_per_group = e->mode == EPI_STATS || e->mode == EPI_BNBWD ? e->imgs_per_group : 0;
+  p.aux = e->aux; p.coef = e->coef;
+  if (e->mode == EPI_BNBWD || e->mode == EPI_ACTBWD) { p.act = e->act; p.alpha = e->alpha; p.bias = nullptr; p.scale = nullptr; }
+}
 
-int k_tc_fprop(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out, int act, float alpha, cudaStream_t s, const float* scale) {
-  TcConvParams p{}; p.mode = 0; p.scale = scale; p.dbg = tc_dbg();
-  if (!pick_row_tile(g.N, g.OH, g.OW, 128, &p.Nt, &p.Ht, &p.Wt)) return -1;
+// w_mn = 0: w is [O][taps][C] (reduction contiguous).  w_mn = 1 (1x1 geometry only): w is [C][O] -- the dense layer's own [nOut][nIn] weight
+// read as the operand of its input-gradient GEMM (reduction over nOut), no transposed copy.
+int k_tc_fprop(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out, int act, float alpha, cudaStream_t s, const TcEpi* epi, int w_mn) {
+  TcConvParams p{}; p.mode = 0;
+  if (!pick_row_tile(g.N, g.OH, g.OW, 128, &p.Nt, &p.Ht, &p.Wt) || !tc_epi_ok(epi, p.Nt)) return -1;
+  if (w_mn && (g.KH != 1 || g.KW != 1)) return -1;
   const int BN = pick_bn_fill(g.O, (long)g.N * g.OH * g.OW / 128);
   p.GH = g.OH; p.GW = g.OW; p.tiles_y = g.OH / p.Ht; p.taps_h = g.KH; p.taps_w = g.KW; p.chunks = g.C / 64; p.KW = g.KW;
-  p.SH = g.SH; p.SW = g.SW; p.PH = g.PH; p.PW = g.PW; p.OC = g.O; p.outH = g.OH; p.outW = g.OW; p.bias = bias; p.act = act; p.alpha = alpha; p.out = out;
+  p.SH = g.SH; p.SW = g.SW; p.PH = g.PH; p.PW = g.PW; p.OC = g.O; p.outH = g.OH; p.outW = g.OW; p.out = out; p.b_mn = w_mn;
+  fill_epi(p, bias, act, alpha, epi);
   CUtensorMap tmA, tmB;
   cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
   cuuint64_t strides[3] = {(cuuint64_t)g.C * 2, (cuuint64_t)g.W * g.C * 2, (cuuint64_t)g.H * g.W * g.C * 2};
@@ -743,17 +670,19 @@ int k_tc_fprop(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* w
   cuuint32_t es[4] = {1, (cuuint32_t)g.SW, (cuuint32_t)g.SH, 1};
   if (make_map_bf16(&tmA, x, 4, dims, strides, box, es)) return -1;
   dim3 grid((unsigned)(g.N * g.OH * g.OW / 128), (unsigned)(g.O / BN), 1);
-  const int CL = pick_cluster(grid.x);
-  if (weight_map(&tmB, w, g.O, g.KH * g.KW, g.C, BN / CL)) return -1;
-  return dispatch_conv(BN, CL, tmA, tmB, p, grid, s);
+  if (w_mn ? weight_map(&tmB, w, g.C, 1, g.O, 64) : weight_map(&tmB, w, g.O, g.KH * g.KW, g.C, BN)) return -1;
+  return dispatch_conv(BN, tmA, tmB, p, grid, s);
 }
 
-int k_tc_dgrad(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat16* wt, const float* bias, __nv_bfloat16* dx, int act, float alpha, cudaStream_t s, const float* scale) {
-  TcConvParams p{}; p.mode = 1; p.scale = scale; p.dbg = tc_dbg();
-  if (!pick_row_tile(g.N, g.OH, g.OW, 128, &p.Nt, &p.Ht, &p.Wt)) return -1;
+// conv input gradient = transposed-conv forward, 4x4 s2 p1, in sub-pixel phase form.  w is the STRAIGHT copy [O][16][C]: the reduction runs
+// over O, so the weight tile is MN-major ({64 c, 1 tap, 64 o} boxes).
+int k_tc_dgrad(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* dx, int act, float alpha, cudaStream_t s, const TcEpi* epi) {
+  TcConvParams p{}; p.mode = 1;
+  if (!pick_row_tile(g.N, g.OH, g.OW, 128, &p.Nt, &p.Ht, &p.Wt) || !tc_epi_ok(epi, p.Nt)) return -1;
   const int BN = pick_bn_fill(g.C, (long)g.N * g.OH * g.OW / 128 * 4);
   p.GH = g.OH; p.GW = g.OW; p.tiles_y = g.OH / p.Ht; p.taps_h = 2; p.taps_w = 2; p.chunks = g.O / 64; p.KW = 4;
-  p.SH = 1; p.SW = 1; p.PH = 0; p.PW = 0; p.OC = g.C; p.outH = g.H; p.outW = g.W; p.bias = bias; p.act = act; p.alpha = alpha; p.out = dx;
+  p.SH = 1; p.SW = 1; p.PH = 0; p.PW = 0; p.OC = g.C; p.outH = g.H; p.outW = g.W; p.out = dx; p.b_mn = 1;
+  fill_epi(p, bias, act, alpha, epi);
   CUtensorMap tmA, tmB;
   cuuint64_t dims[4] = {(cuuint64_t)g.O, (cuuint64_t)g.OW, (cuuint64_t)g.OH, (cuuint64_t)g.N};
   cuuint64_t strides[3] = {(cuuint64_t)g.O * 2, (cuuint64_t)g.OW * g.O * 2, (cuuint64_t)g.OH * g.OW * g.O * 2};
@@ -761,9 +690,8 @@ int k_tc_dgrad(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat16* 
   cuuint32_t es[4] = {1, 1, 1, 1};
   if (make_map_bf16(&tmA, dy, 4, dims, strides, box, es)) return -1;
   dim3 grid((unsigned)(g.N * g.OH * g.OW / 128), (unsigned)(g.C / BN), 4);
-  const int CL = pick_cluster(grid.x);
-  if (weight_map(&tmB, wt, g.C, 16, g.O, BN / CL)) return -1;       // transposed shadow [C][taps][O]
-  return dispatch_conv(BN, CL, tmA, tmB, p, grid, s);
+  if (weight_map(&tmB, w, g.O, 16, g.C, 64)) return -1;
+  return dispatch_conv(BN, tmA, tmB, p, grid, s);
 }
 
 // ------------------------------------------------------------------ transposed conv onto <= 4 channels ------
@@ -772,7 +700,7 @@ bool tc_deconv_ps_shape(const ConvGeom& g) { return is_k4s2p1_geom(g) && g.C >= 
 bool tc_deconv_ps_supported(const ConvGeom& g) { int a, b, c; return tc_deconv_ps_shape(g) && pick_row_tile(g.N, g.OH, g.OW, 128, &a, &b, &c); }
 size_t k_tc_deconv_ps_weight_elems(const ConvGeom& g) { return tc_deconv_ps_shape(g) ? (size_t)16 * 9 * g.O : 0; }
 // w [O][4][4][C] fp32 master -> wps [(py,px,c4)][(dyr,dxc)][O] bf16; dy row offset dyr serves (py, filter row r): -1 -> (0,3); 0 -> (0,1),(1,2); +1 -> (1,0)
-__global__ void pack_deconv_ps_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wps, int O, int C) { pdl_prologue();
+__global__ void pack_deconv_ps_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wps, int O, int C) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x; if (idx >= 16 * 9 * O) return;
   const int o = idx % O, t = (idx / O) % 9, n = idx / (9 * O);
   const int py = n >> 3, px = (n >> 2) & 1, c = n & 3, dyr = t / 3 - 1, dxc = t % 3 - 1;
@@ -781,13 +709,15 @@ __global__ void pack_deconv_ps_kernel(const float* __restrict__ w, __nv_bfloat16
   wps[idx] = __float2bfloat16((r >= 0 && sx >= 0 && c < C) ? w[((size_t)o * 16 + r * 4 + sx) * C + c] : 0.f);
 }
 void k_pack_deconv_ps(const float* w, __nv_bfloat16* wps, int O, int C, cudaStream_t s) {
-  launch_pdl(pack_deconv_ps_kernel, dim3((16 * 9 * O + 255) / 256), dim3(256), (size_t)0, s, w, wps, O, C); LAUNCHED();
+  pack_deconv_ps_kernel<<<(16 * 9 * O + 255) / 256, 256, 0, s>>>(w, wps, O, C); LAUNCHED();
 }
-int k_tc_deconv_ps(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat16* wps, const float* bias, __nv_bfloat16* dx, int act, float alpha, cudaStream_t s) {
-  TcConvParams p{}; p.mode = 0; p.dbg = 0;
+int k_tc_deconv_ps(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat16* wps, const float* bias, __nv_bfloat16* dx, int act, float alpha, cudaStream_t s, const TcEpi* epi) {
+  TcConvParams p{}; p.mode = 0;
   if (!tc_deconv_ps_shape(g) || !pick_row_tile(g.N, g.OH, g.OW, 128, &p.Nt, &p.Ht, &p.Wt)) return -1;
+  if (epi && epi->mode != EPI_PLAIN && epi->mode != EPI_ACTBWD) return -1;
   p.GH = g.OH; p.GW = g.OW; p.tiles_y = g.OH / p.Ht; p.taps_h = 3; p.taps_w = 3; p.chunks = g.O / 64; p.KW = 3;
-  p.SH = 1; p.SW = 1; p.PH = 1; p.PW = 1; p.OC = g.C; p.outH = g.H; p.outW = g.W; p.bias = bias; p.act = act; p.alpha = alpha; p.out = dx;
+  p.SH = 1; p.SW = 1; p.PH = 1; p.PW = 1; p.OC = g.C; p.outH = g.H; p.outW = g.W; p.out = dx;
+  fill_epi(p, bias, act, alpha, epi);
   CUtensorMap tmA, tmB;
   cuuint64_t dims[4] = {(cuuint64_t)g.O, (cuuint64_t)g.OW, (cuuint64_t)g.OH, (cuuint64_t)g.N};
   cuuint64_t strides[3] = {(cuuint64_t)g.O * 2, (cuuint64_t)g.OW * g.O * 2, (cuuint64_t)g.OH * g.OW * g.O * 2};
@@ -795,11 +725,10 @@ int k_tc_deconv_ps(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat
   if (make_map_bf16(&tmA, dy, 4, dims, strides, box, es)) return -1;
   if (weight_map(&tmB, wps, 16, 9, g.O, 16)) return -1;
   using S = TcSmem<16, 4>;
-  static bool attr_set = false;
-  if (!attr_set) { if (cudaFuncSetAttribute(tc_conv_kernel<16, 4, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) return -2; attr_set = true; }
   dim3 grid((unsigned)((long)g.N * g.OH * g.OW / 128), 1, 1);
-  launch_pdl(tc_conv_kernel<16, 4, 1, false, true>, grid, dim3(192), (size_t)S::TOTAL, s, tmA, tmB, p);
-  LAUNCHED();
+  if (p.epi == EPI_ACTBWD) { TC_SET_SMEM_ONCE((tc_conv_kernel<16, 4, EPI_ACTBWD, false, true>), S::TOTAL); tc_conv_kernel<16, 4, EPI_ACTBWD, false, true><<<grid, 192, S::TOTAL, s>>>(tmA, tmB, p); }
+  else { TC_SET_SMEM_ONCE((tc_conv_kernel<16, 4, EPI_PLAIN, false, true>), S::TOTAL); tc_conv_kernel<16, 4, EPI_PLAIN, false, true><<<grid, 192, S::TOTAL, s>>>(tmA, tmB, p); }
+  LAUNCHED(); g_tc_last_kernel = "tc_conv_kernel<16,4,PS>";
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
 }
 
@@ -875,7 +804,7 @@ __device__ __forceinline__ void edge_build_row(const TcEdgeParams& p, const uint
                  case 3: edge_build_row_c<3>(p, slab, tile, row, ones); break; default: edge_build_row_c<4>(p, slab, tile, row, ones); break; }
 }
 
-__global__ void __launch_bounds__(128) tc_edge_conv_kernel(const TcEdgeParams p) { pdl_prologue();
+__global__ void __launch_bounds__(128) tc_edge_conv_kernel(const TcEdgeParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -957,7 +886,7 @@ __global__ void __launch_bounds__(128) tc_edge_conv_kernel(const TcEdgeParams p)
 // dy rows are copied as they are (64 channels = 128 B), xcol rows are built as above.  O = 64 fills half of the M = 128 instruction;
 // the second 64-row block of the A descriptor points at the xcol tile (LBO = 16 KB), those accumulator rows are never read.
 // Each CTA walks tiles_per_cta consecutive tiles (split over pixels), accumulating in TMEM, and writes one fp32 partial.
-__global__ void __launch_bounds__(128) tc_edge_wgrad_kernel(const TcEdgeParams p) { pdl_prologue();
+__global__ void __launch_bounds__(128) tc_edge_wgrad_kernel(const TcEdgeParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -1052,15 +981,15 @@ int k_tc_edge_conv(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat1
   p.x = x; p.w = w; p.bias = bias; p.out = out; p.N = g.N; p.H = g.H; p.W = g.W; p.C = g.C; p.OH = g.OH; p.OW = g.OW; p.O = g.O; p.tiles_y = g.OH / p.Ht;
   p.tiles_total = g.N * p.tiles_y; p.act = act; p.alpha = alpha;
   const size_t smem = 1024 + 24576 + EDGE_SLAB_BYTES + 64;
-  static bool attr_set = false;
-  if (!attr_set) { if (cudaFuncSetAttribute(tc_edge_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2; attr_set = true; }
+  TC_SET_SMEM_ONCE(tc_edge_conv_kernel, smem);
   static int target = -1; if (target < 0) { const char* e = getenv("B2G_EDGE_CONV_CTAS"); target = e ? atoi(e) : 592; if (target < 1) target = 592; }
   p.tiles_per_cta = (p.tiles_total + target - 1) / target;
-  launch_pdl(tc_edge_conv_kernel, dim3((unsigned)((p.tiles_total + p.tiles_per_cta - 1) / p.tiles_per_cta), (unsigned)(g.O / 64)), dim3(128), smem, s, p);
-  LAUNCHED();
+  tc_edge_conv_kernel<<<dim3((unsigned)((p.tiles_total + p.tiles_per_cta - 1) / p.tiles_per_cta), (unsigned)(g.O / 64)), 128, smem, s>>>(p);
+  LAUNCHED(); g_tc_last_kernel = "tc_edge_conv_kernel";
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
 }
-int k_tc_edge_wgrad(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* db, float* scratch, size_t scratch_floats, int accumulate, cudaStream_t s) {
+static void reduce_or_defer(ReduceList* defer, const float* src, float* dst, size_t n, int splits, size_t stride, int accumulate, cudaStream_t s);
+int k_tc_edge_wgrad(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* db, float* scratch, size_t scratch_floats, int accumulate, cudaStream_t s, ReduceList* defer) {
   TcEdgeParams p{}; if (!edge_tile(g, &p.Ht) || g.O != 64) return -1;
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(dy) & 15)) return -1;
   p.x = x; p.dy = dy; p.part = scratch; p.N = g.N; p.H = g.H; p.W = g.W; p.C = g.C; p.OH = g.OH; p.OW = g.OW; p.O = g.O; p.tiles_y = g.OH / p.Ht;
@@ -1069,13 +998,12 @@ int k_tc_edge_wgrad(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat
   if ((size_t)ctas * (n + 64) > scratch_floats) return -5;
   if (db && g.C < 4) p.part_b = scratch + (size_t)ctas * n;
   const size_t smem = 1024 + 32768 + EDGE_SLAB_BYTES + 64;
-  static bool attr_set = false;
-  if (!attr_set) { if (cudaFuncSetAttribute(tc_edge_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2; attr_set = true; }
-  launch_pdl(tc_edge_wgrad_kernel, dim3((unsigned)ctas), dim3(128), smem, s, p);
-  LAUNCHED();
+  TC_SET_SMEM_ONCE(tc_edge_wgrad_kernel, smem);
+  tc_edge_wgrad_kernel<<<dim3((unsigned)ctas), 128, smem, s>>>(p);
+  LAUNCHED(); g_tc_last_kernel = "tc_edge_wgrad_kernel";
   if (cudaPeekAtLastError() != cudaSuccess) return -3;
-  k_reduce_splits(scratch, dw, n, ctas, n, accumulate, s);
-  if (p.part_b) k_reduce_splits(p.part_b, db, 64, ctas, 64, accumulate, s);
+  reduce_or_defer(defer, scratch, dw, n, ctas, n, accumulate, s);
+  if (p.part_b) reduce_or_defer(defer, p.part_b, db, 64, ctas, 64, accumulate, s);
   return p.part_b ? 1 : 0;      // 1: the bias gradient (column sums of dy) was produced as well
 }
 
@@ -1107,7 +1035,7 @@ struct TcWgradSmem {
 };
 
 template <int BNW, int STAGES>
-__global__ void __launch_bounds__(192) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, const TcWgradParams p) { pdl_prologue();
+__global__ void __launch_bounds__(192) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, const TcWgradParams p) {
   using S = TcWgradSmem<BNW, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -1195,7 +1123,7 @@ struct TcWgrad2Smem {
   static constexpr int A_BYTES = 4 * 64 * 128, B_BYTES = 4 * 64 * 128, STAGE_BYTES = A_BYTES + B_BYTES, STAGES = 3;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES, TOTAL = BAR_OFF + 256 + 1024;
 };
-__global__ void __launch_bounds__(192) tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, const TcWgradParams p) { pdl_prologue();
+__global__ void __launch_bounds__(192) tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, const TcWgradParams p) {
   using S = TcWgrad2Smem; constexpr int STAGES = S::STAGES, BNW = 256;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -1279,17 +1207,24 @@ __global__ void __launch_bounds__(192) tc_wgrad2_kernel(const __grid_constant__ 
 }
 
 static int wgrad_bnw(const ConvGeom& g) { if (g.C % 64) return 0; const long cols = (long)g.KH * g.KW * g.C; return cols % 256 == 0 ? 256 : cols % 128 == 0 ? 128 : 64; }
-static bool wgrad_mt2(const ConvGeom& g) {
-  static int on = -1; if (on < 0) { const char* e = getenv("B2G_WGRAD_MT2"); on = (e && e[0] == '1') ? 1 : 0; }
-  return on && g.O % 256 == 0 && wgrad_bnw(g) == 256;
-}
-static int tc_wgrad_splits(const ConvGeom& g) {
+static int wgrad_target() { static int target = -1; if (target < 0) { const char* e = getenv("B2G_WGRAD_CTAS"); target = e ? atoi(e) : 148; if (target < 1) target = 148; } return target; }
+// one CTA per SM (192 KB of smem): choose the split count so that the whole grid is ONE wave (<= 148 CTAs); measured: D2 wgrad 52 -> 39 us
+static int wgrad_splits_for(const ConvGeom& g, int o_tile) {
   const int bnw = wgrad_bnw(g); if (!bnw) return 1;
-  long tiles = (long)(g.O / (wgrad_mt2(g) ? 256 : 128)) * (g.KH * g.KW * g.C / bnw), kbt = (long)g.N * g.OH * g.OW / 64;
-  // one CTA per SM (192 KB of smem): choose the split count so that the whole grid is ONE wave (<= 148 CTAs); measured: D2 wgrad 52 -> 39 us
-  static int target = -1; if (target < 0) { const char* e = getenv("B2G_WGRAD_CTAS"); target = e ? atoi(e) : 148; }
-  long sp = target / tiles, cap = kbt / 8; if (cap < 1) cap = 1; if (sp > cap) sp = cap; if (sp < 1) sp = 1; return (int)sp;
+  long tiles = (long)(g.O / o_tile) * (g.KH * g.KW * g.C / bnw), kbt = (long)g.N * g.OH * g.OW / 64;
+  long sp = wgrad_target() / tiles, cap = kbt / 8; if (cap < 1) cap = 1; if (sp > cap) sp = cap; if (sp < 1) sp = 1; return (int)sp;
 }
+// M = 256 (two accumulators, tc_wgrad2_kernel) shares every activation tile between 256 output channels.  Measured on B200 (round 2,
+// profiles/r02_kernel_bench_mt2.md): a win where each CTA still walks >= 12 K-blocks (D3 39.7 -> 37.0 us, D4 43.1 -> 37.0 us), a loss where
+// the doubled tile leaves 7-8 K-blocks per CTA (G2 29.2 -> 30.9, G3 28.3 -> 30.9): prologue / epilogue dominate there.  B2G_WGRAD_MT2=0|1 forces.
+static bool wgrad_mt2(const ConvGeom& g) {
+  static int force = -2; if (force == -2) { const char* e = getenv("B2G_WGRAD_MT2"); force = e ? (e[0] == '1' ? 1 : 0) : -1; }
+  if (g.O % 256 || wgrad_bnw(g) != 256 || force == 0) return false;
+  if (force == 1) return true;
+  const long kbt = (long)g.N * g.OH * g.OW / 64; const int sp = wgrad_splits_for(g, 256);
+  return (kbt + sp - 1) / sp >= 12;
+}
+static int tc_wgrad_splits(const ConvGeom& g) { return wgrad_splits_for(g, wgrad_mt2(g) ? 256 : 128); }
 bool tc_wgrad_supported(const ConvGeom& g) {
   int a, b, c;
   return g.O % 128 == 0 && wgrad_bnw(g) != 0 && g.SH >= 1 && g.SH <= 2 && g.SW == g.SH && ((long)g.N * g.OH * g.OW) % 64 == 0 &&
@@ -1297,20 +1232,26 @@ bool tc_wgrad_supported(const ConvGeom& g) {
 }
 size_t k_tc_wgrad_scratch_floats(const ConvGeom& g) {
   if (!tc_wgrad_supported(g)) return 0;
-  return (size_t)tc_wgrad_splits(g) * g.O * g.KH * g.KW * g.C;
+  return (size_t)std::max(wgrad_splits_for(g, 128), g.O % 256 == 0 ? wgrad_splits_for(g, 256) : 1) * g.O * g.KH * g.KW * g.C;
 }
 
 template <int BNW, int STAGES>
-static int launch_wgrad(const CUtensorMap& tmDy, const CUtensorMap& tmX, const TcWgradParams& p, dim3 grid, cudaStream_t s) {
+static int launch_wgrad(const CUtensorMap& tmDy, const CUtensorMap& tmX, const TcWgradParams& p, dim3 grid, cudaStream_t s, const char* name) {
   using S = TcWgradSmem<BNW, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) { if (cudaFuncSetAttribute(tc_wgrad_kernel<BNW, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) return -2; attr_set = true; }
-  launch_pdl(tc_wgrad_kernel<BNW, STAGES>, dim3(grid), dim3(192), (size_t)(S::TOTAL), s, tmDy, tmX, p);
-  LAUNCHED();
+  TC_SET_SMEM_ONCE((tc_wgrad_kernel<BNW, STAGES>), S::TOTAL);
+  tc_wgrad_kernel<BNW, STAGES><<<grid, 192, S::TOTAL, s>>>(tmDy, tmX, p);
+  LAUNCHED(); g_tc_last_kernel = name;
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
 }
 
-int k_tc_wgrad(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* scratch, size_t scratch_floats, int accumulate, cudaStream_t s) {
+// the split-K partials land in `scratch`; their fixed-order sum into dw is either launched here or, with `defer`, queued for the caller's
+// one k_reduce_multi launch at the end of the backward pass (scratch must then stay untouched until that launch)
+static void reduce_or_defer(ReduceList* defer, const float* src, float* dst, size_t n, int splits, size_t stride, int accumulate, cudaStream_t s) {
+  if (defer && !accumulate && defer->count < ReduceList::MAX_JOBS) { reduce_list_push(defer, src, dst, (int64_t)n, splits, (int64_t)stride); return; }
+  k_reduce_splits(src, dst, n, splits, stride, accumulate, s);
+}
+
+int k_tc_wgrad(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* scratch, size_t scratch_floats, int accumulate, cudaStream_t s, ReduceList* defer) {
   TcWgradParams p{};
   if (!pick_row_tile(g.N, g.OH, g.OW, 64, &p.Nt, &p.Ht, &p.Wt)) return -1;
   const int BNW = wgrad_bnw(g); const size_t n = (size_t)g.O * g.KH * g.KW * g.C;
@@ -1330,19 +1271,18 @@ int k_tc_wgrad(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* d
   dim3 grid((unsigned)splits, (unsigned)(p.taps * g.C / BNW), (unsigned)(g.O / 128));
   int rc;
   if (wgrad_mt2(g)) {
-    static bool attr2 = false;
-    if (!attr2) { if (cudaFuncSetAttribute(tc_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcWgrad2Smem::TOTAL) != cudaSuccess) return -2; attr2 = true; }
+    TC_SET_SMEM_ONCE(tc_wgrad2_kernel, TcWgrad2Smem::TOTAL);
     grid.z = (unsigned)(g.O / 256);
-    launch_pdl(tc_wgrad2_kernel, dim3(grid), dim3(192), (size_t)TcWgrad2Smem::TOTAL, s, tmDy, tmX, p); LAUNCHED();
+    tc_wgrad2_kernel<<<grid, 192, TcWgrad2Smem::TOTAL, s>>>(tmDy, tmX, p); LAUNCHED(); g_tc_last_kernel = "tc_wgrad2_kernel";
     rc = cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
   } else
   switch (BNW) {
-    case 64: rc = launch_wgrad<64, 4>(tmDy, tmX, p, grid, s); break;
-    case 128: rc = launch_wgrad<128, 4>(tmDy, tmX, p, grid, s); break;
-    default: rc = launch_wgrad<256, 4>(tmDy, tmX, p, grid, s); break;
+    case 64: rc = launch_wgrad<64, 4>(tmDy, tmX, p, grid, s, "tc_wgrad_kernel<64,4>"); break;
+    case 128: rc = launch_wgrad<128, 4>(tmDy, tmX, p, grid, s, "tc_wgrad_kernel<128,4>"); break;
+    default: rc = launch_wgrad<256, 4>(tmDy, tmX, p, grid, s, "tc_wgrad_kernel<256,4>"); break;
   }
   if (rc) return rc;
-  k_reduce_splits(scratch, dw, n, splits, n, accumulate, s);
+  reduce_or_defer(defer, scratch, dw, n, splits, n, accumulate, s);
   return 0;
 }
 

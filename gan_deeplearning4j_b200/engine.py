@@ -172,7 +172,8 @@ class Net:
     # --- checkpoint / resume (ModelSerializer.writeModel, J:606-618; serializer.py) ---
     def save(self, path, save_updater: bool = True):
         from . import serializer
-        serializer.save_net(self, path, self.specs, self.input_shape, save_updater, {"precision": "bf16" if self.precision == BF16 else "fp32", "max_batch": self.max_batch})
+        serializer.save_net(self, path, self.specs, self.input_shape, save_updater,
+                            {"precision": "bf16" if self.precision == BF16 else "fp32", "max_batch": self.max_batch, "iteration": self.iteration()})
 
     def restore(self, path, load_updater: bool = True):
         """Loads parameters (and updater state) of a checkpoint written by save() into this net (same architecture)."""
@@ -215,6 +216,21 @@ class Net:
     def average_parameters(self):
         """ParameterAveragingTrainingMaster: params and updater state <- mean over ranks (J:325-330)."""
         check(self.lib.b2g_net_average_parameters(self.h))
+
+    def iteration(self) -> int:
+        """The updater's iteration counter (Adam's t - 1); part of a checkpoint."""
+        v = C.c_int64()
+        check(self.lib.b2g_net_get_iteration(self.h, C.byref(v)))
+        return v.value
+
+    def set_iteration(self, it: int):
+        check(self.lib.b2g_net_set_iteration(self.h, int(it)))
+
+    def simt_gemm_calls(self) -> int:
+        """BF16 nets: GEMM-shaped operations that ran on the SIMT kernels instead of tcgen05 since creation."""
+        v = C.c_uint64()
+        check(self.lib.b2g_net_simt_gemm_calls(self.h, C.byref(v)))
+        return v.value
 
     def input_gradient(self, batch: int) -> np.ndarray:
         out = np.empty((batch, int(np.prod(self.input_shape))), np.float32)
@@ -280,3 +296,27 @@ def test_conv(ctx: Context, kind: int, impl: int, precision: int, geom: Dict[str
     ms = C.c_float()
     check(ctx.lib.b2g_test_conv(ctx.h, kind, impl, precision, C.byref(g), _fp(a), _fp(b), _fp(out), iters, C.byref(ms)))
     return out, ms.value
+
+
+EPI_PLAIN, EPI_STATS, EPI_BNBWD, EPI_ACTBWD = 0, 1, 2, 3
+
+
+def test_conv_ex(ctx: Context, kind: int, geom: Dict[str, int], a, b, out_size: int, *, epi: int = 0, act: str = "identity", alpha: float = 0.0,
+                 bias=None, scale=None, groups: int = 1, aux=None, coef=None, iters: int = 1):
+    """tcgen05 fprop (kind 0) / dgrad (kind 1) with the epilogue the training step uses.  Returns (out, stats or None, kernel name, ms)."""
+    g = _lib.ConvGeom(**geom)
+    a, b = _f32(a).ravel(), _f32(b).ravel()
+    out = np.empty(out_size, np.float32)
+    oc = geom["o"] if kind == 0 else geom["c"]
+    o = _lib.TestConvOpts()
+    o.epi, o.act, o.alpha, o.groups = epi, ACTS[act], alpha, groups
+    keep = []
+    for name, v in (("bias", bias), ("scale", scale), ("aux", aux), ("coef", coef)):
+        if v is not None:
+            arr = _f32(v).ravel(); keep.append(arr); setattr(o, name, _fp(arr))
+    stats = None
+    if epi in (EPI_STATS, EPI_BNBWD):
+        stats = np.zeros((groups, 2, oc), np.float64); o.stats = stats.ctypes.data_as(C.POINTER(C.c_double))
+    ms = C.c_float()
+    check(ctx.lib.b2g_test_conv_ex(ctx.h, kind, 1, BF16, C.byref(g), _fp(a), _fp(b), _fp(out), iters, C.byref(ms), C.byref(o)))
+    return out, stats, o.kernel.decode(), ms.value

@@ -96,4 +96,7 @@ def restore_into(net, path, load_updater: bool = True) -> Dict:
     net.set_params(m["params"])
     if load_updater and m["updater_state"] is not None:
         net.set_updater_state(m["updater_state"])
+        # Adam's bias correction depends on the iteration count: warm moments with t = 1 would diverge from an uninterrupted run
+        if "iteration" in m["meta"] and hasattr(net, "set_iteration"):
+            net.set_iteration(int(m["meta"]["iteration"]))
     return m

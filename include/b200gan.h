@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define B2G_VERSION 100
+#define B2G_VERSION 101
 #define B2G_NAME_LEN 64
 
 typedef struct b2g_ctx b2g_ctx;
@@ -154,6 +154,13 @@ int32_t b2g_net_get_input_gradient(b2g_net* net, int32_t batch, float* host);
 /* ComputationGraph.fit(DataSet) (J:426,471 via SparkComputationGraph): one minibatch =
  * computeGradientAndScore + [gradient all-reduce if a communicator is attached] + updater + params.subi. */
 int32_t b2g_net_fit(b2g_net* net, const float* x, const float* y, int32_t batch, float* score);
+/* The updater's iteration counter (BaseMultiLayerUpdater's iteration; Adam's t = iteration + 1).  ModelSerializer keeps it in
+ * configuration.json ("iterationCount"); a restore that drops it restarts Adam's bias correction with warm moments (J:606-618). */
+int32_t b2g_net_get_iteration(b2g_net* net, int64_t* out);
+int32_t b2g_net_set_iteration(b2g_net* net, int64_t iteration);
+/* BF16 nets: how many GEMM-shaped operations ran on the SIMT kernels instead of tcgen05 since creation (skinny layers by design, or a
+ * shape the tensor-core kernels do not tile).  north_star: no silent fallback -- bench.py prints it per step. */
+int32_t b2g_net_simt_gemm_calls(b2g_net* net, uint64_t* out);
 
 /* ---------------------------------------------------------------- the fused GAN step -------------- */
 /* The adversarial iteration J:408-471 with dis / gan / gen sharing storage (the 28 setParam copies J:429-510
@@ -206,6 +213,24 @@ typedef struct {
 } b2g_conv_geom;
 int32_t b2g_test_conv(b2g_ctx* ctx, int32_t kind, int32_t impl, int32_t precision, const b2g_conv_geom* g,
                       const float* x_or_dy, const float* w_or_x, float* out, int32_t iters, float* ms_per_iter);
+/* The same with the epilogue the training step actually uses (impl 1, kind 0 / 1): bias, folded inference-BatchNorm scale, activation,
+ * and the fused BatchNorm epilogues of kernels_tc.cu.  `kernel` returns the name of the tcgen05 kernel that was dispatched, so a parity
+ * test can assert that it exercised the variant the benchmark runs (persistent MT=2, one-wave split-K, ...). */
+typedef struct {
+  int32_t epi;            /* 0 plain; 1 + statistics (sum, sum of squares per group and channel) of the stored outputs;
+                             2 BatchNorm-backward epilogue: out = acc * act'(aux*scale+shift), statistics sum out, sum out*xhat;
+                             3 activation-backward epilogue: out = acc * act'(aux) with aux the forward output */
+  int32_t act; float alpha;
+  const float* bias;      /* [C_out] or NULL */
+  const float* scale;     /* [C_out] or NULL: out = act(acc*scale + bias) */
+  int32_t groups;         /* statistics groups (the batch split evenly, like real | fake in the D step) */
+  const float* aux;       /* epi 2: the BatchNorm input z; epi 3: the forward output a (NHWC, shape of the result) */
+  const float* coef;      /* epi 2: [groups][4][C_out] = scale, shift, mean, invstd */
+  double* stats;          /* out (epi 1 / 2): [groups][2][C_out] */
+  char kernel[64];        /* out */
+} b2g_test_conv_opts;
+int32_t b2g_test_conv_ex(b2g_ctx* ctx, int32_t kind, int32_t impl, int32_t precision, const b2g_conv_geom* g,
+                         const float* x_or_dy, const float* w_or_x, float* out, int32_t iters, float* ms_per_iter, b2g_test_conv_opts* opts);
 
 #ifdef __cplusplus
 }

@@ -35,7 +35,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
     for n in names:
         assert hasattr(lib, n), f"libb200gan.so does not export {n}"
     assert sorted(b.PROTOTYPES) == names, set(names) ^ set(b.PROTOTYPES)
-    assert lib.b2g_version() == 100
+    assert lib.b2g_version() == 101
 
 
 def test_jni_symbols_exported_without_jni_h(lib):

@@ -1,0 +1,229 @@
+"""Parity of the BENCHMARKED path at the BENCHMARKED sizes: every tcgen05 kernel variant that the C2 step
+(64x64x3 DCGAN, batch 128; reference call sites J:135-150, J:203-219) dispatches -- persistent two-M-tile conv, one-CTA-per-tile conv,
+folded-BatchNorm (AFFINE) epilogue, the fused BatchNorm epilogues (EPI_STATS / EPI_BNBWD / EPI_ACTBWD), one-wave split-K weight gradient,
+M = 256 weight gradient, the 3-channel edge kernels -- runs here through the C-ABI test hook with the PRODUCTION dispatch, the hook reports
+which kernel ran (asserted), and the result is compared with the CPU oracle (oracle/dl4j_oracle.py ConvolutionLayer / Deconvolution2D
+semantics) on the same bf16-rounded operands:
+    bf16 outputs:  |got - ref| <= 2^-8 |ref| + 2e-3 rms(ref)        (one bf16 rounding is 2^-9 relative; fp32 accumulation order)
+    fp32 wgrad:    max|got - ref| <= 1e-4 max|ref|
+The oracle evaluates whole sampled images (first / last, around the persistent kernel's 148-item wrap, the real|fake group boundary) for
+fprop / dgrad, and the full batch in image chunks (the weight gradient is a sum over images) for wgrad.
+"""
+import numpy as np
+import pytest
+
+from oracle import dl4j_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+N = 128     # C2 per-GPU batch; the D step runs 2N
+
+
+@pytest.fixture(scope="module")
+def b200():
+    import gan_deeplearning4j_b200 as b
+    ctx = b.Context(0)
+    yield b, ctx
+    ctx.close()
+
+
+def bf16_round(a):
+    import torch
+    return torch.tensor(np.asarray(a, np.float32)).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+def check_bf16(got, ref, what):
+    got = np.asarray(got, np.float64); ref = np.asarray(ref, np.float64)
+    tol = 2.0 ** -8 * np.abs(ref) + 2e-3 * np.sqrt(np.mean(ref ** 2)) + 1e-30
+    bad = np.abs(got - ref) > tol
+    assert not bad.any(), f"{what}: {bad.sum()} of {bad.size} elements outside 2^-8|ref| + 2e-3 rms; worst |d|={np.abs(got - ref).max():.4g} rms={np.sqrt(np.mean(ref ** 2)):.4g}"
+
+
+def sample_images(n):
+    return sorted(set(i for i in (0, 1, 36, 37, 73, 74, n // 2 - 1, n // 2, n - 2, n - 1) if 0 <= i < n))
+
+
+def conv_layer(c, oc, wt):
+    l = o.Conv2D(c, oc, (4, 4), (2, 2), (1, 1), has_bias=False); l.init(np.random.default_rng(0), np.float64); l.params["W"] = wt.astype(np.float64); return l
+
+
+def geom_of(n, h, c, oc):
+    return dict(n=n, h=h, w=h, c=c, oh=h // 2, ow=h // 2, o=oc, kh=4, kw=4, sh=2, sw=2, ph=1, pw=1)
+
+
+def act_fwd(name, z, alpha):
+    return {"identity": lambda: z, "relu": lambda: np.maximum(z, 0), "lrelu": lambda: np.where(z > 0, z, alpha * z), "tanh": lambda: np.tanh(z)}[name]()
+
+
+def act_grad_pre(name, u, alpha):
+    return {"identity": lambda: np.ones_like(u), "relu": lambda: (u > 0).astype(np.float64), "lrelu": lambda: np.where(u > 0, 1.0, alpha)}[name]()
+
+
+# (name, batch, conv-input size h, c, o, expected kernel)   -- conv geometry 4x4 s2 p1: x [n,h,h,c] -> y [n,h/2,h/2,o]
+FPROP = [
+    ("D2 fprop, D step (2N, real|fake)", 2 * N, 32, 64, 128, "tc_conv_persistent_kernel<128,4,2>"),
+    ("D3 fprop, D step", 2 * N, 16, 128, 256, "tc_conv_kernel<128,3>"),
+    ("D4 fprop, D step", 2 * N, 8, 256, 512, "tc_conv_kernel<64,4>"),
+    ("D2 fprop, G step / G4 input gradient", N, 32, 64, 128, "tc_conv_kernel<128,3>"),
+    ("D3 fprop, G step / G3 input gradient", N, 16, 128, 256, "tc_conv_kernel<64,4>"),
+    ("D4 fprop, G step / G2 input gradient", N, 8, 256, 512, "tc_conv_kernel<64,4>"),
+]
+
+
+@pytest.mark.parametrize("case", FPROP, ids=[c[0] for c in FPROP])
+@pytest.mark.parametrize("epi", ["stats", "bnbwd_relu", "plain_bias_lrelu"])
+def test_fprop_production_dispatch(b200, case, epi):
+    """conv forward (D2-D4) with the BatchNorm statistics epilogue, and the same kernel as the generator's input-gradient GEMM with the
+    BatchNorm-backward epilogue (J:197-199 BatchNormalization + ReLU below each transposed conv)."""
+    b, ctx = b200
+    name, n, h, c, oc, kernel = case
+    rng = np.random.default_rng(11)
+    x = bf16_round(rng.standard_normal((n, h, h, c))); wt = bf16_round(rng.standard_normal((oc, 4, 4, c)) / np.sqrt(16 * c))
+    g = geom_of(n, h, c, oc); oh = h // 2
+    groups = 2 if n == 2 * N else 1
+    idx = sample_images(n)
+    lay = conv_layer(c, oc, wt.transpose(0, 3, 1, 2))
+    ref = lay.forward(x[idx].transpose(0, 3, 1, 2).astype(np.float64), True).transpose(0, 2, 3, 1)        # [len(idx), oh, oh, oc]
+    if epi == "stats":
+        out, stats, k, _ = b.test_conv_ex(ctx, 0, g, x, wt, n * oh * oh * oc, epi=b.EPI_STATS, groups=groups)
+        out = out.reshape(n, oh, oh, oc)
+        check_bf16(out[idx], ref, name)
+        # the statistics are those of the STORED bf16 tensor, per (group, channel): exact up to fp32 summation order inside a 128-row tile
+        og = out.reshape(groups, -1, oc).astype(np.float64)
+        np.testing.assert_allclose(stats[:, 0, :], og.sum(1), rtol=2e-5, atol=2e-3)
+        np.testing.assert_allclose(stats[:, 1, :], (og ** 2).sum(1), rtol=2e-5, atol=2e-3)
+    elif epi == "plain_bias_lrelu":
+        bias = rng.standard_normal(oc).astype(np.float32) * 0.1
+        out, _, k, _ = b.test_conv_ex(ctx, 0, g, x, wt, n * oh * oh * oc, act="lrelu", alpha=0.2, bias=bias)
+        check_bf16(out.reshape(n, oh, oh, oc)[idx], act_fwd("lrelu", ref + bias.astype(np.float64), 0.2), name)
+    else:
+        # the GEMM result is the epsilon w.r.t. the output of BatchNorm+ReLU; z = that BatchNorm's input, coef = its forward coefficients
+        z = bf16_round(rng.standard_normal((n, oh, oh, oc)))
+        mean = rng.standard_normal((groups, oc)) * 0.2; invstd = rng.uniform(0.5, 2.0, (groups, oc)); gamma = rng.uniform(0.5, 1.5, oc); beta = rng.standard_normal(oc) * 0.3
+        sc = gamma * invstd; sh = beta - mean * sc
+        coef = np.stack([sc, sh, mean, invstd], 1).astype(np.float32)            # [groups][4][oc]
+        out, stats, k, _ = b.test_conv_ex(ctx, 0, g, x, wt, n * oh * oh * oc, epi=b.EPI_BNBWD, act="relu", groups=groups, aux=z, coef=coef)
+        out = out.reshape(n, oh, oh, oc)
+        cf = coef.astype(np.float64)
+        gi = np.array([i // (n // groups) for i in idx])
+        u = z[idx].astype(np.float64) * cf[gi, 0][:, None, None, :] + cf[gi, 1][:, None, None, :]
+        check_bf16(out[idx], ref * act_grad_pre("relu", u, 0.0), name)
+        zg = z.reshape(groups, -1, oc).astype(np.float64); og = out.reshape(groups, -1, oc).astype(np.float64)
+        xh = (zg - cf[:, 2][:, None, :]) * cf[:, 3][:, None, :]
+        np.testing.assert_allclose(stats[:, 0, :], og.sum(1), rtol=2e-5, atol=2e-3)
+        np.testing.assert_allclose(stats[:, 1, :], (og * xh).sum(1), rtol=2e-5, atol=5e-3)
+    assert k == kernel, f"{name}: dispatched {k}, the C2 step is expected to run {kernel}"
+
+
+# conv geometry: dy [n,h/2,h/2,o] -> dx [n,h,h,c]  (= transposed-conv forward o -> c)
+DGRAD = [
+    ("D2 dgrad, D step (2N)", 2 * N, 32, 64, 128, "tc_conv_persistent_kernel<64,4,2>"),
+    ("D3 dgrad, D step", 2 * N, 16, 128, 256, "tc_conv_persistent_kernel<128,4,2>"),
+    ("D4 dgrad, D step", 2 * N, 8, 256, 512, "tc_conv_kernel<128,3>"),
+    ("G4 forward / D2 dgrad, G step (N)", N, 32, 64, 128, "tc_conv_persistent_kernel<64,4,2>"),
+    ("G3 forward / D3 dgrad, G step", N, 16, 128, 256, "tc_conv_kernel<128,3>"),
+    ("G2 forward / D4 dgrad, G step", N, 8, 256, 512, "tc_conv_kernel<64,4>"),
+]
+
+
+@pytest.mark.parametrize("case", DGRAD, ids=[c[0] for c in DGRAD])
+@pytest.mark.parametrize("epi", ["stats", "bnbwd_lrelu", "affine_relu", "actbwd_lrelu"])
+def test_dgrad_production_dispatch(b200, case, epi):
+    """Deconvolution2D forward = conv input gradient in sub-pixel phase form, weights read as MN-major tiles from the straight [O][16][C] copy:
+    train-mode generator forward (statistics epilogue), inference-mode generator forward (folded BatchNorm + ReLU: gen.output, J:420),
+    discriminator input gradients with the BatchNorm-backward / LeakyReLU-backward epilogues."""
+    b, ctx = b200
+    name, n, h, c, oc, kernel = case
+    rng = np.random.default_rng(12)
+    dy = bf16_round(rng.standard_normal((n, h // 2, h // 2, oc))); wt = bf16_round(rng.standard_normal((oc, 4, 4, c)) / np.sqrt(4 * oc))
+    g = geom_of(n, h, c, oc)
+    groups = 2 if n == 2 * N else 1
+    idx = sample_images(n)
+    lay = conv_layer(c, oc, wt.transpose(0, 3, 1, 2))
+    lay.forward(np.zeros((len(idx), c, h, h)), True)
+    ref = lay.backward(dy[idx].transpose(0, 3, 1, 2).astype(np.float64)).transpose(0, 2, 3, 1)           # [len(idx), h, h, c]
+    size = n * h * h * c
+    if epi == "stats":
+        out, stats, k, _ = b.test_conv_ex(ctx, 1, g, dy, wt, size, epi=b.EPI_STATS, groups=groups)
+        out = out.reshape(n, h, h, c); check_bf16(out[idx], ref, name)
+        og = out.reshape(groups, -1, c).astype(np.float64)
+        np.testing.assert_allclose(stats[:, 0, :], og.sum(1), rtol=2e-5, atol=2e-3)
+        np.testing.assert_allclose(stats[:, 1, :], (og ** 2).sum(1), rtol=2e-5, atol=2e-3)
+    elif epi == "affine_relu":
+        scale = rng.uniform(0.5, 1.5, c).astype(np.float32); shift = (rng.standard_normal(c) * 0.2).astype(np.float32)
+        out, _, k, _ = b.test_conv_ex(ctx, 1, g, dy, wt, size, act="relu", bias=shift, scale=scale)
+        check_bf16(out.reshape(n, h, h, c)[idx], act_fwd("relu", ref * scale.astype(np.float64) + shift.astype(np.float64), 0.0), name)
+    elif epi == "actbwd_lrelu":
+        a = bf16_round(rng.standard_normal((n, h, h, c)))
+        out, _, k, _ = b.test_conv_ex(ctx, 1, g, dy, wt, size, epi=b.EPI_ACTBWD, act="lrelu", alpha=0.2, aux=a)
+        check_bf16(out.reshape(n, h, h, c)[idx], ref * np.where(a[idx] > 0, 1.0, 0.2), name)
+    else:
+        z = bf16_round(rng.standard_normal((n, h, h, c)))
+        mean = rng.standard_normal((groups, c)) * 0.2; invstd = rng.uniform(0.5, 2.0, (groups, c)); gamma = rng.uniform(0.5, 1.5, c); beta = rng.standard_normal(c) * 0.3
+        sc = gamma * invstd; sh = beta - mean * sc
+        coef = np.stack([sc, sh, mean, invstd], 1).astype(np.float32)
+        out, stats, k, _ = b.test_conv_ex(ctx, 1, g, dy, wt, size, epi=b.EPI_BNBWD, act="lrelu", alpha=0.2, groups=groups, aux=z, coef=coef)
+        out = out.reshape(n, h, h, c); cf = coef.astype(np.float64)
+        gi = np.array([i // (n // groups) for i in idx])
+        u = z[idx].astype(np.float64) * cf[gi, 0][:, None, None, :] + cf[gi, 1][:, None, None, :]
+        check_bf16(out[idx], ref * act_grad_pre("lrelu", u, 0.2), name)
+        zg = z.reshape(groups, -1, c).astype(np.float64); og = out.reshape(groups, -1, c).astype(np.float64)
+        xh = (zg - cf[:, 2][:, None, :]) * cf[:, 3][:, None, :]
+        np.testing.assert_allclose(stats[:, 0, :], og.sum(1), rtol=2e-5, atol=2e-3)
+        np.testing.assert_allclose(stats[:, 1, :], (og * xh).sum(1), rtol=2e-5, atol=5e-3)
+    assert k == kernel, f"{name}: dispatched {k}, the C2 step is expected to run {kernel}"
+
+
+WGRAD = [
+    ("D2 wgrad, D step (2N)", 2 * N, 32, 64, 128, "tc_wgrad_kernel<256,4>"),
+    ("D3 wgrad, D step", 2 * N, 16, 128, 256, "tc_wgrad2_kernel"),
+    ("D4 wgrad, D step", 2 * N, 8, 256, 512, "tc_wgrad2_kernel"),
+    ("G4 wgrad (N)", N, 32, 64, 128, "tc_wgrad_kernel<256,4>"),
+    ("G3 wgrad", N, 16, 128, 256, "tc_wgrad_kernel<256,4>"),
+    ("G2 wgrad", N, 8, 256, 512, "tc_wgrad_kernel<256,4>"),
+]
+
+
+@pytest.mark.parametrize("case", WGRAD, ids=[c[0] for c in WGRAD])
+def test_wgrad_production_dispatch(b200, case):
+    """dW = sum over the whole batch: one-wave split-K grids (<= 148 CTAs) with fp32 partials and the fixed-order reduction; M = 256 kernel
+    where each CTA still walks >= 12 K-blocks.  Oracle: ConvolutionLayer.backpropGradient on image chunks, summed (dW is linear in the batch)."""
+    b, ctx = b200
+    name, n, h, c, oc, kernel = case
+    rng = np.random.default_rng(13)
+    x = bf16_round(rng.standard_normal((n, h, h, c))); dy = bf16_round(rng.standard_normal((n, h // 2, h // 2, oc)))
+    g = geom_of(n, h, c, oc)
+    opts = b._lib.TestConvOpts()
+    import ctypes as C
+    out = np.empty(oc * 16 * c, np.float32); ms = C.c_float()
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    xa, da = np.ascontiguousarray(x.ravel()), np.ascontiguousarray(dy.ravel())
+    b.engine.check(ctx.lib.b2g_test_conv_ex(ctx.h, 2, 1, b.BF16, C.byref(b._lib.ConvGeom(**g)), fp(xa), fp(da), fp(out), 1, C.byref(ms), C.byref(opts)))
+    lay = conv_layer(c, oc, np.zeros((oc, c, 4, 4)))
+    ref = np.zeros((oc, c, 4, 4))
+    for i0 in range(0, n, 32):
+        lay.forward(x[i0:i0 + 32].transpose(0, 3, 1, 2).astype(np.float64), True)
+        lay.backward(dy[i0:i0 + 32].transpose(0, 3, 1, 2).astype(np.float64)); ref += lay.grads["W"]
+    ref = ref.transpose(0, 2, 3, 1)
+    err = np.abs(out.reshape(oc, 4, 4, c) - ref).max() / np.abs(ref).max()
+    assert err < 1e-4, (name, err)
+    assert opts.kernel.decode() == kernel, f"{name}: dispatched {opts.kernel.decode()}, expected {kernel}"
+
+
+def test_edge_kernels_full_size(b200):
+    """D1 (3 -> 64 image channels, J:135-140 analogue in the 64x64 DCGAN) and G-last at the C2 batch: tcgen05 edge kernels (impl 3)."""
+    b, ctx = b200
+    rng = np.random.default_rng(14)
+    n, h, c, oc = 2 * N, 64, 3, 64
+    x = bf16_round(rng.uniform(-1, 1, (n, h, h, c))); wt = bf16_round(rng.standard_normal((oc, 4, 4, c)) / np.sqrt(16 * c)); dy = bf16_round(rng.standard_normal((n, h // 2, h // 2, oc)))
+    g = geom_of(n, h, c, oc); idx = sample_images(n)
+    lay = conv_layer(c, oc, wt.transpose(0, 3, 1, 2))
+    y = lay.forward(x[idx].transpose(0, 3, 1, 2).astype(np.float64), True).transpose(0, 2, 3, 1)
+    dx = lay.backward(dy[idx].transpose(0, 3, 1, 2).astype(np.float64)).transpose(0, 2, 3, 1)
+    got, _ = b.test_conv(ctx, 0, 3, b.BF16, g, x, wt, n * 32 * 32 * oc); check_bf16(got.reshape(n, 32, 32, oc)[idx], y, "D1 fprop (tc_edge_conv_kernel)")
+    got, _ = b.test_conv(ctx, 1, 3, b.BF16, g, dy, wt, n * h * h * c); check_bf16(got.reshape(n, h, h, c)[idx], dx, "D1 dgrad / G-last forward (pixel-shuffle tcgen05 conv)")
+    ref = np.zeros((oc, c, 4, 4))
+    for i0 in range(0, n, 64):
+        lay.forward(x[i0:i0 + 64].transpose(0, 3, 1, 2).astype(np.float64), True); lay.backward(dy[i0:i0 + 64].transpose(0, 3, 1, 2).astype(np.float64)); ref += lay.grads["W"]
+    got, _ = b.test_conv(ctx, 2, 3, b.BF16, g, x, dy, oc * 16 * c)
+    assert np.abs(got.reshape(oc, 4, 4, c) - ref.transpose(0, 2, 3, 1)).max() / np.abs(ref).max() < 1e-4
