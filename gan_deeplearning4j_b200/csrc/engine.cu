@@ -889,7 +889,7 @@ struct b2g_gan {
   float *y_d = nullptr, *y_g = nullptr;   // [2N] = y_real | y_fake ; [N]
   float* loss_dev = nullptr;              // [4]: d_real_sum, d_fake_sum, g_sum
   float* stage = nullptr; size_t stage_floats = 0;
-  cudaGraph_t graph = nullptr, graph1 = nullptr; cudaGraphExec_t exec = nullptr, exec1 = nullptr; int graph_batch = 0; uint64_t graph_launches = 0;
+  cudaGraph_t graph = nullptr, graph1 = nullptr; cudaGraphExec_t exec = nullptr, exec1 = nullptr; int graph_batch = 0; uint64_t graph_launches = 0, graph_simt_g = 0, graph_simt_d = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr; float last_ms = 0.f; int last_batch = 1; bool nccl_warm = false;
   cudaStream_t copy_stream = nullptr; cudaEvent_t ev_x = nullptr; bool ev1_valid = false;   // x_real's H2D runs under the generator's forward
   std::vector<void*> allocs;
@@ -1004,7 +1004,7 @@ extern "C" int32_t b2g_gan_step_resident(b2g_gan* g, int32_t batch) {
     if (!g->exec || g->graph_batch != batch) {
       if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; } if (g->graph) { cudaGraphDestroy(g->graph); g->graph = nullptr; }
       if (g->exec1) { cudaGraphExecDestroy(g->exec1); g->exec1 = nullptr; } if (g->graph1) { cudaGraphDestroy(g->graph1); g->graph1 = nullptr; }
-      uint64_t before = g_launch_count;
+      uint64_t before = g_launch_count; const uint64_t sg0 = g->G->simt_gemm_calls, sd0 = g->D->simt_gemm_calls;
       CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
       int32_t r = gan_step_part1(g, batch);
       cudaError_t e = cudaStreamEndCapture(s, &g->graph1);
@@ -1013,12 +1013,13 @@ extern "C" int32_t b2g_gan_step_resident(b2g_gan* g, int32_t batch) {
       r = gan_step_part2(g, batch);
       e = cudaStreamEndCapture(s, &g->graph);
       g->graph_launches = g_launch_count - before; g_launch_count = before;
+      g->graph_simt_g = g->G->simt_gemm_calls - sg0; g->graph_simt_d = g->D->simt_gemm_calls - sd0; g->G->simt_gemm_calls = sg0; g->D->simt_gemm_calls = sd0;
       if (r) return r; if (e != cudaSuccess) return fail(B2G_ERR_CUDA, "graph capture: %s", cudaGetErrorString(e));
       CU(cudaGraphInstantiate(&g->exec1, g->graph1, 0)); CU(cudaGraphInstantiate(&g->exec, g->graph, 0)); g->graph_batch = batch;
     }
     CU(cudaGraphLaunch(g->exec1, s));
     CU(cudaStreamWaitEvent(s, g->ev_x, 0));
-    CU(cudaGraphLaunch(g->exec, s)); g_launch_count += g->graph_launches;
+    CU(cudaGraphLaunch(g->exec, s)); g_launch_count += g->graph_launches; g->G->simt_gemm_calls += g->graph_simt_g; g->D->simt_gemm_calls += g->graph_simt_d;
   }
   CU(cudaEventRecord(g->ev1, s)); g->ev1_valid = true;
   return 0;
@@ -1159,4 +1160,30 @@ extern "C" int32_t b2g_test_conv_ex(b2g_ctx* c, int32_t kind, int32_t impl, int3
 }
 extern "C" int32_t b2g_test_conv(b2g_ctx* c, int32_t kind, int32_t impl, int32_t precision, const b2g_conv_geom* gg, const float* a_host, const float* b_host, float* out, int32_t iters, float* ms_per_iter) {
   return b2g_test_conv_ex(c, kind, impl, precision, gg, a_host, b_host, out, iters, ms_per_iter, nullptr);
+}
+
+// Times the HBM-bound kernels of the step in isolation (bench.py's `hbm` roofline entries): every launch is bracketed by its own CUDA events
+// on the library stream and preceded by an L2 flush (a 256 MiB memset), so the operands really come from HBM as they do inside a step.
+// ms[0] = one updater pass over `net` (Adam: 28 B/param + 2 B bf16 operand copy; the net's parameters are perturbed -- bench only),
+// ms[1] = BatchNorm apply (read + write a [groups*rows x C] bf16 tensor), ms[2] = BatchNorm backward apply (two reads + one write).
+extern "C" int32_t b2g_test_hbm_kernels(b2g_net* n, int32_t rows, int32_t channels, int32_t iters, float* ms3) {
+  if (!n || !ms3 || rows < 8 || iters < 1) return fail(B2G_ERR_ARG, "bad arguments"); b2g_ctx* c = n->ctx; CU(cudaSetDevice(c->device)); cudaStream_t s = c->stream;
+  if (!k_bn_vec_ok(PREC_BF16, channels)) return fail(B2G_ERR_UNSUPPORTED, "channels %d not supported by the vector BatchNorm kernels", channels);
+  const size_t ne = (size_t)rows * channels; __nv_bfloat16 *x = nullptr, *e = nullptr, *y = nullptr; float *coef = nullptr, *gb = nullptr; unsigned long long* acc = nullptr;
+  CU(cudaMalloc(&x, 2 * ne)); CU(cudaMalloc(&e, 2 * ne)); CU(cudaMalloc(&y, 2 * ne)); CU(cudaMalloc(&coef, 4 * 4 * channels)); CU(cudaMalloc(&gb, 4 * 4 * channels)); CU(cudaMalloc(&acc, 8 * k_bn_acc_elems(channels, 1)));
+  CU(cudaMemsetAsync(x, 0x3c, 2 * ne, s)); CU(cudaMemsetAsync(e, 0x3c, 2 * ne, s)); CU(cudaMemsetAsync(acc, 0, 8 * k_bn_acc_elems(channels, 1), s)); k_fill_f32(coef, 1.0f, 4 * channels, s); k_fill_f32(gb, 1.0f, 4 * channels, s);
+  cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  ms3[0] = ms3[1] = ms3[2] = 0.f;
+  for (int which = 0; which < 3; ++which) for (int it = -1; it < iters; ++it) {
+    B2(b2g_flush_l2(c));
+    CU(cudaEventRecord(e0, s));
+    if (which == 0) k_updater(n->params, n->grads, n->st0, n->st1, n->segs_dev, n->chunk_seg_dev, n->chunk_off_dev, n->nchunks, 1.0f, 1.0f, n->step_dev, n->upd_ticket, n->shadow, s);
+    else if (which == 1) k_bn_apply_acc(x, y, rows, channels, 1, acc, gb, gb + channels, ACT_LRELU, 0.2f, 1e-5f, coef, gb + 2 * channels, gb + 3 * channels, nullptr, nullptr, 0.9f, s);
+    else k_bn_bwd_apply_acc(x, e, y, rows, channels, 1, coef, ACT_LRELU, 0.2f, 1, acc, gb, gb + channels, 0, s);
+    CU(cudaEventRecord(e1, s)); CU(cudaEventSynchronize(e1));
+    float ms = 0.f; CU(cudaEventElapsedTime(&ms, e0, e1)); if (it >= 0) ms3[which] += ms / iters;
+  }
+  CHECK_KERNELS();
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(x); cudaFree(e); cudaFree(y); cudaFree(coef); cudaFree(gb); cudaFree(acc);
+  return 0;
 }

@@ -232,6 +232,12 @@ class Net:
         check(self.lib.b2g_net_simt_gemm_calls(self.h, C.byref(v)))
         return v.value
 
+    def time_hbm_kernels(self, rows: int, channels: int, iters: int = 10):
+        """(updater, BatchNorm apply, BatchNorm backward apply) ms per launch, each after an L2 flush.  Perturbs the parameters: bench only."""
+        ms = np.zeros(3, np.float32)
+        check(self.lib.b2g_test_hbm_kernels(self.h, rows, channels, iters, _fp(ms)))
+        return [float(v) for v in ms]
+
     def input_gradient(self, batch: int) -> np.ndarray:
         out = np.empty((batch, int(np.prod(self.input_shape))), np.float32)
         check(self.lib.b2g_net_get_input_gradient(self.h, batch, _fp(out)))

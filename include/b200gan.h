@@ -232,6 +232,10 @@ typedef struct {
 int32_t b2g_test_conv_ex(b2g_ctx* ctx, int32_t kind, int32_t impl, int32_t precision, const b2g_conv_geom* g,
                          const float* x_or_dy, const float* w_or_x, float* out, int32_t iters, float* ms_per_iter, b2g_test_conv_opts* opts);
 
+/* Times the HBM-bound kernels in isolation, each launch after an L2 flush (bench.py's `hbm` roofline entries): ms[0] one updater pass over
+ * `net` (perturbs its parameters: bench only), ms[1] BatchNorm apply and ms[2] BatchNorm backward apply on a [rows x channels] bf16 tensor. */
+int32_t b2g_test_hbm_kernels(b2g_net* net, int32_t rows, int32_t channels, int32_t iters, float* ms3);
+
 #ifdef __cplusplus
 }
 #endif

@@ -130,10 +130,12 @@ static int net_init(cr_net* n, const cr_layer* ls, int nl, int in_c, int in_h, i
     switch (d->type) {
       case L_CONV: l->oh = (h - d->k + 2 * d->p) / d->s + 1; l->ow = (w - d->k + 2 * d->p) / d->s + 1;
         if (d->has_bias) { l->off_b = off; off += d->cout; } l->off_w = off; off += (int64_t)d->cout * d->cin * d->k * d->k;
-        if ((size_t)l->oh * l->ow * d->cin * d->k * d->k > maxcol) maxcol = (size_t)l->oh * l->ow * d->cin * d->k * d->k; break;
+        if ((size_t)l->oh * l->ow * d->cin * d->k * d->k > maxcol) { maxcol = (size_t)l->oh * l->ow * d->cin * d->k * d->k; }
+        break;
       case L_DECONV: l->oh = d->s * (h - 1) + d->k - 2 * d->p; l->ow = d->s * (w - 1) + d->k - 2 * d->p;
         if (d->has_bias) { l->off_b = off; off += d->cout; } l->off_w = off; off += (int64_t)d->cin * d->cout * d->k * d->k;
-        if ((size_t)h * w * d->cout * d->k * d->k > maxcol) maxcol = (size_t)h * w * d->cout * d->k * d->k; break;
+        if ((size_t)h * w * d->cout * d->k * d->k > maxcol) { maxcol = (size_t)h * w * d->cout * d->k * d->k; }
+        break;
       case L_DENSE: l->oh = l->ow = 1; d->cin = c * h * w; l->off_w = off; off += (int64_t)d->cin * d->cout; if (d->has_bias) { l->off_b = off; off += d->cout; } break;
       case L_BN: d->cout = c; l->oh = h; l->ow = w; l->off_gamma = off; off += 4 * (int64_t)c; break;
       case L_ACT: d->cout = c; l->oh = h; l->ow = w; break;
@@ -159,7 +161,8 @@ static void rows_to_nchw_bias_act(const float* rows, int N, int C, int HW, const
 #pragma omp parallel for collapse(2) schedule(static)
   for (int n = 0; n < N; ++n) for (int c = 0; c < C; ++c) for (int p = 0; p < HW; ++p) {
     const float v = rows[((size_t)n * HW + p) * C + c] + (bias ? bias[c] : 0.f); const size_t o = ((size_t)n * C + c) * HW + p;
-    if (z) z[o] = v; out[o] = actf(act, v, al); }
+    if (z) { z[o] = v; }
+    out[o] = actf(act, v, al); }
 }
 static void nchw_to_rows(const float* x, int N, int C, int HW, float* rows) {
 #pragma omp parallel for collapse(2) schedule(static)
@@ -216,12 +219,11 @@ static const float* net_backward(cr_net* n, const float* x, const float* eps, in
     float* nx = bufs[bi]; if (nx == cur) { bi ^= 1; nx = bufs[bi]; }
     switch (d->type) {
       case L_CONV: case L_DECONV: case L_DENSE: {
-        const size_t oe = (size_t)N * d->cout * l->oh * l->ow; float* delta = bufs[bi ^ 1] == cur ? (float*)cur : nx;
+        const size_t oe = (size_t)N * d->cout * l->oh * l->ow;
         /* delta = eps * act'(z) (separate pass), then as rows [N*P][Cout] */
         float* dl = (float*)malloc(4 * oe);
 #pragma omp parallel for schedule(static)
         for (size_t e = 0; e < oe; ++e) dl[e] = cur[e] * (l->z ? actg(d->act, l->z[e], d->alpha) : 1.f);
-        (void)delta;
         if (d->type == L_CONV) { const int kk = d->cin * d->k * d->k, P = l->oh * l->ow; float* d2d = (float*)malloc(4 * oe);
           nchw_to_rows(dl, N, d->cout, P, d2d);
           if (want_wgrad) { im2col(lin, N, d->cin, l->ih, l->iw, d->k, d->s, d->p, l->oh, l->ow, n->col);
@@ -305,6 +307,7 @@ int64_t cpuref_num_params(void* h, int net) { cr_gan* q = (cr_gan*)h; return net
 void cpuref_set_params(void* h, int net, const float* p) { cr_gan* q = (cr_gan*)h; cr_net* n = net ? &q->D : &q->G; memcpy(n->params, p, 4 * n->np); }
 void cpuref_get_params(void* h, int net, float* p) { cr_gan* q = (cr_gan*)h; cr_net* n = net ? &q->D : &q->G; memcpy(p, n->params, 4 * n->np); }
 int cpuref_threads(void) { return omp_get_max_threads(); }
+void cpuref_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 /* oracle gan_step: x_fake = G(z_d) with inference-mode BN; D on real and fake as two minibatches (own BN statistics), gradients summed /2N,
  * one Adam step; G step through train-mode D with labels y_gen, D untouched; one Adam step.  losses = {d_real, d_fake, g} means. */
 void cpuref_step(void* h, const float* x_real, const float* z_d, const float* z_g, const float* y_real, const float* y_fake, const float* y_gen, int N, float* losses) {

@@ -71,7 +71,7 @@ def test_edge_im2col_row_layout():
 
 
 def test_bench_reference_arm_prints_the_contract_line():
-    env = dict(os.environ, B2G_CPU_ENGINE="numpy")
+    env = dict(os.environ)          # default engine: oracle/cpu_ref.c (the C + OpenMP restatement of the DL4J CPU algorithm)
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "c5", "--steps", "2", "--warmup", "1"],
                          capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stderr[-500:]

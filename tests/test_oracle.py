@@ -14,6 +14,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
+from helpers import randomize
 from oracle import dl4j_oracle as o
 
 
@@ -432,6 +433,35 @@ def test_torch_cpu_step_matches_numpy_oracle():
         t.G.export(); t.D.export()
         assert np.abs(G.params_flat() - G2.params_flat()).max() < 1e-9
         assert np.abs(D.params_flat() - D2.params_flat()).max() < 1e-9
+
+
+def test_c_reference_matches_numpy_oracle():
+    """oracle/cpu_ref.c -- the C + OpenMP restatement of DL4J's nd4j-native algorithm (im2col + SGEMM + separate passes, NCHW fp32) that
+    bench.py times as the CPU arm (SURVEY.md 8d(i), P:104-108) -- computes the same adversarial step as dl4j_oracle.gan_step: three
+    iterations of the DCGAN (transposed convs, BatchNorm, LeakyReLU / ReLU / tanh, Adam) and of the MLP-GAN, fp32 against the fp64 oracle.
+    It also pins the golden step fixture (tests/golden/gan_step_dcgan16.npz losses) through the oracle it is compared with."""
+    from oracle import cpu_ref
+    from gan_deeplearning4j_b200 import models as m
+    q = o.Quirks(xent_clip_eps=0.0)
+    rng = np.random.default_rng(5)
+    dc = o.synthetic_batch(8, 16, 3, 12, seed=3)
+    n = 16
+    mlp = (rng.standard_normal((n, 24)), rng.uniform(-1, 1, (n, 10)), rng.uniform(-1, 1, (n, 10)), 1 + 0.05 * rng.standard_normal((n, 1)), 0.05 * rng.standard_normal((n, 1)), np.ones((n, 1)))
+    cases = [(o.dcgan_generator(16, 12, 8, 3, quirks=q), o.dcgan_discriminator(16, 8, 3, quirks=q), m.dcgan_generator(16, 12, 8, 3), m.dcgan_discriminator(16, 8, 3), 12, (3, 16, 16), dc),
+             (o.mlp_generator(10, 32, 24, quirks=q), o.mlp_discriminator(24, 32, quirks=q), m.mlp_generator(10, 32, 24), m.mlp_discriminator(24, 32), 10, (24,), mlp)]
+    for G, D, gs, ds, z, shape, data in cases:
+        randomize(G, rng); randomize(D, rng)
+        data = [np.asarray(a, np.float64) for a in data]
+        c = cpu_ref.CpuRefGan(gs, ds, z, shape, data[0].shape[0])
+        assert c.num_params(0) == G.num_params() and c.num_params(1) == D.num_params()
+        c.set_params(0, G.params_flat()); c.set_params(1, D.params_flat())
+        for _ in range(3):
+            r, rc = o.gan_step(G, D, *data), c.step(*data)
+            for k in ("loss_d_real", "loss_d_fake", "loss_g"):
+                assert abs(r[k] - rc[k]) < 2e-6 * max(1.0, abs(r[k])), (k, r[k], rc[k])
+            for net, ref in ((0, G), (1, D)):
+                assert np.abs(c.get_params(net) - ref.params_flat()).max() < 5e-6 * np.abs(ref.params_flat()).max()
+        c.close()
 
 
 def test_golden_vectors_pin_the_oracle():

@@ -19,7 +19,7 @@ for v in variants:
     env = dict(os.environ)
     for kv in v.split():
         k, _, val = kv.partition("="); env[k] = val
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", steps, "--config", config, "--no-cpu"], capture_output=True, text=True, env=env)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", steps, "--config", config, "--no-cpu", "--no-extra"], capture_output=True, text=True, env=env)
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     if out.returncode or not lines:
         rows.append((v or "(default)", float("nan"), float("nan"), out.stderr.strip().splitlines()[-1][:80] if out.stderr.strip() else "failed")); continue
