@@ -44,7 +44,7 @@ class ConvGeom(C.Structure):
 class TestConvOpts(C.Structure):
     """b2g_test_conv_opts: the epilogue a kernel-level parity test asks for, and the name of the kernel that ran."""
     _fields_ = [("epi", C.c_int32), ("act", C.c_int32), ("alpha", C.c_float), ("bias", C.POINTER(C.c_float)), ("scale", C.POINTER(C.c_float)),
-                ("groups", C.c_int32), ("aux", C.POINTER(C.c_float)), ("coef", C.POINTER(C.c_float)), ("stats", C.POINTER(C.c_double)), ("kernel", C.c_char * 64)]
+                ("groups", C.c_int32), ("aux", C.POINTER(C.c_float)), ("aux2", C.POINTER(C.c_float)), ("stats", C.POINTER(C.c_double)), ("kernel", C.c_char * 64)]
 
 
 _vp, _i32, _i64, _fp = C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_float)

@@ -566,7 +566,7 @@ static int32_t net_backward(b2g_net* n, const void* net_in, void* eps, int rows,
     if (k < 0) { if (input_act && fuse_act) { *e = *input_act; *target = -2; return true; } return false; }
     LayerRT& b = n->L[k];
     if (fuse_bn && b.d.type == B2G_LAYER_BATCHNORM && b.fwd_fused && !b.d.frozen && b.fwd_groups == groups) {
-      e->mode = EPI_BNBWD; e->acc = b.acc_bwd; e->imgs_per_group = R / groups; e->aux = (const __nv_bfloat16*)(k == 0 ? net_in : n->L[k - 1].out); e->coef = b.bn_coef;
+      e->mode = EPI_BNBWD; e->acc = b.acc_bwd; e->imgs_per_group = R / groups; e->aux = (const __nv_bfloat16*)b.out; e->aux2 = (const __nv_bfloat16*)(k == 0 ? net_in : n->L[k - 1].out);
       e->act = b.fused_act; e->alpha = b.fused_alpha; *target = k; return true;
     }
     if (fuse_act && k == i - 1 && b.has_gemm() && b.d.act != B2G_ACT_IDENTITY && b.d.type != B2G_LAYER_OUTPUT) {
@@ -908,8 +908,7 @@ static int32_t gan_step_part1(b2g_gan* g, int N) {
 static int32_t gan_step_part2(b2g_gan* g, int N) {
   b2g_net *G = g->G, *D = g->D; cudaStream_t s = G->ctx->stream;
   // 1. (part 1) x_fake = gen.output(z_d) (J:420) was written straight into the second half of D's input batch.
-  // x_real arrived on the copy stream meanwhile; only the discriminator needs it
-  k_nchw_f32_to_nhwc(D->prec, g->stage, D->input, N, D->cfg.in_c, D->cfg.in_h * D->cfg.in_w, s);
+  // x_real arrived (and was converted to the device layout) on the copy stream meanwhile; only the discriminator needs it
   // 3a (hoisted). The generator's train-mode forward on z_g depends only on G's parameters, which the D step does not touch:
   // run it on a second stream underneath the whole D step.
   cudaStream_t s3 = G->ctx->side2;
@@ -974,10 +973,11 @@ extern "C" int32_t b2g_gan_upload(b2g_gan* g, const float* x_real, const float* 
   if (batch < 1 || batch > g->N) return fail(B2G_ERR_SHAPE, "batch %d outside [1,%d]", batch, g->N);
   b2g_net *G = g->G, *D = g->D; cudaStream_t s = G->ctx->stream; CU(cudaSetDevice(G->ctx->device));
   size_t nx = (size_t)batch * D->in_elems, nz = (size_t)batch * G->in_elems;
-  // x_real (the only large input) goes over a separate copy stream and is converted inside the step, after the generator's forward;
+  // x_real (the only large input) goes over a separate copy stream, where it is also converted to the device layout;
   // the staging buffer is free once the previous step's conversion has run (ev1 marks the end of that step)
   if (g->ev1_valid) CU(cudaStreamWaitEvent(g->copy_stream, g->ev1, 0));
   CU(cudaMemcpyAsync(g->stage, x_real, sizeof(float) * nx, cudaMemcpyHostToDevice, g->copy_stream));
+  k_nchw_f32_to_nhwc(D->prec, g->stage, D->input, batch, D->cfg.in_c, D->cfg.in_h * D->cfg.in_w, g->copy_stream);     // NCHW fp32 -> NHWC in the net's type, off the step's critical path
   CU(cudaEventRecord(g->ev_x, g->copy_stream));
   CU(cudaMemcpyAsync(G->stage_f32, z_d, sizeof(float) * nz, cudaMemcpyHostToDevice, s));
   k_nchw_f32_to_nhwc(G->prec, G->stage_f32, g->z_d, batch, G->cfg.in_c, G->cfg.in_h * G->cfg.in_w, s);
@@ -1103,7 +1103,7 @@ extern "C" int32_t b2g_test_conv_ex(b2g_ctx* c, int32_t kind, int32_t impl, int3
     if (!ok) return fail(B2G_ERR_UNSUPPORTED, "no skinny-layer kernel (impl %d) for this shape", impl);
   }
   float *fa = nullptr, *fb = nullptr, *fo = nullptr, *scratch = nullptr; void *ta = nullptr, *tb = nullptr, *to = nullptr; __nv_bfloat16* wps = nullptr;
-  float *d_bias = nullptr, *d_scale = nullptr, *d_coef = nullptr, *d_auxf = nullptr; __nv_bfloat16* d_aux = nullptr; unsigned long long* d_acc = nullptr;
+  float *d_bias = nullptr, *d_scale = nullptr, *d_coef = nullptr, *d_auxf = nullptr; __nv_bfloat16 *d_aux = nullptr, *d_aux2 = nullptr; unsigned long long* d_acc = nullptr;
   size_t sc = std::max(std::max(k_simt_wgrad_scratch_floats(g), k_tc_wgrad_scratch_floats(g)), std::max(k_edge_wgrad_scratch_floats(g), k_tc_edge_wgrad_scratch_floats(g))) + 16;
   CU(cudaMalloc(&fa, 4 * na)); CU(cudaMalloc(&fb, 4 * nb)); CU(cudaMalloc(&fo, 4 * no)); CU(cudaMalloc(&scratch, 4 * sc));
   CU(cudaMalloc(&ta, ts * na)); CU(cudaMalloc(&tb, ts * nb)); CU(cudaMalloc(&to, ts * no));
@@ -1122,7 +1122,10 @@ extern "C" int32_t b2g_test_conv_ex(b2g_ctx* c, int32_t kind, int32_t impl, int3
       if (!opt->aux) return fail(B2G_ERR_ARG, "epilogue %d needs aux", opt->epi);
       CU(cudaMalloc(&d_auxf, 4 * no)); CU(cudaMalloc(&d_aux, 2 * no)); CU(cudaMemcpyAsync(d_auxf, opt->aux, 4 * no, cudaMemcpyHostToDevice, s)); k_cast_f32_to_bf16(d_auxf, d_aux, no, s); epi.aux = d_aux;
     }
-    if (opt->epi == EPI_BNBWD) { if (!opt->coef) return fail(B2G_ERR_ARG, "epilogue 2 needs coef"); CU(cudaMalloc(&d_coef, 4 * 4 * groups * oc)); CU(cudaMemcpyAsync(d_coef, opt->coef, 4 * 4 * groups * oc, cudaMemcpyHostToDevice, s)); epi.coef = d_coef; }
+    if (opt->epi == EPI_BNBWD) {      // aux = the BatchNorm(+activation) output y, aux2 = its input z
+      if (!opt->aux2) return fail(B2G_ERR_ARG, "epilogue 2 needs aux2 (the BatchNorm input z)");
+      CU(cudaMalloc(&d_coef, 4 * no)); CU(cudaMalloc(&d_aux2, 2 * no)); CU(cudaMemcpyAsync(d_coef, opt->aux2, 4 * no, cudaMemcpyHostToDevice, s)); k_cast_f32_to_bf16(d_coef, d_aux2, no, s); epi.aux2 = d_aux2;
+    }
     if (opt->epi || opt->scale) pe = &epi;
   }
   cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
@@ -1155,7 +1158,7 @@ extern "C" int32_t b2g_test_conv_ex(b2g_ctx* c, int32_t kind, int32_t impl, int3
   float ms = 0.f; CU(cudaEventElapsedTime(&ms, e0, e1)); if (ms_per_iter) *ms_per_iter = ms / reps;
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   cudaFree(fa); cudaFree(fb); cudaFree(fo); cudaFree(scratch); cudaFree(ta); cudaFree(tb); cudaFree(to); if (wps) cudaFree(wps);
-  if (d_bias) cudaFree(d_bias); if (d_scale) cudaFree(d_scale); if (d_coef) cudaFree(d_coef); if (d_auxf) cudaFree(d_auxf); if (d_aux) cudaFree(d_aux); if (d_acc) cudaFree(d_acc);
+  if (d_bias) cudaFree(d_bias); if (d_scale) cudaFree(d_scale); if (d_coef) cudaFree(d_coef); if (d_auxf) cudaFree(d_auxf); if (d_aux) cudaFree(d_aux); if (d_aux2) cudaFree(d_aux2); if (d_acc) cudaFree(d_acc);
   return 0;
 }
 extern "C" int32_t b2g_test_conv(b2g_ctx* c, int32_t kind, int32_t impl, int32_t precision, const b2g_conv_geom* gg, const float* a_host, const float* b_host, float* out, int32_t iters, float* ms_per_iter) {

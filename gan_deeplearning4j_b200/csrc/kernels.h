@@ -62,7 +62,9 @@ void k_bn_apply_acc(const void* x, void* y, int rows_per_group, int C, int group
                     int act, float alpha, float eps, float* coef, const float* run_mean, const float* run_var, float* g_mean, float* g_var, float decay, cudaStream_t s);
 // sum dy', sum dy'*xhat -> acc with dy' = eps_out * act'(x*scale+shift)   (producers without the EPI_BNBWD epilogue)
 void k_bn_bwd_stats_acc(const void* x, const void* eps_out, int rows_per_group, int C, int groups, const float* coef, int act, float alpha, unsigned long long* acc, cudaStream_t s);
-// eps_in = scale * (dy' - mean(dy') - xhat*mean(dy'*xhat)); premul != 0: eps_out already holds dy'.  Block 0 adds dgamma / dbeta (summed over groups).
+// eps_in = scale * (dy' - mean(dy') - xhat*mean(dy'*xhat)).  premul = 0: eps_out is the raw epsilon and acc = (sum dy', sum dy'*xhat) from
+// k_bn_bwd_stats_acc; premul = 1: eps_out already holds dy' and acc = (sum dy', sum dy'*z) from the EPI_BNBWD epilogue, converted here in
+// double: sum dy'*xhat = invstd * (sum dy'*z - mean * sum dy').  Block 0 adds dgamma / dbeta (summed over groups).
 void k_bn_bwd_apply_acc(const void* x, const void* eps_out, void* eps_in, int rows_per_group, int C, int groups, const float* coef, int act, float alpha, int premul,
                         const unsigned long long* acc, float* g_gamma, float* g_beta, int want_param_grads, cudaStream_t s);
 
@@ -155,11 +157,11 @@ enum { EPI_PLAIN = 0, EPI_STATS = 1, EPI_BNBWD = 2, EPI_ACTBWD = 3 };
 struct TcEpi {
   int mode;                    // EPI_*
   const float* scale;          // EPI_PLAIN / EPI_STATS: out = act(acc*scale[c] + bias[c]) (inference-mode BatchNorm folded in), may be null
-  unsigned long long* acc;     // EPI_STATS: sum / sum-of-squares of the outputs; EPI_BNBWD: sum dy', sum dy'*xhat   [groups][2][2][OC]
+  unsigned long long* acc;     // EPI_STATS: sum / sum-of-squares of the outputs; EPI_BNBWD: sum dy', sum dy'*z   [groups][2][2][OC]
   int imgs_per_group;          // statistics group = image index / imgs_per_group
-  const __nv_bfloat16* aux;    // EPI_BNBWD: the BatchNorm layer's input z; EPI_ACTBWD: the forward output a of the layer whose act' is applied
-  const float* coef;           // EPI_BNBWD: [groups][4][OC] from k_bn_apply_acc
-  int act; float alpha;        // EPI_BNBWD / EPI_ACTBWD: the activation whose derivative multiplies the result
+  const __nv_bfloat16* aux;    // EPI_BNBWD / EPI_ACTBWD: the forward OUTPUT of the (BatchNorm +) activation whose derivative multiplies the result
+  const __nv_bfloat16* aux2;   // EPI_BNBWD: the BatchNorm layer's input z
+  int act; float alpha;        // EPI_BNBWD / EPI_ACTBWD: that activation
 };
 // w: the bf16 weight copy [O][taps][C].  w_mn = 1 (1x1 geometry): w is [C][O], the dense layer's own weight as its input-gradient operand.
 int k_tc_fprop(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out, int act, float alpha, cudaStream_t s, const TcEpi* epi = nullptr, int w_mn = 0);

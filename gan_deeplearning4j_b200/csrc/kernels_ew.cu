@@ -495,7 +495,8 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_acc_kernel(const uint4* _
     double tb = 0.0, tg = 0.0;
     for (int g = 0; g < groups; ++g) {
       const unsigned long long* a = accp + (size_t)g * 4 * C;
-      const double s1 = sacc_read(a, (size_t)C, (size_t)c), s2 = sacc_read(a + 2 * (size_t)C, (size_t)C, (size_t)c);
+      const double s1 = sacc_read(a, (size_t)C, (size_t)c); double s2 = sacc_read(a + 2 * (size_t)C, (size_t)C, (size_t)c);
+      if (PREMUL) s2 = (double)coef[(size_t)(g * 4 + 3) * C + c] * (s2 - (double)coef[(size_t)(g * 4 + 2) * C + c] * s1);      // (sum dy'*z) -> sum dy'*xhat
       s_k[(g * 2 + 0) * C + c] = (float)(s1 / rows); s_k[(g * 2 + 1) * C + c] = (float)(s2 / rows); tb += s1; tg += s2;
     }
     if (writer) { g_beta[c] += (float)tb; g_gamma[c] += (float)tg; }

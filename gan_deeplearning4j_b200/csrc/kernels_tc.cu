@@ -100,6 +100,12 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint64_t desc_kmajor_sw128(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// the same with an explicit stride between 8-row groups.  Measured on B200 (tools/exp_desc.cu, profiles/r02_exp_desc_shifted_descriptors.txt): the
+// 128B swizzle is a function of the ABSOLUTE shared-memory address, so a descriptor may start at any 128-byte row of a TMA-written tile and
+// use any group stride (base_offset field 0): one "halo" tile kept in shared memory feeds every filter tap through shifted descriptors.
+__device__ __forceinline__ uint64_t desc_kmajor_sw128_sbo(uint32_t saddr, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
 // MN-major 128B-swizzled tile (operand stored [K rows][64 MN elements]): 8-K-row groups 1024 B apart (SBO),
 // 64-element MN blocks `lbo_bytes` apart (LBO).
 __device__ __forceinline__ uint64_t desc_mnmajor_sw128(uint32_t saddr, uint32_t lbo_bytes) {
@@ -117,9 +123,10 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_
 //   EPI_PLAIN   out = act(acc * scale[c] + bias[c])                 (scale / bias optional: inference-mode BatchNorm folded in)
 //   EPI_STATS   EPI_PLAIN + per-(group, channel) sum / sum of squares of the bf16-rounded outputs: the train-mode BatchNorm
 //               statistics of the layer that follows come out of the producing GEMM (SURVEY section 7 step 5, J:132-134,197-199)
-//   EPI_BNBWD   the GEMM produces the epsilon w.r.t. the OUTPUT of a BatchNorm(+activation) layer; the epilogue reads that
-//               layer's input z at the same pixel, out = eps * act'(gamma*xhat+beta) and accumulates sum(out), sum(out * xhat):
-//               the two reductions of BatchNorm backward fall out of the dgrad epilogue
+//   EPI_BNBWD   the GEMM produces the epsilon w.r.t. the OUTPUT y of a BatchNorm(+activation) layer; the epilogue reads y and that
+//               layer's input z at the same pixel, out = eps * act'(y) (derivative from the stored output: no per-channel
+//               coefficients in the epilogue) and accumulates sum(out), sum(out * z): the two reductions of BatchNorm backward fall
+//               out of the dgrad epilogue (the consumer turns sum(out*z) into sum(out*xhat) = invstd*(sum(out*z) - mean*sum(out)) in double)
 //   EPI_ACTBWD  out = eps * act'(a) with a = the forward output of the layer below (D1's LeakyReLU, G-last's tanh)
 // Statistics: 32 rows x 32 columns per warp are column-reduced by a shuffle butterfly (31 shuffles per statistic), the four
 // epilogue warps are folded through shared memory in fixed order, and one value per (tile, channel) is added into a 128-bit
@@ -143,8 +150,8 @@ struct TcConvParams {
   int epi;
   unsigned long long* acc;  // EPI_STATS / EPI_BNBWD: [groups][2][2][OC] (statistic, hi | lo, channel)
   int imgs_per_group;
-  const __nv_bfloat16* aux; // EPI_BNBWD: the BatchNorm input z; EPI_ACTBWD: the forward output a   (same NHWC shape as `out`)
-  const float* coef;        // EPI_BNBWD: [groups][4][OC] = scale (gamma*invstd), shift (beta - mean*scale), mean, invstd
+  const __nv_bfloat16* aux; // EPI_BNBWD / EPI_ACTBWD: the forward output whose act' multiplies the result   (same NHWC shape as `out`)
+  const __nv_bfloat16* aux2;// EPI_BNBWD: the BatchNorm input z
 };
 
 template <int BN, int STAGES, int EPI = EPI_PLAIN>
@@ -183,30 +190,29 @@ __device__ __forceinline__ void epi_tile(const TcConvParams& p, uint32_t taddr, 
 #pragma unroll 1
   for (int c0 = 0; c0 < BN; c0 += 32) {
     uint32_t v[32];
-    uint4 ax[4];
+    uint4 ax[4], az[4];
     if constexpr (EPI >= EPI_BNBWD) {
       const uint4* ap = reinterpret_cast<const uint4*>(p.aux + roff + c0);
 #pragma unroll
       for (int i = 0; i < 4; ++i) ax[i] = ap[i];
     }
+    if constexpr (EPI == EPI_BNBWD) {
+      const uint4* zp = reinterpret_cast<const uint4*>(p.aux2 + roff + c0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) az[i] = zp[i];
+    }
     tmem_ld32(taddr + (uint32_t)c0, v);
     tmem_ld_wait();
     float o[32], s2[32];
     if constexpr (EPI == EPI_BNBWD) {
-      const float4* cs = reinterpret_cast<const float4*>(p.coef + (size_t)group * 4 * p.OC + nb0 + c0);
-      const int q4 = p.OC >> 2;     // float4 stride between the four coefficient arrays
-      const __nv_bfloat162* zb = reinterpret_cast<const __nv_bfloat162*>(ax);
+      const __nv_bfloat162* yb = reinterpret_cast<const __nv_bfloat162*>(ax);
+      const __nv_bfloat162* zb = reinterpret_cast<const __nv_bfloat162*>(az);
 #define B2G_BNBWD_LOOP(ACTC)                                                                                                   \
-  _Pragma("unroll") for (int j4 = 0; j4 < 8; ++j4) {                                                                           \
-    const float4 sc = cs[j4], sh = cs[q4 + j4], mu = cs[2 * q4 + j4], is = cs[3 * q4 + j4];                                    \
-    const float2 za = __bfloat1622float2(zb[2 * j4]), zc = __bfloat1622float2(zb[2 * j4 + 1]);                                 \
-    const float z4[4] = {za.x, za.y, zc.x, zc.y}, sc4[4] = {sc.x, sc.y, sc.z, sc.w}, sh4[4] = {sh.x, sh.y, sh.z, sh.w};        \
-    const float mu4[4] = {mu.x, mu.y, mu.z, mu.w}, is4[4] = {is.x, is.y, is.z, is.w};                                          \
-    _Pragma("unroll") for (int e = 0; e < 4; ++e) {                                                                            \
-      const int j = 4 * j4 + e;                                                                                                \
-      s2[j] = (z4[e] - mu4[e]) * is4[e];                                                                                       \
-      o[j] = __uint_as_float(v[j]) * act_grad_from_pre(ACTC, fmaf(z4[e], sc4[e], sh4[e]), p.alpha);                            \
-    }                                                                                                                          \
+  _Pragma("unroll") for (int j = 0; j < 16; ++j) {                                                                             \
+    const float2 y2 = __bfloat1622float2(yb[j]), z2 = __bfloat1622float2(zb[j]);                                               \
+    o[2 * j] = __uint_as_float(v[2 * j]) * act_grad_from_out(ACTC, y2.x, p.alpha);                                             \
+    o[2 * j + 1] = __uint_as_float(v[2 * j + 1]) * act_grad_from_out(ACTC, y2.y, p.alpha);                                     \
+    s2[2 * j] = z2.x; s2[2 * j + 1] = z2.y;                                                                                    \
   }
       if (p.act == ACT_LRELU) { B2G_BNBWD_LOOP(ACT_LRELU) }
       else if (p.act == ACT_RELU) { B2G_BNBWD_LOOP(ACT_RELU) }
@@ -649,7 +655,7 @@ static void fill_epi(TcConvParams& p, const float* bias, int act, float alpha, c
   p.bias = bias; p.act = act; p.alpha = alpha; p.epi = EPI_PLAIN;
   if (!e) return;
   p.scale = e->scale; p.epi = e->mode; p.acc = e->acc; p.imgs_per_group = e->mode == EPI_STATS || e->mode == EPI_BNBWD ? e->imgs_per_group : 0;
-  p.aux = e->aux; p.coef = e->coef;
+  p.aux = e->aux; p.aux2 = e->aux2;
   if (e->mode == EPI_BNBWD || e->mode == EPI_ACTBWD) { p.act = e->act; p.alpha = e->alpha; p.bias = nullptr; p.scale = nullptr; }
 }
 
@@ -711,6 +717,8 @@ __global__ void pack_deconv_ps_kernel(const float* __restrict__ w, __nv_bfloat16
 void k_pack_deconv_ps(const float* w, __nv_bfloat16* wps, int O, int C, cudaStream_t s) {
   pack_deconv_ps_kernel<<<(16 * 9 * O + 255) / 256, 256, 0, s>>>(w, wps, O, C); LAUNCHED();
 }
+static int ps_halo_on();
+static int launch_ps_halo(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat16* wps, const TcConvParams& q, cudaStream_t s);
 int k_tc_deconv_ps(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat16* wps, const float* bias, __nv_bfloat16* dx, int act, float alpha, cudaStream_t s, const TcEpi* epi) {
   TcConvParams p{}; p.mode = 0;
   if (!tc_deconv_ps_shape(g) || !pick_row_tile(g.N, g.OH, g.OW, 128, &p.Nt, &p.Ht, &p.Wt)) return -1;
@@ -718,6 +726,7 @@ int k_tc_deconv_ps(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat
   p.GH = g.OH; p.GW = g.OW; p.tiles_y = g.OH / p.Ht; p.taps_h = 3; p.taps_w = 3; p.chunks = g.O / 64; p.KW = 3;
   p.SH = 1; p.SW = 1; p.PH = 1; p.PW = 1; p.OC = g.C; p.outH = g.H; p.outW = g.W; p.out = dx;
   fill_epi(p, bias, act, alpha, epi);
+  if (ps_halo_on() && g.O == 64 && g.OH % 16 == 0 && g.OW % 8 == 0) return launch_ps_halo(g, dy, wps, p, s);
   CUtensorMap tmA, tmB;
   cuuint64_t dims[4] = {(cuuint64_t)g.O, (cuuint64_t)g.OW, (cuuint64_t)g.OH, (cuuint64_t)g.N};
   cuuint64_t strides[3] = {(cuuint64_t)g.O * 2, (cuuint64_t)g.OW * g.O * 2, (cuuint64_t)g.OH * g.OW * g.O * 2};
@@ -729,6 +738,141 @@ int k_tc_deconv_ps(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat
   if (p.epi == EPI_ACTBWD) { TC_SET_SMEM_ONCE((tc_conv_kernel<16, 4, EPI_ACTBWD, false, true>), S::TOTAL); tc_conv_kernel<16, 4, EPI_ACTBWD, false, true><<<grid, 192, S::TOTAL, s>>>(tmA, tmB, p); }
   else { TC_SET_SMEM_ONCE((tc_conv_kernel<16, 4, EPI_PLAIN, false, true>), S::TOTAL); tc_conv_kernel<16, 4, EPI_PLAIN, false, true><<<grid, 192, S::TOTAL, s>>>(tmA, tmB, p); }
   LAUNCHED(); g_tc_last_kernel = "tc_conv_kernel<16,4,PS>";
+  return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
+}
+
+// ------------------------------------------------------------------ the same with a shared-memory halo ------
+// The 3x3 form above re-fetches the 128-pixel activation tile from L2 once per tap (9 x 16.8 MB at the C2 batch: the kernel ran at the
+// L2->SM limit, 26 us).  Here the tile is 16 rows x 8 columns of the dy grid, its 18 x 10 halo (zero-filled outside the image by TMA) is
+// loaded ONCE, and the nine taps are nine descriptors into it: tap (dyr, dxc) starts (1+dyr)*10 + (1+dxc) rows of 128 B into the halo, an
+// 8-row group (one image row of the tile) every 10 rows (SBO = 1280 B).  All nine packed weight tiles (18 KB) stay resident; a persistent
+// CTA walks tiles with a 3-deep halo ring and two TMEM accumulators.  dy is read once: 16.8 MB instead of 151 MB.
+struct TcPsHaloParams {
+  int tiles_x, tiles_y, total_tiles;      // tiles of 16 x 8 dy pixels
+  int C, outH, outW;                      // output image: C <= 4 channels, 2*GH x 2*GW
+  const float* bias; int act; float alpha; __nv_bfloat16* out; const __nv_bfloat16* aux;
+};
+static constexpr int PSH_STAGES = 3, PSH_HALO_BYTES = 18 * 10 * 128, PSH_STAGE_BYTES = 23 * 1024, PSH_W_BYTES = 9 * 16 * 128;
+static constexpr int PSH_BAR_OFF = PSH_STAGES * PSH_STAGE_BYTES + PSH_W_BYTES, PSH_SMEM = PSH_BAR_OFF + 256 + 1024;
+
+template <int EPI>
+__global__ void __launch_bounds__(192) tc_deconv_ps_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcPsHaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t wsm = smem_base + PSH_STAGES * PSH_STAGE_BYTES;
+  const uint32_t bar_full = smem_base + PSH_BAR_OFF, bar_empty = bar_full + 8 * PSH_STAGES, bar_w = bar_empty + 8 * PSH_STAGES, bar_tfull = bar_w + 8, bar_tempty = bar_tfull + 16;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + PSH_BAR_OFF + 8 * (2 * PSH_STAGES + 1 + 4));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    prefetch_map(&tmA); prefetch_map(&tmW);
+    for (int s = 0; s < PSH_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_w, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(smem_u32((const void*)tmem_slot), 64); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int per_img = p.tiles_x * p.tiles_y;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_w, PSH_W_BYTES);
+      for (int t = 0; t < 9; ++t) tma_load_3d(wsm + t * 2048, &tmW, bar_w, 0, t, 0);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int s = it % PSH_STAGES; const uint32_t ph = (it / PSH_STAGES) & 1;
+        const int n = tile / per_img, r = tile % per_img, y0 = (r / p.tiles_x) * 16, x0 = (r % p.tiles_x) * 8;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        mbar_expect_tx(bar_full + 8 * s, PSH_HALO_BYTES);
+        tma_load_4d(smem_base + s * PSH_STAGE_BYTES, &tmA, bar_full + 8 * s, 0, x0 - 1, y0 - 1, n);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, 16, 0, 0);
+      mbar_wait(bar_w, 0);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int s = it % PSH_STAGES; const uint32_t ph = (it / PSH_STAGES) & 1, acc = it & 1, aph = (it >> 1) & 1;
+        mbar_wait(bar_tempty + 8 * acc, aph ^ 1);
+        mbar_wait(bar_full + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t halo = smem_base + s * PSH_STAGE_BYTES;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint64_t adesc = desc_kmajor_sw128_sbo(halo + (uint32_t)(((tap / 3) * 10 + (tap % 3)) * 128), 1280), bdesc = desc_kmajor_sw128(wsm + tap * 2048);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + acc * 32, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)(tap | k));
+        }
+        umma_commit(bar_empty + 8 * s);
+        umma_commit(bar_tfull + 8 * acc);
+      }
+    }
+  } else {
+    const int q = warp & 3, row = q * 32 + lane, yy = row >> 3, xx = row & 7;
+    const int C = p.C;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+      const int n = tile / per_img, r = tile % per_img, gy = (r / p.tiles_x) * 16 + yy, gx = (r % p.tiles_x) * 8 + xx;
+      mbar_wait(bar_tfull + 8 * acc, aph);
+      tc_fence_after();
+      uint32_t v[32];                       // 32 columns per accumulator; [0,16) carry the tile: (py, px, c4)
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 32, v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);      // the values are in registers: the MMA issuer may overwrite the accumulator
+#pragma unroll
+      for (int ppy = 0; ppy < 2; ++ppy) {
+        const size_t doff = (((size_t)n * p.outH + 2 * gy + ppy) * p.outW + 2 * gx) * C;
+        __nv_bfloat16* dst = p.out + doff;
+        float o[8];
+#pragma unroll
+        for (int ppx = 0; ppx < 2; ++ppx)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float a = __uint_as_float(v[(ppy * 2 + ppx) * 4 + c]);
+            if constexpr (EPI == EPI_ACTBWD) { if (c < C) a *= act_grad_from_out(p.act, __bfloat162float(p.aux[doff + ppx * C + c]), p.alpha); }
+            else { if (p.bias && c < C) a += p.bias[c]; a = act_fwd(p.act, a, p.alpha); }
+            o[ppx * 4 + c] = a;
+          }
+        if (C == 3) {         // 6 contiguous bf16 = three aligned 32-bit stores
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[4]), h2 = __floats2bfloat162_rn(o[5], o[6]);
+          uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+          d32[0] = *reinterpret_cast<uint32_t*>(&h0); d32[1] = *reinterpret_cast<uint32_t*>(&h1); d32[2] = *reinterpret_cast<uint32_t*>(&h2);
+        } else {
+#pragma unroll
+          for (int ppx = 0; ppx < 2; ++ppx)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) if (c < C) dst[ppx * C + c] = __float2bfloat16(o[ppx * 4 + c]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 64); }
+}
+
+static int ps_halo_on() { static int on = -1; if (on < 0) { const char* e = getenv("B2G_PS_HALO"); on = (e && e[0] == '0') ? 0 : 1; } return on; }
+static int launch_ps_halo(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat16* wps, const TcConvParams& q, cudaStream_t s) {
+  TcPsHaloParams p{}; p.tiles_x = g.OW / 8; p.tiles_y = g.OH / 16; p.total_tiles = g.N * p.tiles_x * p.tiles_y; p.C = g.C; p.outH = g.H; p.outW = g.W;
+  p.bias = q.bias; p.act = q.act; p.alpha = q.alpha; p.out = q.out; p.aux = q.aux;
+  CUtensorMap tmA, tmW;
+  cuuint64_t dims[4] = {(cuuint64_t)g.O, (cuuint64_t)g.OW, (cuuint64_t)g.OH, (cuuint64_t)g.N};
+  cuuint64_t strides[3] = {(cuuint64_t)g.O * 2, (cuuint64_t)g.OW * g.O * 2, (cuuint64_t)g.OH * g.OW * g.O * 2};
+  cuuint32_t box[4] = {64, 10, 18, 1}; cuuint32_t es[4] = {1, 1, 1, 1};
+  if (make_map_bf16(&tmA, dy, 4, dims, strides, box, es)) return -1;
+  if (weight_map(&tmW, wps, 16, 9, g.O, 16)) return -1;
+  static int sms = 0; if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, tc_device());
+  const int grid = p.total_tiles < 2 * sms ? p.total_tiles : 2 * sms;
+  if (q.epi == EPI_ACTBWD) { TC_SET_SMEM_ONCE(tc_deconv_ps_halo_kernel<EPI_ACTBWD>, PSH_SMEM); tc_deconv_ps_halo_kernel<EPI_ACTBWD><<<grid, 192, PSH_SMEM, s>>>(tmA, tmW, p); }
+  else { TC_SET_SMEM_ONCE(tc_deconv_ps_halo_kernel<EPI_PLAIN>, PSH_SMEM); tc_deconv_ps_halo_kernel<EPI_PLAIN><<<grid, 192, PSH_SMEM, s>>>(tmA, tmW, p); }
+  LAUNCHED(); g_tc_last_kernel = "tc_deconv_ps_halo_kernel";
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
 }
 

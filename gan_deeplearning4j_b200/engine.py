@@ -308,7 +308,7 @@ EPI_PLAIN, EPI_STATS, EPI_BNBWD, EPI_ACTBWD = 0, 1, 2, 3
 
 
 def test_conv_ex(ctx: Context, kind: int, geom: Dict[str, int], a, b, out_size: int, *, epi: int = 0, act: str = "identity", alpha: float = 0.0,
-                 bias=None, scale=None, groups: int = 1, aux=None, coef=None, iters: int = 1):
+                 bias=None, scale=None, groups: int = 1, aux=None, aux2=None, iters: int = 1):
     """tcgen05 fprop (kind 0) / dgrad (kind 1) with the epilogue the training step uses.  Returns (out, stats or None, kernel name, ms)."""
     g = _lib.ConvGeom(**geom)
     a, b = _f32(a).ravel(), _f32(b).ravel()
@@ -317,7 +317,7 @@ def test_conv_ex(ctx: Context, kind: int, geom: Dict[str, int], a, b, out_size: 
     o = _lib.TestConvOpts()
     o.epi, o.act, o.alpha, o.groups = epi, ACTS[act], alpha, groups
     keep = []
-    for name, v in (("bias", bias), ("scale", scale), ("aux", aux), ("coef", coef)):
+    for name, v in (("bias", bias), ("scale", scale), ("aux", aux), ("aux2", aux2)):
         if v is not None:
             arr = _f32(v).ravel(); keep.append(arr); setattr(o, name, _fp(arr))
     stats = None

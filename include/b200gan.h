@@ -218,14 +218,15 @@ int32_t b2g_test_conv(b2g_ctx* ctx, int32_t kind, int32_t impl, int32_t precisio
  * test can assert that it exercised the variant the benchmark runs (persistent MT=2, one-wave split-K, ...). */
 typedef struct {
   int32_t epi;            /* 0 plain; 1 + statistics (sum, sum of squares per group and channel) of the stored outputs;
-                             2 BatchNorm-backward epilogue: out = acc * act'(aux*scale+shift), statistics sum out, sum out*xhat;
+                             2 BatchNorm-backward epilogue: out = acc * act'(aux) (aux = the BatchNorm+activation output y), statistics sum out, sum out*aux2
+                               (aux2 = the BatchNorm input z);
                              3 activation-backward epilogue: out = acc * act'(aux) with aux the forward output */
   int32_t act; float alpha;
   const float* bias;      /* [C_out] or NULL */
   const float* scale;     /* [C_out] or NULL: out = act(acc*scale + bias) */
   int32_t groups;         /* statistics groups (the batch split evenly, like real | fake in the D step) */
-  const float* aux;       /* epi 2: the BatchNorm input z; epi 3: the forward output a (NHWC, shape of the result) */
-  const float* coef;      /* epi 2: [groups][4][C_out] = scale, shift, mean, invstd */
+  const float* aux;       /* epi 2 / 3: the forward output whose activation derivative multiplies the result (NHWC, shape of the result) */
+  const float* aux2;      /* epi 2: the BatchNorm input z (same shape) */
   double* stats;          /* out (epi 1 / 2): [groups][2][C_out] */
   char kernel[64];        /* out */
 } b2g_test_conv_opts;

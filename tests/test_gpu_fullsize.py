@@ -55,10 +55,6 @@ def act_fwd(name, z, alpha):
     return {"identity": lambda: z, "relu": lambda: np.maximum(z, 0), "lrelu": lambda: np.where(z > 0, z, alpha * z), "tanh": lambda: np.tanh(z)}[name]()
 
 
-def act_grad_pre(name, u, alpha):
-    return {"identity": lambda: np.ones_like(u), "relu": lambda: (u > 0).astype(np.float64), "lrelu": lambda: np.where(u > 0, 1.0, alpha)}[name]()
-
-
 # (name, batch, conv-input size h, c, o, expected kernel)   -- conv geometry 4x4 s2 p1: x [n,h,h,c] -> y [n,h/2,h/2,o]
 FPROP = [
     ("D2 fprop, D step (2N, real|fake)", 2 * N, 32, 64, 128, "tc_conv_persistent_kernel<128,4,2>"),
@@ -97,21 +93,15 @@ def test_fprop_production_dispatch(b200, case, epi):
         out, _, k, _ = b.test_conv_ex(ctx, 0, g, x, wt, n * oh * oh * oc, act="lrelu", alpha=0.2, bias=bias)
         check_bf16(out.reshape(n, oh, oh, oc)[idx], act_fwd("lrelu", ref + bias.astype(np.float64), 0.2), name)
     else:
-        # the GEMM result is the epsilon w.r.t. the output of BatchNorm+ReLU; z = that BatchNorm's input, coef = its forward coefficients
+        # the GEMM result is the epsilon w.r.t. the output y of BatchNorm+ReLU; z = that BatchNorm's input: out = eps * relu'(y), statistics sum out, sum out*z
         z = bf16_round(rng.standard_normal((n, oh, oh, oc)))
-        mean = rng.standard_normal((groups, oc)) * 0.2; invstd = rng.uniform(0.5, 2.0, (groups, oc)); gamma = rng.uniform(0.5, 1.5, oc); beta = rng.standard_normal(oc) * 0.3
-        sc = gamma * invstd; sh = beta - mean * sc
-        coef = np.stack([sc, sh, mean, invstd], 1).astype(np.float32)            # [groups][4][oc]
-        out, stats, k, _ = b.test_conv_ex(ctx, 0, g, x, wt, n * oh * oh * oc, epi=b.EPI_BNBWD, act="relu", groups=groups, aux=z, coef=coef)
+        y = bf16_round(np.maximum(z * rng.uniform(0.5, 1.5, oc) + rng.standard_normal(oc) * 0.3, 0))
+        out, stats, k, _ = b.test_conv_ex(ctx, 0, g, x, wt, n * oh * oh * oc, epi=b.EPI_BNBWD, act="relu", groups=groups, aux=y, aux2=z)
         out = out.reshape(n, oh, oh, oc)
-        cf = coef.astype(np.float64)
-        gi = np.array([i // (n // groups) for i in idx])
-        u = z[idx].astype(np.float64) * cf[gi, 0][:, None, None, :] + cf[gi, 1][:, None, None, :]
-        check_bf16(out[idx], ref * act_grad_pre("relu", u, 0.0), name)
+        check_bf16(out[idx], ref * (y[idx] > 0), name)
         zg = z.reshape(groups, -1, oc).astype(np.float64); og = out.reshape(groups, -1, oc).astype(np.float64)
-        xh = (zg - cf[:, 2][:, None, :]) * cf[:, 3][:, None, :]
         np.testing.assert_allclose(stats[:, 0, :], og.sum(1), rtol=2e-5, atol=2e-3)
-        np.testing.assert_allclose(stats[:, 1, :], (og * xh).sum(1), rtol=2e-5, atol=5e-3)
+        np.testing.assert_allclose(stats[:, 1, :], (og * zg).sum(1), rtol=2e-5, atol=5e-3)
     assert k == kernel, f"{name}: dispatched {k}, the C2 step is expected to run {kernel}"
 
 
@@ -159,18 +149,14 @@ def test_dgrad_production_dispatch(b200, case, epi):
         check_bf16(out.reshape(n, h, h, c)[idx], ref * np.where(a[idx] > 0, 1.0, 0.2), name)
     else:
         z = bf16_round(rng.standard_normal((n, h, h, c)))
-        mean = rng.standard_normal((groups, c)) * 0.2; invstd = rng.uniform(0.5, 2.0, (groups, c)); gamma = rng.uniform(0.5, 1.5, c); beta = rng.standard_normal(c) * 0.3
-        sc = gamma * invstd; sh = beta - mean * sc
-        coef = np.stack([sc, sh, mean, invstd], 1).astype(np.float32)
-        out, stats, k, _ = b.test_conv_ex(ctx, 1, g, dy, wt, size, epi=b.EPI_BNBWD, act="lrelu", alpha=0.2, groups=groups, aux=z, coef=coef)
-        out = out.reshape(n, h, h, c); cf = coef.astype(np.float64)
-        gi = np.array([i // (n // groups) for i in idx])
-        u = z[idx].astype(np.float64) * cf[gi, 0][:, None, None, :] + cf[gi, 1][:, None, None, :]
-        check_bf16(out[idx], ref * act_grad_pre("lrelu", u, 0.2), name)
+        u = z * rng.uniform(0.5, 1.5, c) + rng.standard_normal(c) * 0.3
+        y = bf16_round(np.where(u > 0, u, 0.2 * u))
+        out, stats, k, _ = b.test_conv_ex(ctx, 1, g, dy, wt, size, epi=b.EPI_BNBWD, act="lrelu", alpha=0.2, groups=groups, aux=y, aux2=z)
+        out = out.reshape(n, h, h, c)
+        check_bf16(out[idx], ref * np.where(y[idx] > 0, 1.0, 0.2), name)
         zg = z.reshape(groups, -1, c).astype(np.float64); og = out.reshape(groups, -1, c).astype(np.float64)
-        xh = (zg - cf[:, 2][:, None, :]) * cf[:, 3][:, None, :]
         np.testing.assert_allclose(stats[:, 0, :], og.sum(1), rtol=2e-5, atol=2e-3)
-        np.testing.assert_allclose(stats[:, 1, :], (og * xh).sum(1), rtol=2e-5, atol=5e-3)
+        np.testing.assert_allclose(stats[:, 1, :], (og * zg).sum(1), rtol=2e-5, atol=5e-3)
     assert k == kernel, f"{name}: dispatched {k}, the C2 step is expected to run {kernel}"
 
 
