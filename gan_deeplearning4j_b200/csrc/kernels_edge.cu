@@ -39,7 +39,7 @@ template <typename T> __device__ __forceinline__ void load8_any(const T* p, floa
 // One thread per dy-grid position (n,qy,qx): reads its 3x3 neighbourhood once, writes the 2x2 output block.
 template <typename T, typename TW>
 __global__ void __launch_bounds__(128) edge_deconv_small_c_kernel(const T* __restrict__ dy, const TW* __restrict__ w, const float* __restrict__ bias, T* __restrict__ dx,
-                                                                   int N, int OH, int OW, int O, int C, int act, float alpha) {
+                                                                   int N, int OH, int OW, int O, int C, int act, float alpha) { pdl_enter();
   extern __shared__ float4 ws4[];      // [16 taps][O] : (c0,c1,c2,c3)
   for (int i = threadIdx.x; i < 16 * O; i += blockDim.x) {
     int tap = i / O, o = i % O; float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -110,7 +110,7 @@ __device__ __forceinline__ void store16(__nv_bfloat16* dst, const float (&a)[16]
 // 12-element row segments, weights from smem as [k][O] so a warp's reads are broadcasts / conflict-free.
 template <typename T, typename TW>
 __global__ void __launch_bounds__(128) edge_conv_small_cin_kernel(const T* __restrict__ x, const TW* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out,
-                                                                   int N, int H, int W, int C, int OH, int OW, int O, int act, float alpha) {
+                                                                   int N, int H, int W, int C, int OH, int OW, int O, int act, float alpha) { pdl_enter();
   extern __shared__ float wsf[];      // [16*C][O]
   const int K = 16 * C;
   for (int i = threadIdx.x; i < K * O; i += blockDim.x) { int o = i / K, k = i % K; wsf[k * O + o] = ldw(w, (size_t)i); }   // coalesced global read
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(128) edge_conv_small_cin_kernel(const T* __res
 // one dy pair and the 4*C contiguous x values of its filter row from smem and does 2*4*C FMAs.  Each CTA reduces a contiguous pixel range;
 // partials [grid][O*16*C] are summed by k_reduce_splits.
 template <typename T>
-__global__ void edge_wgrad_small_cin_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ part, int N, int H, int W, int C, int OH, int OW, int O, int pix_per_cta) {
+__global__ void edge_wgrad_small_cin_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ part, int N, int H, int W, int C, int OH, int OW, int O, int pix_per_cta) { pdl_enter();
   extern __shared__ float sm[];
   const int TP = 64;                           // pixels per smem tile
   float* sdy = sm;                             // [TP][O]
@@ -224,7 +224,7 @@ __global__ void edge_wgrad_small_cin_kernel(const T* __restrict__ x, const T* __
 
 // ------------------------------------------------------------------ (d) layers with <=4 output units -------------
 template <typename T, typename TW>
-__global__ void __launch_bounds__(128) dense_small_o_fwd_kernel(const T* __restrict__ x, const TW* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out, int K, int O, int act, float alpha) {
+__global__ void __launch_bounds__(128) dense_small_o_fwd_kernel(const T* __restrict__ x, const TW* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out, int K, int O, int act, float alpha) { pdl_enter();
   const int n = blockIdx.x; __shared__ float red[4][4];
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   const T* xr = x + (size_t)n * K;
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(128) dense_small_o_fwd_kernel(const T* __restr
   if (threadIdx.x < O) { float a = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x]; stf(out, (size_t)n * O + threadIdx.x, act_fwd(act, a + (bias ? bias[threadIdx.x] : 0.f), alpha)); }
 }
 template <typename T, typename TW>
-__global__ void dense_small_o_dgrad_kernel(const T* __restrict__ dy, const TW* __restrict__ w, T* __restrict__ dx, int N, int K, int O) {
+__global__ void dense_small_o_dgrad_kernel(const T* __restrict__ dy, const TW* __restrict__ w, T* __restrict__ dx, int N, int K, int O) { pdl_enter();
   const size_t total = (size_t)N * K;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int k = i % K; const size_t n = i / K; float a = 0.f;
@@ -248,7 +248,7 @@ __global__ void dense_small_o_dgrad_kernel(const T* __restrict__ dy, const TW* _
   }
 }
 template <typename T>
-__global__ void dense_small_o_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ part, int N, int K, int O, int rows_per_split) {
+__global__ void dense_small_o_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ part, int N, int K, int O, int rows_per_split) { pdl_enter();
   const int k = blockIdx.x * blockDim.x + threadIdx.x; if (k >= K) return;
   const int n0 = blockIdx.y * rows_per_split, n1 = min(N, n0 + rows_per_split);
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -269,7 +269,7 @@ __device__ __forceinline__ void st2(__nv_bfloat16* p, float a, float b) { *reint
 // The thread's weights for 16 o are fetched together, one chunk ahead of the FMAs (register double buffer): one global latency per 16 o.
 template <typename T, typename TW>
 __global__ void __launch_bounds__(128) dense_small_k_dgrad_kernel(const T* __restrict__ dy, const TW* __restrict__ w, const float* __restrict__ bias, T* __restrict__ dx,
-                                                                   int N, int C, int O, int act, float alpha) {
+                                                                   int N, int C, int O, int act, float alpha) { pdl_enter();
   constexpr int OC = 16;                                  // o per chunk
   __shared__ __align__(16) float sz[8][128];             // [n][o], zero padded to a multiple of OC
   const int cb = blockIdx.x * 256, c = cb + threadIdx.x * 2, n0 = blockIdx.y * 8, OP = (O + OC - 1) / OC * OC;
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(128) dense_small_k_dgrad_kernel(const T* __res
 // dw[o][c] = sum_n dy[n][o] * x[n][c]: thread = 2 adjacent c x 16 o, the whole batch reduced in the CTA (no split, deterministic);
 // rows are consumed 8 at a time so that eight global loads are in flight per thread
 template <typename T>
-__global__ void __launch_bounds__(128) dense_small_k_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw, int N, int C, int O) {
+__global__ void __launch_bounds__(128) dense_small_k_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw, int N, int C, int O) { pdl_enter();
   __shared__ __align__(16) float sd[128][16];            // [n][o local]
   const int c = (blockIdx.x * 128 + threadIdx.x) * 2, o0 = blockIdx.y * 16;
   float acc[16][2];

@@ -16,10 +16,11 @@
 namespace b2g {
 
 uint64_t g_launch_count = 0;
+int g_pdl_enabled = -1;
 
 // ---------------------------------------------------------------- layout -----------------------------
 template <typename T>
-__global__ void nchw_f32_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int N, int C, int HW) {
+__global__ void nchw_f32_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int N, int C, int HW) { pdl_enter();
   // one thread per destination element (coalesced writes; reads strided by HW, served by L2)
   size_t total = (size_t)N * C * HW;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -28,7 +29,7 @@ __global__ void nchw_f32_to_nhwc_kernel(const float* __restrict__ src, T* __rest
   }
 }
 template <typename T>
-__global__ void nhwc_to_nchw_f32_kernel(const T* __restrict__ src, float* __restrict__ dst, int N, int C, int HW) {
+__global__ void nhwc_to_nchw_f32_kernel(const T* __restrict__ src, float* __restrict__ dst, int N, int C, int HW) { pdl_enter();
   size_t total = (size_t)N * C * HW;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int p = i % HW; size_t t = i / HW; int c = t % C; size_t n = t / C;
@@ -36,7 +37,7 @@ __global__ void nhwc_to_nchw_f32_kernel(const T* __restrict__ src, float* __rest
   }
 }
 template <typename T>
-__global__ void permute_kernel(const T* __restrict__ src, T* __restrict__ dst, int N, int C, int HW, int to_nhwc) {
+__global__ void permute_kernel(const T* __restrict__ src, T* __restrict__ dst, int N, int C, int HW, int to_nhwc) { pdl_enter();
   size_t total = (size_t)N * C * HW;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     if (to_nhwc) { int c = i % C; size_t t = i / C; int p = t % HW; size_t n = t / HW; dst[i] = src[(n * C + c) * HW + p]; }
@@ -66,7 +67,7 @@ void k_permute(int prec, const void* src, void* dst, int N, int C, int HW, int t
   size_t n = (size_t)N * C * HW; if (!n) return;
   DISPATCH_PREC(prec, T, (launch_pdl(permute_kernel<T>, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, (const T*)src, (T*)dst, N, C, HW, to_nhwc))); LAUNCHED();
 }
-__global__ void cast_f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+__global__ void cast_f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) { pdl_enter();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = __float2bfloat16_rn(src[i]);
 }
 void k_cast_f32_to_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t s) {
@@ -96,7 +97,7 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
 }
 
 template <typename T>
-__global__ void bn_stats_partial_kernel(const T* __restrict__ x, int rows, int C, int S, float* __restrict__ psum, float* __restrict__ psq) {
+__global__ void bn_stats_partial_kernel(const T* __restrict__ x, int rows, int C, int S, float* __restrict__ psum, float* __restrict__ psq) { pdl_enter();
   int g = blockIdx.y;
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= S * C) return;
@@ -125,7 +126,7 @@ __device__ __forceinline__ void block_fold_write(float (&acc)[NV][8], int C, int
     for (int v = 0; v < NV; ++v) { float a = 0.f; for (int k = 0; k < TY; ++k) a += sred[v][k * C + c]; dst[v][row_off + c] = a; }
   }
 }
-__global__ void __launch_bounds__(256) bn_stats_partial_bf16x8_kernel(const uint4* __restrict__ x, int rows, int C, int S, float* __restrict__ psum, float* __restrict__ psq) {
+__global__ void __launch_bounds__(256) bn_stats_partial_bf16x8_kernel(const uint4* __restrict__ x, int rows, int C, int S, float* __restrict__ psum, float* __restrict__ psq) { pdl_enter();
   const int g = blockIdx.y, C8 = C / 8, TY = 256 / C8, c8 = threadIdx.x % C8, ty = threadIdx.x / C8, sl = blockIdx.x;
   const int chunk = (rows + S - 1) / S, r0 = sl * chunk, r1 = min(rows, r0 + chunk);
   const uint4* xg = x + (size_t)g * rows * C8;
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(256) bn_stats_partial_bf16x8_kernel(const uint
 // stage 2: block = 32 adjacent channels x 16 slice lanes (coalesced 128-byte rows of the partial arrays), fixed-order tree in double
 __global__ void __launch_bounds__(1024) bn_stats_final_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int rows, int C, int S, int groups, float eps,
                                       float* __restrict__ mean, float* __restrict__ invstd,
-                                      const float* __restrict__ run_mean, const float* __restrict__ run_var, float* g_mean, float* g_var, float decay) {
+                                      const float* __restrict__ run_mean, const float* __restrict__ run_var, float* g_mean, float* g_var, float decay) { pdl_enter();
   __shared__ double sa[32][33], sb[32][33];      // 32 channels x 32 slice lanes: S <= 256 partial rows in ONE batch of 8 loads per thread
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, c = blockIdx.x * 32 + tx;
   double acc_gm = 0.0, acc_gv = 0.0;
@@ -182,11 +183,11 @@ void k_bn_stats(int prec, const void* x, int rows, int C, int groups, float* scr
   LAUNCHED();
   launch_pdl(bn_stats_final_kernel, dim3((C + 31) / 32), dim3(1024), (size_t)(0), s, psum, psq, rows, C, S, groups, eps, mean, invstd, run_mean, run_var, g_mean, g_var, decay); LAUNCHED();
 }
-__global__ void bn_prep_infer_kernel(const float* __restrict__ rm, const float* __restrict__ rv, int C, int groups, float eps, float* mean, float* invstd) {
+__global__ void bn_prep_infer_kernel(const float* __restrict__ rm, const float* __restrict__ rv, int C, int groups, float eps, float* mean, float* invstd) { pdl_enter();
   int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= C * groups) return;
   int c = i % C; mean[i] = rm[c]; invstd[i] = 1.0f / sqrtf(rv[c] + eps);
 }
-__global__ void bn_fold_kernel(const float* __restrict__ rm, const float* __restrict__ rv, const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ cb, int C, float eps, float* scale, float* shift) {
+__global__ void bn_fold_kernel(const float* __restrict__ rm, const float* __restrict__ rv, const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ cb, int C, float eps, float* scale, float* shift) { pdl_enter();
   int c = blockIdx.x * blockDim.x + threadIdx.x; if (c >= C) return;
   const float sc = gamma[c] / sqrtf(rv[c] + eps); scale[c] = sc; shift[c] = beta[c] - rm[c] * sc + (cb ? cb[c] * sc : 0.f);
 }
@@ -199,7 +200,7 @@ void k_bn_prep_infer(const float* run_mean, const float* run_var, int C, int gro
 
 template <typename T>
 __global__ void bn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, int rows, int C, int groups, const float* __restrict__ mean,
-                                const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int act, float alpha) {
+                                const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int act, float alpha) { pdl_enter();
   size_t per_group = (size_t)rows * C, total = per_group * groups;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int c = i % C; int g = i / per_group;
@@ -211,7 +212,7 @@ __global__ void bn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, int 
 // meets the same 8 channels: their coefficients are loaded once per group instead of 4-6 scalar loads per element.
 template <int ACTC>
 __global__ void __launch_bounds__(256, 3) bn_apply_bf16x8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int rows, int C, int groups, const float* __restrict__ mean,
-                                       const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int act, float alpha) {
+                                       const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int act, float alpha) { pdl_enter();
   const int C8 = C / 8; const size_t per_group = (size_t)rows * C8;
   const size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
   const int c0 = (int)(t0 % C8) * 8;
@@ -249,7 +250,7 @@ void k_bn_apply(int prec, const void* x, void* y, int rows, int C, int groups, c
 template <typename T>
 __global__ void bn_bwd_partial_kernel(const T* __restrict__ x, const T* __restrict__ eo, int rows, int C, int S, const float* __restrict__ mean,
                                       const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int act, float alpha,
-                                      float* __restrict__ p1, float* __restrict__ p2) {
+                                      float* __restrict__ p1, float* __restrict__ p2) { pdl_enter();
   int g = blockIdx.y;
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= S * C) return;
@@ -267,7 +268,7 @@ __global__ void bn_bwd_partial_kernel(const T* __restrict__ x, const T* __restri
 template <int ACTC>
 __global__ void __launch_bounds__(256, 3) bn_bwd_partial_bf16x8_kernel(const uint4* __restrict__ x, const uint4* __restrict__ eo, int rows, int C, int S, const float* __restrict__ mean,
                                              const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int act, float alpha,
-                                             float* __restrict__ p1, float* __restrict__ p2) {
+                                             float* __restrict__ p1, float* __restrict__ p2) { pdl_enter();
   const int g = blockIdx.y, C8 = C / 8, TY = 256 / C8, c8 = threadIdx.x % C8, ty = threadIdx.x / C8, sl = blockIdx.x;
   const int chunk = (rows + S - 1) / S, r0 = sl * chunk, r1 = min(rows, r0 + chunk);
   const uint4* xg = x + (size_t)g * rows * C8; const uint4* eg = eo + (size_t)g * rows * C8;
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_partial_bf16x8_kernel(const uin
 template <int ACTC>
 __global__ void __launch_bounds__(256, 2) bn_bwd_apply_bf16x8_kernel(const uint4* __restrict__ x, const uint4* __restrict__ eo, uint4* __restrict__ ei, int rows, int C, int groups,
                                            const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                           const float* __restrict__ beta, int act, float alpha, const float* __restrict__ c1, const float* __restrict__ c2) {
+                                           const float* __restrict__ beta, int act, float alpha, const float* __restrict__ c1, const float* __restrict__ c2) { pdl_enter();
   // same hoisting as bn_apply_bf16x8_kernel: one thread, one channel octet
   const int C8 = C / 8; const size_t per_group = (size_t)rows * C8;
   const size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_bf16x8_kernel(const uint4
   }
 }
 __global__ void __launch_bounds__(1024) bn_bwd_final_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int rows, int C, int S, int groups,
-                                    float* __restrict__ c1, float* __restrict__ c2, float* g_gamma, float* g_beta, int want) {
+                                    float* __restrict__ c1, float* __restrict__ c2, float* g_gamma, float* g_beta, int want) { pdl_enter();
   __shared__ double sa[32][33], sb[32][33];      // 32 channels x 32 slice lanes: S <= 256 partial rows in ONE batch of 8 loads per thread
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, c = blockIdx.x * 32 + tx;
   double tg = 0.0, tb = 0.0;
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(1024) bn_bwd_final_kernel(const float* __restr
 template <typename T>
 __global__ void bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ eo, T* __restrict__ ei, int rows, int C, int groups,
                                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                    const float* __restrict__ beta, int act, float alpha, const float* __restrict__ c1, const float* __restrict__ c2) {
+                                    const float* __restrict__ beta, int act, float alpha, const float* __restrict__ c1, const float* __restrict__ c2) { pdl_enter();
   size_t per_group = (size_t)rows * C, total = per_group * groups;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int c = i % C; int g = i / per_group; int k = g * C + c;
@@ -390,7 +391,7 @@ __device__ __forceinline__ void block_fold_acc(float (&acc)[NV][8], int C, int c
     for (int v = 0; v < NV; ++v) { float a = 0.f; for (int k = 0; k < TY; ++k) a += sred[v][k * C + c]; sacc_add(accbase + (size_t)v * 2 * C, (size_t)C, (size_t)c, a); }
   }
 }
-__global__ void __launch_bounds__(256) bn_stats_acc_kernel(const uint4* __restrict__ x, int rows, int C, int S, unsigned long long* __restrict__ accp) {
+__global__ void __launch_bounds__(256) bn_stats_acc_kernel(const uint4* __restrict__ x, int rows, int C, int S, unsigned long long* __restrict__ accp) { pdl_enter();
   const int g = blockIdx.y, C8 = C / 8, TY = 256 / C8, c8 = threadIdx.x % C8, ty = threadIdx.x / C8, sl = blockIdx.x;
   const int chunk = (rows + S - 1) / S, r0 = sl * chunk, r1 = min(rows, r0 + chunk);
   const uint4* xg = x + (size_t)g * rows * C8;
@@ -412,7 +413,7 @@ void k_bn_stats_acc(const void* x, int rows, int C, int groups, unsigned long lo
 template <int ACTC>
 __global__ void __launch_bounds__(256, 3) bn_apply_acc_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int rows, int C, int groups, const unsigned long long* __restrict__ accp,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta, int act, float alpha, float eps, float* __restrict__ coef,
-                                                             const float* __restrict__ run_mean, const float* __restrict__ run_var, float* g_mean, float* g_var, float decay) {
+                                                             const float* __restrict__ run_mean, const float* __restrict__ run_var, float* g_mean, float* g_var, float decay) { pdl_enter();
   extern __shared__ float s_cf[];
   const bool writer = blockIdx.x == 0;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -463,7 +464,7 @@ void k_bn_apply_acc(const void* x, void* y, int rows, int C, int groups, const u
 
 template <int ACTC>
 __global__ void __launch_bounds__(256, 3) bn_bwd_stats_acc_kernel(const uint4* __restrict__ x, const uint4* __restrict__ eo, int rows, int C, int S, const float* __restrict__ coef,
-                                                                 int act, float alpha, unsigned long long* __restrict__ accp) {
+                                                                 int act, float alpha, unsigned long long* __restrict__ accp) { pdl_enter();
   const int g = blockIdx.y, C8 = C / 8, TY = 256 / C8, c8 = threadIdx.x % C8, ty = threadIdx.x / C8, sl = blockIdx.x;
   const int chunk = (rows + S - 1) / S, r0 = sl * chunk, r1 = min(rows, r0 + chunk);
   const uint4* xg = x + (size_t)g * rows * C8; const uint4* eg = eo + (size_t)g * rows * C8;
@@ -488,7 +489,7 @@ void k_bn_bwd_stats_acc(const void* x, const void* eps_out, int rows, int C, int
 template <int ACTC, bool PREMUL>
 __global__ void __launch_bounds__(256, 2) bn_bwd_apply_acc_kernel(const uint4* __restrict__ x, const uint4* __restrict__ eo, uint4* __restrict__ ei, int rows, int C, int groups,
                                                                  const float* __restrict__ coef, int act, float alpha, const unsigned long long* __restrict__ accp,
-                                                                 float* g_gamma, float* g_beta, int want) {
+                                                                 float* g_gamma, float* g_beta, int want) { pdl_enter();
   extern __shared__ float s_k[];
   const bool writer = blockIdx.x == 0 && want;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -538,11 +539,11 @@ void k_bn_bwd_apply_acc(const void* x, const void* eps_out, void* eps_in, int ro
 
 // ---------------------------------------------------------------- activations ---------------------------
 template <typename T>
-__global__ void act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, size_t n, int act, float alpha) {
+__global__ void act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, size_t n, int act, float alpha) { pdl_enter();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) stf(y, i, act_fwd(act, ldf(x, i), alpha));
 }
 template <typename T>
-__global__ void act_bwd_out_kernel(const T* __restrict__ a, const T* __restrict__ eo, T* __restrict__ ei, size_t n, int act, float alpha) {
+__global__ void act_bwd_out_kernel(const T* __restrict__ a, const T* __restrict__ eo, T* __restrict__ ei, size_t n, int act, float alpha) { pdl_enter();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     stf(ei, i, ldf(eo, i) * act_grad_from_out(act, ldf(a, i), alpha));
 }
@@ -551,7 +552,7 @@ void k_act_fwd(int prec, const void* x, void* y, size_t n, int act, float alpha,
 }
 // bf16, 16-byte vectors (n % 8 == 0): the D1 / G-last activation derivative runs over the largest tensors of the step
 template <int ACTC>
-__global__ void __launch_bounds__(256, 4) act_bwd_out_bf16x8_kernel(const uint4* __restrict__ a, const uint4* __restrict__ eo, uint4* __restrict__ ei, size_t n8, int act, float alpha) {
+__global__ void __launch_bounds__(256, 4) act_bwd_out_bf16x8_kernel(const uint4* __restrict__ a, const uint4* __restrict__ eo, uint4* __restrict__ ei, size_t n8, int act, float alpha) { pdl_enter();
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += 4 * stride) {
     uint4 aa[4], ea[4];
@@ -577,7 +578,7 @@ void k_sigmoid_out(int prec, const void* z, void* p, size_t n, cudaStream_t s) {
 
 // ---------------------------------------------------------------- max-pool / upsample ---------------------
 template <typename T>
-__global__ void maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint8_t* __restrict__ arg, int N, int H, int W, int C, int OH, int OW, int KH, int KW, int SH, int SW) {
+__global__ void maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint8_t* __restrict__ arg, int N, int H, int W, int C, int OH, int OW, int KH, int KW, int SH, int SW) { pdl_enter();
   size_t total = (size_t)N * OH * OW * C;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int c = i % C; size_t t = i / C; int ox = t % OW; t /= OW; int oy = t % OH; size_t n = t / OH;
@@ -590,7 +591,7 @@ __global__ void maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, u
   }
 }
 template <typename T>
-__global__ void maxpool_bwd_kernel(const T* __restrict__ eo, const uint8_t* __restrict__ arg, T* __restrict__ ei, int N, int H, int W, int C, int OH, int OW, int KH, int KW, int SH, int SW) {
+__global__ void maxpool_bwd_kernel(const T* __restrict__ eo, const uint8_t* __restrict__ arg, T* __restrict__ ei, int N, int H, int W, int C, int OH, int OW, int KH, int KW, int SH, int SW) { pdl_enter();
   // gather form (deterministic): each input pixel sums the eps of the windows whose arg-max it is
   size_t total = (size_t)N * H * W * C;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -613,7 +614,7 @@ void k_maxpool_bwd(int prec, const void* eo, const uint8_t* arg, void* ei, int N
   DISPATCH_PREC(prec, T, (launch_pdl(maxpool_bwd_kernel<T>, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, (const T*)eo, arg, (T*)ei, N, H, W, C, OH, OW, KH, KW, SH, SW))); LAUNCHED();
 }
 template <typename T>
-__global__ void upsample_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int f) {
+__global__ void upsample_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int f) { pdl_enter();
   size_t total = (size_t)N * H * f * W * f * C;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int c = i % C; size_t t = i / C; int ox = t % (W * f); t /= (W * f); int oy = t % (H * f); size_t n = t / (H * f);
@@ -621,7 +622,7 @@ __global__ void upsample_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, 
   }
 }
 template <typename T>
-__global__ void upsample_bwd_kernel(const T* __restrict__ eo, T* __restrict__ ei, int N, int H, int W, int C, int f) {
+__global__ void upsample_bwd_kernel(const T* __restrict__ eo, T* __restrict__ ei, int N, int H, int W, int C, int f) { pdl_enter();
   size_t total = (size_t)N * H * W * C;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int c = i % C; size_t t = i / C; int ix = t % W; t /= W; int iy = t % H; size_t n = t / H;
@@ -642,7 +643,7 @@ void k_upsample_bwd(int prec, const void* eo, void* ei, int N, int H, int W, int
 // ---------------------------------------------------------------- XENT ---------------------------------
 // LossBinaryXENT + sigmoid on the logit (J:159-163): clip_eps>0 DL4J-exact, 0 = BCE-with-logits.
 template <typename T>
-__global__ void xent_kernel(const T* __restrict__ z, const float* __restrict__ y, T* __restrict__ dz, float* __restrict__ loss_sums, int rows, float clip) {
+__global__ void xent_kernel(const T* __restrict__ z, const float* __restrict__ y, T* __restrict__ dz, float* __restrict__ loss_sums, int rows, float clip) { pdl_enter();
   int g = blockIdx.x;
   __shared__ double red[32];
   double acc = 0.0;
@@ -671,7 +672,7 @@ void k_xent(int prec, const void* z, const float* y, void* dz, float* loss_sums,
 
 // LossMCXENT with softmax (J:357-362), K classes per row: one thread per row, block-level loss sum
 template <typename T>
-__global__ void softmax_xent_kernel(const T* __restrict__ z, const float* __restrict__ y, T* __restrict__ dz, T* __restrict__ p_out, float* __restrict__ loss_sum, int rows, int K) {
+__global__ void softmax_xent_kernel(const T* __restrict__ z, const float* __restrict__ y, T* __restrict__ dz, T* __restrict__ p_out, float* __restrict__ loss_sum, int rows, int K) { pdl_enter();
   __shared__ double red[32];
   double acc = 0.0;
   for (int r = threadIdx.x; r < rows; r += blockDim.x) {
@@ -694,13 +695,13 @@ void k_softmax_xent(int prec, const void* z, const float* y, void* dz, void* p_o
 
 // ---------------------------------------------------------------- column sum / misc reductions -----------
 template <typename T>
-__global__ void colsum_partial_kernel(const T* __restrict__ x, int rows, int C, int S, float* __restrict__ p) {
+__global__ void colsum_partial_kernel(const T* __restrict__ x, int rows, int C, int S, float* __restrict__ p) { pdl_enter();
   int idx = blockIdx.x * blockDim.x + threadIdx.x; if (idx >= S * C) return;
   int c = idx % C, sl = idx / C; float a = 0.f;
   for (int r = sl; r < rows; r += S) a += ldf(x, (size_t)r * C + c);
   p[(size_t)sl * C + c] = a;
 }
-__global__ void __launch_bounds__(256) colsum_partial_bf16x8_kernel(const uint4* __restrict__ x, int rows, int C, int S, float* __restrict__ p) {
+__global__ void __launch_bounds__(256) colsum_partial_bf16x8_kernel(const uint4* __restrict__ x, int rows, int C, int S, float* __restrict__ p) { pdl_enter();
   const int C8 = C / 8, TY = 256 / C8, c8 = threadIdx.x % C8, ty = threadIdx.x / C8, sl = blockIdx.x;
   const int chunk = (rows + S - 1) / S, r0 = sl * chunk, r1 = min(rows, r0 + chunk);
   float acc[1][8];
@@ -712,7 +713,7 @@ __global__ void __launch_bounds__(256) colsum_partial_bf16x8_kernel(const uint4*
   float* const dst[1] = {p};
   block_fold_write<1>(acc, C, C8, c8, ty, TY, dst, (size_t)sl * C);
 }
-__global__ void __launch_bounds__(512) colsum_final_kernel(const float* __restrict__ p, int C, int S, float* out, int accumulate) {
+__global__ void __launch_bounds__(512) colsum_final_kernel(const float* __restrict__ p, int C, int S, float* out, int accumulate) { pdl_enter();
   __shared__ double sa[16][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, c = blockIdx.x * 32 + tx;
   double a = 0.0;
@@ -730,7 +731,7 @@ __global__ void __launch_bounds__(512) colsum_final_kernel(const float* __restri
 // bf16, C <= 4 (the G-last bias gradient: 3 channels x every pixel of the batch), rows % 8 == 0: a thread walks groups of 8 pixels = C 16-byte
 // vectors (element k of a group belongs to channel k % C), block-folds its C sums and writes one partial row; <= 256 partial rows
 template <int C>
-__global__ void __launch_bounds__(256) colsum_small_c_kernel(const uint4* __restrict__ x, size_t groups8, float* __restrict__ p) {
+__global__ void __launch_bounds__(256) colsum_small_c_kernel(const uint4* __restrict__ x, size_t groups8, float* __restrict__ p) { pdl_enter();
   float acc[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) acc[c] = 0.f;
@@ -769,7 +770,7 @@ void k_colsum(int prec, const void* x, int rows, int C, float* scratch, float* o
   LAUNCHED();
   launch_pdl(colsum_final_kernel, dim3((C + 31) / 32), dim3(512), (size_t)(0), s, scratch, C, S, out, accumulate); LAUNCHED();
 }
-__global__ void sumsq_segments_kernel(const float* __restrict__ p, const int64_t* off, const int64_t* len, const float* coef, int nseg, double* out) {
+__global__ void sumsq_segments_kernel(const float* __restrict__ p, const int64_t* off, const int64_t* len, const float* coef, int nseg, double* out) { pdl_enter();
   __shared__ double red[32];
   double acc = 0.0;
   for (int sgi = 0; sgi < nseg; ++sgi) {
@@ -785,7 +786,7 @@ __global__ void sumsq_segments_kernel(const float* __restrict__ p, const int64_t
 void k_sumsq_segments(const float* p, const int64_t* so, const int64_t* sl, const float* sc, int nseg, double* out, cudaStream_t s) {
   launch_pdl(sumsq_segments_kernel, dim3(1), dim3(1024), (size_t)(0), s, p, so, sl, sc, nseg, out); LAUNCHED();
 }
-__global__ void reduce_splits_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n, int splits, size_t stride, int accumulate) {
+__global__ void reduce_splits_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n, int splits, size_t stride, int accumulate) { pdl_enter();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float a = accumulate ? dst[i] : 0.f;
     for (int k = 0; k < splits; ++k) a += src[(size_t)k * stride + i];
@@ -794,7 +795,7 @@ __global__ void reduce_splits_kernel(const float* __restrict__ src, float* __res
 }
 // many splits, few outputs (the 3-channel edge weight gradients: ~300 partials of 3072 values): one warp per output element, lanes
 // stride over the splits, fixed-order shuffle tree
-__global__ void reduce_splits_wide_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n, int splits, size_t stride, int accumulate) {
+__global__ void reduce_splits_wide_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n, int splits, size_t stride, int accumulate) { pdl_enter();
   const size_t o = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5; const int lane = threadIdx.x & 31;
   if (o >= n) return;
   float a = 0.f;
@@ -817,7 +818,7 @@ void reduce_list_push(ReduceList* rl, const float* src, float* dst, int64_t n, i
   const bool wide = splits >= 64 && n <= (1 << 16);
   j.blocks = wide ? -(int)((n + 7) / 8) : (int)((n + 1023) / 1024);      // negative: warp-per-output mode
 }
-__global__ void __launch_bounds__(256) reduce_multi_kernel(const ReduceList rl) {
+__global__ void __launch_bounds__(256) reduce_multi_kernel(const ReduceList rl) { pdl_enter();
   int b = blockIdx.x, ji = 0;
   while (ji < rl.count) { const int nb = abs(rl.jobs[ji].blocks); if (b < nb) break; b -= nb; ++ji; }
   if (ji >= rl.count) return;
@@ -850,41 +851,68 @@ void k_reduce_multi(const ReduceList& rl, cudaStream_t s) {
 
 // ---------------------------------------------------------------- updater -------------------------------
 // One pass over params: 28 B/param for Adam (read p,g,m,v; write p,m,v), 20 B/param RmsProp, +2 B bf16 shadow.
+__device__ __forceinline__ float upd_elem(const UpdSeg& sg, float g, float p, float& s0, float& s1, float gscale, float alpha_t) {
+  g *= gscale;
+  if (sg.clip > 0.f) g = fminf(fmaxf(g, -sg.clip), sg.clip);
+  float u;
+  if (sg.kind == 0) u = sg.lr * g;
+  else if (sg.kind == 1) { s0 = sg.b1 * s0 + (1.0f - sg.b1) * g * g; u = sg.lr * g / (sqrtf(s0) + sg.eps); }
+  else if (sg.kind == 2) { s0 = sg.b1 * s0 + (1.0f - sg.b1) * g; s1 = sg.b2 * s1 + (1.0f - sg.b2) * g * g; u = alpha_t * s0 / (sqrtf(s1) + sg.eps); }
+  else u = g;
+  if (sg.l2 != 0.f) u = fmaf(sg.l2, p, u);
+  return p - u;
+}
+__device__ __forceinline__ void upd_shadow(const UpdSeg& sg, __nv_bfloat16* __restrict__ shadow, int64_t i, __nv_bfloat16 pb) {
+  shadow[sg.off_bf + (i - sg.off)] = pb;
+  if (sg.off_ps >= 0) {       // [O][4][4][C] element -> its one slot of the packed [(py,px,c4)][(dyr,dxc)][O] pixel-shuffle operand (kernels_tc.cu pack_deconv_ps_kernel)
+    const int e = (int)(i - sg.off), c = e % sg.ps_C, tap = (e / sg.ps_C) % 16, o = e / (sg.ps_C * 16), r = tap >> 2, sx = tap & 3;
+    const int py = (r == 0 || r == 2) ? 1 : 0, dyr = r == 3 ? -1 : r == 0 ? 1 : 0, px = (sx == 0 || sx == 2) ? 1 : 0, dxc = sx == 3 ? -1 : sx == 0 ? 1 : 0;
+    shadow[sg.off_ps + ((int64_t)((py * 8 + px * 4 + c) * 9 + (dyr + 1) * 3 + (dxc + 1))) * sg.ps_O + o] = pb;
+  }
+}
 __global__ void __launch_bounds__(256) updater_kernel(float* __restrict__ params, const float* __restrict__ grads, float* __restrict__ st0, float* __restrict__ st1,
                                                       const UpdSeg* __restrict__ segs, const int32_t* __restrict__ chunk_seg, const int64_t* __restrict__ chunk_off,
-                                                      float inv_mb, float inv_world, int* __restrict__ step, unsigned* __restrict__ ticket, __nv_bfloat16* __restrict__ shadow) {
+                                                      float inv_mb, float inv_world, int* __restrict__ step, unsigned* __restrict__ ticket, __nv_bfloat16* __restrict__ shadow) { pdl_enter();
   const UpdSeg sg = segs[chunk_seg[blockIdx.x]];
   const int64_t base = chunk_off[blockIdx.x];
   const int64_t end = min(base + (int64_t)UPD_CHUNK, sg.off + sg.len);
   const int t = *step + 1;
   float alpha_t = 0.f;
   if (sg.kind == 2) alpha_t = sg.lr * sqrtf(1.0f - powf(sg.b2, (float)t)) / (1.0f - powf(sg.b1, (float)t));
-  // four elements per thread per pass, every load issued before the first use: the kernel is latency-, not bandwidth-bound otherwise
   const float gscale = sg.div_mb ? inv_mb : inv_world;     // BN running-stat pseudo-gradients: no /mb, mean over ranks
-  for (int64_t i0 = base + threadIdx.x; i0 < end; i0 += 4 * blockDim.x) {
-    float gv[4], pv[4], s0[4], s1[4];
+  const bool has0 = sg.kind == 1 || sg.kind == 2, has1 = sg.kind == 2, sh = shadow && sg.off_bf >= 0;
+  if (((base | end) & 3) == 0 && (!sh || ((sg.off_bf + (base - sg.off)) & 3) == 0)) {
+    // 16-byte path: a full 4096-element chunk is four float4 per thread and array, all 16 loads issued before the first use
+    float4 gv[4], pv[4], s0[4], s1[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { const int64_t i = i0 + q * (int64_t)blockDim.x; const bool ok = i < end;
-      gv[q] = ok ? grads[i] : 0.f; pv[q] = ok ? params[i] : 0.f; s0[q] = (ok && (sg.kind == 1 || sg.kind == 2)) ? st0[i] : 0.f; s1[q] = (ok && sg.kind == 2) ? st1[i] : 0.f; }
+    for (int q = 0; q < 4; ++q) { const int64_t i = base + 4 * (threadIdx.x + q * (int64_t)blockDim.x); const bool ok = i < end; const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      gv[q] = ok ? *reinterpret_cast<const float4*>(grads + i) : z; pv[q] = ok ? *reinterpret_cast<const float4*>(params + i) : z;
+      s0[q] = (ok && has0) ? *reinterpret_cast<const float4*>(st0 + i) : z; s1[q] = (ok && has1) ? *reinterpret_cast<const float4*>(st1 + i) : z; }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { const int64_t i = i0 + q * (int64_t)blockDim.x; if (i >= end) continue;
-      float g = gv[q] * gscale;
-      if (sg.clip > 0.f) g = fminf(fmaxf(g, -sg.clip), sg.clip);
-      float p = pv[q], u;
-      if (sg.kind == 0) u = sg.lr * g;
-      else if (sg.kind == 1) { float c = sg.b1 * s0[q] + (1.0f - sg.b1) * g * g; st0[i] = c; u = sg.lr * g / (sqrtf(c) + sg.eps); }
-      else if (sg.kind == 2) { float m = sg.b1 * s0[q] + (1.0f - sg.b1) * g; float v = sg.b2 * s1[q] + (1.0f - sg.b2) * g * g; st0[i] = m; st1[i] = v; u = alpha_t * m / (sqrtf(v) + sg.eps); }
-      else u = g;
-      if (sg.l2 != 0.f) u = fmaf(sg.l2, p, u);
-      p -= u; params[i] = p;
-      if (shadow && sg.off_bf >= 0) {
-        const __nv_bfloat16 pb = __float2bfloat16_rn(p);
-        shadow[sg.off_bf + (i - sg.off)] = pb;
-        if (sg.off_ps >= 0) {       // [O][4][4][C] element -> its one slot of the packed [(py,px,c4)][(dyr,dxc)][O] pixel-shuffle operand (kernels_tc.cu pack_deconv_ps_kernel)
-          const int e = (int)(i - sg.off), c = e % sg.ps_C, tap = (e / sg.ps_C) % 16, o = e / (sg.ps_C * 16), r = tap >> 2, sx = tap & 3;
-          const int py = (r == 0 || r == 2) ? 1 : 0, dyr = r == 3 ? -1 : r == 0 ? 1 : 0, px = (sx == 0 || sx == 2) ? 1 : 0, dxc = sx == 3 ? -1 : sx == 0 ? 1 : 0;
-          shadow[sg.off_ps + ((int64_t)((py * 8 + px * 4 + c) * 9 + (dyr + 1) * 3 + (dxc + 1))) * sg.ps_O + o] = pb;
-        }
+    for (int q = 0; q < 4; ++q) { const int64_t i = base + 4 * (threadIdx.x + q * (int64_t)blockDim.x); if (i >= end) continue;
+      float4 p4;
+      p4.x = upd_elem(sg, gv[q].x, pv[q].x, s0[q].x, s1[q].x, gscale, alpha_t); p4.y = upd_elem(sg, gv[q].y, pv[q].y, s0[q].y, s1[q].y, gscale, alpha_t);
+      p4.z = upd_elem(sg, gv[q].z, pv[q].z, s0[q].z, s1[q].z, gscale, alpha_t); p4.w = upd_elem(sg, gv[q].w, pv[q].w, s0[q].w, s1[q].w, gscale, alpha_t);
+      *reinterpret_cast<float4*>(params + i) = p4;
+      if (has0) *reinterpret_cast<float4*>(st0 + i) = s0[q];
+      if (has1) *reinterpret_cast<float4*>(st1 + i) = s1[q];
+      if (sh) {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(p4.x, p4.y), hi = __floats2bfloat162_rn(p4.z, p4.w);
+        if (sg.off_ps < 0) *reinterpret_cast<uint2*>(shadow + sg.off_bf + (i - sg.off)) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+        else { upd_shadow(sg, shadow, i, lo.x); upd_shadow(sg, shadow, i + 1, lo.y); upd_shadow(sg, shadow, i + 2, hi.x); upd_shadow(sg, shadow, i + 3, hi.y); }
+      }
+    }
+  } else {
+    for (int64_t i0 = base + threadIdx.x; i0 < end; i0 += 4 * blockDim.x) {
+      float gv[4], pv[4], s0[4], s1[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const int64_t i = i0 + q * (int64_t)blockDim.x; const bool ok = i < end;
+        gv[q] = ok ? grads[i] : 0.f; pv[q] = ok ? params[i] : 0.f; s0[q] = (ok && has0) ? st0[i] : 0.f; s1[q] = (ok && has1) ? st1[i] : 0.f; }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const int64_t i = i0 + q * (int64_t)blockDim.x; if (i >= end) continue;
+        const float p = upd_elem(sg, gv[q], pv[q], s0[q], s1[q], gscale, alpha_t);
+        params[i] = p; if (has0) st0[i] = s0[q]; if (has1) st1[i] = s1[q];
+        if (sh) upd_shadow(sg, shadow, i, __float2bfloat16_rn(p));
       }
     }
   }
@@ -901,10 +929,10 @@ void k_updater(float* params, const float* grads, float* st0, float* st1, const 
   if (!nchunks) return;
   launch_pdl(updater_kernel, dim3(nchunks), dim3(256), (size_t)(0), s, params, grads, st0, st1, segs, chunk_seg, chunk_off, inv_mb, inv_world, step_dev, ticket, shadow); LAUNCHED();
 }
-__global__ void fill_f32_kernel(float* p, float v, size_t n) {
+__global__ void fill_f32_kernel(float* p, float v, size_t n) { pdl_enter();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
-__global__ void scale_f32_kernel(float* p, float v, size_t n) {
+__global__ void scale_f32_kernel(float* p, float v, size_t n) { pdl_enter();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] *= v;
 }
 void k_scale_f32(float* p, float v, size_t n, cudaStream_t s) { if (!n) return; launch_pdl(scale_f32_kernel, dim3(ew_blocks(n)), dim3(256), (size_t)(0), s, p, v, n); LAUNCHED(); }

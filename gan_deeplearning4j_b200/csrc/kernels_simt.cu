@@ -126,7 +126,7 @@ struct WgradProb {
 };
 
 template <class Prob>
-__global__ void __launch_bounds__(256) simt_gemm_kernel(Prob p, int k_per_split) {
+__global__ void __launch_bounds__(256) simt_gemm_kernel(Prob p, int k_per_split) { pdl_enter();
   __shared__ float As[TK][TM + 4];
   __shared__ float Bs[TK][TN + 4];
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;

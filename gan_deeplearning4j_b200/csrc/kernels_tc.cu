@@ -353,6 +353,7 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();         // barrier init / TMEM allocation above overlap the predecessor's tail; global memory is touched only below
 
   if (warp == 0) {
     if (lane == 0) {
@@ -476,6 +477,8 @@ __global__ void __launch_bounds__(192) tc_conv_persistent_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();      // single-wave grid: the successor may be scheduled behind us right away
+  pdl_wait();         // barrier init / TMEM allocation above overlap the predecessor's tail; global memory is touched only below
 
   // item -> (m group, n tile, phase): m fastest so that concurrently running CTAs share the weight tile in L2
   auto decode = [&](int item, int& mg, int& nb0, int& py, int& px) { mg = item % m_groups; const int r = item / m_groups; nb0 = (r % n_tiles) * BN; const int ph = r / n_tiles; py = ph >> 1; px = ph & 1; };
@@ -591,7 +594,7 @@ template <int BN, int STAGES, int EPI, bool AFFINE>
 static int launch_conv_e(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvParams& p, dim3 grid, cudaStream_t s) {
   using S = TcSmem<BN, STAGES, EPI>;
   TC_SET_SMEM_ONCE((tc_conv_kernel<BN, STAGES, EPI, AFFINE, false>), S::TOTAL);
-  tc_conv_kernel<BN, STAGES, EPI, AFFINE, false><<<grid, 192, S::TOTAL, s>>>(tmA, tmB, p);
+  launch_pdl(tc_conv_kernel<BN, STAGES, EPI, AFFINE, false>, dim3(grid), dim3(192), (size_t)(S::TOTAL), s, tmA, tmB, p);
   LAUNCHED();
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
 }
@@ -611,7 +614,7 @@ static int launch_convp_e(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   TC_SET_SMEM_ONCE((tc_conv_persistent_kernel<BN, STAGES, MT, EPI, AFFINE>), S::TOTAL);
   static int sms = 0; if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, tc_device());
   const int items = m_groups * n_tiles * phases; const int grid = items < sms ? items : sms;
-  tc_conv_persistent_kernel<BN, STAGES, MT, EPI, AFFINE><<<grid, 192, S::TOTAL, s>>>(tmA, tmB, p, m_groups, n_tiles, phases);
+  launch_pdl(tc_conv_persistent_kernel<BN, STAGES, MT, EPI, AFFINE>, dim3(grid), dim3(192), (size_t)(S::TOTAL), s, tmA, tmB, p, m_groups, n_tiles, phases);
   LAUNCHED();
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
 }
@@ -706,7 +709,7 @@ bool tc_deconv_ps_shape(const ConvGeom& g) { return is_k4s2p1_geom(g) && g.C >= 
 bool tc_deconv_ps_supported(const ConvGeom& g) { int a, b, c; return tc_deconv_ps_shape(g) && pick_row_tile(g.N, g.OH, g.OW, 128, &a, &b, &c); }
 size_t k_tc_deconv_ps_weight_elems(const ConvGeom& g) { return tc_deconv_ps_shape(g) ? (size_t)16 * 9 * g.O : 0; }
 // w [O][4][4][C] fp32 master -> wps [(py,px,c4)][(dyr,dxc)][O] bf16; dy row offset dyr serves (py, filter row r): -1 -> (0,3); 0 -> (0,1),(1,2); +1 -> (1,0)
-__global__ void pack_deconv_ps_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wps, int O, int C) {
+__global__ void pack_deconv_ps_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wps, int O, int C) { pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x; if (idx >= 16 * 9 * O) return;
   const int o = idx % O, t = (idx / O) % 9, n = idx / (9 * O);
   const int py = n >> 3, px = (n >> 2) & 1, c = n & 3, dyr = t / 3 - 1, dxc = t % 3 - 1;
@@ -715,7 +718,7 @@ __global__ void pack_deconv_ps_kernel(const float* __restrict__ w, __nv_bfloat16
   wps[idx] = __float2bfloat16((r >= 0 && sx >= 0 && c < C) ? w[((size_t)o * 16 + r * 4 + sx) * C + c] : 0.f);
 }
 void k_pack_deconv_ps(const float* w, __nv_bfloat16* wps, int O, int C, cudaStream_t s) {
-  pack_deconv_ps_kernel<<<(16 * 9 * O + 255) / 256, 256, 0, s>>>(w, wps, O, C); LAUNCHED();
+  launch_pdl(pack_deconv_ps_kernel, dim3((16 * 9 * O + 255) / 256), dim3(256), (size_t)(0), s, w, wps, O, C); LAUNCHED();
 }
 static int ps_halo_on();
 static int launch_ps_halo(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat16* wps, const TcConvParams& q, cudaStream_t s);
@@ -735,8 +738,8 @@ int k_tc_deconv_ps(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat
   if (weight_map(&tmB, wps, 16, 9, g.O, 16)) return -1;
   using S = TcSmem<16, 4>;
   dim3 grid((unsigned)((long)g.N * g.OH * g.OW / 128), 1, 1);
-  if (p.epi == EPI_ACTBWD) { TC_SET_SMEM_ONCE((tc_conv_kernel<16, 4, EPI_ACTBWD, false, true>), S::TOTAL); tc_conv_kernel<16, 4, EPI_ACTBWD, false, true><<<grid, 192, S::TOTAL, s>>>(tmA, tmB, p); }
-  else { TC_SET_SMEM_ONCE((tc_conv_kernel<16, 4, EPI_PLAIN, false, true>), S::TOTAL); tc_conv_kernel<16, 4, EPI_PLAIN, false, true><<<grid, 192, S::TOTAL, s>>>(tmA, tmB, p); }
+  if (p.epi == EPI_ACTBWD) { TC_SET_SMEM_ONCE((tc_conv_kernel<16, 4, EPI_ACTBWD, false, true>), S::TOTAL); launch_pdl(tc_conv_kernel<16, 4, EPI_ACTBWD, false, true>, dim3(grid), dim3(192), (size_t)(S::TOTAL), s, tmA, tmB, p); }
+  else { TC_SET_SMEM_ONCE((tc_conv_kernel<16, 4, EPI_PLAIN, false, true>), S::TOTAL); launch_pdl(tc_conv_kernel<16, 4, EPI_PLAIN, false, true>, dim3(grid), dim3(192), (size_t)(S::TOTAL), s, tmA, tmB, p); }
   LAUNCHED(); g_tc_last_kernel = "tc_conv_kernel<16,4,PS>";
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
 }
@@ -776,6 +779,8 @@ __global__ void __launch_bounds__(192) tc_deconv_ps_halo_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();      // single-wave grid: the successor may be scheduled behind us right away
+  pdl_wait();         // barrier init / TMEM allocation above overlap the predecessor's tail; global memory is touched only below
   const int per_img = p.tiles_x * p.tiles_y;
 
   if (warp == 0) {
@@ -870,8 +875,8 @@ static int launch_ps_halo(const ConvGeom& g, const __nv_bfloat16* dy, const __nv
   if (weight_map(&tmW, wps, 16, 9, g.O, 16)) return -1;
   static int sms = 0; if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, tc_device());
   const int grid = p.total_tiles < 2 * sms ? p.total_tiles : 2 * sms;
-  if (q.epi == EPI_ACTBWD) { TC_SET_SMEM_ONCE(tc_deconv_ps_halo_kernel<EPI_ACTBWD>, PSH_SMEM); tc_deconv_ps_halo_kernel<EPI_ACTBWD><<<grid, 192, PSH_SMEM, s>>>(tmA, tmW, p); }
-  else { TC_SET_SMEM_ONCE(tc_deconv_ps_halo_kernel<EPI_PLAIN>, PSH_SMEM); tc_deconv_ps_halo_kernel<EPI_PLAIN><<<grid, 192, PSH_SMEM, s>>>(tmA, tmW, p); }
+  if (q.epi == EPI_ACTBWD) { TC_SET_SMEM_ONCE(tc_deconv_ps_halo_kernel<EPI_ACTBWD>, PSH_SMEM); launch_pdl(tc_deconv_ps_halo_kernel<EPI_ACTBWD>, dim3(grid), dim3(192), (size_t)(PSH_SMEM), s, tmA, tmW, p); }
+  else { TC_SET_SMEM_ONCE(tc_deconv_ps_halo_kernel<EPI_PLAIN>, PSH_SMEM); launch_pdl(tc_deconv_ps_halo_kernel<EPI_PLAIN>, dim3(grid), dim3(192), (size_t)(PSH_SMEM), s, tmA, tmW, p); }
   LAUNCHED(); g_tc_last_kernel = "tc_deconv_ps_halo_kernel";
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
 }
@@ -948,7 +953,7 @@ __device__ __forceinline__ void edge_build_row(const TcEdgeParams& p, const uint
                  case 3: edge_build_row_c<3>(p, slab, tile, row, ones); break; default: edge_build_row_c<4>(p, slab, tile, row, ones); break; }
 }
 
-__global__ void __launch_bounds__(128) tc_edge_conv_kernel(const TcEdgeParams p) {
+__global__ void __launch_bounds__(128) tc_edge_conv_kernel(const TcEdgeParams p) { pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -1030,7 +1035,7 @@ __global__ void __launch_bounds__(128) tc_edge_conv_kernel(const TcEdgeParams p)
 // dy rows are copied as they are (64 channels = 128 B), xcol rows are built as above.  O = 64 fills half of the M = 128 instruction;
 // the second 64-row block of the A descriptor points at the xcol tile (LBO = 16 KB), those accumulator rows are never read.
 // Each CTA walks tiles_per_cta consecutive tiles (split over pixels), accumulating in TMEM, and writes one fp32 partial.
-__global__ void __launch_bounds__(128) tc_edge_wgrad_kernel(const TcEdgeParams p) {
+__global__ void __launch_bounds__(128) tc_edge_wgrad_kernel(const TcEdgeParams p) { pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -1128,7 +1133,7 @@ int k_tc_edge_conv(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat1
   TC_SET_SMEM_ONCE(tc_edge_conv_kernel, smem);
   static int target = -1; if (target < 0) { const char* e = getenv("B2G_EDGE_CONV_CTAS"); target = e ? atoi(e) : 592; if (target < 1) target = 592; }
   p.tiles_per_cta = (p.tiles_total + target - 1) / target;
-  tc_edge_conv_kernel<<<dim3((unsigned)((p.tiles_total + p.tiles_per_cta - 1) / p.tiles_per_cta), (unsigned)(g.O / 64)), 128, smem, s>>>(p);
+  launch_pdl(tc_edge_conv_kernel, dim3(dim3((unsigned)((p.tiles_total + p.tiles_per_cta - 1) / p.tiles_per_cta), (unsigned)(g.O / 64))), dim3(128), (size_t)(smem), s, p);
   LAUNCHED(); g_tc_last_kernel = "tc_edge_conv_kernel";
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
 }
@@ -1143,7 +1148,7 @@ int k_tc_edge_wgrad(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat
   if (db && g.C < 4) p.part_b = scratch + (size_t)ctas * n;
   const size_t smem = 1024 + 32768 + EDGE_SLAB_BYTES + 64;
   TC_SET_SMEM_ONCE(tc_edge_wgrad_kernel, smem);
-  tc_edge_wgrad_kernel<<<dim3((unsigned)ctas), 128, smem, s>>>(p);
+  launch_pdl(tc_edge_wgrad_kernel, dim3(dim3((unsigned)ctas)), dim3(128), (size_t)(smem), s, p);
   LAUNCHED(); g_tc_last_kernel = "tc_edge_wgrad_kernel";
   if (cudaPeekAtLastError() != cudaSuccess) return -3;
   reduce_or_defer(defer, scratch, dw, n, ctas, n, accumulate, s);
@@ -1202,6 +1207,8 @@ __global__ void __launch_bounds__(192) tc_wgrad_kernel(const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();      // single-wave grid: the successor may be scheduled behind us right away
+  pdl_wait();         // barrier init / TMEM allocation above overlap the predecessor's tail; global memory is touched only below
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1289,6 +1296,8 @@ __global__ void __launch_bounds__(192) tc_wgrad2_kernel(const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();      // single-wave grid: the successor may be scheduled behind us right away
+  pdl_wait();         // barrier init / TMEM allocation above overlap the predecessor's tail; global memory is touched only below
   if (warp == 0) {
     if (lane == 0) {
       for (int i = 0; i < num_kb; ++i) {
@@ -1383,7 +1392,7 @@ template <int BNW, int STAGES>
 static int launch_wgrad(const CUtensorMap& tmDy, const CUtensorMap& tmX, const TcWgradParams& p, dim3 grid, cudaStream_t s, const char* name) {
   using S = TcWgradSmem<BNW, STAGES>;
   TC_SET_SMEM_ONCE((tc_wgrad_kernel<BNW, STAGES>), S::TOTAL);
-  tc_wgrad_kernel<BNW, STAGES><<<grid, 192, S::TOTAL, s>>>(tmDy, tmX, p);
+  launch_pdl(tc_wgrad_kernel<BNW, STAGES>, dim3(grid), dim3(192), (size_t)(S::TOTAL), s, tmDy, tmX, p);
   LAUNCHED(); g_tc_last_kernel = name;
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
 }
@@ -1417,7 +1426,7 @@ int k_tc_wgrad(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* d
   if (wgrad_mt2(g)) {
     TC_SET_SMEM_ONCE(tc_wgrad2_kernel, TcWgrad2Smem::TOTAL);
     grid.z = (unsigned)(g.O / 256);
-    tc_wgrad2_kernel<<<grid, 192, TcWgrad2Smem::TOTAL, s>>>(tmDy, tmX, p); LAUNCHED(); g_tc_last_kernel = "tc_wgrad2_kernel";
+    launch_pdl(tc_wgrad2_kernel, dim3(grid), dim3(192), (size_t)(TcWgrad2Smem::TOTAL), s, tmDy, tmX, p); LAUNCHED(); g_tc_last_kernel = "tc_wgrad2_kernel";
     rc = cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
   } else
   switch (BNW) {
