@@ -213,3 +213,135 @@ def test_edge_kernels_full_size(b200):
         lay.forward(x[i0:i0 + 64].transpose(0, 3, 1, 2).astype(np.float64), True); lay.backward(dy[i0:i0 + 64].transpose(0, 3, 1, 2).astype(np.float64)); ref += lay.grads["W"]
     got, _ = b.test_conv(ctx, 2, 3, b.BF16, g, x, dy, oc * 16 * c)
     assert np.abs(got.reshape(oc, 4, 4, c) - ref.transpose(0, 2, 3, 1)).max() / np.abs(ref).max() < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------
+# Whole step in BF16 at the BASELINE sizes, layer by layer with injected inputs:
+# every layer's oracle is evaluated on the GPU's OWN input to that layer, so one layer's bf16 rounding never hides in the next one's
+# tolerance; the backward pass is the oracle's exact backward through the layers whose caches hold those injected activations.
+# ------------------------------------------------------------------------------------------------
+def _fro(a, b):
+    a = np.asarray(a, np.float64).ravel(); b = np.asarray(b, np.float64).ravel()
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
+def _inject_forward(onet, bnet, specs, x_in, batch, what):
+    """Runs the oracle net layer by layer, each layer on the GPU's activation of the layer below; checks every produced tensor."""
+    cur = np.asarray(x_in, np.float32)
+    shape = cur.shape
+    i = 0
+    while i < len(specs):
+        t = specs[i]["type"]; l = onet.layers[i]
+        fused = t == "batchnorm" and i + 1 < len(specs) and specs[i + 1]["type"] == "activation"
+        ref = l.forward(cur.reshape(shape), True)
+        if fused:       # the engine stores BatchNorm+activation as one tensor
+            ref = onet.layers[i + 1].forward(ref, True)
+        shape = ref.shape
+        if t in ("conv2d", "deconv2d", "dense", "batchnorm", "output"):
+            got = bnet.activation(i, batch).reshape(shape)
+            if t == "output":
+                got_cmp, ref_cmp = got, l._z.reshape(shape)          # the engine keeps the logits; the oracle's forward returns sigmoid(z)
+            else:
+                got_cmp, ref_cmp = got, ref
+            check_bf16(got_cmp, ref_cmp, f"{what} layer {i} ({specs[i].get('name', t)})")
+            cur = got if t != "output" else got                       # inject the GPU's tensor into the next layer
+            if t == "output":
+                l._z = got.reshape(l._z.shape).astype(l._z.dtype)
+        else:
+            cur = ref
+        i += 2 if fused else 1
+    return cur.reshape(shape)
+
+
+def _grads_by_tensor(onet, flat):
+    out, off = {}, 0
+    for li, l in enumerate(onet.layers):
+        if not l.has_params:
+            continue
+        for pname, shp, _ in l.param_specs():
+            n = int(np.prod(shp)); out[(li, pname)] = flat[off:off + n]; off += n
+    assert off == flat.size
+    return out
+
+
+def _flat_order(l, pname):
+    """oracle gradient tensor -> the element order of DL4J's flattened view (dense W is 'f'-order)."""
+    g = np.asarray(l.grads[pname], np.float64)
+    return g.ravel(order="F") if (isinstance(l, o.Dense) and pname == "W") else g.ravel()
+
+
+STEP_CASES = [("c2", 64, 100, 64, 128), ("c4", 128, 100, 64, 32), ("c5", 0, 128, 1024, 8192)]
+
+
+@pytest.mark.parametrize("case", STEP_CASES, ids=[c[0] for c in STEP_CASES])
+def test_bf16_whole_step_layer_by_layer(b200, case):
+    """BASELINE configs[1] / [3] per GPU: D's train pass (computeGradientAndScore on 2N images) and the generator step through D, BF16.
+    Forward: every conv / transposed conv / BatchNorm(+activation) tensor within one bf16 rounding of the oracle on the same input.
+    Backward: every gradient tensor against the oracle's exact backward from the injected activations: relative Frobenius error <= 3e-2
+    (ten bf16-rounded epsilon tensors deep), cosine >= 0.999."""
+    b, ctx = b200
+    from gan_deeplearning4j_b200 import models as m
+    from helpers import oracle_from_specs, push_params, randomize
+    name, size, z, nf, n = case
+    rng = np.random.default_rng(21)
+    if name == "c5":        # MLP-GAN (BASELINE configs[4]): dense tensor-core path, samples of d = 256 features
+        gs, ds, dshape = m.mlp_generator(z, nf, 256), m.mlp_discriminator(256, nf), (256,)
+        data = [rng.uniform(-1, 1, (n, 256)), rng.uniform(-1, 1, (n, z)), rng.uniform(-1, 1, (n, z)), 1 + 0.05 * rng.standard_normal((n, 1)), 0.05 * rng.standard_normal((n, 1)), np.ones((n, 1))]
+        data = [np.asarray(a, np.float32) for a in data]
+    else:
+        gs, ds, dshape = m.dcgan_generator(size, z, nf, 3), m.dcgan_discriminator(size, nf, 3), (3, size, size)
+        data = [np.asarray(a, np.float32) for a in o.synthetic_batch(n, size, 3, z, seed=5)]
+    q = o.Quirks(xent_clip_eps=0.0)
+    G = oracle_from_specs(gs, (z,), quirks=q, dtype=np.float32, seed=1); D = oracle_from_specs(ds, dshape, quirks=q, dtype=np.float32, seed=2, flat_input=False)
+    randomize(G, rng); randomize(D, rng)
+    bG = b.Net(ctx, gs, (z,), max_batch=n, precision=b.BF16, xent_clip_eps=0.0)
+    bD = b.Net(ctx, ds, dshape, max_batch=2 * n, precision=b.BF16, xent_clip_eps=0.0, bn_groups=2)
+    push_params(G, bG); push_params(D, bD)
+    # ---- D alone on 2N images (one BatchNorm group): forward tensors and every D gradient
+    x2 = np.concatenate([data[0], rng.uniform(-1, 1, data[0].shape).astype(np.float32)]); y2 = np.concatenate([data[3], data[4]])
+    bD.compute_gradient_and_score(x2, y2)
+    # the tensor-core path holds bf16 weights: the oracle must see the same operands
+    for net in (G, D):
+        for l in net.layers:
+            if l.has_params and "W" in l.params:
+                l.params["W"] = bf16_round(l.params["W"]).astype(np.float32)
+    _inject_forward(D, bD, ds, bf16_round(x2), 2 * n, "D (2N)")
+    loss_sum, eps = D.layers[-1].score_and_eps(y2.astype(np.float32))
+    if isinstance(D.layers[-1], o.Output):
+        eps = D.layers[-1].backward(eps)
+    D.backward_from_prefix(eps)
+    got = _grads_by_tensor(D, bD.gradients())
+    for (li, pname), gv in got.items():
+        if pname in ("mean", "var"):
+            continue
+        ref = _flat_order(D.layers[li], pname)
+        fro = _fro(gv, ref); cos = float(np.dot(gv, ref) / (np.linalg.norm(gv) * np.linalg.norm(ref) + 1e-30))
+        assert fro < 3e-2 and cos > 0.999, (f"D grad {ds[li].get('name')}.{pname}", fro, cos)
+    # ---- the adversarial step: afterwards the nets hold the G-step pass (G train forward on z_g, D train forward on G's output)
+    pD_before = bD.params()
+    gan = b.Gan(bG, bD, use_cuda_graph=False)
+    gan.step(*data)
+    # D was updated once before the G step ran through it: give the oracle those parameters (G's are still the pre-update ones it ran with)
+    D.set_params_flat(bD.params().astype(np.float32))
+    for l in D.layers:
+        if l.has_params and "W" in l.params:
+            l.params["W"] = bf16_round(l.params["W"]).astype(np.float32)
+    assert np.abs(bD.params() - pD_before).max() > 0
+    xg = _inject_forward(G, bG, gs, bf16_round(data[2]), n, "G (train, z_g)")
+    _inject_forward(D, bD, ds, xg, n, "D (G step)")
+    loss_sum, eps = D.layers[-1].score_and_eps(data[5].astype(np.float32))
+    if isinstance(D.layers[-1], o.Output):
+        eps = D.layers[-1].backward(eps)
+    eps_x = D.backward_from_prefix(eps)
+    eps_g = eps_x.reshape(xg.shape)
+    for l in reversed(G.layers):
+        eps_g = l.backward(eps_g)
+    got = _grads_by_tensor(G, bG.gradients())
+    for (li, pname), gv in got.items():
+        if pname in ("mean", "var"):
+            continue
+        ref = _flat_order(G.layers[li], pname)
+        fro = _fro(gv, ref); cos = float(np.dot(gv, ref) / (np.linalg.norm(gv) * np.linalg.norm(ref) + 1e-30))
+        assert fro < 3e-2 and cos > 0.999, (f"G grad {gs[li].get('name')}.{pname}", fro, cos)
+    assert bD.simt_gemm_calls() > 0        # the skinny layers (the logit; z -> 4x4 in the DCGANs) are SIMT by design, and counted
+    gan.close(); bG.close(); bD.close()
