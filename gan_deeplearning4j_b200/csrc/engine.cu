@@ -126,6 +126,9 @@ struct b2g_net {
   int last_rows = 0;
   cudaStream_t fwd_stream = nullptr;   // when set, net_forward launches here instead of ctx->stream
   bool grad_allreduce = true;          // false: parameter-averaging mode (b2g_net_average_parameters)
+  bool sync_bn = false;                // cross-replica BatchNorm statistics: the 64-bit statistic accumulators are all-reduced
+  bool ar_bf16 = false;                // gradient all-reduce payload in bf16 (half the bytes; default fp32 for parity)
+  __nv_bfloat16* ar_buf = nullptr;
   int ar_split_layer = -1; int64_t ar_split_off = 0;   // gradients of layers >= ar_split_layer (= grads[ar_split_off, n_params)) are all-reduced while backward continues
   bool ar_tail_sent = false;
   std::vector<void*> allocs;
@@ -384,6 +387,8 @@ static inline cudaStream_t fstream(const b2g_net* n) { return n->fwd_stream ? n-
 // side, K = 100 G-first) are counted too.
 static inline void note_simt(b2g_net* n) { if (n->prec == PREC_BF16) ++n->simt_gemm_calls; }
 
+// sync_bn: the number of replicas whose statistics are pooled (1 = local statistics, what Spark workers do in the reference)
+static inline int sync_bn_world(const b2g_net* n) { return (n->sync_bn && n->ctx->comm && n->ctx->world > 1) ? n->ctx->world : 1; }
 // `scale` (inference-mode BatchNorm folded into the epilogue) must be honoured; `fuse` (EPI_STATS / EPI_BNBWD / EPI_ACTBWD) is opportunistic:
 // *fused tells the caller whether the kernel that ran did it -- if not, the unfused elementwise kernels follow.
 static int32_t gemm_fprop(b2g_net* n, const LayerRT& l, const ConvGeom& g, const void* x, const float* bias, void* out, int act, float alpha,
@@ -490,8 +495,10 @@ static int32_t net_forward(b2g_net* n, const void* in, const FwdOpts& o, const v
         l.fwd_fused = false;
         if (bn_train && l.bn_coef && fuse_bn) {
           if (!l.stats_by_producer) k_bn_stats_acc(cur, rows_pg, l.oc, o.groups, l.acc_fwd, s);
+          const int reps = sync_bn_world(n);
+          if (reps > 1) NC(g_nccl.ar(l.acc_fwd, l.acc_fwd, k_bn_acc_elems(l.oc, o.groups), /*ncclUint64*/ 5, /*ncclSum*/ 0, n->ctx->comm, s));      // integer sums: bit-identical on every rank
           k_bn_apply_acc(cur, out, rows_pg, l.oc, o.groups, l.acc_fwd, n->params + l.off_gamma, n->params + l.off_beta, l.fused_act, l.fused_alpha, d.bn_eps, l.bn_coef,
-                         n->params + l.off_mean, n->params + l.off_var, o.update_running ? n->grads + l.off_mean : nullptr, o.update_running ? n->grads + l.off_var : nullptr, d.bn_decay, s);
+                         n->params + l.off_mean, n->params + l.off_var, o.update_running ? n->grads + l.off_mean : nullptr, o.update_running ? n->grads + l.off_var : nullptr, d.bn_decay, s, reps);
           l.fwd_fused = true; l.stats_by_producer = false; l.fwd_groups = o.groups;
           break;
         }
@@ -520,7 +527,7 @@ static int32_t net_forward(b2g_net* n, const void* in, const FwdOpts& o, const v
 // backward continues.
 static bool ar_overlap_on(const b2g_net* n) {
   static int on = -1; if (on < 0) { const char* e = getenv("B2G_AR_OVERLAP"); on = (e && e[0] == '1') ? 1 : 0; }
-  return on && n->ctx->comm && n->ctx->world > 1 && n->grad_allreduce && n->ar_split_layer > 0;
+  return on && n->ctx->comm && n->ctx->world > 1 && n->grad_allreduce && n->ar_split_layer > 0 && !n->sync_bn;
 }
 static void flush_pending_reduce(b2g_net* n, cudaStream_t s2) { if (n->pending.count) { k_reduce_multi(n->pending, s2); n->pending.count = 0; } }
 
@@ -617,7 +624,9 @@ static int32_t net_backward(b2g_net* n, const void* net_in, void* eps, int rows,
         int rows_pg = (R / groups) * l.oh * l.ow; void* nx = need_in ? other(cur) : nullptr;
         if (l.fwd_fused && l.fwd_groups == groups) {
           if (!l.bwd_premul) k_bn_bwd_stats_acc(lin, cur, rows_pg, l.oc, groups, l.bn_coef, l.fused_act, l.fused_alpha, l.acc_bwd, s);
-          k_bn_bwd_apply_acc(lin, cur, nx, rows_pg, l.oc, groups, l.bn_coef, l.fused_act, l.fused_alpha, l.bwd_premul ? 1 : 0, l.acc_bwd, n->grads + l.off_gamma, n->grads + l.off_beta, want_wgrad_l ? 1 : 0, s);
+          const int reps = sync_bn_world(n);
+          if (reps > 1) NC(g_nccl.ar(l.acc_bwd, l.acc_bwd, k_bn_acc_elems(l.oc, groups), /*ncclUint64*/ 5, /*ncclSum*/ 0, n->ctx->comm, s));
+          k_bn_bwd_apply_acc(lin, cur, nx, rows_pg, l.oc, groups, l.bn_coef, l.fused_act, l.fused_alpha, l.bwd_premul ? 1 : 0, l.acc_bwd, n->grads + l.off_gamma, n->grads + l.off_beta, want_wgrad_l ? 1 : 0, s, reps);
           l.bwd_premul = false;
         } else
         k_bn_bwd(n->prec, lin, cur, nx, rows_pg, l.oc, groups, l.bn_mean, l.bn_invstd, n->params + l.off_gamma, n->params + l.off_beta, l.fused_act, l.fused_alpha,
@@ -653,6 +662,12 @@ static int32_t net_allreduce_grads(b2g_net* n) {
     cudaEventRecord(c->ev_c0, c->stream); cudaStreamWaitEvent(c->comm_stream, c->ev_c0, 0);
     NC(g_nccl.ar(n->grads, n->grads, (size_t)n->ar_split_off, /*ncclFloat32*/ 7, /*ncclSum*/ 0, c->comm, c->comm_stream));
     cudaEventRecord(c->ev_c2, c->comm_stream); cudaStreamWaitEvent(c->stream, c->ev_c2, 0);
+    return 0;
+  }
+  if (n->ar_bf16 && n->ar_buf) {     // half the bytes on the wire: round to bf16, sum in bf16, widen (option; the default fp32 payload keeps DP bit-identical to one GPU)
+    k_cast_f32_to_bf16(n->grads, n->ar_buf, (size_t)n->n_params, c->stream);
+    NC(g_nccl.ar(n->ar_buf, n->ar_buf, (size_t)n->n_params, /*ncclBfloat16*/ 9, /*ncclSum*/ 0, c->comm, c->stream));
+    k_nhwc_to_nchw_f32(PREC_BF16, n->ar_buf, n->grads, 1, 1, (int)n->n_params, c->stream);
     return 0;
   }
   NC(g_nccl.ar(n->grads, n->grads, (size_t)n->n_params, /*ncclFloat32*/ 7, /*ncclSum*/ 0, c->comm, c->stream));
@@ -909,20 +924,28 @@ static int32_t gan_step_part2(b2g_gan* g, int N) {
   b2g_net *G = g->G, *D = g->D; cudaStream_t s = G->ctx->stream;
   // 1. (part 1) x_fake = gen.output(z_d) (J:420) was written straight into the second half of D's input batch.
   // x_real arrived (and was converted to the device layout) on the copy stream meanwhile; only the discriminator needs it
-  // 3a (hoisted). The generator's train-mode forward on z_g depends only on G's parameters, which the D step does not touch:
-  // run it on a second stream underneath the whole D step.
-  cudaStream_t s3 = G->ctx->side2;
-  CU(cudaEventRecord(G->ctx->ev_a, s)); CU(cudaStreamWaitEvent(s3, G->ctx->ev_a, 0));
-  CU(cudaMemsetAsync(G->grads, 0, sizeof(float) * G->n_params, s3));
-  const void* xg = nullptr; FwdOpts og2{N, 1, true, true, nullptr};
-  G->fwd_stream = s3; int32_t rg = net_forward(G, g->z_g, og2, &xg); G->fwd_stream = nullptr; B2(rg);
-  CU(cudaEventRecord(G->ctx->ev_b, s3));
+  // 3a (hoisted). The generator's train-mode forward on z_g depends only on G's parameters, which the D step does not touch: it runs on a
+  // second stream -- on one GPU underneath the whole D step; with a communicator underneath the D gradient all-reduce + updater, where the
+  // SMs would otherwise idle on the network (measured on 2 x B200, round 2: the all-reduce pair costs ~0.17 ms per step when exposed).
+  // (with sync_bn the generator's BatchNorm all-reduces must keep one issue order with the discriminator's on every rank: no hoisting)
+  cudaStream_t s3 = (G->sync_bn || D->sync_bn) ? s : G->ctx->side2;
+  const bool under_allreduce = G->ctx->comm && G->ctx->world > 1 && D->grad_allreduce && s3 != s;
+  const void* xg = nullptr;
+  auto hoisted_g_forward = [&]() -> int32_t {
+    CU(cudaEventRecord(G->ctx->ev_a, s)); CU(cudaStreamWaitEvent(s3, G->ctx->ev_a, 0));
+    CU(cudaMemsetAsync(G->grads, 0, sizeof(float) * G->n_params, s3));
+    FwdOpts og2{N, 1, true, true, nullptr};
+    G->fwd_stream = s3; int32_t rg = net_forward(G, g->z_g, og2, &xg); G->fwd_stream = nullptr; B2(rg);
+    CU(cudaEventRecord(G->ctx->ev_b, s3)); return 0;
+  };
+  if (!under_allreduce) B2(hoisted_g_forward());
   // 2. D update on (x_real, y_real) | (x_fake, y_fake): two BN groups, one batched pass (J:414-426)
   CU(cudaMemsetAsync(D->grads, 0, sizeof(float) * D->n_params, s));
   const void* logits = nullptr; FwdOpts od{2 * N, 2, true, true, nullptr};
   B2(net_forward(D, D->input, od, &logits));
   k_xent(D->prec, logits, g->y_d, D->epsA, g->loss_dev, N, 2, D->cfg.xent_clip_eps, s);
   B2(net_backward(D, D->input, D->epsA, 2 * N, 2, true, false, /*allreduce_follows=*/true));
+  if (under_allreduce) B2(hoisted_g_forward());
   B2(net_allreduce_grads(D));
   B2(net_update(D, 2 * N));
   // 3. G update through D on (z_g, y_gen) (J:465-471); D's parameters / running stats / updater state untouched
@@ -1063,6 +1086,12 @@ extern "C" int32_t b2g_ctx_comm_init(b2g_ctx* c, int32_t world, int32_t rank, co
 }
 extern "C" int32_t b2g_ctx_comm_destroy(b2g_ctx* c) { if (c && c->comm) { g_nccl.destroy(c->comm); c->comm = nullptr; c->world = 1; c->rank = 0; } return 0; }
 extern "C" int32_t b2g_net_set_grad_allreduce(b2g_net* n, int32_t enabled) { if (!n) return fail(B2G_ERR_ARG, "null"); n->grad_allreduce = enabled != 0; return 0; }
+extern "C" int32_t b2g_net_set_sync_bn(b2g_net* n, int32_t enabled) { if (!n) return fail(B2G_ERR_ARG, "null"); if (enabled && n->prec != PREC_BF16) return fail(B2G_ERR_UNSUPPORTED, "sync_bn rides on the fused BatchNorm path (BF16 nets)"); n->sync_bn = enabled != 0; return 0; }
+extern "C" int32_t b2g_net_set_grad_payload_bf16(b2g_net* n, int32_t enabled) {
+  if (!n) return fail(B2G_ERR_ARG, "null"); CU(cudaSetDevice(n->ctx->device));
+  if (enabled && !n->ar_buf) B2(dalloc(n, &n->ar_buf, sizeof(__nv_bfloat16) * (size_t)n->n_params));
+  n->ar_bf16 = enabled != 0; return 0;
+}
 extern "C" int32_t b2g_net_average_parameters(b2g_net* n) {
   if (!n) return fail(B2G_ERR_ARG, "null"); b2g_ctx* c = n->ctx; CU(cudaSetDevice(c->device));
   if (!c->comm || c->world == 1) return 0;

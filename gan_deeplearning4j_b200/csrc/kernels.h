@@ -59,14 +59,15 @@ void k_bn_stats_acc(const void* x, int rows_per_group, int C, int groups, unsign
 // y = act(x*scale+shift); block 0 also leaves coef[groups][4][C] = {scale = gamma*invstd, shift = beta - mean*scale, mean, invstd} for the
 // backward pass and (g_mean != null) the DL4J running-stat pseudo-gradients averaged over groups
 void k_bn_apply_acc(const void* x, void* y, int rows_per_group, int C, int groups, const unsigned long long* acc, const float* gamma, const float* beta,
-                    int act, float alpha, float eps, float* coef, const float* run_mean, const float* run_var, float* g_mean, float* g_var, float decay, cudaStream_t s);
+                    int act, float alpha, float eps, float* coef, const float* run_mean, const float* run_var, float* g_mean, float* g_var, float decay, cudaStream_t s, int replicas = 1);
 // sum dy', sum dy'*xhat -> acc with dy' = eps_out * act'(x*scale+shift)   (producers without the EPI_BNBWD epilogue)
 void k_bn_bwd_stats_acc(const void* x, const void* eps_out, int rows_per_group, int C, int groups, const float* coef, int act, float alpha, unsigned long long* acc, cudaStream_t s);
 // eps_in = scale * (dy' - mean(dy') - xhat*mean(dy'*xhat)).  premul = 0: eps_out is the raw epsilon and acc = (sum dy', sum dy'*xhat) from
 // k_bn_bwd_stats_acc; premul = 1: eps_out already holds dy' and acc = (sum dy', sum dy'*z) from the EPI_BNBWD epilogue, converted here in
 // double: sum dy'*xhat = invstd * (sum dy'*z - mean * sum dy').  Block 0 adds dgamma / dbeta (summed over groups).
 void k_bn_bwd_apply_acc(const void* x, const void* eps_out, void* eps_in, int rows_per_group, int C, int groups, const float* coef, int act, float alpha, int premul,
-                        const unsigned long long* acc, float* g_gamma, float* g_beta, int want_param_grads, cudaStream_t s);
+                        const unsigned long long* acc, float* g_gamma, float* g_beta, int want_param_grads, cudaStream_t s, int replicas = 1);
+// replicas > 1 (sync_bn): acc holds the all-reduced sums of `replicas` ranks, each contributing rows_per_group rows per group
 
 // ---- activations / pooling / upsampling -----------------------------------------------------------
 void k_act_fwd(int prec, const void* x, void* y, size_t n, int act, float alpha, cudaStream_t s);

@@ -413,14 +413,15 @@ void k_bn_stats_acc(const void* x, int rows, int C, int groups, unsigned long lo
 template <int ACTC>
 __global__ void __launch_bounds__(256, 3) bn_apply_acc_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int rows, int C, int groups, const unsigned long long* __restrict__ accp,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta, int act, float alpha, float eps, float* __restrict__ coef,
-                                                             const float* __restrict__ run_mean, const float* __restrict__ run_var, float* g_mean, float* g_var, float decay) { pdl_enter();
+                                                             const float* __restrict__ run_mean, const float* __restrict__ run_var, float* g_mean, float* g_var, float decay, int replicas) { pdl_enter();
   extern __shared__ float s_cf[];
+  const double cnt = (double)rows * replicas;       // sync_bn: the accumulators hold the sums of every replica (all-reduced 64-bit integers)
   const bool writer = blockIdx.x == 0;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     double agm = 0.0, agv = 0.0;
     for (int g = 0; g < groups; ++g) {
       const unsigned long long* a = accp + (size_t)g * 4 * C;
-      const double mu = sacc_read(a, (size_t)C, (size_t)c) / rows; double var = sacc_read(a + 2 * (size_t)C, (size_t)C, (size_t)c) / rows - mu * mu; if (var < 0) var = 0;
+      const double mu = sacc_read(a, (size_t)C, (size_t)c) / cnt; double var = sacc_read(a + 2 * (size_t)C, (size_t)C, (size_t)c) / cnt - mu * mu; if (var < 0) var = 0;
       const float is = (float)(1.0 / sqrt(var + (double)eps)), sc = gamma[c] * is, sh = fmaf(-(float)mu, sc, beta[c]);
       s_cf[(g * 2 + 0) * C + c] = sc; s_cf[(g * 2 + 1) * C + c] = sh;
       if (writer) {
@@ -455,10 +456,10 @@ __global__ void __launch_bounds__(256, 3) bn_apply_acc_kernel(const uint4* __res
   }
 }
 void k_bn_apply_acc(const void* x, void* y, int rows, int C, int groups, const unsigned long long* acc, const float* gamma, const float* beta, int act, float alpha, float eps,
-                    float* coef, const float* run_mean, const float* run_var, float* g_mean, float* g_var, float decay, cudaStream_t s) {
+                    float* coef, const float* run_mean, const float* run_var, float* g_mean, float* g_var, float decay, cudaStream_t s, int replicas) {
   const size_t smem = sizeof(float) * 2 * groups * C;
   DISPATCH_ACT(act, ACTC, launch_pdl(bn_apply_acc_kernel<ACTC>, dim3(vec4_blocks((size_t)rows * C / 8)), dim3(256), smem, s, (const uint4*)x, (uint4*)y, rows, C, groups, acc, gamma, beta, act, alpha, eps,
-                                     coef, run_mean, run_var, g_mean, g_var, decay));
+                                     coef, run_mean, run_var, g_mean, g_var, decay, replicas));
   LAUNCHED();
 }
 
@@ -489,8 +490,9 @@ void k_bn_bwd_stats_acc(const void* x, const void* eps_out, int rows, int C, int
 template <int ACTC, bool PREMUL>
 __global__ void __launch_bounds__(256, 2) bn_bwd_apply_acc_kernel(const uint4* __restrict__ x, const uint4* __restrict__ eo, uint4* __restrict__ ei, int rows, int C, int groups,
                                                                  const float* __restrict__ coef, int act, float alpha, const unsigned long long* __restrict__ accp,
-                                                                 float* g_gamma, float* g_beta, int want) { pdl_enter();
+                                                                 float* g_gamma, float* g_beta, int want, int replicas) { pdl_enter();
   extern __shared__ float s_k[];
+  const double cnt = (double)rows * replicas;       // sync_bn: global sums; dgamma / dbeta are left as (global sum) / replicas, the gradient all-reduce restores the sum
   const bool writer = blockIdx.x == 0 && want;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     double tb = 0.0, tg = 0.0;
@@ -498,9 +500,9 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_acc_kernel(const uint4* _
       const unsigned long long* a = accp + (size_t)g * 4 * C;
       const double s1 = sacc_read(a, (size_t)C, (size_t)c); double s2 = sacc_read(a + 2 * (size_t)C, (size_t)C, (size_t)c);
       if (PREMUL) s2 = (double)coef[(size_t)(g * 4 + 3) * C + c] * (s2 - (double)coef[(size_t)(g * 4 + 2) * C + c] * s1);      // (sum dy'*z) -> sum dy'*xhat
-      s_k[(g * 2 + 0) * C + c] = (float)(s1 / rows); s_k[(g * 2 + 1) * C + c] = (float)(s2 / rows); tb += s1; tg += s2;
+      s_k[(g * 2 + 0) * C + c] = (float)(s1 / cnt); s_k[(g * 2 + 1) * C + c] = (float)(s2 / cnt); tb += s1; tg += s2;
     }
-    if (writer) { g_beta[c] += (float)tb; g_gamma[c] += (float)tg; }
+    if (writer) { g_beta[c] += (float)(tb / replicas); g_gamma[c] += (float)(tg / replicas); }
   }
   __syncthreads();
   if (!ei) return;
@@ -529,11 +531,11 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_acc_kernel(const uint4* _
   }
 }
 void k_bn_bwd_apply_acc(const void* x, const void* eps_out, void* eps_in, int rows, int C, int groups, const float* coef, int act, float alpha, int premul,
-                        const unsigned long long* acc, float* g_gamma, float* g_beta, int want, cudaStream_t s) {
+                        const unsigned long long* acc, float* g_gamma, float* g_beta, int want, cudaStream_t s, int replicas) {
   const size_t smem = sizeof(float) * 2 * groups * C;
   const dim3 grid(eps_in ? vec4_blocks((size_t)rows * C / 8) : 1);
-  if (premul) { launch_pdl(bn_bwd_apply_acc_kernel<ACT_IDENTITY, true>, grid, dim3(256), smem, s, (const uint4*)x, (const uint4*)eps_out, (uint4*)eps_in, rows, C, groups, coef, act, alpha, acc, g_gamma, g_beta, want); }
-  else { DISPATCH_ACT(act, ACTC, launch_pdl(bn_bwd_apply_acc_kernel<ACTC, false>, grid, dim3(256), smem, s, (const uint4*)x, (const uint4*)eps_out, (uint4*)eps_in, rows, C, groups, coef, act, alpha, acc, g_gamma, g_beta, want)); }
+  if (premul) { launch_pdl(bn_bwd_apply_acc_kernel<ACT_IDENTITY, true>, grid, dim3(256), smem, s, (const uint4*)x, (const uint4*)eps_out, (uint4*)eps_in, rows, C, groups, coef, act, alpha, acc, g_gamma, g_beta, want, replicas); }
+  else { DISPATCH_ACT(act, ACTC, launch_pdl(bn_bwd_apply_acc_kernel<ACTC, false>, grid, dim3(256), smem, s, (const uint4*)x, (const uint4*)eps_out, (uint4*)eps_in, rows, C, groups, coef, act, alpha, acc, g_gamma, g_beta, want, replicas)); }
   LAUNCHED();
 }
 

@@ -213,6 +213,13 @@ class Net:
         """False = the reference's parameter-averaging mode: fit() updates locally, average_parameters() synchronises."""
         check(self.lib.b2g_net_set_grad_allreduce(self.h, int(enabled)))
 
+    def set_sync_bn(self, enabled: bool):
+        """Cross-replica BatchNorm statistics: W ranks x N/W then equals 1 rank x N."""
+        check(self.lib.b2g_net_set_sync_bn(self.h, int(enabled)))
+
+    def set_grad_payload_bf16(self, enabled: bool):
+        check(self.lib.b2g_net_set_grad_payload_bf16(self.h, int(enabled)))
+
     def average_parameters(self):
         """ParameterAveragingTrainingMaster: params and updater state <- mean over ranks (J:325-330)."""
         check(self.lib.b2g_net_average_parameters(self.h))

@@ -198,6 +198,12 @@ int32_t b2g_ctx_comm_destroy(b2g_ctx* ctx);
  * next to the per-update gradient all-reduce north_star mandates. */
 int32_t b2g_net_set_grad_allreduce(b2g_net* net, int32_t enabled);
 int32_t b2g_net_average_parameters(b2g_net* net);
+/* SURVEY.md 8e options.  sync_bn: BatchNorm statistics (forward sums and the two backward reductions) are pooled over all ranks -- the 64-bit
+ * integer accumulators are all-reduced, so every rank derives bit-identical statistics and "W ranks x N/W == 1 rank x N" holds; default off
+ * (= local statistics per replica, what the reference's Spark workers do).  BF16 nets only.
+ * grad_payload_bf16: the gradient all-reduce travels as bf16 (half the bytes); default fp32 (data parallel == single GPU, bit for bit). */
+int32_t b2g_net_set_sync_bn(b2g_net* net, int32_t enabled);
+int32_t b2g_net_set_grad_payload_bf16(b2g_net* net, int32_t enabled);
 /* all-reduce an arbitrary device float buffer on the ctx stream (tests) */
 int32_t b2g_ctx_allreduce_test(b2g_ctx* ctx, float* host_inout, int64_t n);
 
