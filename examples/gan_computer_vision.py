@@ -14,7 +14,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import gan_deeplearning4j_b200 as b
-from gan_deeplearning4j_b200 import data, models as m
+from gan_deeplearning4j_b200 import data, models as m, parallel
 
 PARAMS = {"batchnorm": ("gamma", "beta", "mean", "var"), "conv2d": ("W", "b"), "dense": ("W", "b"), "output": ("W", "b")}
 
@@ -64,7 +64,8 @@ def main():
         if len(x) < n:
             break
         x_fake = gen.output(rng.uniform(-1, 1, (n, z)))                                                                          # J:420
-        dis.fit(x, 1 + soft_real); dis.fit(x_fake, 0 + soft_fake)                                                                # J:414-426 (two minibatches)
+        # J:414-426: the RDD holds two DataSets -> two Spark workers, one minibatch each, parameters AND updater state averaged (J:325-330)
+        parallel.fit_parameter_averaging(dis, [(x, 1 + soft_real), (x_fake, 0 + soft_fake)], averaging_frequency=10)
         copy_params(gan, [dict(s, name=s["name"].replace("dis_", "gan_dis_", 1)) for s in dis_s], dis,
                     lambda nm: nm.replace("gan_dis_", "dis_", 1), {k.replace("dis_", "gan_dis_", 1): v for k, v in cin_dis.items()})  # J:429-460
         gan.fit(rng.uniform(-1, 1, (n, z)), np.ones((n, 1)))                                                                     # J:465-471

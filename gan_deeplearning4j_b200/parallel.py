@@ -43,3 +43,30 @@ def attach_communicator(ctx, dist, rank: int, world: int):
         return ctx
     ctx.comm_init(world, rank, exchange_unique_id(dist, rank, comm_unique_id))
     return ctx
+
+
+def fit_parameter_averaging(net, datasets, averaging_frequency: int = 1):
+    """SparkComputationGraph.fit(rdd) with a ParameterAveragingTrainingMaster in ONE process (J:325-333, J:426; Python/gan.ipynb:177-187):
+    every DataSet of the RDD goes to its own worker; each worker starts from the broadcast (parameters, updater state, iteration count), fits
+    its minibatches -- at most `averaging_frequency` of them between two averagings -- and the driver then averages parameters AND updater
+    state over the workers.  One native net plays the workers in turn (snapshot / restore), exactly what local[4] Spark does with model copies.
+    `datasets`: list of workers, each a (x, y) pair or a list of (x, y) minibatches.  Returns the workers' last scores."""
+    import numpy as np
+    workers = [[d] if isinstance(d, tuple) else list(d) for d in datasets]
+    if len(workers) == 1 and len(workers[0]) == 1:
+        return [net.fit(*workers[0][0])]
+    scores = [None] * len(workers)
+    longest = max(len(w) for w in workers)
+    for start in range(0, longest, max(1, averaging_frequency)):
+        p0, s0, it0 = net.params(), net.updater_state(), net.iteration()
+        psum, ssum, used, steps = np.zeros_like(p0, np.float64), np.zeros_like(s0, np.float64), 0, 0
+        for wi, w in enumerate(workers):
+            mine = w[start:start + max(1, averaging_frequency)]
+            if not mine:
+                continue
+            net.set_params(p0); net.set_updater_state(s0); net.set_iteration(it0)
+            for x, y in mine:
+                scores[wi] = net.fit(x, y)
+            psum += net.params(); ssum += net.updater_state(); used += 1; steps = max(steps, len(mine))
+        net.set_params((psum / used).astype(np.float32)); net.set_updater_state((ssum / used).astype(np.float32)); net.set_iteration(it0 + steps)
+    return scores

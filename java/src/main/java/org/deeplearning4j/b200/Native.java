@@ -25,6 +25,12 @@ public final class Native {
     public static native int netGetParams(long net, long hostAddr, long n);
     public static native int netSetParams(long net, long hostAddr, long n);
     public static native int netGetUpdaterState(long net, long hostAddr, long n);
+    public static native int netSetUpdaterState(long net, long hostAddr, long n);
+    public static native int netGetIteration(long net, long outAddr);
+    public static native int netSetIteration(long net, long iteration);
+    public static native int netSimtGemmCalls(long net, long outAddr);
+    public static native int netSetSyncBn(long net, int enabled);
+    public static native int netSetGradPayloadBf16(long net, int enabled);
     public static native int netOutput(long net, long xAddr, int batch, int train, long outAddr);
     public static native int netFit(long net, long xAddr, long yAddr, int batch, long scoreAddr);
     public static native int ganCreate(long gen, long dis, int fakeBnTrain, int useGraph, long outHandleAddr);

@@ -48,6 +48,10 @@ public class ComputationGraph {
     /** Updater state in the library's [state0 | state1] order (RmsProp cache / Adam m, then Adam v), 2 x numParams values. */
     public INDArray updaterState() { int n = 2 * (int) numParams(); FloatBuffer b = Native.direct(4 * n).asFloatBuffer(); Native.check(Native.netGetUpdaterState(net, Native.address(b), n)); float[] d = new float[n]; b.get(d); return new INDArray(d, 1, n); }
     /** The layer list as JSON (this library's specification, not DL4J's Jackson schema) -- ModelSerializer's configuration.json entry. */
+    public void setUpdaterState(INDArray st) { Native.check(Native.netSetUpdaterState(net, Native.address(Native.floats(st.data)), st.length())); }
+    /** BaseMultiLayerUpdater's iteration count (Adam's t - 1); part of a checkpoint and of the state a Spark worker starts from. */
+    public long getIterationCount() { ByteBuffer o = Native.direct(8); Native.check(Native.netGetIteration(net, Native.address(o))); return o.getLong(0); }
+    public void setIterationCount(long it) { Native.check(Native.netSetIteration(net, it)); }
     public String configurationJson() {
         StringBuilder s = new StringBuilder("{\"format\": \"b200gan layer specs\", \"layers\": [");
         for (int i = 0; i < layers.size(); ++i) { Layer l = layers.get(i); s.append(i == 0 ? "" : ", ").append("{\"name\": \"").append(l.name).append("\", \"type\": ").append(l.type).append(", \"nIn\": ").append(l.nIn).append(", \"nOut\": ").append(l.nOut).append("}"); }

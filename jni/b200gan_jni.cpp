@@ -39,6 +39,12 @@ FN(netGetParam)(JNIEnv_*, jclass, jlong net, jlong layerNameAddr, jlong paramNam
 FN(netGetParams)(JNIEnv_*, jclass, jlong net, jlong hostAddr, jlong n) { return b2g_net_get_params(P(b2g_net*, net), P(float*, hostAddr), n); }
 FN(netSetParams)(JNIEnv_*, jclass, jlong net, jlong hostAddr, jlong n) { return b2g_net_set_params(P(b2g_net*, net), P(const float*, hostAddr), n); }
 FN(netGetUpdaterState)(JNIEnv_*, jclass, jlong net, jlong hostAddr, jlong n) { return b2g_net_get_updater_state(P(b2g_net*, net), P(float*, hostAddr), n); }
+FN(netSetUpdaterState)(JNIEnv_*, jclass, jlong net, jlong hostAddr, jlong n) { return b2g_net_set_updater_state(P(b2g_net*, net), P(const float*, hostAddr), n); }
+FN(netGetIteration)(JNIEnv_*, jclass, jlong net, jlong outAddr) { return b2g_net_get_iteration(P(b2g_net*, net), P(int64_t*, outAddr)); }
+FN(netSetIteration)(JNIEnv_*, jclass, jlong net, jlong it) { return b2g_net_set_iteration(P(b2g_net*, net), it); }
+FN(netSimtGemmCalls)(JNIEnv_*, jclass, jlong net, jlong outAddr) { return b2g_net_simt_gemm_calls(P(b2g_net*, net), P(uint64_t*, outAddr)); }
+FN(netSetSyncBn)(JNIEnv_*, jclass, jlong net, jint enabled) { return b2g_net_set_sync_bn(P(b2g_net*, net), enabled); }
+FN(netSetGradPayloadBf16)(JNIEnv_*, jclass, jlong net, jint enabled) { return b2g_net_set_grad_payload_bf16(P(b2g_net*, net), enabled); }
 FN(netOutput)(JNIEnv_*, jclass, jlong net, jlong xAddr, jint batch, jint train, jlong outAddr) {
   return b2g_net_output(P(b2g_net*, net), P(const float*, xAddr), batch, train, P(float*, outAddr));
 }

@@ -638,3 +638,87 @@ def test_fp32_gan_step_matches_golden_fixture(b200):
         assert rel_err(bD.params(), gold[f"d_params{it}"]) < 2 * TOL, it
         assert rel_err(bG.params(), gold[f"g_params{it}"]) < 2 * TOL, it
     gan.close(); bG.close(); bD.close()
+
+
+def test_checkpoint_resume_equals_uninterrupted_run(b200, tmp_path):
+    """ModelSerializer.writeModel / restore (J:606-618) with the updater state AND the iteration counter: N steps, save, restore into a
+    fresh net, M more steps == N+M uninterrupted steps, bit for bit (Adam's bias correction depends on t: ADVICE round 1)."""
+    b, ctx = b200
+    from gan_deeplearning4j_b200 import models as m
+    specs = m.dcgan_discriminator(16, 8, 3, lr=1e-2)
+    rng = np.random.default_rng(9)
+    xs = [rng.uniform(-1, 1, (8, 3, 16, 16)).astype(np.float32) for _ in range(5)]; ys = [rng.uniform(0, 1, (8, 1)).astype(np.float32) for _ in range(5)]
+    for prec in (b.FP32, b.BF16):
+        a = b.Net(ctx, specs, (3, 16, 16), max_batch=8, precision=prec, xent_clip_eps=0.0, seed=3)
+        for i in range(5):
+            a.fit(xs[i], ys[i])
+        c = b.Net(ctx, specs, (3, 16, 16), max_batch=8, precision=prec, xent_clip_eps=0.0, seed=3)
+        for i in range(3):
+            c.fit(xs[i], ys[i])
+        assert c.iteration() == 3
+        path = str(tmp_path / f"ckpt_{prec}.zip"); c.save(path)
+        r = b.Net(ctx, specs, (3, 16, 16), max_batch=8, precision=prec, xent_clip_eps=0.0, seed=99)       # different init: everything must come from the file
+        meta = r.restore(path)
+        assert r.iteration() == 3 and meta["meta"]["iteration"] == 3
+        for i in range(3, 5):
+            r.fit(xs[i], ys[i])
+        assert np.array_equal(r.params(), a.params()) and np.array_equal(r.updater_state(), a.updater_state()) and r.iteration() == 5
+        # without the counter the resumed Adam restarts its bias correction: the run must diverge (this is what the counter is for)
+        w = b.Net(ctx, specs, (3, 16, 16), max_batch=8, precision=prec, xent_clip_eps=0.0, seed=99)
+        w.set_params(c.params()); w.set_updater_state(c.updater_state())
+        for i in range(3, 5):
+            w.fit(xs[i], ys[i])
+        assert not np.array_equal(w.params(), a.params())
+        for net in (a, c, r, w):
+            net.close()
+
+
+def test_xavier_init_statistics(b200):
+    """WeightInit.XAVIER (J:127): W ~ N(0, 2/(fanIn+fanOut)) with conv fanIn = nIn*kH*kW, fanOut = nOut*kH*kW/(sH*sW); biases 0;
+    BatchNorm gamma 1, beta 0, mean 0, var 1 -- the formula the oracle's Layer.init restates (dl4j_oracle.Conv2D.fans)."""
+    b, ctx = b200
+    from gan_deeplearning4j_b200 import models as m
+    for specs, shape, onet in ((m.dcgan_discriminator(64, 64, 3), (3, 64, 64), o.dcgan_discriminator(64, 64, 3)), (m.dcgan_generator(64, 100, 64, 3), (100,), o.dcgan_generator(64, 100, 64, 3))):
+        net = b.Net(ctx, specs, shape, max_batch=2, precision=b.FP32, seed=666)
+        other = b.Net(ctx, specs, shape, max_batch=2, precision=b.FP32, seed=667)
+        for s, l in zip(specs, onet.layers):
+            if s["type"] in ("conv2d", "deconv2d"):
+                fi, fo = l.fans()
+                w = net.get_param(s["name"], "W", int(np.prod(l.params["W"].shape)))
+                want = np.sqrt(2.0 / (fi + fo))
+                if w.size >= 4096:
+                    assert abs(w.std() / want - 1.0) < 0.05 and abs(w.mean()) < 0.05 * want, (s["name"], w.std(), want)
+                assert not np.array_equal(w, other.get_param(s["name"], "W", w.size))          # the seed matters
+                if s.get("has_bias", True):
+                    assert np.all(net.get_param(s["name"], "b", s["n_out"]) == 0)
+            elif s["type"] == "batchnorm":
+                c = l.params["gamma"].size
+                assert np.all(net.get_param(s["name"], "gamma", c) == 1) and np.all(net.get_param(s["name"], "beta", c) == 0)
+                assert np.all(net.get_param(s["name"], "mean", c) == 0) and np.all(net.get_param(s["name"], "var", c) == 1)
+        again = b.Net(ctx, specs, shape, max_batch=2, precision=b.FP32, seed=666)
+        assert np.array_equal(again.params(), net.params())                                    # .seed(666): reproducible
+        for n_ in (net, other, again):
+            n_.close()
+
+
+def test_single_process_parameter_averaging_matches_oracle(b200):
+    """parallel.fit_parameter_averaging == SparkComputationGraph.fit with a ParameterAveragingTrainingMaster (J:325-333, J:426): two workers,
+    one minibatch each, parameters AND updater state averaged -- against the oracle's parameter_average of two fitted copies (FP32 mode)."""
+    import copy
+    b, ctx = b200
+    from gan_deeplearning4j_b200 import models as m, parallel
+    specs = m.reference_discriminator(0.002)
+    rng = np.random.default_rng(17)
+    onet = oracle_from_specs(specs, (1, 28, 28), grad_clip=1.0); randomize(onet, rng)
+    bnet = b.Net(ctx, specs, (1, 28, 28), max_batch=8, precision=b.FP32, grad_clip=1.0)
+    push_params(onet, bnet)
+    d = [(rng.uniform(0, 1, (8, 1, 28, 28)), 1 + 0.05 * rng.standard_normal((8, 1))), (rng.uniform(0, 1, (8, 1, 28, 28)), 0.05 * rng.standard_normal((8, 1)))]
+    w0, w1 = copy.deepcopy(onet), copy.deepcopy(onet)
+    w0.fit(*d[0]); w1.fit(*d[1])
+    o.parameter_average([w0, w1], onet)
+    parallel.fit_parameter_averaging(bnet, d, averaging_frequency=10)
+    # RmsProp(lr, 1e-8, 1e-8) behaves like lr*sign(g): elements whose gradient is numerically zero may land one lr apart (see DESIGN.md 1)
+    diff = np.abs(bnet.params() - onet.params_flat())
+    assert diff.max() <= 2 * 0.002 + 1e-6 and (diff > 1e-5).mean() < 0.02, (diff.max(), (diff > 1e-5).mean())
+    assert bnet.iteration() == 1
+    bnet.close()
