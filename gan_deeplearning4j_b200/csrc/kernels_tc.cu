@@ -161,7 +161,8 @@ struct TcSmem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int STAT_OFF = BAR_OFF + 256;
-  static constexpr int TOTAL = STAT_OFF + ((EPI == EPI_STATS || EPI == EPI_BNBWD) ? 4 * 2 * BN * 4 : 0) + 1024;   // + barriers + statistics + alignment slack
+  static constexpr int STG_OFF = STAT_OFF + ((EPI == EPI_STATS || EPI == EPI_BNBWD) ? 4 * 2 * BN * 4 : 0);
+  static constexpr int TOTAL = STG_OFF + (BN >= 32 ? 4 * 2048 : 0) + 1024;   // + barriers + statistics + epilogue staging + alignment slack
 };
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }    // the four epilogue warps only
@@ -180,26 +181,58 @@ __device__ __forceinline__ void warp_colsum32(float (&a)[32], int lane) {
   }
 }
 
-// One 128-row x BN-column accumulator tile: TMEM -> registers -> epilogue arithmetic -> bf16 -> 16-byte stores of the NHWC channel run.
+// One 128-row x BN-column accumulator tile: TMEM -> registers -> epilogue arithmetic -> bf16 -> global.
 // taddr = TMEM address of (this warp's lane quadrant, first column of the tile); roff = element offset of (pixel, first channel) in `out`.
+// A thread owns one accumulator row, but a warp instruction in which every lane touches its own row costs the load/store unit 32
+// wavefronts of 16 B each.  Global traffic therefore goes through a per-warp 2 KB staging area `stg` ([32 rows][4 x 16 B], XOR-swizzled so
+// that both access patterns are bank-conflict free): four lanes cover the 64 B of one row, a warp instruction covers 8 rows = 16 full
+// sectors.  The same transposition brings the auxiliary operands (forward output y, BN input z) in, and the loads for the next 32 columns
+// are issued before the arithmetic of the current ones so that their latency hides behind it.
+static constexpr int EPI_STG_BYTES = 4 * 2048;
 template <int BN, int EPI, bool AFFINE>
-__device__ __forceinline__ void epi_tile(const TcConvParams& p, uint32_t taddr, size_t roff, int nb0, int group, float* sst, int q, int lane, int ep_tid) {
+__device__ __forceinline__ void epi_tile(const TcConvParams& p, uint32_t taddr, size_t roff, int nb0, int group, float* sst, uint4* stg, int q, int lane, int ep_tid) {
   constexpr bool stats = EPI == EPI_STATS || EPI == EPI_BNBWD;
-  __nv_bfloat16* orow = p.out + roff;
   const bool has_bias = p.bias != nullptr;
+  const int sub = lane >> 2, cq = lane & 3, sx = (lane >> 1) & 3;
+  size_t roff_i[4];                      // element offsets of the rows this lane serves in the transposed pattern: row i*8 + lane/4
+#pragma unroll
+  for (int i = 0; i < 4; ++i) roff_i[i] = __shfl_sync(0xffffffffu, (unsigned long long)roff, i * 8 + sub) + cq * 8;
+  uint4 gy[4], gz[4];
+  if constexpr (EPI >= EPI_BNBWD) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) gy[i] = *reinterpret_cast<const uint4*>(p.aux + roff_i[i]);
+  }
+  if constexpr (EPI == EPI_BNBWD) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) gz[i] = *reinterpret_cast<const uint4*>(p.aux2 + roff_i[i]);
+  }
 #pragma unroll 1
   for (int c0 = 0; c0 < BN; c0 += 32) {
     uint32_t v[32];
     uint4 ax[4], az[4];
     if constexpr (EPI >= EPI_BNBWD) {
-      const uint4* ap = reinterpret_cast<const uint4*>(p.aux + roff + c0);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) ax[i] = ap[i];
+      for (int i = 0; i < 4; ++i) { const int r = i * 8 + sub; stg[r * 4 + (cq ^ ((r >> 1) & 3))] = gy[i]; }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ax[j] = stg[lane * 4 + (j ^ sx)];
+      __syncwarp();
+      if (c0 + 32 < BN) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gy[i] = *reinterpret_cast<const uint4*>(p.aux + roff_i[i] + c0 + 32);
+      }
     }
     if constexpr (EPI == EPI_BNBWD) {
-      const uint4* zp = reinterpret_cast<const uint4*>(p.aux2 + roff + c0);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) az[i] = zp[i];
+      for (int i = 0; i < 4; ++i) { const int r = i * 8 + sub; stg[r * 4 + (cq ^ ((r >> 1) & 3))] = gz[i]; }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) az[j] = stg[lane * 4 + (j ^ sx)];
+      __syncwarp();
+      if (c0 + 32 < BN) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gz[i] = *reinterpret_cast<const uint4*>(p.aux2 + roff_i[i] + c0 + 32);
+      }
     }
     tmem_ld32(taddr + (uint32_t)c0, v);
     tmem_ld_wait();
@@ -252,9 +285,12 @@ __device__ __forceinline__ void epi_tile(const TcConvParams& p, uint32_t taddr, 
       packed[j] = *reinterpret_cast<uint32_t*>(&h);
       if constexpr (stats) { const float2 r = __bfloat1622float2(h); o[2 * j] = r.x; o[2 * j + 1] = r.y; }      // statistics of what is stored
     }
-    uint4* dst = reinterpret_cast<uint4*>(orow + c0);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+    for (int j = 0; j < 4; ++j) stg[lane * 4 + (j ^ sx)] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const int r = i * 8 + sub; *reinterpret_cast<uint4*>(p.out + roff_i[i] + c0) = stg[r * 4 + (cq ^ ((r >> 1) & 3))]; }
+    __syncwarp();
     if constexpr (stats) {
       if constexpr (EPI == EPI_STATS) {
 #pragma unroll
@@ -358,25 +394,29 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ CU
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
+      // one thread feeds the whole pipeline: no integer division inside the loop (ring slot, channel chunk and tap advance as counters)
+      const int ybase = p.mode == 0 ? y0 * p.SH : y0;
+      int s = 0, ch = 0, ta = 0, tb = 0; uint32_t ph = 0;
+      int ax, dy_, wtap; tap_coords(p, 0, 0, py, px, ax, dy_, wtap);
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
-        const int ch = kb % p.chunks, tap = kb / p.chunks, ta = tap / p.taps_w, tb = tap % p.taps_w;
-        int ax, dy_, wtap; tap_coords(p, ta, tb, py, px, ax, dy_, wtap);
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
         mbar_expect_tx(bar_full + 8 * s, S::STAGE_BYTES);
-        tma_load_4d(smem_base + s * S::STAGE_BYTES, &tmA, bar_full + 8 * s, ch * 64, ax, (p.mode == 0 ? y0 * p.SH : y0) + dy_, n0);
+        tma_load_4d(smem_base + s * S::STAGE_BYTES, &tmA, bar_full + 8 * s, ch * 64, ax, ybase + dy_, n0);
         load_b_tile<BN>(p, &tmB, smem_base + s * S::STAGE_BYTES + S::A_BYTES, bar_full + 8 * s, ch, wtap, nb0);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+        if (++ch == p.chunks) { ch = 0; if (++tb == p.taps_w) { tb = 0; ++ta; } tap_coords(p, ta, tb, py, px, ax, dy_, wtap); }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
+      int s = 0; uint32_t ph = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(bar_full + 8 * s, ph);
         tc_fence_after();
         mma_kblock<BN>(tmem_base, smem_base + s * S::STAGE_BYTES, smem_base + s * S::STAGE_BYTES + S::A_BYTES, PS ? 0 : p.b_mn, (uint32_t)kb);
         umma_commit(bar_empty + 8 * s);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
       umma_commit(bar_accum);
     }
@@ -423,7 +463,7 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ CU
       }
     } else {
       const int group = p.imgs_per_group > 0 ? n0 / p.imgs_per_group : 0;
-      epi_tile<BN, EPI, AFFINE>(p, tmem_base + ((uint32_t)(q * 32) << 16), pix * p.OC + nb0, nb0, group, sst, q, lane, (int)threadIdx.x - 64);
+      epi_tile<BN, EPI, AFFINE>(p, tmem_base + ((uint32_t)(q * 32) << 16), pix * p.OC + nb0, nb0, group, sst, reinterpret_cast<uint4*>(smem_gen + S::STG_OFF) + q * 128, q, lane, (int)threadIdx.x - 64);
     }
     tc_fence_before();
   }
@@ -446,7 +486,8 @@ struct TcSmemP {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int STAT_OFF = BAR_OFF + 256;
-  static constexpr int TOTAL = STAT_OFF + ((EPI == EPI_STATS || EPI == EPI_BNBWD) ? 4 * 2 * BN * 4 : 0) + 1024;
+  static constexpr int STG_OFF = STAT_OFF + ((EPI == EPI_STATS || EPI == EPI_BNBWD) ? 4 * 2 * BN * 4 : 0);
+  static constexpr int TOTAL = STG_OFF + 4 * 2048 + 1024;
 };
 
 template <int BN, int STAGES, int MT, int EPI, bool AFFINE>
@@ -486,41 +527,42 @@ __global__ void __launch_bounds__(192) tc_conv_persistent_kernel(const __grid_co
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t kiter = 0;
+      int s = 0; uint32_t ph = 0;        // ring position: counters, no integer division inside the loop
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         int mg, nb0, py, px; decode(item, mg, nb0, py, px);
         int n0[MT], y0[MT];
 #pragma unroll
-        for (int m = 0; m < MT; ++m) tile_origin(mg * MT + m, n0[m], y0[m]);
-        for (int kb = 0; kb < num_kb; ++kb, ++kiter) {
-          const int s = kiter % STAGES; const uint32_t ph = (kiter / STAGES) & 1;
-          const int ch = kb % p.chunks, tap = kb / p.chunks, ta = tap / p.taps_w, tb = tap % p.taps_w;
-          int ax, dy_, wtap; tap_coords(p, ta, tb, py, px, ax, dy_, wtap);
+        for (int m = 0; m < MT; ++m) { tile_origin(mg * MT + m, n0[m], y0[m]); if (p.mode == 0) y0[m] *= p.SH; }
+        int ch = 0, ta = 0, tb = 0;
+        int ax, dy_, wtap; tap_coords(p, 0, 0, py, px, ax, dy_, wtap);
+        for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
           mbar_expect_tx(bar_full + 8 * s, S::STAGE_BYTES);
           const uint32_t st = smem_base + s * S::STAGE_BYTES;
 #pragma unroll
-          for (int m = 0; m < MT; ++m) tma_load_4d(st + m * 16384, &tmA, bar_full + 8 * s, ch * 64, ax, (p.mode == 0 ? y0[m] * p.SH : y0[m]) + dy_, n0[m]);
+          for (int m = 0; m < MT; ++m) tma_load_4d(st + m * 16384, &tmA, bar_full + 8 * s, ch * 64, ax, y0[m] + dy_, n0[m]);
           load_b_tile<BN>(p, &tmB, st + S::A_BYTES, bar_full + 8 * s, ch, wtap, nb0);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+          if (++ch == p.chunks) { ch = 0; if (++tb == p.taps_w) { tb = 0; ++ta; } tap_coords(p, ta, tb, py, px, ax, dy_, wtap); }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      uint32_t kiter = 0, it = 0;
+      uint32_t it = 0, ph = 0; int s = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
         const uint32_t acc = it & 1, aph = (it >> 1) & 1;
         mbar_wait(bar_tempty + 8 * acc, aph ^ 1);          // the epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t tacc = tmem_base + acc * ACC_COLS;
-        for (int kb = 0; kb < num_kb; ++kb, ++kiter) {
-          const int s = kiter % STAGES; const uint32_t ph = (kiter / STAGES) & 1;
+        for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
           const uint32_t st = smem_base + s * S::STAGE_BYTES;
 #pragma unroll
           for (int m = 0; m < MT; ++m) mma_kblock<BN>(tacc + m * BN, st + m * 16384, st + S::A_BYTES, p.b_mn, (uint32_t)kb);
           umma_commit(bar_empty + 8 * s);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         umma_commit(bar_tfull + 8 * acc);
       }
@@ -542,7 +584,7 @@ __global__ void __launch_bounds__(192) tc_conv_persistent_kernel(const __grid_co
         if (p.mode == 0) pix = ((size_t)n * p.outH + gy) * p.outW + gx;
         else pix = ((size_t)n * p.outH + 2 * gy + py) * p.outW + 2 * gx + px;
         const int group = p.imgs_per_group > 0 ? n0 / p.imgs_per_group : 0;
-        epi_tile<BN, EPI, AFFINE>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + m * BN), pix * p.OC + nb0, nb0, group, sst, q, lane, (int)threadIdx.x - 64);
+        epi_tile<BN, EPI, AFFINE>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + m * BN), pix * p.OC + nb0, nb0, group, sst, reinterpret_cast<uint4*>(smem_gen + S::STG_OFF) + q * 128, q, lane, (int)threadIdx.x - 64);
       }
       // all of this warp's TMEM reads of the stage have completed (tcgen05.wait::ld above): hand the accumulator back
       tc_fence_before();
@@ -552,6 +594,126 @@ __global__ void __launch_bounds__(192) tc_conv_persistent_kernel(const __grid_co
   }
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TCOLS); }
+}
+
+// ------------------------------------------------------------------ dgrad (transposed-conv forward) with a shared-memory halo ------
+// The phase-form kernels above fetch the dy tile once per (phase, tap): 16 times.  For the large-grid layers (dy grid >= 16 x 8 per image,
+// 64 output channels: D2's input gradient, the generator's last BatchNorm'd transposed conv) this kernel keeps the 18 x 10 halo of a
+// 16 x 8 dy tile in shared memory -- one TMA box per 64-channel chunk, zero-filled outside the image -- and feeds all 4 phases x 4 taps
+// through shifted descriptors (tools/exp_desc.cu: the 128B swizzle is a function of the absolute shared-memory address), accumulating the
+// four phases in four 64-column TMEM accumulators (x 2 stages: the epilogue of tile i overlaps the MMAs of tile i+1).  Per tile the
+// activations cost 46 KB instead of 512 KB out of L2.  The weights (MN-major tiles from the straight [O][16][C] copy) stream through a
+// 3-deep ring of 32 KB stages = the four taps of one (chunk, phase): measured (B2G_DH_DBG experiments, round 2) a pipeline step costs the
+// single-thread producer / issuer ~600 cycles whatever it carries, so a step must carry >= 16 MMAs (a first version with one 8 KB tap per
+// step ran at 30 us for 8.6 GFLOP; loads off: 31 us, MMAs off: 21 us).  Same epilogues as the other conv kernels (epi_tile).
+static constexpr int DH_HALO_BYTES = 18 * 10 * 128, DH_CHUNK_BYTES = 23 * 1024, DH_HSTAGE_BYTES = 2 * DH_CHUNK_BYTES, DH_WSTAGES = 3, DH_W_BYTES = 4 * 8192;
+static constexpr int DH_W_OFF = 2 * DH_HSTAGE_BYTES, DH_BAR_OFF = DH_W_OFF + DH_WSTAGES * DH_W_BYTES, DH_STAT_OFF = DH_BAR_OFF + 256, DH_STG_OFF = DH_STAT_OFF + 4 * 2 * 64 * 4, DH_SMEM = DH_STG_OFF + 4 * 2048 + 1024;
+
+// phase (py, px) x tap (ta, tb) of the 4x4 s2 p1 transposed conv -> filter tap index r*4+sx and the dy offset (dyr, dxc), as compile-time
+// functions so that the fully unrolled issue loops carry no index arithmetic (the issuing thread's scalar instructions are the bottleneck)
+__host__ __device__ constexpr int dh_r(int pyx, int t) { return pyx == 0 ? (t == 0 ? 1 : 3) : (t == 0 ? 0 : 2); }
+__host__ __device__ constexpr int dh_d(int pyx, int t) { return pyx == 0 ? (t == 0 ? 0 : -1) : (t == 0 ? 1 : 0); }
+template <int EPI, bool AFFINE>
+__global__ void __launch_bounds__(192) tc_dgrad_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcConvParams p,
+                                                             int tiles_x, int tiles_y, int total_tiles, int dbg) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_hfull = smem_base + DH_BAR_OFF, bar_hempty = bar_hfull + 16, bar_wfull = bar_hempty + 16, bar_wempty = bar_wfull + 8 * DH_WSTAGES;
+  const uint32_t bar_tfull = bar_wempty + 8 * DH_WSTAGES, bar_tempty = bar_tfull + 16;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + DH_BAR_OFF + 8 * (2 + 2 + 2 * DH_WSTAGES + 2 + 2));
+  float* sst = reinterpret_cast<float*>(smem_gen + DH_STAT_OFF);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunks = p.chunks, per_img = tiles_x * tiles_y, nsteps = 4 * chunks;      // a step = (chunk, phase): 4 taps
+  if (warp == 0 && lane == 0) {
+    prefetch_map(&tmA); prefetch_map(&tmB);
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_hfull + 8 * i, 1); mbar_init(bar_hempty + 8 * i, 1); mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4); }
+    for (int i = 0; i < DH_WSTAGES; ++i) { mbar_init(bar_wfull + 8 * i, 1); mbar_init(bar_wempty + 8 * i, 1); }
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(smem_u32((const void*)tmem_slot), 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();      // single-wave grid
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t hit = 0, wit = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++hit) {
+        const int hs = hit & 1; const uint32_t hph = (hit >> 1) & 1;
+        const int n = tile / per_img, r = tile % per_img, y0 = (r / tiles_x) * 16, x0 = (r % tiles_x) * 8;
+        mbar_wait(bar_hempty + 8 * hs, hph ^ 1);
+        mbar_expect_tx(bar_hfull + 8 * hs, (uint32_t)chunks * DH_HALO_BYTES);
+        for (int ch = 0; ch < chunks; ++ch) tma_load_4d(smem_base + hs * DH_HSTAGE_BYTES + ch * DH_CHUNK_BYTES, &tmA, bar_hfull + 8 * hs, ch * 64, x0 - 1, y0 - 1, n);
+        for (int ch = 0; ch < chunks; ++ch) {
+#pragma unroll
+          for (int ph = 0; ph < 4; ++ph, ++wit) {
+            const int ws = wit % DH_WSTAGES; const uint32_t wph = (wit / DH_WSTAGES) & 1;
+            mbar_wait(bar_wempty + 8 * ws, wph ^ 1);
+            if (dbg == 1) { mbar_arrive(bar_wfull + 8 * ws); continue; }       // timing experiment: no weight loads
+            mbar_expect_tx(bar_wfull + 8 * ws, DH_W_BYTES);
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              tma_load_3d(smem_base + DH_W_OFF + ws * DH_W_BYTES + t * 8192, &tmB, bar_wfull + 8 * ws, 0, dh_r(ph >> 1, t >> 1) * 4 + dh_r(ph & 1, t & 1), ch * 64);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, 64, 0, 1);
+      uint32_t hit = 0, wit = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++hit) {
+        const int hs = hit & 1; const uint32_t hph = (hit >> 1) & 1, acc = hit & 1, aph = (hit >> 1) & 1;
+        mbar_wait(bar_tempty + 8 * acc, aph ^ 1);
+        mbar_wait(bar_hfull + 8 * hs, hph);
+        tc_fence_after();
+        for (int ch = 0; ch < chunks; ++ch) {
+          const uint64_t abase = desc_kmajor_sw128_sbo(smem_base + hs * DH_HSTAGE_BYTES + ch * DH_CHUNK_BYTES, 1280);
+#pragma unroll
+          for (int ph = 0; ph < 4; ++ph, ++wit) {
+            const int ws = wit % DH_WSTAGES; const uint32_t wph = (wit / DH_WSTAGES) & 1;
+            mbar_wait(bar_wfull + 8 * ws, wph);
+            tc_fence_after();
+            const uint64_t bbase = desc_mnmajor_sw128(smem_base + DH_W_OFF + ws * DH_W_BYTES, 8192);
+            if (dbg != 2)       // timing experiment 2: loads without MMAs
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+#pragma unroll
+              for (int k = 0; k < 4; ++k)      // descriptor start-address field counts 16-byte units: halo row = 8 units, K step = 2 units; weight tap = 512, K step = 128
+                umma_bf16(tmem_base + acc * 256 + ph * 64, abase + (uint64_t)(((1 + dh_d(ph >> 1, t >> 1)) * 10 + (1 + dh_d(ph & 1, t & 1))) * 8 + 2 * k),
+                          bbase + (uint64_t)(t * 512 + k * 128), idesc, (uint32_t)(ch | t | k));
+            umma_commit(bar_wempty + 8 * ws);
+          }
+        }
+        umma_commit(bar_hempty + 8 * hs);
+        umma_commit(bar_tfull + 8 * acc);
+      }
+    }
+  } else {
+    const int q = warp & 3, row = q * 32 + lane, yy = row >> 3, xx = row & 7;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+      const int n = tile / per_img, r = tile % per_img, gy = (r / tiles_x) * 16 + yy, gx = (r % tiles_x) * 8 + xx;
+      const int group = p.imgs_per_group > 0 ? n / p.imgs_per_group : 0;
+      mbar_wait(bar_tfull + 8 * acc, aph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ph = 0; ph < 4; ++ph) {
+        const size_t pix = ((size_t)n * p.outH + 2 * gy + (ph >> 1)) * p.outW + 2 * gx + (ph & 1);
+        epi_tile<64, EPI, AFFINE>(p, tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + ph * 64, pix * p.OC, 0, group, sst, reinterpret_cast<uint4*>(smem_gen + DH_STG_OFF) + q * 128, q, lane, (int)threadIdx.x - 64);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+    }
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 // ------------------------------------------------------------------ host side ------------------------------
@@ -697,9 +859,29 @@ int k_tc_dgrad(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat16* 
   cuuint64_t strides[3] = {(cuuint64_t)g.O * 2, (cuuint64_t)g.OW * g.O * 2, (cuuint64_t)g.OH * g.OW * g.O * 2};
   cuuint32_t box[4] = {64, (cuuint32_t)p.Wt, (cuuint32_t)p.Ht, (cuuint32_t)p.Nt};
   cuuint32_t es[4] = {1, 1, 1, 1};
+  if (weight_map(&tmB, w, g.O, 16, g.C, 64)) return -1;
+  static int halo = -1; if (halo < 0) { const char* e = getenv("B2G_DGRAD_HALO"); halo = (e && e[0] == '0') ? 0 : 1; }
+  if (halo && g.C == 64 && g.O / 64 <= 2 && g.OH % 16 == 0 && g.OW % 8 == 0) {      // large dy grid, 64 output channels: halo-resident kernel
+    box[1] = 10; box[2] = 18; box[3] = 1;
+    if (make_map_bf16(&tmA, dy, 4, dims, strides, box, es)) return -1;
+    const int tx = g.OW / 8, ty = g.OH / 16, total = g.N * tx * ty;
+    static int sms = 0; if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, tc_device());
+    const dim3 hgrid((unsigned)(total < sms ? total : sms));
+    g_tc_last_kernel = "tc_dgrad_halo_kernel";
+    static int dbgv = -1; if (dbgv < 0) { const char* e = getenv("B2G_DH_DBG"); dbgv = e ? atoi(e) : 0; }
+#define B2G_DH_LAUNCH(E, A) do { TC_SET_SMEM_ONCE((tc_dgrad_halo_kernel<E, A>), DH_SMEM); launch_pdl(tc_dgrad_halo_kernel<E, A>, hgrid, dim3(192), (size_t)DH_SMEM, s, tmA, tmB, p, tx, ty, total, dbgv); } while (0)
+    switch (p.epi) {
+      case EPI_STATS: B2G_DH_LAUNCH(EPI_STATS, false); break;
+      case EPI_BNBWD: B2G_DH_LAUNCH(EPI_BNBWD, false); break;
+      case EPI_ACTBWD: B2G_DH_LAUNCH(EPI_ACTBWD, false); break;
+      default: if (p.scale && p.bias) B2G_DH_LAUNCH(EPI_PLAIN, true); else B2G_DH_LAUNCH(EPI_PLAIN, false);
+    }
+#undef B2G_DH_LAUNCH
+    LAUNCHED();
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
+  }
   if (make_map_bf16(&tmA, dy, 4, dims, strides, box, es)) return -1;
   dim3 grid((unsigned)(g.N * g.OH * g.OW / 128), (unsigned)(g.C / BN), 4);
-  if (weight_map(&tmB, w, g.O, 16, g.C, 64)) return -1;
   return dispatch_conv(BN, tmA, tmB, p, grid, s);
 }
 
@@ -1174,13 +1356,24 @@ struct TcWgradParams {
   float* out; size_t split_stride;
 };
 
+// fp32 accumulator rows -> global through a per-warp 4 KB staging area ([32 rows][8 x 16 B], XOR-swizzled): eight lanes cover the 128 B of
+// one row, a warp store instruction writes four complete 128-byte lines instead of 32 scattered 16-byte pieces.
+__device__ __forceinline__ void store_rows_f32x32(const uint32_t (&v)[32], float4* stg, float* const (&rowp)[8], int cc, int lane) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) stg[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const int r = i * 4 + (lane >> 3); *reinterpret_cast<float4*>(rowp[i] + cc) = stg[r * 8 + ((lane & 7) ^ (r & 7))]; }
+  __syncwarp();
+}
 template <int BNW, int STAGES>
 struct TcWgradSmem {
   static constexpr int A_BYTES = 2 * 64 * 128;            // two 64-channel blocks of dy
   static constexpr int B_BYTES = (BNW / 64) * 64 * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+  static constexpr int STG_OFF = BAR_OFF + 256;           // 4 epilogue warps x 4 KB store staging
+  static constexpr int TOTAL = STG_OFF + 4 * 4096 + 1024;
 };
 
 template <int BNW, int STAGES>
@@ -1212,34 +1405,41 @@ __global__ void __launch_bounds__(192) tc_wgrad_kernel(const __grid_constant__ C
 
   if (warp == 0) {
     if (lane == 0) {
+      // the (tap, channel) origin of each 64-column block is fixed for the CTA; ring slot and pixel-block origin advance as counters
+      // (one thread feeds the pipeline -- an integer division per step is time the loads wait for)
+      int xc[BNW / 64], xw[BNW / 64], xh[BNW / 64];
+#pragma unroll
+      for (int j = 0; j < BNW / 64; ++j) { const int col = col0 + j * 64, tap = col / p.C; xc[j] = col % p.C; xw[j] = -p.PW + tap % p.KW; xh[j] = -p.PH + tap / p.KW; }
+      int n0, y0;
+      if (p.Nt > 1) { n0 = kb_beg * p.Nt; y0 = 0; } else { n0 = kb_beg / p.tiles_y; y0 = (kb_beg % p.tiles_y) * p.Ht; }
+      int s = 0; uint32_t ph = 0;
       for (int i = 0; i < num_kb; ++i) {
-        const int kb = kb_beg + i, s = i % STAGES; const uint32_t ph = (i / STAGES) & 1;
-        int n0, y0;
-        if (p.Nt > 1) { n0 = kb * p.Nt; y0 = 0; } else { n0 = kb / p.tiles_y; y0 = (kb % p.tiles_y) * p.Ht; }
+        const int kb = kb_beg + i;
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
         mbar_expect_tx(bar_full + 8 * s, S::STAGE_BYTES);
         const uint32_t a = smem_base + s * S::STAGE_BYTES, b = a + S::A_BYTES;
         tma_load_2d(a, &tmDy, bar_full + 8 * s, o0, kb * 64);
         tma_load_2d(a + 8192, &tmDy, bar_full + 8 * s, o0 + 64, kb * 64);
 #pragma unroll
-        for (int j = 0; j < BNW / 64; ++j) {
-          const int col = col0 + j * 64, tap = col / p.C, c0 = col % p.C, r = tap / p.KW, sx = tap % p.KW;
-          tma_load_4d(b + j * 8192, &tmX, bar_full + 8 * s, c0, -p.PW + sx, y0 * p.SH - p.PH + r, n0);
-        }
+        for (int j = 0; j < BNW / 64; ++j) tma_load_4d(b + j * 8192, &tmX, bar_full + 8 * s, xc[j], xw[j], y0 * p.SH + xh[j], n0);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+        if (p.Nt > 1) n0 += p.Nt; else { y0 += p.Ht; if (y0 >= p.tiles_y * p.Ht) { y0 = 0; ++n0; } }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(128, BNW, 1, 1);
+      int s = 0; uint32_t ph = 0;
       for (int i = 0; i < num_kb; ++i) {
-        const int s = i % STAGES; const uint32_t ph = (i / STAGES) & 1;
         mbar_wait(bar_full + 8 * s, ph);
         tc_fence_after();
         const uint32_t a = smem_base + s * S::STAGE_BYTES, b = a + S::A_BYTES;
+        const uint64_t da = desc_mnmajor_sw128(a, 8192), db = desc_mnmajor_sw128(b, 8192);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)     // 16 pixel rows per MMA = 2048 B down the tile
-          umma_bf16(tmem_base, desc_mnmajor_sw128(a + k * 2048, 8192), desc_mnmajor_sw128(b + k * 2048, 8192), idesc, (i | k) != 0);
+        for (int k = 0; k < 4; ++k)     // 16 pixel rows per MMA = 2048 B down the tile = +128 in the descriptor's 16-byte address field
+          umma_bf16(tmem_base, da + 128 * k, db + 128 * k, idesc, (i | k) != 0);
         umma_commit(bar_empty + 8 * s);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
       umma_commit(bar_accum);
     }
@@ -1250,13 +1450,15 @@ __global__ void __launch_bounds__(192) tc_wgrad_kernel(const __grid_constant__ C
       mbar_wait(bar_accum, 0);
       tc_fence_after();
 #pragma unroll 1
+      float* rowp[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) rowp[i] = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, (unsigned long long)orow, i * 4 + (lane >> 3))) + (lane & 7) * 4;
+      float4* stg = reinterpret_cast<float4*>(smem_gen + S::STG_OFF) + q * 256;
       for (int cc = 0; cc < BNW; cc += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
         tmem_ld_wait();
-        float4* dst = reinterpret_cast<float4*>(orow + cc);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        store_rows_f32x32(v, stg, rowp, cc, lane);
       }
     } else {
       for (int cc = 0; cc < BNW; cc += 4) *reinterpret_cast<float4*>(orow + cc) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1272,7 +1474,7 @@ __global__ void __launch_bounds__(192) tc_wgrad_kernel(const __grid_constant__ C
 // O >= 256 layers (D3, D4, G2, G3).  A separate kernel so that the measured tc_wgrad_kernel above stays untouched.
 struct TcWgrad2Smem {
   static constexpr int A_BYTES = 4 * 64 * 128, B_BYTES = 4 * 64 * 128, STAGE_BYTES = A_BYTES + B_BYTES, STAGES = 3;
-  static constexpr int BAR_OFF = STAGES * STAGE_BYTES, TOTAL = BAR_OFF + 256 + 1024;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES, STG_OFF = BAR_OFF + 256, TOTAL = STG_OFF + 4 * 4096 + 1024;
 };
 __global__ void __launch_bounds__(192) tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, const TcWgradParams p) {
   using S = TcWgrad2Smem; constexpr int STAGES = S::STAGES, BNW = 256;
@@ -1300,36 +1502,41 @@ __global__ void __launch_bounds__(192) tc_wgrad2_kernel(const __grid_constant__ 
   pdl_wait();         // barrier init / TMEM allocation above overlap the predecessor's tail; global memory is touched only below
   if (warp == 0) {
     if (lane == 0) {
+      int xc[4], xw[4], xh[4];           // as in tc_wgrad_kernel: nothing but counters inside the loop
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const int col = col0 + j * 64, tap = col / p.C; xc[j] = col % p.C; xw[j] = -p.PW + tap % p.KW; xh[j] = -p.PH + tap / p.KW; }
+      int n0, y0;
+      if (p.Nt > 1) { n0 = kb_beg * p.Nt; y0 = 0; } else { n0 = kb_beg / p.tiles_y; y0 = (kb_beg % p.tiles_y) * p.Ht; }
+      int s = 0; uint32_t ph = 0;
       for (int i = 0; i < num_kb; ++i) {
-        const int kb = kb_beg + i, s = i % STAGES; const uint32_t ph = (i / STAGES) & 1;
-        int n0, y0;
-        if (p.Nt > 1) { n0 = kb * p.Nt; y0 = 0; } else { n0 = kb / p.tiles_y; y0 = (kb % p.tiles_y) * p.Ht; }
+        const int kb = kb_beg + i;
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
         mbar_expect_tx(bar_full + 8 * s, S::STAGE_BYTES);
         const uint32_t a = smem_base + s * S::STAGE_BYTES, b = a + S::A_BYTES;
 #pragma unroll
         for (int j = 0; j < 4; ++j) tma_load_2d(a + j * 8192, &tmDy, bar_full + 8 * s, o0 + 64 * j, kb * 64);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int col = col0 + j * 64, tap = col / p.C, c0 = col % p.C, r = tap / p.KW, sx = tap % p.KW;
-          tma_load_4d(b + j * 8192, &tmX, bar_full + 8 * s, c0, -p.PW + sx, y0 * p.SH - p.PH + r, n0);
-        }
+        for (int j = 0; j < 4; ++j) tma_load_4d(b + j * 8192, &tmX, bar_full + 8 * s, xc[j], xw[j], y0 * p.SH + xh[j], n0);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+        if (p.Nt > 1) n0 += p.Nt; else { y0 += p.Ht; if (y0 >= p.tiles_y * p.Ht) { y0 = 0; ++n0; } }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(128, BNW, 1, 1);
+      int s = 0; uint32_t ph = 0;
       for (int i = 0; i < num_kb; ++i) {
-        const int s = i % STAGES; const uint32_t ph = (i / STAGES) & 1;
         mbar_wait(bar_full + 8 * s, ph);
         tc_fence_after();
         const uint32_t a = smem_base + s * S::STAGE_BYTES, b = a + S::A_BYTES;
+        const uint64_t da = desc_mnmajor_sw128(a, 8192), db = desc_mnmajor_sw128(b, 8192);
 #pragma unroll
         for (int m = 0; m < 2; ++m)
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + m * BNW, desc_mnmajor_sw128(a + m * 16384 + k * 2048, 8192), desc_mnmajor_sw128(b + k * 2048, 8192), idesc, (i | k) != 0);
+          for (int k = 0; k < 4; ++k)      // +1024 = the second 128-channel half of dy (16 KB), +128 = 16 pixel rows
+            umma_bf16(tmem_base + m * BNW, da + 1024 * m + 128 * k, db + 128 * k, idesc, (i | k) != 0);
         umma_commit(bar_empty + 8 * s);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
       umma_commit(bar_accum);
     }
@@ -1341,13 +1548,15 @@ __global__ void __launch_bounds__(192) tc_wgrad2_kernel(const __grid_constant__ 
       float* orow = p.out + (size_t)split * p.split_stride + (size_t)(o0 + m * 128 + row) * p.taps * p.C + col0;
       if (num_kb > 0) {
 #pragma unroll 1
+        float* rowp[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rowp[i] = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, (unsigned long long)orow, i * 4 + (lane >> 3))) + (lane & 7) * 4;
+        float4* stg = reinterpret_cast<float4*>(smem_gen + S::STG_OFF) + q * 256;
         for (int cc = 0; cc < BNW; cc += 32) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * BNW + cc), v);
           tmem_ld_wait();
-          float4* dst = reinterpret_cast<float4*>(orow + cc);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          store_rows_f32x32(v, stg, rowp, cc, lane);
         }
       } else {
         for (int cc = 0; cc < BNW; cc += 4) *reinterpret_cast<float4*>(orow + cc) = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -211,7 +211,8 @@ int32_t b2g_ctx_allreduce_test(b2g_ctx* ctx, float* host_inout, int64_t n);
 /* Run ONE hot-path kernel on caller-provided host tensors (NHWC, fp32 on host, rounded to bf16 on the
  * device when precision is BF16) and return the fp32 result; used by tests/ and the roofline bench.
  * kind: 0 = conv fprop, 1 = conv dgrad (= deconv fprop), 2 = conv wgrad.
- * impl: 0 = SIMT reference kernel, 1 = tcgen05 tensor-core kernel (B2G_ERR_UNSUPPORTED if the shape has none). */
+ * impl: 0 = SIMT reference kernel, 1 = tcgen05 tensor-core kernel, 2 / 3 = skinny-layer (<= 4 image channels) SIMT / tcgen05 kernels,
+ * 4 = dense 1x1-geometry kernels (B2G_ERR_UNSUPPORTED if the shape has none). */
 typedef struct {
   int32_t n, h, w, c;          /* conv input  (NHWC) */
   int32_t oh, ow, o;           /* conv output (NHWC) */
