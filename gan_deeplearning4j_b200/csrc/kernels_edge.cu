@@ -238,22 +238,56 @@ __global__ void __launch_bounds__(128) dense_small_o_fwd_kernel(const T* __restr
   __syncthreads();
   if (threadIdx.x < O) { float a = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x]; stf(out, (size_t)n * O + threadIdx.x, act_fwd(act, a + (bias ? bias[threadIdx.x] : 0.f), alpha)); }
 }
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 u; __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+// dx[n][k] = sum_o dy[n][o] w[o][k]: pure streaming (one 16-byte store per 8 k), thread = 8 adjacent k of one image
 template <typename T, typename TW>
-__global__ void dense_small_o_dgrad_kernel(const T* __restrict__ dy, const TW* __restrict__ w, T* __restrict__ dx, int N, int K, int O) { pdl_enter();
-  const size_t total = (size_t)N * K;
+__global__ void __launch_bounds__(256) dense_small_o_dgrad_kernel(const T* __restrict__ dy, const TW* __restrict__ w, T* __restrict__ dx, int N, int K, int O) { pdl_enter();
+  const int kv = K >> 3; const size_t total = (size_t)N * kv;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int k = i % K; const size_t n = i / K; float a = 0.f;
-    for (int o = 0; o < O; ++o) a = fmaf(ldf(dy, n * O + o), ldw(w, (size_t)o * K + k), a);
-    stf(dx, i, a);
+    const size_t n = i / kv; const int k = (int)(i - n * kv) << 3;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int o = 0; o < O; ++o) {
+      const float d = ldf(dy, n * O + o); float wv[8]; load8_any(w + (size_t)o * K + k, wv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(d, wv[j], acc[j]);
+    }
+    store8(dx + n * K + k, acc);
   }
 }
+// dw[o][k] = sum_n dy[n][o] x[n][k]: thread = 8 adjacent k, blockIdx.y = a slice of the batch (fixed-order partials, reduced by k_reduce_splits);
+// eight row loads in flight per thread
 template <typename T>
-__global__ void dense_small_o_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ part, int N, int K, int O, int rows_per_split) { pdl_enter();
-  const int k = blockIdx.x * blockDim.x + threadIdx.x; if (k >= K) return;
+__global__ void __launch_bounds__(128) dense_small_o_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ part, int N, int K, int O, int rows_per_split) { pdl_enter();
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) << 3; if (k >= K) return;
   const int n0 = blockIdx.y * rows_per_split, n1 = min(N, n0 + rows_per_split);
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int n = n0; n < n1; ++n) { const float v = ldf(x, (size_t)n * K + k); for (int o = 0; o < O; ++o) acc[o] = fmaf(ldf(dy, (size_t)n * O + o), v, acc[o]); }
-  for (int o = 0; o < O; ++o) part[(size_t)blockIdx.y * O * K + (size_t)o * K + k] = acc[o];
+  float acc[4][8];
+#pragma unroll
+  for (int o = 0; o < 4; ++o)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[o][j] = 0.f;
+  for (int nb = n0; nb < n1; nb += 8) {
+    float v[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) { if (nb + r < n1) load8(x + (size_t)(nb + r) * K + k, v[r]); else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[r][j] = 0.f; } }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) if (nb + r < n1) {
+#pragma unroll
+      for (int o = 0; o < 4; ++o) if (o < O) { const float d = ldf(dy, (size_t)(nb + r) * O + o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[o][j] = fmaf(d, v[r][j], acc[o][j]); }
+    }
+  }
+  for (int o = 0; o < O; ++o) store8(part + (size_t)blockIdx.y * O * K + (size_t)o * K + k, acc[o]);
 }
 
 // ------------------------------------------------------------------ (e) 1x1 layers with a short reduction (G-first: z -> 4x4 map) -----
@@ -338,6 +372,139 @@ __global__ void __launch_bounds__(128) dense_small_k_wgrad_kernel(const T* __res
   for (int j = 0; j < 16; ++j) if (o0 + j < O) st2(dw + (size_t)(o0 + j) * C + c, acc[j][0], acc[j][1]);
 }
 
+
+// ------------------------------------------------------------------ (e') the same two GEMMs on warp-level tensor-core MMAs (bf16 operands) ---
+// out[n][c] = sum_o z[n][o] W[o][c] (N x 100 x 8192) and dW[o][c] = sum_n z[n][o] dOut[n][c] (100 x N x 8192) are 0.2 GFLOP each: the
+// SIMT kernels above spend ~18 us on instruction issue (ncu: 43 % issue-slot busy at 25 % occupancy).  mma.sync.m16n8k16 with ldmatrix
+// fragments cuts the instruction count ~10x; the tcgen05 path does not apply (reduction of 100 is not a multiple of 64 and the operand
+// rows are not 16-byte multiples for TMA).  Operands are staged once per CTA in shared memory, rows padded so that every ldmatrix
+// phase touches 8 distinct 16-byte bank groups.
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t& r0, uint32_t& r1, const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+static constexpr int DK_AP = 136, DK_BP = 72;     // shared-memory row pitches (bf16 elements): 272 B and 144 B, both 16-byte multiples
+// forward: CTA = 64 images x 64 columns, warp = 16 images x 64 columns; the reduction (O <= 128, zero padded to a multiple of 16) is resident
+// z tile [ROWS images][O] -> shared [ROWS][DK_AP], zero padded to OP columns and past the batch; four loads in flight per thread
+template <int ROWS, int OP>
+__device__ __forceinline__ void dk_fill_z(const __nv_bfloat16* __restrict__ z, __nv_bfloat16* sA, int n0, int N, int O, int tid) {
+  constexpr int HALF = OP / 2, TOTAL = ROWS * HALF;
+#pragma unroll 1
+  for (int i0 = tid; i0 < TOTAL; i0 += 128 * 16) {
+    __nv_bfloat162 v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int i = i0 + u * 128, r = i / HALF, o = (i - r * HALF) * 2, n = n0 + r;
+      v[u] = __floats2bfloat162_rn(0.f, 0.f);
+      if (i < TOTAL && n < N) {
+        if (!(O & 1)) { if (o < O) v[u] = *reinterpret_cast<const __nv_bfloat162*>(z + (size_t)n * O + o); }
+        else { if (o < O) v[u].x = z[(size_t)n * O + o]; if (o + 1 < O) v[u].y = z[(size_t)n * O + o + 1]; }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) { const int i = i0 + u * 128, r = i / HALF, o = (i - r * HALF) * 2; if (i < TOTAL) *reinterpret_cast<__nv_bfloat162*>(sA + r * DK_AP + o) = v[u]; }
+  }
+}
+template <int KT>
+__global__ void __launch_bounds__(128) dense_k_fwd_mma_kernel(const __nv_bfloat16* __restrict__ z, const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
+                                                              __nv_bfloat16* __restrict__ out, int N, int C, int O, int act, float alpha) { pdl_enter();
+  __shared__ __align__(16) __nv_bfloat16 sA[64 * DK_AP];      // [image][o]
+  __shared__ __align__(16) __nv_bfloat16 sB[128 * DK_BP];     // [o][column]
+  constexpr int OP = KT * 16;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, c0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  dk_fill_z<64, OP>(z, sA, n0, N, O, tid);
+#pragma unroll
+  for (int i = tid; i < OP * 8; i += 128) {                   // 8 x 16 B per weight row, all loads of a thread in flight together
+    const int o = i >> 3, j = i & 7;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (o < O) v = __ldg(reinterpret_cast<const uint4*>(w + (size_t)o * C + c0) + j);
+    *reinterpret_cast<uint4*>(sB + o * DK_BP + j * 8) = v;
+  }
+  __syncthreads();
+  float acc[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
+  // ldmatrix row addresses: A (x4, no transpose) matrices = (rows 0-7 | 8-15) x (k 0-7 | 8-15); B (x2, transposed) = k 0-7 | 8-15 of one 8-column block
+  const __nv_bfloat16* aptr = sA + (warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * DK_AP + (lane >> 4) * 8;
+  const __nv_bfloat16* bptr = sB + ((lane & 7) + ((lane >> 3) & 1) * 8) * DK_BP;
+#pragma unroll
+  for (int k0 = 0; k0 < OP; k0 += 16) {
+    uint32_t a[4]; ldsm_x4(a, aptr + k0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { uint32_t b0, b1; ldsm_x2_t(b0, b1, bptr + k0 * DK_BP + j * 8); mma_bf16_16816(acc[j], a, b0, b1); }
+  }
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j * 8 + 2 * t; const float b0 = bias ? bias[c] : 0.f, b1 = bias ? bias[c + 1] : 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int n = n0 + warp * 16 + g + h * 8;
+      if (n < N) *reinterpret_cast<__nv_bfloat162*>(out + (size_t)n * C + c) = __floats2bfloat162_rn(act_fwd(act, acc[j][2 * h] + b0, alpha), act_fwd(act, acc[j][2 * h + 1] + b1, alpha));
+    }
+  }
+}
+// weight gradient: CTA = all O (<= 128, padded to OP) x 64 columns, warp = OP x 16 columns; the batch is consumed 64 images at a time in a
+// fixed order (deterministic, no split).  A = z^T comes out of the [image][o] tile through transposing ldmatrix.
+template <int KT>
+__global__ void __launch_bounds__(128) dense_k_wgrad_mma_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ z, float* __restrict__ dw, int N, int C, int O) { pdl_enter();
+  __shared__ __align__(16) __nv_bfloat16 sZ[64 * DK_AP];     // [image][o]
+  __shared__ __align__(16) __nv_bfloat16 sX[64 * DK_BP];     // [image][column]
+  constexpr int OP = KT * 16, MT = KT;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, c0 = blockIdx.x * 64;
+  float acc[MT][2][4];
+#pragma unroll
+  for (int m = 0; m < MT; ++m)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { acc[m][j][0] = acc[m][j][1] = acc[m][j][2] = acc[m][j][3] = 0.f; }
+  for (int nb = 0; nb < N; nb += 64) {
+    __syncthreads();
+    dk_fill_z<64, OP>(z, sZ, nb, N, O, tid);
+#pragma unroll
+    for (int i = tid; i < 64 * 8; i += 128) {
+      const int r = i >> 3, j = i & 7; const int n = nb + r;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (n < N) v = __ldg(reinterpret_cast<const uint4*>(x + (size_t)n * C + c0) + j);
+      *reinterpret_cast<uint4*>(sX + r * DK_BP + j * 8) = v;
+    }
+    __syncthreads();
+    // A^T tile stored [k = image][m = o]: x4.trans matrices = (m 0-7 | 8-15) x (k 0-7 | 8-15) -> a0..a3
+    const __nv_bfloat16* aptr = sZ + ((lane & 7) + (lane >> 4) * 8) * DK_AP + ((lane >> 3) & 1) * 8;
+    const __nv_bfloat16* bptr = sX + ((lane & 7) + ((lane >> 3) & 1) * 8) * DK_BP + warp * 16;
+#pragma unroll
+    for (int k0 = 0; k0 < 64; k0 += 16) {
+      uint32_t b[2][2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) ldsm_x2_t(b[j][0], b[j][1], bptr + k0 * DK_BP + j * 8);
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        uint32_t a[4]; ldsm_x4_t(a, aptr + k0 * DK_AP + m * 16);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) mma_bf16_16816(acc[m][j], a, b[j][0], b[j][1]);
+      }
+    }
+  }
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int m = 0; m < MT; ++m)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int o = m * 16 + g + h * 8;
+        if (o < O) *reinterpret_cast<float2*>(dw + (size_t)o * C + c0 + warp * 16 + j * 8 + 2 * t) = make_float2(acc[m][j][2 * h], acc[m][j][2 * h + 1]);
+      }
+}
+
 // ------------------------------------------------------------------ host wrappers ---------------------------------
 static bool is_k4s2p1(const ConvGeom& g) { return g.KH == 4 && g.KW == 4 && g.SH == 2 && g.SW == 2 && g.PH == 1 && g.PW == 1 && g.H == 2 * g.OH && g.W == 2 * g.OW; }
 bool edge_deconv_small_c_supported(const ConvGeom& g) { return is_k4s2p1(g) && g.C <= 4 && g.O % 8 == 0 && g.O <= 128; }
@@ -380,11 +547,25 @@ void k_dense_small_k_dgrad(int prec, int wprec, const ConvGeom& g, const void* d
   dim3 grid(g.C / 256, (g.N + 7) / 8);
   if (prec == PREC_F32) launch_pdl(dense_small_k_dgrad_kernel<float, float>, grid, dim3(128), (size_t)0, s, (const float*)dy, (const float*)w, bias, (float*)dx, g.N, g.C, g.O, act, alpha);
   else if (wprec == PREC_F32) launch_pdl(dense_small_k_dgrad_kernel<__nv_bfloat16, float>, grid, dim3(128), (size_t)0, s, (const __nv_bfloat16*)dy, (const float*)w, bias, (__nv_bfloat16*)dx, g.N, g.C, g.O, act, alpha);
+  else if ((reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(dy) & 3) == 0 && (reinterpret_cast<uintptr_t>(dx) & 3) == 0)
+    switch ((g.O + 15) / 16) {
+#define B2G_DK_FWD(KT) case KT: launch_pdl(dense_k_fwd_mma_kernel<KT>, dim3(g.C / 64, (g.N + 63) / 64), dim3(128), (size_t)0, s, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)dx, g.N, g.C, g.O, act, alpha); break;
+      B2G_DK_FWD(1) B2G_DK_FWD(2) B2G_DK_FWD(3) B2G_DK_FWD(4) B2G_DK_FWD(5) B2G_DK_FWD(6) B2G_DK_FWD(7) B2G_DK_FWD(8)
+#undef B2G_DK_FWD
+    }
   else launch_pdl(dense_small_k_dgrad_kernel<__nv_bfloat16, __nv_bfloat16>, grid, dim3(128), (size_t)0, s, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)dx, g.N, g.C, g.O, act, alpha);
   LAUNCHED();
 }
 void k_dense_small_k_wgrad(int prec, const ConvGeom& g, const void* x, const void* dy, float* dw, cudaStream_t s) {
   dim3 grid(g.C / 256, (g.O + 15) / 16);
+  if (prec == PREC_BF16 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(dy) & 3) == 0 && (reinterpret_cast<uintptr_t>(dw) & 7) == 0 && (((size_t)g.C * 4) & 7) == 0) {
+    switch ((g.O + 15) / 16) {
+#define B2G_DK_WG(KT) case KT: launch_pdl(dense_k_wgrad_mma_kernel<KT>, dim3(g.C / 64), dim3(128), (size_t)0, s, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw, g.N, g.C, g.O); break;
+      B2G_DK_WG(1) B2G_DK_WG(2) B2G_DK_WG(3) B2G_DK_WG(4) B2G_DK_WG(5) B2G_DK_WG(6) B2G_DK_WG(7) B2G_DK_WG(8)
+#undef B2G_DK_WG
+    }
+    LAUNCHED(); return;
+  }
   DISPATCH_PREC(prec, T, (launch_pdl(dense_small_k_wgrad_kernel<T>, grid, dim3(128), (size_t)0, s, (const T*)x, (const T*)dy, dw, g.N, g.C, g.O))); LAUNCHED();
 }
 void k_dense_small_o_fwd(int prec, int wprec, const ConvGeom& g, const void* x, const void* w, const float* bias, void* out, int act, float alpha, cudaStream_t s) {
@@ -394,17 +575,17 @@ void k_dense_small_o_fwd(int prec, int wprec, const ConvGeom& g, const void* x, 
   LAUNCHED();
 }
 void k_dense_small_o_dgrad(int prec, int wprec, const ConvGeom& g, const void* dy, const void* w, void* dx, cudaStream_t s) {
-  size_t tot = (size_t)g.N * g.C; int blocks = (int)((tot + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+  size_t tot = (size_t)g.N * (g.C / 8); int blocks = (int)((tot + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
   if (prec == PREC_F32) launch_pdl(dense_small_o_dgrad_kernel<float, float>, dim3(blocks), dim3(256), (size_t)(0), s, (const float*)dy, (const float*)w, (float*)dx, g.N, g.C, g.O);
   else if (wprec == PREC_F32) launch_pdl(dense_small_o_dgrad_kernel<__nv_bfloat16, float>, dim3(blocks), dim3(256), (size_t)(0), s, (const __nv_bfloat16*)dy, (const float*)w, (__nv_bfloat16*)dx, g.N, g.C, g.O);
   else launch_pdl(dense_small_o_dgrad_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(blocks), dim3(256), (size_t)(0), s, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)w, (__nv_bfloat16*)dx, g.N, g.C, g.O);
   LAUNCHED();
 }
-static int dense_wgrad_splits(const ConvGeom& g) { int sp = (g.N + 31) / 32; if (sp > 16) sp = 16; if (sp < 1) sp = 1; return sp; }
+static int dense_wgrad_splits(const ConvGeom& g) { int sp = (g.N + 7) / 8; if (sp > 32) sp = 32; if (sp < 1) sp = 1; return sp; }
 size_t k_dense_small_o_wgrad_scratch_floats(const ConvGeom& g) { return dense_small_o_supported(g) ? (size_t)dense_wgrad_splits(g) * g.O * g.C : 0; }
 void k_dense_small_o_wgrad(int prec, const ConvGeom& g, const void* x, const void* dy, float* dw, float* scratch, int accumulate, cudaStream_t s) {
   const int sp = dense_wgrad_splits(g), rps = (g.N + sp - 1) / sp; const size_t n = (size_t)g.O * g.C;
-  dim3 grid((g.C + 127) / 128, sp);
+  dim3 grid((g.C / 8 + 127) / 128, sp);
   DISPATCH_PREC(prec, T, (launch_pdl(dense_small_o_wgrad_kernel<T>, dim3(grid), dim3(128), (size_t)(0), s, (const T*)x, (const T*)dy, scratch, g.N, g.C, g.O, rps))); LAUNCHED();
   k_reduce_splits(scratch, dw, n, sp, n, accumulate, s);
 }

@@ -1142,7 +1142,8 @@ __global__ void __launch_bounds__(128) tc_edge_conv_kernel(const TcEdgeParams p)
   uint8_t* sA = sm; uint8_t* sB = sm + 16384; uint8_t* slab = sm + 24576;
   const uint32_t bar = smem_base + 24576 + EDGE_SLAB_BYTES;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + 24576 + EDGE_SLAB_BYTES + 8);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint4* stg = reinterpret_cast<uint4*>(sm + 24576 + EDGE_SLAB_BYTES + 64) + warp * 128;      // 2 KB per warp
   const int nb0 = blockIdx.y * 64, K = 16 * p.C;
   const int t_beg = blockIdx.x * p.tiles_per_cta, t_end = min(p.tiles_total, t_beg + p.tiles_per_cta);
   if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
@@ -1203,9 +1204,17 @@ __global__ void __launch_bounds__(128) tc_edge_conv_kernel(const TcEdgeParams p)
       else if (p.act == ACT_LRELU) { B2G_EDGE_EPI(ACT_LRELU) }
       else { B2G_EDGE_EPI(p.act) }
 #undef B2G_EDGE_EPI
-      uint4* dst = reinterpret_cast<uint4*>(orow + c0);
+      // coalesced stores through the per-warp staging area (see epi_tile): four lanes per 64-byte row piece
 #pragma unroll
-      for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+      for (int j = 0; j < 4; ++j) stg[lane * 4 + (j ^ ((lane >> 1) & 3))] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = i * 8 + (lane >> 2);
+        __nv_bfloat16* rp = reinterpret_cast<__nv_bfloat16*>(__shfl_sync(0xffffffffu, (unsigned long long)orow, r));
+        *reinterpret_cast<uint4*>(rp + c0 + (lane & 3) * 8) = stg[r * 4 + ((lane & 3) ^ ((r >> 1) & 3))];
+      }
+      __syncwarp();
     }
   }
   tc_fence_before();
@@ -1311,7 +1320,7 @@ int k_tc_edge_conv(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat1
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return -1;
   p.x = x; p.w = w; p.bias = bias; p.out = out; p.N = g.N; p.H = g.H; p.W = g.W; p.C = g.C; p.OH = g.OH; p.OW = g.OW; p.O = g.O; p.tiles_y = g.OH / p.Ht;
   p.tiles_total = g.N * p.tiles_y; p.act = act; p.alpha = alpha;
-  const size_t smem = 1024 + 24576 + EDGE_SLAB_BYTES + 64;
+  const size_t smem = 1024 + 24576 + EDGE_SLAB_BYTES + 64 + 4 * 2048;
   TC_SET_SMEM_ONCE(tc_edge_conv_kernel, smem);
   static int target = -1; if (target < 0) { const char* e = getenv("B2G_EDGE_CONV_CTAS"); target = e ? atoi(e) : 592; if (target < 1) target = 592; }
   p.tiles_per_cta = (p.tiles_total + target - 1) / target;

@@ -345,3 +345,32 @@ def test_bf16_whole_step_layer_by_layer(b200, case):
         assert fro < 3e-2 and cos > 0.999, (f"G grad {gs[li].get('name')}.{pname}", fro, cos)
     assert bD.simt_gemm_calls() > 0        # the skinny layers (the logit; z -> 4x4 in the DCGANs) are SIMT by design, and counted
     gan.close(); bG.close(); bD.close()
+
+
+# (name, batch, C, O): 1x1 geometry.  G-first (z -> 4x4 x nf*8 map, J:189-196 Deconvolution2D on the 1x1 latent "image") is the dgrad form
+# with the reduction over O latent inputs; D-last (J:159-163 OutputLayer, one logit per image) is the fprop form with O = 1.
+DENSE_K = [("G-first, C2 (z=100 -> 8192)", N, 8192, 100), ("G-first, ragged batch / odd latent size", 77, 1024, 13), ("G-first, batch 2N, z=128", 2 * N, 2048, 128)]
+DENSE_O = [("D-last, D step (2N)", 2 * N, 8192, 1), ("D-last, ragged batch", 37, 1024, 1)]
+
+
+def dense_geom(n, c, oc):
+    return dict(n=n, h=1, w=1, c=c, oh=1, ow=1, o=oc, kh=1, kw=1, sh=1, sw=1, ph=0, pw=0)
+
+
+@pytest.mark.parametrize("case", DENSE_K + DENSE_O, ids=[c[0] for c in DENSE_K + DENSE_O])
+def test_dense_kernels(b200, case):
+    """The 1x1-geometry layers at the ends of the stack through the C-ABI hook (impl 4): input-gradient form (= G-first forward),
+    weight gradient, and for O = 1 the forward dot product; reference = float64 matmul of the same bf16-rounded operands."""
+    b, ctx = b200
+    name, n, c, oc = case
+    rng = np.random.default_rng(5)
+    g = dense_geom(n, c, oc)
+    dy = bf16_round(rng.standard_normal((n, oc))); wt = bf16_round(rng.standard_normal((oc, c)) / np.sqrt(oc)); x = bf16_round(rng.standard_normal((n, c)))
+    got, _ = b.test_conv(ctx, 1, 4, b.BF16, g, dy, wt, n * c)
+    check_bf16(got.reshape(n, c), dy.astype(np.float64) @ wt.astype(np.float64), name + " dgrad form")
+    got, _ = b.test_conv(ctx, 2, 4, b.BF16, g, x, dy, oc * c)
+    ref = dy.astype(np.float64).T @ x.astype(np.float64)
+    assert np.abs(got.reshape(oc, c) - ref).max() <= 1e-4 * np.abs(ref).max(), name + " wgrad"
+    if oc <= 4:
+        got, _ = b.test_conv(ctx, 0, 4, b.BF16, g, x, wt, n * oc)
+        check_bf16(got.reshape(n, oc), x.astype(np.float64) @ wt.astype(np.float64).T, name + " fprop")
