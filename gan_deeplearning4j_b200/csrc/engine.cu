@@ -910,6 +910,22 @@ struct b2g_gan {
   std::vector<void*> allocs;
 };
 
+// B2G_PHASES=1 (diagnostic, eager launches only -- events inside a captured graph carry no time): CUDA events on the main stream at the
+// phase boundaries of the step; b2g_gan_step_resident prints the intervals to stderr.  The side streams are not marked: an interval is the
+// main-stream critical path between two boundaries, including whatever it had to wait for.
+static bool phases_on() { static int v = -1; if (v < 0) { const char* e = getenv("B2G_PHASES"); v = (e && atoi(e)) ? 1 : 0; } return v == 1; }
+static cudaEvent_t g_ph_ev[24]; static const char* g_ph_name[24]; static int g_ph_n = 0;
+static void phase_mark(cudaStream_t s, const char* name) {
+  if (!phases_on()) return; cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone; cudaStreamIsCapturing(s, &st); if (st != cudaStreamCaptureStatusNone || g_ph_n >= 24) return;
+  if (!g_ph_ev[g_ph_n]) cudaEventCreate(&g_ph_ev[g_ph_n]);
+  cudaEventRecord(g_ph_ev[g_ph_n], s); g_ph_name[g_ph_n++] = name;
+}
+static void phase_report(cudaStream_t s) {
+  if (!phases_on() || g_ph_n < 2) { g_ph_n = 0; return; }
+  cudaStreamSynchronize(s); float tot = 0.f;
+  for (int i = 1; i < g_ph_n; ++i) { float ms = 0.f; cudaEventElapsedTime(&ms, g_ph_ev[i - 1], g_ph_ev[i]); tot += ms; fprintf(stderr, "[b2g phase] %-34s %8.1f us\n", g_ph_name[i], ms * 1e3f); }
+  fprintf(stderr, "[b2g phase] %-34s %8.1f us\n", "total", tot * 1e3f); g_ph_n = 0;
+}
 // part 1: x_fake = gen.output(z_d) -- needs nothing from the host but z_d.  part 2: everything that touches x_real.
 // They are two graphs so that the copy-stream event of x_real's H2D can be waited on between them (a captured stream may not
 // wait on work outside its capture).
@@ -918,7 +934,10 @@ static int32_t gan_step_part1(b2g_gan* g, int N) {
   const size_t ts = prec_size(D->prec);
   void* fake_dst = (char*)D->input + ts * (size_t)N * D->in_elems;
   FwdOpts og{N, 1, g->cfg.fake_bn_train != 0, false, fake_dst};
-  return net_forward(G, g->z_d, og, nullptr);
+  phase_mark(G->ctx->stream, "start");
+  int32_t r = net_forward(G, g->z_d, og, nullptr);
+  phase_mark(G->ctx->stream, "G forward (inference) on z_d");
+  return r;
 }
 static int32_t gan_step_part2(b2g_gan* g, int N) {
   b2g_net *G = g->G, *D = g->D; cudaStream_t s = G->ctx->stream;
@@ -943,24 +962,32 @@ static int32_t gan_step_part2(b2g_gan* g, int N) {
   CU(cudaMemsetAsync(D->grads, 0, sizeof(float) * D->n_params, s));
   const void* logits = nullptr; FwdOpts od{2 * N, 2, true, true, nullptr};
   B2(net_forward(D, D->input, od, &logits));
+  phase_mark(s, "D forward 2N (+hoisted G fwd fork)");
   k_xent(D->prec, logits, g->y_d, D->epsA, g->loss_dev, N, 2, D->cfg.xent_clip_eps, s);
   B2(net_backward(D, D->input, D->epsA, 2 * N, 2, true, false, /*allreduce_follows=*/true));
+  phase_mark(s, "D loss + backward 2N (join wgrad)");
   if (under_allreduce) B2(hoisted_g_forward());
   B2(net_allreduce_grads(D));
   B2(net_update(D, 2 * N));
+  phase_mark(s, "D all-reduce + update");
   // 3. G update through D on (z_g, y_gen) (J:465-471); D's parameters / running stats / updater state untouched
   CU(cudaStreamWaitEvent(s, G->ctx->ev_b, 0));
+  phase_mark(s, "wait for hoisted G train forward");
   FwdOpts od2{N, 1, true, false, nullptr};
   B2(net_forward(D, xg, od2, &logits));
+  phase_mark(s, "D forward N");
   k_xent(D->prec, logits, g->y_g, D->epsA, g->loss_dev + 2, N, 1, D->cfg.xent_clip_eps, s);
   // the generator's output activation (tanh) is differentiated inside D's last input-gradient kernel when that kernel can (EPI_ACTBWD)
   TcEpi ga{}; const LayerRT& gl = G->L.back(); bool ga_done = false;
   const bool ga_can = gl.has_gemm() && gl.d.act != B2G_ACT_IDENTITY && gl.d.type != B2G_LAYER_OUTPUT;
   if (ga_can) { ga.mode = EPI_ACTBWD; ga.aux = (const __nv_bfloat16*)xg; ga.act = gl.d.act; ga.alpha = gl.d.act_alpha; }
   B2(net_backward(D, xg, D->epsA, N, 1, false, true, false, ga_can ? &ga : nullptr, &ga_done));
+  phase_mark(s, "D input gradient N");
   B2(net_backward(G, g->z_g, D->input_grad, N, 1, true, false, /*allreduce_follows=*/true, nullptr, nullptr, ga_done));
+  phase_mark(s, "G backward (join wgrad)");
   B2(net_allreduce_grads(G));
   B2(net_update(G, N));
+  phase_mark(s, "G all-reduce + update");
   return 0;
 }
 
@@ -1022,7 +1049,7 @@ extern "C" int32_t b2g_gan_step_resident(b2g_gan* g, int32_t batch) {
   if (c->comm) g->nccl_warm = true;
   g->last_batch = batch;
   CU(cudaEventRecord(g->ev0, s));
-  if (!use_graph) { B2(gan_step_part1(g, batch)); CU(cudaStreamWaitEvent(s, g->ev_x, 0)); B2(gan_step_part2(g, batch)); }
+  if (!use_graph) { B2(gan_step_part1(g, batch)); CU(cudaStreamWaitEvent(s, g->ev_x, 0)); B2(gan_step_part2(g, batch)); phase_report(s); }
   else {
     if (!g->exec || g->graph_batch != batch) {
       if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; } if (g->graph) { cudaGraphDestroy(g->graph); g->graph = nullptr; }

@@ -415,13 +415,19 @@ __global__ void __launch_bounds__(256, 3) bn_apply_acc_kernel(const uint4* __res
                                                              const float* __restrict__ gamma, const float* __restrict__ beta, int act, float alpha, float eps, float* __restrict__ coef,
                                                              const float* __restrict__ run_mean, const float* __restrict__ run_var, float* g_mean, float* g_var, float decay, int replicas) { pdl_enter();
   extern __shared__ float s_cf[];
-  const double cnt = (double)rows * replicas;       // sync_bn: the accumulators hold the sums of every replica (all-reduced 64-bit integers)
+  const double cnt = (double)rows * replicas, inv_cnt = 1.0 / cnt;       // sync_bn: the accumulators hold the sums of every replica (all-reduced 64-bit integers)
   const bool writer = blockIdx.x == 0;
+  const int C8 = C / 8; const size_t per_group = (size_t)rows * C8;
+  const size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  // the first batch of activation loads does not depend on the statistics: it flies while the coefficients are derived
+  uint4 xa[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) if (t0 + q * stride < per_group) xa[q] = x[t0 + q * stride];
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     double agm = 0.0, agv = 0.0;
     for (int g = 0; g < groups; ++g) {
       const unsigned long long* a = accp + (size_t)g * 4 * C;
-      const double mu = sacc_read(a, (size_t)C, (size_t)c) / cnt; double var = sacc_read(a + 2 * (size_t)C, (size_t)C, (size_t)c) / cnt - mu * mu; if (var < 0) var = 0;
+      const double mu = sacc_read(a, (size_t)C, (size_t)c) * inv_cnt; double var = sacc_read(a + 2 * (size_t)C, (size_t)C, (size_t)c) * inv_cnt - mu * mu; if (var < 0) var = 0;
       const float is = (float)(1.0 / sqrt(var + (double)eps)), sc = gamma[c] * is, sh = fmaf(-(float)mu, sc, beta[c]);
       s_cf[(g * 2 + 0) * C + c] = sc; s_cf[(g * 2 + 1) * C + c] = sh;
       if (writer) {
@@ -433,18 +439,19 @@ __global__ void __launch_bounds__(256, 3) bn_apply_acc_kernel(const uint4* __res
     if (writer && g_mean) { g_mean[c] = (float)(agm / groups); g_var[c] = (float)(agv / groups); }
   }
   __syncthreads();
-  const int C8 = C / 8; const size_t per_group = (size_t)rows * C8;
-  const size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
   const int c0 = (int)(t0 % C8) * 8;
+  bool preloaded = true;
   for (int g = 0; g < groups; ++g) {
     float sc[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { sc[j] = s_cf[(g * 2 + 0) * C + c0 + j]; sh[j] = s_cf[(g * 2 + 1) * C + c0 + j]; }
     const uint4* xg = x + g * per_group; uint4* yg = y + g * per_group;
     for (size_t i = t0; i < per_group; i += 4 * stride) {        // four independent 16-byte loads in flight per thread
-      uint4 xa[4];
+      if (!preloaded) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) if (i + q * stride < per_group) xa[q] = xg[i + q * stride];
+        for (int q = 0; q < 4; ++q) if (i + q * stride < per_group) xa[q] = xg[i + q * stride];
+      }
+      preloaded = false;
 #pragma unroll
       for (int q = 0; q < 4; ++q) if (i + q * stride < per_group) {
         float v[8]; unpack8(xa[q], v);
@@ -492,23 +499,29 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_acc_kernel(const uint4* _
                                                                  const float* __restrict__ coef, int act, float alpha, const unsigned long long* __restrict__ accp,
                                                                  float* g_gamma, float* g_beta, int want, int replicas) { pdl_enter();
   extern __shared__ float s_k[];
-  const double cnt = (double)rows * replicas;       // sync_bn: global sums; dgamma / dbeta are left as (global sum) / replicas, the gradient all-reduce restores the sum
+  const double cnt = (double)rows * replicas, inv_cnt = 1.0 / cnt;       // sync_bn: global sums; dgamma / dbeta are left as (global sum) / replicas, the gradient all-reduce restores the sum
   const bool writer = blockIdx.x == 0 && want;
+  const int C8 = C / 8; const size_t per_group = (size_t)rows * C8;
+  const size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  uint4 xa[4], ea[4];      // first batch of loads: independent of the sums, in flight during the prologue
+  if (ei) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) if (t0 + q * stride < per_group) { xa[q] = x[t0 + q * stride]; ea[q] = eo[t0 + q * stride]; }
+  }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     double tb = 0.0, tg = 0.0;
     for (int g = 0; g < groups; ++g) {
       const unsigned long long* a = accp + (size_t)g * 4 * C;
       const double s1 = sacc_read(a, (size_t)C, (size_t)c); double s2 = sacc_read(a + 2 * (size_t)C, (size_t)C, (size_t)c);
       if (PREMUL) s2 = (double)coef[(size_t)(g * 4 + 3) * C + c] * (s2 - (double)coef[(size_t)(g * 4 + 2) * C + c] * s1);      // (sum dy'*z) -> sum dy'*xhat
-      s_k[(g * 2 + 0) * C + c] = (float)(s1 / cnt); s_k[(g * 2 + 1) * C + c] = (float)(s2 / cnt); tb += s1; tg += s2;
+      s_k[(g * 2 + 0) * C + c] = (float)(s1 * inv_cnt); s_k[(g * 2 + 1) * C + c] = (float)(s2 * inv_cnt); tb += s1; tg += s2;
     }
     if (writer) { g_beta[c] += (float)(tb / replicas); g_gamma[c] += (float)(tg / replicas); }
   }
   __syncthreads();
   if (!ei) return;
-  const int C8 = C / 8; const size_t per_group = (size_t)rows * C8;
-  const size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
   const int c0 = (int)(t0 % C8) * 8;
+  bool preloaded = true;
   for (int g = 0; g < groups; ++g) {
     float sc[8], sh[8], mu[8], is[8], k1[8], k2[8];
 #pragma unroll
@@ -516,9 +529,11 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_acc_kernel(const uint4* _
       k1[j] = s_k[(g * 2 + 0) * C + c]; k2[j] = s_k[(g * 2 + 1) * C + c]; }
     const uint4* xg = x + g * per_group; const uint4* eg = eo + g * per_group; uint4* ig = ei + g * per_group;
     for (size_t i = t0; i < per_group; i += 4 * stride) {
-      uint4 xa[4], ea[4];
+      if (!preloaded) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) if (i + q * stride < per_group) { xa[q] = xg[i + q * stride]; ea[q] = eg[i + q * stride]; }
+        for (int q = 0; q < 4; ++q) if (i + q * stride < per_group) { xa[q] = xg[i + q * stride]; ea[q] = eg[i + q * stride]; }
+      }
+      preloaded = false;
 #pragma unroll
       for (int q = 0; q < 4; ++q) if (i + q * stride < per_group) {
         float xv[8], ev[8], o[8]; unpack8(xa[q], xv); unpack8(ea[q], ev);

@@ -52,6 +52,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 __device__ int g_tc_timeout_flag = 0;
 // bounded wait: a wrong expect_tx byte count or a bad descriptor must not hang the GPU -- trap instead
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -59,6 +60,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   for (uint32_t it = 0; it < (1u << 26); ++it) {
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     if (done) return;
+  }
+  g_tc_timeout_flag = 1; __trap();
+}
+// the same for the many threads of the epilogue warps, which wait for a whole main loop: back off between polls so that the polling does not
+// compete with the two single threads that drive the pipeline
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t it = 0; it < (1u << 24); ++it) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return;
+    __nanosleep(128);
   }
   g_tc_timeout_flag = 1; __trap();
 }
@@ -73,6 +85,15 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// One lane of a CONVERGED warp (elect.sync).  The single-thread roles are written as "whole warp runs the loop, the elected lane issues":
+// nvcc then emits the uniform-datapath instructions (UTMALDG / UTCHMMA / UTCBAR) once, predicated.  Under a divergent `if (lane == 0)` it
+// wraps each of them in an ELECT / BRA.U.ANY loop with R2UR transfers: measured (tools/exp_step_cost.cu) 69 instead of 48 cycles per
+// N = 64 MMA and ~140 cycles more per pipeline step.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred P1;\n\t.reg .b32 rx;\n\telect.sync rx|P1, %1;\n\t@P1 mov.s32 %0, 1;\n\t}" : "+r"(pred) : "r"(0xffffffffu));
+  return pred != 0;
 }
 __device__ __forceinline__ void prefetch_map(const CUtensorMap* map) { asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -152,6 +173,7 @@ struct TcConvParams {
   int imgs_per_group;
   const __nv_bfloat16* aux; // EPI_BNBWD / EPI_ACTBWD: the forward output whose act' multiplies the result   (same NHWC shape as `out`)
   const __nv_bfloat16* aux2;// EPI_BNBWD: the BatchNorm input z
+  int dbg;                  // B2G_TC_DBG (timing experiments only, results are garbage): 1 = no loads, 2 = no MMAs, 3 = no epilogue stores
 };
 
 template <int BN, int STAGES, int EPI = EPI_PLAIN>
@@ -289,7 +311,7 @@ __device__ __forceinline__ void epi_tile(const TcConvParams& p, uint32_t taddr, 
     for (int j = 0; j < 4; ++j) stg[lane * 4 + (j ^ sx)] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
     __syncwarp();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { const int r = i * 8 + sub; *reinterpret_cast<uint4*>(p.out + roff_i[i] + c0) = stg[r * 4 + (cq ^ ((r >> 1) & 3))]; }
+    for (int i = 0; i < 4; ++i) { const int r = i * 8 + sub; if (p.dbg != 3) *reinterpret_cast<uint4*>(p.out + roff_i[i] + c0) = stg[r * 4 + (cq ^ ((r >> 1) & 3))]; }
     __syncwarp();
     if constexpr (stats) {
       if constexpr (EPI == EPI_STATS) {
@@ -392,34 +414,37 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ CU
   pdl_wait();         // barrier init / TMEM allocation above overlap the predecessor's tail; global memory is touched only below
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      // one thread feeds the whole pipeline: no integer division inside the loop (ring slot, channel chunk and tap advance as counters)
-      const int ybase = p.mode == 0 ? y0 * p.SH : y0;
-      int s = 0, ch = 0, ta = 0, tb = 0; uint32_t ph = 0;
-      int ax, dy_, wtap; tap_coords(p, 0, 0, py, px, ax, dy_, wtap);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(bar_empty + 8 * s, ph ^ 1);
-        mbar_expect_tx(bar_full + 8 * s, S::STAGE_BYTES);
-        tma_load_4d(smem_base + s * S::STAGE_BYTES, &tmA, bar_full + 8 * s, ch * 64, ax, ybase + dy_, n0);
-        load_b_tile<BN>(p, &tmB, smem_base + s * S::STAGE_BYTES + S::A_BYTES, bar_full + 8 * s, ch, wtap, nb0);
-        if (++s == STAGES) { s = 0; ph ^= 1; }
-        if (++ch == p.chunks) { ch = 0; if (++tb == p.taps_w) { tb = 0; ++ta; } tap_coords(p, ta, tb, py, px, ax, dy_, wtap); }
+    // ===== TMA producer (converged warp, elected lane issues): no integer division inside the loop -- ring slot, channel chunk and tap advance as counters =====
+    const int ybase = p.mode == 0 ? y0 * p.SH : y0;
+    int s = 0, ch = 0, ta = 0, tb = 0; uint32_t ph = 0;
+    int ax, dy_, wtap; tap_coords(p, 0, 0, py, px, ax, dy_, wtap);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(bar_empty + 8 * s, ph ^ 1);
+      if (elect_one_sync()) {
+        if (p.dbg == 1) mbar_arrive(bar_full + 8 * s); else {
+          mbar_expect_tx(bar_full + 8 * s, S::STAGE_BYTES);
+          tma_load_4d(smem_base + s * S::STAGE_BYTES, &tmA, bar_full + 8 * s, ch * 64, ax, ybase + dy_, n0);
+          load_b_tile<BN>(p, &tmB, smem_base + s * S::STAGE_BYTES + S::A_BYTES, bar_full + 8 * s, ch, wtap, nb0); }
       }
+      __syncwarp();
+      if (++s == STAGES) { s = 0; ph ^= 1; }
+      if (++ch == p.chunks) { ch = 0; if (++tb == p.taps_w) { tb = 0; ++ta; } tap_coords(p, ta, tb, py, px, ax, dy_, wtap); }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      int s = 0; uint32_t ph = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(bar_full + 8 * s, ph);
-        tc_fence_after();
-        mma_kblock<BN>(tmem_base, smem_base + s * S::STAGE_BYTES, smem_base + s * S::STAGE_BYTES + S::A_BYTES, PS ? 0 : p.b_mn, (uint32_t)kb);
+    // ===== MMA issuer (converged warp, elected lane issues) =====
+    int s = 0; uint32_t ph = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(bar_full + 8 * s, ph);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        if (p.dbg != 2) mma_kblock<BN>(tmem_base, smem_base + s * S::STAGE_BYTES, smem_base + s * S::STAGE_BYTES + S::A_BYTES, PS ? 0 : p.b_mn, (uint32_t)kb);
         umma_commit(bar_empty + 8 * s);
-        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
-      umma_commit(bar_accum);
+      __syncwarp();
+      if (++s == STAGES) { s = 0; ph ^= 1; }
     }
+    if (elect_one_sync()) umma_commit(bar_accum);
+    __syncwarp();
   } else {
     // ===== epilogue: TMEM lane quadrant = warp % 4 =====
     const int q = warp & 3;
@@ -429,7 +454,7 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ CU
     size_t pix;
     if (p.mode == 0) pix = ((size_t)n * p.outH + gy) * p.outW + gx;
     else pix = ((size_t)n * p.outH + 2 * gy + py) * p.outW + 2 * gx + px;
-    mbar_wait(bar_accum, 0);
+    if (p.dbg == 4) mbar_wait(bar_accum, 0); else mbar_wait_relaxed(bar_accum, 0);
     tc_fence_after();
     if constexpr (PS) {
       uint32_t v[32];                       // 32 columns are allocated; [0,16) carry the tile
@@ -477,7 +502,6 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ CU
 // limit.  This kernel attacks both: one resident CTA per SM walks a static list of work items (MT adjacent 128-row tiles x one
 // weight tile x one phase), the smem ring keeps flowing across items, and TWO TMEM accumulator stages let the 4 epilogue warps drain
 // item i while the MMA issuer already works on item i+1.  MT = 2 shares each weight tile between two M tiles (25 % fewer bytes out of L2).
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 
 template <int BN, int STAGES, int MT, int EPI = EPI_PLAIN>
 struct TcSmemP {
@@ -526,46 +550,50 @@ __global__ void __launch_bounds__(192) tc_conv_persistent_kernel(const __grid_co
   auto tile_origin = [&](int mt, int& n0, int& y0) { if (p.Nt > 1) { n0 = mt * p.Nt; y0 = 0; } else { n0 = mt / p.tiles_y; y0 = (mt % p.tiles_y) * p.Ht; } };
 
   if (warp == 0) {
-    if (lane == 0) {
-      int s = 0; uint32_t ph = 0;        // ring position: counters, no integer division inside the loop
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        int mg, nb0, py, px; decode(item, mg, nb0, py, px);
-        int n0[MT], y0[MT];
+    // producer: converged warp, elected lane issues (see elect_one_sync)
+    int s = 0; uint32_t ph = 0;        // ring position: counters, no integer division inside the loop
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      int mg, nb0, py, px; decode(item, mg, nb0, py, px);
+      int n0[MT], y0[MT];
 #pragma unroll
-        for (int m = 0; m < MT; ++m) { tile_origin(mg * MT + m, n0[m], y0[m]); if (p.mode == 0) y0[m] *= p.SH; }
-        int ch = 0, ta = 0, tb = 0;
-        int ax, dy_, wtap; tap_coords(p, 0, 0, py, px, ax, dy_, wtap);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+      for (int m = 0; m < MT; ++m) { tile_origin(mg * MT + m, n0[m], y0[m]); if (p.mode == 0) y0[m] *= p.SH; }
+      int ch = 0, ta = 0, tb = 0;
+      int ax, dy_, wtap; tap_coords(p, 0, 0, py, px, ax, dy_, wtap);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        if (elect_one_sync()) {
           mbar_expect_tx(bar_full + 8 * s, S::STAGE_BYTES);
           const uint32_t st = smem_base + s * S::STAGE_BYTES;
 #pragma unroll
           for (int m = 0; m < MT; ++m) tma_load_4d(st + m * 16384, &tmA, bar_full + 8 * s, ch * 64, ax, y0[m] + dy_, n0[m]);
           load_b_tile<BN>(p, &tmB, st + S::A_BYTES, bar_full + 8 * s, ch, wtap, nb0);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
-          if (++ch == p.chunks) { ch = 0; if (++tb == p.taps_w) { tb = 0; ++ta; } tap_coords(p, ta, tb, py, px, ax, dy_, wtap); }
         }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+        if (++ch == p.chunks) { ch = 0; if (++tb == p.taps_w) { tb = 0; ++ta; } tap_coords(p, ta, tb, py, px, ax, dy_, wtap); }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      uint32_t it = 0, ph = 0; int s = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
-        const uint32_t acc = it & 1, aph = (it >> 1) & 1;
-        mbar_wait(bar_tempty + 8 * acc, aph ^ 1);          // the epilogue has drained this accumulator stage
+    uint32_t it = 0, ph = 0; int s = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+      const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+      mbar_wait(bar_tempty + 8 * acc, aph ^ 1);          // the epilogue has drained this accumulator stage
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + acc * ACC_COLS;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(bar_full + 8 * s, ph);
         tc_fence_after();
-        const uint32_t tacc = tmem_base + acc * ACC_COLS;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(bar_full + 8 * s, ph);
-          tc_fence_after();
+        if (elect_one_sync()) {
           const uint32_t st = smem_base + s * S::STAGE_BYTES;
 #pragma unroll
           for (int m = 0; m < MT; ++m) mma_kblock<BN>(tacc + m * BN, st + m * 16384, st + S::A_BYTES, p.b_mn, (uint32_t)kb);
           umma_commit(bar_empty + 8 * s);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(bar_tfull + 8 * acc);
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
+      if (elect_one_sync()) umma_commit(bar_tfull + 8 * acc);
+      __syncwarp();
     }
   } else {
     const int q = warp & 3, row = q * 32 + lane;
@@ -596,125 +624,9 @@ __global__ void __launch_bounds__(192) tc_conv_persistent_kernel(const __grid_co
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TCOLS); }
 }
 
-// ------------------------------------------------------------------ dgrad (transposed-conv forward) with a shared-memory halo ------
-// The phase-form kernels above fetch the dy tile once per (phase, tap): 16 times.  For the large-grid layers (dy grid >= 16 x 8 per image,
-// 64 output channels: D2's input gradient, the generator's last BatchNorm'd transposed conv) this kernel keeps the 18 x 10 halo of a
-// 16 x 8 dy tile in shared memory -- one TMA box per 64-channel chunk, zero-filled outside the image -- and feeds all 4 phases x 4 taps
-// through shifted descriptors (tools/exp_desc.cu: the 128B swizzle is a function of the absolute shared-memory address), accumulating the
-// four phases in four 64-column TMEM accumulators (x 2 stages: the epilogue of tile i overlaps the MMAs of tile i+1).  Per tile the
-// activations cost 46 KB instead of 512 KB out of L2.  The weights (MN-major tiles from the straight [O][16][C] copy) stream through a
-// 3-deep ring of 32 KB stages = the four taps of one (chunk, phase): measured (B2G_DH_DBG experiments, round 2) a pipeline step costs the
-// single-thread producer / issuer ~600 cycles whatever it carries, so a step must carry >= 16 MMAs (a first version with one 8 KB tap per
-// step ran at 30 us for 8.6 GFLOP; loads off: 31 us, MMAs off: 21 us).  Same epilogues as the other conv kernels (epi_tile).
-static constexpr int DH_HALO_BYTES = 18 * 10 * 128, DH_CHUNK_BYTES = 23 * 1024, DH_HSTAGE_BYTES = 2 * DH_CHUNK_BYTES, DH_WSTAGES = 3, DH_W_BYTES = 4 * 8192;
-static constexpr int DH_W_OFF = 2 * DH_HSTAGE_BYTES, DH_BAR_OFF = DH_W_OFF + DH_WSTAGES * DH_W_BYTES, DH_STAT_OFF = DH_BAR_OFF + 256, DH_STG_OFF = DH_STAT_OFF + 4 * 2 * 64 * 4, DH_SMEM = DH_STG_OFF + 4 * 2048 + 1024;
-
-// phase (py, px) x tap (ta, tb) of the 4x4 s2 p1 transposed conv -> filter tap index r*4+sx and the dy offset (dyr, dxc), as compile-time
-// functions so that the fully unrolled issue loops carry no index arithmetic (the issuing thread's scalar instructions are the bottleneck)
-__host__ __device__ constexpr int dh_r(int pyx, int t) { return pyx == 0 ? (t == 0 ? 1 : 3) : (t == 0 ? 0 : 2); }
-__host__ __device__ constexpr int dh_d(int pyx, int t) { return pyx == 0 ? (t == 0 ? 0 : -1) : (t == 0 ? 1 : 0); }
-template <int EPI, bool AFFINE>
-__global__ void __launch_bounds__(192) tc_dgrad_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcConvParams p,
-                                                             int tiles_x, int tiles_y, int total_tiles, int dbg) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_hfull = smem_base + DH_BAR_OFF, bar_hempty = bar_hfull + 16, bar_wfull = bar_hempty + 16, bar_wempty = bar_wfull + 8 * DH_WSTAGES;
-  const uint32_t bar_tfull = bar_wempty + 8 * DH_WSTAGES, bar_tempty = bar_tfull + 16;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + DH_BAR_OFF + 8 * (2 + 2 + 2 * DH_WSTAGES + 2 + 2));
-  float* sst = reinterpret_cast<float*>(smem_gen + DH_STAT_OFF);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int chunks = p.chunks, per_img = tiles_x * tiles_y, nsteps = 4 * chunks;      // a step = (chunk, phase): 4 taps
-  if (warp == 0 && lane == 0) {
-    prefetch_map(&tmA); prefetch_map(&tmB);
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_hfull + 8 * i, 1); mbar_init(bar_hempty + 8 * i, 1); mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4); }
-    for (int i = 0; i < DH_WSTAGES; ++i) { mbar_init(bar_wfull + 8 * i, 1); mbar_init(bar_wempty + 8 * i, 1); }
-    fence_mbar_init();
-  }
-  if (warp == 1) { tmem_alloc(smem_u32((const void*)tmem_slot), 512); tmem_relinquish(); }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  pdl_trigger();      // single-wave grid
-  pdl_wait();
-
-  if (warp == 0) {
-    if (lane == 0) {
-      uint32_t hit = 0, wit = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++hit) {
-        const int hs = hit & 1; const uint32_t hph = (hit >> 1) & 1;
-        const int n = tile / per_img, r = tile % per_img, y0 = (r / tiles_x) * 16, x0 = (r % tiles_x) * 8;
-        mbar_wait(bar_hempty + 8 * hs, hph ^ 1);
-        mbar_expect_tx(bar_hfull + 8 * hs, (uint32_t)chunks * DH_HALO_BYTES);
-        for (int ch = 0; ch < chunks; ++ch) tma_load_4d(smem_base + hs * DH_HSTAGE_BYTES + ch * DH_CHUNK_BYTES, &tmA, bar_hfull + 8 * hs, ch * 64, x0 - 1, y0 - 1, n);
-        for (int ch = 0; ch < chunks; ++ch) {
-#pragma unroll
-          for (int ph = 0; ph < 4; ++ph, ++wit) {
-            const int ws = wit % DH_WSTAGES; const uint32_t wph = (wit / DH_WSTAGES) & 1;
-            mbar_wait(bar_wempty + 8 * ws, wph ^ 1);
-            if (dbg == 1) { mbar_arrive(bar_wfull + 8 * ws); continue; }       // timing experiment: no weight loads
-            mbar_expect_tx(bar_wfull + 8 * ws, DH_W_BYTES);
-#pragma unroll
-            for (int t = 0; t < 4; ++t)
-              tma_load_3d(smem_base + DH_W_OFF + ws * DH_W_BYTES + t * 8192, &tmB, bar_wfull + 8 * ws, 0, dh_r(ph >> 1, t >> 1) * 4 + dh_r(ph & 1, t & 1), ch * 64);
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(128, 64, 0, 1);
-      uint32_t hit = 0, wit = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++hit) {
-        const int hs = hit & 1; const uint32_t hph = (hit >> 1) & 1, acc = hit & 1, aph = (hit >> 1) & 1;
-        mbar_wait(bar_tempty + 8 * acc, aph ^ 1);
-        mbar_wait(bar_hfull + 8 * hs, hph);
-        tc_fence_after();
-        for (int ch = 0; ch < chunks; ++ch) {
-          const uint64_t abase = desc_kmajor_sw128_sbo(smem_base + hs * DH_HSTAGE_BYTES + ch * DH_CHUNK_BYTES, 1280);
-#pragma unroll
-          for (int ph = 0; ph < 4; ++ph, ++wit) {
-            const int ws = wit % DH_WSTAGES; const uint32_t wph = (wit / DH_WSTAGES) & 1;
-            mbar_wait(bar_wfull + 8 * ws, wph);
-            tc_fence_after();
-            const uint64_t bbase = desc_mnmajor_sw128(smem_base + DH_W_OFF + ws * DH_W_BYTES, 8192);
-            if (dbg != 2)       // timing experiment 2: loads without MMAs
-#pragma unroll
-            for (int t = 0; t < 4; ++t)
-#pragma unroll
-              for (int k = 0; k < 4; ++k)      // descriptor start-address field counts 16-byte units: halo row = 8 units, K step = 2 units; weight tap = 512, K step = 128
-                umma_bf16(tmem_base + acc * 256 + ph * 64, abase + (uint64_t)(((1 + dh_d(ph >> 1, t >> 1)) * 10 + (1 + dh_d(ph & 1, t & 1))) * 8 + 2 * k),
-                          bbase + (uint64_t)(t * 512 + k * 128), idesc, (uint32_t)(ch | t | k));
-            umma_commit(bar_wempty + 8 * ws);
-          }
-        }
-        umma_commit(bar_hempty + 8 * hs);
-        umma_commit(bar_tfull + 8 * acc);
-      }
-    }
-  } else {
-    const int q = warp & 3, row = q * 32 + lane, yy = row >> 3, xx = row & 7;
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const uint32_t acc = it & 1, aph = (it >> 1) & 1;
-      const int n = tile / per_img, r = tile % per_img, gy = (r / tiles_x) * 16 + yy, gx = (r % tiles_x) * 8 + xx;
-      const int group = p.imgs_per_group > 0 ? n / p.imgs_per_group : 0;
-      mbar_wait(bar_tfull + 8 * acc, aph);
-      tc_fence_after();
-#pragma unroll 1
-      for (int ph = 0; ph < 4; ++ph) {
-        const size_t pix = ((size_t)n * p.outH + 2 * gy + (ph >> 1)) * p.outW + 2 * gx + (ph & 1);
-        epi_tile<64, EPI, AFFINE>(p, tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + ph * 64, pix * p.OC, 0, group, sst, reinterpret_cast<uint4*>(smem_gen + DH_STG_OFF) + q * 128, q, lane, (int)threadIdx.x - 64);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-    }
-  }
-  __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
-}
+// (A dgrad kernel with the dy tile resident in shared memory -- 18 x 10 halo, the 16 (phase, tap) operands read through shifted descriptors,
+// four phase accumulators -- was built and measured in round 2: 16.6 vs 19.5 us in isolation for D2's input gradient, but the training step
+// was 1 % SLOWER with it (profiles/r02_experiments.md); removed.  The pixel-shuffle kernel below keeps the technique where it pays.)
 
 // ------------------------------------------------------------------ host side ------------------------------
 const char* g_tc_last_kernel = "";       // name of the tcgen05 kernel the most recent k_tc_* call dispatched (parity tests assert it)
@@ -734,8 +646,9 @@ static bool pick_row_tile(int N, int GH, int GW, int rows, int* Nt, int* Ht, int
 static int pick_bn(int OC) { return OC % 256 == 0 ? 256 : OC % 128 == 0 ? 128 : OC % 64 == 0 ? 64 : 0; }
 // Small layers (few M tiles) are latency-bound per CTA, not bandwidth-bound: prefer narrower N tiles until the grid covers the 148 SMs.
 static int pick_bn_fill(int OC, long m_tiles_x_phases) {
+  static int min_ctas = -1; if (min_ctas < 0) { const char* e = getenv("B2G_BN_MIN_CTAS"); min_ctas = e ? atoi(e) : 148; if (min_ctas < 1) min_ctas = 148; }
   int bn = pick_bn(OC);
-  while (bn > 64 && m_tiles_x_phases * (OC / bn) < 148) bn /= 2;
+  while (bn > 64 && m_tiles_x_phases * (OC / bn) < min_ctas) bn /= 2;
   return bn;
 }
 
@@ -801,6 +714,8 @@ static int dispatch_conv(int BN, const CUtensorMap& tmA, const CUtensorMap& tmB,
     if (BN == 128) return launch_convp<128, 4, 2>(tmA, tmB, p, grid.x / 2, grid.y, grid.z, s, "tc_conv_persistent_kernel<128,4,2>");
     return launch_convp<64, 4, 2>(tmA, tmB, p, grid.x / 2, grid.y, grid.z, s, "tc_conv_persistent_kernel<64,4,2>");
   }
+  // Measured and not kept (round 2, profiles/r02_experiments.md): a deeper ring (8 x 24 KB / 6 x 32 KB) when only one CTA fits per SM, one
+  // commit per 2 / 4 ring slots, a second producer thread for the weight tiles -- none moved the K loop, which is bound by the issuing thread.
   switch (BN) {
     case 64: return launch_conv<64, 4>(tmA, tmB, p, grid, s, "tc_conv_kernel<64,4>");
     case 128: return launch_conv<128, 3>(tmA, tmB, p, grid, s, "tc_conv_kernel<128,3>");
@@ -817,6 +732,8 @@ static int weight_map(CUtensorMap* m, const __nv_bfloat16* w, int rows, int taps
   return make_map_bf16(m, w, 3, dims, strides, box, es);
 }
 static void fill_epi(TcConvParams& p, const float* bias, int act, float alpha, const TcEpi* e) {
+  static int dbg = -1; if (dbg < 0) { const char* ev = getenv("B2G_TC_DBG"); dbg = ev ? atoi(ev) : 0; }
+  p.dbg = dbg;
   p.bias = bias; p.act = act; p.alpha = alpha; p.epi = EPI_PLAIN;
   if (!e) return;
   p.scale = e->scale; p.epi = e->mode; p.acc = e->acc; p.imgs_per_group = e->mode == EPI_STATS || e->mode == EPI_BNBWD ? e->imgs_per_group : 0;
@@ -860,26 +777,6 @@ int k_tc_dgrad(const ConvGeom& g, const __nv_bfloat16* dy, const __nv_bfloat16* 
   cuuint32_t box[4] = {64, (cuuint32_t)p.Wt, (cuuint32_t)p.Ht, (cuuint32_t)p.Nt};
   cuuint32_t es[4] = {1, 1, 1, 1};
   if (weight_map(&tmB, w, g.O, 16, g.C, 64)) return -1;
-  static int halo = -1; if (halo < 0) { const char* e = getenv("B2G_DGRAD_HALO"); halo = (e && e[0] == '0') ? 0 : 1; }
-  if (halo && g.C == 64 && g.O / 64 <= 2 && g.OH % 16 == 0 && g.OW % 8 == 0) {      // large dy grid, 64 output channels: halo-resident kernel
-    box[1] = 10; box[2] = 18; box[3] = 1;
-    if (make_map_bf16(&tmA, dy, 4, dims, strides, box, es)) return -1;
-    const int tx = g.OW / 8, ty = g.OH / 16, total = g.N * tx * ty;
-    static int sms = 0; if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, tc_device());
-    const dim3 hgrid((unsigned)(total < sms ? total : sms));
-    g_tc_last_kernel = "tc_dgrad_halo_kernel";
-    static int dbgv = -1; if (dbgv < 0) { const char* e = getenv("B2G_DH_DBG"); dbgv = e ? atoi(e) : 0; }
-#define B2G_DH_LAUNCH(E, A) do { TC_SET_SMEM_ONCE((tc_dgrad_halo_kernel<E, A>), DH_SMEM); launch_pdl(tc_dgrad_halo_kernel<E, A>, hgrid, dim3(192), (size_t)DH_SMEM, s, tmA, tmB, p, tx, ty, total, dbgv); } while (0)
-    switch (p.epi) {
-      case EPI_STATS: B2G_DH_LAUNCH(EPI_STATS, false); break;
-      case EPI_BNBWD: B2G_DH_LAUNCH(EPI_BNBWD, false); break;
-      case EPI_ACTBWD: B2G_DH_LAUNCH(EPI_ACTBWD, false); break;
-      default: if (p.scale && p.bias) B2G_DH_LAUNCH(EPI_PLAIN, true); else B2G_DH_LAUNCH(EPI_PLAIN, false);
-    }
-#undef B2G_DH_LAUNCH
-    LAUNCHED();
-    return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
-  }
   if (make_map_bf16(&tmA, dy, 4, dims, strides, box, es)) return -1;
   dim3 grid((unsigned)(g.N * g.OH * g.OW / 128), (unsigned)(g.C / BN), 4);
   return dispatch_conv(BN, tmA, tmB, p, grid, s);
@@ -966,28 +863,33 @@ __global__ void __launch_bounds__(192) tc_deconv_ps_halo_kernel(const __grid_con
   const int per_img = p.tiles_x * p.tiles_y;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // producer: converged warp, elected lane issues
+    if (elect_one_sync()) {
       mbar_expect_tx(bar_w, PSH_W_BYTES);
       for (int t = 0; t < 9; ++t) tma_load_3d(wsm + t * 2048, &tmW, bar_w, 0, t, 0);
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const int s = it % PSH_STAGES; const uint32_t ph = (it / PSH_STAGES) & 1;
-        const int n = tile / per_img, r = tile % per_img, y0 = (r / p.tiles_x) * 16, x0 = (r % p.tiles_x) * 8;
-        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+    }
+    __syncwarp();
+    int s = 0; uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int n = tile / per_img, r = tile % per_img, y0 = (r / p.tiles_x) * 16, x0 = (r % p.tiles_x) * 8;
+      mbar_wait(bar_empty + 8 * s, ph ^ 1);
+      if (elect_one_sync()) {
         mbar_expect_tx(bar_full + 8 * s, PSH_HALO_BYTES);
         tma_load_4d(smem_base + s * PSH_STAGE_BYTES, &tmA, bar_full + 8 * s, 0, x0 - 1, y0 - 1, n);
       }
+      __syncwarp();
+      if (++s == PSH_STAGES) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(128, 16, 0, 0);
-      mbar_wait(bar_w, 0);
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const int s = it % PSH_STAGES; const uint32_t ph = (it / PSH_STAGES) & 1, acc = it & 1, aph = (it >> 1) & 1;
-        mbar_wait(bar_tempty + 8 * acc, aph ^ 1);
-        mbar_wait(bar_full + 8 * s, ph);
-        tc_fence_after();
+    constexpr uint32_t idesc = make_idesc(128, 16, 0, 0);
+    mbar_wait(bar_w, 0);
+    uint32_t it = 0; int s = 0; uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+      mbar_wait(bar_tempty + 8 * acc, aph ^ 1);
+      mbar_wait(bar_full + 8 * s, ph);
+      tc_fence_after();
+      if (elect_one_sync()) {
         const uint32_t halo = smem_base + s * PSH_STAGE_BYTES;
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
@@ -998,6 +900,8 @@ __global__ void __launch_bounds__(192) tc_deconv_ps_halo_kernel(const __grid_con
         umma_commit(bar_empty + 8 * s);
         umma_commit(bar_tfull + 8 * acc);
       }
+      __syncwarp();
+      if (++s == PSH_STAGES) { s = 0; ph ^= 1; }
     }
   } else {
     const int q = warp & 3, row = q * 32 + lane, yy = row >> 3, xx = row & 7;
@@ -1176,7 +1080,7 @@ __global__ void __launch_bounds__(128) tc_edge_conv_kernel(const TcEdgeParams p)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (tid == 0) {
+    if (warp == 0 && elect_one_sync()) {       // warp 0 is converged here: one elected lane issues (see elect_one_sync)
       constexpr uint32_t idesc = make_idesc(128, 64, 0, 0);
       const uint64_t adesc = desc_kmajor_sw128(smem_base), bdesc = desc_kmajor_sw128(smem_base + 16384);
 #pragma unroll
@@ -1262,7 +1166,7 @@ __global__ void __launch_bounds__(128) tc_edge_wgrad_kernel(const TcEdgeParams p
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (tid == 0) {
+    if (warp == 0 && elect_one_sync()) {
       constexpr uint32_t idesc = make_idesc(128, 64, 1, 1);
 #pragma unroll
       for (int k = 0; k < 8; ++k)       // 16 pixel rows per MMA
@@ -1413,45 +1317,48 @@ __global__ void __launch_bounds__(192) tc_wgrad_kernel(const __grid_constant__ C
   pdl_wait();         // barrier init / TMEM allocation above overlap the predecessor's tail; global memory is touched only below
 
   if (warp == 0) {
-    if (lane == 0) {
-      // the (tap, channel) origin of each 64-column block is fixed for the CTA; ring slot and pixel-block origin advance as counters
-      // (one thread feeds the pipeline -- an integer division per step is time the loads wait for)
-      int xc[BNW / 64], xw[BNW / 64], xh[BNW / 64];
+    // producer (converged warp, elected lane issues).  The (tap, channel) origin of each 64-column block is fixed for the CTA; ring slot and
+    // pixel-block origin advance as counters (an integer division per step is time the loads wait for)
+    int xc[BNW / 64], xw[BNW / 64], xh[BNW / 64];
 #pragma unroll
-      for (int j = 0; j < BNW / 64; ++j) { const int col = col0 + j * 64, tap = col / p.C; xc[j] = col % p.C; xw[j] = -p.PW + tap % p.KW; xh[j] = -p.PH + tap / p.KW; }
-      int n0, y0;
-      if (p.Nt > 1) { n0 = kb_beg * p.Nt; y0 = 0; } else { n0 = kb_beg / p.tiles_y; y0 = (kb_beg % p.tiles_y) * p.Ht; }
-      int s = 0; uint32_t ph = 0;
-      for (int i = 0; i < num_kb; ++i) {
-        const int kb = kb_beg + i;
-        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+    for (int j = 0; j < BNW / 64; ++j) { const int col = col0 + j * 64, tap = col / p.C; xc[j] = col % p.C; xw[j] = -p.PW + tap % p.KW; xh[j] = -p.PH + tap / p.KW; }
+    int n0, y0;
+    if (p.Nt > 1) { n0 = kb_beg * p.Nt; y0 = 0; } else { n0 = kb_beg / p.tiles_y; y0 = (kb_beg % p.tiles_y) * p.Ht; }
+    int s = 0; uint32_t ph = 0;
+    for (int i = 0; i < num_kb; ++i) {
+      const int kb = kb_beg + i;
+      mbar_wait(bar_empty + 8 * s, ph ^ 1);
+      if (elect_one_sync()) {
         mbar_expect_tx(bar_full + 8 * s, S::STAGE_BYTES);
         const uint32_t a = smem_base + s * S::STAGE_BYTES, b = a + S::A_BYTES;
         tma_load_2d(a, &tmDy, bar_full + 8 * s, o0, kb * 64);
         tma_load_2d(a + 8192, &tmDy, bar_full + 8 * s, o0 + 64, kb * 64);
 #pragma unroll
         for (int j = 0; j < BNW / 64; ++j) tma_load_4d(b + j * 8192, &tmX, bar_full + 8 * s, xc[j], xw[j], y0 * p.SH + xh[j], n0);
-        if (++s == STAGES) { s = 0; ph ^= 1; }
-        if (p.Nt > 1) n0 += p.Nt; else { y0 += p.Ht; if (y0 >= p.tiles_y * p.Ht) { y0 = 0; ++n0; } }
       }
+      __syncwarp();
+      if (++s == STAGES) { s = 0; ph ^= 1; }
+      if (p.Nt > 1) n0 += p.Nt; else { y0 += p.Ht; if (y0 >= p.tiles_y * p.Ht) { y0 = 0; ++n0; } }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(128, BNW, 1, 1);
-      int s = 0; uint32_t ph = 0;
-      for (int i = 0; i < num_kb; ++i) {
-        mbar_wait(bar_full + 8 * s, ph);
-        tc_fence_after();
+    constexpr uint32_t idesc = make_idesc(128, BNW, 1, 1);
+    int s = 0; uint32_t ph = 0;
+    for (int i = 0; i < num_kb; ++i) {
+      mbar_wait(bar_full + 8 * s, ph);
+      tc_fence_after();
+      if (elect_one_sync()) {
         const uint32_t a = smem_base + s * S::STAGE_BYTES, b = a + S::A_BYTES;
         const uint64_t da = desc_mnmajor_sw128(a, 8192), db = desc_mnmajor_sw128(b, 8192);
 #pragma unroll
         for (int k = 0; k < 4; ++k)     // 16 pixel rows per MMA = 2048 B down the tile = +128 in the descriptor's 16-byte address field
           umma_bf16(tmem_base, da + 128 * k, db + 128 * k, idesc, (i | k) != 0);
         umma_commit(bar_empty + 8 * s);
-        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
-      umma_commit(bar_accum);
+      __syncwarp();
+      if (++s == STAGES) { s = 0; ph ^= 1; }
     }
+    if (elect_one_sync()) umma_commit(bar_accum);
+    __syncwarp();
   } else {
     const int q = warp & 3, row = q * 32 + lane;
     float* orow = p.out + (size_t)split * p.split_stride + (size_t)(o0 + row) * p.taps * p.C + col0;
@@ -1510,33 +1417,34 @@ __global__ void __launch_bounds__(192) tc_wgrad2_kernel(const __grid_constant__ 
   pdl_trigger();      // single-wave grid: the successor may be scheduled behind us right away
   pdl_wait();         // barrier init / TMEM allocation above overlap the predecessor's tail; global memory is touched only below
   if (warp == 0) {
-    if (lane == 0) {
-      int xc[4], xw[4], xh[4];           // as in tc_wgrad_kernel: nothing but counters inside the loop
+    int xc[4], xw[4], xh[4];           // as in tc_wgrad_kernel: converged warp, elected lane issues, nothing but counters inside the loop
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { const int col = col0 + j * 64, tap = col / p.C; xc[j] = col % p.C; xw[j] = -p.PW + tap % p.KW; xh[j] = -p.PH + tap / p.KW; }
-      int n0, y0;
-      if (p.Nt > 1) { n0 = kb_beg * p.Nt; y0 = 0; } else { n0 = kb_beg / p.tiles_y; y0 = (kb_beg % p.tiles_y) * p.Ht; }
-      int s = 0; uint32_t ph = 0;
-      for (int i = 0; i < num_kb; ++i) {
-        const int kb = kb_beg + i;
-        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+    for (int j = 0; j < 4; ++j) { const int col = col0 + j * 64, tap = col / p.C; xc[j] = col % p.C; xw[j] = -p.PW + tap % p.KW; xh[j] = -p.PH + tap / p.KW; }
+    int n0, y0;
+    if (p.Nt > 1) { n0 = kb_beg * p.Nt; y0 = 0; } else { n0 = kb_beg / p.tiles_y; y0 = (kb_beg % p.tiles_y) * p.Ht; }
+    int s = 0; uint32_t ph = 0;
+    for (int i = 0; i < num_kb; ++i) {
+      const int kb = kb_beg + i;
+      mbar_wait(bar_empty + 8 * s, ph ^ 1);
+      if (elect_one_sync()) {
         mbar_expect_tx(bar_full + 8 * s, S::STAGE_BYTES);
         const uint32_t a = smem_base + s * S::STAGE_BYTES, b = a + S::A_BYTES;
 #pragma unroll
         for (int j = 0; j < 4; ++j) tma_load_2d(a + j * 8192, &tmDy, bar_full + 8 * s, o0 + 64 * j, kb * 64);
 #pragma unroll
         for (int j = 0; j < 4; ++j) tma_load_4d(b + j * 8192, &tmX, bar_full + 8 * s, xc[j], xw[j], y0 * p.SH + xh[j], n0);
-        if (++s == STAGES) { s = 0; ph ^= 1; }
-        if (p.Nt > 1) n0 += p.Nt; else { y0 += p.Ht; if (y0 >= p.tiles_y * p.Ht) { y0 = 0; ++n0; } }
       }
+      __syncwarp();
+      if (++s == STAGES) { s = 0; ph ^= 1; }
+      if (p.Nt > 1) n0 += p.Nt; else { y0 += p.Ht; if (y0 >= p.tiles_y * p.Ht) { y0 = 0; ++n0; } }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(128, BNW, 1, 1);
-      int s = 0; uint32_t ph = 0;
-      for (int i = 0; i < num_kb; ++i) {
-        mbar_wait(bar_full + 8 * s, ph);
-        tc_fence_after();
+    constexpr uint32_t idesc = make_idesc(128, BNW, 1, 1);
+    int s = 0; uint32_t ph = 0;
+    for (int i = 0; i < num_kb; ++i) {
+      mbar_wait(bar_full + 8 * s, ph);
+      tc_fence_after();
+      if (elect_one_sync()) {
         const uint32_t a = smem_base + s * S::STAGE_BYTES, b = a + S::A_BYTES;
         const uint64_t da = desc_mnmajor_sw128(a, 8192), db = desc_mnmajor_sw128(b, 8192);
 #pragma unroll
@@ -1545,10 +1453,12 @@ __global__ void __launch_bounds__(192) tc_wgrad2_kernel(const __grid_constant__ 
           for (int k = 0; k < 4; ++k)      // +1024 = the second 128-channel half of dy (16 KB), +128 = 16 pixel rows
             umma_bf16(tmem_base + m * BNW, da + 1024 * m + 128 * k, db + 128 * k, idesc, (i | k) != 0);
         umma_commit(bar_empty + 8 * s);
-        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
-      umma_commit(bar_accum);
+      __syncwarp();
+      if (++s == STAGES) { s = 0; ph ^= 1; }
     }
+    if (elect_one_sync()) umma_commit(bar_accum);
+    __syncwarp();
   } else {
     const int q = warp & 3, row = q * 32 + lane;
     if (num_kb > 0) { mbar_wait(bar_accum, 0); tc_fence_after(); }

@@ -1,5 +1,5 @@
 """Parity of the BENCHMARKED path at the BENCHMARKED sizes: every tcgen05 kernel variant that the C2 step
-(64x64x3 DCGAN, batch 128; reference call sites J:135-150, J:203-219) dispatches -- persistent two-M-tile conv, one-CTA-per-tile conv, halo-resident dgrad (shifted descriptors),
+(64x64x3 DCGAN, batch 128; reference call sites J:135-150, J:203-219) dispatches -- persistent two-M-tile conv, one-CTA-per-tile conv, halo-resident pixel-shuffle deconv (shifted descriptors),
 folded-BatchNorm (AFFINE) epilogue, the fused BatchNorm epilogues (EPI_STATS / EPI_BNBWD / EPI_ACTBWD), one-wave split-K weight gradient,
 M = 256 weight gradient, the 3-channel edge kernels -- runs here through the C-ABI test hook with the PRODUCTION dispatch, the hook reports
 which kernel ran (asserted), and the result is compared with the CPU oracle (oracle/dl4j_oracle.py ConvolutionLayer / Deconvolution2D
@@ -107,10 +107,10 @@ def test_fprop_production_dispatch(b200, case, epi):
 
 # conv geometry: dy [n,h/2,h/2,o] -> dx [n,h,h,c]  (= transposed-conv forward o -> c)
 DGRAD = [
-    ("D2 dgrad, D step (2N)", 2 * N, 32, 64, 128, "tc_dgrad_halo_kernel"),
+    ("D2 dgrad, D step (2N)", 2 * N, 32, 64, 128, "tc_conv_persistent_kernel<64,4,2>"),
     ("D3 dgrad, D step", 2 * N, 16, 128, 256, "tc_conv_persistent_kernel<128,4,2>"),
     ("D4 dgrad, D step", 2 * N, 8, 256, 512, "tc_conv_kernel<128,3>"),
-    ("G4 forward / D2 dgrad, G step (N)", N, 32, 64, 128, "tc_dgrad_halo_kernel"),
+    ("G4 forward / D2 dgrad, G step (N)", N, 32, 64, 128, "tc_conv_persistent_kernel<64,4,2>"),
     ("G3 forward / D3 dgrad, G step", N, 16, 128, 256, "tc_conv_kernel<128,3>"),
     ("G2 forward / D4 dgrad, G step", N, 8, 256, 512, "tc_conv_kernel<64,4>"),
 ]
