@@ -538,7 +538,8 @@ static void flush_pending_reduce(b2g_net* n, cudaStream_t s2) { if (n->pending.c
 // top_act_done: the epsilon handed in has already been multiplied by the last layer's act' (the mirror image of the above).
 static int32_t net_backward(b2g_net* n, const void* net_in, void* eps, int rows, int groups, bool want_wgrad, bool need_input_grad, bool allreduce_follows = false,
                             const TcEpi* input_act = nullptr, bool* input_act_done = nullptr, bool top_act_done = false) {
-  cudaStream_t s = n->ctx->stream, s2 = n->ctx->side; const int R = rows;
+  static int fork_on = -1; if (fork_on < 0) { const char* e = getenv("B2G_WGRAD_FORK"); fork_on = (e && e[0] == '0') ? 0 : 1; }
+  cudaStream_t s = n->ctx->stream, s2 = fork_on ? n->ctx->side : n->ctx->stream; const int R = rows;
   void* cur = eps;
   if (input_act_done) *input_act_done = false;
   static int fuse_bn = -1; if (fuse_bn < 0) { const char* e = getenv("B2G_FUSE_BN"); fuse_bn = (e && e[0] == '0') ? 0 : 1; }

@@ -646,6 +646,8 @@ static bool pick_row_tile(int N, int GH, int GW, int rows, int* Nt, int* Ht, int
 static int pick_bn(int OC) { return OC % 256 == 0 ? 256 : OC % 128 == 0 ? 128 : OC % 64 == 0 ? 64 : 0; }
 // Small layers (few M tiles) are latency-bound per CTA, not bandwidth-bound: prefer narrower N tiles until the grid covers the 148 SMs.
 static int pick_bn_fill(int OC, long m_tiles_x_phases) {
+  // measured (round 2): a threshold of 128 makes D3 fprop 2N / D4 dgrad 2N faster in isolation (17.1 -> 15.6, 17.5 -> 15.8 us, tile 128 x 256) and
+  // the whole step 1.6 % SLOWER (the wide-tile CTAs take an SM each while the weight-gradient stream wants to share it): 148 stays
   static int min_ctas = -1; if (min_ctas < 0) { const char* e = getenv("B2G_BN_MIN_CTAS"); min_ctas = e ? atoi(e) : 148; if (min_ctas < 1) min_ctas = 148; }
   int bn = pick_bn(OC);
   while (bn > 64 && m_tiles_x_phases * (OC / bn) < min_ctas) bn /= 2;
@@ -669,6 +671,7 @@ template <int BN, int STAGES, int EPI, bool AFFINE>
 static int launch_conv_e(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcConvParams& p, dim3 grid, cudaStream_t s) {
   using S = TcSmem<BN, STAGES, EPI>;
   TC_SET_SMEM_ONCE((tc_conv_kernel<BN, STAGES, EPI, AFFINE, false>), S::TOTAL);
+  // (an early pdl_trigger for grids that are resident at once was measured: the step got 1.1 % slower -- profiles/r02_experiments.md)
   launch_pdl(tc_conv_kernel<BN, STAGES, EPI, AFFINE, false>, dim3(grid), dim3(192), (size_t)(S::TOTAL), s, tmA, tmB, p);
   LAUNCHED();
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
