@@ -161,11 +161,20 @@ def cpu_stepper(cfg, engine, batch):
         from oracle import cpu_ref
         gs, ds, gin, din = build_specs(cfg)
         c = cpu_ref.CpuRefGan(gs, ds, cfg["z"], din, batch)
-        c.set_threads(cores)
         rng = np.random.default_rng(666)
         for net in (0, 1):          # DCGAN-style N(0, 0.02) weights on top of the BatchNorm defaults
             p = c.get_params(net); p += 0.02 * rng.standard_normal(p.size).astype(np.float32); c.set_params(net, p)
-        return (lambda data: c.step(*data)), f"oracle/cpu_ref.c: C+OpenMP restatement of DL4J nd4j-native (NCHW fp32, im2col + packed SGEMM + separate bias/activation/BatchNorm/Adam passes), {cores} threads", cores
+        # "all the host threads it can use": more threads than the small GEMMs can feed is slower (64 threads ran at half the rate of 16 on the
+        # GPU box), so the thread count is the best of a short ladder, one timed step each after a warm-up step
+        ladder = sorted({t for t in (cores, cores // 2, cores // 4, 16, 8) if 1 <= t <= cores}, reverse=True)
+        data = synthetic(cfg, batch, 667); c.set_threads(ladder[0]); c.step(*data)
+        best, best_t, tried = ladder[0], None, []
+        for t in ladder:
+            c.set_threads(t); t0 = time.perf_counter(); c.step(*data); dt = time.perf_counter() - t0; tried.append(f"{t}: {dt * 1e3:.0f} ms")
+            if best_t is None or dt < best_t: best, best_t = t, dt
+        c.set_threads(best)
+        return (lambda data: c.step(*data)), (f"oracle/cpu_ref.c: C+OpenMP restatement of DL4J nd4j-native (NCHW fp32, im2col + packed SGEMM + separate bias/activation/BatchNorm/Adam passes), "
+                                              f"{best} threads (best of one timed step each: {', '.join(tried)})"), best
     from oracle import dl4j_oracle as o
     G, D = _oracle_nets(cfg)
     if engine == "torch":
@@ -279,8 +288,9 @@ def tensor_rooflines(b, ctx, cfg, batch, peaks):
         except Exception:
             prof = None
     roof = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
-            "traffic": (prof or {}).get("dram_bytes_per_launch") if prof and prof.get("name") == dom["name"] else None,
-            "traffic_unit": "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r02_ncu_dominant.json)",
+            "traffic": ((prof or {}).get("workloads", {}).get(dom["name"]) or {}).get("dram_bytes_per_launch"),
+            "traffic_l2_to_sm": ((prof or {}).get("workloads", {}).get(dom["name"]) or {}).get("l2_to_sm_bytes_per_launch"),
+            "traffic_unit": "bytes/launch: `traffic` = ncu dram__bytes_read.sum + dram__bytes_write.sum, `traffic_l2_to_sm` = l1tex__m_xbar2l1tex_read_bytes.sum (profiles/r02_ncu_dominant.json, one `ncu --set full` launch of this workload)",
             "algorithmic_bytes": dom["bytes"], "kernel": f"{dom['kernel']}: {dom['name']}", "flops_per_launch": dom["flops"], "ms_per_launch": dom["ms"],
             "share_of_tensor_time": dom["ms"] * dom["count"] / tot_ms, "peak_source": peaks["source"] + " (burst cuBLAS bf16)",
             "how": "the tensor-core launch with the largest time share of the step, timed alone with CUDA events on the library stream (10 launches, warm L2)"}
@@ -346,6 +356,14 @@ def run_ours(args, cfg, rank, world, local_rank):
         ctx.comm_init(world, rank, ids[0])
     n = cfg["batch"]
     G, D, gan = make_gan(b, ctx, cfg, n)
+    dp_opts = {"grad_payload": "fp32", "sync_bn": False, "allreduce": "nccl"}      # data-parallel options (defaults; the env switches are for A/B runs)
+    if world > 1 and os.environ.get("B2G_P2P_AR", "1") != "0":       # collective: both nets, same order on every rank
+        ok = [D.enable_p2p_allreduce(), G.enable_p2p_allreduce()]
+        dp_opts["allreduce"] = "peer-memory kernel (CUDA IPC over NVLink)" if all(ok) else "nccl"
+    if world > 1 and os.environ.get("B2G_BENCH_AR_BF16") == "1":
+        G.set_grad_payload_bf16(True); D.set_grad_payload_bf16(True); dp_opts["grad_payload"] = "bf16"
+    if world > 1 and os.environ.get("B2G_BENCH_SYNC_BN") == "1":
+        G.set_sync_bn(True); D.set_sync_bn(True); dp_opts["sync_bn"] = True
     data = synthetic(cfg, n, 666 + rank)    # each rank draws its own slice
     pinned = [torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).pin_memory() for a in data]
     ptrs = [t.data_ptr() for t in pinned]
@@ -426,14 +444,14 @@ def run_ours(args, cfg, rank, world, local_rank):
         step_tf = F * ips / world / 1e12
         cpu_base = None       # the CPU leg runs on rank 0 at N=1 only (the other ranks would idle in the process group meanwhile)
         if world == 1 and not args.no_cpu:
-            cpu_ips, cpu_sec, cpu_sample, cpu_engine, cores = cpu_step_rate(args.config, n, 3, 1, budget_s=30.0)
+            cpu_ips, cpu_sec, cpu_sample, cpu_engine, cores = cpu_step_rate(args.config, n, 10, 1, budget_s=30.0)
             cpu_base = {"value": cpu_ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": f"3 steps x batch {cpu_sample} of the same workload, {cpu_engine}"}
         unit = "samples/s" if cfg.get("mlp") else "images/s"
         line = {
             "metric": "images/sec (full G+D step)", "value": ips, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": cfg["desc"], "global_batch": global_batch, "parallelism": f"dp{world}", "l2": "flushed between steps (256 MiB memset, outside the per-step CUDA-event brackets)",
-                       "fake_bn": "inference (gen.output, J:420)", "cuda_graph": os.environ.get("B2G_GRAPH_NCCL", "1") != "0" or world == 1, "step": "G(z_d) -> D update on real|fake -> G update through D"},
+                       "fake_bn": "inference (gen.output, J:420)", "cuda_graph": os.environ.get("B2G_GRAPH_NCCL", "1") != "0" or world == 1, "step": "G(z_d) -> D update on real|fake -> G update through D", **({"dp": dp_opts} if world > 1 else {})},
             "roofline": roof, "roofline_family": fam, "hbm": hbm,
             "step_roofline": {"algorithmic_gflop_per_image": F / 1e9, "achieved_tflops_per_gpu": step_tf, "peak": peaks["bf16_tflops_sustained"], "frac": step_tf / peaks["bf16_tflops_sustained"],
                               "peak_source": peaks["source"] + " (sustained cuBLAS bf16)"},

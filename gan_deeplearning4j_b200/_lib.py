@@ -96,6 +96,7 @@ PROTOTYPES = {
     "b2g_net_average_parameters": (_i32, [_vp]),
     "b2g_net_set_sync_bn": (_i32, [_vp, _i32]),
     "b2g_net_set_grad_payload_bf16": (_i32, [_vp, _i32]),
+    "b2g_net_enable_p2p_allreduce": (_i32, [_vp, C.POINTER(C.c_int32)]),
     "b2g_ctx_allreduce_test": (_i32, [_vp, _fp, _i64]),
     "b2g_test_conv": (_i32, [_vp, _i32, _i32, _i32, C.POINTER(ConvGeom), _fp, _fp, _fp, _i32, _fp]),
     "b2g_test_hbm_kernels": (_i32, [_vp, _i32, _i32, _i32, _fp]),

@@ -40,9 +40,10 @@ struct NcclId { char internal[128]; };
 typedef int (*fn_ncclGetUniqueId)(NcclId*);
 typedef int (*fn_ncclCommInitRank)(void**, int, NcclId, int);
 typedef int (*fn_ncclAllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_ncclAllGather)(const void*, void*, size_t, int, void*, cudaStream_t);
 typedef int (*fn_ncclCommDestroy)(void*);
 typedef const char* (*fn_ncclGetErrorString)(int);
-static struct { void* h; fn_ncclGetUniqueId uid; fn_ncclCommInitRank init; fn_ncclAllReduce ar; fn_ncclCommDestroy destroy; fn_ncclGetErrorString errstr; } g_nccl = {};
+static struct { void* h; fn_ncclGetUniqueId uid; fn_ncclCommInitRank init; fn_ncclAllReduce ar; fn_ncclAllGather ag; fn_ncclCommDestroy destroy; fn_ncclGetErrorString errstr; } g_nccl = {};
 static int32_t nccl_load() {
   if (g_nccl.h) return 0;
   const char* names[] = {"libnccl.so.2", "libnccl.so"};
@@ -51,6 +52,7 @@ static int32_t nccl_load() {
   g_nccl.uid = (fn_ncclGetUniqueId)dlsym(g_nccl.h, "ncclGetUniqueId");
   g_nccl.init = (fn_ncclCommInitRank)dlsym(g_nccl.h, "ncclCommInitRank");
   g_nccl.ar = (fn_ncclAllReduce)dlsym(g_nccl.h, "ncclAllReduce");
+  g_nccl.ag = (fn_ncclAllGather)dlsym(g_nccl.h, "ncclAllGather");
   g_nccl.destroy = (fn_ncclCommDestroy)dlsym(g_nccl.h, "ncclCommDestroy");
   g_nccl.errstr = (fn_ncclGetErrorString)dlsym(g_nccl.h, "ncclGetErrorString");
   if (!g_nccl.uid || !g_nccl.init || !g_nccl.ar || !g_nccl.destroy) return fail(B2G_ERR_NCCL, "libnccl is missing symbols");
@@ -69,6 +71,8 @@ struct b2g_ctx {
   cudaEvent_t ev_c0 = nullptr, ev_c1 = nullptr, ev_c2 = nullptr;
   cudaDeviceProp prop;
   void* comm = nullptr; int world = 1, rank = 0;
+  // gradient all-reduce over peer memory (b2g_net_enable_p2p_allreduce): this GPU's flag words, its {epoch, counter} and every rank's flags as mapped here
+  unsigned* p2p_flags = nullptr; unsigned* p2p_state = nullptr; unsigned* p2p_peer_flags[8] = {}; bool p2p_flags_mapped = false;
   bool tc_ok = false;
   cudaEvent_t t0 = nullptr, t1 = nullptr; void* flush_buf = nullptr; size_t flush_bytes = 0;
 };
@@ -128,6 +132,7 @@ struct b2g_net {
   bool grad_allreduce = true;          // false: parameter-averaging mode (b2g_net_average_parameters)
   bool sync_bn = false;                // cross-replica BatchNorm statistics: the 64-bit statistic accumulators are all-reduced
   bool ar_bf16 = false;                // gradient all-reduce payload in bf16 (half the bytes; default fp32 for parity)
+  bool p2p = false; float* p2p_peer_grads[8] = {};      // every rank's gradient vector as mapped into this process (CUDA IPC)
   __nv_bfloat16* ar_buf = nullptr;
   int ar_split_layer = -1; int64_t ar_split_off = 0;   // gradients of layers >= ar_split_layer (= grads[ar_split_off, n_params)) are all-reduced while backward continues
   bool ar_tail_sent = false;
@@ -671,6 +676,11 @@ static int32_t net_allreduce_grads(b2g_net* n) {
     k_nhwc_to_nchw_f32(PREC_BF16, n->ar_buf, n->grads, 1, 1, (int)n->n_params, c->stream);
     return 0;
   }
+  if (n->p2p) {        // one kernel over NVLink peer memory instead of the NCCL ring (measured on 2 x B200: see DESIGN.md)
+    P2pArgs a{}; for (int r = 0; r < c->world; ++r) { a.grads[r] = n->p2p_peer_grads[r]; a.flags[r] = c->p2p_peer_flags[r]; }
+    a.rank = c->rank; a.world = c->world; a.n = (size_t)n->n_params; a.state = c->p2p_state;
+    k_p2p_allreduce(a, c->stream); CHECK_KERNELS(); return 0;
+  }
   NC(g_nccl.ar(n->grads, n->grads, (size_t)n->n_params, /*ncclFloat32*/ 7, /*ncclSum*/ 0, c->comm, c->stream));
   return 0;
 }
@@ -707,6 +717,8 @@ extern "C" int32_t b2g_ctx_create(int32_t device, b2g_ctx** out) {
 }
 extern "C" int32_t b2g_ctx_destroy(b2g_ctx* c) {
   if (!c) return 0; cudaSetDevice(c->device);
+  if (c->p2p_flags_mapped) for (int r = 0; r < c->world; ++r) if (r != c->rank && c->p2p_peer_flags[r]) cudaIpcCloseMemHandle(c->p2p_peer_flags[r]);
+  if (c->p2p_flags) cudaFree(c->p2p_flags); if (c->p2p_state) cudaFree(c->p2p_state);
   if (c->comm && g_nccl.destroy) g_nccl.destroy(c->comm);
   if (c->t0) { cudaEventDestroy(c->t0); cudaEventDestroy(c->t1); } if (c->flush_buf) cudaFree(c->flush_buf);
   if (c->side) cudaStreamDestroy(c->side); if (c->side2) cudaStreamDestroy(c->side2); if (c->ev_a) cudaEventDestroy(c->ev_a); if (c->ev_b) cudaEventDestroy(c->ev_b);
@@ -750,6 +762,7 @@ extern "C" int32_t b2g_net_create(b2g_ctx* ctx, const b2g_net_config* cfg, const
 extern "C" int32_t b2g_net_destroy(b2g_net* n) {
   if (!n) return 0; cudaSetDevice(n->ctx->device); cudaStreamSynchronize(n->ctx->stream); cudaStreamSynchronize(n->ctx->side);
   for (auto e : n->ev_fork) if (e) cudaEventDestroy(e); for (auto e : n->ev_done) if (e) cudaEventDestroy(e); if (n->ev_join) cudaEventDestroy(n->ev_join);
+  if (n->p2p) for (int r = 0; r < n->ctx->world; ++r) if (r != n->ctx->rank && n->p2p_peer_grads[r]) cudaIpcCloseMemHandle(n->p2p_peer_grads[r]);
   for (void* p : n->allocs) cudaFree(p); delete n; return 0;
 }
 extern "C" int32_t b2g_net_num_params(b2g_net* n, int64_t* out) { if (!n || !out) return fail(B2G_ERR_ARG, "null"); *out = n->n_params; return 0; }
@@ -1119,6 +1132,46 @@ extern "C" int32_t b2g_net_set_grad_payload_bf16(b2g_net* n, int32_t enabled) {
   if (!n) return fail(B2G_ERR_ARG, "null"); CU(cudaSetDevice(n->ctx->device));
   if (enabled && !n->ar_buf) B2(dalloc(n, &n->ar_buf, sizeof(__nv_bfloat16) * (size_t)n->n_params));
   n->ar_bf16 = enabled != 0; return 0;
+}
+// COLLECTIVE (every rank, same order of nets): maps every rank's gradient vector and flag words into this process (cudaIpc*, handles
+// exchanged with ncclAllGather) and switches the net's gradient all-reduce to the peer-memory kernel (kernels_ew.cu p2p_allreduce_kernel).
+// If any rank cannot map (different nodes, IPC disabled) every rank stays on ncclAllReduce; *enabled reports the common outcome.
+extern "C" int32_t b2g_net_enable_p2p_allreduce(b2g_net* n, int32_t* enabled) {
+  if (!n) return fail(B2G_ERR_ARG, "null"); b2g_ctx* c = n->ctx; CU(cudaSetDevice(c->device)); if (enabled) *enabled = 0;
+  if (!c->comm || c->world < 2) return 0;
+  if (c->world > 8 || !g_nccl.ag) return 0;
+  cudaStream_t s = c->stream;
+  if (!c->p2p_flags) { CU(cudaMalloc(&c->p2p_flags, 16 * sizeof(unsigned))); CU(cudaMalloc(&c->p2p_state, 2 * sizeof(unsigned)));
+                       CU(cudaMemsetAsync(c->p2p_flags, 0, 16 * sizeof(unsigned), s)); CU(cudaMemsetAsync(c->p2p_state, 0, 2 * sizeof(unsigned), s)); CU(cudaStreamSynchronize(s)); }
+  struct Pair { cudaIpcMemHandle_t flags, grads; };
+  Pair mine; memset(&mine, 0, sizeof(mine)); float ok = 1.f;
+  if (cudaIpcGetMemHandle(&mine.flags, c->p2p_flags) != cudaSuccess || cudaIpcGetMemHandle(&mine.grads, n->grads) != cudaSuccess) { cudaGetLastError(); ok = 0.f; }
+  std::vector<Pair> all(c->world);
+  char *d_send = nullptr, *d_recv = nullptr; float* d_ok = nullptr;
+  CU(cudaMalloc(&d_send, sizeof(Pair))); CU(cudaMalloc(&d_recv, sizeof(Pair) * c->world)); CU(cudaMalloc(&d_ok, sizeof(float)));
+  CU(cudaMemcpyAsync(d_send, &mine, sizeof(Pair), cudaMemcpyHostToDevice, s));
+  NC(g_nccl.ag(d_send, d_recv, sizeof(Pair), /*ncclChar*/ 0, c->comm, s));
+  CU(cudaMemcpyAsync(all.data(), d_recv, sizeof(Pair) * c->world, cudaMemcpyDeviceToHost, s)); CU(cudaStreamSynchronize(s));
+  float* pg[8] = {}; unsigned* pf[8] = {};
+  for (int r = 0; r < c->world && ok > 0.f; ++r) {
+    if (r == c->rank) { pg[r] = n->grads; pf[r] = c->p2p_flags; continue; }
+    void* q = nullptr;
+    if (cudaIpcOpenMemHandle(&q, all[r].grads, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0.f; break; }
+    pg[r] = (float*)q;
+    if (c->p2p_flags_mapped) pf[r] = c->p2p_peer_flags[r];
+    else { if (cudaIpcOpenMemHandle(&q, all[r].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0.f; break; } pf[r] = (unsigned*)q; }
+  }
+  // the decision must be common: sum of the ranks' verdicts
+  CU(cudaMemcpyAsync(d_ok, &ok, sizeof(float), cudaMemcpyHostToDevice, s)); NC(g_nccl.ar(d_ok, d_ok, 1, 7, 0, c->comm, s));
+  float sum = 0.f; CU(cudaMemcpyAsync(&sum, d_ok, sizeof(float), cudaMemcpyDeviceToHost, s)); CU(cudaStreamSynchronize(s));
+  cudaFree(d_send); cudaFree(d_recv); cudaFree(d_ok);
+  if (sum < (float)c->world - 0.5f) {      // somebody failed: undo the mappings made here
+    for (int r = 0; r < c->world; ++r) { if (r == c->rank) continue; if (pg[r]) cudaIpcCloseMemHandle(pg[r]); if (!c->p2p_flags_mapped && pf[r]) cudaIpcCloseMemHandle(pf[r]); }
+    return 0;
+  }
+  for (int r = 0; r < c->world; ++r) { n->p2p_peer_grads[r] = pg[r]; c->p2p_peer_flags[r] = pf[r]; }
+  c->p2p_flags_mapped = true; n->p2p = true; if (enabled) *enabled = 1;
+  return 0;
 }
 extern "C" int32_t b2g_net_average_parameters(b2g_net* n) {
   if (!n) return fail(B2G_ERR_ARG, "null"); b2g_ctx* c = n->ctx; CU(cudaSetDevice(c->device));

@@ -119,6 +119,12 @@ void k_updater(float* params, const float* grads, float* st0, float* st1, const 
 static const int UPD_CHUNK = 4096;
 void k_fill_f32(float* p, float v, size_t n, cudaStream_t s);
 void k_scale_f32(float* p, float v, size_t n, cudaStream_t s);
+// Gradient all-reduce over NVLink peer memory (one process per GPU, buffers exchanged as CUDA IPC handles): ONE kernel per GPU does
+// entry barrier -> reduce-scatter (this GPU sums its 1/world slice from every peer, fixed rank order) -> all-gather (writes the sum into
+// every peer's buffer) -> exit barrier.  grads[r] / flags[r] are rank r's buffers as mapped into this process (r == rank: the local ones);
+// flags = 16 words per GPU (entry[8] | exit[8], indexed by the signalling rank), state = {epoch, finished-block counter} (local).
+struct P2pArgs { float* grads[8]; unsigned* flags[8]; int rank, world; size_t n; unsigned* state; };
+void k_p2p_allreduce(const P2pArgs& a, cudaStream_t s);
 
 // ---- GEMM-shaped kernels, SIMT (fp32 FMA) -----------------------------------------------------------------
 // fprop:  out[m][o] = act(sum_k A[m][k] w[o][k] + bias[o]),  m=(n,oy,ox), k=(r,s,c);  w layout [O][KH][KW][C]

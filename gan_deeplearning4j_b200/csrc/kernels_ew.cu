@@ -554,6 +554,58 @@ void k_bn_bwd_apply_acc(const void* x, const void* eps_out, void* eps_in, int ro
   LAUNCHED();
 }
 
+
+// ---------------------------------------------------------------- gradient all-reduce over peer memory ----------------
+// (kernels.h: P2pArgs).  System-scope release / acquire on the flag words order the peer-memory data accesses; every slice of the vector has
+// exactly one reader-writer GPU, so the sum is written in place.  The sum order is rank 0..W-1 on every GPU: all replicas hold identical bits.
+// Waits are bounded: a rank that never arrives traps the kernel (an error the host sees) instead of hanging the GPU.
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) { unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void p2p_wait_all(const unsigned* flags, int world, unsigned e) {
+  for (int r = 0; r < world; ++r) {
+    unsigned it = 0;
+    while ((int)(ld_acquire_sys(flags + r) - e) < 0) { if (++it > (1u << 27)) __trap(); __nanosleep(32); }
+  }
+}
+__global__ void __launch_bounds__(512) p2p_allreduce_kernel(const P2pArgs a) {
+  __shared__ unsigned s_e;
+  if (threadIdx.x == 0) s_e = *reinterpret_cast<volatile unsigned*>(a.state) + 1;
+  __syncthreads();
+  const unsigned e = s_e; const int W = a.world;
+  unsigned* mine = a.flags[a.rank];
+  if (blockIdx.x == 0 && threadIdx.x < W) st_release_sys(a.flags[threadIdx.x] + a.rank, e);       // "my gradients are final" -> every rank (this kernel runs after backward in stream order)
+  if (threadIdx.x == 0) p2p_wait_all(mine, W, e);                                                   // every rank's gradients are final
+  __syncthreads();
+  const size_t nv = a.n / 4, chunk = (nv + W - 1) / W, v0 = min(nv, (size_t)a.rank * chunk), v1 = min(nv, v0 + chunk);
+  for (size_t i = v0 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < v1; i += (size_t)gridDim.x * blockDim.x) {
+    float4 acc = __ldcg(reinterpret_cast<const float4*>(a.grads[0]) + i);
+    for (int r = 1; r < W; ++r) { const float4 v = __ldcg(reinterpret_cast<const float4*>(a.grads[r]) + i); acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+    for (int r = 0; r < W; ++r) __stcg(reinterpret_cast<float4*>(a.grads[r]) + i, acc);
+  }
+  if (a.rank == W - 1 && blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {      // the last n % 4 elements
+    const size_t i = nv * 4 + threadIdx.x; float acc = __ldcg(a.grads[0] + i);
+    for (int r = 1; r < W; ++r) acc += __ldcg(a.grads[r] + i);
+    for (int r = 0; r < W; ++r) __stcg(a.grads[r] + i, acc);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(a.state + 1, 1u);
+    if (t == gridDim.x - 1) {            // last block of this GPU: its slice is complete everywhere
+      a.state[1] = 0;
+      for (int r = 0; r < W; ++r) st_release_sys(a.flags[r] + 8 + a.rank, e);
+      p2p_wait_all(mine + 8, W, e);      // every slice has landed in this GPU's buffer: the updater may read it
+      *reinterpret_cast<volatile unsigned*>(a.state) = e;
+      __threadfence();
+    }
+  }
+}
+void k_p2p_allreduce(const P2pArgs& a, cudaStream_t s) {
+  const size_t slice = (a.n / 4 + a.world - 1) / a.world;
+  int blocks = (int)((slice + 2047) / 2048); if (blocks > 120) blocks = 120; if (blocks < 1) blocks = 1;      // all blocks resident at once (the barriers spin)
+  p2p_allreduce_kernel<<<blocks, 512, 0, s>>>(a); LAUNCHED();      // plain launch: starts after backward has completed, never lets the updater in early
+}
+
 // ---------------------------------------------------------------- activations ---------------------------
 template <typename T>
 __global__ void act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, size_t n, int act, float alpha) { pdl_enter();

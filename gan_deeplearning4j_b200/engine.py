@@ -220,6 +220,13 @@ class Net:
     def set_grad_payload_bf16(self, enabled: bool):
         check(self.lib.b2g_net_set_grad_payload_bf16(self.h, int(enabled)))
 
+    def enable_p2p_allreduce(self) -> bool:
+        """COLLECTIVE (every rank, nets in the same order): gradient all-reduce as one kernel over NVLink peer memory (CUDA IPC) instead of
+        ncclAllReduce; returns whether every rank could map its peers (otherwise all ranks stay on NCCL)."""
+        out = C.c_int32(0)
+        check(self.lib.b2g_net_enable_p2p_allreduce(self.h, C.byref(out)))
+        return bool(out.value)
+
     def average_parameters(self):
         """ParameterAveragingTrainingMaster: params and updater state <- mean over ranks (J:325-330)."""
         check(self.lib.b2g_net_average_parameters(self.h))

@@ -204,6 +204,11 @@ int32_t b2g_net_average_parameters(b2g_net* net);
  * grad_payload_bf16: the gradient all-reduce travels as bf16 (half the bytes); default fp32 (data parallel == single GPU, bit for bit). */
 int32_t b2g_net_set_sync_bn(b2g_net* net, int32_t enabled);
 int32_t b2g_net_set_grad_payload_bf16(b2g_net* net, int32_t enabled);
+/* COLLECTIVE over the communicator (every rank, nets in the same order): map every rank's gradient vector into this process (CUDA IPC over
+ * NVLink) and run the gradient all-reduce as ONE peer-memory kernel (reduce-scatter + all-gather, fixed summation order: replicas stay
+ * bit-identical) instead of ncclAllReduce.  *enabled = 1 if every rank could map, else all ranks keep NCCL.  Replaces the network transport of
+ * ParameterAveragingTrainingMaster's aggregation (reference J:325-333) on one NVSwitch node. */
+int32_t b2g_net_enable_p2p_allreduce(b2g_net* net, int32_t* enabled);
 /* all-reduce an arbitrary device float buffer on the ctx stream (tests) */
 int32_t b2g_ctx_allreduce_test(b2g_ctx* ctx, float* host_inout, int64_t n);
 

@@ -1,5 +1,5 @@
 """A/B the library's experiment switches in ONE gpurun call: runs bench.py (short, no CPU leg) once per environment variant and prints a table.
-usage: python tools/ab_switches.py [--steps 100] [--config c2] "B2G_TC_DEEP=1" "B2G_WGRAD_CTAS=296" "B2G_TC_DEEP=1 B2G_AR_OVERLAP=1" ...
+usage: python tools/ab_switches.py [--steps 100] [--config c2] [--gpus 2] "B2G_TC_DEEP=1" "B2G_WGRAD_CTAS=296" "B2G_TC_DEEP=1 B2G_AR_OVERLAP=1" ...
 The first row is always the default configuration.  Numbers are for comparison inside one call only (same box, same clocks)."""
 import json
 import os
@@ -8,18 +8,20 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 args = sys.argv[1:]
-steps, config = "100", "c2"
+steps, config, gpus = "100", "c2", "1"
 while args and args[0].startswith("--"):
     k = args.pop(0)
     if k == "--steps": steps = args.pop(0)
     elif k == "--config": config = args.pop(0)
+    elif k == "--gpus": gpus = args.pop(0)
 variants = [""] + args
 rows = []
 for v in variants:
     env = dict(os.environ)
     for kv in v.split():
         k, _, val = kv.partition("="); env[k] = val
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", steps, "--config", config, "--no-cpu", "--no-extra"], capture_output=True, text=True, env=env)
+    launcher = [sys.executable] if gpus == "1" else [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", gpus, "--master-addr", "127.0.0.1", "--master-port", str(29520 + len(rows))]
+    out = subprocess.run(launcher + [os.path.join(ROOT, "bench.py"), "--gpus", gpus, "--steps", steps, "--config", config, "--no-cpu", "--no-extra"], capture_output=True, text=True, env=env)
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     if out.returncode or not lines:
         rows.append((v or "(default)", float("nan"), float("nan"), out.stderr.strip().splitlines()[-1][:80] if out.stderr.strip() else "failed")); continue

@@ -35,6 +35,11 @@ def make(seed_shift, prec):
     gs, ds = m.dcgan_generator(size, z, nf, 3, lr=1e-3), m.dcgan_discriminator(size, nf, 3, lr=1e-3)
     G = b.Net(ctx, gs, (z,), max_batch=n, precision=prec, xent_clip_eps=0.0, seed=1)
     D = b.Net(ctx, ds, (3, size, size), max_batch=2 * n, precision=prec, xent_clip_eps=0.0, bn_groups=2, seed=2)
+    if os.environ.get("B2G_P2P_AR", "1") != "0":        # collective: gradient all-reduce as one peer-memory kernel (CUDA IPC), else ncclAllReduce
+        ok = [D.enable_p2p_allreduce(), G.enable_p2p_allreduce()]
+        out["allreduce_transport"] = "peer-memory kernel" if all(ok) else "nccl (peer mapping unavailable)"
+    else:
+        out["allreduce_transport"] = "nccl"
     rng = np.random.default_rng(100 + seed_shift)
     data = [rng.uniform(-1, 1, (n, 3, size, size)), rng.uniform(-1, 1, (n, z)), rng.uniform(-1, 1, (n, z)),
             1 + 0.05 * rng.standard_normal((n, 1)), 0.05 * rng.standard_normal((n, 1)), np.ones((n, 1))]
