@@ -31,6 +31,7 @@ public final class Native {
     public static native int netSimtGemmCalls(long net, long outAddr);
     public static native int netSetSyncBn(long net, int enabled);
     public static native int netSetGradPayloadBf16(long net, int enabled);
+    public static native int netEnableP2pAllreduce(long net, long outEnabledAddr);   // collective over the communicator: b2g_net_enable_p2p_allreduce
     public static native int netOutput(long net, long xAddr, int batch, int train, long outAddr);
     public static native int netFit(long net, long xAddr, long yAddr, int batch, long scoreAddr);
     public static native int ganCreate(long gen, long dis, int fakeBnTrain, int useGraph, long outHandleAddr);

@@ -45,6 +45,7 @@ FN(netSetIteration)(JNIEnv_*, jclass, jlong net, jlong it) { return b2g_net_set_
 FN(netSimtGemmCalls)(JNIEnv_*, jclass, jlong net, jlong outAddr) { return b2g_net_simt_gemm_calls(P(b2g_net*, net), P(uint64_t*, outAddr)); }
 FN(netSetSyncBn)(JNIEnv_*, jclass, jlong net, jint enabled) { return b2g_net_set_sync_bn(P(b2g_net*, net), enabled); }
 FN(netSetGradPayloadBf16)(JNIEnv_*, jclass, jlong net, jint enabled) { return b2g_net_set_grad_payload_bf16(P(b2g_net*, net), enabled); }
+FN(netEnableP2pAllreduce)(JNIEnv_*, jclass, jlong net, jlong outAddr) { return b2g_net_enable_p2p_allreduce(P(b2g_net*, net), P(int32_t*, outAddr)); }
 FN(netOutput)(JNIEnv_*, jclass, jlong net, jlong xAddr, jint batch, jint train, jlong outAddr) {
   return b2g_net_output(P(b2g_net*, net), P(const float*, xAddr), batch, train, P(float*, outAddr));
 }

@@ -41,7 +41,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 def test_jni_symbols_exported_without_jni_h(lib):
     out = subprocess.run(["nm", "-D", "--defined-only", os.path.join(ROOT, "gan_deeplearning4j_b200", "lib", "libb200gan.so")], capture_output=True, text=True).stdout
     for n in ("ctxCreate", "netCreate", "netFit", "netOutput", "netSetParam", "netGetParam", "ganCreate", "ganStep", "ctxCommInit",
-              "netSetUpdaterState", "netGetIteration", "netSetIteration", "netSetSyncBn", "netAverageParameters"):
+              "netSetUpdaterState", "netGetIteration", "netSetIteration", "netSetSyncBn", "netAverageParameters", "netEnableP2pAllreduce"):
         assert f"Java_org_deeplearning4j_b200_Native_{n}" in out
 
 
