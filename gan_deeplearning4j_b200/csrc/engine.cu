@@ -627,6 +627,10 @@ static int32_t net_backward(b2g_net* n, const void* net_in, void* eps, int rows,
           B2(gemm_fprop(n, l, g, cur, nullptr, nx, ACT_IDENTITY, 0.f, nullptr, can ? &e : nullptr, &fused)); note_fused(tgt, e, fused); cur = nx; }
       } break;
       case B2G_LAYER_BATCHNORM: {
+        // FrozenLayer BatchNorm ran in test mode (running statistics): it has no parameter gradients, and its input gradient would be the
+        // affine-only dy * gamma * invstd, not the batch-statistics form below.  The reference never differentiates through its frozen
+        // trunk (J:335-370: only the new head trains), so that case is refused rather than computed wrongly.
+        if (d.frozen) { if (need_in) return fail(B2G_ERR_UNSUPPORTED, "layer %d: a gradient through a frozen BatchNorm (trainable layer or input gradient below it) is not implemented", i); break; }
         int rows_pg = (R / groups) * l.oh * l.ow; void* nx = need_in ? other(cur) : nullptr;
         if (l.fwd_fused && l.fwd_groups == groups) {
           if (!l.bwd_premul) k_bn_bwd_stats_acc(lin, cur, rows_pg, l.oc, groups, l.bn_coef, l.fused_act, l.fused_alpha, l.acc_bwd, s);
