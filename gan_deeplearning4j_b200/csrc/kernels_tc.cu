@@ -1288,12 +1288,12 @@ struct TcWgradSmem {
   static constexpr int B_BYTES = (BNW / 64) * 64 * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int STG_OFF = BAR_OFF + 256;           // 4 epilogue warps x 4 KB store staging
-  static constexpr int TOTAL = STG_OFF + 4 * 4096 + 1024;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;      // (the epilogue's store staging reuses the drained ring: 8 warps x 4 KB)
+  static_assert(STAGES * STAGE_BYTES >= 8 * 4096, "store staging lives in the pipeline ring");
 };
 
 template <int BNW, int STAGES>
-__global__ void __launch_bounds__(192) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, const TcWgradParams p) {
+__global__ void __launch_bounds__(320) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, const TcWgradParams p) {
   using S = TcWgradSmem<BNW, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -1363,24 +1363,27 @@ __global__ void __launch_bounds__(192) tc_wgrad_kernel(const __grid_constant__ C
     if (elect_one_sync()) umma_commit(bar_accum);
     __syncwarp();
   } else {
-    const int q = warp & 3, row = q * 32 + lane;
+    // EIGHT epilogue warps: the single-wave grid exposes the whole epilogue (128 KB of fp32 partials per CTA), so two warps share each TMEM
+    // lane quadrant (warp % 4) and split the columns; their store staging lives in the drained pipeline ring
+    const int q = warp & 3, row = q * 32 + lane, half = (warp - 2) >> 2;
+    constexpr int HC = BNW >= 64 ? BNW / 2 : BNW;
     float* orow = p.out + (size_t)split * p.split_stride + (size_t)(o0 + row) * p.taps * p.C + col0;
     if (num_kb > 0) {
-      mbar_wait(bar_accum, 0);
+      mbar_wait_relaxed(bar_accum, 0);
       tc_fence_after();
-#pragma unroll 1
       float* rowp[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) rowp[i] = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, (unsigned long long)orow, i * 4 + (lane >> 3))) + (lane & 7) * 4;
-      float4* stg = reinterpret_cast<float4*>(smem_gen + S::STG_OFF) + q * 256;
-      for (int cc = 0; cc < BNW; cc += 32) {
+      float4* stg = reinterpret_cast<float4*>(smem_gen) + (warp - 2) * 256;
+#pragma unroll 1
+      for (int cc = half * HC; cc < (half + 1) * HC && cc < BNW; cc += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
         tmem_ld_wait();
         store_rows_f32x32(v, stg, rowp, cc, lane);
       }
     } else {
-      for (int cc = 0; cc < BNW; cc += 4) *reinterpret_cast<float4*>(orow + cc) = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int cc = half * HC; cc < (half + 1) * HC && cc < BNW; cc += 4) *reinterpret_cast<float4*>(orow + cc) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     tc_fence_before();
   }
@@ -1393,9 +1396,9 @@ __global__ void __launch_bounds__(192) tc_wgrad_kernel(const __grid_constant__ C
 // O >= 256 layers (D3, D4, G2, G3).  A separate kernel so that the measured tc_wgrad_kernel above stays untouched.
 struct TcWgrad2Smem {
   static constexpr int A_BYTES = 4 * 64 * 128, B_BYTES = 4 * 64 * 128, STAGE_BYTES = A_BYTES + B_BYTES, STAGES = 3;
-  static constexpr int BAR_OFF = STAGES * STAGE_BYTES, STG_OFF = BAR_OFF + 256, TOTAL = STG_OFF + 4 * 4096 + 1024;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES, TOTAL = BAR_OFF + 256 + 1024;      // store staging reuses the drained ring
 };
-__global__ void __launch_bounds__(192) tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, const TcWgradParams p) {
+__global__ void __launch_bounds__(320) tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, const TcWgradParams p) {
   using S = TcWgrad2Smem; constexpr int STAGES = S::STAGES, BNW = 256;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -1463,18 +1466,18 @@ __global__ void __launch_bounds__(192) tc_wgrad2_kernel(const __grid_constant__ 
     if (elect_one_sync()) umma_commit(bar_accum);
     __syncwarp();
   } else {
-    const int q = warp & 3, row = q * 32 + lane;
-    if (num_kb > 0) { mbar_wait(bar_accum, 0); tc_fence_after(); }
+    const int q = warp & 3, row = q * 32 + lane, half = (warp - 2) >> 2;      // eight epilogue warps: see tc_wgrad_kernel
+    if (num_kb > 0) { mbar_wait_relaxed(bar_accum, 0); tc_fence_after(); }
 #pragma unroll 1
     for (int m = 0; m < 2; ++m) {
       float* orow = p.out + (size_t)split * p.split_stride + (size_t)(o0 + m * 128 + row) * p.taps * p.C + col0;
       if (num_kb > 0) {
-#pragma unroll 1
         float* rowp[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) rowp[i] = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, (unsigned long long)orow, i * 4 + (lane >> 3))) + (lane & 7) * 4;
-        float4* stg = reinterpret_cast<float4*>(smem_gen + S::STG_OFF) + q * 256;
-        for (int cc = 0; cc < BNW; cc += 32) {
+        float4* stg = reinterpret_cast<float4*>(smem_gen) + (warp - 2) * 256;
+#pragma unroll 1
+        for (int cc = half * (BNW / 2); cc < (half + 1) * (BNW / 2); cc += 32) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * BNW + cc), v);
           tmem_ld_wait();
@@ -1523,7 +1526,7 @@ template <int BNW, int STAGES>
 static int launch_wgrad(const CUtensorMap& tmDy, const CUtensorMap& tmX, const TcWgradParams& p, dim3 grid, cudaStream_t s, const char* name) {
   using S = TcWgradSmem<BNW, STAGES>;
   TC_SET_SMEM_ONCE((tc_wgrad_kernel<BNW, STAGES>), S::TOTAL);
-  launch_pdl(tc_wgrad_kernel<BNW, STAGES>, dim3(grid), dim3(192), (size_t)(S::TOTAL), s, tmDy, tmX, p);
+  launch_pdl(tc_wgrad_kernel<BNW, STAGES>, dim3(grid), dim3(320), (size_t)(S::TOTAL), s, tmDy, tmX, p);
   LAUNCHED(); g_tc_last_kernel = name;
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
 }
@@ -1557,7 +1560,7 @@ int k_tc_wgrad(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* d
   if (wgrad_mt2(g)) {
     TC_SET_SMEM_ONCE(tc_wgrad2_kernel, TcWgrad2Smem::TOTAL);
     grid.z = (unsigned)(g.O / 256);
-    launch_pdl(tc_wgrad2_kernel, dim3(grid), dim3(192), (size_t)(TcWgrad2Smem::TOTAL), s, tmDy, tmX, p); LAUNCHED(); g_tc_last_kernel = "tc_wgrad2_kernel";
+    launch_pdl(tc_wgrad2_kernel, dim3(grid), dim3(320), (size_t)(TcWgrad2Smem::TOTAL), s, tmDy, tmX, p); LAUNCHED(); g_tc_last_kernel = "tc_wgrad2_kernel";
     rc = cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
   } else
   switch (BNW) {
