@@ -165,14 +165,14 @@ WGRAD = [
     ("D3 wgrad, D step", 2 * N, 16, 128, 256, "tc_wgrad2_kernel"),
     ("D4 wgrad, D step", 2 * N, 8, 256, 512, "tc_wgrad2_kernel"),
     ("G4 wgrad (N)", N, 32, 64, 128, "tc_wgrad_kernel<256,4>"),
-    ("G3 wgrad", N, 16, 128, 256, "tc_wgrad_kernel<256,4>"),
-    ("G2 wgrad", N, 8, 256, 512, "tc_wgrad_kernel<256,4>"),
+    ("G3 wgrad", N, 16, 128, 256, "tc_wgrad2_kernel"),
+    ("G2 wgrad", N, 8, 256, 512, "tc_wgrad2_kernel"),
 ]
 
 
 @pytest.mark.parametrize("case", WGRAD, ids=[c[0] for c in WGRAD])
 def test_wgrad_production_dispatch(b200, case):
-    """dW = sum over the whole batch: one-wave split-K grids (<= 148 CTAs) with fp32 partials and the fixed-order reduction; M = 256 kernel
+    """dW = sum over the whole batch: half-wave split-K grids (<= 74 CTAs, beside the input-gradient chain) with fp32 partials and the fixed-order reduction; M = 256 kernel
     where each CTA still walks >= 12 K-blocks.  Oracle: ConvolutionLayer.backpropGradient on image chunks, summed (dW is linear in the batch)."""
     b, ctx = b200
     name, n, h, c, oc, kernel = case
