@@ -1229,7 +1229,7 @@ int k_tc_edge_conv(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat1
   p.tiles_total = g.N * p.tiles_y; p.act = act; p.alpha = alpha;
   const size_t smem = 1024 + 24576 + EDGE_SLAB_BYTES + 64 + 4 * 2048;
   TC_SET_SMEM_ONCE(tc_edge_conv_kernel, smem);
-  static int target = -1; if (target < 0) { const char* e = getenv("B2G_EDGE_CONV_CTAS"); target = e ? atoi(e) : 592; if (target < 1) target = 592; }
+  static int target = -1; if (target < 0) { const char* e = getenv("B2G_EDGE_CONV_CTAS"); target = e ? atoi(e) : 1184; if (target < 1) target = 1184; }      // measured (round 2): 296 -> 0.8816, 592 -> 0.8834, 1184 -> 0.8759 ms per step
   p.tiles_per_cta = (p.tiles_total + target - 1) / target;
   launch_pdl(tc_edge_conv_kernel, dim3(dim3((unsigned)((p.tiles_total + p.tiles_per_cta - 1) / p.tiles_per_cta), (unsigned)(g.O / 64))), dim3(128), (size_t)(smem), s, p);
   LAUNCHED(); g_tc_last_kernel = "tc_edge_conv_kernel";
@@ -1391,107 +1391,9 @@ __global__ void __launch_bounds__(320) tc_wgrad_kernel(const __grid_constant__ C
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, BNW < 32 ? 32 : BNW); }
 }
 
-// Experiment (B2G_WGRAD_MT2=1, not yet measured): one CTA owns 256 output channels -- four dy blocks and two accumulators (2 x 256 = all 512
-// TMEM columns) -- so each activation (x) tile in shared memory feeds twice the MMAs: bytes out of L2 per MAC drop by a third for the
-// O >= 256 layers (D3, D4, G2, G3).  A separate kernel so that the measured tc_wgrad_kernel above stays untouched.
-struct TcWgrad2Smem {
-  static constexpr int A_BYTES = 4 * 64 * 128, B_BYTES = 4 * 64 * 128, STAGE_BYTES = A_BYTES + B_BYTES, STAGES = 3;
-  static constexpr int BAR_OFF = STAGES * STAGE_BYTES, TOTAL = BAR_OFF + 256 + 1024;      // store staging reuses the drained ring
-};
-__global__ void __launch_bounds__(320) tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, const TcWgradParams p) {
-  using S = TcWgrad2Smem; constexpr int STAGES = S::STAGES, BNW = 256;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_full = smem_base + S::BAR_OFF, bar_empty = bar_full + 8 * STAGES, bar_accum = bar_empty + 8 * STAGES;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + S::BAR_OFF + 8 * (2 * STAGES + 1));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int split = blockIdx.x, col0 = blockIdx.y * BNW, o0 = blockIdx.z * 256;
-  const int kb_beg = split * p.kb_per_split, kb_end = min(p.kb_total, kb_beg + p.kb_per_split);
-  const int num_kb = max(0, kb_end - kb_beg);
-  if (warp == 0 && lane == 0) {
-    prefetch_map(&tmDy); prefetch_map(&tmX);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    mbar_init(bar_accum, 1);
-    fence_mbar_init();
-  }
-  if (warp == 1) { tmem_alloc(smem_u32((const void*)tmem_slot), 512); tmem_relinquish(); }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  pdl_trigger();      // single-wave grid: the successor may be scheduled behind us right away
-  pdl_wait();         // barrier init / TMEM allocation above overlap the predecessor's tail; global memory is touched only below
-  if (warp == 0) {
-    int xc[4], xw[4], xh[4];           // as in tc_wgrad_kernel: converged warp, elected lane issues, nothing but counters inside the loop
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { const int col = col0 + j * 64, tap = col / p.C; xc[j] = col % p.C; xw[j] = -p.PW + tap % p.KW; xh[j] = -p.PH + tap / p.KW; }
-    int n0, y0;
-    if (p.Nt > 1) { n0 = kb_beg * p.Nt; y0 = 0; } else { n0 = kb_beg / p.tiles_y; y0 = (kb_beg % p.tiles_y) * p.Ht; }
-    int s = 0; uint32_t ph = 0;
-    for (int i = 0; i < num_kb; ++i) {
-      const int kb = kb_beg + i;
-      mbar_wait(bar_empty + 8 * s, ph ^ 1);
-      if (elect_one_sync()) {
-        mbar_expect_tx(bar_full + 8 * s, S::STAGE_BYTES);
-        const uint32_t a = smem_base + s * S::STAGE_BYTES, b = a + S::A_BYTES;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) tma_load_2d(a + j * 8192, &tmDy, bar_full + 8 * s, o0 + 64 * j, kb * 64);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) tma_load_4d(b + j * 8192, &tmX, bar_full + 8 * s, xc[j], xw[j], y0 * p.SH + xh[j], n0);
-      }
-      __syncwarp();
-      if (++s == STAGES) { s = 0; ph ^= 1; }
-      if (p.Nt > 1) n0 += p.Nt; else { y0 += p.Ht; if (y0 >= p.tiles_y * p.Ht) { y0 = 0; ++n0; } }
-    }
-  } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc(128, BNW, 1, 1);
-    int s = 0; uint32_t ph = 0;
-    for (int i = 0; i < num_kb; ++i) {
-      mbar_wait(bar_full + 8 * s, ph);
-      tc_fence_after();
-      if (elect_one_sync()) {
-        const uint32_t a = smem_base + s * S::STAGE_BYTES, b = a + S::A_BYTES;
-        const uint64_t da = desc_mnmajor_sw128(a, 8192), db = desc_mnmajor_sw128(b, 8192);
-#pragma unroll
-        for (int m = 0; m < 2; ++m)
-#pragma unroll
-          for (int k = 0; k < 4; ++k)      // +1024 = the second 128-channel half of dy (16 KB), +128 = 16 pixel rows
-            umma_bf16(tmem_base + m * BNW, da + 1024 * m + 128 * k, db + 128 * k, idesc, (i | k) != 0);
-        umma_commit(bar_empty + 8 * s);
-      }
-      __syncwarp();
-      if (++s == STAGES) { s = 0; ph ^= 1; }
-    }
-    if (elect_one_sync()) umma_commit(bar_accum);
-    __syncwarp();
-  } else {
-    const int q = warp & 3, row = q * 32 + lane, half = (warp - 2) >> 2;      // eight epilogue warps: see tc_wgrad_kernel
-    if (num_kb > 0) { mbar_wait_relaxed(bar_accum, 0); tc_fence_after(); }
-#pragma unroll 1
-    for (int m = 0; m < 2; ++m) {
-      float* orow = p.out + (size_t)split * p.split_stride + (size_t)(o0 + m * 128 + row) * p.taps * p.C + col0;
-      if (num_kb > 0) {
-        float* rowp[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) rowp[i] = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, (unsigned long long)orow, i * 4 + (lane >> 3))) + (lane & 7) * 4;
-        float4* stg = reinterpret_cast<float4*>(smem_gen) + (warp - 2) * 256;
-#pragma unroll 1
-        for (int cc = half * (BNW / 2); cc < (half + 1) * (BNW / 2); cc += 32) {
-          uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * BNW + cc), v);
-          tmem_ld_wait();
-          store_rows_f32x32(v, stg, rowp, cc, lane);
-        }
-      } else {
-        for (int cc = 0; cc < BNW; cc += 4) *reinterpret_cast<float4*>(orow + cc) = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
-}
+// (An M = 256 variant -- four dy blocks, two accumulators = all 512 TMEM columns, each activation tile shared by 256 output channels -- was kept
+// through most of round 2: 7-14 % faster alone on the O >= 256 layers, 1-2 % SLOWER inside the step once the weight gradients ran as half-wave
+// grids beside the input-gradient chain (profiles/r02_experiments.md).  Removed.)
 
 static int wgrad_bnw(const ConvGeom& g) { if (g.C % 64) return 0; const long cols = (long)g.KH * g.KW * g.C; return cols % 256 == 0 ? 256 : cols % 128 == 0 ? 128 : 64; }
 // CTA target of the split-K weight gradients.  Measured (round 2, whole C2 step): 296 -> 0.936 ms, 148 -> 0.895, 111 -> 0.886, 74 -> 0.876, 56 -> 0.885,
@@ -1504,17 +1406,7 @@ static int wgrad_splits_for(const ConvGeom& g, int o_tile) {
   long tiles = (long)(g.O / o_tile) * (g.KH * g.KW * g.C / bnw), kbt = (long)g.N * g.OH * g.OW / 64;
   long sp = wgrad_target() / tiles, cap = kbt / 8; if (cap < 1) cap = 1; if (sp > cap) sp = cap; if (sp < 1) sp = 1; return (int)sp;
 }
-// M = 256 (two accumulators, tc_wgrad2_kernel) shares every activation tile between 256 output channels.  Measured on B200 (round 2,
-// profiles/r02_kernel_bench_mt2.md): a win where each CTA still walks >= 12 K-blocks (D3 39.7 -> 37.0 us, D4 43.1 -> 37.0 us), a loss where
-// the doubled tile leaves 7-8 K-blocks per CTA (G2 29.2 -> 30.9, G3 28.3 -> 30.9): prologue / epilogue dominate there.  B2G_WGRAD_MT2=0|1 forces.
-static bool wgrad_mt2(const ConvGeom& g) {
-  static int force = -2; if (force == -2) { const char* e = getenv("B2G_WGRAD_MT2"); force = e ? (e[0] == '1' ? 1 : 0) : -1; }
-  if (g.O % 256 || wgrad_bnw(g) != 256 || force == 0) return false;
-  if (force == 1) return true;
-  const long kbt = (long)g.N * g.OH * g.OW / 64; const int sp = wgrad_splits_for(g, 256);
-  return (kbt + sp - 1) / sp >= 12;
-}
-static int tc_wgrad_splits(const ConvGeom& g) { return wgrad_splits_for(g, wgrad_mt2(g) ? 256 : 128); }
+static int tc_wgrad_splits(const ConvGeom& g) { return wgrad_splits_for(g, 128); }
 bool tc_wgrad_supported(const ConvGeom& g) {
   int a, b, c;
   return g.O % 128 == 0 && wgrad_bnw(g) != 0 && g.SH >= 1 && g.SH <= 2 && g.SW == g.SH && ((long)g.N * g.OH * g.OW) % 64 == 0 &&
@@ -1522,7 +1414,7 @@ bool tc_wgrad_supported(const ConvGeom& g) {
 }
 size_t k_tc_wgrad_scratch_floats(const ConvGeom& g) {
   if (!tc_wgrad_supported(g)) return 0;
-  return (size_t)std::max(wgrad_splits_for(g, 128), g.O % 256 == 0 ? wgrad_splits_for(g, 256) : 1) * g.O * g.KH * g.KW * g.C;
+  return (size_t)wgrad_splits_for(g, 128) * g.O * g.KH * g.KW * g.C;
 }
 
 template <int BNW, int STAGES>
@@ -1560,12 +1452,6 @@ int k_tc_wgrad(const ConvGeom& g, const __nv_bfloat16* x, const __nv_bfloat16* d
     if (make_map_bf16(&tmX, x, 4, dims, strides, box, es)) return -1; }
   dim3 grid((unsigned)splits, (unsigned)(p.taps * g.C / BNW), (unsigned)(g.O / 128));
   int rc;
-  if (wgrad_mt2(g)) {
-    TC_SET_SMEM_ONCE(tc_wgrad2_kernel, TcWgrad2Smem::TOTAL);
-    grid.z = (unsigned)(g.O / 256);
-    launch_pdl(tc_wgrad2_kernel, dim3(grid), dim3(320), (size_t)(TcWgrad2Smem::TOTAL), s, tmDy, tmX, p); LAUNCHED(); g_tc_last_kernel = "tc_wgrad2_kernel";
-    rc = cudaPeekAtLastError() == cudaSuccess ? 0 : -3;
-  } else
   switch (BNW) {
     case 64: rc = launch_wgrad<64, 4>(tmDy, tmX, p, grid, s, "tc_wgrad_kernel<64,4>"); break;
     case 128: rc = launch_wgrad<128, 4>(tmDy, tmX, p, grid, s, "tc_wgrad_kernel<128,4>"); break;

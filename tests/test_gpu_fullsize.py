@@ -1,7 +1,7 @@
 """Parity of the BENCHMARKED path at the BENCHMARKED sizes: every tcgen05 kernel variant that the C2 step
 (64x64x3 DCGAN, batch 128; reference call sites J:135-150, J:203-219) dispatches -- persistent two-M-tile conv, one-CTA-per-tile conv, halo-resident pixel-shuffle deconv (shifted descriptors),
-folded-BatchNorm (AFFINE) epilogue, the fused BatchNorm epilogues (EPI_STATS / EPI_BNBWD / EPI_ACTBWD), one-wave split-K weight gradient,
-M = 256 weight gradient, the 3-channel edge kernels -- runs here through the C-ABI test hook with the PRODUCTION dispatch, the hook reports
+folded-BatchNorm (AFFINE) epilogue, the fused BatchNorm epilogues (EPI_STATS / EPI_BNBWD / EPI_ACTBWD), half-wave split-K weight gradient,
+the 3-channel edge kernels -- runs here through the C-ABI test hook with the PRODUCTION dispatch, the hook reports
 which kernel ran (asserted), and the result is compared with the CPU oracle (oracle/dl4j_oracle.py ConvolutionLayer / Deconvolution2D
 semantics) on the same bf16-rounded operands:
     bf16 outputs:  |got - ref| <= 2^-8 |ref| + 2e-3 rms(ref)        (one bf16 rounding is 2^-9 relative; fp32 accumulation order)
@@ -162,18 +162,18 @@ def test_dgrad_production_dispatch(b200, case, epi):
 
 WGRAD = [
     ("D2 wgrad, D step (2N)", 2 * N, 32, 64, 128, "tc_wgrad_kernel<256,4>"),
-    ("D3 wgrad, D step", 2 * N, 16, 128, 256, "tc_wgrad2_kernel"),
-    ("D4 wgrad, D step", 2 * N, 8, 256, 512, "tc_wgrad2_kernel"),
+    ("D3 wgrad, D step", 2 * N, 16, 128, 256, "tc_wgrad_kernel<256,4>"),
+    ("D4 wgrad, D step", 2 * N, 8, 256, 512, "tc_wgrad_kernel<256,4>"),
     ("G4 wgrad (N)", N, 32, 64, 128, "tc_wgrad_kernel<256,4>"),
-    ("G3 wgrad", N, 16, 128, 256, "tc_wgrad2_kernel"),
-    ("G2 wgrad", N, 8, 256, 512, "tc_wgrad2_kernel"),
+    ("G3 wgrad", N, 16, 128, 256, "tc_wgrad_kernel<256,4>"),
+    ("G2 wgrad", N, 8, 256, 512, "tc_wgrad_kernel<256,4>"),
 ]
 
 
 @pytest.mark.parametrize("case", WGRAD, ids=[c[0] for c in WGRAD])
 def test_wgrad_production_dispatch(b200, case):
-    """dW = sum over the whole batch: half-wave split-K grids (<= 74 CTAs, beside the input-gradient chain) with fp32 partials and the fixed-order reduction; M = 256 kernel
-    where each CTA still walks >= 12 K-blocks.  Oracle: ConvolutionLayer.backpropGradient on image chunks, summed (dW is linear in the batch)."""
+    """dW = sum over the whole batch: half-wave split-K grids (<= 74 CTAs, beside the input-gradient chain) with fp32 partials and the fixed-order
+    reduction.  Oracle: ConvolutionLayer.backpropGradient on image chunks, summed (dW is linear in the batch)."""
     b, ctx = b200
     name, n, h, c, oc, kernel = case
     rng = np.random.default_rng(13)

@@ -18,7 +18,7 @@ TENSOR = {
     "d4_fprop_n_conv64": (["D4 fprop, G step (N)", "G2 input gradient = fprop form (N)"], 8.589934592),
     "d3_fprop_2n_conv128": (["D3 fprop, D step (2N)"], 17.179869184),
     "d2_wgrad_2n": (["D2 wgrad, D step (2N)"], 17.179869184),
-    "d3_wgrad_2n": (["D3 wgrad, D step (2N)"], 17.179869184),
+    "d3_wgrad_2n": (["D3 wgrad, D step (2N)", "D4 wgrad, D step (2N)"], 17.179869184),
 }
 STEP = ["bn_bwd_apply_acc_kernel", "bn_apply_acc_kernel", "updater_kernel", "reduce_multi_kernel"]
 SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "us": 1.0, "ns": 1e-3, "ms": 1e3, "%": 1.0, "": 1.0, "cycle": 1.0, "register/thread": 1.0,
