@@ -124,3 +124,39 @@ def test_checkpoint_container_round_trip_and_nd4j_stream_layout(tmp_path):
     legacy = io.BytesIO(); legacy.write(struct.pack(">H", 4) + b"HEAP" + struct.pack(">i", 8) + struct.pack(">H", 3) + b"INT" + np.array([2, 1, 3, 3, 1, 0, 1, 99], ">i4").tobytes())
     legacy.write(struct.pack(">H", 4) + b"HEAP" + struct.pack(">i", 3) + struct.pack(">H", 5) + b"FLOAT" + np.array([1, 2, 3], ">f4").tobytes()); legacy.seek(0)
     assert np.array_equal(sz.read_nd4j_array(legacy), np.array([[1, 2, 3]], np.float32))
+
+
+def test_peer_memory_allreduce_slicing_and_sum_order():
+    """Index arithmetic of p2p_allreduce_kernel (kernels_ew.cu) restated: the 16-byte vectors of the gradient are cut into W slices, rank r reduces
+    slice r from every peer in rank order and writes it back to every peer; the n % 4 tail belongs to the last rank.  Every element must have
+    exactly one reader-writer rank (the in-place all-gather is only safe then), and the result must be the rank-ordered fp32 sum on every replica
+    (ParameterAveragingTrainingMaster aggregation, J:325-333, as a sum; the updater divides)."""
+    rng = np.random.default_rng(7)
+    for world in (2, 3, 4, 8):
+        for n in (1, 3, 4, 5, 1023, 1024, 2763841):
+            nv = n // 4
+            chunk = (nv + world - 1) // world
+            owner = np.full(n, -1, np.int64)
+            for r in range(world):
+                v0 = min(nv, r * chunk); v1 = min(nv, v0 + chunk)
+                assert (owner[4 * v0:4 * v1] == -1).all()
+                owner[4 * v0:4 * v1] = r
+            owner[4 * nv:] = world - 1
+            assert (owner >= 0).all() and (owner < world).all(), (world, n)
+        n = 1031
+        grads = [rng.standard_normal(n).astype(np.float32) for _ in range(world)]
+        want = grads[0].copy()
+        for r in range(1, world):
+            want = (want + grads[r]).astype(np.float32)            # rank order 0..W-1, fp32 at every step: what every replica must hold
+        nv = n // 4; chunk = (nv + world - 1) // world
+        bufs = [g.copy() for g in grads]
+        for r in range(world):                                      # each rank's reduce-scatter + all-gather over its slice (+ the tail on the last rank)
+            v0 = min(nv, r * chunk); v1 = min(nv, v0 + chunk)
+            idx = np.r_[4 * v0:4 * v1, (np.arange(4 * nv, n) if r == world - 1 else np.arange(0))].astype(np.int64)
+            acc = bufs[0][idx].copy()
+            for q in range(1, world):
+                acc = (acc + bufs[q][idx]).astype(np.float32)
+            for q in range(world):
+                bufs[q][idx] = acc
+        for q in range(world):
+            assert np.array_equal(bufs[q], want), (world, q)
