@@ -1400,7 +1400,7 @@ static int wgrad_bnw(const ConvGeom& g) { if (g.C % 64) return 0; const long col
 // 40 -> 0.903: the weight-gradient kernels run on the side stream beside the input-gradient chain, and half a wave leaves that chain the other SMs
 // (and halves the fp32 partials the deferred reduce reads).
 static int wgrad_target() { static int target = -1; if (target < 0) { const char* e = getenv("B2G_WGRAD_CTAS"); target = e ? atoi(e) : 74; if (target < 1) target = 74; } return target; }
-// one CTA per SM (192 KB of smem): choose the split count so that the whole grid is ONE wave (<= 148 CTAs); measured: D2 wgrad 52 -> 39 us
+// one CTA per SM (192 KB of smem): choose the split count so that the whole grid is at most wgrad_target() CTAs (half a wave by default, see above)
 static int wgrad_splits_for(const ConvGeom& g, int o_tile) {
   const int bnw = wgrad_bnw(g); if (!bnw) return 1;
   long tiles = (long)(g.O / o_tile) * (g.KH * g.KW * g.C / bnw), kbt = (long)g.N * g.OH * g.OW / 64;

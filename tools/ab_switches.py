@@ -1,5 +1,5 @@
 """A/B the library's experiment switches in ONE gpurun call: runs bench.py (short, no CPU leg) once per environment variant and prints a table.
-usage: python tools/ab_switches.py [--steps 100] [--config c2] [--gpus 2] "B2G_TC_DEEP=1" "B2G_WGRAD_CTAS=296" "B2G_TC_DEEP=1 B2G_AR_OVERLAP=1" ...
+usage: python tools/ab_switches.py [--steps 100] [--config c2] [--gpus 2] "B2G_TC_PERSIST=0" "B2G_WGRAD_CTAS=148" "B2G_WGRAD_CTAS=111 B2G_EDGE_CONV_CTAS=592" ...
 The first row is always the default configuration.  Numbers are for comparison inside one call only (same box, same clocks)."""
 import json
 import os
