@@ -1396,10 +1396,11 @@ __global__ void __launch_bounds__(320) tc_wgrad_kernel(const __grid_constant__ C
 // grids beside the input-gradient chain (profiles/r02_experiments.md).  Removed.)
 
 static int wgrad_bnw(const ConvGeom& g) { if (g.C % 64) return 0; const long cols = (long)g.KH * g.KW * g.C; return cols % 256 == 0 ? 256 : cols % 128 == 0 ? 128 : 64; }
-// CTA target of the split-K weight gradients.  Measured (round 2, whole C2 step): 296 -> 0.936 ms, 148 -> 0.895, 111 -> 0.886, 74 -> 0.876, 56 -> 0.885,
-// 40 -> 0.903: the weight-gradient kernels run on the side stream beside the input-gradient chain, and half a wave leaves that chain the other SMs
-// (and halves the fp32 partials the deferred reduce reads).
-static int wgrad_target() { static int target = -1; if (target < 0) { const char* e = getenv("B2G_WGRAD_CTAS"); target = e ? atoi(e) : 74; if (target < 1) target = 74; } return target; }
+// CTA target of the split-K weight gradients.  Measured (round 2, whole C2 step, several boxes; profiles/r02_experiments.md): 296 -> 0.936 ms,
+// 148 -> 0.881-0.897, 111 -> 0.864-0.886, 96 -> 0.855, 74 -> 0.863-0.883 (0.879 in the run where 96 gave 0.855), 56 -> 0.877-0.885, 40 -> 0.903: the
+// weight-gradient kernels run on the side stream beside the input-gradient chain, and two thirds of a wave leaves that chain the other SMs (and
+// cuts the fp32 partials the deferred reduce reads).
+static int wgrad_target() { static int target = -1; if (target < 0) { const char* e = getenv("B2G_WGRAD_CTAS"); target = e ? atoi(e) : 96; if (target < 1) target = 96; } return target; }
 // one CTA per SM (192 KB of smem): choose the split count so that the whole grid is at most wgrad_target() CTAs (half a wave by default, see above)
 static int wgrad_splits_for(const ConvGeom& g, int o_tile) {
   const int bnw = wgrad_bnw(g); if (!bnw) return 1;

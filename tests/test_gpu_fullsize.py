@@ -1,6 +1,6 @@
 """Parity of the BENCHMARKED path at the BENCHMARKED sizes: every tcgen05 kernel variant that the C2 step
 (64x64x3 DCGAN, batch 128; reference call sites J:135-150, J:203-219) dispatches -- persistent two-M-tile conv, one-CTA-per-tile conv, halo-resident pixel-shuffle deconv (shifted descriptors),
-folded-BatchNorm (AFFINE) epilogue, the fused BatchNorm epilogues (EPI_STATS / EPI_BNBWD / EPI_ACTBWD), half-wave split-K weight gradient,
+folded-BatchNorm (AFFINE) epilogue, the fused BatchNorm epilogues (EPI_STATS / EPI_BNBWD / EPI_ACTBWD), two-thirds-wave split-K weight gradient,
 the 3-channel edge kernels -- runs here through the C-ABI test hook with the PRODUCTION dispatch, the hook reports
 which kernel ran (asserted), and the result is compared with the CPU oracle (oracle/dl4j_oracle.py ConvolutionLayer / Deconvolution2D
 semantics) on the same bf16-rounded operands:
@@ -172,7 +172,7 @@ WGRAD = [
 
 @pytest.mark.parametrize("case", WGRAD, ids=[c[0] for c in WGRAD])
 def test_wgrad_production_dispatch(b200, case):
-    """dW = sum over the whole batch: half-wave split-K grids (<= 74 CTAs, beside the input-gradient chain) with fp32 partials and the fixed-order
+    """dW = sum over the whole batch: split-K grids of at most 96 CTAs (beside the input-gradient chain) with fp32 partials and the fixed-order
     reduction.  Oracle: ConvolutionLayer.backpropGradient on image chunks, summed (dW is linear in the batch)."""
     b, ctx = b200
     name, n, h, c, oc, kernel = case
